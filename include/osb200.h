@@ -1,0 +1,119 @@
+/* osb200.h — C ABI of libosb200.so, the B200 (sm_100a) implementation of the OptiSpeech
+ * synthesis / training hot path.
+ *
+ * The reference (mush42/optispeech @ 3bdde20) is pure Python/PyTorch and has NO native
+ * interface; every entry point below therefore names the reference *Python* function it
+ * replaces (file:line relative to the reference checkout).  The host side
+ * (optispeech_b200/, Python) binds these with ctypes — see INTEGRATION.md for the stub a
+ * reference maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never
+ *     allocates or frees device memory and never synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
+ *     functions are CUDA-graph-capture safe;
+ *   - return value: 0 = OSB_OK, negative = osb_status, positive = cudaError_t of the launch;
+ *   - activations are channels-last: a (B, T, C) tensor is B*T rows of C contiguous values;
+ *   - "h16" buffers hold IEEE fp16 (the tensor-core operand type), "f32" buffers fp32.
+ */
+#ifndef OSB200_H_
+#define OSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum osb_status {
+  OSB_OK = 0,
+  OSB_ERR_SHAPE = -1,     /* unsupported / inconsistent shape            */
+  OSB_ERR_ALIGN = -2,     /* pointer or leading dimension not aligned    */
+  OSB_ERR_ARCH = -3,      /* device is not sm_100                         */
+  OSB_ERR_DRIVER = -4,    /* cuTensorMapEncodeTiled unavailable / failed  */
+  OSB_ERR_WORKSPACE = -5, /* workspace too small                          */
+  OSB_ERR_ARG = -6        /* null pointer / bad enum                      */
+} osb_status;
+
+/* library bookkeeping ------------------------------------------------------------------- */
+int osb_version(void);                        /* ABI version, bumps on any signature change */
+const char* osb_strerror(int status);         /* static string for a negative osb_status    */
+unsigned long long osb_launch_count(void);    /* kernels launched by this library so far    */
+int osb_check_device(int device);             /* OSB_OK iff `device` is compute capability 10.x */
+
+/* ---------------------------------------------------------------------------------------
+ * Tensor-core contraction with fused epilogue (tcgen05.mma, TMA-staged operands, TMEM
+ * accumulators).  Computes, for every batch b, row t and output channel n,
+ *
+ *     acc[b,t,n] = sum_{tap<taps} sum_{k<K} A[b, t + tap - pad, k] * W[tap, n, k]
+ *
+ * (rows outside [0,T) read as zero, i.e. Conv1d zero padding), then applies `epi`.
+ * With taps = 1 this is nn.Linear; with taps = k it is nn.Conv1d(kernel_size=k,
+ * padding=pad) on channels-last data.
+ *
+ * Replaces: nn.Linear / nn.Conv1d call sites of the reference —
+ *   ConvNeXtBlock.pwconv1/pwconv2        optispeech/model/generator/modules/convnext.py:24-26,39-41
+ *   VariancePredictor.conv[i][0]/.linear optispeech/model/generator/modules/core.py:66-81,92-96
+ *   AlignmentModule.{t,f}_conv*          optispeech/model/generator/alignments.py:34-40,55-64
+ *   WaveNeXt.embed, WaveNeXtHead.linear_* optispeech/model/vocoder/wavenext/__init__.py:24-25,43-47,67,83
+ * ------------------------------------------------------------------------------------- */
+typedef enum osb_epilogue {
+  OSB_EPI_BIAS = 0,     /* out_f32 = acc + bias                     (flags: CLIP, KEEPMASK, OUT_H16)  */
+  OSB_EPI_GELU = 1,     /* out_h16 = gelu_erf(acc + bias)           (flags: SAVE_PRE -> aux_h16)     */
+  OSB_EPI_RESID = 2,    /* out_f32 = (resid + gamma*(acc+bias)*row_scale[b]) * keep[b,t]              */
+  OSB_EPI_RELU_LN = 3,  /* y = LN(relu(acc+bias)) -> out_h16; needs BN == N (flags: DOT, SAVE_PRE)    */
+  OSB_EPI_BIAS_LN = 4,  /* out_f32 = LN(acc + bias); needs BN == N  (flags: OUT_H16)                  */
+  OSB_EPI_RELU = 5      /* out_h16 = relu(acc + bias)               (flags: none)                     */
+} osb_epilogue;
+
+enum {
+  OSB_FLAG_CLIP = 1,      /* clamp result to [-1, 1]                     (WaveNeXtHead, wavenext/__init__.py:47) */
+  OSB_FLAG_KEEPMASK = 2,  /* multiply row by (1 - pad_mask[b,t])                                               */
+  OSB_FLAG_OUT_H16 = 4,   /* also write an fp16 copy of the result to aux_h16                                  */
+  OSB_FLAG_SAVE_PRE = 8,  /* write the pre-activation / pre-LN value as fp16 to aux_h16 (for backward)         */
+  OSB_FLAG_DOT = 16       /* RELU_LN only: out_dot[b,t] = <LN row, dot_w> + dot_b, 0 at padded rows            */
+};
+
+typedef struct osb_gemm_desc {
+  /* operands */
+  const void* a;        /* fp16 (B, T, lda) activations, K valid columns                           */
+  const void* w;        /* fp16 (taps, N, ldw) packed weights, K valid columns                     */
+  int64_t lda, ldw;     /* leading dimensions in elements, multiples of 8                          */
+  int32_t B, T, N, K;   /* batch, rows per batch, output channels, contraction length per tap      */
+  int32_t taps, pad;    /* kernel size and left zero padding                                       */
+  /* epilogue */
+  int32_t epi;          /* osb_epilogue                                                            */
+  int32_t flags;        /* OSB_FLAG_*                                                              */
+  void* out;            /* fp32 or fp16 (B*T, ldo) primary output (see osb_epilogue)               */
+  void* aux_h16;        /* optional fp16 (B*T, ldo) secondary output                               */
+  int64_t ldo;          /* leading dimension of out / aux / resid, elements                        */
+  const float* bias;    /* (N) or NULL                                                             */
+  const float* resid;   /* RESID: fp32 (B*T, ldo)                                                  */
+  const float* gamma;   /* RESID: (N) layer scale                                                  */
+  const float* row_scale; /* RESID: optional (B) DropPath scale per sample (NULL = 1)              */
+  const uint8_t* pad_mask; /* optional (B*T) bytes, 1 = padded position                            */
+  const float* ln_w;    /* *_LN: (N) LayerNorm weight                                              */
+  const float* ln_b;    /* *_LN: (N) LayerNorm bias                                                */
+  float ln_eps;
+  const float* dot_w;   /* DOT: (N) weight of the trailing Linear(N -> 1)                          */
+  float dot_b;          /* DOT: its bias                                                           */
+  float* out_dot;       /* DOT: (B*T) fp32                                                         */
+} osb_gemm_desc;
+
+int osb_gemm(const osb_gemm_desc* desc, void* stream);
+
+/* Weight-gradient contraction (split over rows, fp32 atomic accumulation into dw):
+ *     dw[tap, n, k] += sum_{b,t} dy[b, t, n] * a[b, t + tap - pad, k]
+ * dy: fp16 (B, T, ldy) ; a: fp16 (B, T, lda) ; dw: fp32 (taps, N, K) (must be zeroed or hold the
+ * running accumulation).  Both operands are consumed MN-major straight from their
+ * channels-last layout (no transposes in HBM).
+ * Replaces autograd's Conv1d/Linear weight gradient for the layers listed above. */
+int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
+                   int32_t N, int32_t K, int32_t taps, int32_t pad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB200_H_ */

@@ -1,0 +1,97 @@
+"""ctypes binding of libosb200.so (declared in include/osb200.h).
+
+The product path has no fallback: importing this module without a built library, or calling
+into it on a machine without a B200, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = _PKG_DIR / "libosb200.so"
+
+OSB_OK = 0
+
+# osb_epilogue
+EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU = range(6)
+# flags
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT = 1, 2, 4, 8, 16
+
+
+class GemmDesc(C.Structure):
+    """Mirror of `osb_gemm_desc` (include/osb200.h)."""
+
+    _fields_ = [
+        ("a", C.c_void_p),
+        ("w", C.c_void_p),
+        ("lda", C.c_int64),
+        ("ldw", C.c_int64),
+        ("B", C.c_int32),
+        ("T", C.c_int32),
+        ("N", C.c_int32),
+        ("K", C.c_int32),
+        ("taps", C.c_int32),
+        ("pad", C.c_int32),
+        ("epi", C.c_int32),
+        ("flags", C.c_int32),
+        ("out", C.c_void_p),
+        ("aux_h16", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p),
+        ("gamma", C.c_void_p),
+        ("row_scale", C.c_void_p),
+        ("pad_mask", C.c_void_p),
+        ("ln_w", C.c_void_p),
+        ("ln_b", C.c_void_p),
+        ("ln_eps", C.c_float),
+        ("dot_w", C.c_void_p),
+        ("dot_b", C.c_float),
+        ("out_dot", C.c_void_p),
+    ]
+
+
+class OsbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libosb200.so, failing loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise OsbError(
+            f"{LIB_PATH} is missing: run `python -m optispeech_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU/PyTorch fallback for the B200 hot path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    lib.osb_version.restype = C.c_int
+    lib.osb_strerror.restype = C.c_char_p
+    lib.osb_strerror.argtypes = [C.c_int]
+    lib.osb_launch_count.restype = C.c_ulonglong
+    lib.osb_check_device.argtypes = [C.c_int]
+    lib.osb_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    lib.osb_gemm_wgrad.argtypes = [
+        C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == OSB_OK:
+        return
+    lib = load()
+    if status < 0:
+        raise OsbError(f"{what}: {lib.osb_strerror(status).decode()} (osb_status {status})")
+    raise OsbError(f"{what}: CUDA error {status}")
+
+
+def launch_count() -> int:
+    return int(load().osb_launch_count())
