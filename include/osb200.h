@@ -98,7 +98,7 @@ typedef struct osb_gemm_desc {
   const float* ln_b;    /* *_LN: (N) LayerNorm bias                                                */
   float ln_eps;
   const float* dot_w;   /* DOT: (N) weight of the trailing Linear(N -> 1)                          */
-  float dot_b;          /* DOT: its bias                                                           */
+  const float* dot_b;   /* DOT: (1) its bias (device pointer, may be NULL = 0)                     */
   float* out_dot;       /* DOT: (B*T) fp32                                                         */
 } osb_gemm_desc;
 
@@ -112,6 +112,59 @@ int osb_gemm(const osb_gemm_desc* desc, void* stream);
  * Replaces autograd's Conv1d/Linear weight gradient for the layers listed above. */
 int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
                    int32_t N, int32_t K, int32_t taps, int32_t pad, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HBM-bound kernels of the synthesis path (osb_pointwise.cu).  Rows are channels-last.
+ * ------------------------------------------------------------------------------------- */
+
+/* out[b,t,:] = sqrt(dim)*table[ids[b,t]] + scale[0]*[sin(t*inv_freq) | cos(t*inv_freq)]   (fp32)
+ * Replaces TextEmbedding.forward (optispeech/model/generator/modules/core.py:25-31) and
+ * ScaledSinusoidalEmbedding.forward (modules/layers.py:59-71); dropout is the caller's job. */
+int osb_embed_text(const int64_t* ids, const float* table, const float* inv_freq, const float* scale, float* out,
+                   int32_t B, int32_t T, int32_t dim, int32_t n_vocab, void* stream);
+
+/* xhat[b,t,:] = normalise_C( bias + sum_j w[:,j] * x[b,t+j-3,:] )  as fp16 (no affine: the
+ * LayerNorm weight/bias are folded into the pointwise-1 GEMM weights by the host), rstd optional.
+ * Replaces ConvNeXtBlock.dwconv + .norm (modules/convnext.py:22-23,36-38).  C in {128,256,384,512}. */
+int osb_dwconv_ln(const float* x, const float* w /*(C,7)*/, const float* bias, void* xhat_h16, float* rstd /*(B*T) or NULL*/,
+                  int32_t B, int32_t T, int32_t C, float eps, void* stream);
+
+/* Row LayerNorm with affine; fp32 and/or fp16 output.  Replaces ConvNeXtBackbone.final_layer_norm
+ * (modules/convnext.py:84,102) and WaveNeXt.norm (vocoder/wavenext/__init__.py:68,84). */
+int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
+                  float eps, void* stream);
+
+/* out = (x + bias + Conv1d(1->C, k, same)(val)) * (1 - pad_mask).  Replaces PitchPredictor.forward/
+ * infer's embed + add + mask (modules/core.py:152-176). */
+int osb_variance_embed(const float* x, const float* val /*(B,T)*/, const float* w /*(C,k)*/, const float* bias,
+                       const uint8_t* pad_mask, float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize,
+                       void* stream);
+
+/* dur = clamp(ceil((exp(log_d) - clip_val) * factor), 0) as int64, 0 at pads; lengths[b] = sum_t dur.
+ * Replaces DurationPredictor.infer (modules/core.py:126-133) and y_lengths (generator/__init__.py:258). */
+int osb_durations(const float* log_d, const uint8_t* pad_mask, int64_t* dur, int64_t* lengths, int32_t B, int32_t T,
+                  float factor, float clip_val, void* stream);
+
+/* centres = cumsum(dur) - dur/2 (fp32) and csum = inclusive cumsum (int64, optional).  dur is int64 or fp32.
+ * Replaces GaussianUpsampling's `c` (generator/alignments.py:167) and expand_by_duration's cumsum (:287). */
+int osb_centres(const void* dur, int32_t dur_is_i64, float* centres, int64_t* csum, int32_t B, int32_t T, void* stream);
+
+/* y[b,t,:] = softmax_i(-delta*(t*[t<y_len] - c_i)^2 over i < x_len) @ hs[b].  Replaces
+ * GaussianUpsampling.forward (generator/alignments.py:159-173) without materialising p_attn in HBM. */
+int osb_gaussian_upsample(const float* hs, const float* centres, const int64_t* x_len, const int64_t* y_len, float* out_f32,
+                          void* out_h16, int32_t B, int32_t Tx, int32_t Tm, int32_t C, float delta, void* stream);
+
+/* Hard length regulator: out[b,t,:] = x[b, i(t), :] with csum[i-1] <= t < csum[i]; zero past the length.
+ * index_out (optional, int32, -1 past the length) is the bit-exact indexing target.
+ * Replaces expand_by_duration (generator/alignments.py:283-297). */
+int osb_expand_gather(const float* x, const int64_t* csum, float* out, int32_t* index_out, int32_t B, int32_t Tx, int32_t Tm,
+                      int32_t C, void* stream);
+
+/* dst[r,c] = fp16(src[r*src_ld + c*src_cs] * col_scale[c]) for c < cols, 0 for cols <= c < dst_ld.
+ * Weight/activation packing for the tensor-core operands (no reference counterpart: the
+ * reference's `16-mixed` autocast does this implicitly, configs/trainer/default.yaml:11). */
+int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, int64_t dst_ld,
+                 int64_t rows, int32_t cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ class GemmDesc(C.Structure):
         ("ln_b", C.c_void_p),
         ("ln_eps", C.c_float),
         ("dot_w", C.c_void_p),
-        ("dot_b", C.c_float),
+        ("dot_b", C.c_void_p),
         ("out_dot", C.c_void_p),
     ]
 
@@ -80,8 +80,34 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
     ]
+    P, I32, I64, F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sigs = {
+        "osb_embed_text": [P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, P],
+        "osb_layernorm": [P, P, P, P, P, I64, I32, F, P],
+        "osb_variance_embed": [P, P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_durations": [P, P, P, P, I32, I32, F, F, P],
+        "osb_centres": [P, I32, P, P, I32, I32, P],
+        "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
+        "osb_expand_gather": [P, P, P, P, I32, I32, I32, I32, P],
+        "osb_pack_h16": [P, I64, I64, P, P, I64, I64, I32, P],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.osb_gemm.restype = C.c_int
+    lib.osb_gemm_wgrad.restype = C.c_int
     _lib = lib
     return lib
+
+
+def exported_symbols() -> list[str]:
+    """Names every entry point include/osb200.h declares (checked by the CPU test-suite)."""
+    import re
+
+    header = (_PKG_DIR.parent / "include" / "osb200.h").read_text()
+    return sorted(set(re.findall(r"\b(osb_[a-z0-9_]+)\s*\(", header)))
 
 
 def check(status: int, what: str) -> None:

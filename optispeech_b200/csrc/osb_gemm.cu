@@ -38,7 +38,7 @@ struct GemmKParams {
   const float* ln_b;
   float ln_eps;
   const float* dot_w;
-  float dot_b;
+  const float* dot_b;
   float* out_dot;
 };
 
@@ -200,7 +200,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         }
       }
     }
-    if ((p.flags & OSB_FLAG_DOT) && valid) p.out_dot[row] = padded ? 0.f : (dot + p.dot_b);
+    if ((p.flags & OSB_FLAG_DOT) && valid) p.out_dot[row] = padded ? 0.f : (dot + (p.dot_b != nullptr ? __ldg(p.dot_b) : 0.f));
   }
 }
 

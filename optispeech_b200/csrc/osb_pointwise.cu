@@ -1,0 +1,480 @@
+// osb_pointwise.cu — HBM-bound kernels of the synthesis path (everything that is not a GEMM):
+// text embedding, depthwise-conv7 + LayerNorm, standalone LayerNorm, variance embedding,
+// duration rounding + scan, Gaussian upsampling, hard length-regulator gather, fp32->fp16 packing.
+//
+// Layout: channels-last rows of C contiguous fp32 values; one warp owns one row (position) and
+// each lane owns C/32 channels as float4 groups, so every global access is a 512-byte coalesced
+// warp transaction.
+#include "osb_host.h"
+#include "osb_ptx.cuh"
+
+namespace osb {
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+__device__ __forceinline__ void store_h4(__half* dst, float a, float b, float c, float d) {
+  __half2 h0 = __floats2half2_rn(a, b);
+  __half2 h1 = __floats2half2_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+// ------------------------------------------------------------------------------------------
+// text embedding: out[b,t,:] = sqrt(dim) * E[id] + scale * [sin(t*f) | cos(t*f)]
+// ------------------------------------------------------------------------------------------
+__global__ void embed_text_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                  const float* __restrict__ inv_freq, const float* __restrict__ scale_p, float* __restrict__ out,
+                                  int rows, int T, int dim, int n_vocab, float embed_scale) {
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int t = row % T;
+  long long id = ids[row];
+  if (id < 0 || id >= n_vocab) id = 0;
+  const float scale = scale_p[0];
+  const int half = dim >> 1;
+  const float* e = table + id * dim;
+  float* o = out + static_cast<long long>(row) * dim;
+  for (int c = lane; c < dim; c += 32) {
+    const int j = c < half ? c : c - half;
+    const float ang = static_cast<float>(t) * inv_freq[j];
+    const float pe = c < half ? sinf(ang) : cosf(ang);
+    o[c] = embed_scale * e[c] + pe * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise conv (k=7, zero pad 3, bias) + LayerNorm statistics.
+// Writes xhat = (d - mean) * rstd as fp16 (the LN affine is folded into the following pointwise
+// GEMM at weight-packing time) and optionally rstd (needed by the backward pass).
+// Each warp walks POS consecutive positions with a 7-row sliding window held in registers.
+// ------------------------------------------------------------------------------------------
+template <int VPL>  // float4 groups per lane: C = 128 * VPL
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w /*(C,7)*/, const float* __restrict__ bias,
+                 __half* __restrict__ xhat, float* __restrict__ rstd_out, int B, int T, int pos_per_warp, float eps) {
+  constexpr int C = 128 * VPL;
+  __shared__ float sw[7][C];
+  __shared__ float sb[C];
+  for (int i = threadIdx.x; i < C * 7; i += blockDim.x) sw[i % 7][i / 7] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int groups_per_batch = (T + pos_per_warp - 1) / pos_per_warp;
+  const int gw = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (gw >= B * groups_per_batch) return;
+  const int b = gw / groups_per_batch;
+  const int t_begin = (gw % groups_per_batch) * pos_per_warp;
+  const int t_end = min(T, t_begin + pos_per_warp);
+  const float* xb = x + static_cast<long long>(b) * T * C;
+
+  float4 win[7][VPL];  // win[j] = row (t + j - 3)
+  auto load_row = [&](int t, float4 (&dst)[VPL]) {
+    if (t >= 0 && t < T) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) dst[v] = *reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C + v * 128 + lane * 4);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < 6; ++j) load_row(t_begin + j - 3, win[j + 1]);
+
+  for (int t = t_begin; t < t_end; ++t) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) win[j][v] = win[j + 1][v];
+    load_row(t + 3, win[6]);
+
+    float4 d[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int c = v * 128 + lane * 4;
+      float4 acc = *reinterpret_cast<const float4*>(&sb[c]);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float4 wj = *reinterpret_cast<const float4*>(&sw[j][c]);
+        acc.x = fmaf(wj.x, win[j][v].x, acc.x);
+        acc.y = fmaf(wj.y, win[j][v].y, acc.y);
+        acc.z = fmaf(wj.z, win[j][v].z, acc.z);
+        acc.w = fmaf(wj.w, win[j][v].w, acc.w);
+      }
+      d[v] = acc;
+      s += (acc.x + acc.y) + (acc.z + acc.w);
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
+      q += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+    const long long row = static_cast<long long>(b) * T + t;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+      store_h4(xhat + row * C + v * 128 + lane * 4, d[v].x * rstd, d[v].y * rstd, d[v].z * rstd, d[v].w * rstd);
+    if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim: one warp per row. Optional fp32 and fp16 outputs.
+// ------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ out_f32,
+                 __half* __restrict__ out_h16, long long rows, float eps) {
+  constexpr int C = 128 * VPL;
+  const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 d[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    d[v] = *reinterpret_cast<const float4*>(x + row * C + v * 128 + lane * 4);
+    s += (d[v].x + d[v].y) + (d[v].z + d[v].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
+    q += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = v * 128 + lane * 4;
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    float4 y;
+    y.x = d[v].x * rstd * ww.x + bb.x;
+    y.y = d[v].y * rstd * ww.y + bb.y;
+    y.z = d[v].z * rstd * ww.z + bb.z;
+    y.w = d[v].w * rstd * ww.w + bb.w;
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+    if (out_h16 != nullptr) store_h4(out_h16 + row * C + c, y.x, y.y, y.z, y.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// variance embedding: out = (x + bias + conv1d(val; 1->C, k taps, same)) * keep
+// ------------------------------------------------------------------------------------------
+__global__ void variance_embed_kernel(const float* __restrict__ x, const float* __restrict__ val, const float* __restrict__ w /*(C,k)*/,
+                                      const float* __restrict__ bias, const uint8_t* __restrict__ pad_mask, float* __restrict__ out_f32,
+                                      __half* __restrict__ out_h16, int B, int T, int C, int ksize) {
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= B * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / T, t = row % T;
+  const int halfk = (ksize - 1) / 2;
+  float v[16];
+  for (int j = 0; j < ksize; ++j) {
+    const int tt = t + j - halfk;
+    v[j] = (tt >= 0 && tt < T) ? val[b * T + tt] : 0.f;
+  }
+  const float keep = (pad_mask != nullptr && pad_mask[row]) ? 0.f : 1.f;
+  for (int c = lane; c < C; c += 32) {
+    float acc = bias[c];
+    for (int j = 0; j < ksize; ++j) acc = fmaf(w[c * ksize + j], v[j], acc);
+    const float y = (x[static_cast<long long>(row) * C + c] + acc) * keep;
+    if (out_f32 != nullptr) out_f32[static_cast<long long>(row) * C + c] = y;
+    if (out_h16 != nullptr) out_h16[static_cast<long long>(row) * C + c] = __float2half_rn(y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// durations: d = clamp(ceil((exp(logd) - clip) * factor), 0) as int64, 0 at pads; per-sample
+// length, and Gaussian centres c = cumsum(d) - d/2.  One block per sample (Tx <= 4096).
+// ------------------------------------------------------------------------------------------
+__global__ void duration_kernel(const float* __restrict__ log_d, const uint8_t* __restrict__ pad_mask, long long* __restrict__ dur,
+                                long long* __restrict__ lengths, int T, float factor, float clip_val) {
+  const int b = blockIdx.x;
+  long long local = 0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float d = ceilf((expf(log_d[b * T + t]) - clip_val) * factor);
+    long long di = static_cast<long long>(d);  // matches .long() (truncation) for finite values
+    if (!(d == d)) di = 0;
+    if (di < 0) di = 0;
+    if (pad_mask[b * T + t]) di = 0;
+    dur[b * T + t] = di;
+    local += di;
+  }
+  __shared__ long long red[32];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long s = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += red[i];
+    lengths[b] = s;
+  }
+}
+
+// cumsum of durations (int64 or fp32 input) -> centres (fp32) and inclusive cumsum (int64). One warp per sample.
+template <typename DT>
+__global__ void centres_kernel(const DT* __restrict__ dur, float* __restrict__ centres, long long* __restrict__ csum_out, int B, int T) {
+  const int b = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  double carry = 0.0;  // exact for integer-valued durations
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const double d = t < T ? static_cast<double>(dur[b * T + t]) : 0.0;
+    double s = d;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double n = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += n;
+    }
+    s += carry;
+    if (t < T) {
+      // reference: ds.cumsum(-1) - ds / 2, evaluated in fp32 (alignments.py:167)
+      centres[b * T + t] = static_cast<float>(s) - static_cast<float>(d) * 0.5f;
+      if (csum_out != nullptr) csum_out[b * T + t] = static_cast<long long>(s);
+    }
+    carry = __shfl_sync(0xffffffffu, s, 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gaussian upsampling: y[b,t,:] = softmax_i(-delta (t*hmask - c_i)^2 | valid i) @ hs[b,:,:]
+// Block = FR frames x C channels; the attention row is computed once per frame in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int FR>
+__global__ void __launch_bounds__(256)
+gaussian_upsample_kernel(const float* __restrict__ hs, const float* __restrict__ centres, const long long* __restrict__ x_len,
+                         const long long* __restrict__ y_len, float* __restrict__ out_f32, __half* __restrict__ out_h16, int Tx, int Tm,
+                         int C, float delta) {
+  extern __shared__ float sp[];  // FR * Tx attention weights
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FR;
+  const int nx = static_cast<int>(x_len[b]);
+  const int ny = static_cast<int>(y_len[b]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // one warp per frame builds the softmax row
+  for (int f = warp; f < FR; f += (blockDim.x >> 5)) {
+    const int t = t0 + f;
+    if (t >= Tm) continue;
+    const float tf = (t < ny) ? static_cast<float>(t) : 0.f;
+    float* p = sp + f * Tx;
+    float mx = -INFINITY;
+    for (int i = lane; i < Tx; i += 32) {
+      float e = -INFINITY;
+      if (i < nx) {
+        const float diff = tf - centres[b * Tx + i];
+        e = -delta * (diff * diff);
+      }
+      p[i] = e;
+      mx = fmaxf(mx, e);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int i = lane; i < Tx; i += 32) {
+      const float e = (i < nx) ? expf(p[i] - mx) : 0.f;
+      p[i] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int i = lane; i < Tx; i += 32) p[i] *= inv;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[FR];
+#pragma unroll
+    for (int f = 0; f < FR; ++f) acc[f] = 0.f;
+    const float* h = hs + static_cast<long long>(b) * Tx * C + c;
+    for (int i = 0; i < nx; ++i) {
+      const float hv = h[static_cast<long long>(i) * C];
+#pragma unroll
+      for (int f = 0; f < FR; ++f) acc[f] = fmaf(sp[f * Tx + i], hv, acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < FR; ++f) {
+      const int t = t0 + f;
+      if (t < Tm) {
+        const long long o = (static_cast<long long>(b) * Tm + t) * C + c;
+        if (out_f32 != nullptr) out_f32[o] = acc[f];
+        if (out_h16 != nullptr) out_h16[o] = __float2half_rn(acc[f]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// hard length regulator (expand_by_duration): out[b,t,:] = x[b, token(t), :], token(t) = first i
+// with csum[i] > t; zero beyond the sample's length.  Also emits the index (bit-exact target).
+// ------------------------------------------------------------------------------------------
+__global__ void expand_gather_kernel(const float* __restrict__ x, const long long* __restrict__ csum, float* __restrict__ out,
+                                     int* __restrict__ index_out, int B, int Tx, int Tm, int C) {
+  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= B * Tm) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / Tm, t = row % Tm;
+  const long long* cs = csum + static_cast<long long>(b) * Tx;
+  int idx = -1;
+  if (t < cs[Tx - 1]) {
+    int lo = 0, hi = Tx - 1;  // first i with cs[i] > t
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cs[mid] > t) hi = mid; else lo = mid + 1;
+    }
+    idx = lo;
+  }
+  if (index_out != nullptr && lane == 0) index_out[row] = idx;
+  for (int c = lane; c < C; c += 32)
+    out[static_cast<long long>(row) * C + c] = idx >= 0 ? x[(static_cast<long long>(b) * Tx + idx) * C + c] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 -> fp16 packing with optional per-column scale and row/column padding:
+//   dst[r, c] = half(src[r * src_ld + c * src_cs] * (col_scale ? col_scale[c] : 1))   for r < rows, c < cols
+//   zero elsewhere (c in [cols, dst_ld))
+// ------------------------------------------------------------------------------------------
+__global__ void pack_h16_kernel(const float* __restrict__ src, long long src_ld, long long src_cs, const float* __restrict__ col_scale,
+                                __half* __restrict__ dst, long long dst_ld, long long rows, int cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * dst_ld) return;
+  const long long r = i / dst_ld;
+  const int c = static_cast<int>(i % dst_ld);
+  float v = 0.f;
+  if (c < cols) {
+    v = src[r * src_ld + c * src_cs];
+    if (col_scale != nullptr) v *= col_scale[c];
+  }
+  dst[i] = __float2half_rn(v);
+}
+
+}  // namespace
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" int osb_embed_text(const int64_t* ids, const float* table, const float* inv_freq, const float* scale, float* out,
+                              int32_t B, int32_t T, int32_t dim, int32_t n_vocab, void* stream) {
+  OSB_REQUIRE(ids && table && inv_freq && scale && out, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0 && dim > 0 && dim % 2 == 0, OSB_ERR_SHAPE);
+  const int rows = B * T;
+  embed_text_kernel<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), table, inv_freq, scale, out, rows, T, dim, n_vocab, sqrtf(static_cast<float>(dim)));
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_dwconv_ln(const float* x, const float* w, const float* bias, void* xhat_h16, float* rstd, int32_t B, int32_t T,
+                             int32_t C, float eps, void* stream) {
+  OSB_REQUIRE(x && w && bias && xhat_h16, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384 || C == 128 || C == 512), OSB_ERR_SHAPE);
+  const int ppw = T >= 64 ? 16 : 8;
+  const int groups = B * ((T + ppw - 1) / ppw);
+  const int blocks = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __half* o = static_cast<__half*>(xhat_h16);
+  switch (C / 128) {
+    case 1: dwconv_ln_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
+    case 2: dwconv_ln_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
+    case 3: dwconv_ln_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
+    case 4: dwconv_ln_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
+                             float eps, void* stream) {
+  OSB_REQUIRE(x && w && b && (out_f32 || out_h16), OSB_ERR_ARG);
+  OSB_REQUIRE(rows > 0 && (C == 128 || C == 256 || C == 384 || C == 512), OSB_ERR_SHAPE);
+  const unsigned blocks = static_cast<unsigned>((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __half* oh = static_cast<__half*>(out_h16);
+  switch (C / 128) {
+    case 1: layernorm_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
+    case 2: layernorm_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
+    case 3: layernorm_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
+    case 4: layernorm_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_variance_embed(const float* x, const float* val, const float* w, const float* bias, const uint8_t* pad_mask,
+                                  float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize, void* stream) {
+  OSB_REQUIRE(x && val && w && bias && (out_f32 || out_h16), OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0 && C > 0 && ksize > 0 && ksize <= 16 && (ksize & 1), OSB_ERR_SHAPE);
+  const int rows = B * T;
+  variance_embed_kernel<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, val, w, bias, pad_mask, out_f32, static_cast<__half*>(out_h16), B, T, C, ksize);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_durations(const float* log_d, const uint8_t* pad_mask, int64_t* dur, int64_t* lengths, int32_t B, int32_t T,
+                             float factor, float clip_val, void* stream) {
+  OSB_REQUIRE(log_d && pad_mask && dur && lengths, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0, OSB_ERR_SHAPE);
+  duration_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(log_d, pad_mask, reinterpret_cast<long long*>(dur),
+                                                                   reinterpret_cast<long long*>(lengths), T, factor, clip_val);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_centres(const void* dur, int32_t dur_is_i64, float* centres, int64_t* csum, int32_t B, int32_t T, void* stream) {
+  OSB_REQUIRE(dur && centres, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0, OSB_ERR_SHAPE);
+  const int blocks = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dur_is_i64)
+    centres_kernel<long long><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(static_cast<const long long*>(dur), centres,
+                                                                      reinterpret_cast<long long*>(csum), B, T);
+  else
+    centres_kernel<float><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(static_cast<const float*>(dur), centres,
+                                                                  reinterpret_cast<long long*>(csum), B, T);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_gaussian_upsample(const float* hs, const float* centres, const int64_t* x_len, const int64_t* y_len, float* out_f32,
+                                     void* out_h16, int32_t B, int32_t Tx, int32_t Tm, int32_t C, float delta, void* stream) {
+  OSB_REQUIRE(hs && centres && x_len && y_len && (out_f32 || out_h16), OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tx > 0 && Tm > 0 && C > 0, OSB_ERR_SHAPE);
+  constexpr int FR = 8;
+  const size_t smem = static_cast<size_t>(FR) * Tx * sizeof(float);
+  OSB_REQUIRE(smem <= 48 * 1024, OSB_ERR_SHAPE);
+  dim3 grid((Tm + FR - 1) / FR, B);
+  gaussian_upsample_kernel<FR><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      hs, centres, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(y_len), out_f32,
+      static_cast<__half*>(out_h16), Tx, Tm, C, delta);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_expand_gather(const float* x, const int64_t* csum, float* out, int32_t* index_out, int32_t B, int32_t Tx,
+                                 int32_t Tm, int32_t C, void* stream) {
+  OSB_REQUIRE(x && csum && out, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tx > 0 && Tm > 0 && C > 0, OSB_ERR_SHAPE);
+  const int rows = B * Tm;
+  expand_gather_kernel<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const long long*>(csum), out, index_out, B, Tx, Tm, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, int64_t dst_ld,
+                            int64_t rows, int32_t cols, void* stream) {
+  OSB_REQUIRE(src && dst, OSB_ERR_ARG);
+  OSB_REQUIRE(rows > 0 && cols > 0 && dst_ld >= cols, OSB_ERR_SHAPE);
+  const long long n = rows * dst_ld;
+  pack_h16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, src_ld, src_cs, col_scale, static_cast<__half*>(dst), dst_ld, rows, cols);
+  count_launch();
+  return launch_status();
+}

@@ -1,0 +1,133 @@
+"""ConvNeXt blocks on the B200 path.
+
+Mirrors optispeech/model/generator/modules/convnext.py (reference @ 3bdde20): same class names,
+constructor arguments, parameter names/shapes (`gamma`, `dwconv.*`, `norm.*`, `pwconv1.*`,
+`pwconv2.*`, `final_layer_norm.*`) and forward signatures.  The nn.Conv1d / nn.LayerNorm /
+nn.Linear children are parameter containers only; compute goes through libosb200:
+
+    dwconv7 + LayerNorm statistics   -> osb_dwconv_ln   (fp16 xhat; LN affine folded into pwconv1)
+    pwconv1 + bias + erf-GELU        -> osb_gemm (tcgen05, EPI_GELU)
+    pwconv2 + bias, gamma, DropPath, residual, pad mask -> osb_gemm (tcgen05, EPI_RESID)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .... import ops
+from ...packing import PackedCache, pack_linear
+
+
+class DropPath(nn.Module):
+    """Per-sample stochastic depth (reference convnext.py:106-132).  On this path the Bernoulli
+    scale is drawn per sample on the device and applied inside the pwconv2 epilogue."""
+
+    def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def sample_scale(self, batch: int, device) -> Optional[torch.Tensor]:
+        if self.drop_prob == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        scale = torch.empty(batch, device=device, dtype=torch.float32).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            scale.div_(keep)
+        return scale
+
+    def forward(self, x):
+        scale = self.sample_scale(x.shape[0], x.device)
+        return x if scale is None else x * scale.view(-1, *([1] * (x.ndim - 1)))
+
+    def extra_repr(self):
+        return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+class ConvNeXtBlock(nn.Module):
+    def __init__(self, dim: int, intermediate_dim: int, drop_path: float = 0.0, layer_scale_init_value: float = None):
+        super().__init__()
+        self.dim = dim
+        self.intermediate_dim = intermediate_dim
+        self.dwconv = nn.Conv1d(dim, dim, kernel_size=7, padding=3, groups=dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.pwconv1 = nn.Linear(dim, intermediate_dim)
+        self.act = nn.GELU()
+        self.pwconv2 = nn.Linear(intermediate_dim, dim)
+        self.gamma = (
+            nn.Parameter(layer_scale_init_value * torch.ones(dim), requires_grad=True)
+            if layer_scale_init_value > 0
+            else None
+        )
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self._packed = PackedCache()
+
+    # -- packed operands -------------------------------------------------------------------
+    def packed(self):
+        srcs = [self.norm.weight, self.norm.bias, self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight]
+
+        def build():
+            w1 = pack_linear(self.pwconv1.weight, col_scale=self.norm.weight.detach().contiguous())
+            b1 = (self.pwconv1.bias + self.pwconv1.weight @ self.norm.bias).contiguous()
+            w2 = pack_linear(self.pwconv2.weight)
+            return w1, b1, w2
+
+        return self._packed.get("fwd", srcs, build)
+
+    def forward_cl(self, x: torch.Tensor, pad_mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
+        """Channels-last forward: x (B,T,C) fp32 -> (B,T,C) fp32, pad mask (B,T) uint8 applied to the output
+        (the reference's ConvNeXtBackbone multiplies by the mask right after each block, convnext.py:98-101)."""
+        w1, b1, w2 = self.packed()
+        xhat, _ = ops.dwconv_ln(x, self.dwconv.weight.view(self.dim, 7), self.dwconv.bias, self.norm.eps)
+        h, _, _ = ops.gemm(xhat, w1, epi=ops.EPI_GELU, bias=b1)
+        scale = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
+        gamma = self.gamma if self.gamma is not None else torch.ones(self.dim, device=x.device)
+        out, _, _ = ops.gemm(h, w2, epi=ops.EPI_RESID, bias=self.pwconv2.bias, resid=x, gamma=gamma, row_scale=scale,
+                             pad_mask=pad_mask_u8, flags=ops.FLAG_KEEPMASK if pad_mask_u8 is not None else 0)
+        return out
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference signature: x (B, C, T) -> (B, C, T)."""
+        return self.forward_cl(x.transpose(1, 2).contiguous(), None).transpose(1, 2)
+
+
+class ConvNeXtBackbone(nn.Module):
+    """Reference: modules/convnext.py:50-103."""
+
+    def __init__(
+        self,
+        dim: int,
+        intermediate_dim: int,
+        num_layers: int,
+        drop_path: float = 0.0,
+        layer_scale_init_value: Optional[float] = None,
+    ):
+        super().__init__()
+        layer_scale_init_value = layer_scale_init_value or 1 / num_layers
+        rates = [r.item() for r in torch.linspace(0, drop_path, num_layers)]
+        self.convnext = nn.ModuleList(
+            [
+                ConvNeXtBlock(dim=dim, intermediate_dim=intermediate_dim, drop_path=r,
+                              layer_scale_init_value=layer_scale_init_value)
+                for r in rates
+            ]
+        )
+        self.final_layer_norm = nn.LayerNorm(dim, eps=1e-6)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, (nn.Conv1d, nn.Linear)):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            nn.init.constant_(m.bias, 0)
+
+    def forward(self, x: torch.Tensor, padding_mask: Optional[torch.Tensor] = None, want_h16: bool = False):
+        """x (B,T,C) fp32, padding_mask (B,T) bool True = pad -> (B,T,C) fp32 [, fp16 copy]."""
+        x = x.contiguous()
+        mask_u8 = None if padding_mask is None else padding_mask.to(torch.uint8).contiguous()
+        for blk in self.convnext:
+            x = blk.forward_cl(x, mask_u8)
+        ln = self.final_layer_norm
+        o32, o16 = ops.layernorm(x, ln.weight, ln.bias, ln.eps, f32=True, h16=want_h16)
+        return (o32, o16) if want_h16 else o32

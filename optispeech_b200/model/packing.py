@@ -1,0 +1,59 @@
+"""Packed tensor-core operands derived from fp32 master parameters.
+
+The CUDA kernels consume fp16 weights in (taps, N, K) layout; nn.Parameters stay fp32 with the
+reference's shapes so `state_dict` is interchangeable.  Packed copies are cached per module and
+rebuilt when any source parameter changes (tracked through the tensors' in-place version
+counters and storage pointers), e.g. after an optimizer step or `load_state_dict`.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterable, Tuple
+
+import torch
+
+
+class PackedCache:
+    def __init__(self):
+        self._store: Dict[str, Tuple[tuple, object]] = {}
+
+    @staticmethod
+    def _key(params: Iterable[torch.Tensor]) -> tuple:
+        return tuple((p.data_ptr(), p._version, p.device.index) for p in params)
+
+    def get(self, name: str, params: Iterable[torch.Tensor], build: Callable[[], object]):
+        params = list(params)
+        key = self._key(params)
+        hit = self._store.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self._store[name] = (key, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+def pack_linear(weight: torch.Tensor, col_scale: torch.Tensor | None = None, k_pad: int | None = None) -> torch.Tensor:
+    """(N, K) fp32 -> (1, N, Kp) fp16, optionally scaling column k by col_scale[k]."""
+    from .. import ops
+
+    N, K = weight.shape
+    Kp = k_pad or K
+    w = weight.detach().contiguous()
+    return ops.pack_h16(w, rows=N, cols=K, src_ld=K, dst_ld=Kp, col_scale=col_scale).view(1, N, Kp)
+
+
+def pack_conv(weight: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
+    """Conv1d weight (N, Cin, k) fp32 -> (k, N, Cin_pad) fp16 (one K-major matrix per tap)."""
+    from .. import ops
+
+    N, Cin, k = weight.shape
+    Kp = k_pad or Cin
+    w = weight.detach().contiguous()
+    out = torch.empty((k, N, Kp), device=w.device, dtype=torch.float16)
+    for tap in range(k):
+        # element (n, c) of tap lives at w[n, c, tap] = base + n*Cin*k + c*k + tap
+        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_ld=Kp, out=out[tap])
+    return out

@@ -1,0 +1,173 @@
+"""Tensor-level wrappers over the C ABI (include/osb200.h).
+
+Each function takes CUDA tensors, allocates outputs with torch (device memory and streams are
+PyTorch's job here), and enqueues the library's kernels on the current stream.  There is no
+fallback: non-CUDA tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_RELU, EPI_RELU_LN, EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK,
+                   FLAG_OUT_H16, FLAG_SAVE_PRE)
+
+__all__ = [
+    "gemm", "embed_text", "dwconv_ln", "layernorm", "variance_embed", "durations", "centres", "gaussian_upsample",
+    "expand_gather", "pack_h16", "EPI_BIAS", "EPI_GELU", "EPI_RESID", "EPI_RELU_LN", "EPI_BIAS_LN", "EPI_RELU",
+    "FLAG_CLIP", "FLAG_KEEPMASK", "FLAG_OUT_H16", "FLAG_SAVE_PRE", "FLAG_DOT",
+]
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.OsbError("optispeech_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.OsbError("optispeech_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32, t.dtype
+    return t
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
+         bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None):
+    """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
+
+    a: fp16 (B,T,lda); w: fp16 (taps,N,ldw); outputs are allocated when not given.  Returns `out`."""
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 3 and w.dim() == 3
+    B, T, lda = a.shape
+    taps, N, ldw = w.shape
+    K = K if K is not None else min(lda, ldw)
+    f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN)
+    if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)):
+        out = torch.empty((B, T, N), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
+    if (flags & (FLAG_OUT_H16 | FLAG_SAVE_PRE)) and aux is None:
+        aux = torch.empty((B, T, N), device=a.device, dtype=torch.float16)
+    if (flags & FLAG_DOT) and out_dot is None:
+        out_dot = torch.empty((B, T), device=a.device, dtype=torch.float32)
+    d = _lib.GemmDesc()
+    d.a, d.w, d.lda, d.ldw = _ptr(a), _ptr(w), lda, ldw
+    d.B, d.T, d.N, d.K, d.taps, d.pad = B, T, N, K, taps, pad
+    d.epi, d.flags = epi, flags
+    d.out, d.aux_h16, d.ldo = _ptr(out), _ptr(aux), N
+    d.bias, d.resid, d.gamma, d.row_scale = _ptr(bias), _ptr(resid), _ptr(gamma), _ptr(row_scale)
+    d.pad_mask = _ptr(pad_mask)
+    d.ln_w, d.ln_b, d.ln_eps = _ptr(ln_w), _ptr(ln_b), ln_eps
+    d.dot_w, d.dot_b, d.out_dot = _ptr(dot_w), _ptr(dot_b), _ptr(out_dot)
+    _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
+    return out, aux, out_dot
+
+
+def gemm_wgrad(dy: torch.Tensor, a: torch.Tensor, dw: torch.Tensor, *, taps: int = 1, pad: int = 0, K: Optional[int] = None):
+    """dw[tap,n,k] += sum_{b,t} dy[b,t,n] a[b,t+tap-pad,k]; dy, a fp16 channels-last; dw fp32 (taps,N,K)."""
+    assert dy.dtype == torch.float16 and a.dtype == torch.float16 and dw.dtype == torch.float32
+    B, T, N = dy.shape
+    K = K if K is not None else a.shape[2]
+    _lib.check(_lib.load().osb_gemm_wgrad(_ptr(dy), dy.shape[2], _ptr(a), a.shape[2], _ptr(dw), B, T, N, K, taps, pad, _stream()),
+               "osb_gemm_wgrad")
+    return dw
+
+
+def embed_text(ids, table, inv_freq, scale):
+    B, T = ids.shape
+    dim = table.shape[1]
+    out = torch.empty((B, T, dim), device=ids.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_embed_text(_ptr(ids), _ptr(_f32(table)), _ptr(_f32(inv_freq)), _ptr(_f32(scale)), _ptr(out), B, T, dim,
+                                          table.shape[0], _stream()), "osb_embed_text")
+    return out
+
+
+def dwconv_ln(x, w, bias, eps: float, want_rstd: bool = False):
+    B, T, Cc = x.shape
+    xhat = torch.empty((B, T, Cc), device=x.device, dtype=torch.float16)
+    rstd = torch.empty((B, T), device=x.device, dtype=torch.float32) if want_rstd else None
+    _lib.check(_lib.load().osb_dwconv_ln(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(xhat), _ptr(rstd), B, T, Cc, eps, _stream()),
+               "osb_dwconv_ln")
+    return xhat, rstd
+
+
+def layernorm(x, w, b, eps: float, f32: bool = True, h16: bool = False):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    o32 = torch.empty_like(x) if f32 else None
+    o16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if h16 else None
+    _lib.check(_lib.load().osb_layernorm(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(b)), _ptr(o32), _ptr(o16), rows, Cc, eps, _stream()),
+               "osb_layernorm")
+    return o32, o16
+
+
+def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False):
+    B, T, Cc = x.shape
+    k = w.shape[-1]
+    o32 = torch.empty_like(x) if f32 else None
+    o16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if h16 else None
+    _lib.check(_lib.load().osb_variance_embed(_ptr(_f32(x)), _ptr(_f32(val)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(pad_mask), _ptr(o32),
+                                              _ptr(o16), B, T, Cc, k, _stream()), "osb_variance_embed")
+    return o32, o16
+
+
+def durations(log_d, pad_mask, factor: float, clip_val: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, T = log_d.shape
+    dur = torch.empty((B, T), device=log_d.device, dtype=torch.int64)
+    lengths = torch.empty((B,), device=log_d.device, dtype=torch.int64)
+    _lib.check(_lib.load().osb_durations(_ptr(_f32(log_d)), _ptr(pad_mask), _ptr(dur), _ptr(lengths), B, T, float(factor), float(clip_val),
+                                         _stream()), "osb_durations")
+    return dur, lengths
+
+
+def centres(dur, want_csum: bool = True):
+    B, T = dur.shape
+    assert dur.dtype in (torch.int64, torch.float32)
+    c = torch.empty((B, T), device=dur.device, dtype=torch.float32)
+    cs = torch.empty((B, T), device=dur.device, dtype=torch.int64) if want_csum else None
+    _lib.check(_lib.load().osb_centres(_ptr(dur), 1 if dur.dtype == torch.int64 else 0, _ptr(c), _ptr(cs), B, T, _stream()), "osb_centres")
+    return c, cs
+
+
+def gaussian_upsample(hs, centres_, x_len, y_len, Tm: int, delta: float = 0.1, f32: bool = True, h16: bool = False):
+    B, Tx, Cc = hs.shape
+    o32 = torch.empty((B, Tm, Cc), device=hs.device, dtype=torch.float32) if f32 else None
+    o16 = torch.empty((B, Tm, Cc), device=hs.device, dtype=torch.float16) if h16 else None
+    _lib.check(_lib.load().osb_gaussian_upsample(_ptr(_f32(hs)), _ptr(centres_), _ptr(x_len), _ptr(y_len), _ptr(o32), _ptr(o16), B, Tx, Tm,
+                                                 Cc, delta, _stream()), "osb_gaussian_upsample")
+    return o32, o16
+
+
+def expand_gather(x, csum, Tm: int):
+    B, Tx, Cc = x.shape
+    out = torch.empty((B, Tm, Cc), device=x.device, dtype=torch.float32)
+    idx = torch.empty((B, Tm), device=x.device, dtype=torch.int32)
+    _lib.check(_lib.load().osb_expand_gather(_ptr(_f32(x)), _ptr(csum), _ptr(out), _ptr(idx), B, Tx, Tm, Cc, _stream()), "osb_expand_gather")
+    return out, idx
+
+
+def pack_h16(src: torch.Tensor, *, rows: int, cols: int, src_ld: int, src_cs: int = 1, dst_ld: Optional[int] = None, col_scale=None,
+             out: Optional[torch.Tensor] = None):
+    """fp32 -> fp16 with optional column scale, source strides (elements) and zero column padding."""
+    dst_ld = dst_ld or cols
+    if out is None:
+        out = torch.empty((rows, dst_ld), device=src.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_pack_h16(_ptr(_f32(src)), src_ld, src_cs, _ptr(col_scale), _ptr(out), dst_ld, rows, cols, _stream()),
+               "osb_pack_h16")
+    return out
+
+
+def to_h16(x: torch.Tensor, pad_to: Optional[int] = None) -> torch.Tensor:
+    """Channels-last fp32 activation -> fp16 operand copy (optionally zero-padding the channel dim)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = pack_h16(x, rows=rows, cols=Cc, src_ld=Cc, dst_ld=pad_to or Cc)
+    return out.view(*x.shape[:-1], pad_to or Cc)

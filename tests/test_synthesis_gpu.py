@@ -1,0 +1,80 @@
+"""GPU parity of the synthesis path against the CPU oracle (full-size ConvNeXt config,
+deterministic weights).  Calls go through the C ABI (libosb200.so)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as O
+from oracle.spec import ModelSpec, deterministic_state_dict, generator_shapes
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, Tx, seed=1234, ragged=True):
+    g = torch.Generator().manual_seed(seed)
+    x_lengths = torch.randint(Tx // 2, Tx + 1, (B,), generator=g)
+    x_lengths[0] = Tx
+    if not ragged:
+        x_lengths[:] = Tx
+    x = torch.randint(1, 159, (B, Tx), generator=g)
+    x = x * (torch.arange(Tx)[None, :] < x_lengths[:, None])
+    return x, x_lengths
+
+
+@pytest.fixture(scope="module")
+def setup(cuda_device):
+    from optispeech_b200.factory import build_generator, model_config_from_spec
+
+    spec = ModelSpec()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    gen = build_generator(model_config_from_spec(spec))
+    missing, unexpected = gen.load_state_dict(sd, strict=True)
+    gen = gen.to(cuda_device).eval()
+    return spec, sd, gen
+
+
+@pytest.mark.parametrize("B,Tx", [(1, 57), (3, 120)])
+def test_synthesise_matches_oracle(setup, cuda_device, B, Tx):
+    spec, sd, gen = setup
+    x, x_lengths = _inputs(B, Tx)
+    ref = O.synthesise(sd, spec, x, x_lengths, 1.0, 1.0, 1.0)
+    out = gen.synthesise(x.to(cuda_device), x_lengths, d_factor=1.0, p_factor=1.0, e_factor=1.0, durations=ref["durations"])
+    # integer outputs: bit-exact given the same durations
+    assert torch.equal(out["durations"], ref["durations"])
+    assert torch.equal(out["wav_lengths"], ref["wav_lengths"])
+    assert out["wav"].shape == ref["wav"].shape
+    # floating point: fp16 tensor-core operands with fp32 accumulation; north-star tolerance 1e-3 on the waveform
+    for b in range(B):
+        n = int(ref["wav_lengths"][b])
+        err = (out["wav"][b, :n] - ref["wav"][b, :n]).abs().max().item()
+        assert err <= 1e-3, f"waveform max-abs diff {err:.3e} (sample {b})"
+    assert (out["pitch"] - ref["pitch"]).abs().max().item() <= 2e-2
+    assert (out["energy"] - ref["energy"]).abs().max().item() <= 2e-2
+    dec = out["_device"]["decoder_out"].cpu()
+    assert (dec - ref["y"]).abs().max().item() <= 3e-2
+    f0 = out["_device"]["f0_cond"].cpu()
+    assert torch.allclose(f0, ref["f0_cond"], atol=2e-2)
+
+
+def test_predicted_durations_close(setup, cuda_device):
+    """Without injection the rounded durations may flip by one frame where exp(logd)*factor sits on an integer
+    boundary; everything else must agree."""
+    spec, sd, gen = setup
+    x, x_lengths = _inputs(2, 96)
+    ref = O.synthesise(sd, spec, x, x_lengths, 1.1, 1.6, 1.2)
+    out = gen.synthesise(x.to(cuda_device), x_lengths, d_factor=1.1, p_factor=1.6, e_factor=1.2)
+    diff = (out["durations"] - ref["durations"]).abs()
+    assert diff.max().item() <= 1
+    assert (diff > 0).float().mean().item() < 0.02
+
+
+def test_expand_indices_bit_exact(cuda_device):
+    from optispeech_b200.model.generator.alignments import expand_indices
+
+    g = torch.Generator().manual_seed(7)
+    d = torch.randint(0, 9, (5, 77), generator=g)
+    d[2] = 0
+    d[2, 5] = 3
+    Tm = int(d.sum(1).max())
+    got = expand_indices(d.to(cuda_device), Tm).cpu().to(torch.int64)
+    assert torch.equal(got, O.expand_indices(d, Tm))

@@ -59,7 +59,8 @@ def run_nt(name, B, T, K, N, taps, pad, epi, flags=0, timing=True):
     d.row_scale = None
     d.pad_mask = pad_mask.data_ptr()
     d.ln_w, d.ln_b, d.ln_eps = ln_w.data_ptr(), ln_b.data_ptr(), 1e-6
-    d.dot_w, d.dot_b, d.out_dot = dot_w.data_ptr(), 0.25, out_dot.data_ptr()
+    dot_b = torch.full((1,), 0.25, device=dev)
+    d.dot_w, d.dot_b, d.out_dot = dot_w.data_ptr(), dot_b.data_ptr(), out_dot.data_ptr()
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.osb_gemm(C.byref(d), C.c_void_p(st))
     torch.cuda.synchronize()
