@@ -73,7 +73,12 @@ enum {
   OSB_FLAG_KEEPMASK = 2,  /* multiply row by (1 - pad_mask[b,t])                                               */
   OSB_FLAG_OUT_H16 = 4,   /* also write an fp16 copy of the result to aux_h16                                  */
   OSB_FLAG_SAVE_PRE = 8,  /* write the pre-activation / pre-LN value as fp16 to aux_h16 (for backward)         */
-  OSB_FLAG_DOT = 16       /* RELU_LN only: out_dot[b,t] = <LN row, dot_w> + dot_b, 0 at padded rows            */
+  OSB_FLAG_DOT = 16,      /* RELU_LN only: out_dot[b,t] = <LN row, dot_w> + dot_b, 0 at padded rows            */
+  /* Split precision ("fp16x3"): a value v is carried as hi = fp16(v), lo = fp16(v - hi) and the product
+   * is accumulated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in the fp32 TMEM accumulator (~2^-21 relative
+   * error instead of 2^-11).  Needed to hold the 1e-3 waveform tolerance at full-scale amplitude. */
+  OSB_FLAG_SPLIT_IN = 32, /* a is (B,T,[hi K | lo K]) with lda >= 2K; w is (2, taps, N, ldw): [0] = hi parts, [1] = lo parts */
+  OSB_FLAG_SPLIT_OUT = 64 /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                 */
 };
 
 typedef struct osb_gemm_desc {
@@ -127,18 +132,18 @@ int osb_embed_text(const int64_t* ids, const float* table, const float* inv_freq
  * LayerNorm weight/bias are folded into the pointwise-1 GEMM weights by the host), rstd optional.
  * Replaces ConvNeXtBlock.dwconv + .norm (modules/convnext.py:22-23,36-38).  C in {128,256,384,512}. */
 int osb_dwconv_ln(const float* x, const float* w /*(C,7)*/, const float* bias, void* xhat_h16, float* rstd /*(B*T) or NULL*/,
-                  int32_t B, int32_t T, int32_t C, float eps, void* stream);
+                  int32_t B, int32_t T, int32_t C, float eps, int32_t split /* rows [hi C | lo C] */, void* stream);
 
 /* Row LayerNorm with affine; fp32 and/or fp16 output.  Replaces ConvNeXtBackbone.final_layer_norm
  * (modules/convnext.py:84,102) and WaveNeXt.norm (vocoder/wavenext/__init__.py:68,84). */
 int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
-                  float eps, void* stream);
+                  float eps, int32_t split, void* stream);
 
 /* out = (x + bias + Conv1d(1->C, k, same)(val)) * (1 - pad_mask).  Replaces PitchPredictor.forward/
  * infer's embed + add + mask (modules/core.py:152-176). */
 int osb_variance_embed(const float* x, const float* val /*(B,T)*/, const float* w /*(C,k)*/, const float* bias,
                        const uint8_t* pad_mask, float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize,
-                       void* stream);
+                       int32_t split, void* stream);
 
 /* dur = clamp(ceil((exp(log_d) - clip_val) * factor), 0) as int64, 0 at pads; lengths[b] = sum_t dur.
  * Replaces DurationPredictor.infer (modules/core.py:126-133) and y_lengths (generator/__init__.py:258). */
@@ -160,11 +165,12 @@ int osb_gaussian_upsample(const float* hs, const float* centres, const int64_t* 
 int osb_expand_gather(const float* x, const int64_t* csum, float* out, int32_t* index_out, int32_t B, int32_t Tx, int32_t Tm,
                       int32_t C, void* stream);
 
-/* dst[r,c] = fp16(src[r*src_ld + c*src_cs] * col_scale[c]) for c < cols, 0 for cols <= c < dst_ld.
+/* v = src[r*src_ld + c*src_cs] * col_scale[c];  dst[r*dst_rs + c] = hi = fp16(v) for c < cols, 0 for cols <= c < dst_cols;
+ * if dst_lo != NULL also dst_lo[r*dst_rs + c] = fp16(v - hi).
  * Weight/activation packing for the tensor-core operands (no reference counterpart: the
  * reference's `16-mixed` autocast does this implicitly, configs/trainer/default.yaml:11). */
-int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, int64_t dst_ld,
-                 int64_t rows, int32_t cols, void* stream);
+int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, void* dst_lo, int64_t dst_rs,
+                 int32_t dst_cols, int64_t rows, int32_t cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ OSB_OK = 0
 # osb_epilogue
 EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU = range(6)
 # flags
-FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT = 1, 2, 4, 8, 16
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT = 1, 2, 4, 8, 16, 32, 64
 
 
 class GemmDesc(C.Structure):
@@ -83,14 +83,14 @@ def load() -> C.CDLL:
     P, I32, I64, F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
         "osb_embed_text": [P, P, P, P, P, I32, I32, I32, I32, P],
-        "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, P],
-        "osb_layernorm": [P, P, P, P, P, I64, I32, F, P],
-        "osb_variance_embed": [P, P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, I32, P],
+        "osb_layernorm": [P, P, P, P, P, I64, I32, F, I32, P],
+        "osb_variance_embed": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_durations": [P, P, P, P, I32, I32, F, F, P],
         "osb_centres": [P, I32, P, P, I32, I32, P],
         "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
         "osb_expand_gather": [P, P, P, P, I32, I32, I32, I32, P],
-        "osb_pack_h16": [P, I64, I64, P, P, I64, I64, I32, P],
+        "osb_pack_h16": [P, I64, I64, P, P, P, I64, I32, I64, I32, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

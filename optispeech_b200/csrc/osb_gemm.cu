@@ -75,6 +75,25 @@ __device__ __forceinline__ void st_f32x32(float* dst, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
+__device__ __forceinline__ void st_h16x32_lo(__half* dst, const float (&v)[32]) {
+  // residual after fp16 rounding: lo = fp16(v - float(fp16(v)))
+  float r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = v[i] - __half2float(__float2half_rn(v[i]));
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    __half2 h0 = __floats2half2_rn(r[i], r[i + 1]);
+    __half2 h1 = __floats2half2_rn(r[i + 2], r[i + 3]);
+    __half2 h2 = __floats2half2_rn(r[i + 4], r[i + 5]);
+    __half2 h3 = __floats2half2_rn(r[i + 6], r[i + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dst + i) = u;
+  }
+}
 __device__ __forceinline__ void st_h16x32(__half* dst, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
@@ -88,6 +107,18 @@ __device__ __forceinline__ void st_h16x32(__half* dst, const float (&v)[32]) {
     u.z = *reinterpret_cast<uint32_t*>(&h2);
     u.w = *reinterpret_cast<uint32_t*>(&h3);
     *reinterpret_cast<uint4*>(dst + i) = u;
+  }
+}
+
+// fp16 destination row `row`, columns [n, n+32): plain (stride ldo) or split [hi ldo | lo ldo] (stride 2*ldo)
+__device__ __forceinline__ void store_h(const GemmKParams& p, void* base, long long row, int n, const float (&v)[32]) {
+  __half* hb = static_cast<__half*>(base);
+  if (p.flags & OSB_FLAG_SPLIT_OUT) {
+    __half* r = hb + row * (2 * p.ldo);
+    st_h16x32(r + n, v);
+    st_h16x32_lo(r + p.ldo + n, v);
+  } else {
+    st_h16x32(hb + row * p.ldo + n, v);
   }
 }
 
@@ -117,17 +148,17 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         for (int i = 0; i < 32; ++i) v[i] *= keep;
         if (valid) {
           st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
-          if (p.flags & OSB_FLAG_OUT_H16) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
+          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, n, v);
         }
       } else if constexpr (EPI == OSB_EPI_GELU) {
         if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        if (valid) st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + n, v);
+        if (valid) store_h(p, p.out, row, n, v);
       } else if constexpr (EPI == OSB_EPI_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        if (valid) st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + n, v);
+        if (valid) store_h(p, p.out, row, n, v);
       } else {  // RESID
         if (valid) {
           const float* rp = p.resid + row * p.ldo + n;
@@ -140,7 +171,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
             v[i + 3] = (r4.w + __ldg(p.gamma + n + i + 3) * v[i + 3] * rs) * keep;
           }
           st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
-          if (p.flags & OSB_FLAG_OUT_H16) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
+          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, n, v);
         }
       }
     }
@@ -193,10 +224,10 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       }
       if (valid) {
         if constexpr (EPI == OSB_EPI_RELU_LN) {
-          if (p.out != nullptr) st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + c0, v);
+          if (p.out != nullptr) store_h(p, p.out, row, c0, v);
         } else {
           st_f32x32(static_cast<float*>(p.out) + row * p.ldo + c0, v);
-          if (p.flags & OSB_FLAG_OUT_H16) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
+          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, c0, v);
         }
       }
     }
@@ -241,7 +272,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int t0 = (blockIdx.x % p.m_tiles) * BM;
   const int n0 = blockIdx.y * BN;
   const int num_kb = (p.K + BKE - 1) / BKE;
-  const int iters = p.taps * num_kb;
+  // split precision: three passes over K per tap — (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo)
+  const bool split_in = (p.flags & OSB_FLAG_SPLIT_IN) != 0;
+  const int nsub = split_in ? 3 : 1;
+  const int iters = p.taps * nsub * num_kb;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -250,14 +284,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (it / Cfg::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        const int tap = it / num_kb;
-        const int kb = it - tap * num_kb;
+        const int tap = it / (nsub * num_kb);
+        const int rem = it - tap * (nsub * num_kb);
+        const int sub = rem / num_kb;
+        const int kb = rem - sub * num_kb;
+        const int a_k = kb * BKE + (sub == 1 ? p.K : 0);
+        const int w_slice = tap + (sub == 2 ? p.taps : 0);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
-        tma_load_3d(sA, &tmA, &full_bar[s], kb * BKE, t0 + tap - p.pad, b);
+        tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 + tap - p.pad, b);
 #pragma unroll
         for (int c = 0; c < Cfg::NCHUNK; ++c)
-          tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], kb * BKE, n0 + c * Cfg::NINST, tap);
+          tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], kb * BKE, n0 + c * Cfg::NINST, w_slice);
       }
     }
   } else if (warp == 1) {
@@ -517,10 +555,14 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   OSB_REQUIRE(bn > 0, OSB_ERR_SHAPE);
   const int ninst = bn <= 256 ? bn : bn / 2;
 
+  const bool split_in = (d->flags & OSB_FLAG_SPLIT_IN) != 0;
+  if (split_in) OSB_REQUIRE(d->K % BKE == 0 && d->lda >= 2 * static_cast<int64_t>(d->K), OSB_ERR_SHAPE);
   CUtensorMap tmA, tmW;
-  int rc = make_tmap_3d(&tmA, d->a, TMA_F16, d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda, BKE, BM);
+  int rc = make_tmap_3d(&tmA, d->a, TMA_F16, split_in ? 2 * d->K : d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda,
+                        BKE, BM);
   if (rc != OSB_OK) return rc;
-  rc = make_tmap_3d(&tmW, d->w, TMA_F16, d->K, d->N, d->taps, d->ldw, static_cast<uint64_t>(d->N) * d->ldw, BKE, ninst);
+  rc = make_tmap_3d(&tmW, d->w, TMA_F16, d->K, d->N, split_in ? 2 * d->taps : d->taps, d->ldw, static_cast<uint64_t>(d->N) * d->ldw,
+                    BKE, ninst);
   if (rc != OSB_OK) return rc;
 
   GemmKParams p;

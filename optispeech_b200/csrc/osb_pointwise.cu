@@ -22,6 +22,23 @@ __device__ __forceinline__ void store_h4(__half* dst, float a, float b, float c,
   *reinterpret_cast<uint2*>(dst) = u;
 }
 
+// hi/lo split store: dst_hi[0..3] = fp16(v), dst_lo[0..3] = fp16(v - hi)
+__device__ __forceinline__ void store_h4_split(__half* dst_hi, __half* dst_lo, float a, float b, float c, float d) {
+  store_h4(dst_hi, a, b, c, d);
+  store_h4(dst_lo, a - __half2float(__float2half_rn(a)), b - __half2float(__float2half_rn(b)),
+           c - __half2float(__float2half_rn(c)), d - __half2float(__float2half_rn(d)));
+}
+// row pointer + column for an fp16 destination that is either plain (rows of C) or split (rows of [hi C | lo C])
+__device__ __forceinline__ void store_h4_row(__half* base, long long row, int C, int c, int split, float a, float b, float cc,
+                                             float d) {
+  if (split) {
+    __half* r = base + row * (2LL * C);
+    store_h4_split(r + c, r + C + c, a, b, cc, d);
+  } else {
+    store_h4(base + row * C + c, a, b, cc, d);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // text embedding: out[b,t,:] = sqrt(dim) * E[id] + scale * [sin(t*f) | cos(t*f)]
 // ------------------------------------------------------------------------------------------
@@ -55,7 +72,7 @@ __global__ void embed_text_kernel(const long long* __restrict__ ids, const float
 template <int VPL>  // float4 groups per lane: C = 128 * VPL
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w /*(C,7)*/, const float* __restrict__ bias,
-                 __half* __restrict__ xhat, float* __restrict__ rstd_out, int B, int T, int pos_per_warp, float eps) {
+                 __half* __restrict__ xhat, float* __restrict__ rstd_out, int B, int T, int pos_per_warp, float eps, int split) {
   constexpr int C = 128 * VPL;
   __shared__ float sw[7][C];
   __shared__ float sb[C];
@@ -120,7 +137,7 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w /*(C,7
     const long long row = static_cast<long long>(b) * T + t;
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
-      store_h4(xhat + row * C + v * 128 + lane * 4, d[v].x * rstd, d[v].y * rstd, d[v].z * rstd, d[v].w * rstd);
+      store_h4_row(xhat, row, C, v * 128 + lane * 4, split, d[v].x * rstd, d[v].y * rstd, d[v].z * rstd, d[v].w * rstd);
     if (rstd_out != nullptr && lane == 0) rstd_out[row] = rstd;
   }
 }
@@ -131,7 +148,7 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w /*(C,7
 template <int VPL>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ out_f32,
-                 __half* __restrict__ out_h16, long long rows, float eps) {
+                 __half* __restrict__ out_h16, long long rows, float eps, int split) {
   constexpr int C = 128 * VPL;
   const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -162,7 +179,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     y.z = d[v].z * rstd * ww.z + bb.z;
     y.w = d[v].w * rstd * ww.w + bb.w;
     if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
-    if (out_h16 != nullptr) store_h4(out_h16 + row * C + c, y.x, y.y, y.z, y.w);
+    if (out_h16 != nullptr) store_h4_row(out_h16, row, C, c, split, y.x, y.y, y.z, y.w);
   }
 }
 
@@ -171,7 +188,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 // ------------------------------------------------------------------------------------------
 __global__ void variance_embed_kernel(const float* __restrict__ x, const float* __restrict__ val, const float* __restrict__ w /*(C,k)*/,
                                       const float* __restrict__ bias, const uint8_t* __restrict__ pad_mask, float* __restrict__ out_f32,
-                                      __half* __restrict__ out_h16, int B, int T, int C, int ksize) {
+                                      __half* __restrict__ out_h16, int B, int T, int C, int ksize, int split) {
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= B * T) return;
   const int lane = threadIdx.x & 31;
@@ -188,7 +205,15 @@ __global__ void variance_embed_kernel(const float* __restrict__ x, const float* 
     for (int j = 0; j < ksize; ++j) acc = fmaf(w[c * ksize + j], v[j], acc);
     const float y = (x[static_cast<long long>(row) * C + c] + acc) * keep;
     if (out_f32 != nullptr) out_f32[static_cast<long long>(row) * C + c] = y;
-    if (out_h16 != nullptr) out_h16[static_cast<long long>(row) * C + c] = __float2half_rn(y);
+    if (out_h16 != nullptr) {
+      const __half hi = __float2half_rn(y);
+      if (split) {
+        out_h16[static_cast<long long>(row) * 2 * C + c] = hi;
+        out_h16[static_cast<long long>(row) * 2 * C + C + c] = __float2half_rn(y - __half2float(hi));
+      } else {
+        out_h16[static_cast<long long>(row) * C + c] = hi;
+      }
+    }
   }
 }
 
@@ -341,17 +366,20 @@ __global__ void expand_gather_kernel(const float* __restrict__ x, const long lon
 //   zero elsewhere (c in [cols, dst_ld))
 // ------------------------------------------------------------------------------------------
 __global__ void pack_h16_kernel(const float* __restrict__ src, long long src_ld, long long src_cs, const float* __restrict__ col_scale,
-                                __half* __restrict__ dst, long long dst_ld, long long rows, int cols) {
+                                __half* __restrict__ dst, __half* __restrict__ dst_lo, long long dst_rs, int dst_cols, long long rows,
+                                int cols) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= rows * dst_ld) return;
-  const long long r = i / dst_ld;
-  const int c = static_cast<int>(i % dst_ld);
+  if (i >= rows * dst_cols) return;
+  const long long r = i / dst_cols;
+  const int c = static_cast<int>(i % dst_cols);
   float v = 0.f;
   if (c < cols) {
     v = src[r * src_ld + c * src_cs];
     if (col_scale != nullptr) v *= col_scale[c];
   }
-  dst[i] = __float2half_rn(v);
+  const __half hi = __float2half_rn(v);
+  dst[r * dst_rs + c] = hi;
+  if (dst_lo != nullptr) dst_lo[r * dst_rs + c] = __float2half_rn(v - __half2float(hi));
 }
 
 }  // namespace
@@ -371,7 +399,7 @@ extern "C" int osb_embed_text(const int64_t* ids, const float* table, const floa
 }
 
 extern "C" int osb_dwconv_ln(const float* x, const float* w, const float* bias, void* xhat_h16, float* rstd, int32_t B, int32_t T,
-                             int32_t C, float eps, void* stream) {
+                             int32_t C, float eps, int32_t split, void* stream) {
   OSB_REQUIRE(x && w && bias && xhat_h16, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384 || C == 128 || C == 512), OSB_ERR_SHAPE);
   const int ppw = T >= 64 ? 16 : 8;
@@ -380,39 +408,40 @@ extern "C" int osb_dwconv_ln(const float* x, const float* w, const float* bias, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __half* o = static_cast<__half*>(xhat_h16);
   switch (C / 128) {
-    case 1: dwconv_ln_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
-    case 2: dwconv_ln_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
-    case 3: dwconv_ln_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
-    case 4: dwconv_ln_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps); break;
+    case 1: dwconv_ln_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps, split); break;
+    case 2: dwconv_ln_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps, split); break;
+    case 3: dwconv_ln_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps, split); break;
+    case 4: dwconv_ln_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, bias, o, rstd, B, T, ppw, eps, split); break;
   }
   count_launch();
   return launch_status();
 }
 
 extern "C" int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
-                             float eps, void* stream) {
+                             float eps, int32_t split, void* stream) {
   OSB_REQUIRE(x && w && b && (out_f32 || out_h16), OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && (C == 128 || C == 256 || C == 384 || C == 512), OSB_ERR_SHAPE);
   const unsigned blocks = static_cast<unsigned>((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __half* oh = static_cast<__half*>(out_h16);
   switch (C / 128) {
-    case 1: layernorm_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
-    case 2: layernorm_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
-    case 3: layernorm_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
-    case 4: layernorm_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps); break;
+    case 1: layernorm_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
+    case 2: layernorm_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
+    case 3: layernorm_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
+    case 4: layernorm_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
   }
   count_launch();
   return launch_status();
 }
 
 extern "C" int osb_variance_embed(const float* x, const float* val, const float* w, const float* bias, const uint8_t* pad_mask,
-                                  float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize, void* stream) {
+                                  float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize, int32_t split,
+                                  void* stream) {
   OSB_REQUIRE(x && val && w && bias && (out_f32 || out_h16), OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && C > 0 && ksize > 0 && ksize <= 16 && (ksize & 1), OSB_ERR_SHAPE);
   const int rows = B * T;
   variance_embed_kernel<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, val, w, bias, pad_mask, out_f32, static_cast<__half*>(out_h16), B, T, C, ksize);
+      x, val, w, bias, pad_mask, out_f32, static_cast<__half*>(out_h16), B, T, C, ksize, split);
   count_launch();
   return launch_status();
 }
@@ -468,13 +497,13 @@ extern "C" int osb_expand_gather(const float* x, const int64_t* csum, float* out
   return launch_status();
 }
 
-extern "C" int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, int64_t dst_ld,
-                            int64_t rows, int32_t cols, void* stream) {
+extern "C" int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, void* dst_lo,
+                            int64_t dst_rs, int32_t dst_cols, int64_t rows, int32_t cols, void* stream) {
   OSB_REQUIRE(src && dst, OSB_ERR_ARG);
-  OSB_REQUIRE(rows > 0 && cols > 0 && dst_ld >= cols, OSB_ERR_SHAPE);
-  const long long n = rows * dst_ld;
+  OSB_REQUIRE(rows > 0 && cols > 0 && dst_cols >= cols && dst_rs >= dst_cols, OSB_ERR_SHAPE);
+  const long long n = rows * dst_cols;
   pack_h16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, src_ld, src_cs, col_scale, static_cast<__half*>(dst), dst_ld, rows, cols);
+      src, src_ld, src_cs, col_scale, static_cast<__half*>(dst), static_cast<__half*>(dst_lo), dst_rs, dst_cols, rows, cols);
   count_launch();
   return launch_status();
 }

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from ... import ops
+from ... import ops, precision
 from ...utils import sequence_mask
 from .alignments import GaussianUpsampling, expand_by_duration
 
@@ -87,8 +87,9 @@ class OptiSpeechGenerator(nn.Module):
         x_mask = sequence_mask(x_lengths, x.shape[1])
         in_pad = ~x_mask
 
+        split = precision.use_split(False)
         h, _ = self.text_embedding(x)
-        h, h16 = self.encoder(h, in_pad, want_h16=True)
+        h, h16 = self.encoder(h, in_pad, want_h16=True, split=split)
 
         if (self.num_speakers > 1) and sids is None:
             sids = torch.zeros(x.shape[0], dtype=torch.long, device=dev)
@@ -96,7 +97,7 @@ class OptiSpeechGenerator(nn.Module):
             lids = torch.zeros(x.shape[0], dtype=torch.long, device=dev)
         if sids is not None or lids is not None:
             h = self._speaker_language(h, sids, lids).contiguous()
-            h16 = ops.to_h16(h)
+            h16 = ops.to_h16(h, split=split)
 
         d_pred, y_lengths = self.duration_predictor.infer(h, in_pad, factor=d_factor, x_h16=h16)
         if durations is None:
@@ -121,11 +122,11 @@ class OptiSpeechGenerator(nn.Module):
         tgt_pad = ~y_mask
 
         y = self.feature_upsampler(hs=h, ds=durations, h_masks=y_mask, d_masks=x_mask, x_lengths=x_lengths, y_lengths=y_lengths)
-        y, y16 = self.decoder(y, tgt_pad, want_h16=True)
+        y, y16 = self.decoder(y, tgt_pad, want_h16=True, split=split)
         t1.record()
 
         f0_cond, _ = expand_by_duration(pitch.unsqueeze(-1), durations, max_len=y_max_length)
-        wav = self.vocoder.forward_cl(y16, tgt_pad)
+        wav = self.vocoder.forward_cl(y16, tgt_pad, split)
         wav_lengths = y_lengths * self.hop_length
         t2.record()
 

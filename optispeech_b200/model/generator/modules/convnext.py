@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .... import ops
+from .... import ops, precision
 from ...packing import PackedCache, pack_linear
 
 
@@ -76,21 +76,22 @@ class ConvNeXtBlock(nn.Module):
 
         return self._packed.get("fwd", srcs, build)
 
-    def forward_cl(self, x: torch.Tensor, pad_mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
+    def forward_cl(self, x: torch.Tensor, pad_mask_u8: Optional[torch.Tensor], split: bool = False) -> torch.Tensor:
         """Channels-last forward: x (B,T,C) fp32 -> (B,T,C) fp32, pad mask (B,T) uint8 applied to the output
         (the reference's ConvNeXtBackbone multiplies by the mask right after each block, convnext.py:98-101)."""
         w1, b1, w2 = self.packed()
-        xhat, _ = ops.dwconv_ln(x, self.dwconv.weight.view(self.dim, 7), self.dwconv.bias, self.norm.eps)
-        h, _, _ = ops.gemm(xhat, w1, epi=ops.EPI_GELU, bias=b1)
+        fin = ops.FLAG_SPLIT_IN if split else 0
+        xhat, _ = ops.dwconv_ln(x, self.dwconv.weight.view(self.dim, 7), self.dwconv.bias, self.norm.eps, split=split)
+        h, _, _ = ops.gemm(xhat, w1, epi=ops.EPI_GELU, bias=b1, flags=fin | (ops.FLAG_SPLIT_OUT if split else 0))
         scale = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
         gamma = self.gamma if self.gamma is not None else torch.ones(self.dim, device=x.device)
         out, _, _ = ops.gemm(h, w2, epi=ops.EPI_RESID, bias=self.pwconv2.bias, resid=x, gamma=gamma, row_scale=scale,
-                             pad_mask=pad_mask_u8, flags=ops.FLAG_KEEPMASK if pad_mask_u8 is not None else 0)
+                             pad_mask=pad_mask_u8, flags=fin | (ops.FLAG_KEEPMASK if pad_mask_u8 is not None else 0))
         return out
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Reference signature: x (B, C, T) -> (B, C, T)."""
-        return self.forward_cl(x.transpose(1, 2).contiguous(), None).transpose(1, 2)
+        return self.forward_cl(x.transpose(1, 2).contiguous(), None, precision.use_split(self.training)).transpose(1, 2)
 
 
 class ConvNeXtBackbone(nn.Module):
@@ -122,12 +123,14 @@ class ConvNeXtBackbone(nn.Module):
             nn.init.trunc_normal_(m.weight, std=0.02)
             nn.init.constant_(m.bias, 0)
 
-    def forward(self, x: torch.Tensor, padding_mask: Optional[torch.Tensor] = None, want_h16: bool = False):
-        """x (B,T,C) fp32, padding_mask (B,T) bool True = pad -> (B,T,C) fp32 [, fp16 copy]."""
+    def forward(self, x: torch.Tensor, padding_mask: Optional[torch.Tensor] = None, want_h16: bool = False,
+                split: Optional[bool] = None):
+        """x (B,T,C) fp32, padding_mask (B,T) bool True = pad -> (B,T,C) fp32 [, fp16 operand copy]."""
         x = x.contiguous()
+        split = precision.use_split(self.training) if split is None else split
         mask_u8 = None if padding_mask is None else padding_mask.to(torch.uint8).contiguous()
         for blk in self.convnext:
-            x = blk.forward_cl(x, mask_u8)
+            x = blk.forward_cl(x, mask_u8, split)
         ln = self.final_layer_norm
-        o32, o16 = ops.layernorm(x, ln.weight, ln.bias, ln.eps, f32=True, h16=want_h16)
+        o32, o16 = ops.layernorm(x, ln.weight, ln.bias, ln.eps, f32=True, h16=want_h16, split=split)
         return (o32, o16) if want_h16 else o32

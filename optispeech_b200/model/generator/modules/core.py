@@ -16,7 +16,7 @@ import math
 import torch
 from torch import nn
 
-from .... import ops
+from .... import ops, precision
 from ...packing import PackedCache, pack_conv
 from .layers import LayerNorm, ScaledSinusoidalEmbedding
 
@@ -65,9 +65,10 @@ class VariancePredictor(nn.Module):
         srcs = [layer[0].weight for layer in self.conv]
         return self._packed.get("fwd", srcs, lambda: [pack_conv(layer[0].weight) for layer in self.conv])
 
-    def forward_h16(self, x_h16: torch.Tensor, pad_mask_u8: torch.Tensor) -> torch.Tensor:
-        """x fp16 (B,T,dim), pad mask (B,T) uint8 -> (B,T) fp32 predictions, 0 at pads."""
+    def forward_h16(self, x_h16: torch.Tensor, pad_mask_u8: torch.Tensor, split: bool = False) -> torch.Tensor:
+        """x fp16 (B,T,dim) (or split (B,T,2*dim)), pad mask (B,T) uint8 -> (B,T) fp32 predictions, 0 at pads."""
         ws = self.packed()
+        fl = (ops.FLAG_SPLIT_IN | ops.FLAG_SPLIT_OUT) if split else 0
         pad = (self.kernel_size - 1) // 2
         h = x_h16
         n = len(self.conv)
@@ -75,10 +76,11 @@ class VariancePredictor(nn.Module):
             conv, ln = layer[0], layer[2]
             last = i == n - 1
             if not last:
-                h, _, _ = ops.gemm(h, ws[i], epi=ops.EPI_RELU_LN, pad=pad, bias=conv.bias, ln_w=ln.weight, ln_b=ln.bias,
+                h, _, _ = ops.gemm(h, ws[i], epi=ops.EPI_RELU_LN, flags=fl, pad=pad, bias=conv.bias, ln_w=ln.weight, ln_b=ln.bias,
                                    ln_eps=ln.eps)
             else:
-                _, _, out = ops.gemm(h, ws[i], epi=ops.EPI_RELU_LN, flags=ops.FLAG_DOT, pad=pad, bias=conv.bias,
+                _, _, out = ops.gemm(h, ws[i], epi=ops.EPI_RELU_LN, flags=ops.FLAG_DOT | (ops.FLAG_SPLIT_IN if split else 0), pad=pad,
+                                     bias=conv.bias,
                                      ln_w=ln.weight, ln_b=ln.bias, ln_eps=ln.eps, dot_w=self.linear.weight.view(-1),
                                      dot_b=self.linear.bias,
                                      pad_mask=pad_mask_u8)
@@ -86,7 +88,8 @@ class VariancePredictor(nn.Module):
 
     def forward(self, x: torch.Tensor, padding_mask) -> torch.Tensor:
         """Reference signature: x (B,T,dim) fp32, padding_mask (B,T) bool -> (B,T)."""
-        return self.forward_h16(ops.to_h16(x.contiguous()), padding_mask.to(torch.uint8).contiguous())
+        split = precision.use_split(self.training)
+        return self.forward_h16(ops.to_h16(x.contiguous(), split=split), padding_mask.to(torch.uint8).contiguous(), split)
 
 
 class DurationPredictor(VariancePredictor):
@@ -96,9 +99,11 @@ class DurationPredictor(VariancePredictor):
 
     @torch.inference_mode()
     def infer(self, x, mask, factor=1.0, x_h16=None):
-        """-> (durations int64 (B,T), lengths int64 (B,)); reference returns durations only (core.py:115-133)."""
+        """-> (durations int64 (B,T), lengths int64 (B,)); reference returns durations only (core.py:115-133).
+        `x_h16`, when given, must be in the current inference operand format (see precision.use_split)."""
         mask_u8 = mask.to(torch.uint8).contiguous()
-        log_d = self.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous()), mask_u8)
+        split = precision.use_split(False)
+        log_d = self.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         return ops.durations(log_d, mask_u8, factor, self.clip_val)
 
 
@@ -114,24 +119,26 @@ class PitchPredictor(nn.Module):
             torch.nn.Dropout(embed_dropout),
         )
 
-    def _embed_add(self, x, values, mask_u8, want_h16):
+    def _embed_add(self, x, values, mask_u8, want_h16, split=False):
         conv = self.embed[0]
         return ops.variance_embed(x.contiguous(), values.contiguous(), conv.weight.view(self.dim, -1), conv.bias, mask_u8,
-                                  f32=True, h16=want_h16)
+                                  f32=True, h16=want_h16, split=split)
 
     def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor):
         """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics."""
         mask_u8 = padding_mask.to(torch.uint8).contiguous()
-        preds = self.predictor.forward_h16(ops.to_h16(x.contiguous()), mask_u8)
+        split = precision.use_split(self.training)
+        preds = self.predictor.forward_h16(ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         out, _ = self._embed_add(x, target, mask_u8, False)
         return out, preds
 
     @torch.inference_mode()
     def infer(self, x, padding_mask, factor=1.0, x_h16=None, want_h16=False):
         mask_u8 = padding_mask.to(torch.uint8).contiguous()
-        preds = self.predictor.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous()), mask_u8)
+        split = precision.use_split(False)
+        preds = self.predictor.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         preds = preds * factor
-        o32, o16 = self._embed_add(x, preds, mask_u8, want_h16)
+        o32, o16 = self._embed_add(x, preds, mask_u8, want_h16, split)
         if want_h16:
             return o32, preds, o16
         return o32, preds

@@ -1,6 +1,7 @@
 """Packed tensor-core operands derived from fp32 master parameters.
 
-The CUDA kernels consume fp16 weights in (taps, N, K) layout; nn.Parameters stay fp32 with the
+The CUDA kernels consume fp16 weights in (2, taps, N, K) layout ([0] = hi = fp16(w), [1] = lo =
+fp16(w - hi), the second only read in split-precision mode); nn.Parameters stay fp32 with the
 reference's shapes so `state_dict` is interchangeable.  Packed copies are cached per module and
 rebuilt when any source parameter changes (tracked through the tensors' in-place version
 counters and storage pointers), e.g. after an optimizer step or `load_state_dict`.
@@ -36,24 +37,26 @@ class PackedCache:
 
 
 def pack_linear(weight: torch.Tensor, col_scale: torch.Tensor | None = None, k_pad: int | None = None) -> torch.Tensor:
-    """(N, K) fp32 -> (1, N, Kp) fp16, optionally scaling column k by col_scale[k]."""
+    """(N, K) fp32 -> (2, 1, N, Kp) fp16 hi/lo; column k optionally scaled by col_scale[k] first."""
     from .. import ops
 
     N, K = weight.shape
     Kp = k_pad or K
     w = weight.detach().contiguous()
-    return ops.pack_h16(w, rows=N, cols=K, src_ld=K, dst_ld=Kp, col_scale=col_scale).view(1, N, Kp)
+    out = torch.empty((2, 1, N, Kp), device=w.device, dtype=torch.float16)
+    ops.pack_h16(w, rows=N, cols=K, src_ld=K, dst_cols=Kp, col_scale=col_scale, out=out[0, 0], out_lo=out[1, 0])
+    return out
 
 
 def pack_conv(weight: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
-    """Conv1d weight (N, Cin, k) fp32 -> (k, N, Cin_pad) fp16 (one K-major matrix per tap)."""
+    """Conv1d weight (N, Cin, k) fp32 -> (2, k, N, Cin_pad) fp16 hi/lo (one K-major matrix per tap)."""
     from .. import ops
 
     N, Cin, k = weight.shape
     Kp = k_pad or Cin
     w = weight.detach().contiguous()
-    out = torch.empty((k, N, Kp), device=w.device, dtype=torch.float16)
+    out = torch.empty((2, k, N, Kp), device=w.device, dtype=torch.float16)
     for tap in range(k):
         # element (n, c) of tap lives at w[n, c, tap] = base + n*Cin*k + c*k + tap
-        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_ld=Kp, out=out[tap])
+        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_cols=Kp, out=out[0, tap], out_lo=out[1, tap])
     return out

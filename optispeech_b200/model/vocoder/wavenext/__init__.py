@@ -17,7 +17,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .... import ops
+from .... import ops, precision
 from ...generator.modules import ConvNeXtBackbone
 from ...packing import PackedCache, pack_conv, pack_linear
 
@@ -43,14 +43,15 @@ class WaveNeXtHead(nn.Module):
 
         return self._packed.get("fold", srcs, build)
 
-    def forward_h16(self, x_h16: torch.Tensor) -> torch.Tensor:
-        """x fp16 (B,T,dim) -> clipped audio (B, T*hop) fp32."""
+    def forward_h16(self, x_h16: torch.Tensor, split: bool = False) -> torch.Tensor:
+        """x fp16 (B,T,dim) (or split (B,T,2*dim)) -> clipped audio (B, T*hop) fp32."""
         w, b = self.packed()
-        out, _, _ = ops.gemm(x_h16, w, epi=ops.EPI_BIAS, flags=ops.FLAG_CLIP, bias=b)
+        out, _, _ = ops.gemm(x_h16, w, epi=ops.EPI_BIAS, flags=ops.FLAG_CLIP | (ops.FLAG_SPLIT_IN if split else 0), bias=b)
         return out.view(out.shape[0], -1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.forward_h16(ops.to_h16(x.contiguous()))
+        split = precision.use_split(self.training)
+        return self.forward_h16(ops.to_h16(x.contiguous(), split=split), split)
 
 
 class WaveNeXt(nn.Module):
@@ -75,14 +76,15 @@ class WaveNeXt(nn.Module):
         self.head = WaveNeXtHead(dim=dim, n_fft=n_fft, hop_length=hop_length)
         self._packed = PackedCache()
 
-    def forward_cl(self, x_h16: torch.Tensor, padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Channels-last entry: x fp16 (B,T,input_channels) -> (B, T*hop)."""
+    def forward_cl(self, x_h16: torch.Tensor, padding_mask: Optional[torch.Tensor] = None, split: bool = False) -> torch.Tensor:
+        """Channels-last entry: x fp16 (B,T,input_channels) (or split (B,T,2*input_channels)) -> (B, T*hop)."""
         w = self._packed.get("embed", [self.embed.weight], lambda: pack_conv(self.embed.weight))
-        h, _, _ = ops.gemm(x_h16, w, epi=ops.EPI_BIAS_LN, pad=3, bias=self.embed.bias, ln_w=self.norm.weight,
-                           ln_b=self.norm.bias, ln_eps=self.norm.eps)
-        _, h16 = self.backbone(h, padding_mask, want_h16=True)
-        return self.head.forward_h16(h16)
+        h, _, _ = ops.gemm(x_h16, w, epi=ops.EPI_BIAS_LN, flags=ops.FLAG_SPLIT_IN if split else 0, pad=3, bias=self.embed.bias,
+                           ln_w=self.norm.weight, ln_b=self.norm.bias, ln_eps=self.norm.eps)
+        _, h16 = self.backbone(h, padding_mask, want_h16=True, split=split)
+        return self.head.forward_h16(h16, split)
 
     def forward(self, x, f0, padding_mask=None):
         """Reference signature: x (B, C, T)."""
-        return self.forward_cl(ops.to_h16(x.transpose(1, 2).contiguous()), padding_mask)
+        split = precision.use_split(self.training)
+        return self.forward_cl(ops.to_h16(x.transpose(1, 2).contiguous(), split=split), padding_mask, split)

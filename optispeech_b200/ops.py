@@ -13,12 +13,12 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_RELU, EPI_RELU_LN, EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK,
-                   FLAG_OUT_H16, FLAG_SAVE_PRE)
+                   FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_SPLIT_IN, FLAG_SPLIT_OUT)
 
 __all__ = [
     "gemm", "embed_text", "dwconv_ln", "layernorm", "variance_embed", "durations", "centres", "gaussian_upsample",
     "expand_gather", "pack_h16", "EPI_BIAS", "EPI_GELU", "EPI_RESID", "EPI_RELU_LN", "EPI_BIAS_LN", "EPI_RELU",
-    "FLAG_CLIP", "FLAG_KEEPMASK", "FLAG_OUT_H16", "FLAG_SAVE_PRE", "FLAG_DOT",
+    "FLAG_CLIP", "FLAG_KEEPMASK", "FLAG_OUT_H16", "FLAG_SAVE_PRE", "FLAG_DOT", "FLAG_SPLIT_IN", "FLAG_SPLIT_OUT",
 ]
 
 
@@ -26,9 +26,9 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    if t is None:
-        return None
+def _ptr(t):
+    if t is None or isinstance(t, int):
+        return t
     if not t.is_cuda:
         raise _lib.OsbError("optispeech_b200 ops need CUDA tensors (no CPU fallback)")
     if not t.is_contiguous():
@@ -46,15 +46,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
          ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
-    a: fp16 (B,T,lda); w: fp16 (taps,N,ldw); outputs are allocated when not given.  Returns `out`."""
-    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 3 and w.dim() == 3
+    a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
+    w = (2,taps,N,ldw).  fp16 outputs are (B,T,N), or (B,T,2N) = [hi|lo] with FLAG_SPLIT_OUT.
+    Outputs are allocated when not given.  Returns (out, aux, out_dot)."""
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 3
     B, T, lda = a.shape
-    taps, N, ldw = w.shape
-    K = K if K is not None else min(lda, ldw)
+    if flags & FLAG_SPLIT_IN:
+        assert w.dim() == 4 and w.shape[0] == 2
+        _, taps, N, ldw = w.shape
+        K = K if K is not None else min(lda // 2, ldw)
+    else:
+        if w.dim() == 4:  # packed (2, taps, N, K): single-pass mode uses the hi parts only
+            w = w[0]
+        taps, N, ldw = w.shape
+        K = K if K is not None else min(lda, ldw)
     f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN)
+    hN = 2 * N if (flags & FLAG_SPLIT_OUT) else N
     if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)):
-        out = torch.empty((B, T, N), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
-    if (flags & (FLAG_OUT_H16 | FLAG_SAVE_PRE)) and aux is None:
+        out = torch.empty((B, T, N if f32_out else hN), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
+    if (flags & FLAG_OUT_H16) and aux is None:
+        aux = torch.empty((B, T, hN), device=a.device, dtype=torch.float16)
+    if (flags & FLAG_SAVE_PRE) and aux is None:
         aux = torch.empty((B, T, N), device=a.device, dtype=torch.float16)
     if (flags & FLAG_DOT) and out_dot is None:
         out_dot = torch.empty((B, T), device=a.device, dtype=torch.float32)
@@ -90,32 +102,36 @@ def embed_text(ids, table, inv_freq, scale):
     return out
 
 
-def dwconv_ln(x, w, bias, eps: float, want_rstd: bool = False):
+def dwconv_ln(x, w, bias, eps: float, want_rstd: bool = False, split: bool = False):
     B, T, Cc = x.shape
-    xhat = torch.empty((B, T, Cc), device=x.device, dtype=torch.float16)
+    xhat = torch.empty((B, T, 2 * Cc if split else Cc), device=x.device, dtype=torch.float16)
     rstd = torch.empty((B, T), device=x.device, dtype=torch.float32) if want_rstd else None
-    _lib.check(_lib.load().osb_dwconv_ln(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(xhat), _ptr(rstd), B, T, Cc, eps, _stream()),
-               "osb_dwconv_ln")
+    _lib.check(_lib.load().osb_dwconv_ln(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(xhat), _ptr(rstd), B, T, Cc, eps,
+                                         int(split), _stream()), "osb_dwconv_ln")
     return xhat, rstd
 
 
-def layernorm(x, w, b, eps: float, f32: bool = True, h16: bool = False):
+def _h16_like(x, split: bool):
+    return torch.empty((*x.shape[:-1], (2 if split else 1) * x.shape[-1]), device=x.device, dtype=torch.float16)
+
+
+def layernorm(x, w, b, eps: float, f32: bool = True, h16: bool = False, split: bool = False):
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     o32 = torch.empty_like(x) if f32 else None
-    o16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if h16 else None
-    _lib.check(_lib.load().osb_layernorm(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(b)), _ptr(o32), _ptr(o16), rows, Cc, eps, _stream()),
-               "osb_layernorm")
+    o16 = _h16_like(x, split) if h16 else None
+    _lib.check(_lib.load().osb_layernorm(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(b)), _ptr(o32), _ptr(o16), rows, Cc, eps, int(split),
+                                         _stream()), "osb_layernorm")
     return o32, o16
 
 
-def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False):
+def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False, split: bool = False):
     B, T, Cc = x.shape
     k = w.shape[-1]
     o32 = torch.empty_like(x) if f32 else None
-    o16 = torch.empty(x.shape, device=x.device, dtype=torch.float16) if h16 else None
+    o16 = _h16_like(x, split) if h16 else None
     _lib.check(_lib.load().osb_variance_embed(_ptr(_f32(x)), _ptr(_f32(val)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(pad_mask), _ptr(o32),
-                                              _ptr(o16), B, T, Cc, k, _stream()), "osb_variance_embed")
+                                              _ptr(o16), B, T, Cc, k, int(split), _stream()), "osb_variance_embed")
     return o32, o16
 
 
@@ -154,20 +170,26 @@ def expand_gather(x, csum, Tm: int):
     return out, idx
 
 
-def pack_h16(src: torch.Tensor, *, rows: int, cols: int, src_ld: int, src_cs: int = 1, dst_ld: Optional[int] = None, col_scale=None,
-             out: Optional[torch.Tensor] = None):
-    """fp32 -> fp16 with optional column scale, source strides (elements) and zero column padding."""
-    dst_ld = dst_ld or cols
+def pack_h16(src: torch.Tensor, *, rows: int, cols: int, src_ld: int, src_cs: int = 1, dst_cols: Optional[int] = None, col_scale=None,
+             out: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, dst_rs: Optional[int] = None):
+    """fp32 -> fp16 (hi) and optionally the rounding residual (lo), with source strides (elements), optional
+    per-column scale and zero column padding up to dst_cols.  Destination row stride dst_rs (default dst_cols)."""
+    dst_cols = dst_cols or cols
+    dst_rs = dst_rs or dst_cols
     if out is None:
-        out = torch.empty((rows, dst_ld), device=src.device, dtype=torch.float16)
-    _lib.check(_lib.load().osb_pack_h16(_ptr(_f32(src)), src_ld, src_cs, _ptr(col_scale), _ptr(out), dst_ld, rows, cols, _stream()),
-               "osb_pack_h16")
+        out = torch.empty((rows, dst_cols), device=src.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_pack_h16(_ptr(_f32(src)), src_ld, src_cs, _ptr(col_scale), _ptr(out), _ptr(out_lo), dst_rs, dst_cols, rows,
+                                        cols, _stream()), "osb_pack_h16")
     return out
 
 
-def to_h16(x: torch.Tensor, pad_to: Optional[int] = None) -> torch.Tensor:
-    """Channels-last fp32 activation -> fp16 operand copy (optionally zero-padding the channel dim)."""
+def to_h16(x: torch.Tensor, pad_to: Optional[int] = None, split: bool = False) -> torch.Tensor:
+    """Channels-last fp32 activation -> fp16 operand copy: plain (.., Cp) or split (.., [hi Cp | lo Cp])."""
     Cc = x.shape[-1]
+    Cp = pad_to or Cc
     rows = x.numel() // Cc
-    out = pack_h16(x, rows=rows, cols=Cc, src_ld=Cc, dst_ld=pad_to or Cc)
-    return out.view(*x.shape[:-1], pad_to or Cc)
+    if not split:
+        return pack_h16(x, rows=rows, cols=Cc, src_ld=Cc, dst_cols=Cp).view(*x.shape[:-1], Cp)
+    out = torch.empty((rows, 2 * Cp), device=x.device, dtype=torch.float16)
+    pack_h16(x, rows=rows, cols=Cc, src_ld=Cc, dst_cols=Cp, dst_rs=2 * Cp, out=out, out_lo=out.data_ptr() + 2 * Cp)
+    return out.view(*x.shape[:-1], 2 * Cp)

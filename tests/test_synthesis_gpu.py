@@ -33,12 +33,21 @@ def setup(cuda_device):
     return spec, sd, gen
 
 
+# (precision, waveform tolerance): "fp16x3" is the synthesis default and must meet the north-star 1e-3 bound;
+# plain "fp16" (the training operand format) is checked against the looser bound its 2^-11 operand rounding allows.
+@pytest.mark.parametrize("prec,wav_tol,feat_tol", [("fp16x3", 1e-3, 2e-3), ("fp16", 8e-3, 3e-2)])
 @pytest.mark.parametrize("B,Tx", [(1, 57), (3, 120)])
-def test_synthesise_matches_oracle(setup, cuda_device, B, Tx):
+def test_synthesise_matches_oracle(setup, cuda_device, B, Tx, prec, wav_tol, feat_tol):
+    from optispeech_b200 import precision
+
     spec, sd, gen = setup
     x, x_lengths = _inputs(B, Tx)
     ref = O.synthesise(sd, spec, x, x_lengths, 1.0, 1.0, 1.0)
-    out = gen.synthesise(x.to(cuda_device), x_lengths, d_factor=1.0, p_factor=1.0, e_factor=1.0, durations=ref["durations"])
+    precision.set_inference_precision(prec)
+    try:
+        out = gen.synthesise(x.to(cuda_device), x_lengths, d_factor=1.0, p_factor=1.0, e_factor=1.0, durations=ref["durations"])
+    finally:
+        precision.set_inference_precision("fp16x3")
     # integer outputs: bit-exact given the same durations
     assert torch.equal(out["durations"], ref["durations"])
     assert torch.equal(out["wav_lengths"], ref["wav_lengths"])
@@ -47,13 +56,14 @@ def test_synthesise_matches_oracle(setup, cuda_device, B, Tx):
     for b in range(B):
         n = int(ref["wav_lengths"][b])
         err = (out["wav"][b, :n] - ref["wav"][b, :n]).abs().max().item()
-        assert err <= 1e-3, f"waveform max-abs diff {err:.3e} (sample {b})"
-    assert (out["pitch"] - ref["pitch"]).abs().max().item() <= 2e-2
-    assert (out["energy"] - ref["energy"]).abs().max().item() <= 2e-2
+        print(f"[{prec}] B={B} Tx={Tx} sample {b}: waveform max-abs diff {err:.3e}")
+        assert err <= wav_tol, f"waveform max-abs diff {err:.3e} (sample {b})"
+    assert (out["pitch"] - ref["pitch"]).abs().max().item() <= feat_tol
+    assert (out["energy"] - ref["energy"]).abs().max().item() <= feat_tol
     dec = out["_device"]["decoder_out"].cpu()
-    assert (dec - ref["y"]).abs().max().item() <= 3e-2
+    assert (dec - ref["y"]).abs().max().item() <= feat_tol
     f0 = out["_device"]["f0_cond"].cpu()
-    assert torch.allclose(f0, ref["f0_cond"], atol=2e-2)
+    assert torch.allclose(f0, ref["f0_cond"], atol=feat_tol)
 
 
 def test_predicted_durations_close(setup, cuda_device):
