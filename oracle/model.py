@@ -282,11 +282,23 @@ def forward_sum_loss_explicit(log_p_attn, ilens, olens, blank_logprob: float = -
 
 
 def fastspeech2_losses(d_outs, p_outs, e_outs, ds, ps, es, ilens):
-    """loss.py:83-140 with use_masking=True: MSE(log d_hat, log(d + 1e-8)), SmoothL1 for pitch / energy."""
-    m = sequence_mask(ilens, int(ilens.max()))
-    dl = F.mse_loss(d_outs[m], torch.log(ds[m].float() + 1e-8))
-    pl = F.smooth_l1_loss(p_outs[m], ps[m])
-    el = F.smooth_l1_loss(e_outs[m], es[m])
+    """loss.py:83-140 as the reference *actually evaluates it* (use_masking=True, (B,Tx,1) inputs).
+
+    The reference's masks have a stray singleton axis (make_non_pad_mask -> (B,1,Tx), utils/model.py:19-21), so
+    `masked_select` broadcasts instead of selecting the non-pad positions:
+      * duration: d_outs (B,Tx,1) x mask (B,1,Tx) -> element (b,i) is taken len_b times, for EVERY i < Tx
+        (padded positions included: prediction 0 vs target log(0 + 1e-8));
+      * pitch / energy: outs (B,Tx,1) x mask (B,1,Tx,1) -> element (b,i) is taken once per sample a with len_a > i.
+    Both reduce with 'mean', i.e. a weighted mean with those multiplicities.  MSE in the log domain for durations
+    (loss.py:31-47), SmoothL1(beta=1) for pitch and energy (loss.py:77-78)."""
+    B, Tx = d_outs.shape
+    lens = ilens.to(torch.float32)
+    d_err = (d_outs - torch.log(ds.float() + 1e-8)) ** 2                      # (B, Tx)
+    dl = (d_err.sum(dim=1) * lens).sum() / (lens.sum() * Tx)
+    w = (torch.arange(Tx)[None, :] < ilens[:, None]).to(torch.float32).sum(dim=0)  # (Tx,) samples longer than i
+    denom = w.sum() * B
+    pl = (F.smooth_l1_loss(p_outs, ps, reduction="none") * w[None, :]).sum() / denom
+    el = (F.smooth_l1_loss(e_outs, es, reduction="none") * w[None, :]).sum() / denom
     return dl, pl, el
 
 

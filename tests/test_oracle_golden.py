@@ -1,0 +1,144 @@
+"""Pins the CPU oracle (oracle/) against golden vectors produced by the real reference modules
+(tests/golden/make_golden.py).  Runs without a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as L
+from oracle import model as O
+from oracle.spec import ModelSpec, deterministic_state_dict, generator_shapes, tiny_spec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+SPECS = {"tiny": tiny_spec, "full": ModelSpec}
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_state_dict_layout_matches_reference(name):
+    with open(os.path.join(GOLD, "state_dict_shapes.json")) as f:
+        ref = json.load(f)[name]
+    mine = {k: list(v) for k, v in generator_shapes(SPECS[name]()).items()}
+    assert mine == ref
+    if name == "full":  # SURVEY Appendix C / README.md:168 known answers
+        total = sum(int(np.prod(v)) for v in mine.values())
+        align = sum(int(np.prod(v)) for k, v in mine.items() if k.startswith("alignment_module"))
+        assert total == 16_493_702 and total - align == 15_891_334
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_synthesise_matches_reference(name):
+    fx = _load(f"generator_{name}.npz")
+    spec = SPECS[name]()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    if name == "tiny":  # the tiny fixture carries its state_dict: the formula must reproduce it bit-for-bit
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), fx[f"sd/{k}"]), k
+    out = O.synthesise(sd, spec, _t(fx["x"]), _t(fx["x_lengths"]), 1.1, 1.6, 1.2)
+    assert np.array_equal(out["durations"].numpy(), fx["durations"])
+    assert np.array_equal(out["wav_lengths"].numpy(), fx["wav_lengths"])
+    assert np.abs(out["wav"].numpy() - fx["wav"]).max() <= 2e-5
+    assert np.abs(out["pitch"].numpy() - fx["pitch"]).max() <= 1e-5
+    assert np.abs(out["energy"].numpy() - fx["energy"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_training_forward_backward_matches_reference(name):
+    fx = _load(f"generator_{name}.npz")
+    spec = SPECS[name]()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.generator_forward(sd, spec, _t(fx["train_x"]), _t(fx["train_x_lengths"]), _t(fx["train_mel"]), _t(fx["train_mel_lengths"]),
+                              _t(fx["train_pitches"]), _t(fx["train_energies"]), _t(fx["train_seg_rand"]))
+    assert np.array_equal(out["start_idx"].numpy(), fx["train_start_idx"])
+    for key in ("loss", "align_loss", "duration_loss", "pitch_loss", "energy_loss"):
+        assert abs(out[key].item() - float(fx[f"train_{key}"])) <= 2e-5 * max(1.0, abs(float(fx[f"train_{key}"]))), key
+    assert np.abs(out["wav_hat"].detach().numpy() - fx["train_wav_hat"]).max() <= 2e-5
+    out["loss"].backward()
+    keys = [str(k) for k in fx["train_grad_keys"]]
+    for k, ref_norm in zip(keys, fx["train_grad_norms"]):
+        g = sd[k].grad
+        if ref_norm < 0:  # parameter that never receives a gradient in the reference (decoder, vocoder, ...)
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            assert g is not None, k
+            assert abs(float(g.norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6) + 1e-7, k
+    if name == "tiny":
+        for k in keys:
+            gk = f"grad/{k}"
+            if gk in fx.files:
+                ref = fx[gk]
+                assert np.abs(sd[k].grad.numpy() - ref).max() <= 1e-4 * max(1e-3, np.abs(ref).max()), k
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_spectral_losses_match_reference(name):
+    fx = _load(f"generator_{name}.npz")
+    spec = SPECS[name]()
+    fb = L.mel_filterbank(spec.sample_rate, spec.n_fft, spec.n_feats, spec.f_min, spec.f_max)
+    assert np.abs(fb.numpy() - fx["mel_fb"]).max() <= 1e-6
+    wav_hat = _t(fx["train_wav_hat"]).clone().requires_grad_(True)
+    wav = _t(fx["val_wav_gt"])
+    ml, stft_l, sc, mag = L.forward_val_losses(wav, wav_hat, spec, fb)
+    assert abs(ml.item() - float(fx["val_mel_loss"])) <= 1e-4 * float(fx["val_mel_loss"])
+    assert abs(sc.item() - float(fx["val_sc_loss"])) <= 1e-5
+    assert abs(mag.item() - float(fx["val_mag_loss"])) <= 1e-5
+    (ml + stft_l).backward()
+    ref = fx["val_dwav_hat"]
+    assert np.abs(wav_hat.grad.numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    # the crop of the ground-truth waveform (base_lightning_module.py:38-43)
+    crop = O.crop_wav_segments(fx["train_wav"], _t(fx["train_start_idx"]), spec.segment_size, spec.hop_length)
+    assert np.array_equal(crop.numpy(), fx["val_wav_gt"])
+
+
+def test_monotonic_alignment_search_bit_exact():
+    fx = _load("algorithms.npz")
+    for i in range(6):
+        A = O.monotonic_alignment_search(fx[f"mas{i}_lp"])
+        assert np.array_equal(A, fx[f"mas{i}_A"]), i
+
+
+def test_viterbi_average_forwardsum():
+    fx = _load("algorithms.npz")
+    lp, tl, fl = _t(fx["vd_lp"]), _t(fx["vd_tl"]), _t(fx["vd_fl"])
+    ds, bin_loss = O.viterbi_decode(lp, tl, fl)
+    assert np.array_equal(ds.numpy(), fx["vd_ds"])
+    assert abs(bin_loss.item() - float(fx["vd_bin"])) <= 1e-6
+    avg = O.average_by_duration(ds, _t(fx["avg_xs"]).squeeze(-1), tl, fl)
+    assert np.abs(avg.numpy() - fx["avg_out"]).max() <= 1e-6
+    assert abs(O.forward_sum_loss(lp, tl, fl).item() - float(fx["fs_loss"])) <= 1e-5
+    assert abs(O.forward_sum_loss_explicit(lp, tl, fl).item() - float(fx["fs_loss"])) <= 1e-4
+
+
+def test_length_regulators():
+    fx = _load("algorithms.npz")
+    hs, d = _t(fx["gu_hs"]), _t(fx["gu_d"])
+    up = O.gaussian_upsampling(hs, d, _t(fx["gu_hmask"]), _t(fx["gu_dmask"]))
+    assert np.abs(up.numpy() - fx["gu_out"]).max() <= 1e-6
+    upf = O.gaussian_upsampling(hs, d.float(), _t(fx["gu_hmask"]), _t(fx["gu_dmask"]))
+    assert np.abs(upf.numpy() - fx["gu_out_float"]).max() <= 1e-6
+    ex, exl = O.expand_by_duration(hs, d)
+    assert np.array_equal(ex.numpy(), fx["ex_out"]) and np.array_equal(exl.numpy(), fx["ex_len"])
+    # integer form: frame -> token index reproduces the dense one-hot expansion exactly
+    Tm = int(exl.max())
+    idx = O.expand_indices(d, Tm)
+    gathered = torch.where(idx[..., None] >= 0, torch.gather(hs, 1, idx.clamp(min=0)[..., None].expand(-1, -1, hs.shape[-1])),
+                           torch.zeros(()))
+    assert np.array_equal(gathered.numpy(), fx["ex_out"])
+
+
+def test_beta_binomial_prior():
+    fx = _load("algorithms.npz")
+    for T, N in [(5, 3), (31, 9), (110, 24)]:
+        assert np.abs(O.beta_binomial_log_prior(T, N) - fx[f"prior_{T}_{N}"]).max() <= 1e-9
