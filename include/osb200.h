@@ -62,10 +62,18 @@ int osb_check_device(int device);             /* OSB_OK iff `device` is compute 
 typedef enum osb_epilogue {
   OSB_EPI_BIAS = 0,     /* out_f32 = acc + bias                     (flags: CLIP, KEEPMASK, OUT_H16)  */
   OSB_EPI_GELU = 1,     /* out_h16 = gelu_erf(acc + bias)           (flags: SAVE_PRE -> aux_h16)     */
-  OSB_EPI_RESID = 2,    /* out_f32 = (resid + gamma*(acc+bias)*row_scale[b]) * keep[b,t]              */
+  OSB_EPI_RESID = 2,    /* out_f32 = (resid + gamma*(acc+bias)*row_scale[b]) * keep[b,t]  (SAVE_PRE: aux = fp16(acc+bias)) */
   OSB_EPI_RELU_LN = 3,  /* y = LN(relu(acc+bias)) -> out_h16; needs BN == N (flags: DOT, SAVE_PRE)    */
   OSB_EPI_BIAS_LN = 4,  /* out_f32 = LN(acc + bias); needs BN == N  (flags: OUT_H16)                  */
-  OSB_EPI_RELU = 5      /* out_h16 = relu(acc + bias)               (flags: none)                     */
+  OSB_EPI_RELU = 5,     /* out_h16 = relu(acc + bias)               (flags: none)                     */
+  /* backward epilogues (acc is a gradient; aux_in_h16 is an activation saved by the forward pass) */
+  OSB_EPI_GELU_BWD = 6,    /* out_h16 = acc * gelu_erf'(aux_in)                                          */
+  OSB_EPI_LN_BWD = 7,      /* out_f32 = LayerNorm backward of acc wrt its input, given xhat = aux_in and
+                              rstd = row_stat (no affine: it is folded into the GEMM weights); BN == N   */
+  OSB_EPI_RELU_LN_BWD = 8, /* acc = grad of a RELU_LN output y; aux_in = r = relu(conv) saved by SAVE_PRE;
+                              out_h16 = grad wrt the conv output = LN_bwd(acc * ln_w; r) * [r > 0];
+                              with OUT_H16 also aux_h16 = fp16(acc) (for the LN parameter gradients); BN == N */
+  OSB_EPI_RELU_BWD = 9     /* out_h16 = acc * [aux_in > 0]                                               */
 } osb_epilogue;
 
 enum {
@@ -78,7 +86,8 @@ enum {
    * is accumulated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in the fp32 TMEM accumulator (~2^-21 relative
    * error instead of 2^-11).  Needed to hold the 1e-3 waveform tolerance at full-scale amplitude. */
   OSB_FLAG_SPLIT_IN = 32, /* a is (B,T,[hi K | lo K]) with lda >= 2K; w is (2, taps, N, ldw): [0] = hi parts, [1] = lo parts */
-  OSB_FLAG_SPLIT_OUT = 64 /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                 */
+  OSB_FLAG_SPLIT_OUT = 64, /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                */
+  OSB_FLAG_RELU = 128      /* EPI_BIAS only: out = relu(acc + bias)                                                */
 };
 
 typedef struct osb_gemm_desc {
@@ -105,6 +114,8 @@ typedef struct osb_gemm_desc {
   const float* dot_w;   /* DOT: (N) weight of the trailing Linear(N -> 1)                          */
   const float* dot_b;   /* DOT: (1) its bias (device pointer, may be NULL = 0)                     */
   float* out_dot;       /* DOT: (B*T) fp32                                                         */
+  const void* aux_in_h16; /* *_BWD: fp16 (B*T, ldo) saved activation                                */
+  const float* row_stat;  /* LN_BWD: (B*T) rstd saved by osb_dwconv_ln                              */
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);
@@ -171,6 +182,71 @@ int osb_expand_gather(const float* x, const int64_t* csum, float* out, int32_t* 
  * reference's `16-mixed` autocast does this implicitly, configs/trainer/default.yaml:11). */
 int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, void* dst_lo, int64_t dst_rs,
                  int32_t dst_cols, int64_t rows, int32_t cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HBM-bound backward kernels (osb_backward.cu).  They replace what torch.autograd derives for the
+ * reference modules named at each entry; parameter gradients are ACCUMULATED (+=) into caller-zeroed
+ * fp32 buffers.  Incoming gradients may carry the host's static loss scale (everything is linear).
+ * ------------------------------------------------------------------------------------- */
+
+/* Backward of the residual epilogue out = (x + gamma * z * row_scale[b]) * keep  (ConvNeXtBlock, convnext.py:42-46,
+ * + the mask of ConvNeXtBackbone.forward :100-101):  dyg = fp16(dout*keep*rs*gamma), dgamma += sum dout*keep*rs*z,
+ * db2 += sum dout*keep*rs*gamma.  z = pwconv2 output (fp16, saved by OSB_EPI_RESID + OSB_FLAG_SAVE_PRE). */
+int osb_resid_bwd_prep(const float* dout, const void* z_h16, const float* gamma, const uint8_t* pad_mask, const float* row_scale,
+                       void* dyg_h16, float* dgamma, float* db2, int64_t rows, int32_t T, int32_t C, void* stream);
+
+/* out[n] += sum_rows x[row, n] for an fp16 (rows, N) matrix: bias gradients of Linear / Conv1d layers. */
+int osb_colsum_h16(const void* x_h16, float* out, int64_t rows, int32_t N, void* stream);
+
+/* Undo the LayerNorm-affine folding of pwconv1 (W1f = W1 diag(ln_w), b1f = b1 + W1 ln_b):
+ * dw1 (in: dW1f, out: dW1 = dW1f * ln_w[c]); dln_w[c] += sum_i dW1f[i,c] W1[i,c]; dln_b[c] += sum_i db1[i] W1[i,c]. */
+int osb_ln_fold_bwd(float* dw1, const float* w1, const float* ln_w, const float* db1, float* dln_w, float* dln_b, int32_t I,
+                    int32_t C, void* stream);
+
+/* Depthwise Conv1d(k=7) backward plus the residual path of the block:
+ * dx = dout*keep + corr(dd, w);  ddw[c,j] += sum dd[b,t,c] x[b,t+j-3,c];  ddb[c] += sum dd.   (convnext.py:22,36) */
+int osb_dwconv_bwd(const float* dd, const float* dout, const float* x, const float* w /*(C,7)*/, const uint8_t* pad_mask, float* dx,
+                   float* ddw, float* ddb, int32_t B, int32_t T, int32_t C, void* stream);
+
+/* LayerNorm(affine) backward, statistics recomputed from x (final_layer_norm, convnext.py:84,102). */
+int osb_layernorm_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int64_t rows, int32_t C,
+                      float eps, void* stream);
+
+/* Backward of a VariancePredictor's tail (core.py:92-96): last LayerNorm + Linear(->1) + masked_fill.
+ * g_conv = fp16 gradient wrt the last Conv1d output (ReLU gate applied); accumulates dlin_w, dlin_b, dln_w, dln_b.
+ * r = relu(conv) of the last layer, fp16, saved by OSB_EPI_RELU_LN + OSB_FLAG_SAVE_PRE. */
+int osb_predictor_tail_bwd(const float* d_out /*(rows)*/, const uint8_t* pad_mask, const void* r_h16, const float* ln_w,
+                           const float* ln_b, const float* lin_w, void* g_conv_h16, float* dlin_w, float* dlin_b, float* dln_w,
+                           float* dln_b, int64_t rows, int32_t C, float eps, void* stream);
+
+/* LayerNorm parameter gradients of an inner predictor layer: dln_w += sum gy*xhat(r), dln_b += sum gy, with
+ * gy = fp16 gradient wrt the layer output (aux of OSB_EPI_RELU_LN_BWD + OSB_FLAG_OUT_H16). */
+int osb_ln_param_grad(const void* gy_h16, const void* r_h16, const float* ln_w, float* dln_w, float* dln_b, int64_t rows, int32_t C,
+                      float eps, void* stream);
+
+/* Backward of osb_variance_embed: dx = dout*keep (optional), dw[c,j] += sum dout*keep*val[b,t+j-h], db[c] += sum dout*keep. */
+int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* pad_mask, float* dx, float* dw, float* db, int32_t B,
+                           int32_t T, int32_t C, int32_t ksize, void* stream);
+
+/* Backward of osb_embed_text: dtable[id] += sqrt(dim)*dout (padding row untouched), dscale += sum dout*pe. */
+int osb_embed_text_bwd(const float* dout, const int64_t* ids, const float* inv_freq, float* dtable, float* dscale, int32_t B,
+                       int32_t T, int32_t dim, int32_t n_vocab, int32_t padding_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Alignment-learning kernels (osb_align.cu) — the reference runs these on the host CPU with numba.
+ * ------------------------------------------------------------------------------------- */
+
+/* Monotonic alignment search per sample over log_p_attn[b, :m_len, :x_len] (fp32 (B,Tm,Tx)): float64 DP with the
+ * reference's float32 first-row running sum and '>=' tie-break, back-track, bincount.
+ * path (B,Tm) int32 = token of each frame (-1 past m_len), durations (B,Tx) fp32.  Bit-exact vs the reference.
+ * Replaces _monotonic_alignment_search + the bincount of viterbi_decode (generator/alignments.py:177-235). */
+int osb_mas(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len, int32_t* path, float* durations, int32_t B,
+            int32_t Tm, int32_t Tx, void* stream);
+
+/* out[b,n] = mean(xs[b, start_n:end_n]) over the duration span of token n (0 for empty spans / pads).
+ * Replaces average_by_duration (generator/alignments.py:242-280). */
+int osb_average_by_duration(const float* ds, const float* xs, const int64_t* x_len, const int64_t* m_len, float* out, int32_t B,
+                            int32_t Tm, int32_t Tx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,9 +14,9 @@ LIB_PATH = _PKG_DIR / "libosb200.so"
 OSB_OK = 0
 
 # osb_epilogue
-EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU = range(6)
+EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD = range(10)
 # flags
-FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT = 1, 2, 4, 8, 16, 32, 64
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class GemmDesc(C.Structure):
@@ -49,6 +49,8 @@ class GemmDesc(C.Structure):
         ("dot_w", C.c_void_p),
         ("dot_b", C.c_void_p),
         ("out_dot", C.c_void_p),
+        ("aux_in_h16", C.c_void_p),
+        ("row_stat", C.c_void_p),
     ]
 
 
@@ -91,6 +93,17 @@ def load() -> C.CDLL:
         "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
         "osb_expand_gather": [P, P, P, P, I32, I32, I32, I32, P],
         "osb_pack_h16": [P, I64, I64, P, P, P, I64, I32, I64, I32, P],
+        "osb_resid_bwd_prep": [P, P, P, P, P, P, P, P, I64, I32, I32, P],
+        "osb_colsum_h16": [P, P, I64, I32, P],
+        "osb_ln_fold_bwd": [P, P, P, P, P, P, I32, I32, P],
+        "osb_dwconv_bwd": [P, P, P, P, P, P, P, P, I32, I32, I32, P],
+        "osb_layernorm_bwd": [P, P, P, P, P, P, I64, I32, F, P],
+        "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, P],
+        "osb_ln_param_grad": [P, P, P, P, P, I64, I32, F, P],
+        "osb_variance_embed_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_embed_text_bwd": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
+        "osb_mas": [P, P, P, P, P, I32, I32, I32, P],
+        "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

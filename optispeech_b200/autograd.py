@@ -1,0 +1,292 @@
+"""torch.autograd glue for the training path: each Function's forward AND backward run libosb200 kernels
+(tcgen05 dgrad / wgrad contractions plus the HBM-bound kernels of osb_backward.cu); autograd itself is only
+the tape.  Activations cross Function boundaries in fp32; inside a Function the tensor-core operands are fp16
+(the reference's own GPU default is `16-mixed`), and gradients carry the caller's static loss scale.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing helpers (fp32 master -> fp16 operands), forward and transposed (dgrad) forms
+# --------------------------------------------------------------------------------------------------
+def pack_nk(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """(N, K) fp32 -> (1, N, Kp) fp16."""
+    N, K = w.shape
+    Kp = k_pad or K
+    return ops.pack_h16(w.contiguous(), rows=N, cols=K, src_ld=K, dst_cols=Kp).view(1, N, Kp)
+
+
+def pack_kn(w: torch.Tensor) -> torch.Tensor:
+    """(N, K) fp32 -> transposed (1, K, N) fp16 (the dgrad operand)."""
+    N, K = w.shape
+    return ops.pack_h16(w.contiguous(), rows=K, cols=N, src_ld=1, src_cs=K).view(1, K, N)
+
+
+def pack_conv_fwd(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """Conv1d weight (N, Cin, k) -> (k, N, Cin_pad) fp16."""
+    N, Cin, k = w.shape
+    Kp = k_pad or Cin
+    w = w.contiguous()
+    out = torch.empty((k, N, Kp), device=w.device, dtype=torch.float16)
+    for tap in range(k):
+        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_cols=Kp, out=out[tap])
+    return out
+
+
+def pack_conv_bwd(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight (N, Cin, k) -> dgrad operand (k, Cin, N) fp16 with the taps reversed:
+    out[tap', c, n] = w[n, c, k-1-tap']."""
+    N, Cin, k = w.shape
+    w = w.contiguous()
+    out = torch.empty((k, Cin, N), device=w.device, dtype=torch.float16)
+    for tp in range(k):
+        ops.pack_h16(w.view(-1)[k - 1 - tp:], rows=Cin, cols=N, src_ld=k, src_cs=Cin * k, out=out[tp])
+    return out
+
+
+def _conv_wgrad(g_h16: torch.Tensor, a_h16: torch.Tensor, N: int, Cin: int, k: int, pad: int) -> torch.Tensor:
+    """-> Conv1d weight gradient in the parameter's (N, Cin, k) layout."""
+    dw = torch.zeros((k, N, Cin), device=g_h16.device, dtype=torch.float32)
+    ops.gemm_wgrad(g_h16, a_h16, dw, taps=k, pad=pad, K=Cin)
+    return dw.permute(1, 2, 0).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# text embedding
+# --------------------------------------------------------------------------------------------------
+class EmbedTextFn(Function):
+    @staticmethod
+    def forward(ctx, ids, table, scale, inv_freq, padding_idx):
+        ctx.save_for_backward(ids, inv_freq)
+        ctx.n_vocab, ctx.padding_idx = table.shape[0], padding_idx
+        return ops.embed_text(ids, table, inv_freq, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, inv_freq = ctx.saved_tensors
+        dtable, dscale = ops.embed_text_bwd(dout.contiguous(), ids, inv_freq, ctx.n_vocab, ctx.padding_idx)
+        return None, dtable, dscale, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# LayerNorm with affine (final_layer_norm of a backbone)
+# --------------------------------------------------------------------------------------------------
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        out, _ = ops.layernorm(x, w, b, eps, f32=True, h16=False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(dout.contiguous(), x, w, ctx.eps)
+        return dx, dw, db, None
+
+
+# --------------------------------------------------------------------------------------------------
+# ConvNeXt block
+# --------------------------------------------------------------------------------------------------
+class ConvNeXtBlockFn(Function):
+    """out = (x + gamma * pw2(gelu(pw1(LN(dwconv7(x))))) * row_scale[b]) * keep      (channels-last)"""
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, pad_mask, row_scale, eps):
+        B, T, C = x.shape
+        w1f = w1 * ln_w                      # fold the LN affine into pwconv1 (packing-time glue on weights)
+        b1f = torch.addmv(b1, w1, ln_b)
+        w1f_h, w2_h = pack_nk(w1f), pack_nk(w2)
+        xhat, rstd = ops.dwconv_ln(x, dw_w.view(C, 7), dw_b, eps, want_rstd=True)
+        h, pre, _ = ops.gemm(xhat, w1f_h, epi=ops.EPI_GELU, flags=ops.FLAG_SAVE_PRE, bias=b1f)
+        flags = ops.FLAG_SAVE_PRE | (ops.FLAG_KEEPMASK if pad_mask is not None else 0)
+        out, z, _ = ops.gemm(h, w2_h, epi=ops.EPI_RESID, flags=flags, bias=b2, resid=x, gamma=gamma, row_scale=row_scale,
+                             pad_mask=pad_mask)
+        ctx.save_for_backward(x, dw_w, ln_w, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, dw_w, ln_w, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale = ctx.saved_tensors
+        B, T, C = x.shape
+        I = w1.shape[0]
+        dout = dout.contiguous()
+        dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
+        # pwconv2: dgrad (with the GELU derivative fused) and wgrad
+        dpre, _, _ = ops.gemm(dyg, pack_kn(w2), epi=ops.EPI_GELU_BWD, aux_in=pre)
+        dw2 = torch.zeros((1, C, I), device=x.device, dtype=torch.float32)
+        ops.gemm_wgrad(dyg, h, dw2)
+        db1 = ops.colsum_h16(dpre)
+        # pwconv1: dgrad (LayerNorm backward fused: the CTA owns whole rows) and wgrad
+        dd, _, _ = ops.gemm(dpre, pack_kn(w1f), epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd)
+        dw1f = torch.zeros((1, I, C), device=x.device, dtype=torch.float32)
+        ops.gemm_wgrad(dpre, xhat, dw1f)
+        dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, db1)
+        dx, ddw, ddb = ops.dwconv_bwd(dd, dout, x, dw_w.view(C, 7), pad_mask)
+        return dx, ddw.view(C, 1, 7), ddb, dln_w, dln_b, dw1, db1, dw2.view(C, I), db2, dgamma, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# VariancePredictor: [Conv1d(k) + ReLU + LayerNorm] * L + Linear(->1) + masked_fill
+# --------------------------------------------------------------------------------------------------
+class VariancePredictorFn(Function):
+    @staticmethod
+    def forward(ctx, x, pad_mask, kernel_size, eps, lin_w, lin_b, *layer_params):
+        """layer_params = (conv_w, conv_b, ln_w, ln_b) per layer.  x fp32 (B,T,C) -> (B,T) fp32."""
+        L = len(layer_params) // 4
+        pad = (kernel_size - 1) // 2
+        a = ops.to_h16(x.contiguous())
+        acts, pres = [a], []
+        out = None
+        for l in range(L):
+            cw, cb, lw, lb = layer_params[4 * l: 4 * l + 4]
+            wp = pack_conv_fwd(cw)
+            if l < L - 1:
+                y, r, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, pad=pad, bias=cb, ln_w=lw, ln_b=lb, ln_eps=eps)
+                acts.append(y)
+            else:
+                _, r, out = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE | ops.FLAG_DOT, pad=pad, bias=cb, ln_w=lw,
+                                     ln_b=lb, ln_eps=eps, dot_w=lin_w.view(-1), dot_b=lin_b, pad_mask=pad_mask)
+            pres.append(r)
+        ctx.save_for_backward(pad_mask, lin_w, *layer_params, *acts, *pres)
+        ctx.L, ctx.k, ctx.eps = L, kernel_size, eps
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L, k, eps = ctx.L, ctx.k, ctx.eps
+        saved = ctx.saved_tensors
+        pad_mask, lin_w = saved[0], saved[1]
+        layer_params = saved[2: 2 + 4 * L]
+        acts = saved[2 + 4 * L: 2 + 5 * L]
+        pres = saved[2 + 5 * L: 2 + 6 * L]
+        pad = (k - 1) // 2
+        grads: List[Optional[torch.Tensor]] = [None] * (4 * L)
+        cw, cb, lw, lb = layer_params[4 * (L - 1): 4 * L]
+        g, dlin_w, dlin_b, dln_w, dln_b = ops.predictor_tail_bwd(d_out.contiguous(), pad_mask, pres[L - 1], lw, lb, lin_w.view(-1), eps)
+        grads[4 * (L - 1) + 2], grads[4 * (L - 1) + 3] = dln_w, dln_b
+        dx = None
+        for l in range(L - 1, -1, -1):
+            cw = layer_params[4 * l]
+            N, Cin, _ = cw.shape
+            grads[4 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
+            grads[4 * l + 1] = ops.colsum_h16(g)
+            if l > 0:
+                lw_prev = layer_params[4 * (l - 1) + 2]
+                g_prev, gy, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, pad=k - 1 - pad,
+                                         aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps)
+                grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3] = ops.ln_param_grad(gy, pres[l - 1], lw_prev, eps)
+                g = g_prev
+            elif ctx.x_needs_grad:
+                dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
+        return (dx, None, None, None, dlin_w.view(1, -1), dlin_b, *grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# stack of Conv1d layers with ReLU between them (AlignmentModule text / feature encoders)
+# --------------------------------------------------------------------------------------------------
+class ConvStackFn(Function):
+    @staticmethod
+    def forward(ctx, x, k_pad, *params):
+        """params = (conv_w (N,Cin,k), conv_b) per layer; ReLU after every layer but the last.
+        x fp32 (B,T,Cin) -> fp32 (B,T,N_last).  k_pad: channel padding of the first operand (e.g. 100 mel bins -> 128)."""
+        L = len(params) // 2
+        a = ops.to_h16(x.contiguous(), pad_to=k_pad or None)
+        acts = [a]
+        out = None
+        for l in range(L):
+            cw, cb = params[2 * l], params[2 * l + 1]
+            k = cw.shape[2]
+            wp = pack_conv_fwd(cw, k_pad=acts[-1].shape[-1])
+            if l < L - 1:
+                y, _, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU, pad=(k - 1) // 2, bias=cb)
+                acts.append(y)
+            else:
+                out, _, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_BIAS, pad=(k - 1) // 2, bias=cb)
+        ctx.save_for_backward(*params, *acts)
+        ctx.L = L
+        ctx.x_needs_grad = x.requires_grad
+        ctx.cin0 = x.shape[-1]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = ctx.L
+        saved = ctx.saved_tensors
+        params, acts = saved[: 2 * L], saved[2 * L:]
+        grads: List[Optional[torch.Tensor]] = [None] * (2 * L)
+        g = ops.to_h16(dout.contiguous())
+        dx = None
+        for l in range(L - 1, -1, -1):
+            cw = params[2 * l]
+            N, Cin, k = cw.shape
+            pad = (k - 1) // 2
+            grads[2 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
+            grads[2 * l + 1] = ops.colsum_h16(g)
+            if l > 0:
+                g, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l])
+            elif ctx.x_needs_grad:
+                dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
+        return (dx, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# variance embedding: out = (x + bias + Conv1d(1->C,k)(val)) * keep
+# --------------------------------------------------------------------------------------------------
+class VarianceEmbedFn(Function):
+    @staticmethod
+    def forward(ctx, x, val, w, b, pad_mask):
+        C = x.shape[-1]
+        ctx.save_for_backward(val, pad_mask)
+        ctx.k = w.shape[-1]
+        ctx.x_needs_grad = x.requires_grad
+        out, _ = ops.variance_embed(x.contiguous(), val.contiguous(), w.view(C, -1), b, pad_mask, f32=True, h16=False)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        val, pad_mask = ctx.saved_tensors
+        dx, dw, db = ops.variance_embed_bwd(dout.contiguous(), val, pad_mask, ctx.k, want_dx=ctx.x_needs_grad)
+        return dx, None, dw.view(dw.shape[0], 1, ctx.k), db, None
+
+
+# --------------------------------------------------------------------------------------------------
+# WaveNeXt head: clip(Linear2(Linear1(x))) with the two Linears folded into one GEMM
+# --------------------------------------------------------------------------------------------------
+class WaveNeXtHeadFn(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2):
+        """x fp32 (B,T,dim); linear_1 (l_fft, dim) + bias, linear_2 (hop, l_fft) -> audio (B, T*hop) in [-1, 1]."""
+        wc = w2 @ w1                      # (hop, dim): no non-linearity between the two Linears (wavenext/__init__.py:43-45)
+        bc = w2 @ b1
+        a = ops.to_h16(x.contiguous())
+        out, _, _ = ops.gemm(a, pack_nk(wc), epi=ops.EPI_BIAS, flags=ops.FLAG_CLIP, bias=bc.contiguous())
+        ctx.save_for_backward(a, out, w1, b1, w2, wc)
+        return out.view(out.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, out, w1, b1, w2, wc = ctx.saved_tensors
+        B, T, hop = out.shape
+        # clip passes gradient only strictly inside (-1, 1)  (torch.clip backward)
+        g32 = (dout.reshape(B, T, hop) * ((out > -1.0) & (out < 1.0))).contiguous()
+        g = ops.to_h16(g32)
+        dx, _, _ = ops.gemm(g, pack_kn(wc), epi=ops.EPI_BIAS)
+        dwc = torch.zeros((1, hop, a.shape[-1]), device=a.device, dtype=torch.float32)
+        ops.gemm_wgrad(g, a, dwc)
+        dwc = dwc[0]
+        dbc = ops.colsum_h16(g)
+        # un-fold: wc = w2 @ w1, bc = w2 @ b1   (small fp32 matrix products on the weights)
+        dw2 = dwc @ w1.t() + torch.outer(dbc, b1)
+        dw1 = w2.t() @ dwc
+        db1 = w2.t() @ dbc
+        return dx, dw1, db1, dw2

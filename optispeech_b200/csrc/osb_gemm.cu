@@ -40,6 +40,8 @@ struct GemmKParams {
   const float* dot_w;
   const float* dot_b;
   float* out_dot;
+  const void* aux_in;
+  const float* row_stat;
 };
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
@@ -69,6 +71,20 @@ __device__ __forceinline__ void ld_chunk(uint32_t taddr, int c0, float (&v)[32])
   tmem_ld_wait();
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void ld_h16x32(const __half* src, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      v[i + 2 * j] = f.x;
+      v[i + 2 * j + 1] = f.y;
+    }
+  }
 }
 
 __device__ __forceinline__ void st_f32x32(float* dst, const float (&v)[32]) {
@@ -129,7 +145,89 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
   const bool padded = (p.pad_mask != nullptr) && valid && (p.pad_mask[row] != 0);
   float v[32];
 
-  if constexpr (EPI == OSB_EPI_BIAS || EPI == OSB_EPI_GELU || EPI == OSB_EPI_RELU || EPI == OSB_EPI_RESID) {
+  if constexpr (EPI == OSB_EPI_GELU_BWD || EPI == OSB_EPI_RELU_BWD) {
+    float pre[32];
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      if (valid) {
+        const int n = n0 + c0;
+        ld_h16x32(static_cast<const __half*>(p.aux_in) + row * p.ldo + n, pre);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if constexpr (EPI == OSB_EPI_GELU_BWD) v[i] *= gelu_erf_grad(pre[i]);
+          else v[i] = pre[i] > 0.f ? v[i] : 0.f;
+        }
+        st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + n, v);
+      }
+    }
+  } else if constexpr (EPI == OSB_EPI_LN_BWD) {
+    // acc = d(xhat); out = (acc - mean(acc) - xhat * mean(acc * xhat)) * rstd       (rows are independent)
+    float xh[32];
+    const float inv_n = 1.f / static_cast<float>(BN);
+    const __half* xrow = static_cast<const __half*>(p.aux_in) + (valid ? row : 0) * p.ldo;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      ld_h16x32(xrow + c0, xh);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s1 += v[i];
+        s2 = fmaf(v[i], xh[i], s2);
+      }
+    }
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+    const float rstd = valid ? p.row_stat[row] : 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      ld_h16x32(xrow + c0, xh);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (v[i] - m1 - xh[i] * m2) * rstd;
+      if (valid) st_f32x32(static_cast<float*>(p.out) + row * p.ldo + c0, v);
+    }
+  } else if constexpr (EPI == OSB_EPI_RELU_LN_BWD) {
+    // recompute the forward LN statistics of r = relu(conv) (fp16-saved), then LN backward and the ReLU gate
+    float r[32];
+    const float inv_n = 1.f / static_cast<float>(BN);
+    const __half* rrow = static_cast<const __half*>(p.aux_in) + (valid ? row : 0) * p.ldo;
+    float s = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_h16x32(rrow + c0, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s += r[i];
+    }
+    const float mean = s * inv_n;
+    float q = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_h16x32(rrow + c0, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q = fmaf(r[i] - mean, r[i] - mean, q);
+    }
+    const float rstd = rsqrtf(q * inv_n + p.ln_eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      ld_h16x32(rrow + c0, r);
+      if (valid && (p.flags & OSB_FLAG_OUT_H16)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float g = v[i] * __ldg(p.ln_w + c0 + i);
+        s1 += g;
+        s2 = fmaf(g, (r[i] - mean) * rstd, s2);
+      }
+    }
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      ld_h16x32(rrow + c0, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float g = v[i] * __ldg(p.ln_w + c0 + i);
+        const float d = (g - m1 - (r[i] - mean) * rstd * m2) * rstd;
+        v[i] = r[i] > 0.f ? d : 0.f;
+      }
+      if (valid) st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + c0, v);
+    }
+  } else if constexpr (EPI == OSB_EPI_BIAS || EPI == OSB_EPI_GELU || EPI == OSB_EPI_RELU || EPI == OSB_EPI_RESID) {
     const float keep = ((p.flags & OSB_FLAG_KEEPMASK) && padded) ? 0.f : 1.f;
     const float rs = (EPI == OSB_EPI_RESID && p.row_scale != nullptr) ? p.row_scale[b] : 1.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -143,6 +241,10 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         if (p.flags & OSB_FLAG_CLIP) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], -1.f), 1.f);
+        }
+        if (p.flags & OSB_FLAG_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
@@ -160,6 +262,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         if (valid) store_h(p, p.out, row, n, v);
       } else {  // RESID
+        if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
         if (valid) {
           const float* rp = p.resid + row * p.ldo + n;
 #pragma unroll
@@ -479,6 +582,7 @@ int dispatch_bn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const Ge
 template <int EPI>
 int dispatch_bn_full(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmKParams& p, cudaStream_t stream) {
   switch (bn) {
+    case 128: return launch_nt<128, EPI>(tmA, tmW, p, stream);
     case 256: return launch_nt<256, EPI>(tmA, tmW, p, stream);
     case 384: return launch_nt<384, EPI>(tmA, tmW, p, stream);
     default: return OSB_ERR_SHAPE;
@@ -550,7 +654,8 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   OSB_REQUIRE(d->lda >= d->K && d->ldw >= d->K && d->ldo >= d->N, OSB_ERR_SHAPE);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
-  const bool full_row = (d->epi == OSB_EPI_RELU_LN || d->epi == OSB_EPI_BIAS_LN);
+  const bool full_row = (d->epi == OSB_EPI_RELU_LN || d->epi == OSB_EPI_BIAS_LN || d->epi == OSB_EPI_LN_BWD ||
+                         d->epi == OSB_EPI_RELU_LN_BWD);
   const int bn = full_row ? d->N : pick_bn(d->N);
   OSB_REQUIRE(bn > 0, OSB_ERR_SHAPE);
   const int ninst = bn <= 256 ? bn : bn / 2;
@@ -573,6 +678,7 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.bias = d->bias; p.resid = d->resid; p.gamma = d->gamma; p.row_scale = d->row_scale;
   p.pad_mask = d->pad_mask; p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps;
   p.dot_w = d->dot_w; p.dot_b = d->dot_b; p.out_dot = d->out_dot;
+  p.aux_in = d->aux_in_h16; p.row_stat = d->row_stat;
 
   if ((d->flags & (OSB_FLAG_OUT_H16 | OSB_FLAG_SAVE_PRE)) && d->aux_h16 == nullptr) return OSB_ERR_ARG;
   if ((d->flags & OSB_FLAG_KEEPMASK) && d->pad_mask == nullptr) return OSB_ERR_ARG;
@@ -597,6 +703,18 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
     case OSB_EPI_BIAS_LN:
       OSB_REQUIRE(d->out != nullptr && d->ln_w != nullptr && d->ln_b != nullptr, OSB_ERR_ARG);
       return dispatch_bn_full<OSB_EPI_BIAS_LN>(bn, tmA, tmW, p, stream);
+    case OSB_EPI_GELU_BWD:
+      OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr, OSB_ERR_ARG);
+      return dispatch_bn<OSB_EPI_GELU_BWD>(bn, tmA, tmW, p, stream);
+    case OSB_EPI_RELU_BWD:
+      OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr, OSB_ERR_ARG);
+      return dispatch_bn<OSB_EPI_RELU_BWD>(bn, tmA, tmW, p, stream);
+    case OSB_EPI_LN_BWD:
+      OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr && d->row_stat != nullptr, OSB_ERR_ARG);
+      return dispatch_bn_full<OSB_EPI_LN_BWD>(bn, tmA, tmW, p, stream);
+    case OSB_EPI_RELU_LN_BWD:
+      OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr && d->ln_w != nullptr, OSB_ERR_ARG);
+      return dispatch_bn_full<OSB_EPI_RELU_LN_BWD>(bn, tmA, tmW, p, stream);
     default:
       return OSB_ERR_ARG;
   }

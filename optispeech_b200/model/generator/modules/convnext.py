@@ -76,6 +76,15 @@ class ConvNeXtBlock(nn.Module):
 
         return self._packed.get("fwd", srcs, build)
 
+    def forward_train(self, x: torch.Tensor, pad_mask_u8: Optional[torch.Tensor]) -> torch.Tensor:
+        """Autograd path (fp16 operands, activations saved for the hand-written backward)."""
+        from ....autograd import ConvNeXtBlockFn
+
+        scale = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
+        gamma = self.gamma if self.gamma is not None else torch.ones(self.dim, device=x.device)
+        return ConvNeXtBlockFn.apply(x, self.dwconv.weight, self.dwconv.bias, self.norm.weight, self.norm.bias, self.pwconv1.weight,
+                                     self.pwconv1.bias, self.pwconv2.weight, self.pwconv2.bias, gamma, pad_mask_u8, scale, self.norm.eps)
+
     def forward_cl(self, x: torch.Tensor, pad_mask_u8: Optional[torch.Tensor], split: bool = False) -> torch.Tensor:
         """Channels-last forward: x (B,T,C) fp32 -> (B,T,C) fp32, pad mask (B,T) uint8 applied to the output
         (the reference's ConvNeXtBackbone multiplies by the mask right after each block, convnext.py:98-101)."""
@@ -127,8 +136,16 @@ class ConvNeXtBackbone(nn.Module):
                 split: Optional[bool] = None):
         """x (B,T,C) fp32, padding_mask (B,T) bool True = pad -> (B,T,C) fp32 [, fp16 operand copy]."""
         x = x.contiguous()
-        split = precision.use_split(self.training) if split is None else split
         mask_u8 = None if padding_mask is None else padding_mask.to(torch.uint8).contiguous()
+        if torch.is_grad_enabled():
+            from ....autograd import LayerNormFn
+
+            for blk in self.convnext:
+                x = blk.forward_train(x, mask_u8)
+            ln = self.final_layer_norm
+            out = LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps)
+            return (out, None) if want_h16 else out
+        split = precision.use_split(self.training) if split is None else split
         for blk in self.convnext:
             x = blk.forward_cl(x, mask_u8, split)
         ln = self.final_layer_norm

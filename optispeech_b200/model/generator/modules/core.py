@@ -34,8 +34,14 @@ class TextEmbedding(nn.Module):
 
     def forward(self, src_tokens):
         """-> (x, embed) like the reference; `embed` (token part only) is not materialised on this path."""
-        x = ops.embed_text(src_tokens.contiguous(), self.embed_tokens.weight, self.embed_positions.inv_freq,
-                           self.embed_positions.scale)
+        if torch.is_grad_enabled():
+            from ....autograd import EmbedTextFn
+
+            x = EmbedTextFn.apply(src_tokens.contiguous(), self.embed_tokens.weight, self.embed_positions.scale,
+                                  self.embed_positions.inv_freq, self.embed_tokens.padding_idx)
+        else:
+            x = ops.embed_text(src_tokens.contiguous(), self.embed_tokens.weight, self.embed_positions.inv_freq,
+                               self.embed_positions.scale)
         x = self.emb_dropout(x)
         return x, None
 
@@ -88,8 +94,17 @@ class VariancePredictor(nn.Module):
 
     def forward(self, x: torch.Tensor, padding_mask) -> torch.Tensor:
         """Reference signature: x (B,T,dim) fp32, padding_mask (B,T) bool -> (B,T)."""
+        mask_u8 = padding_mask.to(torch.uint8).contiguous()
+        if torch.is_grad_enabled():
+            from ....autograd import VariancePredictorFn
+
+            params = []
+            for layer in self.conv:
+                params += [layer[0].weight, layer[0].bias, layer[2].weight, layer[2].bias]
+            return VariancePredictorFn.apply(x, mask_u8, self.kernel_size, self.conv[0][2].eps, self.linear.weight, self.linear.bias,
+                                             *params)
         split = precision.use_split(self.training)
-        return self.forward_h16(ops.to_h16(x.contiguous(), split=split), padding_mask.to(torch.uint8).contiguous(), split)
+        return self.forward_h16(ops.to_h16(x.contiguous(), split=split), mask_u8, split)
 
 
 class DurationPredictor(VariancePredictor):
@@ -127,6 +142,13 @@ class PitchPredictor(nn.Module):
     def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor):
         """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics."""
         mask_u8 = padding_mask.to(torch.uint8).contiguous()
+        if torch.is_grad_enabled():
+            from ....autograd import VarianceEmbedFn
+
+            preds = self.predictor(x, padding_mask)
+            conv = self.embed[0]
+            out = VarianceEmbedFn.apply(x, target.contiguous(), conv.weight, conv.bias, mask_u8)
+            return out, preds
         split = precision.use_split(self.training)
         preds = self.predictor.forward_h16(ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         out, _ = self._embed_add(x, target, mask_u8, False)

@@ -1,16 +1,27 @@
 """Training-only machinery of the generator (alignment learning, losses, training forward).
 
-Mirrors optispeech/model/generator/alignments.py:14-123,177-280 and generator/__init__.py:72-192.
+Mirrors optispeech/model/generator/alignments.py:14-123,177-280, generator/loss.py and
+generator/__init__.py:72-192 (reference @ 3bdde20).
 """
 from __future__ import annotations
 
+import math
+
+import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
+
+from ... import ops
+from ...autograd import ConvStackFn
+from ...utils import sequence_mask
+from ...utils.segments import get_segments
 
 
 class AlignmentModule(nn.Module):
-    """Alignment learning framework (reference alignments.py:14-123): parameter container with the
-    reference's layer names; compute lives in `generator_training_forward`."""
+    """Alignment learning framework (reference alignments.py:14-123), same layer names.  The five Conv1d layers
+    run as tcgen05 implicit GEMMs (ConvStackFn); the beta-binomial prior is evaluated from a log-factorial table
+    (all its arguments are integers), cached per (T, N) like the reference."""
 
     def __init__(self, adim, odim, cache_prior=True):
         super().__init__()
@@ -22,6 +33,155 @@ class AlignmentModule(nn.Module):
         self.f_conv2 = nn.Conv1d(adim, adim, kernel_size=3, padding=1)
         self.f_conv3 = nn.Conv1d(adim, adim, kernel_size=1, padding=0)
 
+    def forward(self, text, feats, text_lengths, feats_lengths, x_masks=None):
+        """text (B,Tx,adim), feats (B,Tm,odim) -> log_p_attn (B,Tm,Tx) with the beta-binomial prior added."""
+        te = ConvStackFn.apply(text, 0, self.t_conv1.weight, self.t_conv1.bias, self.t_conv2.weight, self.t_conv2.bias)
+        odim = feats.shape[-1]
+        fe = ConvStackFn.apply(feats, ((odim + 63) // 64) * 64, self.f_conv1.weight, self.f_conv1.bias, self.f_conv2.weight,
+                               self.f_conv2.bias, self.f_conv3.weight, self.f_conv3.bias)
+        score = -torch.cdist(fe, te, p=2, compute_mode="donot_use_mm_for_euclid_dist")
+        if x_masks is not None:
+            score = score.masked_fill(x_masks.unsqueeze(-2), -np.inf)
+        log_p_attn = F.log_softmax(score, dim=-1)
+        prior = self._generate_prior(text_lengths, feats_lengths, text.shape[1], feats.shape[1]).to(log_p_attn)
+        return log_p_attn + prior
 
-def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids):
-    raise NotImplementedError("training forward is being brought up; see DESIGN.md")
+    @staticmethod
+    def _log_prior(T: int, N: int) -> np.ndarray:
+        """(T, N) float64 log BetaBinomial(k; N, t, T-t+1), t = 1..T, k = 0..N-1 (reference :109-114, scipy definition);
+        every gamma-function argument is an integer, so a log-factorial table is exact."""
+        lf = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, T + N + 2, dtype=np.float64)))])  # lf[m] = log(m!)
+        t = np.arange(1, T + 1)[:, None]
+        k = np.arange(N)[None, :]
+        return (lf[N] - lf[k] - lf[N - k] + lf[k + t - 1] + lf[N - k + T - t] - lf[N + T] - lf[t - 1] - lf[T - t] + lf[T])
+
+    def _generate_prior(self, text_lengths, feats_lengths, T_text=None, T_feats=None, w=1) -> torch.Tensor:
+        tl, fl = text_lengths.tolist(), feats_lengths.tolist()
+        T_text = T_text or max(tl)
+        T_feats = T_feats or max(fl)
+        key_all = (tuple(tl), tuple(fl), T_text, T_feats)
+        hit = self._cache.get("batch")
+        if self.cache_prior and hit is not None and hit[0] == key_all:
+            return hit[1]
+        prior = torch.full((len(tl), T_feats, T_text), fill_value=-np.inf)
+        for b, (N, T) in enumerate(zip(tl, fl)):
+            key = f"{T},{N}"
+            prob = self._cache.get(key) if self.cache_prior else None
+            if prob is None:
+                prob = torch.from_numpy(self._log_prior(T, N)).float()
+                if self.cache_prior:
+                    self._cache[key] = prob
+            prior[b, :T, :N] = prob
+        prior = prior.to(self.t_conv1.weight.device)
+        if self.cache_prior:
+            self._cache["batch"] = (key_all, prior)
+        return prior
+
+
+def viterbi_decode(log_p_attn, text_lengths, feats_lengths):
+    """-> (durations (B,Tx) fp32, bin_loss).  Reference alignments.py:210-239; the search itself runs on the device
+    (osb_mas, bit-exact with the reference's float64 numba code) instead of one host round trip per sample."""
+    B, Tm, Tx = log_p_attn.shape
+    path, ds = ops.mas(log_p_attn.detach().contiguous(), text_lengths.contiguous(), feats_lengths.contiguous())
+    valid = path >= 0
+    picked = torch.gather(log_p_attn, 2, path.clamp(min=0).long().unsqueeze(-1)).squeeze(-1)
+    per_sample = (picked * valid).sum(dim=1) / feats_lengths.to(picked.dtype)
+    bin_loss = -(per_sample.sum()) / B
+    return ds, bin_loss
+
+
+def average_by_duration(ds, xs, text_lengths, feats_lengths):
+    """Reference alignments.py:262-280, on the device (osb_average_by_duration)."""
+    xs = xs.reshape(xs.shape[0], -1) if xs.dim() == 3 else xs
+    return ops.average_by_duration(ds.detach().float().contiguous(), xs.detach().float().contiguous(), text_lengths.contiguous(),
+                                   feats_lengths.contiguous())
+
+
+def forward_sum_loss(log_p_attn, ilens, olens, blank_logprob: float = -1.0):
+    """ForwardSumLoss (reference loss.py:150-194): blank column log(e^-1), per-sample log_softmax over its own
+    (N_b + 1) columns, CTC with targets 1..N_b, 'mean' reduction (divide by N_b), zero_infinity, mean over batch."""
+    B, Tm, Tx = log_p_attn.shape
+    padded = F.pad(log_p_attn, (1, 0), value=blank_logprob)                       # (B, Tm, Tx+1)
+    col_ok = torch.arange(Tx + 1, device=padded.device)[None, :] <= ilens[:, None]  # blank + the sample's own tokens
+    padded = padded.masked_fill(~col_ok[:, None, :], -float("inf"))
+    lp = F.log_softmax(padded, dim=-1).transpose(0, 1)                            # (Tm, B, Tx+1)
+    targets = torch.arange(1, Tx + 1, device=padded.device)[None, :].expand(B, -1)
+    per_sample = F.ctc_loss(lp, targets, olens, ilens, blank=0, reduction="none", zero_infinity=True)
+    return (per_sample / ilens.to(per_sample.dtype)).sum() / B
+
+
+def fastspeech2_losses(d_outs, p_outs, e_outs, ds, ps, es, ilens):
+    """FastSpeech2Loss exactly as the reference evaluates it (loss.py:83-140).  Its masks carry a stray singleton
+    axis, so masked_select broadcasts: the duration term takes element (b,i) len_b times for EVERY i < Tx (padded
+    positions included, target log(0 + 1e-8)); the pitch / energy terms take element (b,i) once per sample whose
+    length exceeds i.  'mean' reduction over those multisets."""
+    B, Tx = d_outs.shape
+    lens = ilens.to(d_outs.dtype)
+    d_err = (d_outs - torch.log(ds.float() + 1e-8)) ** 2
+    d_loss = (d_err.sum(dim=1) * lens).sum() / (lens.sum() * Tx)
+    w = (torch.arange(Tx, device=d_outs.device)[None, :] < ilens[:, None]).to(d_outs.dtype).sum(dim=0)
+    denom = w.sum() * B
+    p_loss = (F.smooth_l1_loss(p_outs, ps, reduction="none") * w[None, :]).sum() / denom
+    e_loss = (F.smooth_l1_loss(e_outs, es, reduction="none") * w[None, :]).sum() / denom
+    return d_loss, p_loss, e_loss
+
+
+def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
+    """Reference generator/__init__.py:72-192.  `seg_rand` (B,) in [0,1) replaces the CPU `torch.rand` draw of
+    get_random_segments (utils/segments.py:32) when given (parity tests); otherwise it is drawn the same way."""
+    dev = x.device
+    f0_real = pitches
+    x_mask = sequence_mask(x_lengths, x.shape[1])
+    mel_mask = sequence_mask(mel_lengths, mel.shape[-1])
+    in_pad, tgt_pad = ~x_mask, ~mel_mask
+
+    h, _ = gen.text_embedding(x)
+    h = gen.encoder(h, in_pad)
+    h = gen._speaker_language(h, sids, lids)
+
+    log_p_attn = gen.alignment_module(text=h, feats=mel.transpose(1, 2), text_lengths=x_lengths, feats_lengths=mel_lengths,
+                                      x_masks=in_pad)
+    durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
+    duration_hat = gen.duration_predictor(h.detach(), in_pad)
+
+    p_avg = average_by_duration(durations, pitches, x_lengths, mel_lengths)
+    e_avg = average_by_duration(durations, energies, x_lengths, mel_lengths)
+
+    h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg)
+    h, energy_hat = gen.energy_predictor(h, in_pad, e_avg)
+
+    # Upsampler, decoder and vocoder input carry no gradient in the reference (the vocoder is fed segment.detach(),
+    # generator/__init__.py:161, and nothing else consumes the decoder output), so they run on the inference kernels.
+    with torch.no_grad():
+        y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
+                                  y_lengths=mel_lengths)
+        y = gen.decoder(y, tgt_pad, split=False)
+        segment_size = min(gen.segment_size, y.shape[1])
+        num_frames = (mel_lengths - 4).to(y.dtype)
+        max_start = (num_frames - segment_size).clamp(min=0)
+        if seg_rand is None:
+            seg_rand = torch.rand([x.shape[0]])
+        start_idx = (seg_rand.to(dev) * max_start).to(torch.long)
+        segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
+        _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt
+
+    wav_hat = gen.vocoder.forward_train(segment)
+
+    d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
+    fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
+    align_loss = fs_loss + bin_loss
+    lc = gen.loss_coeffs
+    loss = align_loss * lc.lambda_align + d_loss * lc.lambda_duration + p_loss * lc.lambda_pitch + e_loss * lc.lambda_energy
+    return {
+        "wav_hat": wav_hat,
+        "start_idx": start_idx,
+        "segment_size": segment_size,
+        "loss": loss,
+        "align_loss": align_loss.detach(),
+        "duration_loss": d_loss.detach(),
+        "pitch_loss": p_loss.detach(),
+        "energy_loss": e_loss.detach(),
+        "_aux": {"log_p_attn": log_p_attn, "durations": durations, "pitch_avg": p_avg, "energy_avg": e_avg,
+                 "duration_hat": duration_hat, "pitch_hat": pitch_hat, "energy_hat": energy_hat, "decoder_out": y,
+                 "forwardsum_loss": fs_loss.detach(), "bin_loss": bin_loss.detach()},
+    }

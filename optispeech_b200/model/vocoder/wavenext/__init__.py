@@ -84,7 +84,20 @@ class WaveNeXt(nn.Module):
         _, h16 = self.backbone(h, padding_mask, want_h16=True, split=split)
         return self.head.forward_h16(h16, split)
 
+    def forward_train(self, x: torch.Tensor, padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Autograd path, channels-last fp32 input (B,T,input_channels) -> (B, T*hop)."""
+        if not torch.is_grad_enabled():
+            return self.forward_cl(ops.to_h16(x.contiguous()), padding_mask, False)
+        from ....autograd import ConvStackFn, LayerNormFn, WaveNeXtHeadFn
+
+        h = ConvStackFn.apply(x, 0, self.embed.weight, self.embed.bias)
+        h = LayerNormFn.apply(h, self.norm.weight, self.norm.bias, self.norm.eps)
+        h = self.backbone(h, padding_mask)
+        return WaveNeXtHeadFn.apply(h, self.head.linear_1.weight, self.head.linear_1.bias, self.head.linear_2.weight)
+
     def forward(self, x, f0, padding_mask=None):
         """Reference signature: x (B, C, T)."""
+        if torch.is_grad_enabled():
+            return self.forward_train(x.transpose(1, 2).contiguous(), padding_mask)
         split = precision.use_split(self.training)
         return self.forward_cl(ops.to_h16(x.transpose(1, 2).contiguous(), split=split), padding_mask, split)

@@ -12,8 +12,9 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_RELU, EPI_RELU_LN, EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK,
-                   FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_SPLIT_IN, FLAG_SPLIT_OUT)
+from ._lib import (EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU, EPI_RELU_BWD, EPI_RELU_LN, EPI_RELU_LN_BWD,
+                   EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_RELU, FLAG_SAVE_PRE, FLAG_SPLIT_IN,
+                   FLAG_SPLIT_OUT)
 
 __all__ = [
     "gemm", "embed_text", "dwconv_ln", "layernorm", "variance_embed", "durations", "centres", "gaussian_upsample",
@@ -43,7 +44,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -60,7 +61,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
             w = w[0]
         taps, N, ldw = w.shape
         K = K if K is not None else min(lda, ldw)
-    f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN)
+    f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN, EPI_LN_BWD)
     hN = 2 * N if (flags & FLAG_SPLIT_OUT) else N
     if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)):
         out = torch.empty((B, T, N if f32_out else hN), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
@@ -79,6 +80,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.pad_mask = _ptr(pad_mask)
     d.ln_w, d.ln_b, d.ln_eps = _ptr(ln_w), _ptr(ln_b), ln_eps
     d.dot_w, d.dot_b, d.out_dot = _ptr(dot_w), _ptr(dot_b), _ptr(out_dot)
+    d.aux_in_h16, d.row_stat = _ptr(aux_in), _ptr(row_stat)
     _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
     return out, aux, out_dot
 
@@ -193,3 +195,110 @@ def to_h16(x: torch.Tensor, pad_to: Optional[int] = None, split: bool = False) -
     out = torch.empty((rows, 2 * Cp), device=x.device, dtype=torch.float16)
     pack_h16(x, rows=rows, cols=Cc, src_ld=Cc, dst_cols=Cp, dst_rs=2 * Cp, out=out, out_lo=out.data_ptr() + 2 * Cp)
     return out.view(*x.shape[:-1], 2 * Cp)
+
+
+# ------------------------------------------------------------------------------------------------
+# backward kernels
+# ------------------------------------------------------------------------------------------------
+def _zeros(shape, like):
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+def resid_bwd_prep(dout, z_h16, gamma, pad_mask, row_scale, T: int):
+    Cc = dout.shape[-1]
+    rows = dout.numel() // Cc
+    dyg = torch.empty(dout.shape, device=dout.device, dtype=torch.float16)
+    dgamma, db2 = _zeros((Cc,), dout), _zeros((Cc,), dout)
+    _lib.check(_lib.load().osb_resid_bwd_prep(_ptr(_f32(dout)), _ptr(z_h16), _ptr(gamma), _ptr(pad_mask), _ptr(row_scale), _ptr(dyg),
+                                              _ptr(dgamma), _ptr(db2), rows, T, Cc, _stream()), "osb_resid_bwd_prep")
+    return dyg, dgamma, db2
+
+
+def colsum_h16(x_h16):
+    N = x_h16.shape[-1]
+    rows = x_h16.numel() // N
+    out = _zeros((N,), x_h16)
+    _lib.check(_lib.load().osb_colsum_h16(_ptr(x_h16), _ptr(out), rows, N, _stream()), "osb_colsum_h16")
+    return out
+
+
+def ln_fold_bwd(dw1f, w1, ln_w, db1):
+    I, Cc = w1.shape
+    dln_w, dln_b = _zeros((Cc,), w1), _zeros((Cc,), w1)
+    _lib.check(_lib.load().osb_ln_fold_bwd(_ptr(dw1f), _ptr(_f32(w1)), _ptr(ln_w), _ptr(db1), _ptr(dln_w), _ptr(dln_b), I, Cc, _stream()),
+               "osb_ln_fold_bwd")
+    return dw1f, dln_w, dln_b
+
+
+def dwconv_bwd(dd, dout, x, w, pad_mask):
+    B, T, Cc = x.shape
+    dx = torch.empty_like(x)
+    ddw, ddb = _zeros((Cc, 7), x), _zeros((Cc,), x)
+    _lib.check(_lib.load().osb_dwconv_bwd(_ptr(_f32(dd)), _ptr(_f32(dout)), _ptr(_f32(x)), _ptr(_f32(w)), _ptr(pad_mask), _ptr(dx),
+                                          _ptr(ddw), _ptr(ddb), B, T, Cc, _stream()), "osb_dwconv_bwd")
+    return dx, ddw, ddb
+
+
+def layernorm_bwd(dy, x, w, eps: float):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dw, db = _zeros((Cc,), x), _zeros((Cc,), x)
+    _lib.check(_lib.load().osb_layernorm_bwd(_ptr(_f32(dy)), _ptr(_f32(x)), _ptr(_f32(w)), _ptr(dx), _ptr(dw), _ptr(db), rows, Cc, eps,
+                                             _stream()), "osb_layernorm_bwd")
+    return dx, dw, db
+
+
+def predictor_tail_bwd(d_out, pad_mask, r_h16, ln_w, ln_b, lin_w, eps: float):
+    Cc = r_h16.shape[-1]
+    rows = r_h16.numel() // Cc
+    g = torch.empty(r_h16.shape, device=r_h16.device, dtype=torch.float16)
+    dlin_w, dlin_b, dln_w, dln_b = _zeros((Cc,), r_h16), _zeros((1,), r_h16), _zeros((Cc,), r_h16), _zeros((Cc,), r_h16)
+    _lib.check(_lib.load().osb_predictor_tail_bwd(_ptr(_f32(d_out)), _ptr(pad_mask), _ptr(r_h16), _ptr(ln_w), _ptr(ln_b), _ptr(lin_w),
+                                                  _ptr(g), _ptr(dlin_w), _ptr(dlin_b), _ptr(dln_w), _ptr(dln_b), rows, Cc, eps,
+                                                  _stream()), "osb_predictor_tail_bwd")
+    return g, dlin_w, dlin_b, dln_w, dln_b
+
+
+def ln_param_grad(gy_h16, r_h16, ln_w, eps: float):
+    Cc = r_h16.shape[-1]
+    rows = r_h16.numel() // Cc
+    dln_w, dln_b = _zeros((Cc,), r_h16), _zeros((Cc,), r_h16)
+    _lib.check(_lib.load().osb_ln_param_grad(_ptr(gy_h16), _ptr(r_h16), _ptr(ln_w), _ptr(dln_w), _ptr(dln_b), rows, Cc, eps, _stream()),
+               "osb_ln_param_grad")
+    return dln_w, dln_b
+
+
+def variance_embed_bwd(dout, val, pad_mask, ksize: int, want_dx: bool = True):
+    B, T, Cc = dout.shape
+    dx = torch.empty_like(dout) if want_dx else None
+    dw, db = _zeros((Cc, ksize), dout), _zeros((Cc,), dout)
+    _lib.check(_lib.load().osb_variance_embed_bwd(_ptr(_f32(dout)), _ptr(_f32(val)), _ptr(pad_mask), _ptr(dx), _ptr(dw), _ptr(db), B, T, Cc,
+                                                  ksize, _stream()), "osb_variance_embed_bwd")
+    return dx, dw, db
+
+
+def embed_text_bwd(dout, ids, inv_freq, n_vocab: int, padding_idx: int):
+    B, T, dim = dout.shape
+    dtable, dscale = _zeros((n_vocab, dim), dout), _zeros((1,), dout)
+    _lib.check(_lib.load().osb_embed_text_bwd(_ptr(_f32(dout)), _ptr(ids), _ptr(inv_freq), _ptr(dtable), _ptr(dscale), B, T, dim, n_vocab,
+                                              padding_idx, _stream()), "osb_embed_text_bwd")
+    return dtable, dscale
+
+
+def mas(log_p_attn, x_len, m_len):
+    """-> (path (B,Tm) int32, durations (B,Tx) fp32); bit-exact monotonic alignment search on the device."""
+    B, Tm, Tx = log_p_attn.shape
+    path = torch.empty((B, Tm), device=log_p_attn.device, dtype=torch.int32)
+    dur = torch.empty((B, Tx), device=log_p_attn.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_mas(_ptr(_f32(log_p_attn)), _ptr(x_len), _ptr(m_len), _ptr(path), _ptr(dur), B, Tm, Tx, _stream()), "osb_mas")
+    return path, dur
+
+
+def average_by_duration(ds, xs, x_len, m_len):
+    B, Tx = ds.shape
+    Tm = xs.shape[1]
+    out = torch.empty((B, Tx), device=ds.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_average_by_duration(_ptr(_f32(ds)), _ptr(_f32(xs)), _ptr(x_len), _ptr(m_len), _ptr(out), B, Tm, Tx, _stream()),
+               "osb_average_by_duration")
+    return out
