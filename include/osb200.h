@@ -199,9 +199,10 @@ int osb_resid_bwd_prep(const float* dout, const void* z_h16, const float* gamma,
 int osb_colsum_h16(const void* x_h16, float* out, int64_t rows, int32_t N, void* stream);
 
 /* Undo the LayerNorm-affine folding of pwconv1 (W1f = W1 diag(ln_w), b1f = b1 + W1 ln_b):
- * dw1 (in: dW1f, out: dW1 = dW1f * ln_w[c]); dln_w[c] += sum_i dW1f[i,c] W1[i,c]; dln_b[c] += sum_i db1[i] W1[i,c]. */
-int osb_ln_fold_bwd(float* dw1, const float* w1, const float* ln_w, const float* db1, float* dln_w, float* dln_b, int32_t I,
-                    int32_t C, void* stream);
+ * dw1 (in: dW1f, out: dW1[i,c] = dW1f[i,c] ln_w[c] + db1[i] ln_b[c]); dln_w[c] += sum_i dW1f[i,c] W1[i,c];
+ * dln_b[c] += sum_i db1[i] W1[i,c]. */
+int osb_ln_fold_bwd(float* dw1, const float* w1, const float* ln_w, const float* ln_b, const float* db1, float* dln_w, float* dln_b,
+                    int32_t I, int32_t C, void* stream);
 
 /* Depthwise Conv1d(k=7) backward plus the residual path of the block:
  * dx = dout*keep + corr(dd, w);  ddw[c,j] += sum dd[b,t,c] x[b,t+j-3,c];  ddb[c] += sum dd.   (convnext.py:22,36) */

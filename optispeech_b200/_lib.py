@@ -95,7 +95,7 @@ def load() -> C.CDLL:
         "osb_pack_h16": [P, I64, I64, P, P, P, I64, I32, I64, I32, P],
         "osb_resid_bwd_prep": [P, P, P, P, P, P, P, P, I64, I32, I32, P],
         "osb_colsum_h16": [P, P, I64, I32, P],
-        "osb_ln_fold_bwd": [P, P, P, P, P, P, I32, I32, P],
+        "osb_ln_fold_bwd": [P, P, P, P, P, P, P, I32, I32, P],
         "osb_dwconv_bwd": [P, P, P, P, P, P, P, P, I32, I32, I32, P],
         "osb_layernorm_bwd": [P, P, P, P, P, P, I64, I32, F, P],
         "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, P],

@@ -110,12 +110,12 @@ class ConvNeXtBlockFn(Function):
         flags = ops.FLAG_SAVE_PRE | (ops.FLAG_KEEPMASK if pad_mask is not None else 0)
         out, z, _ = ops.gemm(h, w2_h, epi=ops.EPI_RESID, flags=flags, bias=b2, resid=x, gamma=gamma, row_scale=row_scale,
                              pad_mask=pad_mask)
-        ctx.save_for_backward(x, dw_w, ln_w, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale)
+        ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, dw_w, ln_w, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale = ctx.saved_tensors
+        x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale = ctx.saved_tensors
         B, T, C = x.shape
         I = w1.shape[0]
         dout = dout.contiguous()
@@ -129,7 +129,7 @@ class ConvNeXtBlockFn(Function):
         dd, _, _ = ops.gemm(dpre, pack_kn(w1f), epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd)
         dw1f = torch.zeros((1, I, C), device=x.device, dtype=torch.float32)
         ops.gemm_wgrad(dpre, xhat, dw1f)
-        dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, db1)
+        dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, ln_b, db1)
         dx, ddw, ddb = ops.dwconv_bwd(dd, dout, x, dw_w.view(C, 7), pad_mask)
         return dx, ddw.view(C, 1, 7), ddb, dln_w, dln_b, dw1, db1, dw2.view(C, I), db2, dgamma, None, None, None
 

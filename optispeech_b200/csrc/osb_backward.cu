@@ -126,25 +126,26 @@ colsum_h16_kernel(const __half* __restrict__ x, float* __restrict__ out, long lo
 // ------------------------------------------------------------------------------------------
 // un-fold the LayerNorm affine that the forward pass folded into pwconv1:
 //   W1f = W1 * diag(ln_w),  b1f = b1 + W1 @ ln_b
-//   dW1[i,c] = dW1f[i,c] * ln_w[c]           (in place)
+//   dW1[i,c] = dW1f[i,c] * ln_w[c] + db1[i] * ln_b[c]           (in place; b1f depends on W1 too)
 //   dln_w[c] += sum_i dW1f[i,c] * W1[i,c] ;  dln_b[c] += sum_i db1[i] * W1[i,c]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ln_fold_bwd_kernel(float* __restrict__ dw1 /* in: dW1f, out: dW1 */, const float* __restrict__ w1, const float* __restrict__ ln_w,
-                   const float* __restrict__ db1, float* __restrict__ dln_w, float* __restrict__ dln_b, int I, int C,
-                   int rows_per_block) {
+                   const float* __restrict__ ln_b, const float* __restrict__ db1, float* __restrict__ dln_w, float* __restrict__ dln_b,
+                   int I, int C, int rows_per_block) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= C) return;
   const int i0 = blockIdx.y * rows_per_block;
   const int i1 = min(I, i0 + rows_per_block);
-  const float lw = ln_w[c];
+  const float lw = ln_w[c], lb = ln_b[c];
   float aw = 0.f, ab = 0.f;
   for (int i = i0; i < i1; ++i) {
     const float g = dw1[static_cast<long long>(i) * C + c];
     const float w = w1[static_cast<long long>(i) * C + c];
+    const float d1 = db1[i];
     aw = fmaf(g, w, aw);
-    ab = fmaf(db1[i], w, ab);
-    dw1[static_cast<long long>(i) * C + c] = g * lw;
+    ab = fmaf(d1, w, ab);
+    dw1[static_cast<long long>(i) * C + c] = fmaf(g, lw, d1 * lb);
   }
   atomicAdd(dln_w + c, aw);
   atomicAdd(dln_b + c, ab);
@@ -456,13 +457,13 @@ extern "C" int osb_colsum_h16(const void* x_h16, float* out, int64_t rows, int32
   return launch_status();
 }
 
-extern "C" int osb_ln_fold_bwd(float* dw1, const float* w1, const float* ln_w, const float* db1, float* dln_w, float* dln_b,
-                               int32_t I, int32_t C, void* stream) {
-  OSB_REQUIRE(dw1 && w1 && ln_w && db1 && dln_w && dln_b, OSB_ERR_ARG);
+extern "C" int osb_ln_fold_bwd(float* dw1, const float* w1, const float* ln_w, const float* ln_b, const float* db1, float* dln_w,
+                               float* dln_b, int32_t I, int32_t C, void* stream) {
+  OSB_REQUIRE(dw1 && w1 && ln_w && ln_b && db1 && dln_w && dln_b, OSB_ERR_ARG);
   OSB_REQUIRE(I > 0 && C > 0, OSB_ERR_SHAPE);
   const int rpb = 32;
-  ln_fold_bwd_kernel<<<dim3((C + 255) / 256, (I + rpb - 1) / rpb), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw1, w1, ln_w, db1,
-                                                                                                              dln_w, dln_b, I, C, rpb);
+  ln_fold_bwd_kernel<<<dim3((C + 255) / 256, (I + rpb - 1) / rpb), 256, 0, static_cast<cudaStream_t>(stream)>>>(dw1, w1, ln_w, ln_b,
+                                                                                                              db1, dln_w, dln_b, I, C, rpb);
   count_launch();
   return launch_status();
 }

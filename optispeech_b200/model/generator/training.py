@@ -85,7 +85,8 @@ def viterbi_decode(log_p_attn, text_lengths, feats_lengths):
     path, ds = ops.mas(log_p_attn.detach().contiguous(), text_lengths.contiguous(), feats_lengths.contiguous())
     valid = path >= 0
     picked = torch.gather(log_p_attn, 2, path.clamp(min=0).long().unsqueeze(-1)).squeeze(-1)
-    per_sample = (picked * valid).sum(dim=1) / feats_lengths.to(picked.dtype)
+    picked = torch.where(valid, picked, torch.zeros((), device=picked.device, dtype=picked.dtype))  # padded frames hold -inf
+    per_sample = picked.sum(dim=1) / feats_lengths.to(picked.dtype)
     bin_loss = -(per_sample.sum()) / B
     return ds, bin_loss
 
@@ -103,7 +104,9 @@ def forward_sum_loss(log_p_attn, ilens, olens, blank_logprob: float = -1.0):
     B, Tm, Tx = log_p_attn.shape
     padded = F.pad(log_p_attn, (1, 0), value=blank_logprob)                       # (B, Tm, Tx+1)
     col_ok = torch.arange(Tx + 1, device=padded.device)[None, :] <= ilens[:, None]  # blank + the sample's own tokens
-    padded = padded.masked_fill(~col_ok[:, None, :], -float("inf"))
+    # columns past the sample's own tokens (and the -inf prior of padded frames) are pushed to a large finite negative:
+    # exp() of it is exactly 0 in fp32, so the normalisation is unchanged, and the CTC backward stays NaN-free
+    padded = padded.masked_fill(~col_ok[:, None, :], -1.0e4).clamp(min=-1.0e4)
     lp = F.log_softmax(padded, dim=-1).transpose(0, 1)                            # (Tm, B, Tx+1)
     targets = torch.arange(1, Tx + 1, device=padded.device)[None, :].expand(B, -1)
     per_sample = F.ctc_loss(lp, targets, olens, ilens, blank=0, reduction="none", zero_infinity=True)

@@ -222,11 +222,11 @@ def colsum_h16(x_h16):
     return out
 
 
-def ln_fold_bwd(dw1f, w1, ln_w, db1):
+def ln_fold_bwd(dw1f, w1, ln_w, ln_b, db1):
     I, Cc = w1.shape
     dln_w, dln_b = _zeros((Cc,), w1), _zeros((Cc,), w1)
-    _lib.check(_lib.load().osb_ln_fold_bwd(_ptr(dw1f), _ptr(_f32(w1)), _ptr(ln_w), _ptr(db1), _ptr(dln_w), _ptr(dln_b), I, Cc, _stream()),
-               "osb_ln_fold_bwd")
+    _lib.check(_lib.load().osb_ln_fold_bwd(_ptr(dw1f), _ptr(_f32(w1)), _ptr(ln_w), _ptr(ln_b), _ptr(db1), _ptr(dln_w), _ptr(dln_b), I, Cc,
+                                           _stream()), "osb_ln_fold_bwd")
     return dw1f, dln_w, dln_b
 
 

@@ -1,0 +1,179 @@
+"""Unit parity of every autograd Function (forward + hand-written backward kernels) against the oracle's fp32
+restatement evaluated with torch.autograd on the same inputs.  Tolerances: fp16 operands, fp32 accumulation."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model as O
+from oracle.spec import PredictorSpec
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+def _check(named_pairs, tol):
+    bad = [(n, rel(a, b)) for n, a, b in named_pairs if not rel(a, b) <= tol]
+    for n, a, b in named_pairs:
+        print(f"  {n}: rel err {rel(a, b):.3e}")
+    assert not bad, bad
+
+
+def test_layernorm_fn(cuda_device):
+    from optispeech_b200.autograd import LayerNormFn
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 50, 256, generator=g).to(cuda_device).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(256, generator=g)).to(cuda_device).requires_grad_(True)
+    b = (0.1 * torch.randn(256, generator=g)).to(cuda_device).requires_grad_(True)
+    dy = torch.randn(3, 50, 256, generator=g).to(cuda_device)
+    y = LayerNormFn.apply(x, w, b, 1e-6)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), dy)
+    yr = F.layer_norm(x, (256,), w, b, 1e-6)
+    rx, rw, rb = torch.autograd.grad(yr, (x, w, b), dy)
+    _check([("y", y, yr), ("dx", gx, rx), ("dw", gw, rw), ("db", gb, rb)], 1e-5)
+
+
+@pytest.mark.parametrize("C,I,T", [(256, 1024, 77), (384, 1152, 64)])
+def test_convnext_block_fn(cuda_device, C, I, T):
+    from optispeech_b200.autograd import ConvNeXtBlockFn
+
+    g = torch.Generator().manual_seed(1)
+    B = 3
+    dev = cuda_device
+    sd = {
+        "b.dwconv.weight": torch.randn(C, 1, 7, generator=g) * 0.3, "b.dwconv.bias": torch.randn(C, generator=g) * 0.1,
+        "b.norm.weight": 1 + 0.1 * torch.randn(C, generator=g), "b.norm.bias": 0.1 * torch.randn(C, generator=g),
+        "b.pwconv1.weight": torch.randn(I, C, generator=g) / C ** 0.5, "b.pwconv1.bias": 0.1 * torch.randn(I, generator=g),
+        "b.pwconv2.weight": torch.randn(C, I, generator=g) / I ** 0.5, "b.pwconv2.bias": 0.1 * torch.randn(C, generator=g),
+        "b.gamma": 0.25 * (1 + 0.1 * torch.randn(C, generator=g)),
+    }
+    sd = {k: v.to(dev).requires_grad_(True) for k, v in sd.items()}
+    x = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True)
+    pad = (torch.arange(T)[None] >= torch.tensor([T, T - 9, T // 2])[:, None]).to(dev)
+    rs = torch.tensor([1.0, 0.0, 1.25]).to(dev)
+    dy = torch.randn(B, T, C, generator=g).to(dev)
+    names = ["dwconv.weight", "dwconv.bias", "norm.weight", "norm.bias", "pwconv1.weight", "pwconv1.bias", "pwconv2.weight",
+             "pwconv2.bias", "gamma"]
+    params = [sd[f"b.{n}"] for n in names]
+    y = ConvNeXtBlockFn.apply(x, *params, pad.to(torch.uint8), rs, 1e-6)
+    grads = torch.autograd.grad(y, (x, *params), dy)
+    yr = O.convnext_block(sd, "b", x, drop_scale=rs) * (1 - pad.float())[..., None]
+    rgrads = torch.autograd.grad(yr, (x, *params), dy)
+    _check([("y", y, yr)] + [(n, a, b) for n, a, b in zip(["dx"] + names, grads, rgrads)], 4e-3)
+
+
+@pytest.mark.parametrize("L,Cmid,k,needs_dx", [(2, 384, 3, True), (5, 256, 5, True), (2, 384, 3, False)])
+def test_variance_predictor_fn(cuda_device, L, Cmid, k, needs_dx):
+    from optispeech_b200.autograd import VariancePredictorFn
+
+    g = torch.Generator().manual_seed(2)
+    B, T, C = 3, 61, 256
+    dev = cuda_device
+    ps = PredictorSpec(L, Cmid, k)
+    sd = {}
+    for i in range(L):
+        cin = C if i == 0 else Cmid
+        sd[f"p.conv.{i}.0.weight"] = torch.randn(Cmid, cin, k, generator=g) / (cin * k) ** 0.5
+        sd[f"p.conv.{i}.0.bias"] = 0.1 * torch.randn(Cmid, generator=g)
+        sd[f"p.conv.{i}.2.weight"] = 1 + 0.1 * torch.randn(Cmid, generator=g)
+        sd[f"p.conv.{i}.2.bias"] = 0.1 * torch.randn(Cmid, generator=g)
+    sd["p.linear.weight"] = torch.randn(1, Cmid, generator=g) / Cmid ** 0.5
+    sd["p.linear.bias"] = torch.randn(1, generator=g)
+    sd = {k_: v.to(dev).requires_grad_(True) for k_, v in sd.items()}
+    x = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(needs_dx)
+    pad = (torch.arange(T)[None] >= torch.tensor([T, T - 9, T // 2])[:, None]).to(dev)
+    dy = torch.randn(B, T, generator=g).to(dev)
+    layer_params = []
+    for i in range(L):
+        layer_params += [sd[f"p.conv.{i}.0.weight"], sd[f"p.conv.{i}.0.bias"], sd[f"p.conv.{i}.2.weight"], sd[f"p.conv.{i}.2.bias"]]
+    y = VariancePredictorFn.apply(x, pad.to(torch.uint8), k, 1e-12, sd["p.linear.weight"], sd["p.linear.bias"], *layer_params)
+    wrt = ([x] if needs_dx else []) + [sd["p.linear.weight"], sd["p.linear.bias"]] + layer_params
+    grads = torch.autograd.grad(y, wrt, dy)
+    yr = O.variance_predictor(sd, "p", x, pad, ps)
+    rgrads = torch.autograd.grad(yr, wrt, dy)
+    names = (["dx"] if needs_dx else []) + ["lin_w", "lin_b"] + [f"l{i}.{n}" for i in range(L) for n in ("cw", "cb", "lnw", "lnb")]
+    # ReLU gates that flip under the fp16-operand forward (vs the fp32 oracle) dominate the error and grow with depth
+    _check([("y", y, yr)] + list(zip(names, grads, rgrads)), 6e-3 if L <= 2 else 4e-2)
+
+
+def test_conv_stack_fn(cuda_device):
+    from optispeech_b200.autograd import ConvStackFn
+
+    g = torch.Generator().manual_seed(3)
+    B, T, Cin, C = 2, 90, 100, 256
+    dev = cuda_device
+    ws = [torch.randn(C, Cin, 3, generator=g) / (Cin * 3) ** 0.5, torch.randn(C, C, 3, generator=g) / (C * 3) ** 0.5,
+          torch.randn(C, C, 1, generator=g) / C ** 0.5]
+    bs = [0.1 * torch.randn(C, generator=g) for _ in range(3)]
+    ws = [w.to(dev).requires_grad_(True) for w in ws]
+    bs = [b.to(dev).requires_grad_(True) for b in bs]
+    x = torch.randn(B, T, Cin, generator=g).to(dev)   # the mel input never needs a gradient
+    dy = torch.randn(B, T, C, generator=g).to(dev)
+    y = ConvStackFn.apply(x, 128, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2])
+    grads = torch.autograd.grad(y, (*ws, *bs), dy)
+    h = x.transpose(1, 2)
+    h = F.relu(F.conv1d(h, ws[0], bs[0], padding=1))
+    h = F.relu(F.conv1d(h, ws[1], bs[1], padding=1))
+    yr = F.conv1d(h, ws[2], bs[2]).transpose(1, 2)
+    rgrads = torch.autograd.grad(yr, (*ws, *bs), dy)
+    names = ["w0", "w1", "w2", "b0", "b1", "b2"]
+    _check([("y", y, yr)] + list(zip(names, grads, rgrads)), 1.5e-2)
+    # text path: 256 -> 256 (k3) -> 256 (k1), input gradient required
+    xt = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True)
+    y = ConvStackFn.apply(xt, 0, ws[1], bs[1], ws[2], bs[2])
+    grads = torch.autograd.grad(y, (xt, ws[1], ws[2]), dy)
+    yr = F.conv1d(F.relu(F.conv1d(xt.transpose(1, 2), ws[1], bs[1], padding=1)), ws[2], bs[2]).transpose(1, 2)
+    rgrads = torch.autograd.grad(yr, (xt, ws[1], ws[2]), dy)
+    _check([("y", y, yr)] + list(zip(["dx", "w1", "w2"], grads, rgrads)), 1.5e-2)
+
+
+def test_embed_and_variance_embed_fn(cuda_device):
+    from optispeech_b200.autograd import EmbedTextFn, VarianceEmbedFn
+
+    g = torch.Generator().manual_seed(4)
+    dev = cuda_device
+    B, T, C, V = 3, 40, 256, 50
+    ids = torch.randint(0, V, (B, T), generator=g).to(dev)
+    table = (0.3 * torch.randn(V, C, generator=g)).to(dev).requires_grad_(True)
+    scale = torch.full((1,), 0.08).to(dev).requires_grad_(True)
+    inv_freq = (2000.0 ** -(torch.arange(C // 2).float() / (C // 2))).to(dev)
+    dy = torch.randn(B, T, C, generator=g).to(dev)
+    y = EmbedTextFn.apply(ids, table, scale, inv_freq, 0)
+    gt, gs = torch.autograd.grad(y, (table, scale), dy)
+    ang = torch.arange(T, device=dev).float()[:, None] * inv_freq[None]
+    yr = C ** 0.5 * F.embedding(ids, table, padding_idx=0) + torch.cat((ang.sin(), ang.cos()), -1) * scale
+    rt, rs_ = torch.autograd.grad(yr, (table, scale), dy)
+    _check([("y", y, yr), ("dtable", gt, rt), ("dscale", gs, rs_)], 1e-5)
+
+    x = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True)
+    val = torch.randn(B, T, generator=g).to(dev)
+    w = (0.3 * torch.randn(C, 1, 9, generator=g)).to(dev).requires_grad_(True)
+    b = (0.1 * torch.randn(C, generator=g)).to(dev).requires_grad_(True)
+    pad = (torch.arange(T)[None] >= torch.tensor([T, T - 9, T // 2])[:, None]).to(dev)
+    y = VarianceEmbedFn.apply(x, val, w, b, pad.to(torch.uint8))
+    grads = torch.autograd.grad(y, (x, w, b), dy)
+    yr = (x + F.conv1d(val.unsqueeze(1), w, b, padding=4).transpose(1, 2)) * (1 - pad.float())[..., None]
+    rgrads = torch.autograd.grad(yr, (x, w, b), dy)
+    _check([("y", y, yr)] + list(zip(["dx", "dw", "db"], grads, rgrads)), 1e-5)
+
+
+def test_wavenext_head_fn(cuda_device):
+    from optispeech_b200.autograd import WaveNeXtHeadFn
+
+    g = torch.Generator().manual_seed(5)
+    dev = cuda_device
+    B, T, C = 2, 64, 384
+    x = torch.randn(B, T, C, generator=g).to(dev).requires_grad_(True)
+    w1 = (torch.randn(1026, C, generator=g) / C ** 0.5).to(dev).requires_grad_(True)
+    b1 = (0.1 * torch.randn(1026, generator=g)).to(dev).requires_grad_(True)
+    w2 = (torch.randn(256, 1026, generator=g) / 1026 ** 0.5 * 0.5).to(dev).requires_grad_(True)
+    dy = torch.randn(B, T * 256, generator=g).to(dev)
+    y = WaveNeXtHeadFn.apply(x, w1, b1, w2)
+    grads = torch.autograd.grad(y, (x, w1, b1, w2), dy)
+    yr = torch.clip(F.linear(F.linear(x, w1, b1), w2).reshape(B, -1), -1.0, 1.0)
+    rgrads = torch.autograd.grad(yr, (x, w1, b1, w2), dy)
+    # elements whose pre-clip value sits within fp16 operand error of +-1 may flip the clip gate; exclude nothing, use a norm bound
+    _check([("y", y, yr)] + list(zip(["dx", "dw1", "db1", "dw2"], grads, rgrads)), 2e-2)
