@@ -116,6 +116,10 @@ typedef struct osb_gemm_desc {
   float* out_dot;       /* DOT: (B*T) fp32                                                         */
   const void* aux_in_h16; /* *_BWD: fp16 (B*T, ldo) saved activation                                */
   const float* row_stat;  /* LN_BWD: (B*T) rstd saved by osb_dwconv_ln                              */
+  /* Dropout after the LayerNorm of RELU_LN (VariancePredictor, core.py:78), element (row, n) keyed by
+   * dropout_seed: forward scales the LN output, RELU_LN_BWD scales the incoming gradient by the same mask. */
+  float dropout_p;        /* 0 disables                                                              */
+  uint64_t dropout_seed;
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);
@@ -150,10 +154,11 @@ int osb_dwconv_ln(const float* x, const float* w /*(C,7)*/, const float* bias, v
 int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
                   float eps, int32_t split, void* stream);
 
-/* out = (x + bias + Conv1d(1->C, k, same)(val)) * (1 - pad_mask).  Replaces PitchPredictor.forward/
- * infer's embed + add + mask (modules/core.py:152-176). */
+/* out = (x + emb_scale * (bias + Conv1d(1->C, k, same)(val))) * (1 - pad_mask); emb_scale (B,T,C) is the optional
+ * dropout mask/(1-p) of the embedding branch (NULL = 1).  Replaces PitchPredictor.forward/infer's embed + add + mask
+ * (modules/core.py:143-176). */
 int osb_variance_embed(const float* x, const float* val /*(B,T)*/, const float* w /*(C,k)*/, const float* bias,
-                       const uint8_t* pad_mask, float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize,
+                       const uint8_t* pad_mask, const float* emb_scale, float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize,
                        int32_t split, void* stream);
 
 /* dur = clamp(ceil((exp(log_d) - clip_val) * factor), 0) as int64, 0 at pads; lengths[b] = sum_t dur.
@@ -218,16 +223,17 @@ int osb_layernorm_bwd(const float* dy, const float* x, const float* w, float* dx
  * r = relu(conv) of the last layer, fp16, saved by OSB_EPI_RELU_LN + OSB_FLAG_SAVE_PRE. */
 int osb_predictor_tail_bwd(const float* d_out /*(rows)*/, const uint8_t* pad_mask, const void* r_h16, const float* ln_w,
                            const float* ln_b, const float* lin_w, void* g_conv_h16, float* dlin_w, float* dlin_b, float* dln_w,
-                           float* dln_b, int64_t rows, int32_t C, float eps, void* stream);
+                           float* dln_b, int64_t rows, int32_t C, float eps, float dropout_p, uint64_t dropout_seed, void* stream);
 
 /* LayerNorm parameter gradients of an inner predictor layer: dln_w += sum gy*xhat(r), dln_b += sum gy, with
  * gy = fp16 gradient wrt the layer output (aux of OSB_EPI_RELU_LN_BWD + OSB_FLAG_OUT_H16). */
 int osb_ln_param_grad(const void* gy_h16, const void* r_h16, const float* ln_w, float* dln_w, float* dln_b, int64_t rows, int32_t C,
                       float eps, void* stream);
 
-/* Backward of osb_variance_embed: dx = dout*keep (optional), dw[c,j] += sum dout*keep*val[b,t+j-h], db[c] += sum dout*keep. */
-int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* pad_mask, float* dx, float* dw, float* db, int32_t B,
-                           int32_t T, int32_t C, int32_t ksize, void* stream);
+/* Backward of osb_variance_embed: dx = dout*keep (optional), dw[c,j] += sum dout*keep*emb_scale*val[b,t+j-h],
+ * db[c] += sum dout*keep*emb_scale. */
+int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* pad_mask, const float* emb_scale, float* dx, float* dw,
+                           float* db, int32_t B, int32_t T, int32_t C, int32_t ksize, void* stream);
 
 /* Backward of osb_embed_text: dtable[id] += sqrt(dim)*dout (padding row untouched), dscale += sum dout*pe. */
 int osb_embed_text_bwd(const float* dout, const int64_t* ids, const float* inv_freq, float* dtable, float* dscale, int32_t B,
@@ -248,6 +254,20 @@ int osb_mas(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len,
  * Replaces average_by_duration (generator/alignments.py:242-280). */
 int osb_average_by_duration(const float* ds, const float* xs, const int64_t* x_len, const int64_t* m_len, float* out, int32_t B,
                             int32_t Tm, int32_t Tx, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Optimizer over one flat fp32 bucket (osb_optim.cu).  Replaces, for the generator / discriminator parameter
+ * groups, Lightning's clip_gradients(norm) + torch.optim.AdamW.step of BaseLightningModule.training_step
+ * (optispeech/model/base_lightning_module.py:99-105,119-125; configs/model/optimizer/adamw.yaml).
+ * ------------------------------------------------------------------------------------- */
+
+/* stats[0] += sum g^2, stats[1] = 1 if a non-finite value was seen.  stats must be zeroed by the caller. */
+int osb_grad_sumsq(const float* g, int64_t n, float* stats /*(2)*/, void* stream);
+
+/* Fused: unscale by inv_scale, clip by global norm (max_norm <= 0 disables), decoupled-weight-decay Adam update with
+ * bias correction for `step` (1-based).  Skipped entirely when stats[1] != 0 (non-finite gradient). */
+int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step, float max_norm, float inv_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,8 @@ class GemmDesc(C.Structure):
         ("out_dot", C.c_void_p),
         ("aux_in_h16", C.c_void_p),
         ("row_stat", C.c_void_p),
+        ("dropout_p", C.c_float),
+        ("dropout_seed", C.c_uint64),
     ]
 
 
@@ -87,7 +89,7 @@ def load() -> C.CDLL:
         "osb_embed_text": [P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, I32, P],
         "osb_layernorm": [P, P, P, P, P, I64, I32, F, I32, P],
-        "osb_variance_embed": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, P],
+        "osb_variance_embed": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_durations": [P, P, P, P, I32, I32, F, F, P],
         "osb_centres": [P, I32, P, P, I32, I32, P],
         "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
@@ -98,11 +100,13 @@ def load() -> C.CDLL:
         "osb_ln_fold_bwd": [P, P, P, P, P, P, P, I32, I32, P],
         "osb_dwconv_bwd": [P, P, P, P, P, P, P, P, I32, I32, I32, P],
         "osb_layernorm_bwd": [P, P, P, P, P, P, I64, I32, F, P],
-        "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, P],
+        "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, F, C.c_uint64, P],
         "osb_ln_param_grad": [P, P, P, P, P, I64, I32, F, P],
-        "osb_variance_embed_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_variance_embed_bwd": [P, P, P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_embed_text_bwd": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_mas": [P, P, P, P, P, I32, I32, I32, P],
+        "osb_grad_sumsq": [P, I64, P, P],
+        "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],
     }
     for name, argtypes in sigs.items():

@@ -139,8 +139,9 @@ class ConvNeXtBlockFn(Function):
 # --------------------------------------------------------------------------------------------------
 class VariancePredictorFn(Function):
     @staticmethod
-    def forward(ctx, x, pad_mask, kernel_size, eps, lin_w, lin_b, *layer_params):
-        """layer_params = (conv_w, conv_b, ln_w, ln_b) per layer.  x fp32 (B,T,C) -> (B,T) fp32."""
+    def forward(ctx, x, pad_mask, kernel_size, eps, dropout_p, dropout_seed, lin_w, lin_b, *layer_params):
+        """layer_params = (conv_w, conv_b, ln_w, ln_b) per layer.  x fp32 (B,T,C) -> (B,T) fp32.
+        dropout_p > 0 applies dropout after every LayerNorm (core.py:78); layer l uses seed dropout_seed + l."""
         L = len(layer_params) // 4
         pad = (kernel_size - 1) // 2
         a = ops.to_h16(x.contiguous())
@@ -150,14 +151,17 @@ class VariancePredictorFn(Function):
             cw, cb, lw, lb = layer_params[4 * l: 4 * l + 4]
             wp = pack_conv_fwd(cw)
             if l < L - 1:
-                y, r, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, pad=pad, bias=cb, ln_w=lw, ln_b=lb, ln_eps=eps)
+                y, r, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, pad=pad, bias=cb, ln_w=lw, ln_b=lb, ln_eps=eps,
+                                   dropout_p=dropout_p, dropout_seed=dropout_seed + l)
                 acts.append(y)
             else:
                 _, r, out = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE | ops.FLAG_DOT, pad=pad, bias=cb, ln_w=lw,
-                                     ln_b=lb, ln_eps=eps, dot_w=lin_w.view(-1), dot_b=lin_b, pad_mask=pad_mask)
+                                     ln_b=lb, ln_eps=eps, dot_w=lin_w.view(-1), dot_b=lin_b, pad_mask=pad_mask, dropout_p=dropout_p,
+                                     dropout_seed=dropout_seed + l)
             pres.append(r)
         ctx.save_for_backward(pad_mask, lin_w, *layer_params, *acts, *pres)
         ctx.L, ctx.k, ctx.eps = L, kernel_size, eps
+        ctx.drop_p, ctx.drop_seed = dropout_p, dropout_seed
         ctx.x_needs_grad = x.requires_grad
         return out
 
@@ -172,7 +176,8 @@ class VariancePredictorFn(Function):
         pad = (k - 1) // 2
         grads: List[Optional[torch.Tensor]] = [None] * (4 * L)
         cw, cb, lw, lb = layer_params[4 * (L - 1): 4 * L]
-        g, dlin_w, dlin_b, dln_w, dln_b = ops.predictor_tail_bwd(d_out.contiguous(), pad_mask, pres[L - 1], lw, lb, lin_w.view(-1), eps)
+        g, dlin_w, dlin_b, dln_w, dln_b = ops.predictor_tail_bwd(d_out.contiguous(), pad_mask, pres[L - 1], lw, lb, lin_w.view(-1), eps,
+                                                                 ctx.drop_p, ctx.drop_seed + L - 1)
         grads[4 * (L - 1) + 2], grads[4 * (L - 1) + 3] = dln_w, dln_b
         dx = None
         for l in range(L - 1, -1, -1):
@@ -183,12 +188,13 @@ class VariancePredictorFn(Function):
             if l > 0:
                 lw_prev = layer_params[4 * (l - 1) + 2]
                 g_prev, gy, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, pad=k - 1 - pad,
-                                         aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps)
+                                         aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps, dropout_p=ctx.drop_p,
+                                         dropout_seed=ctx.drop_seed + l - 1)
                 grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3] = ops.ln_param_grad(gy, pres[l - 1], lw_prev, eps)
                 g = g_prev
             elif ctx.x_needs_grad:
                 dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
-        return (dx, None, None, None, dlin_w.view(1, -1), dlin_b, *grads)
+        return (dx, None, None, None, None, None, dlin_w.view(1, -1), dlin_b, *grads)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -244,19 +250,20 @@ class ConvStackFn(Function):
 # --------------------------------------------------------------------------------------------------
 class VarianceEmbedFn(Function):
     @staticmethod
-    def forward(ctx, x, val, w, b, pad_mask):
+    def forward(ctx, x, val, w, b, pad_mask, emb_scale=None):
         C = x.shape[-1]
-        ctx.save_for_backward(val, pad_mask)
+        ctx.save_for_backward(val, pad_mask, emb_scale)
         ctx.k = w.shape[-1]
         ctx.x_needs_grad = x.requires_grad
-        out, _ = ops.variance_embed(x.contiguous(), val.contiguous(), w.view(C, -1), b, pad_mask, f32=True, h16=False)
+        out, _ = ops.variance_embed(x.contiguous(), val.contiguous(), w.view(C, -1), b, pad_mask, f32=True, h16=False,
+                                    emb_scale=emb_scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        val, pad_mask = ctx.saved_tensors
-        dx, dw, db = ops.variance_embed_bwd(dout.contiguous(), val, pad_mask, ctx.k, want_dx=ctx.x_needs_grad)
-        return dx, None, dw.view(dw.shape[0], 1, ctx.k), db, None
+        val, pad_mask, emb_scale = ctx.saved_tensors
+        dx, dw, db = ops.variance_embed_bwd(dout.contiguous(), val, pad_mask, ctx.k, want_dx=ctx.x_needs_grad, emb_scale=emb_scale)
+        return dx, None, dw.view(dw.shape[0], 1, ctx.k), db, None, None
 
 
 # --------------------------------------------------------------------------------------------------

@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(WPB * 32)
 predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restrict__ gy, const uint8_t* __restrict__ pad_mask,
                         const __half* __restrict__ r, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                         const float* __restrict__ lin_w, __half* __restrict__ g_conv, float* __restrict__ dlin_w,
-                        float* __restrict__ dlin_b, float* __restrict__ dln_w, float* __restrict__ dln_b, long long rows, float eps) {
+                        float* __restrict__ dlin_b, float* __restrict__ dln_w, float* __restrict__ dln_b, long long rows, float eps,
+                        float drop_p, float drop_inv_keep, unsigned long long drop_seed) {
   constexpr int C = 128 * VPL;
   const int lane = threadIdx.x & 31;
   long long r0, r1;
@@ -319,11 +320,19 @@ predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restric
     for (int v = 0; v < VPL; ++v) {
       xh[v].x *= rstd; xh[v].y *= rstd; xh[v].z *= rstd; xh[v].w *= rstd;
       if (tail) {
-        g[v] = make_float4(d * li[v].x, d * li[v].y, d * li[v].z, d * li[v].w);
-        a_lin[v].x = fmaf(d, fmaf(xh[v].x, lw[v].x, lb[v].x), a_lin[v].x);
-        a_lin[v].y = fmaf(d, fmaf(xh[v].y, lw[v].y, lb[v].y), a_lin[v].y);
-        a_lin[v].z = fmaf(d, fmaf(xh[v].z, lw[v].z, lb[v].z), a_lin[v].z);
-        a_lin[v].w = fmaf(d, fmaf(xh[v].w, lw[v].w, lb[v].w), a_lin[v].w);
+        float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);  // dropout mask (with 1/keep) of the forward pass
+        if (drop_p > 0.f) {
+          const unsigned long long base = static_cast<unsigned long long>(row) * C + v * 128 + lane * 4;
+          mk.x = dropout_scale(drop_seed, base + 0, drop_p, drop_inv_keep);
+          mk.y = dropout_scale(drop_seed, base + 1, drop_p, drop_inv_keep);
+          mk.z = dropout_scale(drop_seed, base + 2, drop_p, drop_inv_keep);
+          mk.w = dropout_scale(drop_seed, base + 3, drop_p, drop_inv_keep);
+        }
+        g[v] = make_float4(d * li[v].x * mk.x, d * li[v].y * mk.y, d * li[v].z * mk.z, d * li[v].w * mk.w);
+        a_lin[v].x = fmaf(d * mk.x, fmaf(xh[v].x, lw[v].x, lb[v].x), a_lin[v].x);
+        a_lin[v].y = fmaf(d * mk.y, fmaf(xh[v].y, lw[v].y, lb[v].y), a_lin[v].y);
+        a_lin[v].z = fmaf(d * mk.z, fmaf(xh[v].z, lw[v].z, lb[v].z), a_lin[v].z);
+        a_lin[v].w = fmaf(d * mk.w, fmaf(xh[v].w, lw[v].w, lb[v].w), a_lin[v].w);
       } else {
         g[v] = ldh4(gy + row * C + v * 128 + lane * 4);
       }
@@ -366,7 +375,8 @@ predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restric
 //   dx = dout * keep ; dw[c,j] += sum dout*keep*val[b,t+j-h] ; db[c] += sum dout*keep
 // ------------------------------------------------------------------------------------------
 __global__ void variance_embed_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ val,
-                                          const uint8_t* __restrict__ pad_mask, float* __restrict__ dx, float* __restrict__ dw,
+                                          const uint8_t* __restrict__ pad_mask, const float* __restrict__ emb_scale,
+                                          float* __restrict__ dx, float* __restrict__ dw,
                                           float* __restrict__ db, int T, int C, int ksize, int TT) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -381,11 +391,12 @@ __global__ void variance_embed_bwd_kernel(const float* __restrict__ dout, const 
     const float keep = (pad_mask != nullptr && pad_mask[row]) ? 0.f : 1.f;
     const float g = dout[row * C + c] * keep;
     if (dx != nullptr) dx[row * C + c] = g;
-    ab += g;
+    const float ge = emb_scale != nullptr ? g * emb_scale[row * C + c] : g;  // gradient of the (dropped) embedding branch
+    ab += ge;
     for (int j = 0; j < ksize; ++j) {
       const int tt = t + j - halfk;
       const float v = (tt >= 0 && tt < T) ? val[static_cast<long long>(b) * T + tt] : 0.f;
-      aw[j] = fmaf(g, v, aw[j]);
+      aw[j] = fmaf(ge, v, aw[j]);
     }
   }
   for (int j = 0; j < ksize; ++j) atomicAdd(dw + c * ksize + j, aw[j]);
@@ -493,14 +504,18 @@ extern "C" int osb_layernorm_bwd(const float* dy, const float* x, const float* w
 
 extern "C" int osb_predictor_tail_bwd(const float* d_out, const uint8_t* pad_mask, const void* r_h16, const float* ln_w,
                                       const float* ln_b, const float* lin_w, void* g_conv_h16, float* dlin_w, float* dlin_b,
-                                      float* dln_w, float* dln_b, int64_t rows, int32_t C, float eps, void* stream) {
+                                      float* dln_w, float* dln_b, int64_t rows, int32_t C, float eps, float dropout_p,
+                                      uint64_t dropout_seed, void* stream) {
   OSB_REQUIRE(d_out && r_h16 && ln_w && ln_b && lin_w && g_conv_h16 && dlin_w && dlin_b && dln_w && dln_b, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
+  OSB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, OSB_ERR_ARG);
+  const float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 0.f;
   const int grid = grid_for_rows(rows, 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         d_out, nullptr, pad_mask, static_cast<const __half*>(r_h16), ln_w, ln_b, lin_w,
-                        static_cast<__half*>(g_conv_h16), dlin_w, dlin_b, dln_w, dln_b, rows, eps)));
+                        static_cast<__half*>(g_conv_h16), dlin_w, dlin_b, dln_w, dln_b, rows, eps, dropout_p, inv_keep,
+                        static_cast<unsigned long long>(dropout_seed))));
   count_launch();
   return launch_status();
 }
@@ -513,19 +528,20 @@ extern "C" int osb_ln_param_grad(const void* gy_h16, const void* r_h16, const fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         nullptr, static_cast<const __half*>(gy_h16), nullptr, static_cast<const __half*>(r_h16), ln_w, nullptr,
-                        nullptr, nullptr, nullptr, nullptr, dln_w, dln_b, rows, eps)));
+                        nullptr, nullptr, nullptr, nullptr, dln_w, dln_b, rows, eps, 0.f, 0.f, 0ull)));
   count_launch();
   return launch_status();
 }
 
-extern "C" int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* pad_mask, float* dx, float* dw, float* db,
+extern "C" int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* pad_mask, const float* emb_scale, float* dx,
+                                      float* dw, float* db,
                                       int32_t B, int32_t T, int32_t C, int32_t ksize, void* stream) {
   OSB_REQUIRE(dout && val && dw && db, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && C > 0 && ksize > 0 && ksize <= 16, OSB_ERR_SHAPE);
   const int TT = 32;
   const int threads = 128;
   dim3 grid((C + threads - 1) / threads, (T + TT - 1) / TT, B);
-  variance_embed_bwd_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(dout, val, pad_mask, dx, dw, db, T, C, ksize, TT);
+  variance_embed_bwd_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(dout, val, pad_mask, emb_scale, dx, dw, db, T, C, ksize, TT);
   count_launch();
   return launch_status();
 }

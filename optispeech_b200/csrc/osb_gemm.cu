@@ -42,6 +42,9 @@ struct GemmKParams {
   float* out_dot;
   const void* aux_in;
   const float* row_stat;
+  float drop_p;
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
@@ -204,9 +207,14 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
     }
     const float rstd = rsqrtf(q * inv_n + p.ln_eps);
     float s1 = 0.f, s2 = 0.f;
+    const unsigned long long dbase = static_cast<unsigned long long>(valid ? row : 0) * BN;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
       ld_h16x32(rrow + c0, r);
+      if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+      }
       if (valid && (p.flags & OSB_FLAG_OUT_H16)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -219,6 +227,10 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
       ld_h16x32(rrow + c0, r);
+      if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const float g = v[i] * __ldg(p.ln_w + c0 + i);
@@ -320,6 +332,11 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         v[i] = (v[i] - mean) * rstd * __ldg(p.ln_w + c0 + i) + __ldg(p.ln_b + c0 + i);
+      }
+      if (kRelu && p.drop_p > 0.f) {
+        const unsigned long long base = static_cast<unsigned long long>(valid ? row : 0) * BN + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, base + i, p.drop_p, p.drop_inv_keep);
       }
       if (p.flags & OSB_FLAG_DOT) {
 #pragma unroll
@@ -679,6 +696,9 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.pad_mask = d->pad_mask; p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps;
   p.dot_w = d->dot_w; p.dot_b = d->dot_b; p.out_dot = d->out_dot;
   p.aux_in = d->aux_in_h16; p.row_stat = d->row_stat;
+  p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed;
+  p.drop_inv_keep = d->dropout_p > 0.f && d->dropout_p < 1.f ? 1.f / (1.f - d->dropout_p) : 0.f;
+  OSB_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, OSB_ERR_ARG);
 
   if ((d->flags & (OSB_FLAG_OUT_H16 | OSB_FLAG_SAVE_PRE)) && d->aux_h16 == nullptr) return OSB_ERR_ARG;
   if ((d->flags & OSB_FLAG_KEEPMASK) && d->pad_mask == nullptr) return OSB_ERR_ARG;

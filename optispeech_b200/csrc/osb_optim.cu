@@ -1,0 +1,99 @@
+// osb_optim.cu — optimizer kernels over one flat fp32 parameter / gradient bucket:
+// global gradient norm (with non-finite detection) and fused unscale + clip-by-global-norm + AdamW.
+// HBM-bound: one pass over the gradient for the norm, one pass over (p, g, m, v) for the update.
+#include "osb_host.h"
+#include "osb_ptx.cuh"
+
+namespace osb {
+namespace {
+
+// stats[0] += sum g^2 ; stats[1] = 1 if any element is non-finite
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ stats) {
+  float acc = 0.f;
+  bool bad = false;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = g4[i];
+    acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    acc += g[i] * g[i];
+  bad = !isfinite(acc);
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  __shared__ int sbad;
+  if (threadIdx.x == 0) sbad = 0;
+  __syncthreads();
+  if (bad) sbad = 1;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(stats, s);
+    if (sbad || !isfinite(s)) stats[1] = 1.f;
+  }
+}
+
+struct AdamArgs {
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, inv_scale;
+};
+
+// torch.optim.AdamW (decoupled weight decay) preceded by clip_grad_norm_(max_norm) on the unscaled gradient:
+//   total = sqrt(stats[0]) * inv_scale ; coef = min(1, max_norm / (total + 1e-6)) ; g = g * inv_scale * coef
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// The whole update is skipped when the gradient holds a non-finite value (stats[1] != 0).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+             const float* __restrict__ stats, AdamArgs a) {
+  if (stats[1] != 0.f) return;
+  const float total = sqrtf(stats[0]) * a.inv_scale;
+  float coef = a.max_norm > 0.f ? a.max_norm / (total + 1e-6f) : 1.f;
+  coef = fminf(coef, 1.f) * a.inv_scale;
+  const float decay = 1.f - a.lr * a.weight_decay;
+  const float step = a.lr / a.bc1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * decay;
+    const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
+    const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
+    pi -= step * mi / (sqrtf(vi) / a.bc2_sqrt + a.eps);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+}  // namespace
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" int osb_grad_sumsq(const float* g, int64_t n, float* stats, void* stream) {
+  OSB_REQUIRE(g && stats, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0, OSB_ERR_SHAPE);
+  OSB_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, OSB_ERR_ALIGN);
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, stats);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int64_t step, float max_norm, float inv_scale, void* stream) {
+  OSB_REQUIRE(p && g && m && v && stats, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0 && step > 0, OSB_ERR_SHAPE);
+  AdamArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  a.bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  a.max_norm = max_norm; a.inv_scale = inv_scale;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, stats, a);
+  count_launch();
+  return launch_status();
+}

@@ -187,7 +187,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 // variance embedding: out = (x + bias + conv1d(val; 1->C, k taps, same)) * keep
 // ------------------------------------------------------------------------------------------
 __global__ void variance_embed_kernel(const float* __restrict__ x, const float* __restrict__ val, const float* __restrict__ w /*(C,k)*/,
-                                      const float* __restrict__ bias, const uint8_t* __restrict__ pad_mask, float* __restrict__ out_f32,
+                                      const float* __restrict__ bias, const uint8_t* __restrict__ pad_mask,
+                                      const float* __restrict__ emb_scale, float* __restrict__ out_f32,
                                       __half* __restrict__ out_h16, int B, int T, int C, int ksize, int split) {
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= B * T) return;
@@ -203,6 +204,7 @@ __global__ void variance_embed_kernel(const float* __restrict__ x, const float* 
   for (int c = lane; c < C; c += 32) {
     float acc = bias[c];
     for (int j = 0; j < ksize; ++j) acc = fmaf(w[c * ksize + j], v[j], acc);
+    if (emb_scale != nullptr) acc *= emb_scale[static_cast<long long>(row) * C + c];  // dropout on the embedding branch
     const float y = (x[static_cast<long long>(row) * C + c] + acc) * keep;
     if (out_f32 != nullptr) out_f32[static_cast<long long>(row) * C + c] = y;
     if (out_h16 != nullptr) {
@@ -435,13 +437,13 @@ extern "C" int osb_layernorm(const float* x, const float* w, const float* b, flo
 }
 
 extern "C" int osb_variance_embed(const float* x, const float* val, const float* w, const float* bias, const uint8_t* pad_mask,
-                                  float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize, int32_t split,
+                                  const float* emb_scale, float* out_f32, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t ksize, int32_t split,
                                   void* stream) {
   OSB_REQUIRE(x && val && w && bias && (out_f32 || out_h16), OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && C > 0 && ksize > 0 && ksize <= 16 && (ksize & 1), OSB_ERR_SHAPE);
   const int rows = B * T;
   variance_embed_kernel<<<(rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, val, w, bias, pad_mask, out_f32, static_cast<__half*>(out_h16), B, T, C, ksize, split);
+      x, val, w, bias, pad_mask, emb_scale, out_f32, static_cast<__half*>(out_h16), B, T, C, ksize, split);
   count_launch();
   return launch_status();
 }

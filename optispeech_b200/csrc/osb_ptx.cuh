@@ -221,6 +221,17 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Counter-based dropout: element `idx` of the tensor tagged `seed` is kept with probability 1-p and scaled by
+// 1/(1-p).  Stateless (splitmix64 finaliser of seed + idx), so the backward pass regenerates the forward mask.
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, unsigned long long idx, float p, float inv_keep) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : inv_keep;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -69,6 +69,35 @@ def generator_partial(cfg: dict):
     )
 
 
+def build_model(cfg: dict | None = None, train_args: dict | None = None, text_processor=None, max_steps: int = 2_000_000):
+    """OptiSpeech with the defaults of configs/model/optispeech.yaml (AdamW 2e-4 / (0.8, 0.99) / 1e-2, cosine warm-up 1000)."""
+    from transformers import get_cosine_schedule_with_warmup
+
+    from .model import OptiSpeech
+    from .model.vocoder.wavenext.disc import VocosDiscriminator
+
+    cfg = cfg or DEFAULT_MODEL
+    targs = dict(cache_generator_outputs=True, gradient_clip_val=10, gradient_accumulate_batches=None, pretraining_steps=1000,
+                 evaluate_periodicity=False, evaluate_utmos=False, evaluate_pesq=False)
+    targs.update(train_args or {})
+    fe = SimpleNamespace(**cfg["feature_extractor"])
+    data_args = SimpleNamespace(name="synthetic", num_speakers=cfg["num_speakers"], text_processor=text_processor, feature_extractor=fe,
+                                batch_size=32, data_statistics=None)
+    model = OptiSpeech(
+        dim=cfg["dim"],
+        generator=generator_partial(cfg),
+        vocoder=partial(WaveNeXt, **cfg["vocoder"]),
+        discriminator=partial(VocosDiscriminator, loss_coeffs=SimpleNamespace(**cfg["disc_loss_coeffs"])),
+        train_args=SimpleNamespace(**targs),
+        data_args=data_args,
+        inference_args=SimpleNamespace(d_factor=1.1, p_factor=1.6, e_factor=1.2),
+        optimizer=partial(torch.optim.AdamW, lr=2e-4, betas=[0.8, 0.99], weight_decay=1e-2),
+        scheduler=partial(get_cosine_schedule_with_warmup, num_warmup_steps=1000, num_training_steps=-1),
+    )
+    model.max_steps = max_steps
+    return model
+
+
 def build_generator(cfg: dict | None = None) -> OptiSpeechGenerator:
     cfg = cfg or DEFAULT_MODEL
     fe = SimpleNamespace(**cfg["feature_extractor"])

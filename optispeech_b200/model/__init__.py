@@ -1,0 +1,1 @@
+from .optispeech import OptiSpeech

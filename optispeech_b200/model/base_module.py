@@ -1,0 +1,238 @@
+"""Training-step orchestration without Lightning.
+
+Restates optispeech/model/base_lightning_module.py:24-186,294-303 (reference @ 3bdde20) in plain PyTorch:
+manual optimisation of generator and discriminator, gradient-accumulation scaling, clip-by-norm + optimizer +
+scheduler step, generator pre-training gate.  Lightning's services are replaced by small equivalents with the
+same names (`optimizers`, `lr_schedulers`, `toggle_optimizer`, `manual_backward`, `clip_gradients`, `log_dict`),
+so a `lightning.Trainer` could still drive the module (it only needs `training_step` / `configure_optimizers`).
+
+Departures, all to keep the hot loop free of host synchronisation:
+  * logged values stay on the device (`self.logged`), nothing calls .item() per step;
+  * the ground-truth waveform crop is a device gather (the reference slices a numpy array per sample, :38-43);
+  * `cache_generator_outputs=True` is honoured with `wav_hat.detach()` for the discriminator turn: the reference
+    hands over the attached tensor, which would back-propagate through an already-freed graph (:112-119,161).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from ..optim import FlatAdamW
+
+
+class _FitLoopState:
+    def __init__(self):
+        self.total_batch_idx = 0
+
+
+class BaseModule(nn.Module):
+    """The subset of LightningModule behaviour the reference relies on."""
+
+    def __init__(self):
+        super().__init__()
+        self.hparams = SimpleNamespace()
+        self.automatic_optimization = False
+        self.trainer: Any = None
+        self.logged: Dict[str, torch.Tensor] = {}
+        self._optimizers = None
+        self._schedulers = None
+        self._fit = _FitLoopState()
+        self.loss_scale = 1024.0  # static loss scale for the fp16 tensor-core operands of the backward pass
+        self.ckpt_loaded_epoch = -1
+
+    # -- Lightning-compatible helpers ------------------------------------------------------------
+    def save_hyperparameters(self, hparams: Dict[str, Any]):
+        self.hparams = SimpleNamespace(**hparams)
+
+    @property
+    def device(self) -> torch.device:
+        try:
+            return next(self.parameters()).device
+        except StopIteration:
+            return torch.device("cpu")
+
+    def optimizers(self):
+        if self._optimizers is None:
+            opts, scheds = self.configure_optimizers()
+            self._optimizers = opts
+            self._schedulers = [s["scheduler"] if isinstance(s, dict) else s for s in scheds]
+        return self._optimizers
+
+    def lr_schedulers(self):
+        self.optimizers()
+        return self._schedulers
+
+    def toggle_optimizer(self, opt):
+        """Freeze every parameter the optimizer does not own (Lightning semantics)."""
+        owned = {id(p) for g in opt.param_groups for p in g["params"]}
+        self._toggled = []
+        for p in self.parameters():
+            if id(p) not in owned and p.requires_grad:
+                p.requires_grad_(False)
+                self._toggled.append(p)
+
+    def untoggle_optimizer(self, opt):
+        for p in getattr(self, "_toggled", []):
+            p.requires_grad_(True)
+        self._toggled = []
+
+    def manual_backward(self, loss, **kwargs):
+        (loss * self.loss_scale).backward(**kwargs)
+
+    def clip_gradients(self, opt, gradient_clip_val=None, gradient_clip_algorithm="norm"):
+        """Recorded and applied inside the fused optimizer step (osb_adamw_step clips by the global norm)."""
+        assert gradient_clip_algorithm == "norm"
+        if isinstance(opt, FlatAdamW):
+            opt.max_grad_norm = float(gradient_clip_val or 0.0)
+        elif gradient_clip_val:
+            params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
+            for p in params:
+                p.grad.div_(self.loss_scale)
+            torch.nn.utils.clip_grad_norm_(params, gradient_clip_val)
+
+    def log_dict(self, values: Dict[str, Any], **kwargs):
+        for k, v in values.items():
+            self.logged[k] = v.detach() if isinstance(v, torch.Tensor) else v
+
+    @property
+    def global_step(self) -> int:
+        """Batches processed, divided by the accumulation factor (reference :294-303)."""
+        total = self.trainer.fit_loop.total_batch_idx if self.trainer is not None else self._fit.total_batch_idx
+        acc = self.train_args.gradient_accumulate_batches
+        return int(total // acc) if acc is not None else int(total)
+
+    def on_load_checkpoint(self, checkpoint: Dict[str, Any]) -> None:
+        self.ckpt_loaded_epoch = checkpoint.get("epoch", -1)
+
+    # -- reference training logic -------------------------------------------------------------------
+    def _process_batch(self, batch, vocoder_grad: bool = True):
+        dev = self.device
+        sids, lids = batch.get("sids"), batch.get("lids")
+        gen_outputs = self.generator(
+            x=batch["x"].to(dev), x_lengths=batch["x_lengths"].to(dev), mel=batch["mel"].to(dev),
+            mel_lengths=batch["mel_lengths"].to(dev), pitches=batch["pitches"].to(dev), energies=batch["energies"].to(dev),
+            sids=sids.to(dev) if sids is not None else None, lids=lids.to(dev) if lids is not None else None,
+        )
+        seg = gen_outputs["segment_size"] * self.hop_length
+        wav = batch["wav"]
+        wav = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
+        wav = wav.to(dev, non_blocking=True)
+        start = gen_outputs["start_idx"] * self.hop_length
+        pos = start.view(-1, 1) + torch.arange(seg, device=dev).view(1, -1)
+        gen_outputs["wav"] = torch.gather(wav, 1, pos.clamp(max=wav.shape[1] - 1)).type_as(gen_outputs["wav_hat"])
+        return gen_outputs
+
+    def configure_optimizers(self):
+        gen_params = [{"params": list(self.generator.parameters())}]
+        disc_params = [{"params": list(self.discriminator.parameters())}]
+        make = self.hparams.optimizer
+        target = getattr(make, "func", make)
+        if target is torch.optim.AdamW:  # the fused flat-bucket implementation, same hyper-parameters
+            kw = dict(getattr(make, "keywords", {}))
+            kw["betas"] = tuple(kw.get("betas", (0.9, 0.999)))
+            ws = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+            opt_gen = FlatAdamW(gen_params, loss_scale=self.loss_scale, world_size=ws, **kw)
+            opt_disc = FlatAdamW(disc_params, loss_scale=self.loss_scale, world_size=ws, **kw)
+        else:
+            opt_gen, opt_disc = make(gen_params), make(disc_params)
+        max_steps = (self.trainer.max_steps if self.trainer is not None else getattr(self, "max_steps", 2_000_000)) // 2
+        acc = self.train_args.gradient_accumulate_batches
+        if acc is not None:
+            max_epochs = getattr(self.trainer, "max_epochs", None) if self.trainer is not None else None
+            max_steps = math.ceil(max_steps / acc) * max(max_epochs if max_epochs is not None else -1, 1)
+        sched = self.hparams.scheduler
+        if hasattr(sched, "keywords") and "num_training_steps" in sched.keywords:
+            sched.keywords["num_training_steps"] = max_steps
+        # reference :66-67 passes getattr("self", ...) (a string), i.e. last_epoch is always -1
+        scheduler_gen = sched(opt_gen, last_epoch=-1)
+        scheduler_disc = sched(opt_disc, last_epoch=-1)
+        return ([opt_gen, opt_disc],
+                [{"scheduler": scheduler_gen, "interval": "step"}, {"scheduler": scheduler_disc, "interval": "step"}])
+
+    def training_step(self, batch, batch_idx, **kwargs):
+        acc = self.train_args.gradient_accumulate_batches
+        if acc is not None:
+            loss_scaling_factor = float(acc)
+            should_apply = (batch_idx + 1) % acc == 0
+        else:
+            loss_scaling_factor, should_apply = 1.0, True
+        train_discriminator = self.global_step >= self.train_args.pretraining_steps
+        opt_g, opt_d = self.optimizers()
+        sched_g, sched_d = self.lr_schedulers()
+
+        self.toggle_optimizer(opt_g)
+        loss_g, wav_outputs = self.training_step_g(batch, train_discriminator=train_discriminator)
+        loss_g = loss_g / loss_scaling_factor
+        if should_apply:
+            opt_g.zero_grad()
+        self.manual_backward(loss_g)
+        self.clip_gradients(opt_g, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
+        if should_apply:
+            opt_g.step()
+            sched_g.step()
+        self.untoggle_optimizer(opt_g)
+        self._fit.total_batch_idx += 1
+        if not train_discriminator:
+            return
+
+        self.toggle_optimizer(opt_d)
+        if not self.train_args.cache_generator_outputs:
+            wav_outputs = None
+        loss_d = self.training_step_d(batch, wav_outputs=wav_outputs) / loss_scaling_factor
+        if should_apply:
+            opt_d.zero_grad()
+        self.manual_backward(loss_d)
+        self.clip_gradients(opt_d, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
+        if should_apply:
+            opt_d.step()
+            sched_d.step()
+        self.untoggle_optimizer(opt_d)
+
+    def training_step_g(self, batch, train_discriminator):
+        log_outputs = {}
+        if train_discriminator:
+            gen_outputs = self._process_batch(batch)
+        else:
+            # pre-training: the vocoder output feeds no loss, so its autograd graph is not built
+            self.generator.vocoder_needs_grad = False
+            try:
+                gen_outputs = self._process_batch(batch)
+            finally:
+                self.generator.vocoder_needs_grad = True
+        gen_am_loss = gen_outputs["loss"]
+        log_outputs.update({
+            "total_loss/train_am_loss": gen_am_loss,
+            "gen_subloss/train_alighn_loss": gen_outputs["align_loss"],
+            "gen_subloss/train_duration_loss": gen_outputs["duration_loss"],
+            "gen_subloss/train_pitch_loss": gen_outputs["pitch_loss"],
+            "gen_subloss/train_energy_loss": gen_outputs["energy_loss"],
+        })
+        wav, wav_hat = gen_outputs["wav"], gen_outputs["wav_hat"]
+        if train_discriminator:
+            gen_adv_loss, log_dict = self.discriminator.forward_gen(wav, wav_hat)
+            log_outputs["total_loss/train_gen_adv_loss"] = gen_adv_loss
+            log_outputs.update({f"gen_adv_loss/train_{k}": v for k, v in log_dict.items()})
+        else:
+            gen_adv_loss = 0.0
+        loss = gen_am_loss + gen_adv_loss
+        log_outputs["total_loss/generator"] = loss
+        self.log_dict(log_outputs)
+        return loss, (wav.detach(), wav_hat.detach())
+
+    def training_step_d(self, batch, wav_outputs=None):
+        if wav_outputs is None:
+            with torch.no_grad():
+                gen_outputs = self._process_batch(batch)
+            wav, wav_hat = gen_outputs["wav"], gen_outputs["wav_hat"]
+        else:
+            wav, wav_hat = wav_outputs
+        loss, log_dict = self.discriminator.forward_disc(wav, wav_hat)
+        log_outputs = {"total_loss/discriminator": loss}
+        log_outputs.update({f"discriminator/{k}": v for k, v in log_dict.items()})
+        self.log_dict(log_outputs)
+        return loss

@@ -101,8 +101,10 @@ class VariancePredictor(nn.Module):
             params = []
             for layer in self.conv:
                 params += [layer[0].weight, layer[0].bias, layer[2].weight, layer[2].bias]
-            return VariancePredictorFn.apply(x, mask_u8, self.kernel_size, self.conv[0][2].eps, self.linear.weight, self.linear.bias,
-                                             *params)
+            p_drop = float(self.conv[0][3].p) if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64)) if p_drop > 0.0 else 0  # CPU generator: no device sync
+            return VariancePredictorFn.apply(x, mask_u8, self.kernel_size, self.conv[0][2].eps, p_drop, seed, self.linear.weight,
+                                             self.linear.bias, *params)
         split = precision.use_split(self.training)
         return self.forward_h16(ops.to_h16(x.contiguous(), split=split), mask_u8, split)
 
@@ -146,8 +148,11 @@ class PitchPredictor(nn.Module):
             from ....autograd import VarianceEmbedFn
 
             preds = self.predictor(x, padding_mask)
-            conv = self.embed[0]
-            out = VarianceEmbedFn.apply(x, target.contiguous(), conv.weight, conv.bias, mask_u8)
+            conv, drop = self.embed[0], self.embed[1]
+            emb_scale = None
+            if self.training and drop.p > 0.0:  # Dropout on the embedding branch (core.py:143-150)
+                emb_scale = torch.empty(x.shape, device=x.device, dtype=torch.float32).bernoulli_(1.0 - drop.p).div_(1.0 - drop.p)
+            out = VarianceEmbedFn.apply(x, target.contiguous(), conv.weight, conv.bias, mask_u8, emb_scale)
             return out, preds
         split = precision.use_split(self.training)
         preds = self.predictor.forward_h16(ops.to_h16(x.contiguous(), split=split), mask_u8, split)

@@ -168,7 +168,11 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
         segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
         _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt
 
-    wav_hat = gen.vocoder.forward_train(segment)
+    if getattr(gen, "vocoder_needs_grad", True):
+        wav_hat = gen.vocoder.forward_train(segment)
+    else:
+        with torch.no_grad():
+            wav_hat = gen.vocoder.forward_train(segment)
 
     d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
     fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)

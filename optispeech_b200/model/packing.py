@@ -19,7 +19,8 @@ class PackedCache:
 
     @staticmethod
     def _key(params: Iterable[torch.Tensor]) -> tuple:
-        return tuple((p.data_ptr(), p._version, p.device.index) for p in params)
+        # _osb_epoch is bumped by FlatAdamW, whose kernels update parameter storage behind autograd's version counter
+        return tuple((p.data_ptr(), p._version, p.device.index, getattr(p, "_osb_epoch", 0)) for p in params)
 
     def get(self, name: str, params: Iterable[torch.Tensor], build: Callable[[], object]):
         params = list(params)

@@ -44,7 +44,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -81,6 +81,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.ln_w, d.ln_b, d.ln_eps = _ptr(ln_w), _ptr(ln_b), ln_eps
     d.dot_w, d.dot_b, d.out_dot = _ptr(dot_w), _ptr(dot_b), _ptr(out_dot)
     d.aux_in_h16, d.row_stat = _ptr(aux_in), _ptr(row_stat)
+    d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
     _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
     return out, aux, out_dot
 
@@ -127,13 +128,13 @@ def layernorm(x, w, b, eps: float, f32: bool = True, h16: bool = False, split: b
     return o32, o16
 
 
-def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False, split: bool = False):
+def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False, split: bool = False, emb_scale=None):
     B, T, Cc = x.shape
     k = w.shape[-1]
     o32 = torch.empty_like(x) if f32 else None
     o16 = _h16_like(x, split) if h16 else None
-    _lib.check(_lib.load().osb_variance_embed(_ptr(_f32(x)), _ptr(_f32(val)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(pad_mask), _ptr(o32),
-                                              _ptr(o16), B, T, Cc, k, int(split), _stream()), "osb_variance_embed")
+    _lib.check(_lib.load().osb_variance_embed(_ptr(_f32(x)), _ptr(_f32(val)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(pad_mask), _ptr(emb_scale),
+                                              _ptr(o32), _ptr(o16), B, T, Cc, k, int(split), _stream()), "osb_variance_embed")
     return o32, o16
 
 
@@ -249,14 +250,14 @@ def layernorm_bwd(dy, x, w, eps: float):
     return dx, dw, db
 
 
-def predictor_tail_bwd(d_out, pad_mask, r_h16, ln_w, ln_b, lin_w, eps: float):
+def predictor_tail_bwd(d_out, pad_mask, r_h16, ln_w, ln_b, lin_w, eps: float, dropout_p: float = 0.0, dropout_seed: int = 0):
     Cc = r_h16.shape[-1]
     rows = r_h16.numel() // Cc
     g = torch.empty(r_h16.shape, device=r_h16.device, dtype=torch.float16)
     dlin_w, dlin_b, dln_w, dln_b = _zeros((Cc,), r_h16), _zeros((1,), r_h16), _zeros((Cc,), r_h16), _zeros((Cc,), r_h16)
     _lib.check(_lib.load().osb_predictor_tail_bwd(_ptr(_f32(d_out)), _ptr(pad_mask), _ptr(r_h16), _ptr(ln_w), _ptr(ln_b), _ptr(lin_w),
                                                   _ptr(g), _ptr(dlin_w), _ptr(dlin_b), _ptr(dln_w), _ptr(dln_b), rows, Cc, eps,
-                                                  _stream()), "osb_predictor_tail_bwd")
+                                                  float(dropout_p), int(dropout_seed), _stream()), "osb_predictor_tail_bwd")
     return g, dlin_w, dlin_b, dln_w, dln_b
 
 
@@ -269,12 +270,12 @@ def ln_param_grad(gy_h16, r_h16, ln_w, eps: float):
     return dln_w, dln_b
 
 
-def variance_embed_bwd(dout, val, pad_mask, ksize: int, want_dx: bool = True):
+def variance_embed_bwd(dout, val, pad_mask, ksize: int, want_dx: bool = True, emb_scale=None):
     B, T, Cc = dout.shape
     dx = torch.empty_like(dout) if want_dx else None
     dw, db = _zeros((Cc, ksize), dout), _zeros((Cc,), dout)
-    _lib.check(_lib.load().osb_variance_embed_bwd(_ptr(_f32(dout)), _ptr(_f32(val)), _ptr(pad_mask), _ptr(dx), _ptr(dw), _ptr(db), B, T, Cc,
-                                                  ksize, _stream()), "osb_variance_embed_bwd")
+    _lib.check(_lib.load().osb_variance_embed_bwd(_ptr(_f32(dout)), _ptr(_f32(val)), _ptr(pad_mask), _ptr(emb_scale), _ptr(dx), _ptr(dw), _ptr(db),
+                                                  B, T, Cc, ksize, _stream()), "osb_variance_embed_bwd")
     return dx, dw, db
 
 

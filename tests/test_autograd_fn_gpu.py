@@ -89,7 +89,7 @@ def test_variance_predictor_fn(cuda_device, L, Cmid, k, needs_dx):
     layer_params = []
     for i in range(L):
         layer_params += [sd[f"p.conv.{i}.0.weight"], sd[f"p.conv.{i}.0.bias"], sd[f"p.conv.{i}.2.weight"], sd[f"p.conv.{i}.2.bias"]]
-    y = VariancePredictorFn.apply(x, pad.to(torch.uint8), k, 1e-12, sd["p.linear.weight"], sd["p.linear.bias"], *layer_params)
+    y = VariancePredictorFn.apply(x, pad.to(torch.uint8), k, 1e-12, 0.0, 0, sd["p.linear.weight"], sd["p.linear.bias"], *layer_params)
     wrt = ([x] if needs_dx else []) + [sd["p.linear.weight"], sd["p.linear.bias"]] + layer_params
     grads = torch.autograd.grad(y, wrt, dy)
     yr = O.variance_predictor(sd, "p", x, pad, ps)
@@ -177,3 +177,51 @@ def test_wavenext_head_fn(cuda_device):
     rgrads = torch.autograd.grad(yr, (x, w1, b1, w2), dy)
     # elements whose pre-clip value sits within fp16 operand error of +-1 may flip the clip gate; exclude nothing, use a norm bound
     _check([("y", y, yr)] + list(zip(["dx", "dw1", "db1", "dw2"], grads, rgrads)), 2e-2)
+
+
+def test_predictor_dropout_mask_is_consistent_between_forward_and_backward(cuda_device):
+    """Train-mode dropout is counter-based (no stored mask): the backward pass must regenerate exactly the forward mask.
+    The predictor output is linear in the final Linear's weight and affine-linear (to first order) in the LayerNorm biases,
+    so directional finite differences of the forward must match <grad, direction> from the hand-written backward."""
+    from optispeech_b200.autograd import VariancePredictorFn
+
+    g = torch.Generator().manual_seed(9)
+    B, T, C, Cmid, k, L, p, seed = 2, 50, 256, 256, 3, 3, 0.5, 12345
+    dev = cuda_device
+    params = []
+    for i in range(L):
+        cin = C if i == 0 else Cmid
+        params += [torch.randn(Cmid, cin, k, generator=g) / (cin * k) ** 0.5, 0.1 * torch.randn(Cmid, generator=g),
+                   1 + 0.1 * torch.randn(Cmid, generator=g), 0.1 * torch.randn(Cmid, generator=g)]
+    params = [t.to(dev).requires_grad_(True) for t in params]
+    lin_w = (torch.randn(1, Cmid, generator=g) / Cmid ** 0.5).to(dev).requires_grad_(True)
+    lin_b = torch.zeros(1, device=dev, requires_grad=True)
+    x = torch.randn(B, T, C, generator=g).to(dev)
+    pad = torch.zeros(B, T, dtype=torch.uint8, device=dev)
+    dy = torch.randn(B, T, generator=g).to(dev)
+
+    def f(lw=lin_w, ps=params):
+        return VariancePredictorFn.apply(x, pad, k, 1e-12, p, seed, lw, lin_b, *ps)
+
+    y = f()
+    y_eval = VariancePredictorFn.apply(x, pad, k, 1e-12, 0.0, 0, lin_w, lin_b, *params)
+    assert rel(y, y_eval) > 0.1, "dropout had no effect"
+    assert torch.equal(y, f()), "same seed must give the same mask"
+    grads = torch.autograd.grad(y, [lin_w] + params, dy)
+    # exact linearity in lin_w
+    v = torch.randn_like(lin_w)
+    fd = ((f(lw=lin_w + v) - y) * dy).sum()
+    an = (grads[0] * v).sum()
+    print(f"  lin_w directional: fd {float(fd):.5f} analytic {float(an):.5f}")
+    assert abs(float(fd - an)) <= 2e-3 * max(1.0, abs(float(an)))
+    # first-order check through the inner dropout layers: LayerNorm bias of layer 0 and layer 1
+    for li in (0, 1):
+        idx = 4 * li + 3
+        v = torch.randn_like(params[idx])
+        eps = 2e-2
+        ps_p = list(params); ps_p[idx] = params[idx] + eps * v
+        ps_m = list(params); ps_m[idx] = params[idx] - eps * v
+        fd = ((f(ps=ps_p) - f(ps=ps_m)) * dy).sum() / (2 * eps)
+        an = (grads[1 + idx] * v).sum()
+        print(f"  ln_b[{li}] directional: fd {float(fd):.5f} analytic {float(an):.5f}")
+        assert abs(float(fd - an)) <= 5e-2 * max(1.0, abs(float(an)))

@@ -1,0 +1,84 @@
+"""The public training surface on the GPU: OptiSpeech.training_step (reference base_lightning_module.py:78-126)
+in the generator pre-training phase and in the GAN phase, flat-bucket AdamW against torch.optim.AdamW."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.spec import ModelSpec, deterministic_state_dict, generator_shapes
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(spec, B, Tx, Tm, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    xl = torch.randint(Tx // 2, Tx + 1, (B,), generator=g); xl[0] = Tx
+    x = torch.randint(1, 159, (B, Tx), generator=g) * (torch.arange(Tx)[None] < xl[:, None])
+    ml = torch.clamp((xl.float() * (Tm / Tx)).round().long(), max=Tm); ml[0] = Tm
+    mm = torch.arange(Tm)[None] < ml[:, None]
+    return dict(x=x, x_lengths=xl, mel=torch.randn(B, spec.n_feats, Tm, generator=g) * mm[:, None, :], mel_lengths=ml,
+                pitches=torch.randn(B, Tm, generator=g) * mm, energies=torch.randn(B, Tm, generator=g) * mm,
+                wav=(torch.rand(B, Tm * spec.hop_length, generator=g) * 2 - 1).numpy().astype(np.float32), sids=None, lids=None)
+
+
+def test_flat_adamw_matches_torch_adamw(cuda_device):
+    from optispeech_b200.optim import FlatAdamW
+
+    g = torch.Generator().manual_seed(0)
+    shapes = [(256, 1024), (1024,), (7,), (33, 5)]
+    ps = [torch.randn(s, generator=g).to(cuda_device) for s in shapes]
+    a = [torch.nn.Parameter(p.clone()) for p in ps]
+    b = [torch.nn.Parameter(p.clone()) for p in ps]
+    unused = torch.nn.Parameter(torch.ones(5, device=cuda_device))   # never gets a gradient: must stay untouched
+    oa = FlatAdamW([{"params": a + [unused]}], lr=2e-4, betas=(0.8, 0.99), weight_decay=1e-2, max_grad_norm=10.0, loss_scale=512.0)
+    ob = torch.optim.AdamW(b, lr=2e-4, betas=(0.8, 0.99), weight_decay=1e-2)
+    for it in range(5):
+        grads = [torch.randn(s, generator=g).to(cuda_device) * (50.0 if it == 2 else 1.0) for s in shapes]
+        oa.zero_grad(); ob.zero_grad()
+        for p, q, gr in zip(a, b, grads):
+            if p.grad is None:
+                p.grad = (gr * 512.0).clone()
+            else:
+                p.grad.add_(gr * 512.0)
+            q.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_(b, 10.0)
+        oa.step(); ob.step()
+        for p, q in zip(a, b):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), it
+    assert torch.equal(unused.detach(), torch.ones(5, device=cuda_device))
+    # non-finite gradient: the step is skipped
+    before = [p.detach().clone() for p in a]
+    oa.zero_grad()
+    a[0].grad.fill_(float("inf"))
+    oa.step()
+    for p, q in zip(a, before):
+        assert torch.equal(p.detach(), q)
+
+
+def test_training_step_pretraining_and_gan_phase(cuda_device):
+    from optispeech_b200.factory import build_model, model_config_from_spec
+
+    spec = ModelSpec()
+    torch.manual_seed(1234)
+    model = build_model(model_config_from_spec(spec), train_args=dict(pretraining_steps=2))
+    model.generator.load_state_dict(deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0))
+    model = model.to(cuda_device).train()
+    batch = _batch(spec, 2, 40, 170)
+    dec_before = model.generator.decoder.convnext[0].pwconv1.weight.detach().clone()
+    enc_before = model.generator.encoder.convnext[0].pwconv1.weight.detach().clone()
+    voc_before = model.generator.vocoder.backbone.convnext[0].pwconv1.weight.detach().clone()
+    losses = []
+    for i in range(4):   # steps 0,1: generator pre-training; steps 2,3: GAN phase (discriminators on stock PyTorch)
+        model.training_step(batch, i)
+        losses.append(float(model.logged["total_loss/generator"]))
+        assert np.isfinite(losses[-1])
+        if i == 1:
+            assert torch.equal(voc_before, model.generator.vocoder.backbone.convnext[0].pwconv1.weight.detach()), \
+                "vocoder must not move during pre-training"
+    print("generator losses:", losses)
+    assert "total_loss/discriminator" in model.logged and np.isfinite(float(model.logged["total_loss/discriminator"]))
+    assert not torch.equal(enc_before, model.generator.encoder.convnext[0].pwconv1.weight.detach())
+    assert not torch.equal(voc_before, model.generator.vocoder.backbone.convnext[0].pwconv1.weight.detach())
+    # the decoder never receives a gradient at the reference commit (vocoder input is detached) -> untouched, no weight decay
+    assert torch.equal(dec_before, model.generator.decoder.convnext[0].pwconv1.weight.detach())
+    g_opt, d_opt = model.optimizers()
+    assert np.isfinite(g_opt.grad_norm()) and np.isfinite(d_opt.grad_norm())
