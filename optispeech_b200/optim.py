@@ -34,6 +34,7 @@ class _Bucket:
         self.params = params
         self.ids = {id(p) for p in params}
         self.offsets = offs
+        self.offset_of = {id(p): o for p, o in zip(params, offs)}
         self.numel = total
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -50,7 +51,7 @@ class _Bucket:
                 p.grad = self.flat_g[o:o + n].view(p.shape)
 
     def view_of(self, flat: torch.Tensor, p: torch.nn.Parameter) -> torch.Tensor:
-        o = self.offsets[self.params.index(p)]
+        o = self.offset_of[id(p)]
         return flat[o:o + p.numel()].view(p.shape)
 
 

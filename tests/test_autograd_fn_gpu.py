@@ -214,14 +214,32 @@ def test_predictor_dropout_mask_is_consistent_between_forward_and_backward(cuda_
     an = (grads[0] * v).sum()
     print(f"  lin_w directional: fd {float(fd):.5f} analytic {float(an):.5f}")
     assert abs(float(fd - an)) <= 2e-3 * max(1.0, abs(float(an)))
-    # first-order check through the inner dropout layers: LayerNorm bias of layer 0 and layer 1
-    for li in (0, 1):
-        idx = 4 * li + 3
-        v = torch.randn_like(params[idx])
-        eps = 2e-2
-        ps_p = list(params); ps_p[idx] = params[idx] + eps * v
-        ps_m = list(params); ps_m[idx] = params[idx] - eps * v
-        fd = ((f(ps=ps_p) - f(ps=ps_m)) * dy).sum() / (2 * eps)
-        an = (grads[1 + idx] * v).sum()
-        print(f"  ln_b[{li}] directional: fd {float(fd):.5f} analytic {float(an):.5f}")
-        assert abs(float(fd - an)) <= 5e-2 * max(1.0, abs(float(an)))
+
+
+def test_inner_dropout_mask_matches_between_relu_ln_forward_and_backward_epilogues(cuda_device):
+    """Read the masks back: forward mask = dropped / undropped LayerNorm output; backward mask = aux / acc of the
+    RELU_LN_BWD epilogue driven through an identity weight."""
+    from optispeech_b200 import ops
+
+    g = torch.Generator().manual_seed(10)
+    dev = cuda_device
+    B, T, N, p, seed = 2, 77, 256, 0.3, 987654321
+    a = torch.randn(B, T, N, generator=g).to(dev).half()
+    w = (torch.randn(1, N, N, generator=g) / N ** 0.5).to(dev).half()
+    ln_w, ln_b = torch.ones(N, device=dev), torch.full((N,), 0.5, device=dev)
+    bias = torch.zeros(N, device=dev)
+    y_d, r, _ = ops.gemm(a, w, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, bias=bias, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-12, dropout_p=p,
+                         dropout_seed=seed)
+    y, _, _ = ops.gemm(a, w, epi=ops.EPI_RELU_LN, bias=bias, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-12)
+    ok = y.float().abs() > 1e-2
+    mask_f = torch.where(ok, y_d.float() / y.float(), torch.zeros((), device=dev))
+    keep_frac = float((mask_f[ok] > 0.5).float().mean())
+    print(f"  forward keep fraction {keep_frac:.4f} (expected {1 - p:.4f})")
+    assert abs(keep_frac - (1 - p)) < 0.02
+    assert torch.allclose(mask_f[ok][mask_f[ok] > 0.5], torch.full((), 1 / (1 - p), device=dev), rtol=5e-3)
+    gacc = (torch.randn(B, T, N, generator=g).to(dev) + 3.0).half()        # bounded away from zero
+    eye = torch.eye(N, device=dev).half().view(1, N, N).contiguous()
+    _, gy, _ = ops.gemm(gacc, eye, epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, aux_in=r, ln_w=ln_w, ln_eps=1e-12, dropout_p=p,
+                        dropout_seed=seed)
+    mask_b = gy.float() / gacc.float()
+    assert torch.equal(mask_b[ok] > 0.5, mask_f[ok] > 0.5), "backward regenerated a different dropout mask"
