@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the OptiSpeech training hot path on B200 (contract: see the build prompt / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (libosb200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm's CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1], SURVEY §8d "S-train"): ConvNeXt configuration, per-GPU batch of 32 synthetic
+utterances, 192 phoneme positions, 864 mel frames (22.05 kHz, hop 256), random-initialised weights.  One step is
+`OptiSpeech.training_step` in the generator pre-training phase (reference base_lightning_module.py:78-110: generator
+forward, acoustic-model loss, backward, clip-by-norm, AdamW, cosine schedule) — the phase whose every kernel belongs
+to this library; the GAN-phase step (discriminators on stock PyTorch) is reported under "variants".
+Metric: mel frames processed per second (sum of mel_lengths over all ranks / step time).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PER_GPU, TX, TM = 32, 192, 864
+SEED = 1234
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workload
+# --------------------------------------------------------------------------------------------------
+def make_batch(B: int, seed: int, n_feats: int = 100, hop: int = 256):
+    g = torch.Generator().manual_seed(seed)
+    x_lengths = torch.randint(TX // 2, TX + 1, (B,), generator=g)
+    x_lengths[0] = TX
+    x = torch.randint(1, 159, (B, TX), generator=g) * (torch.arange(TX)[None] < x_lengths[:, None])
+    mel_lengths = torch.clamp((4.5 * x_lengths.float()).round().long(), max=TM)
+    mel_lengths[0] = TM
+    mmask = torch.arange(TM)[None] < mel_lengths[:, None]
+    mel = torch.randn(B, n_feats, TM, generator=g) * mmask[:, None, :]
+    pitches = torch.randn(B, TM, generator=g) * mmask
+    energies = torch.randn(B, TM, generator=g) * mmask
+    wav = torch.rand(B, TM * hop, generator=g) * 2 - 1
+    return dict(x=x, x_lengths=x_lengths, mel=mel, mel_lengths=mel_lengths, pitches=pitches, energies=energies, wav=wav,
+                sids=None, lids=None)
+
+
+def batch_bytes(batch) -> int:
+    return int(sum(v.numel() * v.element_size() for v in batch.values() if isinstance(v, torch.Tensor)))
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# --------------------------------------------------------------------------------------------------
+class CpuReferenceStep:
+    """generator.forward + acoustic-model loss backward + clip_grad_norm_(10) + AdamW on the host CPU, through the
+    oracle (plain fp32 PyTorch restatement of the reference modules, pinned to the reference by tests/golden)."""
+
+    def __init__(self, sample_b: int):
+        from oracle.spec import ModelSpec, deterministic_state_dict, generator_shapes
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.spec = ModelSpec()
+        sd = deterministic_state_dict(generator_shapes(self.spec), seed=0, frames_per_token=4.5)
+        self.sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        self.opt = torch.optim.AdamW(list(self.sd.values()), lr=2e-4, betas=(0.8, 0.99), weight_decay=1e-2)
+        full = make_batch(B_PER_GPU, SEED)
+        self.batch = {k: (v[:sample_b] if isinstance(v, torch.Tensor) else v) for k, v in full.items()}
+        self.frames = int(self.batch["mel_lengths"].sum())
+        self.sample_b = sample_b
+
+    def step(self):
+        from oracle import model as O
+
+        b = self.batch
+        out = O.generator_forward(self.sd, self.spec, b["x"], b["x_lengths"], b["mel"], b["mel_lengths"], b["pitches"], b["energies"],
+                                  torch.rand(self.sample_b))
+        self.opt.zero_grad()
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_([p for p in self.sd.values() if p.grad is not None], 10.0)
+        self.opt.step()
+        return float(out["loss"].detach())
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    sample_b = 2
+    ref = CpuReferenceStep(sample_b)
+    for _ in range(max(1, min(args.warmup, 2))):
+        ref.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.step()
+    dt = time.perf_counter() - t0
+    value = ref.frames * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"B={sample_b} of the B={B_PER_GPU} batch per step (Tx={TX}, Tm={TM}), fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "mel_frames_per_sec_train_step", "value": value, "unit": "mel-frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ConvNeXt OptiSpeech training_step (generator pre-training phase), LJSpeech-shape: Tx={TX}, Tm={TM}, "
+                               f"22.05 kHz; reference CPU path via the oracle port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                p = [c.strip() for c in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# main arm
+# --------------------------------------------------------------------------------------------------
+def max_over_ranks(ms: float, world: int, dev) -> float:
+    if world <= 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_steps(fn, steps: int, world: int, dev) -> float:
+    """K steps bracketed by barrier + synchronize on both sides; device time from CUDA events, max over ranks."""
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    return max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    from optispeech_b200 import _lib
+    from optispeech_b200.factory import DEFAULT_MODEL, build_model
+
+    lib = _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(lib.osb_check_device(local_rank), "osb_check_device")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    torch.manual_seed(SEED)
+    model = build_model(DEFAULT_MODEL, train_args=dict(pretraining_steps=10 ** 9)).to(dev).train()
+    host_batch = make_batch(B_PER_GPU, SEED + rank)
+    frames_local = int(host_batch["mel_lengths"].sum())
+    frames_all = frames_local
+    if world > 1:
+        t = torch.tensor([frames_local], device=dev, dtype=torch.int64)
+        torch.distributed.all_reduce(t)
+        frames_all = int(t.item())
+    dev_batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
+    pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
+    h2d = batch_bytes(host_batch)
+
+    def step_resident(i):
+        model.training_step(dev_batch, i)
+
+    def step_e2e(i):
+        model.training_step(pinned, i)  # _process_batch copies every tensor host->device
+        return float(model.logged["total_loss/generator"])  # 4-byte device->host read of the step's loss
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed_steps(step_resident, args.steps, world, dev)
+    launches = (_lib.launch_count() - n0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else {}
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed_steps(step_e2e, args.steps, world, dev)
+
+    # ---- per-kernel device times of one step (separate pass; event recording perturbs the step time) ----
+    roofline, top = None, []
+    if rank == 0:
+        with _lib.LaunchProfiler() as prof:
+            step_resident(0)
+        summ = prof.summary()
+        total_ms = sum(a["total_ms"] for a in summ) or 1.0
+        top = [{"kernel": a["key"], "launches": a["launches"], "total_ms": round(a["total_ms"], 4), "share_of_lib_time": round(a["total_ms"] / total_ms, 4),
+                "avg_us": round(a["avg_us"], 2), "tflops": round(a["flops_per_launch"] / (a["avg_us"] * 1e-6) / 1e12, 2) if a["flops"] else None}
+               for a in summ[:12]]
+        dom = next((a for a in summ if a["flops"] > 0), None)
+        if dom is not None:
+            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            achieved = dom["flops_per_launch"] / (dom["avg_us"] * 1e-6) / 1e12
+            roofline = {"bound": "tensor", "kernel": dom["key"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                        "launches_per_step": dom["launches"], "avg_us": dom["avg_us"]}
+
+    # ---- synthesis (SURVEY §8d S-synth-long: B=8 x 512 phonemes, and S-synth-1) ----
+    synth = {}
+    if rank == 0:
+        model.eval()
+        g = torch.Generator().manual_seed(SEED)
+        for name, (B, Tx) in {"long_B8_Tx512": (8, 512), "single_B1_Tx120": (1, 120)}.items():
+            ids = torch.randint(1, 159, (B, Tx), generator=g)
+            lens = torch.full((B,), Tx, dtype=torch.int64)
+            durs = torch.randint(1, 4, (B, Tx), generator=g)  # ~2 frames / phoneme: random-init duration heads give ~1.6
+            ids_pin = ids.pin_memory()
+            for _ in range(3):
+                out = model.generator.synthesise(ids_pin.to(dev, non_blocking=True), lens, durations=durs)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                out = model.generator.synthesise(ids_pin.to(dev, non_blocking=True), lens, durations=durs)  # returns CPU tensors
+            dt = (time.perf_counter() - t0) / reps
+            nsamp = int(out["wav_lengths"].sum())
+            synth[name] = {"audio_samples_per_s_e2e": nsamp / dt, "rtf": dt / (nsamp / 22050.0), "ms": 1e3 * dt,
+                           "frames": int(nsamp // 256), "precision": "fp16x3"}
+        model.train()
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload through the oracle port ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReferenceStep(2)
+        ref.step()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            ref.step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": ref.frames * n / dt, "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"B=2 of the B={B_PER_GPU} batch (Tx={TX}, Tm={TM}), {n} steps after 1 warm-up, oracle port of the reference CPU path (fp32)"}
+
+    if rank == 0:
+        value = frames_all / (ms * 1e-3)
+        line = {
+            "metric": "mel_frames_per_sec_train_step", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"ConvNeXt OptiSpeech training_step, generator pre-training phase (fwd + bwd + clip + AdamW), "
+                                   f"B={B_PER_GPU}/GPU, Tx={TX}, Tm={TM}, 22.05 kHz hop 256, random-init weights, train mode "
+                                   f"(dropout + DropPath on), fp16 tensor-core operands / fp32 accumulate, loss scale 1024",
+                       "parallelism": f"dp{world}", "l2": "no explicit flush: one step streams > 1 GB of activations through HBM (> 126 MB L2)"},
+            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "top_kernels": top,
+            "synthesis": synth,
+        }
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -138,3 +138,72 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().osb_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py's roofline pass): CUDA events on the launching stream around every entry point
+# --------------------------------------------------------------------------------------------------
+class LaunchProfiler:
+    """Wraps the library's entry points so that every call is bracketed by CUDA events recorded on the current stream.
+    Used for ONE separate profiling pass after the timed region (event recording perturbs timing)."""
+
+    def __init__(self):
+        self.records = []  # (name, key, flops, start_event, end_event)
+        self._saved = {}
+
+    def __enter__(self):
+        import torch
+
+        lib = load()
+        for name in exported_symbols():
+            if name in ("osb_version", "osb_strerror", "osb_launch_count", "osb_check_device"):
+                continue
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+
+            def make(fn=fn, name=name):
+                def wrapped(*args):
+                    key, flops = name, 0.0
+                    if name == "osb_gemm":
+                        d = args[0]._obj
+                        split = 3 if (d.flags & FLAG_SPLIT_IN) else 1
+                        key = f"osb_gemm[epi={d.epi},rows={d.B * d.T},N={d.N},K={d.K},taps={d.taps},passes={split}]"
+                        flops = 2.0 * d.B * d.T * d.N * d.K * d.taps
+                    elif name == "osb_gemm_wgrad":
+                        B, T, N, K, taps = args[5], args[6], args[7], args[8], args[9]
+                        key = f"osb_gemm_wgrad[rows={B * T},N={N},K={K},taps={taps}]"
+                        flops = 2.0 * B * T * N * K * taps
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = fn(*args)
+                    e1.record()
+                    self.records.append((name, key, flops, e0, e1))
+                    return rc
+
+                return wrapped
+
+            setattr(lib, name, make())
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        for name, fn in self._saved.items():
+            setattr(lib, name, fn)
+        self._saved = {}
+
+    def summary(self):
+        """-> list of dicts sorted by total device time: key, launches, total_ms, avg_us, flops_per_launch."""
+        import torch
+
+        torch.cuda.synchronize()
+        agg = {}
+        for name, key, flops, e0, e1 in self.records:
+            a = agg.setdefault(key, dict(key=key, name=name, launches=0, total_ms=0.0, flops=0.0))
+            a["launches"] += 1
+            a["total_ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+        out = sorted(agg.values(), key=lambda a: -a["total_ms"])
+        for a in out:
+            a["avg_us"] = 1e3 * a["total_ms"] / a["launches"]
+            a["flops_per_launch"] = a["flops"] / a["launches"]
+        return out
