@@ -73,7 +73,13 @@ typedef enum osb_epilogue {
   OSB_EPI_RELU_LN_BWD = 8, /* acc = grad of a RELU_LN output y; aux_in = r = relu(conv) saved by SAVE_PRE;
                               out_h16 = grad wrt the conv output = LN_bwd(acc * ln_w; r) * [r > 0];
                               with OUT_H16 also aux_h16 = fp16(acc) (for the LN parameter gradients); BN == N */
-  OSB_EPI_RELU_BWD = 9     /* out_h16 = acc * [aux_in > 0]                                               */
+  OSB_EPI_RELU_BWD = 9,    /* out_h16 = acc * [aux_in > 0]                                               */
+  /* attention of the alignment module (AlignmentModule.forward, generator/alignments.py:66-81), BN == padded N:
+   *   score[t,n] = -sqrt(max(row_stat[t] + bias[b*N+n] - 2*acc, 0))   (row_stat = |f_t|^2, bias = |e_n|^2)
+   *   out_f32[t,n] = score - logsumexp_{n < col_len[b]}(score) + resid[t,n]  (resid = beta-binomial log-prior), -inf for n >= col_len[b]
+   *   out_dot[t] = that logsumexp                                                                           */
+  OSB_EPI_ATTN_LOGP = 10,
+  OSB_EPI_AXPY = 11        /* out_f32 = acc + row_stat[row] * resid[row, n]                                 */
 } osb_epilogue;
 
 enum {
@@ -120,6 +126,9 @@ typedef struct osb_gemm_desc {
    * dropout_seed: forward scales the LN output, RELU_LN_BWD scales the incoming gradient by the same mask. */
   float dropout_p;        /* 0 disables                                                              */
   uint64_t dropout_seed;
+  /* per-batch B operand (batched matmul): w is (B, N, ldw) — with SPLIT_IN (B, N, [hi K | lo K]) — and taps == 1 */
+  int32_t w_batched;
+  const int64_t* col_len; /* ATTN_LOGP: (B) number of valid columns (text length)                    */
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);
@@ -239,6 +248,10 @@ int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* p
 int osb_embed_text_bwd(const float* dout, const int64_t* ids, const float* inv_freq, float* dtable, float* dscale, int32_t B,
                        int32_t T, int32_t dim, int32_t n_vocab, int32_t padding_idx, void* stream);
 
+/* Batched form of osb_gemm_wgrad: dw[b, n, k] += sum_t dy[b, t, n] * a[b, t, k]  (A^T B per batch; dw is (B, N, K)). */
+int osb_gemm_wgrad_batched(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N,
+                           int32_t K, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Alignment-learning kernels (osb_align.cu) — the reference runs these on the host CPU with numba.
  * ------------------------------------------------------------------------------------- */
@@ -268,6 +281,29 @@ int osb_grad_sumsq(const float* g, int64_t n, float* stats /*(2)*/, void* stream
  * bias correction for `step` (1-based).  Skipped entirely when stats[1] != 0 (non-finite gradient). */
 int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int64_t step, float max_norm, float inv_scale, void* stream);
+
+/* Beta-binomial alignment prior on the device: out[b,t,n] = log BetaBinomial(n; N_b, t+1, T_b-t) for t < T_b, n < N_b, -inf
+ * elsewhere; log_factorial[m] = log(m!) in float64 for m <= Tm + Tx.  Replaces AlignmentModule._generate_prior
+ * (generator/alignments.py:85-123: scipy.stats.betabinom per sample on the host). */
+int osb_beta_binomial_prior(const double* log_factorial, int64_t table_len, const int64_t* x_len, const int64_t* m_len, float* out,
+                            int32_t B, int32_t Tm, int32_t Tx, void* stream);
+
+/* out[row] = sum_c x[row,c]^2 : the |f|^2 / |e|^2 terms of the pairwise distance (alignments.py:66-67). */
+int osb_rownorm_sq(const float* x, float* out, int64_t rows, int32_t C, void* stream);
+
+/* Backward of OSB_EPI_ATTN_LOGP with respect to the distance, as a matrix for two contractions:
+ * Wn[b,t,n] = -(dscore/score), dscore = G - softmax*rowsum(G) (fp16, row stride ldw, zero padded);
+ * neg_rsn[b,t] = -sum_n Wn; csn[b,n] += sum_t Wn.  Then dF = neg_rsn*F + Wn@E (OSB_EPI_AXPY) and
+ * dE = -csn*E + Wn^T@F (osb_scale_rows + osb_gemm_wgrad_batched).  Replaces autograd through
+ * torch.norm(feats - text) / log_softmax (alignments.py:66-74). */
+int osb_attn_bwd_prep(const float* G, const float* lp, const float* prior, const float* lse, const int64_t* x_len, const int64_t* m_len,
+                      void* wn_h16, float* neg_rsn, float* csn, int32_t B, int32_t Tm, int32_t Tx, int32_t ldw, void* stream);
+
+/* out[b,c,t] = fp16(x[b,t,c]) (t < T), 0 for T <= t < Tp: per-batch transposed tensor-core operand. */
+int osb_transpose_pack_h16(const float* x, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t Tp, void* stream);
+
+/* out[row,:] = sign * row_scale[row] * x[row,:] */
+int osb_scale_rows(const float* x, const float* row_scale, float* out, int64_t rows, int32_t C, float sign, void* stream);
 
 #ifdef __cplusplus
 }

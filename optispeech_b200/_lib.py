@@ -14,7 +14,7 @@ LIB_PATH = _PKG_DIR / "libosb200.so"
 OSB_OK = 0
 
 # osb_epilogue
-EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD = range(10)
+EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD, EPI_ATTN_LOGP, EPI_AXPY = range(12)
 # flags
 FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU = 1, 2, 4, 8, 16, 32, 64, 128
 
@@ -53,6 +53,8 @@ class GemmDesc(C.Structure):
         ("row_stat", C.c_void_p),
         ("dropout_p", C.c_float),
         ("dropout_seed", C.c_uint64),
+        ("w_batched", C.c_int32),
+        ("col_len", C.c_void_p),
     ]
 
 
@@ -105,6 +107,12 @@ def load() -> C.CDLL:
         "osb_variance_embed_bwd": [P, P, P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_embed_text_bwd": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_mas": [P, P, P, P, P, I32, I32, I32, P],
+        "osb_gemm_wgrad_batched": [P, I64, P, I64, P, I32, I32, I32, I32, P],
+        "osb_rownorm_sq": [P, P, I64, I32, P],
+        "osb_beta_binomial_prior": [P, I64, P, P, P, I32, I32, I32, P],
+        "osb_attn_bwd_prep": [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_transpose_pack_h16": [P, P, I32, I32, I32, I32, P],
+        "osb_scale_rows": [P, P, P, I64, I32, F, P],
         "osb_grad_sumsq": [P, I64, P, P],
         "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],

@@ -297,3 +297,42 @@ class WaveNeXtHeadFn(Function):
         dw1 = w2.t() @ dwc
         db1 = w2.t() @ dbc
         return dx, dw1, db1, dw2
+
+
+# --------------------------------------------------------------------------------------------------
+# attention log-probabilities of the alignment module
+# --------------------------------------------------------------------------------------------------
+class AttnLogProbFn(Function):
+    """log_p_attn[b,t,n] = log_softmax_n(-||f_t - e_n||_2 over n < x_len[b]) + prior[b,t,n]   (alignments.py:66-81).
+
+    ||f - e||^2 = |f|^2 + |e|^2 - 2 f.e with the dot product on the tensor cores in split precision (fp16 hi+lo,
+    three passes, ~2^-21 relative): the (B,Tm,Tx,C) difference tensor of the reference is never formed, and the
+    masked log-softmax + prior run in the GEMM epilogue (one thread owns one attention row)."""
+
+    @staticmethod
+    def forward(ctx, fe, te, prior, x_len, m_len):
+        fe, te = fe.contiguous(), te.contiguous()
+        B, Tm, C = fe.shape
+        Tx = te.shape[1]
+        f16 = ops.to_h16(fe, split=True)
+        e16 = ops.to_h16(te, split=True)
+        nf, ne = ops.rownorm_sq(fe), ops.rownorm_sq(te)
+        lp, _, lse = ops.gemm(f16, e16, epi=ops.EPI_ATTN_LOGP, flags=ops.FLAG_SPLIT_IN, K=C, N=Tx, w_batched=True, row_stat=nf, bias=ne,
+                              resid=prior, col_len=x_len)
+        ctx.save_for_backward(fe, te, lp, lse, prior, x_len, m_len, f16)
+        return lp
+
+    @staticmethod
+    def backward(ctx, G):
+        fe, te, lp, lse, prior, x_len, m_len, f16 = ctx.saved_tensors
+        B, Tm, C = fe.shape
+        Tx = te.shape[1]
+        wn, neg_rsn, csn = ops.attn_bwd_prep(G.contiguous(), lp, prior, lse, x_len, m_len)
+        # dF = -rowsum(Wn) * F + Wn @ E      (contraction over Tx; E transposed per batch is the K-major B operand)
+        eT = ops.transpose_pack_h16(te)                                   # (B, C, Tx8)
+        dF, _, _ = ops.gemm(wn, eT, epi=ops.EPI_AXPY, K=Tx, N=C, w_batched=True, resid=fe, row_stat=neg_rsn)
+        # dE = -colsum(Wn) * E + Wn^T @ F    (contraction over Tm: both operands MN-major, per batch)
+        dE = ops.scale_rows(te, csn, sign=-1.0)
+        f_hi = f16.view(B, Tm, 2 * C)                                      # [hi | lo] rows; the hi halves are the operand
+        ops.gemm_wgrad_batched(wn, f_hi, dE, N=Tx, K=C)
+        return dF, dE, None, None, None

@@ -147,3 +147,163 @@ extern "C" int osb_average_by_duration(const float* ds, const float* xs, const i
   count_launch();
   return launch_status();
 }
+
+// ==========================================================================================
+// Attention (pairwise distance + log-softmax) helpers: squared row norms, backward preparation,
+// batched transpose-pack.  The contractions themselves run on the tcgen05 kernels of osb_gemm.cu.
+// ==========================================================================================
+namespace osb {
+namespace {
+
+// out[row] = sum_c x[row,c]^2, one warp per row
+__global__ void rownorm_sq_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int C) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + row * C + c);
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+// Backward of  lp = log_softmax_n(score) + prior,  score = -dist  with respect to dist, expressed as the matrix
+//   Wn[t,n] = -(dscore[t,n] / score[t,n]),  dscore = G - softmax * rowsum(G)
+// so that  dF = -rsn * F + Wn @ E  and  dE = -csn * E + Wn^T @ F  (rsn / csn = row / column sums of Wn).
+// One warp per (b,t) row.  score is recovered as lp - prior + lse.
+__global__ void attn_bwd_prep_kernel(const float* __restrict__ G, const float* __restrict__ lp, const float* __restrict__ prior,
+                                     const float* __restrict__ lse, const long long* __restrict__ x_len,
+                                     const long long* __restrict__ m_len, __half* __restrict__ Wn, float* __restrict__ neg_rsn,
+                                     float* __restrict__ csn, int B, int Tm, int Tx, int ldw) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(B) * Tm) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  __half* wrow = Wn + row * ldw;
+  if (t >= T) {
+    for (int n = lane; n < ldw; n += 32) wrow[n] = __float2half_rn(0.f);
+    if (lane == 0) neg_rsn[row] = 0.f;
+    return;
+  }
+  const float l = lse[row];
+  float gsum = 0.f;
+  for (int n = lane; n < N; n += 32) gsum += G[row * Tx + n];
+  gsum = warp_sum(gsum);
+  float rs = 0.f;
+  for (int n = lane; n < ldw; n += 32) {
+    float w = 0.f;
+    if (n < N) {
+      const float logp = lp[row * Tx + n] - prior[row * Tx + n];  // log softmax
+      const float score = logp + l;                               // = -dist
+      const float ds = G[row * Tx + n] - expf(logp) * gsum;
+      w = score < 0.f ? -(ds / score) : 0.f;
+      atomicAdd(csn + static_cast<long long>(b) * Tx + n, w);
+    }
+    rs += w;
+    wrow[n] = __float2half_rn(w);
+  }
+  rs = warp_sum(rs);
+  if (lane == 0) neg_rsn[row] = -rs;
+}
+
+// out[b, c, t] = fp16(x[b, t, c]) for t < T, zero for T <= t < Tp   (32x32 shared-memory tiles)
+__global__ void transpose_pack_kernel(const float* __restrict__ x, __half* __restrict__ out, int T, int C, int Tp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int t = t0 + j, c = c0 + tx;
+    tile[j][tx] = (t < T && c < C) ? x[(static_cast<long long>(b) * T + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, t = t0 + tx;
+    if (c < C && t < Tp) out[(static_cast<long long>(b) * C + c) * Tp + t] = __float2half_rn(tile[tx][j]);
+  }
+}
+
+// dE[b,n,:] = -csn[b,n] * E[b,n,:]   (the wgrad contraction then accumulates Wn^T @ F on top)
+__global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ row_scale, float* __restrict__ out, long long rows,
+                                  int C, float sign) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  out[i] = sign * row_scale[i / C] * x[i];
+}
+
+}  // namespace
+}  // namespace osb
+
+namespace osb {
+namespace {
+// log BetaBinomial(k = n; N, a = t+1, b = T-t) for frame t < T and token n < N of each sample, -inf elsewhere.
+// Every gamma-function argument of the scipy definition is an integer, so lf[m] = log(m!) (double) is exact.
+__global__ void beta_binomial_prior_kernel(const double* __restrict__ lf, const long long* __restrict__ x_len,
+                                           const long long* __restrict__ m_len, float* __restrict__ out, int Tm, int Tx) {
+  const int b = blockIdx.z;
+  const int t = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Tx) return;
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  float v = -INFINITY;
+  if (t < T && n < N) {
+    const int a = t + 1;  // alpha = t (1-based), beta = T - alpha + 1
+    v = static_cast<float>(lf[N] - lf[n] - lf[N - n] + lf[n + a - 1] + lf[N - n + T - a] - lf[N + T] - lf[a - 1] - lf[T - a] + lf[T]);
+  }
+  out[(static_cast<long long>(b) * Tm + t) * Tx + n] = v;
+}
+}  // namespace
+}  // namespace osb
+
+extern "C" int osb_beta_binomial_prior(const double* log_factorial, int64_t table_len, const int64_t* x_len, const int64_t* m_len,
+                                       float* out, int32_t B, int32_t Tm, int32_t Tx, void* stream) {
+  OSB_REQUIRE(log_factorial && x_len && m_len && out, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tm > 0 && Tx > 0 && table_len >= static_cast<int64_t>(Tm) + Tx + 1, OSB_ERR_SHAPE);
+  dim3 grid((Tx + 127) / 128, Tm, B);
+  beta_binomial_prior_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      log_factorial, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(m_len), out, Tm, Tx);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_rownorm_sq(const float* x, float* out, int64_t rows, int32_t C, void* stream) {
+  OSB_REQUIRE(x && out, OSB_ERR_ARG);
+  OSB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, OSB_ERR_SHAPE);
+  rownorm_sq_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_attn_bwd_prep(const float* G, const float* lp, const float* prior, const float* lse, const int64_t* x_len,
+                                 const int64_t* m_len, void* wn_h16, float* neg_rsn, float* csn, int32_t B, int32_t Tm, int32_t Tx,
+                                 int32_t ldw, void* stream) {
+  OSB_REQUIRE(G && lp && prior && lse && x_len && m_len && wn_h16 && neg_rsn && csn, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tm > 0 && Tx > 0 && ldw >= Tx && ldw % 8 == 0, OSB_ERR_SHAPE);
+  const long long rows = static_cast<long long>(B) * Tm;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      G, lp, prior, lse, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(m_len),
+      static_cast<__half*>(wn_h16), neg_rsn, csn, B, Tm, Tx, ldw);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_transpose_pack_h16(const float* x, void* out_h16, int32_t B, int32_t T, int32_t C, int32_t Tp, void* stream) {
+  OSB_REQUIRE(x && out_h16, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0 && C > 0 && Tp >= T, OSB_ERR_SHAPE);
+  dim3 grid((Tp + 31) / 32, (C + 31) / 32, B);
+  transpose_pack_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(out_h16), T, C, Tp);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_scale_rows(const float* x, const float* row_scale, float* out, int64_t rows, int32_t C, float sign, void* stream) {
+  OSB_REQUIRE(x && row_scale && out, OSB_ERR_ARG);
+  OSB_REQUIRE(rows > 0 && C > 0, OSB_ERR_SHAPE);
+  const long long n = rows * C;
+  scale_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, row_scale, out, rows, C, sign);
+  count_launch();
+  return launch_status();
+}

@@ -45,6 +45,10 @@ struct GemmKParams {
   float drop_p;
   float drop_inv_keep;
   unsigned long long drop_seed;
+  int w_lo_slice;   // slice offset of the lo parts of W (split precision, shared weights)
+  int w_lo_koff;    // K offset of the lo parts of W (split precision, batched weights stored [hi K | lo K])
+  int w_batch;      // 1: slice index += batch (per-batch B operand)
+  const long long* col_len;
 };
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
@@ -148,7 +152,64 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
   const bool padded = (p.pad_mask != nullptr) && valid && (p.pad_mask[row] != 0);
   float v[32];
 
-  if constexpr (EPI == OSB_EPI_GELU_BWD || EPI == OSB_EPI_RELU_BWD) {
+  if constexpr (EPI == OSB_EPI_ATTN_LOGP) {
+    // the CTA owns whole rows of the (Tm x Tx) attention: distance, masked log-softmax and prior are thread-local
+    const int ncols = p.N;                                              // true number of columns (<= BN)
+    const int nvalid = static_cast<int>(p.col_len[b]) < ncols ? static_cast<int>(p.col_len[b]) : ncols;
+    const float nf = valid ? p.row_stat[row] : 0.f;
+    const float* ne = p.bias + static_cast<long long>(b) * ncols;
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int n = c0 + i;
+        if (n < nvalid) mx = fmaxf(mx, -sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)));
+      }
+    }
+    float sum = 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int n = c0 + i;
+        if (n < nvalid) sum += expf(-sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) - mx);
+      }
+    }
+    const float lse = mx + logf(sum);
+    if (valid && p.out_dot != nullptr) p.out_dot[row] = lse;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      if (valid) {
+        float* orow = static_cast<float*>(p.out) + row * p.ldo;
+        const float* prow = p.resid + row * p.ldo;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = c0 + i;
+          if (n < ncols)
+            orow[n] = n < nvalid ? (-sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) - lse) + prow[n] : -INFINITY;
+        }
+      }
+    }
+  } else if constexpr (EPI == OSB_EPI_AXPY) {
+    const float alpha = valid ? p.row_stat[row] : 0.f;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      ld_chunk(taddr, c0, v);
+      if (valid) {
+        const int n = n0 + c0;
+        const float* rp = p.resid + row * p.ldo + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+          v[i + 0] = fmaf(alpha, r4.x, v[i + 0]);
+          v[i + 1] = fmaf(alpha, r4.y, v[i + 1]);
+          v[i + 2] = fmaf(alpha, r4.z, v[i + 2]);
+          v[i + 3] = fmaf(alpha, r4.w, v[i + 3]);
+        }
+        st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
+      }
+    }
+  } else if constexpr (EPI == OSB_EPI_GELU_BWD || EPI == OSB_EPI_RELU_BWD) {
     float pre[32];
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
@@ -409,13 +470,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int sub = rem / num_kb;
         const int kb = rem - sub * num_kb;
         const int a_k = kb * BKE + (sub == 1 ? p.K : 0);
-        const int w_slice = tap + (sub == 2 ? p.taps : 0);
+        const int w_slice = tap + (sub == 2 ? p.w_lo_slice : 0) + (p.w_batch ? b : 0);
+        const int w_k = kb * BKE + (sub == 2 ? p.w_lo_koff : 0);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 + tap - p.pad, b);
 #pragma unroll
         for (int c = 0; c < Cfg::NCHUNK; ++c)
-          tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], kb * BKE, n0 + c * Cfg::NINST, w_slice);
+          tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], w_k, n0 + c * Cfg::NINST, w_slice);
       }
     }
   } else if (warp == 1) {
@@ -468,6 +530,7 @@ struct WgradParams {
   int T, B, N, K, taps, pad;
   int row_blocks_per_batch;  // ceil(T / 64)
   int splits;
+  int per_batch;             // 1: one (N, K) output per batch (batched matmul A^T B), taps == 1
   float* dw;
 };
 
@@ -500,11 +563,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
   const int n0 = blockIdx.x * WG_TILE;
   const int k0 = blockIdx.y * WG_TILE;
-  const int tap = blockIdx.z / p.splits;
+  const int zsel = blockIdx.z / p.splits;       // tap, or batch in per-batch mode
+  const int tap = p.per_batch ? 0 : zsel;
   const int split = blockIdx.z % p.splits;
-  const int total_rb = p.B * p.row_blocks_per_batch;
-  const int rb_begin = static_cast<int>((static_cast<long long>(total_rb) * split) / p.splits);
-  const int rb_end = static_cast<int>((static_cast<long long>(total_rb) * (split + 1)) / p.splits);
+  const int total_rb = p.per_batch ? p.row_blocks_per_batch : p.B * p.row_blocks_per_batch;
+  const int rb_base = p.per_batch ? zsel * p.row_blocks_per_batch : 0;
+  const int rb_begin = rb_base + static_cast<int>((static_cast<long long>(total_rb) * split) / p.splits);
+  const int rb_end = rb_base + static_cast<int>((static_cast<long long>(total_rb) * (split + 1)) / p.splits);
   const int iters = rb_end - rb_begin;
 
   if (warp == 0) {
@@ -558,7 +623,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     for (int c0 = 0; c0 < WG_TILE; c0 += 32) {
       ld_chunk(taddr, c0, v);
       if (n < p.N) {
-        float* dst = p.dw + (static_cast<long long>(tap) * p.N + n) * p.K + k0 + c0;
+        float* dst = p.dw + (static_cast<long long>(zsel) * p.N + n) * p.K + k0 + c0;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (k0 + c0 + i < p.K) atomicAdd(dst + i, v[i]);
@@ -580,7 +645,7 @@ int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmKParams&
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  dim3 grid(p.B * p.m_tiles, p.N / BN, 1);
+  dim3 grid(p.B * p.m_tiles, (p.N + BN - 1) / BN, 1);
   gemm_nt_kernel<BN, EPI><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, p);
   count_launch();
   return launch_status();
@@ -602,6 +667,20 @@ int dispatch_bn_full(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, con
     case 128: return launch_nt<128, EPI>(tmA, tmW, p, stream);
     case 256: return launch_nt<256, EPI>(tmA, tmW, p, stream);
     case 384: return launch_nt<384, EPI>(tmA, tmW, p, stream);
+    default: return OSB_ERR_SHAPE;
+  }
+}
+
+int dispatch_attn(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmKParams& p, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_nt<64, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 128: return launch_nt<128, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 192: return launch_nt<192, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 256: return launch_nt<256, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 320: return launch_nt<320, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 384: return launch_nt<384, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 448: return launch_nt<448, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
+    case 512: return launch_nt<512, OSB_EPI_ATTN_LOGP>(tmA, tmW, p, stream);
     default: return OSB_ERR_SHAPE;
   }
 }
@@ -667,15 +746,18 @@ using namespace osb;
 extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   OSB_REQUIRE(d != nullptr && d->a != nullptr && d->w != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->taps > 0, OSB_ERR_SHAPE);
-  OSB_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0 && d->ldo % 8 == 0, OSB_ERR_ALIGN);
+  OSB_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0 && (d->ldo % 8 == 0 || d->epi == OSB_EPI_ATTN_LOGP), OSB_ERR_ALIGN);
   OSB_REQUIRE(d->lda >= d->K && d->ldw >= d->K && d->ldo >= d->N, OSB_ERR_SHAPE);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   const bool full_row = (d->epi == OSB_EPI_RELU_LN || d->epi == OSB_EPI_BIAS_LN || d->epi == OSB_EPI_LN_BWD ||
                          d->epi == OSB_EPI_RELU_LN_BWD);
-  const int bn = full_row ? d->N : pick_bn(d->N);
-  OSB_REQUIRE(bn > 0, OSB_ERR_SHAPE);
+  const bool attn = d->epi == OSB_EPI_ATTN_LOGP;
+  const int bn = attn ? ((d->N + 63) / 64) * 64 : (full_row ? d->N : pick_bn(d->N));
+  OSB_REQUIRE(bn > 0 && bn <= 512, OSB_ERR_SHAPE);
   const int ninst = bn <= 256 ? bn : bn / 2;
+  const bool w_batched = d->w_batched != 0;
+  if (w_batched) OSB_REQUIRE(d->taps == 1, OSB_ERR_SHAPE);
 
   const bool split_in = (d->flags & OSB_FLAG_SPLIT_IN) != 0;
   if (split_in) OSB_REQUIRE(d->K % BKE == 0 && d->lda >= 2 * static_cast<int64_t>(d->K), OSB_ERR_SHAPE);
@@ -683,8 +765,14 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   int rc = make_tmap_3d(&tmA, d->a, TMA_F16, split_in ? 2 * d->K : d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda,
                         BKE, BM);
   if (rc != OSB_OK) return rc;
-  rc = make_tmap_3d(&tmW, d->w, TMA_F16, d->K, d->N, split_in ? 2 * d->taps : d->taps, d->ldw, static_cast<uint64_t>(d->N) * d->ldw,
-                    BKE, ninst);
+  if (w_batched) {
+    if (split_in) OSB_REQUIRE(d->ldw >= 2 * static_cast<int64_t>(d->K), OSB_ERR_SHAPE);
+    rc = make_tmap_3d(&tmW, d->w, TMA_F16, split_in ? 2 * d->K : d->K, d->N, d->B, d->ldw, static_cast<uint64_t>(d->N) * d->ldw, BKE,
+                      ninst);
+  } else {
+    rc = make_tmap_3d(&tmW, d->w, TMA_F16, d->K, d->N, split_in ? 2 * d->taps : d->taps, d->ldw, static_cast<uint64_t>(d->N) * d->ldw,
+                      BKE, ninst);
+  }
   if (rc != OSB_OK) return rc;
 
   GemmKParams p;
@@ -696,6 +784,10 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.pad_mask = d->pad_mask; p.ln_w = d->ln_w; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps;
   p.dot_w = d->dot_w; p.dot_b = d->dot_b; p.out_dot = d->out_dot;
   p.aux_in = d->aux_in_h16; p.row_stat = d->row_stat;
+  p.w_batch = w_batched ? 1 : 0;
+  p.w_lo_slice = w_batched ? 0 : d->taps;
+  p.w_lo_koff = w_batched ? d->K : 0;
+  p.col_len = reinterpret_cast<const long long*>(d->col_len);
   p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed;
   p.drop_inv_keep = d->dropout_p > 0.f && d->dropout_p < 1.f ? 1.f / (1.f - d->dropout_p) : 0.f;
   OSB_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, OSB_ERR_ARG);
@@ -729,6 +821,18 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
     case OSB_EPI_RELU_BWD:
       OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr, OSB_ERR_ARG);
       return dispatch_bn<OSB_EPI_RELU_BWD>(bn, tmA, tmW, p, stream);
+    case OSB_EPI_ATTN_LOGP: {
+      OSB_REQUIRE(d->out != nullptr && d->row_stat != nullptr && d->bias != nullptr && d->resid != nullptr && d->col_len != nullptr,
+                  OSB_ERR_ARG);
+      GemmKParams q = p;
+      q.N = d->N;  // true column count; the tile is padded to a multiple of 64 (out-of-range rows of W read as zero)
+      dim3 grid_check(1, 1, 1);
+      (void)grid_check;
+      return dispatch_attn(bn, tmA, tmW, q, stream);
+    }
+    case OSB_EPI_AXPY:
+      OSB_REQUIRE(d->out != nullptr && d->row_stat != nullptr && d->resid != nullptr, OSB_ERR_ARG);
+      return dispatch_bn<OSB_EPI_AXPY>(bn, tmA, tmW, p, stream);
     case OSB_EPI_LN_BWD:
       OSB_REQUIRE(d->out != nullptr && d->aux_in_h16 != nullptr && d->row_stat != nullptr, OSB_ERR_ARG);
       return dispatch_bn_full<OSB_EPI_LN_BWD>(bn, tmA, tmW, p, stream);
@@ -740,8 +844,21 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   }
 }
 
+static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N, int32_t K,
+                      int32_t taps, int32_t pad, int per_batch, void* stream_);
+
 extern "C" int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
                               int32_t N, int32_t K, int32_t taps, int32_t pad, void* stream_) {
+  return wgrad_impl(dy, ldy, a, lda, dw, B, T, N, K, taps, pad, 0, stream_);
+}
+
+extern "C" int osb_gemm_wgrad_batched(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
+                                      int32_t N, int32_t K, void* stream_) {
+  return wgrad_impl(dy, ldy, a, lda, dw, B, T, N, K, 1, 0, 1, stream_);
+}
+
+static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N, int32_t K,
+                      int32_t taps, int32_t pad, int per_batch, void* stream_) {
   OSB_REQUIRE(dy != nullptr && a != nullptr && dw != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0 && taps > 0, OSB_ERR_SHAPE);
   OSB_REQUIRE(ldy % 8 == 0 && lda % 8 == 0, OSB_ERR_ALIGN);
@@ -757,8 +874,10 @@ extern "C" int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_
   p.row_blocks_per_batch = (T + WG_ROWS - 1) / WG_ROWS;
   const int n_tiles = (N + WG_TILE - 1) / WG_TILE;
   const int k_tiles = (K + WG_TILE - 1) / WG_TILE;
-  const int total_rb = B * p.row_blocks_per_batch;
-  int splits = (2 * 148 + n_tiles * k_tiles * taps - 1) / (n_tiles * k_tiles * taps);
+  p.per_batch = per_batch;
+  const int zcount = per_batch ? B : taps;
+  const int total_rb = per_batch ? p.row_blocks_per_batch : B * p.row_blocks_per_batch;
+  int splits = (2 * 148 + n_tiles * k_tiles * zcount - 1) / (n_tiles * k_tiles * zcount);
   if (splits > total_rb) splits = total_rb;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -770,7 +889,7 @@ extern "C" int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  dim3 grid(n_tiles, k_tiles, taps * splits);
+  dim3 grid(n_tiles, k_tiles, zcount * splits);
   gemm_wgrad_kernel<<<grid, 192, WG_SMEM_BYTES, stream>>>(tmDy, tmA, p);
   count_launch();
   return launch_status();

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ... import ops
-from ...autograd import ConvStackFn
+from ...autograd import AttnLogProbFn, ConvStackFn
 from ...utils import sequence_mask
 from ...utils.segments import get_segments
 
@@ -39,12 +39,9 @@ class AlignmentModule(nn.Module):
         odim = feats.shape[-1]
         fe = ConvStackFn.apply(feats, ((odim + 63) // 64) * 64, self.f_conv1.weight, self.f_conv1.bias, self.f_conv2.weight,
                                self.f_conv2.bias, self.f_conv3.weight, self.f_conv3.bias)
-        score = -torch.cdist(fe, te, p=2, compute_mode="donot_use_mm_for_euclid_dist")
-        if x_masks is not None:
-            score = score.masked_fill(x_masks.unsqueeze(-2), -np.inf)
-        log_p_attn = F.log_softmax(score, dim=-1)
-        prior = self._generate_prior(text_lengths, feats_lengths, text.shape[1], feats.shape[1]).to(log_p_attn)
-        return log_p_attn + prior
+        prior = self._generate_prior(text_lengths, feats_lengths, text.shape[1], feats.shape[1])
+        # x_masks is the prefix mask of text_lengths in every reference call site (generator/__init__.py:120-126)
+        return AttnLogProbFn.apply(fe, te, prior, text_lengths.contiguous(), feats_lengths.contiguous())
 
     @staticmethod
     def _log_prior(T: int, N: int) -> np.ndarray:
@@ -56,6 +53,17 @@ class AlignmentModule(nn.Module):
         return (lf[N] - lf[k] - lf[N - k] + lf[k + t - 1] + lf[N - k + T - t] - lf[N + T] - lf[t - 1] - lf[T - t] + lf[T])
 
     def _generate_prior(self, text_lengths, feats_lengths, T_text=None, T_feats=None, w=1) -> torch.Tensor:
+        if text_lengths.is_cuda:
+            # device path: no host round trip for the lengths (the reference loops over .item() per sample, :104-106)
+            T_text = T_text or int(text_lengths.max())
+            T_feats = T_feats or int(feats_lengths.max())
+            need = T_text + T_feats + 2
+            lf = self._cache.get("lf")
+            if lf is None or lf.numel() < need or lf.device != text_lengths.device:
+                tab = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, max(need, 4096), dtype=np.float64)))])
+                lf = torch.from_numpy(tab).to(text_lengths.device)
+                self._cache["lf"] = lf
+            return ops.beta_binomial_prior(lf, text_lengths.contiguous(), feats_lengths.contiguous(), T_feats, T_text)
         tl, fl = text_lengths.tolist(), feats_lengths.tolist()
         T_text = T_text or max(tl)
         T_feats = T_feats or max(fl)

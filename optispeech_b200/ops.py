@@ -12,8 +12,8 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU, EPI_RELU_BWD, EPI_RELU_LN, EPI_RELU_LN_BWD,
-                   EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_RELU, FLAG_SAVE_PRE, FLAG_SPLIT_IN,
+from ._lib import (EPI_ATTN_LOGP, EPI_AXPY, EPI_BIAS, EPI_BIAS_LN, EPI_GELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU, EPI_RELU_BWD, EPI_RELU_LN,
+                   EPI_RELU_LN_BWD, EPI_RESID, FLAG_CLIP, FLAG_DOT, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_RELU, FLAG_SAVE_PRE, FLAG_SPLIT_IN,
                    FLAG_SPLIT_OUT)
 
 __all__ = [
@@ -44,7 +44,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -52,7 +52,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     Outputs are allocated when not given.  Returns (out, aux, out_dot)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 3
     B, T, lda = a.shape
-    if flags & FLAG_SPLIT_IN:
+    if w_batched:
+        assert w.dim() == 3 and w.shape[0] == B
+        taps, ldw = 1, w.shape[2]
+        N = N if N is not None else w.shape[1]
+        K = K if K is not None else (min(lda, ldw) // 2 if (flags & FLAG_SPLIT_IN) else min(lda, ldw))
+    elif flags & FLAG_SPLIT_IN:
         assert w.dim() == 4 and w.shape[0] == 2
         _, taps, N, ldw = w.shape
         K = K if K is not None else min(lda // 2, ldw)
@@ -61,7 +66,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
             w = w[0]
         taps, N, ldw = w.shape
         K = K if K is not None else min(lda, ldw)
-    f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN, EPI_LN_BWD)
+    f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN, EPI_LN_BWD, EPI_ATTN_LOGP, EPI_AXPY)
     hN = 2 * N if (flags & FLAG_SPLIT_OUT) else N
     if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)):
         out = torch.empty((B, T, N if f32_out else hN), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
@@ -69,7 +74,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
         aux = torch.empty((B, T, hN), device=a.device, dtype=torch.float16)
     if (flags & FLAG_SAVE_PRE) and aux is None:
         aux = torch.empty((B, T, N), device=a.device, dtype=torch.float16)
-    if (flags & FLAG_DOT) and out_dot is None:
+    if ((flags & FLAG_DOT) or epi == EPI_ATTN_LOGP) and out_dot is None:
         out_dot = torch.empty((B, T), device=a.device, dtype=torch.float32)
     d = _lib.GemmDesc()
     d.a, d.w, d.lda, d.ldw = _ptr(a), _ptr(w), lda, ldw
@@ -82,6 +87,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.dot_w, d.dot_b, d.out_dot = _ptr(dot_w), _ptr(dot_b), _ptr(out_dot)
     d.aux_in_h16, d.row_stat = _ptr(aux_in), _ptr(row_stat)
     d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
+    d.w_batched, d.col_len = int(w_batched), _ptr(col_len)
     _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
     return out, aux, out_dot
 
@@ -302,4 +308,56 @@ def average_by_duration(ds, xs, x_len, m_len):
     out = torch.empty((B, Tx), device=ds.device, dtype=torch.float32)
     _lib.check(_lib.load().osb_average_by_duration(_ptr(_f32(ds)), _ptr(_f32(xs)), _ptr(x_len), _ptr(m_len), _ptr(out), B, Tm, Tx, _stream()),
                "osb_average_by_duration")
+    return out
+
+
+def gemm_wgrad_batched(dy: torch.Tensor, a: torch.Tensor, dw: torch.Tensor, *, N: int, K: int):
+    """dw[b,n,k] += sum_t dy[b,t,n] a[b,t,k]; dy fp16 (B,T,ldy), a fp16 (B,T,lda), dw fp32 (B,N,K)."""
+    B, T, ldy = dy.shape
+    _lib.check(_lib.load().osb_gemm_wgrad_batched(_ptr(dy), ldy, _ptr(a), a.shape[2], _ptr(dw), B, T, N, K, _stream()), "osb_gemm_wgrad_batched")
+    return dw
+
+
+def rownorm_sq(x):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_rownorm_sq(_ptr(_f32(x)), _ptr(out), rows, Cc, _stream()), "osb_rownorm_sq")
+    return out
+
+
+def attn_bwd_prep(G, lp, prior, lse, x_len, m_len):
+    B, Tm, Tx = lp.shape
+    ldw = (Tx + 7) // 8 * 8
+    wn = torch.empty((B, Tm, ldw), device=lp.device, dtype=torch.float16)
+    neg_rsn = torch.empty((B, Tm), device=lp.device, dtype=torch.float32)
+    csn = torch.zeros((B, Tx), device=lp.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_attn_bwd_prep(_ptr(_f32(G)), _ptr(lp), _ptr(prior), _ptr(lse), _ptr(x_len), _ptr(m_len), _ptr(wn),
+                                             _ptr(neg_rsn), _ptr(csn), B, Tm, Tx, ldw, _stream()), "osb_attn_bwd_prep")
+    return wn, neg_rsn, csn
+
+
+def transpose_pack_h16(x, Tp: Optional[int] = None):
+    B, T, Cc = x.shape
+    Tp = Tp or (T + 7) // 8 * 8
+    out = torch.empty((B, Cc, Tp), device=x.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_transpose_pack_h16(_ptr(_f32(x)), _ptr(out), B, T, Cc, Tp, _stream()), "osb_transpose_pack_h16")
+    return out
+
+
+def scale_rows(x, row_scale, sign: float = 1.0):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().osb_scale_rows(_ptr(_f32(x)), _ptr(row_scale), _ptr(out), rows, Cc, float(sign), _stream()), "osb_scale_rows")
+    return out
+
+
+def beta_binomial_prior(log_factorial, x_len, m_len, Tm: int, Tx: int):
+    """(B,Tm,Tx) fp32 log-prior from the float64 log-factorial table (device-side, no host knowledge of the lengths)."""
+    B = x_len.shape[0]
+    assert log_factorial.dtype == torch.float64
+    out = torch.empty((B, Tm, Tx), device=x_len.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_beta_binomial_prior(_ptr(log_factorial), log_factorial.numel(), _ptr(x_len), _ptr(m_len), _ptr(out), B, Tm,
+                                                   Tx, _stream()), "osb_beta_binomial_prior")
     return out

@@ -243,3 +243,42 @@ def test_inner_dropout_mask_matches_between_relu_ln_forward_and_backward_epilogu
                         dropout_seed=seed)
     mask_b = gy.float() / gacc.float()
     assert torch.equal(mask_b[ok] > 0.5, mask_f[ok] > 0.5), "backward regenerated a different dropout mask"
+
+
+@pytest.mark.parametrize("B,Tm,Tx", [(3, 150, 64), (2, 333, 41), (2, 90, 192)])
+def test_attention_logprob_fn(cuda_device, B, Tm, Tx):
+    """Fused pairwise-distance + masked log-softmax + prior (tcgen05 split precision) vs the reference formulation."""
+    import numpy as np
+    from optispeech_b200 import ops
+    from optispeech_b200.autograd import AttnLogProbFn
+
+    g = torch.Generator().manual_seed(6)
+    dev = cuda_device
+    C = 256
+    fe = torch.randn(B, Tm, C, generator=g).to(dev).requires_grad_(True)
+    te = torch.randn(B, Tx, C, generator=g).to(dev).requires_grad_(True)
+    xl = torch.randint(max(1, Tx // 2), Tx + 1, (B,), generator=g); xl[0] = Tx
+    ml = torch.randint(max(xl.max().item(), Tm // 2), Tm + 1, (B,), generator=g); ml[0] = Tm
+    lf = torch.from_numpy(np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, Tm + Tx + 4, dtype=np.float64)))])).to(dev)
+    prior = ops.beta_binomial_prior(lf, xl.to(dev), ml.to(dev), Tm, Tx)
+    ref_prior = torch.full((B, Tm, Tx), -float("inf"))
+    for b in range(B):
+        ref_prior[b, : ml[b], : xl[b]] = torch.from_numpy(O.beta_binomial_log_prior(int(ml[b]), int(xl[b]))).float()
+    assert torch.equal(torch.isinf(prior.cpu()), torch.isinf(ref_prior))
+    fin = torch.isfinite(ref_prior)
+    assert (prior.cpu()[fin] - ref_prior[fin]).abs().max().item() <= 1e-5
+    lp = AttnLogProbFn.apply(fe, te, prior, xl.to(dev), ml.to(dev))
+    # reference formulation (alignments.py:66-81)
+    dist = torch.norm(fe.unsqueeze(2) - te.unsqueeze(1), p=2, dim=3)
+    x_mask = (torch.arange(Tx)[None] >= xl[:, None]).to(dev)
+    ref = F.log_softmax((-dist).masked_fill(x_mask.unsqueeze(-2), -float("inf")), dim=-1) + prior
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lp), fin)
+    err = (lp[fin] - ref[fin]).abs().max().item()
+    print(f"  log_p_attn max-abs err {err:.3e}")
+    assert err <= 2e-4
+    G = torch.randn(B, Tm, Tx, generator=g).to(dev) * fin
+    gf, ge = torch.autograd.grad(lp, (fe, te), G)
+    ref0 = torch.where(fin, ref, torch.zeros((), device=dev))
+    rf, re_ = torch.autograd.grad(ref0, (fe, te), G)
+    _check([("dF", gf, rf), ("dE", ge, re_)], 3e-3)
