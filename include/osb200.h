@@ -288,6 +288,14 @@ int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
 int osb_beta_binomial_prior(const double* log_factorial, int64_t table_len, const int64_t* x_len, const int64_t* m_len, float* out,
                             int32_t B, int32_t Tm, int32_t Tx, void* stream);
 
+/* Forward-sum alignment loss and its gradient in one launch: per sample, CTC over the frames t < m_len of
+ * log_softmax([blank_logit | log_p_attn[b,t,:x_len]]) with target 1..x_len, nll / x_len ('mean' reduction), 0 when infinite
+ * (zero_infinity).  loss (B) holds the per-sample values (ForwardSumLoss = sum / B); grad (B,Tm,Tx) = d(sum/B)/d(log_p_attn);
+ * alpha_ws is a (B, Tm, 2*Tx+1) fp32 workspace.  Replaces ForwardSumLoss.forward (generator/loss.py:150-194: a Python loop of
+ * F.ctc_loss calls) and its autograd. */
+int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len, float blank_logit, float* alpha_ws,
+                    float* loss, float* grad, int32_t B, int32_t Tm, int32_t Tx, void* stream);
+
 /* out[row] = sum_c x[row,c]^2 : the |f|^2 / |e|^2 terms of the pairwise distance (alignments.py:66-67). */
 int osb_rownorm_sq(const float* x, float* out, int64_t rows, int32_t C, void* stream);
 

@@ -109,6 +109,7 @@ def load() -> C.CDLL:
         "osb_mas": [P, P, P, P, P, I32, I32, I32, P],
         "osb_gemm_wgrad_batched": [P, I64, P, I64, P, I32, I32, I32, I32, P],
         "osb_rownorm_sq": [P, P, I64, I32, P],
+        "osb_forward_sum": [P, P, P, F, P, P, P, I32, I32, I32, P],
         "osb_beta_binomial_prior": [P, I64, P, P, P, I32, I32, I32, P],
         "osb_attn_bwd_prep": [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_transpose_pack_h16": [P, P, I32, I32, I32, I32, P],

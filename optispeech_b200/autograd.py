@@ -336,3 +336,19 @@ class AttnLogProbFn(Function):
         f_hi = f16.view(B, Tm, 2 * C)                                      # [hi | lo] rows; the hi halves are the operand
         ops.gemm_wgrad_batched(wn, f_hi, dE, N=Tx, K=C)
         return dF, dE, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# forward-sum (CTC) alignment loss
+# --------------------------------------------------------------------------------------------------
+class ForwardSumLossFn(Function):
+    @staticmethod
+    def forward(ctx, log_p_attn, x_len, m_len, blank_logit):
+        per_sample, grad = ops.forward_sum(log_p_attn.contiguous(), x_len, m_len, blank_logit)
+        ctx.save_for_backward(grad)
+        return per_sample.sum() / log_p_attn.shape[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return grad * dloss, None, None, None

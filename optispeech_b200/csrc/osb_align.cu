@@ -307,3 +307,161 @@ extern "C" int osb_scale_rows(const float* x, const float* row_scale, float* out
   count_launch();
   return launch_status();
 }
+
+// ==========================================================================================
+// Forward-sum alignment loss: CTC with the identity target (token n at position n), a constant
+// blank logit, per-sample re-normalisation.  One CTA per sample, thread k owns the blank state 2k and
+// the token state 2k+1 of the extended target; alpha is kept in a global workspace for the backward
+// sweep, which runs in the same kernel and emits d(loss)/d(log_p_attn).
+// ==========================================================================================
+namespace osb {
+namespace {
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  return m == -INFINITY ? -INFINITY : m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  return m == -INFINITY ? -INFINITY : m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+__global__ void forward_sum_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
+                                   float blank_logit, float* __restrict__ alpha_ws, float* __restrict__ loss, float* __restrict__ grad,
+                                   int B, int Tm, int Tx) {
+  extern __shared__ float fs_smem[];
+  const int b = blockIdx.x;
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  const int S = 2 * N + 1;
+  const int Smax = 2 * Tx + 1;
+  const int k = threadIdx.x;
+  float* buf0 = fs_smem;              // [Smax + 2] with one -inf guard on each side handled by index checks
+  float* buf1 = buf0 + Smax;
+  float* lse = buf1 + Smax;           // [Tm]
+  const float* lp = lpa + static_cast<long long>(b) * Tm * Tx;
+  float* gr = grad + static_cast<long long>(b) * Tm * Tx;
+  float* aw = alpha_ws + static_cast<long long>(b) * Tm * Smax;
+  const float NEG = -INFINITY;
+
+  if (N <= 0 || T <= 0) {
+    for (int i = k; i < Tm * Tx; i += blockDim.x) gr[i] = 0.f;
+    if (k == 0) loss[b] = 0.f;
+    return;
+  }
+  // per-frame normaliser over [blank | tokens < N]
+  const int warp = k >> 5, lane = k & 31, nwarps = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nwarps) {
+    float m = blank_logit;
+    for (int i = lane; i < N; i += 32) m = fmaxf(m, lp[static_cast<long long>(t) * Tx + i]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < N; i += 32) s += expf(lp[static_cast<long long>(t) * Tx + i] - m);
+    s = warp_sum(s) + expf(blank_logit - m);
+    if (lane == 0) lse[t] = m + logf(s);
+  }
+  __syncthreads();
+
+  const bool has_tok = k < N;
+  const bool active = k <= N;
+  // ---- forward (alpha) ----
+  float* prev = buf0;
+  float* cur = buf1;
+  {
+    const float l0 = lse[0];
+    const float ab = (k == 0) ? blank_logit - l0 : NEG;
+    const float at = (k == 0 && has_tok) ? lp[0] - l0 : NEG;
+    if (active) {
+      prev[2 * k] = ab;
+      aw[2 * k] = ab;
+      if (has_tok) {
+        prev[2 * k + 1] = at;
+        aw[2 * k + 1] = at;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = 1; t < T; ++t) {
+    const float lt = lse[t];
+    if (active) {
+      const float pb = prev[2 * k];
+      const float pm1 = k > 0 ? prev[2 * k - 1] : NEG;
+      const float nb = lse2(pb, pm1) + (blank_logit - lt);
+      cur[2 * k] = nb;
+      aw[static_cast<long long>(t) * Smax + 2 * k] = nb;
+      if (has_tok) {
+        const float nt = lse3(prev[2 * k + 1], pb, pm1) + (lp[static_cast<long long>(t) * Tx + k] - lt);
+        cur[2 * k + 1] = nt;
+        aw[static_cast<long long>(t) * Smax + 2 * k + 1] = nt;
+      }
+    }
+    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
+  }
+  const float ll = lse2(prev[S - 1], S >= 2 ? prev[S - 2] : NEG);
+  const bool finite = ll > -INFINITY && ll < INFINITY;
+  const float nll = -ll;
+  if (k == 0) loss[b] = finite ? nll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
+  const float gscale = finite ? 1.f / (static_cast<float>(N) * static_cast<float>(B)) : 0.f;
+  __syncthreads();
+
+  // ---- backward (beta) + gradient ----
+  {
+    const float lt = lse[T - 1];
+    if (active) {
+      prev[2 * k] = (k == N) ? blank_logit - lt : NEG;
+      if (has_tok) prev[2 * k + 1] = (k == N - 1) ? lp[static_cast<long long>(T - 1) * Tx + k] - lt : NEG;
+    }
+  }
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    const float lt = lse[t];
+    if (has_tok) {
+      const float e = lp[static_cast<long long>(t) * Tx + k] - lt;                 // normalised log-prob of token k
+      const float a = aw[static_cast<long long>(t) * Smax + 2 * k + 1];
+      const float occ = a + prev[2 * k + 1] - e + nll;                             // log posterior occupancy
+      gr[static_cast<long long>(t) * Tx + k] = gscale * (expf(e) - expf(occ));
+    }
+    if (t > 0) {
+      const float lt1 = lse[t - 1];
+      if (active) {
+        const float nb = lse2(prev[2 * k], has_tok ? prev[2 * k + 1] : NEG) + (blank_logit - lt1);
+        cur[2 * k] = nb;
+        if (has_tok) {
+          const float nt = lse3(prev[2 * k + 1], prev[2 * k + 2], (k + 1 < N) ? prev[2 * k + 3] : NEG) +
+                           (lp[static_cast<long long>(t - 1) * Tx + k] - lt1);
+          cur[2 * k + 1] = nt;
+        }
+      }
+      __syncthreads();
+      float* tmp = prev; prev = cur; cur = tmp;
+    }
+  }
+  // zero the padded region
+  for (int i = k; i < Tm * Tx; i += blockDim.x) {
+    const int t = i / Tx, n = i - t * Tx;
+    if (t >= T || n >= N) gr[i] = 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace osb
+
+extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len, float blank_logit, float* alpha_ws,
+                               float* loss, float* grad, int32_t B, int32_t Tm, int32_t Tx, void* stream) {
+  OSB_REQUIRE(log_p_attn && x_len && m_len && alpha_ws && loss && grad, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tm > 0 && Tx > 0 && Tx <= 1023, OSB_ERR_SHAPE);
+  const int nthr = ((Tx + 1 + 31) / 32) * 32;
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(2 * Tx + 1) + Tm);
+  OSB_REQUIRE(smem <= 200 * 1024, OSB_ERR_SHAPE);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(osb::forward_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = 200 * 1024;
+  }
+  osb::forward_sum_kernel<<<B, nthr, smem, static_cast<cudaStream_t>(stream)>>>(
+      log_p_attn, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(m_len), blank_logit, alpha_ws, loss, grad,
+      B, Tm, Tx);
+  osb::count_launch();
+  return osb::launch_status();
+}

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ... import ops
-from ...autograd import AttnLogProbFn, ConvStackFn
+from ...autograd import AttnLogProbFn, ConvStackFn, ForwardSumLossFn
 from ...utils import sequence_mask
 from ...utils.segments import get_segments
 
@@ -109,6 +109,8 @@ def average_by_duration(ds, xs, text_lengths, feats_lengths):
 def forward_sum_loss(log_p_attn, ilens, olens, blank_logprob: float = -1.0):
     """ForwardSumLoss (reference loss.py:150-194): blank column log(e^-1), per-sample log_softmax over its own
     (N_b + 1) columns, CTC with targets 1..N_b, 'mean' reduction (divide by N_b), zero_infinity, mean over batch."""
+    if log_p_attn.is_cuda:
+        return ForwardSumLossFn.apply(log_p_attn, ilens.contiguous(), olens.contiguous(), blank_logprob)
     B, Tm, Tx = log_p_attn.shape
     padded = F.pad(log_p_attn, (1, 0), value=blank_logprob)                       # (B, Tm, Tx+1)
     col_ok = torch.arange(Tx + 1, device=padded.device)[None, :] <= ilens[:, None]  # blank + the sample's own tokens

@@ -245,7 +245,7 @@ def test_inner_dropout_mask_matches_between_relu_ln_forward_and_backward_epilogu
     assert torch.equal(mask_b[ok] > 0.5, mask_f[ok] > 0.5), "backward regenerated a different dropout mask"
 
 
-@pytest.mark.parametrize("B,Tm,Tx", [(3, 150, 64), (2, 333, 41), (2, 90, 192)])
+@pytest.mark.parametrize("B,Tm,Tx", [(3, 150, 64), (2, 333, 41), (2, 400, 192)])
 def test_attention_logprob_fn(cuda_device, B, Tm, Tx):
     """Fused pairwise-distance + masked log-softmax + prior (tcgen05 split precision) vs the reference formulation."""
     import numpy as np
@@ -282,3 +282,33 @@ def test_attention_logprob_fn(cuda_device, B, Tm, Tx):
     ref0 = torch.where(fin, ref, torch.zeros((), device=dev))
     rf, re_ = torch.autograd.grad(ref0, (fe, te), G)
     _check([("dF", gf, rf), ("dE", ge, re_)], 3e-3)
+
+
+def test_forward_sum_loss_fn(cuda_device):
+    """CTC forward-sum kernel (loss + gradient in one launch) vs the oracle's per-sample F.ctc_loss formulation."""
+    from optispeech_b200.autograd import ForwardSumLossFn
+
+    g = torch.Generator().manual_seed(8)
+    dev = cuda_device
+    B, Tm, Tx = 4, 120, 37
+    tl = torch.tensor([37, 20, 1, 30])
+    fl = torch.tensor([120, 64, 5, 30])
+    lp = torch.log_softmax(torch.randn(B, Tm, Tx, generator=g) * 2, dim=-1)
+    for b in range(B):
+        lp[b, fl[b]:, :] = -float("inf")
+        lp[b, :, tl[b]:] = -float("inf")
+    ref_in = lp.clone().requires_grad_(True)
+    ref = O.forward_sum_loss(ref_in, tl, fl)
+    (rg,) = torch.autograd.grad(ref, ref_in)
+    x = lp.to(dev).requires_grad_(True)
+    loss = ForwardSumLossFn.apply(x, tl.to(dev), fl.to(dev), -1.0)
+    (gg,) = torch.autograd.grad(loss, x)
+    print(f"  loss cuda {float(loss):.6f} oracle {float(ref):.6f}")
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    rg = torch.nan_to_num(rg, nan=0.0)
+    _check([("dlogp", gg.cpu(), rg)], 1e-3)
+    # infeasible alignment (more tokens than frames): zero_infinity semantics
+    tl2, fl2 = torch.tensor([10]), torch.tensor([4])
+    lp2 = torch.log_softmax(torch.randn(1, 12, 10, generator=g), dim=-1)
+    l2 = ForwardSumLossFn.apply(lp2.to(dev).requires_grad_(True), tl2.to(dev), fl2.to(dev), -1.0)
+    assert float(l2) == 0.0
