@@ -197,6 +197,11 @@ int osb_expand_gather(const float* x, const int64_t* csum, float* out, int32_t* 
 int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, const float* col_scale, void* dst, void* dst_lo, int64_t dst_rs,
                  int32_t dst_cols, int64_t rows, int32_t cols, void* stream);
 
+/* Conv1d weight (N, Cin, k) fp32 -> fp16 operand for all taps in one launch: forward form (k, N, Kp) or, with
+ * transpose_reverse, the dgrad form (k, Cin, N) with the taps reversed; dst_lo (optional) = rounding residual. */
+int osb_pack_conv_h16(const float* w, void* dst, void* dst_lo, int32_t N, int32_t Cin, int32_t k, int32_t Kp,
+                      int32_t transpose_reverse, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * HBM-bound backward kernels (osb_backward.cu).  They replace what torch.autograd derives for the
  * reference modules named at each entry; parameter gradients are ACCUMULATED (+=) into caller-zeroed

@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
         "osb_expand_gather": [P, P, P, P, I32, I32, I32, I32, P],
         "osb_pack_h16": [P, I64, I64, P, P, P, I64, I32, I64, I32, P],
+        "osb_pack_conv_h16": [P, P, P, I32, I32, I32, I32, I32, P],
         "osb_resid_bwd_prep": [P, P, P, P, P, P, P, P, I64, I32, I32, P],
         "osb_colsum_h16": [P, P, I64, I32, P],
         "osb_ln_fold_bwd": [P, P, P, P, P, P, P, I32, I32, P],

@@ -31,24 +31,13 @@ def pack_kn(w: torch.Tensor) -> torch.Tensor:
 
 def pack_conv_fwd(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     """Conv1d weight (N, Cin, k) -> (k, N, Cin_pad) fp16."""
-    N, Cin, k = w.shape
-    Kp = k_pad or Cin
-    w = w.contiguous()
-    out = torch.empty((k, N, Kp), device=w.device, dtype=torch.float16)
-    for tap in range(k):
-        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_cols=Kp, out=out[tap])
-    return out
+    return ops.pack_conv_h16(w, k_pad=k_pad)
 
 
 def pack_conv_bwd(w: torch.Tensor) -> torch.Tensor:
     """Conv1d weight (N, Cin, k) -> dgrad operand (k, Cin, N) fp16 with the taps reversed:
     out[tap', c, n] = w[n, c, k-1-tap']."""
-    N, Cin, k = w.shape
-    w = w.contiguous()
-    out = torch.empty((k, Cin, N), device=w.device, dtype=torch.float16)
-    for tp in range(k):
-        ops.pack_h16(w.view(-1)[k - 1 - tp:], rows=Cin, cols=N, src_ld=k, src_cs=Cin * k, out=out[tp])
-    return out
+    return ops.pack_conv_h16(w, transpose_reverse=True)
 
 
 def _conv_wgrad(g_h16: torch.Tensor, a_h16: torch.Tensor, N: int, Cin: int, k: int, pad: int) -> torch.Tensor:

@@ -45,17 +45,22 @@ __global__ void mas_kernel(const float* __restrict__ lp, const long long* __rest
   }
   qbuf[i] = q;
   __syncthreads();
+  // the log-probability of the next frame is fetched one iteration ahead: the L2 latency of that load would
+  // otherwise sit on the serial critical path of the recursion
+  float lp_next = (T > 1 && i < N) ? lpb[static_cast<long long>(Tx) + i] : 0.f;
   for (int j = 1; j < T; ++j) {
     const int cur = j & 1, prev = cur ^ 1;
+    const float lp_cur = lp_next;
+    if (j + 1 < T && i < N) lp_next = lpb[static_cast<long long>(j + 1) * Tx + i];
     const double left = (i > 0) ? qbuf[prev * nthr + i - 1] : NEG;
     const bool take_left = (i > 0) && (left >= q);
     const unsigned bits = __ballot_sync(0xffffffffu, take_left);
     if ((i & 31) == 0) flags[static_cast<size_t>(j) * words + (i >> 5)] = bits;
     if (i == 0) {
-      row0 = __fadd_rn(row0, lpb[static_cast<long long>(j) * Tx]);
+      row0 = __fadd_rn(row0, lp_cur);
       q = static_cast<double>(row0);
     } else if (i < N && i <= j) {
-      q = fmax(left, q) + static_cast<double>(lpb[static_cast<long long>(j) * Tx + i]);
+      q = fmax(left, q) + static_cast<double>(lp_cur);
     }
     qbuf[cur * nthr + i] = q;
     __syncthreads();
@@ -380,8 +385,12 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
     }
   }
   __syncthreads();
+  // emissions are fetched one frame ahead so that the L2 latency stays off the serial critical path
+  float e_next = (T > 1 && has_tok) ? lp[static_cast<long long>(Tx) + k] : 0.f;
   for (int t = 1; t < T; ++t) {
     const float lt = lse[t];
+    const float e_cur = e_next;
+    if (t + 1 < T && has_tok) e_next = lp[static_cast<long long>(t + 1) * Tx + k];
     if (active) {
       const float pb = prev[2 * k];
       const float pm1 = k > 0 ? prev[2 * k - 1] : NEG;
@@ -389,7 +398,7 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
       cur[2 * k] = nb;
       aw[static_cast<long long>(t) * Smax + 2 * k] = nb;
       if (has_tok) {
-        const float nt = lse3(prev[2 * k + 1], pb, pm1) + (lp[static_cast<long long>(t) * Tx + k] - lt);
+        const float nt = lse3(prev[2 * k + 1], pb, pm1) + (e_cur - lt);
         cur[2 * k + 1] = nt;
         aw[static_cast<long long>(t) * Smax + 2 * k + 1] = nt;
       }
@@ -413,14 +422,22 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
     }
   }
   __syncthreads();
+  float raw_cur = has_tok ? lp[static_cast<long long>(T - 1) * Tx + k] : 0.f;
+  float a_cur = has_tok ? aw[static_cast<long long>(T - 1) * Smax + 2 * k + 1] : 0.f;
   for (int t = T - 1; t >= 0; --t) {
     const float lt = lse[t];
+    float raw_prev = 0.f, a_prev = 0.f;   // frame t-1, fetched while frame t is being processed
+    if (t > 0 && has_tok) {
+      raw_prev = lp[static_cast<long long>(t - 1) * Tx + k];
+      a_prev = aw[static_cast<long long>(t - 1) * Smax + 2 * k + 1];
+    }
     if (has_tok) {
-      const float e = lp[static_cast<long long>(t) * Tx + k] - lt;                 // normalised log-prob of token k
-      const float a = aw[static_cast<long long>(t) * Smax + 2 * k + 1];
-      const float occ = a + prev[2 * k + 1] - e + nll;                             // log posterior occupancy
+      const float e = raw_cur - lt;                                                // normalised log-prob of token k
+      const float occ = a_cur + prev[2 * k + 1] - e + nll;                         // log posterior occupancy
       gr[static_cast<long long>(t) * Tx + k] = gscale * (expf(e) - expf(occ));
     }
+    raw_cur = raw_prev;
+    a_cur = a_prev;
     if (t > 0) {
       const float lt1 = lse[t - 1];
       if (active) {
@@ -428,7 +445,7 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
         cur[2 * k] = nb;
         if (has_tok) {
           const float nt = lse3(prev[2 * k + 1], prev[2 * k + 2], (k + 1 < N) ? prev[2 * k + 3] : NEG) +
-                           (lp[static_cast<long long>(t - 1) * Tx + k] - lt1);
+                           (raw_prev - lt1);
           cur[2 * k + 1] = nt;
         }
       }

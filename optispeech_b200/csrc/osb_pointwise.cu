@@ -384,10 +384,47 @@ __global__ void pack_h16_kernel(const float* __restrict__ src, long long src_ld,
   if (dst_lo != nullptr) dst_lo[r * dst_rs + c] = __float2half_rn(v - __half2float(hi));
 }
 
+// Conv1d weight (N, Cin, k) fp32 -> fp16 tensor-core operand, all taps in one launch.
+//   forward form  (transpose_reverse = 0): dst[tap][n][c] = w[n][c][tap]            (k, N, Kp), zero for c >= Cin
+//   dgrad form    (transpose_reverse = 1): dst[tap][c][n] = w[n][c][k-1-tap]        (k, Cin, N)
+// dst_lo (optional) receives the fp16 rounding residual (split precision).
+__global__ void pack_conv_h16_kernel(const float* __restrict__ w, __half* __restrict__ dst, __half* __restrict__ dst_lo, int N, int Cin,
+                                     int k, int Kp, int transpose_reverse) {
+  const long long total = transpose_reverse ? static_cast<long long>(k) * Cin * N : static_cast<long long>(k) * N * Kp;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float v = 0.f;
+  if (transpose_reverse) {
+    const int n = static_cast<int>(i % N);
+    const int c = static_cast<int>((i / N) % Cin);
+    const int tap = static_cast<int>(i / (static_cast<long long>(N) * Cin));
+    v = w[(static_cast<long long>(n) * Cin + c) * k + (k - 1 - tap)];
+  } else {
+    const int c = static_cast<int>(i % Kp);
+    const int n = static_cast<int>((i / Kp) % N);
+    const int tap = static_cast<int>(i / (static_cast<long long>(Kp) * N));
+    if (c < Cin) v = w[(static_cast<long long>(n) * Cin + c) * k + tap];
+  }
+  const __half hi = __float2half_rn(v);
+  dst[i] = hi;
+  if (dst_lo != nullptr) dst_lo[i] = __float2half_rn(v - __half2float(hi));
+}
+
 }  // namespace
 }  // namespace osb
 
 using namespace osb;
+
+extern "C" int osb_pack_conv_h16(const float* w, void* dst, void* dst_lo, int32_t N, int32_t Cin, int32_t k, int32_t Kp,
+                                 int32_t transpose_reverse, void* stream) {
+  OSB_REQUIRE(w && dst, OSB_ERR_ARG);
+  OSB_REQUIRE(N > 0 && Cin > 0 && k > 0 && (transpose_reverse || Kp >= Cin), OSB_ERR_SHAPE);
+  const long long total = transpose_reverse ? static_cast<long long>(k) * Cin * N : static_cast<long long>(k) * N * Kp;
+  pack_conv_h16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__half*>(dst), static_cast<__half*>(dst_lo), N, Cin, k, Kp, transpose_reverse);
+  count_launch();
+  return launch_status();
+}
 
 extern "C" int osb_embed_text(const int64_t* ids, const float* table, const float* inv_freq, const float* scale, float* out,
                               int32_t B, int32_t T, int32_t dim, int32_t n_vocab, void* stream) {

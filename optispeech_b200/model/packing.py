@@ -53,11 +53,4 @@ def pack_conv(weight: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
     """Conv1d weight (N, Cin, k) fp32 -> (2, k, N, Cin_pad) fp16 hi/lo (one K-major matrix per tap)."""
     from .. import ops
 
-    N, Cin, k = weight.shape
-    Kp = k_pad or Cin
-    w = weight.detach().contiguous()
-    out = torch.empty((2, k, N, Kp), device=w.device, dtype=torch.float16)
-    for tap in range(k):
-        # element (n, c) of tap lives at w[n, c, tap] = base + n*Cin*k + c*k + tap
-        ops.pack_h16(w.view(-1)[tap:], rows=N, cols=Cin, src_ld=Cin * k, src_cs=k, dst_cols=Kp, out=out[0, tap], out_lo=out[1, tap])
-    return out
+    return ops.pack_conv_h16(weight.detach(), k_pad=k_pad, split=True)

@@ -372,3 +372,17 @@ def forward_sum(log_p_attn, x_len, m_len, blank_logit: float = -1.0):
     _lib.check(_lib.load().osb_forward_sum(_ptr(_f32(log_p_attn)), _ptr(x_len), _ptr(m_len), float(blank_logit), _ptr(ws), _ptr(loss),
                                            _ptr(grad), B, Tm, Tx, _stream()), "osb_forward_sum")
     return loss, grad
+
+
+def pack_conv_h16(w: torch.Tensor, k_pad: Optional[int] = None, transpose_reverse: bool = False, split: bool = False):
+    """Conv1d weight (N, Cin, k) fp32 -> fp16 operand in one launch: (k, N, Kp) forward form or (k, Cin, N) tap-reversed
+    dgrad form; with split -> (2, ...) hi / lo."""
+    N, Cin, k = w.shape
+    Kp = k_pad or Cin
+    shape = (k, Cin, N) if transpose_reverse else (k, N, Kp)
+    out = torch.empty(((2,) + shape) if split else shape, device=w.device, dtype=torch.float16)
+    lo = out[1] if split else None
+    dst = out[0] if split else out
+    _lib.check(_lib.load().osb_pack_conv_h16(_ptr(_f32(w.contiguous())), _ptr(dst), _ptr(lo), N, Cin, k, Kp, int(transpose_reverse),
+                                             _stream()), "osb_pack_conv_h16")
+    return out

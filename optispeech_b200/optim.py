@@ -104,7 +104,6 @@ class FlatAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm: Optional[float] = None):
-        lib = _lib.load()
         max_norm = self.max_grad_norm if max_grad_norm is None else float(max_grad_norm)
         for gi, group in enumerate(self.param_groups):
             b = self._bucket_for(gi, group)
@@ -114,17 +113,23 @@ class FlatAdamW(torch.optim.Optimizer):
                 torch.distributed.all_reduce(b.flat_g, group=self.process_group)
             step = self._steps.get(gi, 0) + 1
             self._steps[gi] = step
-            b.stats.zero_()
-            _lib.check(lib.osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
-            beta1, beta2 = group["betas"]
+            # the all-reduce SUMS the ranks' gradients; the 1/world factor is folded into the unscale factor
             inv_scale = 1.0 / (self.loss_scale * self.world_size)
-            _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
-                                          b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                          float(group["weight_decay"]), step, max_norm, inv_scale, _stream()), "osb_adamw_step")
+            self._kernel_step(b, group, step, max_norm, inv_scale)
             self.last_stats = b.stats
             for p in b.params:  # invalidate packed fp16 copies of these weights (model/packing.py)
                 p._osb_epoch = getattr(p, "_osb_epoch", 0) + 1
         return None
+
+    def _kernel_step(self, b: _Bucket, group, step: int, max_norm: float, inv_scale: float) -> None:
+        """Two launches over the flat bucket: global norm (+ non-finite flag), then unscale + clip + AdamW."""
+        lib = _lib.load()
+        b.stats.zero_()
+        _lib.check(lib.osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
+        beta1, beta2 = group["betas"]
+        _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
+                                      b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
+                                      float(group["weight_decay"]), step, max_norm, inv_scale, _stream()), "osb_adamw_step")
 
     def grad_norm(self) -> float:
         """Unscaled global gradient norm of the last step (reads a device scalar: call outside the hot loop)."""

@@ -1,0 +1,165 @@
+"""Drop-in boundary on the CPU: config composition / instantiation, dotted-path aliases, class surface, state_dict
+layout, checkpoint round trip, value containers, host-side helpers.  No kernels are launched."""
+import functools
+import inspect
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def model():
+    from optispeech_b200.config import build_from_config
+
+    torch.manual_seed(0)
+    return build_from_config("optispeech")
+
+
+def test_compose_matches_reference_yaml_semantics():
+    from optispeech_b200.config import compose_model
+
+    cfg = compose_model("optispeech")
+    assert cfg["_target_"] == "optispeech.model.OptiSpeech" and cfg["dim"] == 256
+    gen = cfg["generator"]
+    assert gen["_target_"] == "optispeech.model.generator.OptiSpeechGenerator" and gen["_partial_"] is True
+    assert gen["encoder"]["_target_"].endswith("ConvNeXtBackbone") and gen["encoder"]["num_layers"] == 4
+    assert gen["pitch_predictor"]["kernel_size"] == 5 and gen["pitch_predictor"]["conv_layer_class"]["_target_"] == "torch.nn.Conv1d"
+    assert cfg["vocoder"]["dim"] == 384 and cfg["vocoder"]["intermediate_dim"] == 1152 and cfg["vocoder"]["num_layers"] == 8
+    assert cfg["optimizer"]["lr"] == pytest.approx(2e-4) and cfg["optimizer"]["betas"] == [0.8, 0.99]
+    assert cfg["data_args"]["feature_extractor"]["sample_rate"] == 22050      # ${data.feature_extractor} interpolation
+    assert cfg["train_args"]["pretraining_steps"] == 1000 and cfg["inference_args"]["p_factor"] == 1.6
+    # `override generator/encoder: transformer` of configs/model/transformer.yaml
+    tcfg = compose_model("transformer")
+    assert tcfg["generator"]["encoder"]["_target_"].endswith("modules.Transformer")
+    assert tcfg["generator"]["decoder"]["attention_heads"] == 2
+    assert tcfg["generator"]["duration_predictor"]["_target_"].endswith("DurationPredictor")
+
+
+def test_instantiated_model_has_reference_layout(model):
+    from optispeech_b200.model import OptiSpeech
+    from optispeech_b200.model.generator import OptiSpeechGenerator
+
+    assert isinstance(model, OptiSpeech) and isinstance(model.generator, OptiSpeechGenerator)
+    with open(os.path.join(GOLD, "state_dict_shapes.json")) as f:
+        ref = json.load(f)["full"]
+    mine = {k: list(v.shape) for k, v in model.generator.state_dict().items()}
+    assert mine == ref, "generator state_dict keys/shapes differ from the reference module's"
+    assert sum(p.numel() for p in model.discriminator.parameters()) == 41_705_968
+    sd = model.state_dict()
+    for k in ("discriminator.melspec_loss.mel_spec.spectrogram.window", "discriminator.melspec_loss.mel_spec.mel_scale.fb",
+              "discriminator.mr_stft_loss.stft_losses.2.window", "discriminator.multiperioddisc.discriminators.0.convs.0.weight_g"):
+        assert k in sd, k
+    assert "generator.text_embedding.embed_positions.inv_freq" not in sd  # non-persistent buffer, as in the reference
+    assert model.sample_rate == 22050 and model.hop_length == 256
+    assert isinstance(model.hparams.optimizer, functools.partial) and model.hparams.optimizer.func is torch.optim.AdamW
+
+
+def test_dotted_paths_of_the_reference_resolve_to_this_implementation():
+    import importlib
+
+    import optispeech_b200.model.generator.modules as real
+
+    alias = importlib.import_module("optispeech.model.generator.modules")
+    assert alias is real
+    from optispeech.model import OptiSpeech as A
+    from optispeech_b200.model import OptiSpeech as B
+
+    assert A is B
+    from optispeech.model.vocoder.wavenext.disc import VocosDiscriminator  # noqa: F401
+    from optispeech.values import InferenceInputs  # noqa: F401
+
+
+def test_constructor_signatures_match_reference():
+    from optispeech_b200.model import OptiSpeech
+    from optispeech_b200.model.generator import OptiSpeechGenerator
+    from optispeech_b200.model.generator.modules import ConvNeXtBackbone, ConvNeXtBlock, TextEmbedding, VariancePredictor
+    from optispeech_b200.model.vocoder.wavenext import WaveNeXt
+
+    def names(fn):
+        return [p for p in inspect.signature(fn).parameters if p != "self"]
+
+    assert names(OptiSpeech.__init__) == ["dim", "generator", "vocoder", "discriminator", "train_args", "data_args", "inference_args",
+                                          "optimizer", "scheduler"]
+    assert names(OptiSpeechGenerator.__init__) == ["dim", "segment_size", "text_embedding", "encoder", "duration_predictor",
+                                                   "pitch_predictor", "energy_predictor", "decoder", "vocoder", "loss_coeffs",
+                                                   "feature_extractor", "num_speakers", "num_languages", "data_statistics", "kwargs"]
+    assert names(ConvNeXtBackbone.__init__) == ["dim", "intermediate_dim", "num_layers", "drop_path", "layer_scale_init_value"]
+    assert names(ConvNeXtBlock.__init__) == ["dim", "intermediate_dim", "drop_path", "layer_scale_init_value"]
+    assert names(WaveNeXt.__init__) == ["input_channels", "dim", "intermediate_dim", "num_layers", "n_fft", "hop_length", "sample_rate",
+                                        "drop_path", "layer_scale_init_value"]
+    assert names(TextEmbedding.__init__) == ["dim", "n_vocab", "dropout", "padding_idx", "max_source_positions"]
+    assert names(VariancePredictor.__init__) == ["dim", "num_layers", "intermediate_dim", "kernel_size", "dropout", "conv_layer_class"]
+    assert names(OptiSpeechGenerator.synthesise)[:7] == ["x", "x_lengths", "sids", "lids", "d_factor", "p_factor", "e_factor"]
+    assert names(OptiSpeechGenerator.forward) == ["x", "x_lengths", "mel", "mel_lengths", "pitches", "energies", "sids", "lids"]
+
+
+def test_reference_error_conventions():
+    from optispeech_b200.factory import build_model
+
+    with pytest.raises(ValueError, match="gradient_accumulate_batches"):
+        build_model(train_args=dict(gradient_accumulate_batches=0))
+    from optispeech_b200.factory import DEFAULT_MODEL
+
+    bad = dict(DEFAULT_MODEL, num_speakers=0)
+    with pytest.raises(ValueError, match="num_speakers"):
+        build_model(bad)
+    m = build_model()
+    with pytest.raises(RuntimeError, match="text_processor"):
+        m.prepare_input("hello")
+
+
+def test_checkpoint_round_trip(model, tmp_path):
+    from optispeech_b200.model import OptiSpeech
+
+    path = tmp_path / "m.ckpt"
+    model.save_checkpoint(str(path), epoch=7, global_step=123)
+    loaded = OptiSpeech.load_from_checkpoint(str(path), map_location="cpu")
+    assert loaded.ckpt_loaded_epoch == 7
+    a, b = model.state_dict(), loaded.state_dict()
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_value_containers():
+    from optispeech_b200.values import InferenceInputs, InferenceOutputs, numpy_pad_sequences, numpy_unpad_sequences
+
+    inp = InferenceInputs.from_ids_and_lengths([[1, 2, 3], [4, 5]], [3, 2], clean_text="x", d_factor=1.1)
+    assert isinstance(inp.x, np.ndarray) and inp.x.dtype == np.int64 and inp.x.tolist() == [[1, 2, 3], [4, 5, 0]]
+    t = inp.as_torch()
+    assert isinstance(t.x, torch.Tensor) and t.x_lengths.tolist() == [3, 2] and t.d_factor == 1.1
+    out = InferenceOutputs(wav=np.zeros((2, 10), dtype=np.float32), wav_lengths=np.array([10, 4]), latency=1, rtf=0.1)
+    assert [len(w) for w in out] == [10, 4]
+    out_t = InferenceOutputs(wav=torch.zeros(2, 10), wav_lengths=torch.tensor([10, 4]), latency=1, rtf=0.1)
+    assert [len(w) for w in out_t.unbatched_wavs()] == [10, 4]
+    assert numpy_pad_sequences([[1], [1, 2]]).shape == (2, 2)
+    with pytest.raises(ValueError):
+        numpy_unpad_sequences(np.zeros((2, 3)), np.array([4, 1]))
+
+
+def test_host_helpers_match_oracle():
+    from optispeech_b200.utils import get_segments, get_segments_numpy, sequence_mask
+    from oracle import model as O
+
+    lens = torch.tensor([5, 2, 7])
+    assert torch.equal(sequence_mask(lens, 7), O.sequence_mask(lens, 7))
+    x = torch.arange(2 * 3 * 20, dtype=torch.float32).view(2, 3, 20)
+    starts = torch.tensor([4, 11])
+    seg = get_segments(x, starts, 6)
+    ref = torch.stack([x[0, :, 4:10], x[1, :, 11:17]])
+    assert torch.equal(seg, ref)
+    assert np.array_equal(get_segments_numpy(x.numpy(), starts.numpy(), 6), ref.numpy())
+
+
+def test_prior_table_matches_scipy_golden():
+    from optispeech_b200.model.generator.training import AlignmentModule
+
+    fx = np.load(os.path.join(GOLD, "algorithms.npz"))
+    for T, N in [(5, 3), (31, 9), (110, 24)]:
+        assert np.abs(AlignmentModule._log_prior(T, N) - fx[f"prior_{T}_{N}"]).max() <= 1e-9

@@ -1,0 +1,74 @@
+"""Data-parallel plumbing with world_size 2 on the gloo backend (CPU): one flat gradient bucket per optimizer is
+all-reduced, and every rank ends up with the parameters a single process would get from the mean gradient.
+
+The CUDA update kernels cannot run here; the test substitutes a torch restatement of the two launches
+(`_kernel_step`) — test infrastructure only — so that bucket construction, static membership, the all-reduce and the
+1/world scaling are exercised exactly as on the GPU."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _torch_kernel_step(self, b, group, step, max_norm, inv_scale):
+    g = b.flat_g * inv_scale
+    total = g.norm()
+    coef = min(1.0, max_norm / (float(total) + 1e-6)) if max_norm > 0 else 1.0
+    g = g * coef
+    beta1, beta2 = group["betas"]
+    b.flat_p.mul_(1 - group["lr"] * group["weight_decay"])
+    b.m.mul_(beta1).add_(g, alpha=1 - beta1)
+    b.v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    b.flat_p.addcdiv_(b.m, (b.v.sqrt() / bc2 ** 0.5).add_(group["eps"]), value=-group["lr"] / bc1)
+    b.stats[0] = (b.flat_g ** 2).sum()
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from optispeech_b200.optim import FlatAdamW
+
+    FlatAdamW._kernel_step = _torch_kernel_step
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(17, 5)), torch.nn.Parameter(torch.randn(33)), torch.nn.Parameter(torch.randn(4, 4))]
+    frozen = torch.nn.Parameter(torch.randn(6))  # never receives a gradient on any rank: static membership excludes it
+    opt = FlatAdamW([{"params": params + [frozen]}], lr=1e-2, betas=(0.8, 0.99), weight_decay=1e-2, max_grad_norm=10.0, loss_scale=8.0,
+                    world_size=world)
+    for it in range(3):
+        opt.zero_grad()
+        g = torch.Generator().manual_seed(100 * it + rank)
+        for p in params:
+            gr = torch.randn(p.shape, generator=g) * 8.0  # carries the loss scale
+            if p.grad is None:
+                p.grad = gr
+            else:
+                p.grad.add_(gr)
+        opt.step()
+    torch.save([p.detach().clone() for p in params] + [frozen.detach().clone()], os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucket_allreduce_matches_single_process(tmp_path):
+    port = 29500 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / "rank0.pt")
+    r1 = torch.load(tmp_path / "rank1.pt")
+    for a, b in zip(r0, r1):
+        assert torch.equal(a, b), "ranks diverged"
+    # single-process reference: torch.optim.AdamW on the mean gradient with clip_grad_norm_(10)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(17, 5)), torch.nn.Parameter(torch.randn(33)), torch.nn.Parameter(torch.randn(4, 4))]
+    frozen = torch.randn(6)
+    opt = torch.optim.AdamW(params, lr=1e-2, betas=(0.8, 0.99), weight_decay=1e-2)
+    for it in range(3):
+        gens = [torch.Generator().manual_seed(100 * it + r) for r in range(2)]
+        for p in params:
+            p.grad = sum(torch.randn(p.shape, generator=g) for g in gens) / 2
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+    for a, b in zip(r0[:3], params):
+        assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(r0[3], frozen), "parameter without gradient must stay untouched (no weight decay)"
