@@ -318,6 +318,26 @@ int osb_transpose_pack_h16(const float* x, void* out_h16, int32_t B, int32_t T, 
 /* out[row,:] = sign * row_scale[row] * x[row,:] */
 int osb_scale_rows(const float* x, const float* row_scale, float* out, int64_t rows, int32_t C, float sign, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused STFT-domain reconstruction losses (osb_spectral.cu): one CTA per frame, shared-memory FFT of the
+ * prediction and the target together, loss partial sums; the backward variant adds d(loss)/d(x_hat).
+ * ------------------------------------------------------------------------------------- */
+
+/* One resolution of MultiResolutionSTFTLoss (disc/loss.py:123-142,197-270): centre/reflect framing, `window` (win values,
+ * centred in n_fft), magnitudes sqrt(clamp(re^2+im^2, clamp_min)).  n_fft in {512, 1024, 2048}.
+ *   forward  (dx_hat == NULL): stats[0] += sum (Ym-Xm)^2, stats[1] += sum Ym^2, stats[2] += sum |log Ym - log Xm|
+ *   backward (dx_hat != NULL): dx_hat += coef[0] * d(sqrt(S1))*sqrt(S1).. i.e. with coef[0] = dL/dSC / (sqrt(S1) sqrt(S2)) and
+ *                              coef[1] = dL/dMAG / count the kernel accumulates dL/dx_hat (fp32 atomics; caller zeroes dx_hat). */
+int osb_stft_loss(const float* x_hat, const float* y, const float* window, int32_t B, int32_t L, int32_t n_fft, int32_t hop,
+                  int32_t win, float clamp_min, double* stats, const float* coef, float* dx_hat, void* stream);
+
+/* MelSpecReconstructionLoss (disc/loss.py:88-120): |STFT| (no clamp) -> fb (n_fft/2+1, n_mels) -> log(clip(., clamp_min)) -> L1.
+ * klo/khi (n_mels): first/last non-zero bin of each filter; jlo/jhi (n_fft/2+1): first/last filter covering each bin.
+ *   forward: stats[2] += sum |log mel_y - log mel_x| ; backward: coef[1] = dL/dMEL / count. */
+int osb_mel_loss(const float* x_hat, const float* y, const float* window, const float* fb, const int32_t* klo, const int32_t* khi,
+                 const int32_t* jlo, const int32_t* jhi, int32_t n_mels, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t win,
+                 float clamp_min, double* stats, const float* coef, float* dx_hat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,6 +115,8 @@ def load() -> C.CDLL:
         "osb_attn_bwd_prep": [P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_transpose_pack_h16": [P, P, I32, I32, I32, I32, P],
         "osb_scale_rows": [P, P, P, I64, I32, F, P],
+        "osb_stft_loss": [P, P, P, I32, I32, I32, I32, I32, F, P, P, P, P],
+        "osb_mel_loss": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F, P, P, P, P],
         "osb_grad_sumsq": [P, I64, P, P],
         "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],

@@ -322,13 +322,15 @@ extern "C" int osb_scale_rows(const float* x, const float* row_scale, float* out
 namespace osb {
 namespace {
 
+// log-sum-exp of the recursion: the arguments of exp are <= 0 and the sum lies in [1, 3], where the hardware
+// ex2 / lg2 approximations are accurate to ~1e-7 absolute; this halves the length of the serial dependency chain.
 __device__ __forceinline__ float lse2(float a, float b) {
   const float m = fmaxf(a, b);
-  return m == -INFINITY ? -INFINITY : m + logf(expf(a - m) + expf(b - m));
+  return m == -INFINITY ? -INFINITY : m + __logf(__expf(a - m) + __expf(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(fmaxf(a, b), c);
-  return m == -INFINITY ? -INFINITY : m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m == -INFINITY ? -INFINITY : m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
 __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,

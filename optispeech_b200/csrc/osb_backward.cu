@@ -109,7 +109,23 @@ colsum_h16_kernel(const __half* __restrict__ x, float* __restrict__ out, long lo
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long r = r0; r < r1; ++r) {
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {  // four independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(x + (r + q) * N + c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[q]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+  for (; r < r1; ++r) {
     const uint4 u = *reinterpret_cast<const uint4*>(x + r * N + c);
     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -460,8 +476,8 @@ extern "C" int osb_colsum_h16(const void* x_h16, float* out, int64_t rows, int32
   OSB_REQUIRE(x_h16 && out, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && N > 0 && N % 8 == 0, OSB_ERR_SHAPE);
   const int gx = (N / 8 + 255) / 256;
-  int rpb = static_cast<int>((rows + 147) / 148);
-  if (rpb < 32) rpb = 32;
+  int rpb = static_cast<int>((rows + 148 * 4 - 1) / (148 * 4));
+  if (rpb < 16) rpb = 16;
   const int gy = static_cast<int>((rows + rpb - 1) / rpb);
   colsum_h16_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), out, rows, N, rpb);
   count_launch();

@@ -877,8 +877,10 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
   p.per_batch = per_batch;
   const int zcount = per_batch ? B : taps;
   const int total_rb = per_batch ? p.row_blocks_per_batch : B * p.row_blocks_per_batch;
-  int splits = (2 * 148 + n_tiles * k_tiles * zcount - 1) / (n_tiles * k_tiles * zcount);
-  if (splits > total_rb) splits = total_rb;
+  // Split the contraction rows over CTAs to fill the machine, but keep >= 6 pipeline iterations per CTA: every CTA pays a
+  // fixed prologue and flushes a 128x128 fp32 tile with atomics, so over-splitting small problems costs more than it gains.
+  int splits = (148 + n_tiles * k_tiles * zcount - 1) / (n_tiles * k_tiles * zcount);
+  if (splits > total_rb / 6) splits = total_rb / 6;
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.dw = dw;

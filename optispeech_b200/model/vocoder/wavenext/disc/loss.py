@@ -58,6 +58,15 @@ class _MelSpec(nn.Module):
         super().__init__()
         self.spectrogram = _Spectrogram(win_length)
         self.mel_scale = _MelScale(n_fft // 2 + 1, n_mels, sample_rate, f_min, f_max)
+        self._ranges = None
+
+    def ranges(self):
+        """Non-zero extents of the triangular filters (derived from `fb`, cached; recomputed if `fb` was reloaded)."""
+        fb = self.mel_scale.fb
+        key = (fb.data_ptr(), fb._version, str(fb.device))
+        if self._ranges is None or self._ranges[0] != key:
+            self._ranges = (key, spectral.filterbank_ranges(fb).to(fb.device))
+        return self._ranges[1]
 
 
 def htk_mel_filterbank(n_freqs: int, n_mels: int, sample_rate: int, f_min: float, f_max: float) -> Tensor:
@@ -84,8 +93,8 @@ class MelSpecReconstructionLoss(nn.Module):
         self.mel_spec = _MelSpec(sample_rate, n_fft, win_length, n_mels, f_min, f_max)
 
     def forward(self, y_hat: Tensor, y: Tensor) -> Tensor:
-        return spectral.mel_l1_loss(y_hat, y, self.mel_spec.spectrogram.window, self.mel_spec.mel_scale.fb, self.n_fft,
-                                    self.hop_length, self.win_length, self.clip_val)
+        return spectral.mel_l1_loss(y_hat, y, self.mel_spec.spectrogram.window, self.mel_spec.mel_scale.fb, self.mel_spec.ranges(),
+                                    self.n_fft, self.hop_length, self.win_length, self.clip_val)
 
 
 class STFTLoss(nn.Module):

@@ -1,31 +1,112 @@
-"""Spectral reconstruction losses: framing (centre / reflect), Hann window, rFFT, magnitude, reductions.
+"""Spectral reconstruction losses on the B200 path: fused framing + window + FFT + magnitude + reduction kernels
+(osb_spectral.cu) with hand-written gradients.
 
 Semantics follow reference disc/loss.py:123-142 (`stft`: sqrt(clamp(re^2+im^2, 1e-7))), :231-270 (spectral
 convergence = ||Y - X||_F / ||Y||_F over the whole batch tensor; log-magnitude L1) and :109-120 (log-mel L1,
-magnitudes NOT clamped before the filterbank, log(clip(., 1e-7)) after).
+magnitudes NOT clamped before the filterbank, log(clip(., 1e-7)) after).  `x_hat` is the prediction (receives the
+gradient), `y` the ground truth.
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
+from torch.autograd import Function
+
+from ..... import _lib
 
 
-def _stft_power(x: torch.Tensor, n_fft: int, hop: int, win: int, window: torch.Tensor) -> torch.Tensor:
-    spec = torch.stft(x, n_fft, hop, win, window, center=True, pad_mode="reflect", return_complex=True)
-    return spec.real ** 2 + spec.imag ** 2  # (B, bins, frames)
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise _lib.OsbError("spectral losses run on the B200 kernels only (no CPU fallback)")
+
+
+class _STFTLossFn(Function):
+    @staticmethod
+    def forward(ctx, x_hat, y, window, n_fft, hop, win):
+        _check_cuda(x_hat, y, window)
+        x_hat, y = x_hat.contiguous().float(), y.contiguous().float()
+        B, L = x_hat.shape
+        stats = torch.zeros(3, device=x_hat.device, dtype=torch.float64)
+        _lib.check(_lib.load().osb_stft_loss(x_hat.data_ptr(), y.data_ptr(), window.data_ptr(), B, L, n_fft, hop, win, 1e-7,
+                                             stats.data_ptr(), None, None, _stream()), "osb_stft_loss")
+        count = B * (1 + L // hop) * (n_fft // 2 + 1)
+        sc = (stats[0].sqrt() / stats[1].sqrt()).float()
+        mag = (stats[2] / count).float()
+        ctx.save_for_backward(x_hat, y, window, stats)
+        ctx.cfg = (n_fft, hop, win, count)
+        return sc, mag
+
+    @staticmethod
+    def backward(ctx, d_sc, d_mag):
+        x_hat, y, window, stats = ctx.saved_tensors
+        n_fft, hop, win, count = ctx.cfg
+        B, L = x_hat.shape
+        coef = torch.stack([d_sc.double() / (stats[0].sqrt() * stats[1].sqrt()), d_mag.double() / count]).float().contiguous()
+        dx = torch.zeros_like(x_hat)
+        _lib.check(_lib.load().osb_stft_loss(x_hat.data_ptr(), y.data_ptr(), window.data_ptr(), B, L, n_fft, hop, win, 1e-7,
+                                             stats.data_ptr(), coef.data_ptr(), dx.data_ptr(), _stream()), "osb_stft_loss(bwd)")
+        return dx, None, None, None, None, None
+
+
+class _MelLossFn(Function):
+    @staticmethod
+    def forward(ctx, x_hat, y, window, fb, ranges, n_fft, hop, win, clip_val):
+        _check_cuda(x_hat, y, window, fb, ranges)
+        x_hat, y = x_hat.contiguous().float(), y.contiguous().float()
+        B, L = x_hat.shape
+        n_mels = fb.shape[1]
+        nb = n_fft // 2 + 1
+        stats = torch.zeros(3, device=x_hat.device, dtype=torch.float64)
+        ptrs = _range_ptrs(ranges, n_mels, nb)
+        _lib.check(_lib.load().osb_mel_loss(x_hat.data_ptr(), y.data_ptr(), window.data_ptr(), fb.data_ptr(), *ptrs, n_mels, B, L, n_fft,
+                                            hop, win, clip_val, stats.data_ptr(), None, None, _stream()), "osb_mel_loss")
+        count = B * (1 + L // hop) * n_mels
+        ctx.save_for_backward(x_hat, y, window, fb, ranges, stats)
+        ctx.cfg = (n_fft, hop, win, clip_val, count)
+        return (stats[2] / count).float()
+
+    @staticmethod
+    def backward(ctx, d_mel):
+        x_hat, y, window, fb, ranges, stats = ctx.saved_tensors
+        n_fft, hop, win, clip_val, count = ctx.cfg
+        B, L = x_hat.shape
+        n_mels = fb.shape[1]
+        coef = torch.stack([torch.zeros((), device=x_hat.device, dtype=torch.float64), d_mel.double() / count]).float().contiguous()
+        dx = torch.zeros_like(x_hat)
+        ptrs = _range_ptrs(ranges, n_mels, n_fft // 2 + 1)
+        _lib.check(_lib.load().osb_mel_loss(x_hat.data_ptr(), y.data_ptr(), window.data_ptr(), fb.data_ptr(), *ptrs, n_mels, B, L, n_fft,
+                                            hop, win, clip_val, stats.data_ptr(), coef.data_ptr(), dx.data_ptr(), _stream()),
+                   "osb_mel_loss(bwd)")
+        return dx, None, None, None, None, None, None, None, None
+
+
+def _range_ptrs(ranges: torch.Tensor, n_mels: int, nb: int):
+    """ranges is one int32 vector [klo (n_mels) | khi (n_mels) | jlo (nb) | jhi (nb)]."""
+    base, es = ranges.data_ptr(), 4
+    return base, base + es * n_mels, base + es * 2 * n_mels, base + es * (2 * n_mels + nb)
+
+
+def filterbank_ranges(fb: torch.Tensor) -> torch.Tensor:
+    """First / last non-zero frequency bin of every mel filter and first / last filter covering every bin (int32)."""
+    nz = (fb.detach().cpu().numpy() != 0)
+    nb, n_mels = nz.shape
+    klo = np.where(nz.any(0), nz.argmax(0), 0)
+    khi = np.where(nz.any(0), nb - 1 - nz[::-1].argmax(0), -1)
+    jlo = np.where(nz.any(1), nz.argmax(1), 0)
+    jhi = np.where(nz.any(1), n_mels - 1 - nz[:, ::-1].argmax(1), -1)
+    return torch.from_numpy(np.concatenate([klo, khi, jlo, jhi]).astype(np.int32))
 
 
 def stft_sc_mag_loss(x_hat, y, window, n_fft: int, hop: int, win: int):
-    xm = torch.sqrt(torch.clamp(_stft_power(x_hat, n_fft, hop, win, window), min=1e-7))
-    ym = torch.sqrt(torch.clamp(_stft_power(y, n_fft, hop, win, window), min=1e-7))
-    sc = torch.linalg.norm((ym - xm).reshape(-1)) / torch.linalg.norm(ym.reshape(-1))
-    mag = (torch.log(ym) - torch.log(xm)).abs().mean()
-    return sc, mag
+    return _STFTLossFn.apply(x_hat, y, window.contiguous().float(), n_fft, hop, win)
 
 
-def mel_l1_loss(x_hat, y, window, fb, n_fft: int, hop: int, win: int, clip_val: float = 1e-7):
-    def log_mel(sig):
-        mag = torch.sqrt(_stft_power(sig, n_fft, hop, win, window))       # (B, bins, frames), power=1, no clamp
-        mel = torch.matmul(mag.transpose(1, 2), fb)                        # (B, frames, n_mels)
-        return torch.log(torch.clip(mel, min=clip_val))
-
-    return (log_mel(y) - log_mel(x_hat)).abs().mean()
+def mel_l1_loss(x_hat, y, window, fb, ranges, n_fft: int, hop: int, win: int, clip_val: float = 1e-7):
+    return _MelLossFn.apply(x_hat, y, window.contiguous().float(), fb.contiguous().float(), ranges, n_fft, hop, win, clip_val)
