@@ -47,23 +47,35 @@ __global__ void mas_kernel(const float* __restrict__ lp, const long long* __rest
   __syncthreads();
   // the log-probability of the next frame is fetched one iteration ahead: the L2 latency of that load would
   // otherwise sit on the serial critical path of the recursion
-  float lp_next = (T > 1 && i < N) ? lpb[static_cast<long long>(Tx) + i] : 0.f;
-  for (int j = 1; j < T; ++j) {
-    const int cur = j & 1, prev = cur ^ 1;
-    const float lp_cur = lp_next;
-    if (j + 1 < T && i < N) lp_next = lpb[static_cast<long long>(j + 1) * Tx + i];
-    const double left = (i > 0) ? qbuf[prev * nthr + i - 1] : NEG;
-    const bool take_left = (i > 0) && (left >= q);
-    const unsigned bits = __ballot_sync(0xffffffffu, take_left);
-    if ((i & 31) == 0) flags[static_cast<size_t>(j) * words + (i >> 5)] = bits;
-    if (i == 0) {
-      row0 = __fadd_rn(row0, lp_cur);
-      q = static_cast<double>(row0);
-    } else if (i < N && i <= j) {
-      q = fmax(left, q) + static_cast<double>(lp_cur);
+  constexpr int G = 8;
+  float lpc[G], lpn[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) lpc[g] = (1 + g < T && i < N) ? lpb[static_cast<long long>(1 + g) * Tx + i] : 0.f;
+  for (int base = 1; base < T; base += G) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) lpn[g] = (base + G + g < T && i < N) ? lpb[static_cast<long long>(base + G + g) * Tx + i] : 0.f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int j = base + g;
+      if (j < T) {  // uniform across the block
+        const int cur = j & 1, prev = cur ^ 1;
+        const float lp_cur = lpc[g];
+        const double left = (i > 0) ? qbuf[prev * nthr + i - 1] : NEG;
+        const bool take_left = (i > 0) && (left >= q);
+        const unsigned bits = __ballot_sync(0xffffffffu, take_left);
+        if ((i & 31) == 0) flags[static_cast<size_t>(j) * words + (i >> 5)] = bits;
+        if (i == 0) {
+          row0 = __fadd_rn(row0, lp_cur);
+          q = static_cast<double>(row0);
+        } else if (i < N && i <= j) {
+          q = fmax(left, q) + static_cast<double>(lp_cur);
+        }
+        qbuf[cur * nthr + i] = q;
+        __syncthreads();
+      }
     }
-    qbuf[cur * nthr + i] = q;
-    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < G; ++g) lpc[g] = lpn[g];
   }
   if (i == 0) {
     int a = N - 1;
@@ -333,133 +345,148 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m == -INFINITY ? -INFINITY : m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
+// per-frame normaliser over [blank | tokens < N]: one warp per (b, t) row, full grid
+__global__ void fs_lse_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
+                              float blank_logit, float* __restrict__ lse_ws, int B, int Tm, int Tx) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(B) * Tm) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  if (t >= T) {
+    if (lane == 0) lse_ws[row] = 0.f;
+    return;
+  }
+  const float* lp = lpa + row * Tx;
+  float m = blank_logit;
+  for (int i = lane; i < N; i += 32) m = fmaxf(m, lp[i]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < N; i += 32) s += expf(lp[i] - m);
+  s = warp_sum(s) + expf(blank_logit - m);
+  if (lane == 0) lse_ws[row] = m + logf(s);
+}
+
+constexpr int FS_G = 8;  // emissions are fetched FS_G frames ahead (registers) so that L2 latency stays off the serial chain
+
+// The serial part: alpha (t = 1 .. T-1) and beta (t = T-2 .. 0) advance in the SAME iteration (independent chains: half
+// the barrier steps).  One CTA per sample; thread k owns blank state 2k and token state 2k+1.
 __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
-                                   float blank_logit, float* __restrict__ alpha_ws, float* __restrict__ loss, float* __restrict__ grad,
-                                   int B, int Tm, int Tx) {
+                                   float blank_logit, const float* __restrict__ lse_ws, float* __restrict__ aw_all,
+                                   float* __restrict__ bw_all, float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx) {
   extern __shared__ float fs_smem[];
   const int b = blockIdx.x;
   const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
   const int S = 2 * N + 1;
   const int Smax = 2 * Tx + 1;
   const int k = threadIdx.x;
-  float* buf0 = fs_smem;              // [Smax + 2] with one -inf guard on each side handled by index checks
-  float* buf1 = buf0 + Smax;
-  float* lse = buf1 + Smax;           // [Tm]
+  float* abuf0 = fs_smem;
+  float* abuf1 = abuf0 + Smax;
+  float* bbuf0 = abuf1 + Smax;
+  float* bbuf1 = bbuf0 + Smax;
+  float* lse = bbuf1 + Smax;  // [Tm]
   const float* lp = lpa + static_cast<long long>(b) * Tm * Tx;
-  float* gr = grad + static_cast<long long>(b) * Tm * Tx;
-  float* aw = alpha_ws + static_cast<long long>(b) * Tm * Smax;
+  float* aw = aw_all + static_cast<long long>(b) * Tm * Tx;
+  float* bw = bw_all + static_cast<long long>(b) * Tm * Tx;
   const float NEG = -INFINITY;
-
   if (N <= 0 || T <= 0) {
-    for (int i = k; i < Tm * Tx; i += blockDim.x) gr[i] = 0.f;
-    if (k == 0) loss[b] = 0.f;
+    if (k == 0) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
     return;
   }
-  // per-frame normaliser over [blank | tokens < N]
-  const int warp = k >> 5, lane = k & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < T; t += nwarps) {
-    float m = blank_logit;
-    for (int i = lane; i < N; i += 32) m = fmaxf(m, lp[static_cast<long long>(t) * Tx + i]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int i = lane; i < N; i += 32) s += expf(lp[static_cast<long long>(t) * Tx + i] - m);
-    s = warp_sum(s) + expf(blank_logit - m);
-    if (lane == 0) lse[t] = m + logf(s);
-  }
+  for (int t = k; t < T; t += blockDim.x) lse[t] = lse_ws[static_cast<long long>(b) * Tm + t];
   __syncthreads();
 
   const bool has_tok = k < N;
   const bool active = k <= N;
-  // ---- forward (alpha) ----
-  float* prev = buf0;
-  float* cur = buf1;
+  float* ap = abuf0; float* ac = abuf1;
+  float* bp = bbuf0; float* bc = bbuf1;
   {
-    const float l0 = lse[0];
-    const float ab = (k == 0) ? blank_logit - l0 : NEG;
-    const float at = (k == 0 && has_tok) ? lp[0] - l0 : NEG;
+    const float l0 = lse[0], lT = lse[T - 1];
     if (active) {
-      prev[2 * k] = ab;
-      aw[2 * k] = ab;
+      ap[2 * k] = (k == 0) ? blank_logit - l0 : NEG;
+      bp[2 * k] = (k == N) ? blank_logit - lT : NEG;
       if (has_tok) {
-        prev[2 * k + 1] = at;
-        aw[2 * k + 1] = at;
+        const float at = (k == 0) ? lp[0] - l0 : NEG;
+        const float bt = (k == N - 1) ? lp[static_cast<long long>(T - 1) * Tx + k] - lT : NEG;
+        ap[2 * k + 1] = at;
+        bp[2 * k + 1] = bt;
+        aw[k] = at;
+        bw[static_cast<long long>(T - 1) * Tx + k] = bt;
       }
     }
   }
   __syncthreads();
-  // emissions are fetched one frame ahead so that the L2 latency stays off the serial critical path
-  float e_next = (T > 1 && has_tok) ? lp[static_cast<long long>(Tx) + k] : 0.f;
-  for (int t = 1; t < T; ++t) {
-    const float lt = lse[t];
-    const float e_cur = e_next;
-    if (t + 1 < T && has_tok) e_next = lp[static_cast<long long>(t + 1) * Tx + k];
-    if (active) {
-      const float pb = prev[2 * k];
-      const float pm1 = k > 0 ? prev[2 * k - 1] : NEG;
-      const float nb = lse2(pb, pm1) + (blank_logit - lt);
-      cur[2 * k] = nb;
-      aw[static_cast<long long>(t) * Smax + 2 * k] = nb;
-      if (has_tok) {
-        const float nt = lse3(prev[2 * k + 1], pb, pm1) + (e_cur - lt);
-        cur[2 * k + 1] = nt;
-        aw[static_cast<long long>(t) * Smax + 2 * k + 1] = nt;
-      }
-    }
-    __syncthreads();
-    float* tmp = prev; prev = cur; cur = tmp;
+  float ea[FS_G], eb[FS_G], ea_n[FS_G], eb_n[FS_G];
+#pragma unroll
+  for (int g = 0; g < FS_G; ++g) {
+    const int i = 1 + g;
+    const bool ok = has_tok && i < T;
+    ea[g] = ok ? lp[static_cast<long long>(i) * Tx + k] : 0.f;
+    eb[g] = ok ? lp[static_cast<long long>(T - 1 - i) * Tx + k] : 0.f;
   }
-  const float ll = lse2(prev[S - 1], S >= 2 ? prev[S - 2] : NEG);
-  const bool finite = ll > -INFINITY && ll < INFINITY;
-  const float nll = -ll;
-  if (k == 0) loss[b] = finite ? nll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
-  const float gscale = finite ? 1.f / (static_cast<float>(N) * static_cast<float>(B)) : 0.f;
-  __syncthreads();
-
-  // ---- backward (beta) + gradient ----
-  {
-    const float lt = lse[T - 1];
-    if (active) {
-      prev[2 * k] = (k == N) ? blank_logit - lt : NEG;
-      if (has_tok) prev[2 * k + 1] = (k == N - 1) ? lp[static_cast<long long>(T - 1) * Tx + k] - lt : NEG;
+  for (int base = 1; base < T; base += FS_G) {
+#pragma unroll
+    for (int g = 0; g < FS_G; ++g) {
+      const int i = base + FS_G + g;
+      const bool ok = has_tok && i < T;
+      ea_n[g] = ok ? lp[static_cast<long long>(i) * Tx + k] : 0.f;
+      eb_n[g] = ok ? lp[static_cast<long long>(T - 1 - i) * Tx + k] : 0.f;
     }
-  }
-  __syncthreads();
-  float raw_cur = has_tok ? lp[static_cast<long long>(T - 1) * Tx + k] : 0.f;
-  float a_cur = has_tok ? aw[static_cast<long long>(T - 1) * Smax + 2 * k + 1] : 0.f;
-  for (int t = T - 1; t >= 0; --t) {
-    const float lt = lse[t];
-    float raw_prev = 0.f, a_prev = 0.f;   // frame t-1, fetched while frame t is being processed
-    if (t > 0 && has_tok) {
-      raw_prev = lp[static_cast<long long>(t - 1) * Tx + k];
-      a_prev = aw[static_cast<long long>(t - 1) * Smax + 2 * k + 1];
-    }
-    if (has_tok) {
-      const float e = raw_cur - lt;                                                // normalised log-prob of token k
-      const float occ = a_cur + prev[2 * k + 1] - e + nll;                         // log posterior occupancy
-      gr[static_cast<long long>(t) * Tx + k] = gscale * (expf(e) - expf(occ));
-    }
-    raw_cur = raw_prev;
-    a_cur = a_prev;
-    if (t > 0) {
-      const float lt1 = lse[t - 1];
-      if (active) {
-        const float nb = lse2(prev[2 * k], has_tok ? prev[2 * k + 1] : NEG) + (blank_logit - lt1);
-        cur[2 * k] = nb;
-        if (has_tok) {
-          const float nt = lse3(prev[2 * k + 1], prev[2 * k + 2], (k + 1 < N) ? prev[2 * k + 3] : NEG) +
-                           (raw_prev - lt1);
-          cur[2 * k + 1] = nt;
+#pragma unroll
+    for (int g = 0; g < FS_G; ++g) {
+      const int i = base + g;
+      if (i < T) {  // uniform across the block
+        const int ta = i, tb = T - 1 - i;
+        const float la = lse[ta], lb = lse[tb];
+        if (active) {
+          const float pb = ap[2 * k];
+          const float pm1 = k > 0 ? ap[2 * k - 1] : NEG;
+          ac[2 * k] = lse2(pb, pm1) + (blank_logit - la);
+          const float qb = bp[2 * k];
+          const float qt = has_tok ? bp[2 * k + 1] : NEG;
+          bc[2 * k] = lse2(qb, qt) + (blank_logit - lb);
+          if (has_tok) {
+            const float nt = lse3(ap[2 * k + 1], pb, pm1) + (ea[g] - la);
+            ac[2 * k + 1] = nt;
+            aw[static_cast<long long>(ta) * Tx + k] = nt;
+            const float mt = lse3(qt, bp[2 * k + 2], (k + 1 < N) ? bp[2 * k + 3] : NEG) + (eb[g] - lb);
+            bc[2 * k + 1] = mt;
+            bw[static_cast<long long>(tb) * Tx + k] = mt;
+          }
         }
+        __syncthreads();
+        float* t0 = ap; ap = ac; ac = t0;
+        float* t1 = bp; bp = bc; bc = t1;
       }
-      __syncthreads();
-      float* tmp = prev; prev = cur; cur = tmp;
     }
+#pragma unroll
+    for (int g = 0; g < FS_G; ++g) { ea[g] = ea_n[g]; eb[g] = eb_n[g]; }
   }
-  // zero the padded region
-  for (int i = k; i < Tm * Tx; i += blockDim.x) {
-    const int t = i / Tx, n = i - t * Tx;
-    if (t >= T || n >= N) gr[i] = 0.f;
+  if (k == 0) {
+    const float ll = lse2(ap[S - 1], S >= 2 ? ap[S - 2] : NEG);
+    const bool finite = ll > -INFINITY && ll < INFINITY;
+    loss[b] = finite ? -ll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
+    nll_ws[b] = finite ? -ll : INFINITY;
   }
+}
+
+// gradient, fully parallel over (b, t, n): softmax minus posterior occupancy, with the per-sample 1/N and the batch 1/B
+__global__ void fs_grad_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
+                               const float* __restrict__ lse_ws, const float* __restrict__ aw, const float* __restrict__ bw,
+                               const float* __restrict__ nll_ws, float* __restrict__ grad, int B, int Tm, int Tx) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Tm * Tx) return;
+  const int n = static_cast<int>(idx % Tx);
+  const long long row = idx / Tx;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  float g = 0.f;
+  const float nll = nll_ws[b];
+  if (t < T && n < N && nll < INFINITY) {
+    const float e = lpa[idx] - lse_ws[row];
+    g = (expf(e) - expf(aw[idx] + bw[idx] - e + nll)) / (static_cast<float>(N) * static_cast<float>(B));
+  }
+  grad[idx] = g;
 }
 
 }  // namespace
@@ -470,7 +497,7 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   OSB_REQUIRE(log_p_attn && x_len && m_len && alpha_ws && loss && grad, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && Tm > 0 && Tx > 0 && Tx <= 1023, OSB_ERR_SHAPE);
   const int nthr = ((Tx + 1 + 31) / 32) * 32;
-  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(2 * Tx + 1) + Tm);
+  const size_t smem = sizeof(float) * (4 * static_cast<size_t>(2 * Tx + 1) + Tm);
   OSB_REQUIRE(smem <= 200 * 1024, OSB_ERR_SHAPE);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -478,9 +505,18 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = 200 * 1024;
   }
-  osb::forward_sum_kernel<<<B, nthr, smem, static_cast<cudaStream_t>(stream)>>>(
-      log_p_attn, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(m_len), blank_logit, alpha_ws, loss, grad,
-      B, Tm, Tx);
-  osb::count_launch();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long plane = static_cast<long long>(B) * Tm * Tx;
+  float* aw = alpha_ws;
+  float* bw = alpha_ws + plane;
+  float* lse_ws = alpha_ws + 2 * plane;
+  float* nll_ws = lse_ws + static_cast<long long>(B) * Tm;
+  const long long* xl = reinterpret_cast<const long long*>(x_len);
+  const long long* ml = reinterpret_cast<const long long*>(m_len);
+  const long long rows = static_cast<long long>(B) * Tm;
+  osb::fs_lse_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, B, Tm, Tx);
+  osb::forward_sum_kernel<<<B, nthr, smem, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+  osb::fs_grad_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
+  osb::count_launch(3);
   return osb::launch_status();
 }

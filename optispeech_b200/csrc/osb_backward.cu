@@ -102,12 +102,19 @@ resid_bwd_prep_kernel(const float* __restrict__ dout, const __half* __restrict__
 // column sums of an fp16 matrix (bias gradients): out[n] += sum_rows x[row, n].  N % 8 == 0.
 // grid = (ceil(N / 2048), row-slabs), 256 threads each owning 8 columns.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// block = (128 column-threads of 8 columns each) x (8 row groups); the row groups are reduced through shared memory so
+// that every block issues ONE atomic per column.
+__global__ void __launch_bounds__(1024)
 colsum_h16_kernel(const __half* __restrict__ x, float* __restrict__ out, long long rows, int N, int rows_per_block) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
-  if (c >= N) return;
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
-  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  __shared__ float red[8][128 * 8 + 8];
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
+  const bool col_ok = c < N;
+  const int rg = threadIdx.y;
+  const long long rb0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
+  const long long per = (rb1 - rb0 + 7) / 8;
+  const long long r0 = rb0 + rg * per;
+  const long long r1 = col_ok ? (r0 + per < rb1 ? r0 + per : rb1) : r0;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   long long r = r0;
   for (; r + 4 <= r1; r += 4) {  // four independent 16-byte loads in flight per thread
@@ -136,7 +143,17 @@ colsum_h16_kernel(const __half* __restrict__ x, float* __restrict__ out, long lo
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + c + j, acc[j]);
+  for (int j = 0; j < 8; ++j) red[rg][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  if (rg == 0 && col_ok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x * 8 + j];
+      atomicAdd(out + c + j, s);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -475,11 +492,12 @@ extern "C" int osb_resid_bwd_prep(const float* dout, const void* z_h16, const fl
 extern "C" int osb_colsum_h16(const void* x_h16, float* out, int64_t rows, int32_t N, void* stream) {
   OSB_REQUIRE(x_h16 && out, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && N > 0 && N % 8 == 0, OSB_ERR_SHAPE);
-  const int gx = (N / 8 + 255) / 256;
-  int rpb = static_cast<int>((rows + 148 * 4 - 1) / (148 * 4));
-  if (rpb < 16) rpb = 16;
+  const int gx = (N / 8 + 127) / 128;
+  int rpb = static_cast<int>((rows * gx + 147) / 148);  // ~one block per SM
+  if (rpb < 128) rpb = 128;
   const int gy = static_cast<int>((rows + rpb - 1) / rpb);
-  colsum_h16_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), out, rows, N, rpb);
+  colsum_h16_kernel<<<dim3(gx, gy), dim3(128, 8), 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), out, rows, N,
+                                                                                         rpb);
   count_launch();
   return launch_status();
 }
