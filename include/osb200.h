@@ -143,6 +143,18 @@ int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, floa
                    int32_t N, int32_t K, int32_t taps, int32_t pad, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ONE kernel per ConvNeXt block, forward (osb_convnext.cu): depthwise-conv7 + LayerNorm prologue on CUDA cores writing the
+ * fp16 A operand into swizzled shared memory, pwconv1 (tcgen05) -> bias + erf-GELU epilogue into shared memory -> pwconv2
+ * (tcgen05, accumulating over 64-column chunks of the intermediate dimension in TMEM) -> bias, layer scale, DropPath scale,
+ * residual and pad mask.  Weights are TMA-streamed fp16: w1f (I, C) = pwconv1.weight * norm.weight (LN affine folded),
+ * b1f = pwconv1.bias + pwconv1.weight @ norm.bias, w2 (C, I).  (C, I) in {(256, 1024), (384, 1152)}.
+ * Replaces ConvNeXtBlock.forward + the mask of ConvNeXtBackbone.forward (modules/convnext.py:34-47,98-101). */
+int osb_convnext_block_fwd(const float* x, const float* dw_w /*(C,7)*/, const float* dw_b, const void* w1f_h16, const float* b1f,
+                           const void* w2_h16, const float* b2, const float* gamma, const float* row_scale /*(B) or NULL*/,
+                           const uint8_t* pad_mask /*(B*T) or NULL*/, float* out, int32_t B, int32_t T, int32_t C, int32_t I, float eps,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * HBM-bound kernels of the synthesis path (osb_pointwise.cu).  Rows are channels-last.
  * ------------------------------------------------------------------------------------- */
 

@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     ]
     P, I32, I64, F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sigs = {
+        "osb_convnext_block_fwd": [P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, F, P],
         "osb_embed_text": [P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, I32, P],
         "osb_layernorm": [P, P, P, P, P, I64, I32, F, I32, P],

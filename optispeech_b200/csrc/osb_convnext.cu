@@ -1,0 +1,349 @@
+// osb_convnext.cu — ONE kernel per ConvNeXt block (forward):
+//
+//   out = (x + gamma * rs[b] * (W2 . gelu(W1f . LNhat(dwconv7(x)) + b1f) + b2)) * keep
+//
+// A CTA owns 128 consecutive positions of one sequence.
+//   prologue   : 8 worker warps compute depthwise-conv7 + LayerNorm statistics on CUDA cores and write the fp16
+//                normalised tile straight into 128B-swizzled shared memory — it IS the A operand of pwconv1;
+//   main loop  : the intermediate dimension I is walked in chunks of 64 columns.  One thread issues
+//                tcgen05.mma for pwconv1 of chunk j (accumulator: 64 TMEM columns, double buffered); the worker
+//                warps read it back (tcgen05.ld), add the bias, apply exact-erf GELU and write the fp16 chunk into
+//                swizzled shared memory, where it is the A operand of pwconv2 for that chunk; pwconv2 accumulates
+//                over all chunks into a second TMEM region (C columns).  The (positions x I) intermediate never
+//                leaves the SM.  Weight chunks are streamed by TMA (one producer thread) through full/empty
+//                mbarriers; pwconv1 of chunk j+1 overlaps the GELU of chunk j and pwconv2 of chunk j-1.
+//   epilogue   : bias, layer scale, DropPath scale, residual, pad mask -> fp32 HBM.
+// HBM traffic per position: 4C bytes read (+ halo) and 4C written, i.e. the algorithmic minimum; the three-kernel
+// path moves an extra 2C + 2*2I + 4C bytes per position.
+#include "osb_host.h"
+#include "osb_ptx.cuh"
+
+namespace osb {
+namespace {
+
+constexpr int FB_M = 128;      // rows per CTA
+constexpr int FB_NC = 64;      // intermediate columns per chunk (= one 128-byte swizzle row of fp16)
+constexpr int FB_WORKERS = 8;  // worker warps (prologue + epilogues)
+constexpr int FB_THREADS = 64 + FB_WORKERS * 32;
+
+struct FusedParams {
+  const float* x;        // (B, T, C) fp32 residual stream
+  const float* dw_w;     // (C, 7)
+  const float* dw_b;     // (C)
+  const float* b1;       // (I) folded bias
+  const float* b2;       // (C)
+  const float* gamma;    // (C)
+  const float* row_scale;   // (B) or null
+  const uint8_t* pad_mask;  // (B*T) or null
+  float* out;            // (B, T, C)
+  int B, T, m_tiles;
+  float eps;
+};
+
+template <int C>
+struct FusedCfg {
+  static constexpr int KB = C / 64;                       // 64-element k-blocks of the A operand
+  static constexpr int A_BYTES = KB * FB_M * 128;          // xhat tile
+  static constexpr int W1_BYTES = KB * FB_NC * 128;        // W1 chunk: 64 rows x C
+  static constexpr int W2_BYTES = C * 128;                 // W2 chunk: C rows x 64
+  static constexpr int H_BYTES = FB_M * 128;               // GELU chunk: 128 rows x 64
+  static constexpr int SMEM = A_BYTES + W1_BYTES + W2_BYTES + 2 * H_BYTES + 1024 + 256;
+  static constexpr int N2 = C <= 256 ? C : C / 2;          // N of one pwconv2 MMA
+  static constexpr int N2_PARTS = C / N2;
+  static constexpr uint32_t ACC1_COL = C;                  // TMEM: [0, C) pwconv2 accumulator, then 2 x 64 for pwconv1
+};
+
+// 16-byte chunk `c16` (0..7) of row `r` inside a [rows x 128 B] tile with the 128-byte swizzle
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c16) { return static_cast<uint32_t>(r * 128 + ((c16 ^ (r & 7)) << 4)); }
+
+template <int C, int I>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FusedParams p) {
+  using Cfg = FusedCfg<C>;
+  constexpr int NCH = I / FB_NC;
+  constexpr int VPL = C / 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW1 = sA + Cfg::A_BYTES;
+  uint8_t* sW2 = sW1 + Cfg::W1_BYTES;
+  uint8_t* sH = sW2 + Cfg::W2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sH + 2 * Cfg::H_BYTES);
+  uint64_t* w1_full = bars + 0;
+  uint64_t* w1_empty = bars + 1;
+  uint64_t* w2_full = bars + 2;
+  uint64_t* w2_empty = bars + 3;
+  uint64_t* acc1_full = bars + 4;   // [2]
+  uint64_t* acc1_empty = bars + 6;  // [2]
+  uint64_t* h_full = bars + 8;      // [2]
+  uint64_t* h_empty = bars + 10;    // [2]
+  uint64_t* a_ready = bars + 12;
+  uint64_t* acc2_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.m_tiles;
+  const int t0 = (blockIdx.x % p.m_tiles) * FB_M;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    mbar_init(w1_full, 1); mbar_init(w1_empty, 1); mbar_init(w2_full, 1); mbar_init(w2_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&acc1_empty[i], FB_WORKERS);
+      mbar_init(&h_full[i], FB_WORKERS);
+      mbar_init(&h_empty[i], 1);
+    }
+    mbar_init(a_ready, FB_WORKERS);
+    mbar_init(acc2_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight chunks =====================
+    if (lane == 0) {
+      for (int j = 0; j < NCH; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(w1_empty, ph ^ 1);
+        mbar_expect_tx(w1_full, Cfg::W1_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < Cfg::KB; ++kb) tma_load_3d(sW1 + kb * (FB_NC * 128), &tmW1, w1_full, kb * 64, j * FB_NC, 0);
+        mbar_wait(w2_empty, ph ^ 1);
+        mbar_expect_tx(w2_full, Cfg::W2_BYTES);
+#pragma unroll
+        for (int part = 0; part < Cfg::N2_PARTS; ++part)
+          tma_load_3d(sW2 + part * (Cfg::N2 * 128), &tmW2, w2_full, j * FB_NC, part * Cfg::N2, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_instr_desc(OSB_F16, FB_M, FB_NC, 0, 0);
+      constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, FB_M, Cfg::N2, 0, 0);
+      const uint32_t a_addr = smem_u32(sA), w1_addr = smem_u32(sW1), w2_addr = smem_u32(sW2), h_addr = smem_u32(sH);
+      mbar_wait(a_ready, 0);
+      tc_fence_after_sync();
+      for (int j = 0; j <= NCH; ++j) {
+        if (j < NCH) {  // pwconv1 of chunk j -> acc1[j & 1]
+          const int buf = j & 1;
+          mbar_wait(w1_full, j & 1);
+          mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * FB_NC;
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_addr + kb * (FB_M * 128) + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(w1_addr + kb * (FB_NC * 128) + k * 32, 16, 1024);
+              umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
+            }
+          umma_commit(w1_empty);
+          umma_commit(&acc1_full[buf]);
+        }
+        if (j >= 1) {   // pwconv2 of chunk j-1: acc2 += gelu_chunk . W2[:, chunk]^T
+          const int jj = j - 1, buf = jj & 1;
+          mbar_wait(w2_full, jj & 1);
+          mbar_wait(&h_full[buf], (jj >> 1) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(h_addr + buf * Cfg::H_BYTES + k * 32, 16, 1024);
+#pragma unroll
+            for (int part = 0; part < Cfg::N2_PARTS; ++part) {
+              const uint64_t db = make_smem_desc_sw128(w2_addr + part * (Cfg::N2 * 128) + k * 32, 16, 1024);
+              umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(w2_empty);
+          umma_commit(&h_empty[buf]);
+        }
+      }
+      umma_commit(acc2_full);
+    }
+  } else {
+    // ===================== worker warps =====================
+    const int ww = warp - 2;          // 0..7
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (ww >> 2);       // which 32-column half of a 64-column chunk / which half of C in the last epilogue
+    // ---- prologue: dwconv7 + LayerNorm statistics -> fp16 xhat in swizzled smem (rows ww*16 .. +16) ----
+    {
+      const float* xb = p.x + static_cast<long long>(b) * p.T * C;
+      float4 win[7][VPL];
+      auto load_row = [&](int t, float4 (&dst)[VPL]) {
+        if (t >= 0 && t < p.T) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) dst[v] = *reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C + v * 128 + lane * 4);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      const int r_begin = ww * 16;
+#pragma unroll
+      for (int jx = 0; jx < 6; ++jx) load_row(t0 + r_begin + jx - 3, win[jx + 1]);
+      for (int r = r_begin; r < r_begin + 16; ++r) {
+        const int t = t0 + r;
+#pragma unroll
+        for (int jx = 0; jx < 6; ++jx)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) win[jx][v] = win[jx + 1][v];
+        load_row(t + 3, win[6]);
+        float4 d[VPL];
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          float4 acc = __ldg(reinterpret_cast<const float4*>(p.dw_b + c));
+          const float* wp = p.dw_w + c * 7;  // dw_w is (C, 7): the 7 taps of one channel are contiguous
+#pragma unroll
+          for (int jx = 0; jx < 7; ++jx) {
+            acc.x = fmaf(__ldg(wp + jx), win[jx][v].x, acc.x);
+            acc.y = fmaf(__ldg(wp + 7 + jx), win[jx][v].y, acc.y);
+            acc.z = fmaf(__ldg(wp + 14 + jx), win[jx][v].z, acc.z);
+            acc.w = fmaf(__ldg(wp + 21 + jx), win[jx][v].w, acc.w);
+          }
+          d[v] = acc;
+          s += (acc.x + acc.y) + (acc.z + acc.w);
+        }
+        const float mean = warp_sum(s) * (1.f / C);
+        float qv = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
+          qv += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
+        }
+        const float rstd = (t < p.T) ? rsqrtf(warp_sum(qv) * (1.f / C) + p.eps) : 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          const int kb = c >> 6, cc = c & 63;
+          __half2 h0 = __floats2half2_rn(d[v].x * rstd, d[v].y * rstd);
+          __half2 h1 = __floats2half2_rn(d[v].z * rstd, d[v].w * rstd);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(sA + kb * (FB_M * 128) + sw128_offset(r, cc >> 3) + (cc & 7) * 2) = u;
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    // ---- per chunk: acc1 -> +bias -> GELU -> fp16 -> swizzled smem (A operand of pwconv2) ----
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int j = 0; j < NCH; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&acc1_full[buf], (j >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t rr[32];
+      tmem_ld_32x32(lane_addr + Cfg::ACC1_COL + buf * FB_NC + half * 32, rr);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc1_empty[buf]);
+      float v[32];
+      const float* bp = p.b1 + j * FB_NC + half * 32;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(rr[i]) + __ldg(bp + i));
+      mbar_wait(&h_empty[buf], ((j >> 1) & 1) ^ 1);
+      uint8_t* hrow = sH + buf * Cfg::H_BYTES;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        __half2 h0 = __floats2half2_rn(v[c4 * 8 + 0], v[c4 * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(v[c4 * 8 + 2], v[c4 * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(v[c4 * 8 + 4], v[c4 * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(v[c4 * 8 + 6], v[c4 * 8 + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(hrow + sw128_offset(row, half * 4 + c4)) = u;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_full[buf]);
+    }
+    // ---- final epilogue: bias, layer scale, DropPath, residual, mask ----
+    mbar_wait(acc2_full, 0);
+    tc_fence_after_sync();
+    const int t = t0 + row;
+    const bool valid = t < p.T;
+    const long long grow = static_cast<long long>(b) * p.T + t;
+    const float keep = (p.pad_mask != nullptr && valid && p.pad_mask[grow]) ? 0.f : 1.f;
+    const float rs = p.row_scale != nullptr ? p.row_scale[b] : 1.f;
+    constexpr int CH = C / 2;  // columns per worker half
+    for (int c0 = half * CH; c0 < (half + 1) * CH; c0 += 32) {
+      uint32_t rr[32];
+      tmem_ld_32x32(lane_addr + c0, rr);
+      tmem_ld_wait();
+      if (valid) {
+        const float* rp = p.x + grow * C + c0;
+        float* op = p.out + grow * C + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+          float4 o;
+          o.x = (r4.x + __ldg(p.gamma + c0 + i + 0) * (__uint_as_float(rr[i + 0]) + __ldg(p.b2 + c0 + i + 0)) * rs) * keep;
+          o.y = (r4.y + __ldg(p.gamma + c0 + i + 1) * (__uint_as_float(rr[i + 1]) + __ldg(p.b2 + c0 + i + 1)) * rs) * keep;
+          o.z = (r4.z + __ldg(p.gamma + c0 + i + 2) * (__uint_as_float(rr[i + 2]) + __ldg(p.b2 + c0 + i + 2)) * rs) * keep;
+          o.w = (r4.w + __ldg(p.gamma + c0 + i + 3) * (__uint_as_float(rr[i + 3]) + __ldg(p.b2 + c0 + i + 3)) * rs) * keep;
+          *reinterpret_cast<float4*>(op + i) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+template <int C, int I>
+int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, cudaStream_t stream) {
+  using Cfg = FusedCfg<C>;
+  CUtensorMap tmW1, tmW2;
+  // W1f: (I, C) K-major, box 64 x 64 ; W2: (C, I) K-major, box 64 x N2
+  int rc = make_tmap_3d(&tmW1, w1_h16, TMA_F16, C, I, 1, C, static_cast<uint64_t>(I) * C, 64, FB_NC);
+  if (rc != OSB_OK) return rc;
+  rc = make_tmap_3d(&tmW2, w2_h16, TMA_F16, I, C, 1, I, static_cast<uint64_t>(C) * I, 64, Cfg::N2);
+  if (rc != OSB_OK) return rc;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  convnext_fused_kernel<C, I><<<p.B * p.m_tiles, FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
+  count_launch();
+  return launch_status();
+}
+
+}  // namespace
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
+                                      const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
+                                      const uint8_t* pad_mask, float* out, int32_t B, int32_t T, int32_t C, int32_t I, float eps,
+                                      void* stream) {
+  OSB_REQUIRE(x && dw_w && dw_b && w1f_h16 && b1f && w2_h16 && b2 && gamma && out, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && T > 0, OSB_ERR_SHAPE);
+  FusedParams p;
+  p.x = x; p.dw_w = dw_w; p.dw_b = dw_b; p.b1 = b1f; p.b2 = b2; p.gamma = gamma; p.row_scale = row_scale; p.pad_mask = pad_mask;
+  p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C == 256 && I == 1024) return launch_fused<256, 1024>(w1f_h16, w2_h16, p, s);
+  if (C == 384 && I == 1152) return launch_fused<384, 1152>(w1f_h16, w2_h16, p, s);
+  return OSB_ERR_SHAPE;
+}

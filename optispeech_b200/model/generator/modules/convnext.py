@@ -89,6 +89,12 @@ class ConvNeXtBlock(nn.Module):
         """Channels-last forward: x (B,T,C) fp32 -> (B,T,C) fp32, pad mask (B,T) uint8 applied to the output
         (the reference's ConvNeXtBackbone multiplies by the mask right after each block, convnext.py:98-101)."""
         w1, b1, w2 = self.packed()
+        if not split and (self.dim, self.intermediate_dim) in ops.FUSED_BLOCK_SHAPES:
+            # single-pass fp16 operands: the whole block is ONE kernel (osb_convnext.cu)
+            scale = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
+            gamma = self.gamma if self.gamma is not None else torch.ones(self.dim, device=x.device)
+            return ops.convnext_block_fwd(x, self.dwconv.weight.view(self.dim, 7), self.dwconv.bias, w1[0, 0], b1, w2[0, 0],
+                                          self.pwconv2.bias, gamma, scale, pad_mask_u8, self.norm.eps)
         fin = ops.FLAG_SPLIT_IN if split else 0
         xhat, _ = ops.dwconv_ln(x, self.dwconv.weight.view(self.dim, 7), self.dwconv.bias, self.norm.eps, split=split)
         h, _, _ = ops.gemm(xhat, w1, epi=ops.EPI_GELU, bias=b1, flags=fin | (ops.FLAG_SPLIT_OUT if split else 0))

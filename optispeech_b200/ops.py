@@ -386,3 +386,17 @@ def pack_conv_h16(w: torch.Tensor, k_pad: Optional[int] = None, transpose_revers
     _lib.check(_lib.load().osb_pack_conv_h16(_ptr(_f32(w.contiguous())), _ptr(dst), _ptr(lo), N, Cin, k, Kp, int(transpose_reverse),
                                              _stream()), "osb_pack_conv_h16")
     return out
+
+
+FUSED_BLOCK_SHAPES = ((256, 1024), (384, 1152))
+
+
+def convnext_block_fwd(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale=None, pad_mask=None, eps: float = 1e-6):
+    """Fused ConvNeXt block forward (one launch).  x fp32 (B,T,C); w1f_h16 fp16 (I,C), w2_h16 fp16 (C,I)."""
+    B, T, Cc = x.shape
+    I = w1f_h16.shape[-2]
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().osb_convnext_block_fwd(_ptr(_f32(x)), _ptr(_f32(dw_w)), _ptr(_f32(dw_b)), _ptr(w1f_h16), _ptr(_f32(b1f)),
+                                                  _ptr(w2_h16), _ptr(_f32(b2)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask),
+                                                  _ptr(out), B, T, Cc, I, float(eps), _stream()), "osb_convnext_block_fwd")
+    return out

@@ -88,3 +88,37 @@ def test_expand_indices_bit_exact(cuda_device):
     Tm = int(d.sum(1).max())
     got = expand_indices(d.to(cuda_device), Tm).cpu().to(torch.int64)
     assert torch.equal(got, O.expand_indices(d, Tm))
+
+
+@pytest.mark.parametrize("C,I,T", [(256, 1024, 300), (384, 1152, 64), (384, 1152, 517), (256, 1024, 7)])
+def test_fused_convnext_block_kernel(cuda_device, C, I, T):
+    """The one-kernel ConvNeXt block (fp16 operands) against the oracle block and against the three-kernel path."""
+    from optispeech_b200 import ops
+    from optispeech_b200.model.generator.modules import ConvNeXtBlock
+
+    g = torch.Generator().manual_seed(31)
+    B = 3
+    blk = ConvNeXtBlock(C, I, drop_path=0.0, layer_scale_init_value=0.25)
+    sd = {
+        "dwconv.weight": torch.randn(C, 1, 7, generator=g) * 0.3, "dwconv.bias": torch.randn(C, generator=g) * 0.1,
+        "norm.weight": 1 + 0.1 * torch.randn(C, generator=g), "norm.bias": 0.1 * torch.randn(C, generator=g),
+        "pwconv1.weight": torch.randn(I, C, generator=g) / C ** 0.5, "pwconv1.bias": 0.1 * torch.randn(I, generator=g),
+        "pwconv2.weight": torch.randn(C, I, generator=g) / I ** 0.5, "pwconv2.bias": 0.1 * torch.randn(C, generator=g),
+        "gamma": 0.25 * (1 + 0.1 * torch.randn(C, generator=g)),
+    }
+    blk.load_state_dict(sd)
+    blk = blk.to(cuda_device).eval()
+    x = torch.randn(B, T, C, generator=g)
+    pad = torch.arange(T)[None] >= torch.tensor([T, max(1, T - 9), max(1, T // 2)])[:, None]
+    ref = O.convnext_block({f"b.{k}": v for k, v in sd.items()}, "b", x) * (1 - pad.float())[..., None]
+    with torch.no_grad():
+        xc, mc = x.to(cuda_device), pad.to(torch.uint8).to(cuda_device)
+        fused = blk.forward_cl(xc, mc, split=False)
+        n0 = ops._lib.launch_count()
+        blk.forward_cl(xc, mc, split=False)
+        assert ops._lib.launch_count() - n0 == 1, "the non-split block must be a single kernel launch"
+        three = blk.forward_cl(xc, mc, split=True)
+    err_f = (fused.cpu() - ref).abs().max().item()
+    err_3 = (three.cpu() - ref).abs().max().item()
+    print(f"  C={C} T={T}: fused(fp16) max-abs err {err_f:.3e}; three-kernel fp16x3 {err_3:.3e}")
+    assert err_f <= 5e-3 and err_3 <= 1e-4
