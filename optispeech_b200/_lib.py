@@ -182,6 +182,10 @@ class LaunchProfiler:
                         split = 3 if (d.flags & FLAG_SPLIT_IN) else 1
                         key = f"osb_gemm[epi={d.epi},rows={d.B * d.T},N={d.N},K={d.K},taps={d.taps},passes={split}]"
                         flops = 2.0 * d.B * d.T * d.N * d.K * d.taps
+                    elif name == "osb_convnext_block_fwd":
+                        B, T, Cc, I = args[11], args[12], args[13], args[14]
+                        key = f"osb_convnext_block_fwd[rows={B * T},C={Cc},I={I}]"
+                        flops = 2.0 * B * T * (2 * Cc * I + 7 * Cc)
                     elif name == "osb_gemm_wgrad":
                         B, T, N, K, taps = args[5], args[6], args[7], args[8], args[9]
                         key = f"osb_gemm_wgrad[rows={B * T},N={N},K={K},taps={taps}]"
