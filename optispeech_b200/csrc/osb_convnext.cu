@@ -38,7 +38,11 @@ struct FusedParams {
   float* out;            // (B, T, C)
   int B, T, m_tiles;
   float eps;
+  long long* trace;      // optional (developer): clock64 timeline of CTA 0, [role][event] (see tools/probe_fused.py)
 };
+
+#define FB_TRACE(role, idx) \
+  do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[(role) * 256 + (idx)] = clock64(); } while (0)
 
 template <int C>
 struct FusedCfg {
@@ -47,7 +51,11 @@ struct FusedCfg {
   static constexpr int W1_BYTES = KB * FB_NC * 128;        // W1 chunk: 64 rows x C
   static constexpr int W2_BYTES = C * 128;                 // W2 chunk: C rows x 64
   static constexpr int H_BYTES = FB_M * 128;               // GELU chunk: 128 rows x 64
-  static constexpr int SMEM = A_BYTES + W1_BYTES + W2_BYTES + 2 * H_BYTES + 1024 + 256;
+  // weight-chunk ring depth: two stages hide the TMA latency; C = 384 only has room for one (A alone is 96 KB)
+  static constexpr int WS = (A_BYTES + 2 * (W1_BYTES + W2_BYTES) + 2 * H_BYTES + 1280 <= 227 * 1024) ? 2 : 1;
+  static constexpr int SMEM = A_BYTES + WS * (W1_BYTES + W2_BYTES) + 2 * H_BYTES + 1024 + 256;
+  static constexpr int OUT_LD = C + 4;                     // padded row stride (floats) of the staged output tile
+  static_assert(FB_M * OUT_LD * 4 <= A_BYTES + WS * (W1_BYTES + W2_BYTES) + 2 * H_BYTES, "staged output tile must fit");
   static constexpr int N2 = C <= 256 ? C : C / 2;          // N of one pwconv2 MMA
   static constexpr int N2_PARTS = C / N2;
   static constexpr uint32_t ACC1_COL = C;                  // TMEM: [0, C) pwconv2 accumulator, then 2 x 64 for pwconv1
@@ -64,22 +72,23 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   constexpr int VPL = C / 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int WS = Cfg::WS;
   uint8_t* sA = smem;
-  uint8_t* sW1 = sA + Cfg::A_BYTES;
-  uint8_t* sW2 = sW1 + Cfg::W1_BYTES;
-  uint8_t* sH = sW2 + Cfg::W2_BYTES;
+  uint8_t* sW1 = sA + Cfg::A_BYTES;                 // [WS]
+  uint8_t* sW2 = sW1 + WS * Cfg::W1_BYTES;          // [WS]
+  uint8_t* sH = sW2 + WS * Cfg::W2_BYTES;           // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sH + 2 * Cfg::H_BYTES);
-  uint64_t* w1_full = bars + 0;
-  uint64_t* w1_empty = bars + 1;
-  uint64_t* w2_full = bars + 2;
-  uint64_t* w2_empty = bars + 3;
-  uint64_t* acc1_full = bars + 4;   // [2]
-  uint64_t* acc1_empty = bars + 6;  // [2]
-  uint64_t* h_full = bars + 8;      // [2]
-  uint64_t* h_empty = bars + 10;    // [2]
-  uint64_t* a_ready = bars + 12;
-  uint64_t* acc2_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* w1_full = bars + 0;     // [2]
+  uint64_t* w1_empty = bars + 2;    // [2]
+  uint64_t* w2_full = bars + 4;     // [2]
+  uint64_t* w2_empty = bars + 6;    // [2]
+  uint64_t* acc1_full = bars + 8;   // [2]
+  uint64_t* acc1_empty = bars + 10; // [2]
+  uint64_t* h_full = bars + 12;     // [2]
+  uint64_t* h_empty = bars + 14;    // [2]
+  uint64_t* a_ready = bars + 16;
+  uint64_t* acc2_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,8 +98,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
-    mbar_init(w1_full, 1); mbar_init(w1_empty, 1); mbar_init(w2_full, 1); mbar_init(w2_empty, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1);
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc1_empty[i], FB_WORKERS);
       mbar_init(&h_full[i], FB_WORKERS);
@@ -110,63 +119,92 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     // ===================== TMA producer: weight chunks =====================
     if (lane == 0) {
       for (int j = 0; j < NCH; ++j) {
-        const uint32_t ph = j & 1;
-        mbar_wait(w1_empty, ph ^ 1);
-        mbar_expect_tx(w1_full, Cfg::W1_BYTES);
+        const int st = j % WS;
+        const uint32_t ph = (j / WS) & 1;
+        mbar_wait(&w1_empty[st], ph ^ 1);
+        FB_TRACE(0, 2 * j);
+        mbar_expect_tx(&w1_full[st], Cfg::W1_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < Cfg::KB; ++kb) tma_load_3d(sW1 + kb * (FB_NC * 128), &tmW1, w1_full, kb * 64, j * FB_NC, 0);
-        mbar_wait(w2_empty, ph ^ 1);
-        mbar_expect_tx(w2_full, Cfg::W2_BYTES);
+        for (int kb = 0; kb < Cfg::KB; ++kb)
+          tma_load_3d(sW1 + st * Cfg::W1_BYTES + kb * (FB_NC * 128), &tmW1, &w1_full[st], kb * 64, j * FB_NC, 0);
+        mbar_wait(&w2_empty[st], ph ^ 1);
+        FB_TRACE(0, 2 * j + 1);
+        mbar_expect_tx(&w2_full[st], Cfg::W2_BYTES);
 #pragma unroll
         for (int part = 0; part < Cfg::N2_PARTS; ++part)
-          tma_load_3d(sW2 + part * (Cfg::N2 * 128), &tmW2, w2_full, j * FB_NC, part * Cfg::N2, 0);
+          tma_load_3d(sW2 + st * Cfg::W2_BYTES + part * (Cfg::N2 * 128), &tmW2, &w2_full[st], j * FB_NC, part * Cfg::N2, 0);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loop with uniform control flow (operands stay in uniform registers); one elected lane
+    // issues tcgen05.mma / tcgen05.commit.
+    {
       constexpr uint32_t idesc1 = make_instr_desc(OSB_F16, FB_M, FB_NC, 0, 0);
       constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, FB_M, Cfg::N2, 0, 0);
       const uint32_t a_addr = smem_u32(sA), w1_addr = smem_u32(sW1), w2_addr = smem_u32(sW2), h_addr = smem_u32(sH);
+      // Descriptors are loop invariant up to a byte offset: build them once and advance the 14-bit start-address field
+      // (units of 16 B) with one integer add per MMA — the single issuing thread is latency bound on its scalar stream.
+      const uint64_t dA0 = make_smem_desc_sw128(a_addr, 16, 1024);
+      const uint64_t dW10 = make_smem_desc_sw128(w1_addr, 16, 1024);
+      const uint64_t dW20 = make_smem_desc_sw128(w2_addr, 16, 1024);
+      const uint64_t dH0 = make_smem_desc_sw128(h_addr, 16, 1024);
+      if (lane == 0) FB_TRACE(1, 0);
       mbar_wait(a_ready, 0);
+      if (lane == 0) FB_TRACE(1, 1);
       tc_fence_after_sync();
       for (int j = 0; j <= NCH; ++j) {
         if (j < NCH) {  // pwconv1 of chunk j -> acc1[j & 1]
           const int buf = j & 1;
-          mbar_wait(w1_full, j & 1);
+          const int st = j % WS;
+          mbar_wait(&w1_full[st], (j / WS) & 1);
+          if (lane == 0) FB_TRACE(1, 2 + 6 * j);
           mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
+          if (lane == 0) FB_TRACE(1, 3 + 6 * j);
           tc_fence_after_sync();
           const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * FB_NC;
+          if (elect_one()) {
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb)
+            for (int kb = 0; kb < Cfg::KB; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc_sw128(a_addr + kb * (FB_M * 128) + k * 32, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(w1_addr + kb * (FB_NC * 128) + k * 32, 16, 1024);
-              umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
-            }
-          umma_commit(w1_empty);
-          umma_commit(&acc1_full[buf]);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = dA0 + static_cast<uint64_t>((kb * (FB_M * 128) + k * 32) >> 4);
+                const uint64_t db = dW10 + static_cast<uint64_t>((st * Cfg::W1_BYTES + kb * (FB_NC * 128) + k * 32) >> 4);
+                umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
+              }
+            umma_commit(&w1_empty[st]);
+            umma_commit(&acc1_full[buf]);
+          }
+          __syncwarp();
+          if (lane == 0) FB_TRACE(1, 4 + 6 * j);
         }
         if (j >= 1) {   // pwconv2 of chunk j-1: acc2 += gelu_chunk . W2[:, chunk]^T
           const int jj = j - 1, buf = jj & 1;
-          mbar_wait(w2_full, jj & 1);
+          const int st = jj % WS;
+          mbar_wait(&w2_full[st], (jj / WS) & 1);
+          if (lane == 0) FB_TRACE(1, 5 + 6 * jj);
           mbar_wait(&h_full[buf], (jj >> 1) & 1);
+          if (lane == 0) FB_TRACE(1, 6 + 6 * jj);
           tc_fence_after_sync();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(h_addr + buf * Cfg::H_BYTES + k * 32, 16, 1024);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = dH0 + static_cast<uint64_t>((buf * Cfg::H_BYTES + k * 32) >> 4);
 #pragma unroll
-            for (int part = 0; part < Cfg::N2_PARTS; ++part) {
-              const uint64_t db = make_smem_desc_sw128(w2_addr + part * (Cfg::N2 * 128) + k * 32, 16, 1024);
-              umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
+              for (int part = 0; part < Cfg::N2_PARTS; ++part) {
+                const uint64_t db = dW20 + static_cast<uint64_t>((st * Cfg::W2_BYTES + part * (Cfg::N2 * 128) + k * 32) >> 4);
+                umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(&w2_empty[st]);
+            umma_commit(&h_empty[buf]);
           }
-          umma_commit(w2_empty);
-          umma_commit(&h_empty[buf]);
+          __syncwarp();
+          if (lane == 0) FB_TRACE(1, 7 + 6 * jj);
         }
       }
-      umma_commit(acc2_full);
+      if (elect_one()) umma_commit(acc2_full);
+      __syncwarp();
     }
   } else {
     // ===================== worker warps =====================
@@ -175,6 +213,14 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     const int half = (ww >> 2);       // which 32-column half of a 64-column chunk / which half of C in the last epilogue
     // ---- prologue: dwconv7 + LayerNorm statistics -> fp16 xhat in swizzled smem (rows ww*16 .. +16) ----
     {
+      // With ~224 KB of shared memory carved out, L1D is only a few KB: the 7 x C filter taps would be re-fetched from L2 for
+      // every row.  The GELU staging buffers are idle until the first chunk, so the taps (tap-major) and the bias live there.
+      float* s_dw = reinterpret_cast<float*>(sH);          // [7][C]
+      float* s_db = s_dw + 7 * C;                          // [C]
+      const int wt = threadIdx.x - 64;                     // 0 .. 255
+      for (int i = wt; i < 7 * C; i += FB_WORKERS * 32) s_dw[(i % 7) * C + i / 7] = p.dw_w[i];
+      for (int i = wt; i < C; i += FB_WORKERS * 32) s_db[i] = p.dw_b[i];
+      asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");   // worker warps only
       const float* xb = p.x + static_cast<long long>(b) * p.T * C;
       float4 win[7][VPL];
       auto load_row = [&](int t, float4 (&dst)[VPL]) {
@@ -189,26 +235,33 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       const int r_begin = ww * 16;
 #pragma unroll
       for (int jx = 0; jx < 6; ++jx) load_row(t0 + r_begin + jx - 3, win[jx + 1]);
+      // rows are requested two iterations before they are needed (the loop is otherwise one DRAM latency per row)
+      float4 q0[VPL], q1[VPL];
+      load_row(t0 + r_begin + 3, q0);
+      load_row(t0 + r_begin + 4, q1);
+#pragma unroll 1
       for (int r = r_begin; r < r_begin + 16; ++r) {
         const int t = t0 + r;
 #pragma unroll
         for (int jx = 0; jx < 6; ++jx)
 #pragma unroll
           for (int v = 0; v < VPL; ++v) win[jx][v] = win[jx + 1][v];
-        load_row(t + 3, win[6]);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) { win[6][v] = q0[v]; q0[v] = q1[v]; }
+        if (r + 2 < r_begin + 16) load_row(t + 5, q1);
         float4 d[VPL];
         float s = 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int c = v * 128 + lane * 4;
-          float4 acc = __ldg(reinterpret_cast<const float4*>(p.dw_b + c));
-          const float* wp = p.dw_w + c * 7;  // dw_w is (C, 7): the 7 taps of one channel are contiguous
+          float4 acc = *reinterpret_cast<const float4*>(s_db + c);
 #pragma unroll
           for (int jx = 0; jx < 7; ++jx) {
-            acc.x = fmaf(__ldg(wp + jx), win[jx][v].x, acc.x);
-            acc.y = fmaf(__ldg(wp + 7 + jx), win[jx][v].y, acc.y);
-            acc.z = fmaf(__ldg(wp + 14 + jx), win[jx][v].z, acc.z);
-            acc.w = fmaf(__ldg(wp + 21 + jx), win[jx][v].w, acc.w);
+            const float4 wj = *reinterpret_cast<const float4*>(s_dw + jx * C + c);
+            acc.x = fmaf(wj.x, win[jx][v].x, acc.x);
+            acc.y = fmaf(wj.y, win[jx][v].y, acc.y);
+            acc.z = fmaf(wj.z, win[jx][v].z, acc.z);
+            acc.w = fmaf(wj.w, win[jx][v].w, acc.w);
           }
           d[v] = acc;
           s += (acc.x + acc.y) + (acc.z + acc.w);
@@ -236,13 +289,24 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      if (ww == 0 && lane == 0) FB_TRACE(2, 0);
+      // all workers must be done with the filter taps before the first GELU chunk overwrites the staging buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");
     }
     // ---- per chunk: acc1 -> +bias -> GELU -> fp16 -> swizzled smem (A operand of pwconv2) ----
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float bias_cur[32], bias_nxt[32];   // the folded pwconv1 bias of this thread's 32 columns, fetched one chunk ahead (L1 is tiny here)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_cur[i] = __ldg(p.b1 + half * 32 + i);
     for (int j = 0; j < NCH; ++j) {
       const int buf = j & 1;
+      if (j + 1 < NCH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bias_nxt[i] = __ldg(p.b1 + (j + 1) * FB_NC + half * 32 + i);
+      }
       mbar_wait(&acc1_full[buf], (j >> 1) & 1);
+      if (ww == 0 && lane == 0) FB_TRACE(2, 1 + 5 * j);
       tc_fence_after_sync();
       uint32_t rr[32];
       tmem_ld_32x32(lane_addr + Cfg::ACC1_COL + buf * FB_NC + half * 32, rr);
@@ -250,11 +314,15 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc1_empty[buf]);
+      if (ww == 0 && lane == 0) FB_TRACE(2, 2 + 5 * j);
       float v[32];
-      const float* bp = p.b1 + j * FB_NC + half * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(rr[i]) + __ldg(bp + i));
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(rr[i]) + bias_cur[i]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bias_cur[i] = bias_nxt[i];
+      if (ww == 0 && lane == 0) FB_TRACE(2, 3 + 5 * j);
       mbar_wait(&h_empty[buf], ((j >> 1) & 1) ^ 1);
+      if (ww == 0 && lane == 0) FB_TRACE(2, 4 + 5 * j);
       uint8_t* hrow = sH + buf * Cfg::H_BYTES;
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -269,40 +337,58 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         u.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(hrow + sw128_offset(row, half * 4 + c4)) = u;
       }
+      if (ww == 0 && lane == 0 && j < 8) FB_TRACE(2, 210 + j);
       fence_proxy_async_smem();
+      if (ww == 0 && lane == 0 && j < 8) FB_TRACE(2, 220 + j);
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[buf]);
+      if (ww == 0 && lane == 0) FB_TRACE(2, 5 + 5 * j);
     }
-    // ---- final epilogue: bias, layer scale, DropPath, residual, mask ----
+    // ---- final epilogue: bias, layer scale, DropPath -> fp32 tile staged in shared memory (all MMA operands are dead
+    //      now), then residual add + pad mask with fully coalesced row-wise global reads / writes ----
     mbar_wait(acc2_full, 0);
+    if (ww == 0 && lane == 0) FB_TRACE(2, 200);
     tc_fence_after_sync();
-    const int t = t0 + row;
-    const bool valid = t < p.T;
-    const long long grow = static_cast<long long>(b) * p.T + t;
-    const float keep = (p.pad_mask != nullptr && valid && p.pad_mask[grow]) ? 0.f : 1.f;
+    float* stile = reinterpret_cast<float*>(smem);
+    constexpr int OLD = Cfg::OUT_LD;
     const float rs = p.row_scale != nullptr ? p.row_scale[b] : 1.f;
     constexpr int CH = C / 2;  // columns per worker half
     for (int c0 = half * CH; c0 < (half + 1) * CH; c0 += 32) {
       uint32_t rr[32];
       tmem_ld_32x32(lane_addr + c0, rr);
       tmem_ld_wait();
-      if (valid) {
-        const float* rp = p.x + grow * C + c0;
-        float* op = p.out + grow * C + c0;
+      float* dst = stile + row * OLD + c0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-          float4 o;
-          o.x = (r4.x + __ldg(p.gamma + c0 + i + 0) * (__uint_as_float(rr[i + 0]) + __ldg(p.b2 + c0 + i + 0)) * rs) * keep;
-          o.y = (r4.y + __ldg(p.gamma + c0 + i + 1) * (__uint_as_float(rr[i + 1]) + __ldg(p.b2 + c0 + i + 1)) * rs) * keep;
-          o.z = (r4.z + __ldg(p.gamma + c0 + i + 2) * (__uint_as_float(rr[i + 2]) + __ldg(p.b2 + c0 + i + 2)) * rs) * keep;
-          o.w = (r4.w + __ldg(p.gamma + c0 + i + 3) * (__uint_as_float(rr[i + 3]) + __ldg(p.b2 + c0 + i + 3)) * rs) * keep;
-          *reinterpret_cast<float4*>(op + i) = o;
-        }
+      for (int i = 0; i < 32; i += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + i));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + i));
+        float4 o;
+        o.x = g4.x * (__uint_as_float(rr[i + 0]) + b4.x) * rs;
+        o.y = g4.y * (__uint_as_float(rr[i + 1]) + b4.y) * rs;
+        o.z = g4.z * (__uint_as_float(rr[i + 2]) + b4.z) * rs;
+        o.w = g4.w * (__uint_as_float(rr[i + 3]) + b4.w) * rs;
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");   // worker warps only
+    for (int r = ww; r < FB_M; r += FB_WORKERS) {          // one warp per row: 512-byte coalesced accesses
+      const int t = t0 + r;
+      if (t >= p.T) break;
+      const long long grow = static_cast<long long>(b) * p.T + t;
+      const float keep = (p.pad_mask != nullptr && p.pad_mask[grow]) ? 0.f : 1.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c = v * 128 + lane * 4;
+        const float4 x4 = *reinterpret_cast<const float4*>(p.x + grow * C + c);
+        const float4 d4 = *reinterpret_cast<const float4*>(stile + r * OLD + c);
+        float4 o;
+        o.x = (x4.x + d4.x) * keep; o.y = (x4.y + d4.y) * keep; o.z = (x4.z + d4.z) * keep; o.w = (x4.w + d4.w) * keep;
+        *reinterpret_cast<float4*>(p.out + grow * C + c) = o;
       }
     }
   }
 
+  if (threadIdx.x == 64) FB_TRACE(2, 201);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -333,6 +419,10 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
 
 using namespace osb;
 
+static long long* g_fused_trace = nullptr;
+/* developer hook (not in the public header): device buffer of 3*256 int64 receiving a clock64 timeline of CTA 0 */
+extern "C" void osb_debug_set_fused_trace(long long* buf) { g_fused_trace = buf; }
+
 extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
                                       const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
                                       const uint8_t* pad_mask, float* out, int32_t B, int32_t T, int32_t C, int32_t I, float eps,
@@ -342,6 +432,7 @@ extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const f
   FusedParams p;
   p.x = x; p.dw_w = dw_w; p.dw_b = dw_b; p.b1 = b1f; p.b2 = b2; p.gamma = gamma; p.row_scale = row_scale; p.pad_mask = pad_mask;
   p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps;
+  p.trace = g_fused_trace;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 256 && I == 1024) return launch_fused<256, 1024>(w1f_h16, w2_h16, p, s);
   if (C == 384 && I == 1152) return launch_fused<384, 1152>(w1f_h16, w2_h16, p, s);

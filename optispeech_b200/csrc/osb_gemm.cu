@@ -481,28 +481,32 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_instr_desc(OSB_F16, BM, Cfg::NINST, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % Cfg::STAGES;
-        const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+    // whole warp, uniform control flow (descriptors live in uniform registers); one elected lane issues
+    constexpr uint32_t idesc = make_instr_desc(OSB_F16, BM, Cfg::NINST, 0, 0);
+    const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % Cfg::STAGES;
+      const uint32_t ph = (it / Cfg::STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint64_t da0 = d0 + static_cast<uint64_t>((s * Cfg::STAGE_BYTES) >> 4);
+        const uint64_t db0 = da0 + static_cast<uint64_t>(Cfg::A_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * UMMA_K_BYTES, 16, 1024);
 #pragma unroll
           for (int c = 0; c < Cfg::NCHUNK; ++c) {
-            const uint64_t db = make_smem_desc_sw128(b_addr + c * Cfg::NINST * ROW_BYTES + k * UMMA_K_BYTES, 16, 1024);
-            umma_ss<false>(tmem_base + c * Cfg::NINST, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_ss<false>(tmem_base + c * Cfg::NINST, da0 + static_cast<uint64_t>((k * UMMA_K_BYTES) >> 4),
+                           db0 + static_cast<uint64_t>((c * Cfg::NINST * ROW_BYTES + k * UMMA_K_BYTES) >> 4), idesc,
+                           (it | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
+    __syncwarp();
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);

@@ -218,8 +218,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // of the GELU value <= 5e-7 for |x| <= 6 — far below the fp16 rounding of the tensor-core operand it feeds — at ~18
 // instructions (one MUFU.RCP, one MUFU.EX2) instead of the ~100 of erff(): the GELU epilogue, not the MMA, bounds the
 // fused ConvNeXt block.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float erfc_pos_as(float z, float& e_out) {
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));   // 1 ulp: far inside the 1.5e-7 error of the formula
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
