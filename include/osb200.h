@@ -126,6 +126,8 @@ typedef struct osb_gemm_desc {
    * dropout_seed: forward scales the LN output, RELU_LN_BWD scales the incoming gradient by the same mask. */
   float dropout_p;        /* 0 disables                                                              */
   uint64_t dropout_seed;
+  const uint64_t* dropout_seed_dev; /* optional device scalar added to dropout_seed (lets a captured CUDA graph draw a new
+                                       mask on every replay: the host bumps / a captured kernel increments the scalar)      */
   /* per-batch B operand (batched matmul): w is (B, N, ldw) — with SPLIT_IN (B, N, [hi K | lo K]) — and taps == 1 */
   int32_t w_batched;
   const int64_t* col_len; /* ATTN_LOGP: (B) number of valid columns (text length)                    */
@@ -249,7 +251,8 @@ int osb_layernorm_bwd(const float* dy, const float* x, const float* w, float* dx
  * r = relu(conv) of the last layer, fp16, saved by OSB_EPI_RELU_LN + OSB_FLAG_SAVE_PRE. */
 int osb_predictor_tail_bwd(const float* d_out /*(rows)*/, const uint8_t* pad_mask, const void* r_h16, const float* ln_w,
                            const float* ln_b, const float* lin_w, void* g_conv_h16, float* dlin_w, float* dlin_b, float* dln_w,
-                           float* dln_b, int64_t rows, int32_t C, float eps, float dropout_p, uint64_t dropout_seed, void* stream);
+                           float* dln_b, int64_t rows, int32_t C, float eps, float dropout_p, uint64_t dropout_seed,
+                           const uint64_t* dropout_seed_dev, void* stream);
 
 /* LayerNorm parameter gradients of an inner predictor layer: dln_w += sum gy*xhat(r), dln_b += sum gy, with
  * gy = fp16 gradient wrt the layer output (aux of OSB_EPI_RELU_LN_BWD + OSB_FLAG_OUT_H16). */
@@ -298,6 +301,11 @@ int osb_grad_sumsq(const float* g, int64_t n, float* stats /*(2)*/, void* stream
  * bias correction for `step` (1-based).  Skipped entirely when stats[1] != 0 (non-finite gradient). */
 int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int64_t step, float max_norm, float inv_scale, void* stream);
+
+/* Same update with the per-step scalars read from device memory — hyper = [lr, 1 - beta1^step, sqrt(1 - beta2^step)] — so that the
+ * launch can live inside a captured CUDA graph while the host keeps driving the LR schedule. */
+int osb_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, const float* hyper, float beta1,
+                       float beta2, float eps, float weight_decay, float max_norm, float inv_scale, void* stream);
 
 /* Beta-binomial alignment prior on the device: out[b,t,n] = log BetaBinomial(n; N_b, t+1, T_b-t) for t < T_b, n < N_b, -inf
  * elsewhere; log_factorial[m] = log(m!) in float64 for m <= Tm + Tx.  Replaces AlignmentModule._generate_prior

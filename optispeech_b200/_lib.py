@@ -53,6 +53,7 @@ class GemmDesc(C.Structure):
         ("row_stat", C.c_void_p),
         ("dropout_p", C.c_float),
         ("dropout_seed", C.c_uint64),
+        ("dropout_seed_dev", C.c_void_p),
         ("w_batched", C.c_int32),
         ("col_len", C.c_void_p),
     ]
@@ -104,7 +105,7 @@ def load() -> C.CDLL:
         "osb_ln_fold_bwd": [P, P, P, P, P, P, P, I32, I32, P],
         "osb_dwconv_bwd": [P, P, P, P, P, P, P, P, I32, I32, I32, P],
         "osb_layernorm_bwd": [P, P, P, P, P, P, I64, I32, F, P],
-        "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, F, C.c_uint64, P],
+        "osb_predictor_tail_bwd": [P, P, P, P, P, P, P, P, P, P, P, I64, I32, F, F, C.c_uint64, P, P],
         "osb_ln_param_grad": [P, P, P, P, P, I64, I32, F, P],
         "osb_variance_embed_bwd": [P, P, P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_embed_text_bwd": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
@@ -120,6 +121,7 @@ def load() -> C.CDLL:
         "osb_mel_loss": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F, P, P, P, P],
         "osb_grad_sumsq": [P, I64, P, P],
         "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
+        "osb_adamw_step_dev": [P, P, P, P, I64, P, P, F, F, F, F, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],
     }
     for name, argtypes in sigs.items():

@@ -315,8 +315,9 @@ predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restric
                         const __half* __restrict__ r, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                         const float* __restrict__ lin_w, __half* __restrict__ g_conv, float* __restrict__ dlin_w,
                         float* __restrict__ dlin_b, float* __restrict__ dln_w, float* __restrict__ dln_b, long long rows, float eps,
-                        float drop_p, float drop_inv_keep, unsigned long long drop_seed) {
+                        float drop_p, float drop_inv_keep, unsigned long long drop_seed, const unsigned long long* drop_seed_dev) {
   constexpr int C = 128 * VPL;
+  if (drop_p > 0.f && drop_seed_dev != nullptr) drop_seed += *drop_seed_dev;
   const int lane = threadIdx.x & 31;
   long long r0, r1;
   warp_rows(rows, r0, r1);
@@ -539,7 +540,7 @@ extern "C" int osb_layernorm_bwd(const float* dy, const float* x, const float* w
 extern "C" int osb_predictor_tail_bwd(const float* d_out, const uint8_t* pad_mask, const void* r_h16, const float* ln_w,
                                       const float* ln_b, const float* lin_w, void* g_conv_h16, float* dlin_w, float* dlin_b,
                                       float* dln_w, float* dln_b, int64_t rows, int32_t C, float eps, float dropout_p,
-                                      uint64_t dropout_seed, void* stream) {
+                                      uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* stream) {
   OSB_REQUIRE(d_out && r_h16 && ln_w && ln_b && lin_w && g_conv_h16 && dlin_w && dlin_b && dln_w && dln_b, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
   OSB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, OSB_ERR_ARG);
@@ -549,7 +550,7 @@ extern "C" int osb_predictor_tail_bwd(const float* d_out, const uint8_t* pad_mas
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         d_out, nullptr, pad_mask, static_cast<const __half*>(r_h16), ln_w, ln_b, lin_w,
                         static_cast<__half*>(g_conv_h16), dlin_w, dlin_b, dln_w, dln_b, rows, eps, dropout_p, inv_keep,
-                        static_cast<unsigned long long>(dropout_seed))));
+                        static_cast<unsigned long long>(dropout_seed), reinterpret_cast<const unsigned long long*>(dropout_seed_dev))));
   count_launch();
   return launch_status();
 }
@@ -562,7 +563,7 @@ extern "C" int osb_ln_param_grad(const void* gy_h16, const void* r_h16, const fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         nullptr, static_cast<const __half*>(gy_h16), nullptr, static_cast<const __half*>(r_h16), ln_w, nullptr,
-                        nullptr, nullptr, nullptr, nullptr, dln_w, dln_b, rows, eps, 0.f, 0.f, 0ull)));
+                        nullptr, nullptr, nullptr, nullptr, dln_w, dln_b, rows, eps, 0.f, 0.f, 0ull, nullptr)));
   count_launch();
   return launch_status();
 }

@@ -45,6 +45,7 @@ struct GemmKParams {
   float drop_p;
   float drop_inv_keep;
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
   int w_lo_slice;   // slice offset of the lo parts of W (split precision, shared weights)
   int w_lo_koff;    // K offset of the lo parts of W (split precision, batched weights stored [hi K | lo K])
   int w_batch;      // 1: slice index += batch (per-batch B operand)
@@ -147,6 +148,8 @@ __device__ __forceinline__ void store_h(const GemmKParams& p, void* base, long l
 
 template <int EPI, int BN>
 __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t taddr, int b, int t, int n0) {
+  unsigned long long drop_seed = p.drop_seed;
+  if (p.drop_p > 0.f && p.drop_seed_dev != nullptr) drop_seed += *p.drop_seed_dev;
   const bool valid = t < p.T;
   const long long row = static_cast<long long>(b) * p.T + t;
   const bool padded = (p.pad_mask != nullptr) && valid && (p.pad_mask[row] != 0);
@@ -274,7 +277,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       ld_h16x32(rrow + c0, r);
       if (p.drop_p > 0.f) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
       }
       if (valid && (p.flags & OSB_FLAG_OUT_H16)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
 #pragma unroll
@@ -290,7 +293,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       ld_h16x32(rrow + c0, r);
       if (p.drop_p > 0.f) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -397,7 +400,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       if (kRelu && p.drop_p > 0.f) {
         const unsigned long long base = static_cast<unsigned long long>(valid ? row : 0) * BN + c0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(p.drop_seed, base + i, p.drop_p, p.drop_inv_keep);
+        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, base + i, p.drop_p, p.drop_inv_keep);
       }
       if (p.flags & OSB_FLAG_DOT) {
 #pragma unroll
@@ -792,7 +795,7 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.w_lo_slice = w_batched ? 0 : d->taps;
   p.w_lo_koff = w_batched ? d->K : 0;
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
-  p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed;
+  p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed; p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(d->dropout_seed_dev);
   p.drop_inv_keep = d->dropout_p > 0.f && d->dropout_p < 1.f ? 1.f / (1.f - d->dropout_p) : 0.f;
   OSB_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, OSB_ERR_ARG);
 

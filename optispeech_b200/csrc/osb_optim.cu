@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, inv_scale;
+  const float* hyper;  // optional device [lr, bc1, bc2_sqrt] overriding the by-value fields (CUDA-graph replay)
 };
 
 // torch.optim.AdamW (decoupled weight decay) preceded by clip_grad_norm_(max_norm) on the unscaled gradient:
@@ -48,6 +49,11 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
              const float* __restrict__ stats, AdamArgs a) {
   if (stats[1] != 0.f) return;
+  if (a.hyper != nullptr) {
+    a.lr = a.hyper[0];
+    a.bc1 = a.hyper[1];
+    a.bc2_sqrt = a.hyper[2];
+  }
   const float total = sqrtf(stats[0]) * a.inv_scale;
   float coef = a.max_norm > 0.f ? a.max_norm / (total + 1e-6f) : 1.f;
   coef = fminf(coef, 1.f) * a.inv_scale;
@@ -90,7 +96,22 @@ extern "C" int osb_adamw_step(float* p, const float* g, float* m, float* v, int6
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.f - powf(beta1, static_cast<float>(step));
   a.bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
-  a.max_norm = max_norm; a.inv_scale = inv_scale;
+  a.max_norm = max_norm; a.inv_scale = inv_scale; a.hyper = nullptr;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, stats, a);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_adamw_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, const float* hyper,
+                                  float beta1, float beta2, float eps, float weight_decay, float max_norm, float inv_scale,
+                                  void* stream) {
+  OSB_REQUIRE(p && g && m && v && stats && hyper, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0, OSB_ERR_SHAPE);
+  AdamArgs a;
+  a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.bc1 = 1.f; a.bc2_sqrt = 1.f;
+  a.max_norm = max_norm; a.inv_scale = inv_scale; a.hyper = hyper;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   adamw_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, stats, a);

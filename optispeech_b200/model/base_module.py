@@ -43,6 +43,9 @@ class BaseModule(nn.Module):
         self._schedulers = None
         self._fit = _FitLoopState()
         self.loss_scale = 1024.0  # static loss scale for the fp16 tensor-core operands of the backward pass
+        self.cuda_graph = False   # True: training_step replays a captured CUDA graph of itself (model/graphed.py)
+        self._graphed = None
+        self._capturing = False
         self.ckpt_loaded_epoch = -1
 
     # -- Lightning-compatible helpers ------------------------------------------------------------
@@ -155,6 +158,16 @@ class BaseModule(nn.Module):
                 [{"scheduler": scheduler_gen, "interval": "step"}, {"scheduler": scheduler_disc, "interval": "step"}])
 
     def training_step(self, batch, batch_idx, **kwargs):
+        """Reference base_lightning_module.py:86-130.  With `self.cuda_graph = True` the same step is captured once per
+        batch shape and training phase and replayed afterwards (one graph launch instead of ~550 kernel launches)."""
+        if self.cuda_graph and not self._capturing:
+            if self._graphed is None:
+                from .graphed import GraphedTrainingStep
+                self._graphed = GraphedTrainingStep(self)
+            return self._graphed(batch, batch_idx)
+        return self._training_step_eager(batch, batch_idx, **kwargs)
+
+    def _training_step_eager(self, batch, batch_idx, **kwargs):
         acc = self.train_args.gradient_accumulate_batches
         if acc is not None:
             loss_scaling_factor = float(acc)
@@ -165,6 +178,9 @@ class BaseModule(nn.Module):
         opt_g, opt_d = self.optimizers()
         sched_g, sched_d = self.lr_schedulers()
 
+        if self.device.type == "cuda":
+            from .. import ops
+            ops.step_counter(self.device).add_(1)  # device-side ingredient of the dropout seeds (graph-replay safe)
         self.toggle_optimizer(opt_g)
         loss_g, wav_outputs = self.training_step_g(batch, train_discriminator=train_discriminator)
         loss_g = loss_g / loss_scaling_factor
@@ -174,9 +190,11 @@ class BaseModule(nn.Module):
         self.clip_gradients(opt_g, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
         if should_apply:
             opt_g.step()
-            sched_g.step()
+            if not self._capturing:  # host bookkeeping of a captured step is done per replay (model/graphed.py)
+                sched_g.step()
         self.untoggle_optimizer(opt_g)
-        self._fit.total_batch_idx += 1
+        if not self._capturing:
+            self._fit.total_batch_idx += 1
         if not train_discriminator:
             return
 
@@ -190,7 +208,8 @@ class BaseModule(nn.Module):
         self.clip_gradients(opt_d, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
         if should_apply:
             opt_d.step()
-            sched_d.step()
+            if not self._capturing:
+                sched_d.step()
         self.untoggle_optimizer(opt_d)
 
     def training_step_g(self, batch, train_discriminator):

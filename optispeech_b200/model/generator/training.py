@@ -173,7 +173,9 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
         num_frames = (mel_lengths - 4).to(y.dtype)
         max_start = (num_frames - segment_size).clamp(min=0)
         if seg_rand is None:
-            seg_rand = torch.rand([x.shape[0]])
+            # inside a CUDA-graph capture the draw has to live on the device (a pageable H2D copy cannot be captured)
+            capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+            seg_rand = torch.rand([x.shape[0]], device=dev) if capturing else torch.rand([x.shape[0]])
         start_idx = (seg_rand.to(dev) * max_start).to(torch.long)
         segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
         _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt

@@ -1,0 +1,141 @@
+"""CUDA-graph replay of OptiSpeech.training_step.
+
+The eager step is ~200 library launches plus ~350 small torch kernels for ~7 ms of device work: the host cannot issue
+them as fast as a B200 retires them.  `GraphedTrainingStep` captures one whole step — forward, losses, backward, gradient
+all-reduce, clip + AdamW — into a `torch.cuda.CUDAGraph` per (batch shapes, training phase) and replays it afterwards.
+
+What makes the captured step reusable:
+  * inputs live in static device buffers refreshed by async copies before each replay;
+  * every per-step scalar is read from device memory: lr / bias corrections (`FlatAdamW.stage_hyper`,
+    osb_adamw_step_dev) and the dropout seeds (host seed + the device step counter, include/osb200.h
+    `dropout_seed_dev`); torch's own RNG ops advance their Philox offset per replay (torch.cuda.graph does that);
+  * host bookkeeping the reference does per step (scheduler.step, batch counters — base_lightning_module.py:86-130)
+    runs on the host around the replay, so `global_step`, the LR schedule and the pre-training gate behave as in eager;
+  * packed fp16 weight copies of trainable parameters are rebuilt inside the graph (their epochs are bumped before the
+    capture); packs of frozen parameters the graph reads are kept alive by the entry.
+
+Gradient accumulation (`gradient_accumulate_batches` > 1) alternates two different steps and stays eager.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..optim import FlatAdamW
+
+
+class _Entry:
+    def __init__(self):
+        self.graph: torch.cuda.CUDAGraph = None
+        self.static: Dict[str, torch.Tensor] = {}
+        self.passthrough: Dict[str, Any] = {}
+        self.keepalive = []
+        self.launches = 0
+        self.train_discriminator = False
+
+
+def _as_tensor(v):
+    return torch.from_numpy(v) if isinstance(v, np.ndarray) else v
+
+
+class GraphedTrainingStep:
+    def __init__(self, module, warmup: int = 3):
+        self.module = module
+        self.warmup = int(warmup)
+        self._entries: Dict[tuple, _Entry] = {}
+        self._warm: Dict[tuple, int] = {}
+        self.replays = 0
+        self.last_entry: _Entry = None
+
+    @staticmethod
+    def _key(batch, train_discriminator: bool) -> tuple:
+        sig = []
+        for k in sorted(batch):
+            v = batch[k]
+            if isinstance(v, (torch.Tensor, np.ndarray)):
+                sig.append((k, tuple(v.shape), str(v.dtype)))
+            else:
+                sig.append((k, repr(v)))
+        return (bool(train_discriminator),) + tuple(sig)
+
+    def __call__(self, batch, batch_idx):
+        m = self.module
+        acc = m.train_args.gradient_accumulate_batches
+        if m.device.type != "cuda" or (acc is not None and acc != 1):
+            return m._training_step_eager(batch, batch_idx)
+        train_discriminator = m.global_step >= m.train_args.pretraining_steps
+        key = self._key(batch, train_discriminator)
+        entry = self._entries.get(key)
+        if entry is None:
+            seen = self._warm.get(key, 0)
+            if seen < self.warmup:  # eager steps build the flat buckets, tables and kernel attributes the capture relies on
+                self._warm[key] = seen + 1
+                return m._training_step_eager(batch, batch_idx)
+            entry = self._capture(batch, batch_idx, train_discriminator)
+            self._entries[key] = entry
+        self._replay(entry, batch)
+        return None
+
+    # ------------------------------------------------------------------------------------------------
+    def _optimizers(self, train_discriminator: bool):
+        opt_g, opt_d = self.module.optimizers()
+        sched_g, sched_d = self.module.lr_schedulers()
+        pairs = [(opt_g, sched_g)]
+        if train_discriminator:
+            pairs.append((opt_d, sched_d))
+        return pairs
+
+    def _capture(self, batch, batch_idx, train_discriminator: bool) -> _Entry:
+        m = self.module
+        dev = m.device
+        e = _Entry()
+        e.train_discriminator = train_discriminator
+        for k, v in batch.items():
+            if isinstance(v, (torch.Tensor, np.ndarray)):
+                e.static[k] = _as_tensor(v).to(dev).clone()
+            else:
+                e.passthrough[k] = v
+        for opt, _ in self._optimizers(train_discriminator):
+            if not isinstance(opt, FlatAdamW):
+                raise RuntimeError("cuda_graph=True needs the FlatAdamW optimizer (torch.optim.AdamW in the config maps to it)")
+            opt.graph_mode = True
+            opt._ensure_hyper(dev)
+            for b in opt.buckets():  # force in-graph re-packing of every trainable weight
+                for p in b.params:
+                    p._osb_epoch = getattr(p, "_osb_epoch", 0) + 1
+        lib = _lib.load()
+        static_batch = dict(e.passthrough)
+        static_batch.update(e.static)
+        world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.osb_launch_count()
+        m._capturing = True
+        try:
+            # the NCCL watchdog thread polls events while we capture: only this thread's calls may invalidate the capture
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
+                m._training_step_eager(static_batch, batch_idx)
+        finally:
+            m._capturing = False
+        e.launches = int(lib.osb_launch_count() - n0)
+        e.graph = graph
+        from .packing import live_packs
+        e.keepalive = live_packs()
+        return e
+
+    def _replay(self, e: _Entry, batch) -> None:
+        m = self.module
+        for k, buf in e.static.items():
+            buf.copy_(_as_tensor(batch[k]), non_blocking=True)
+        pairs = self._optimizers(e.train_discriminator)
+        for opt, _ in pairs:
+            opt.stage_hyper()
+        e.graph.replay()
+        for _, sched in pairs:
+            sched.step()
+        m._fit.total_batch_idx += 1
+        self.replays += 1
+        self.last_entry = e

@@ -10,12 +10,23 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Iterable, Tuple
 
+import weakref
+
 import torch
+
+
+_CACHES = weakref.WeakSet()
+
+
+def live_packs() -> list:
+    """Every packed tensor currently cached by any module (a captured CUDA graph keeps them alive: model/graphed.py)."""
+    return [hit[1] for cache in list(_CACHES) for hit in list(cache._store.values())]
 
 
 class PackedCache:
     def __init__(self):
         self._store: Dict[str, Tuple[tuple, object]] = {}
+        _CACHES.add(self)
 
     @staticmethod
     def _key(params: Iterable[torch.Tensor]) -> tuple:

@@ -23,6 +23,20 @@ __all__ = [
 ]
 
 
+_STEP_COUNTERS = {}
+
+
+def step_counter(device) -> torch.Tensor:
+    """Per-device int64 scalar that the training step increments once per step (on the device).  Counter-based dropout adds it
+    to its seed, so a captured CUDA graph draws fresh masks on every replay without any host-side value baked into the graph."""
+    key = torch.device(device).index or 0
+    t = _STEP_COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros((), device=device, dtype=torch.int64)
+        _STEP_COUNTERS[key] = t
+    return t
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -87,6 +101,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.dot_w, d.dot_b, d.out_dot = _ptr(dot_w), _ptr(dot_b), _ptr(out_dot)
     d.aux_in_h16, d.row_stat = _ptr(aux_in), _ptr(row_stat)
     d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
+    d.dropout_seed_dev = _ptr(step_counter(a.device)) if dropout_p > 0.0 else None
     d.w_batched, d.col_len = int(w_batched), _ptr(col_len)
     _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
     return out, aux, out_dot
@@ -263,7 +278,9 @@ def predictor_tail_bwd(d_out, pad_mask, r_h16, ln_w, ln_b, lin_w, eps: float, dr
     dlin_w, dlin_b, dln_w, dln_b = _zeros((Cc,), r_h16), _zeros((1,), r_h16), _zeros((Cc,), r_h16), _zeros((Cc,), r_h16)
     _lib.check(_lib.load().osb_predictor_tail_bwd(_ptr(_f32(d_out)), _ptr(pad_mask), _ptr(r_h16), _ptr(ln_w), _ptr(ln_b), _ptr(lin_w),
                                                   _ptr(g), _ptr(dlin_w), _ptr(dlin_b), _ptr(dln_w), _ptr(dln_b), rows, Cc, eps,
-                                                  float(dropout_p), int(dropout_seed), _stream()), "osb_predictor_tail_bwd")
+                                                  float(dropout_p), int(dropout_seed),
+                                                  _ptr(step_counter(r_h16.device)) if dropout_p > 0.0 else None, _stream()),
+               "osb_predictor_tail_bwd")
     return g, dlin_w, dlin_b, dln_w, dln_b
 
 

@@ -67,6 +67,11 @@ class FlatAdamW(torch.optim.Optimizer):
         self._buckets: Dict[int, _Bucket] = {}
         self._steps: Dict[int, int] = {}
         self.last_stats: Optional[torch.Tensor] = None
+        # CUDA-graph mode (model/graphed.py): lr and the bias corrections are read from `hyper_dev`, which the host refreshes
+        # with stage_hyper() before every replay; step() then has no per-step host value baked into its launches.
+        self.graph_mode = False
+        self.hyper_host: Optional[torch.Tensor] = None
+        self.hyper_dev: Optional[torch.Tensor] = None
 
     # -- bucket management -----------------------------------------------------------------------
     def _bucket_for(self, gi: int, group) -> Optional[_Bucket]:
@@ -111,10 +116,14 @@ class FlatAdamW(torch.optim.Optimizer):
                 continue
             if self.world_size > 1:
                 torch.distributed.all_reduce(b.flat_g, group=self.process_group)
-            step = self._steps.get(gi, 0) + 1
-            self._steps[gi] = step
             # the all-reduce SUMS the ranks' gradients; the 1/world factor is folded into the unscale factor
             inv_scale = 1.0 / (self.loss_scale * self.world_size)
+            if self.graph_mode:
+                self._kernel_step_dev(b, group, gi, max_norm, inv_scale)
+                self.last_stats = b.stats
+                continue  # step counters and weight epochs are advanced by stage_hyper(), once per replay
+            step = self._steps.get(gi, 0) + 1
+            self._steps[gi] = step
             self._kernel_step(b, group, step, max_norm, inv_scale)
             self.last_stats = b.stats
             for p in b.params:  # invalidate packed fp16 copies of these weights (model/packing.py)
@@ -130,6 +139,42 @@ class FlatAdamW(torch.optim.Optimizer):
         _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
                                       b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                                       float(group["weight_decay"]), step, max_norm, inv_scale, _stream()), "osb_adamw_step")
+
+    def _ensure_hyper(self, device) -> None:
+        if self.hyper_dev is None:
+            n = len(self.param_groups)
+            self.hyper_host = torch.zeros(n, 4, dtype=torch.float32).pin_memory()
+            self.hyper_dev = torch.zeros(n, 4, dtype=torch.float32, device=device)
+
+    def stage_hyper(self) -> None:
+        """Host side of one graph-mode step: advance the step counters, stage [lr, 1-b1^t, sqrt(1-b2^t)] of every group
+        for the captured osb_adamw_step_dev launches (async copy on the current stream) and invalidate packed weights."""
+        for gi, group in enumerate(self.param_groups):
+            b = self._buckets.get(gi)
+            if b is None:
+                continue
+            self._ensure_hyper(b.flat_p.device)
+            step = self._steps.get(gi, 0) + 1
+            self._steps[gi] = step
+            beta1, beta2 = group["betas"]
+            self.hyper_host[gi, 0] = float(group["lr"])
+            self.hyper_host[gi, 1] = 1.0 - beta1 ** step
+            self.hyper_host[gi, 2] = (1.0 - beta2 ** step) ** 0.5
+            for p in b.params:
+                p._osb_epoch = getattr(p, "_osb_epoch", 0) + 1
+        if self.hyper_dev is not None:
+            self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+
+    def _kernel_step_dev(self, b: _Bucket, group, gi: int, max_norm: float, inv_scale: float) -> None:
+        lib = _lib.load()
+        self._ensure_hyper(b.flat_p.device)
+        b.stats.zero_()
+        _lib.check(lib.osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
+        beta1, beta2 = group["betas"]
+        _lib.check(lib.osb_adamw_step_dev(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
+                                          b.stats.data_ptr(), self.hyper_dev[gi].data_ptr(), float(beta1), float(beta2),
+                                          float(group["eps"]), float(group["weight_decay"]), max_norm, inv_scale, _stream()),
+                   "osb_adamw_step_dev")
 
     def grad_norm(self) -> float:
         """Unscaled global gradient norm of the last step (reads a device scalar: call outside the hot loop)."""

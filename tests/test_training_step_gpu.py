@@ -82,3 +82,78 @@ def test_training_step_pretraining_and_gan_phase(cuda_device):
     assert torch.equal(dec_before, model.generator.decoder.convnext[0].pwconv1.weight.detach())
     g_opt, d_opt = model.optimizers()
     assert np.isfinite(g_opt.grad_norm()) and np.isfinite(d_opt.grad_norm())
+
+
+def _no_dropout(model):
+    """Switch every stochastic layer off so that eager and graphed runs are comparable step by step."""
+    from optispeech_b200.model.generator.modules.convnext import ConvNeXtBlock
+
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, ConvNeXtBlock):
+            mod.drop_path = torch.nn.Identity()
+
+
+def test_graphed_training_step_matches_eager(cuda_device):
+    """training_step with cuda_graph=True (3 eager warm-up steps, capture, replays) walks the same trajectory as the
+    eager step: parameters, Adam step counters, LR schedule and global_step all agree after 7 steps."""
+    from optispeech_b200.factory import build_model, model_config_from_spec
+
+    spec = ModelSpec()
+    models = []
+    for graphed in (False, True):
+        torch.manual_seed(99)
+        m = build_model(model_config_from_spec(spec), train_args=dict(pretraining_steps=1000))
+        m.generator.load_state_dict(deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0))
+        m = m.to(cuda_device).train()
+        _no_dropout(m)
+        m.cuda_graph = graphed
+        models.append(m)
+    batches = [_batch(spec, 2, 40, 170, seed=s) for s in (3, 4, 5)]
+    for i in range(7):
+        for m in models:
+            m.training_step(batches[i % 3], i)
+        le, lg = (float(m.logged["total_loss/generator"]) for m in models)
+        print(f"  step {i}: eager loss {le:.5f} graphed loss {lg:.5f}")
+        assert abs(le - lg) <= 2e-3 * max(1.0, abs(le)), i
+    eager, graphed = models
+    assert graphed._graphed is not None and graphed._graphed.replays == 4 and graphed._graphed.last_entry.launches > 50
+    assert eager.global_step == graphed.global_step == 7
+    oe, og = eager.optimizers()[0], graphed.optimizers()[0]
+    assert oe._steps == og._steps
+    assert oe.param_groups[0]["lr"] == og.param_groups[0]["lr"]
+    worst = 0.0
+    for (n, p), (_, q) in zip(eager.generator.named_parameters(), graphed.generator.named_parameters()):
+        worst = max(worst, float((p - q).abs().max()))
+    print("  max |param_eager - param_graphed| after 7 steps:", worst)
+    assert worst < 2e-4   # fp32 atomics in the weight-gradient kernels reorder sums; Adam normalises the scale away
+
+
+def test_graph_replay_draws_fresh_dropout_masks(cuda_device):
+    """The dropout seed of a captured launch is host seed + a device counter: bumping the counter inside the graph gives
+    a new mask on every replay, and the backward epilogue regenerates the same mask as the forward one."""
+    from optispeech_b200 import ops
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    B, T, N, p = 2, 64, 256, 0.4
+    a = torch.randn(B, T, N, generator=g).to(dev).half()
+    w = (torch.randn(1, N, N, generator=g) / N ** 0.5).to(dev).half()
+    ln_w, ln_b, bias = torch.ones(N, device=dev), torch.full((N,), 0.5, device=dev), torch.zeros(N, device=dev)
+    y_ref, _, _ = ops.gemm(a, w, epi=ops.EPI_RELU_LN, bias=bias, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-12)
+    y_out = torch.empty_like(y_ref)
+    ops.gemm(a, w, epi=ops.EPI_RELU_LN, bias=bias, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-12, dropout_p=p, dropout_seed=17, out=y_out)  # warm
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.step_counter(dev).add_(1)
+        ops.gemm(a, w, epi=ops.EPI_RELU_LN, bias=bias, ln_w=ln_w, ln_b=ln_b, ln_eps=1e-12, dropout_p=p, dropout_seed=17, out=y_out)
+    masks = []
+    for _ in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        masks.append((y_out.float().abs() > 0) | (y_ref.float().abs() < 1e-2))
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    for mk in masks:
+        assert abs(float(mk.float().mean()) - (1 - p)) < 0.05
