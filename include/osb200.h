@@ -299,6 +299,12 @@ int osb_grad_sumsq(const float* g, int64_t n, float* stats /*(2)*/, void* stream
 
 /* Fused: unscale by inv_scale, clip by global norm (max_norm <= 0 disables), decoupled-weight-decay Adam update with
  * bias correction for `step` (1-based).  Skipped entirely when stats[1] != 0 (non-finite gradient). */
+/* Multi-tensor gather of one step's gradients into the flat bucket (what torch's AccumulateGrad + a flatten would do in ~100
+ * launches).  table: device int64 [n_tensors][3] = {source pointer (0 = no gradient: zeros), destination offset in floats
+ * (multiple of 4), numel}; chunks: device int32 [n_chunks][2] = {tensor index, chunk index}, 2048 floats per chunk.
+ * stats (optional): stats[0] += sum of squares, stats[1] = 1 on a non-finite value — as osb_grad_sumsq. */
+int osb_grad_gather(const int64_t* table, const int32_t* chunks, int64_t n_chunks, float* flat_g, float* stats, void* stream);
+
 int osb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* stats, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int64_t step, float max_norm, float inv_scale, void* stream);
 

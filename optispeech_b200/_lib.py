@@ -120,6 +120,7 @@ def load() -> C.CDLL:
         "osb_stft_loss": [P, P, P, I32, I32, I32, I32, I32, F, P, P, P, P],
         "osb_mel_loss": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F, P, P, P, P],
         "osb_grad_sumsq": [P, I64, P, P],
+        "osb_grad_gather": [P, P, I64, P, P, P],
         "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
         "osb_adamw_step_dev": [P, P, P, P, I64, P, P, F, F, F, F, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],

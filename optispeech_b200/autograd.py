@@ -42,7 +42,7 @@ def pack_conv_bwd(w: torch.Tensor) -> torch.Tensor:
 
 def _conv_wgrad(g_h16: torch.Tensor, a_h16: torch.Tensor, N: int, Cin: int, k: int, pad: int) -> torch.Tensor:
     """-> Conv1d weight gradient in the parameter's (N, Cin, k) layout."""
-    dw = torch.zeros((k, N, Cin), device=g_h16.device, dtype=torch.float32)
+    dw = ops.zeros((k, N, Cin), g_h16)
     ops.gemm_wgrad(g_h16, a_h16, dw, taps=k, pad=pad, K=Cin)
     return dw.permute(1, 2, 0).contiguous()
 
@@ -58,6 +58,7 @@ class EmbedTextFn(Function):
         return ops.embed_text(ids, table, inv_freq, scale)
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         ids, inv_freq = ctx.saved_tensors
         dtable, dscale = ops.embed_text_bwd(dout.contiguous(), ids, inv_freq, ctx.n_vocab, ctx.padding_idx)
@@ -76,6 +77,7 @@ class LayerNormFn(Function):
         return out
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         x, w = ctx.saved_tensors
         dx, dw, db = ops.layernorm_bwd(dout.contiguous(), x, w, ctx.eps)
@@ -103,6 +105,7 @@ class ConvNeXtBlockFn(Function):
         return out
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale = ctx.saved_tensors
         B, T, C = x.shape
@@ -111,12 +114,12 @@ class ConvNeXtBlockFn(Function):
         dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
         # pwconv2: dgrad (with the GELU derivative fused) and wgrad
         dpre, _, _ = ops.gemm(dyg, pack_kn(w2), epi=ops.EPI_GELU_BWD, aux_in=pre)
-        dw2 = torch.zeros((1, C, I), device=x.device, dtype=torch.float32)
+        dw2 = ops.zeros((1, C, I), x)
         ops.gemm_wgrad(dyg, h, dw2)
         db1 = ops.colsum_h16(dpre)
         # pwconv1: dgrad (LayerNorm backward fused: the CTA owns whole rows) and wgrad
         dd, _, _ = ops.gemm(dpre, pack_kn(w1f), epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd)
-        dw1f = torch.zeros((1, I, C), device=x.device, dtype=torch.float32)
+        dw1f = ops.zeros((1, I, C), x)
         ops.gemm_wgrad(dpre, xhat, dw1f)
         dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, ln_b, db1)
         dx, ddw, ddb = ops.dwconv_bwd(dd, dout, x, dw_w.view(C, 7), pad_mask)
@@ -155,6 +158,7 @@ class VariancePredictorFn(Function):
         return out
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, d_out):
         L, k, eps = ctx.L, ctx.k, ctx.eps
         saved = ctx.saved_tensors
@@ -214,6 +218,7 @@ class ConvStackFn(Function):
         return out
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         L = ctx.L
         saved = ctx.saved_tensors
@@ -249,6 +254,7 @@ class VarianceEmbedFn(Function):
         return out
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         val, pad_mask, emb_scale = ctx.saved_tensors
         dx, dw, db = ops.variance_embed_bwd(dout.contiguous(), val, pad_mask, ctx.k, want_dx=ctx.x_needs_grad, emb_scale=emb_scale)
@@ -270,6 +276,7 @@ class WaveNeXtHeadFn(Function):
         return out.view(out.shape[0], -1)
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dout):
         a, out, w1, b1, w2, wc = ctx.saved_tensors
         B, T, hop = out.shape
@@ -277,7 +284,7 @@ class WaveNeXtHeadFn(Function):
         g32 = (dout.reshape(B, T, hop) * ((out > -1.0) & (out < 1.0))).contiguous()
         g = ops.to_h16(g32)
         dx, _, _ = ops.gemm(g, pack_kn(wc), epi=ops.EPI_BIAS)
-        dwc = torch.zeros((1, hop, a.shape[-1]), device=a.device, dtype=torch.float32)
+        dwc = ops.zeros((1, hop, a.shape[-1]), a)
         ops.gemm_wgrad(g, a, dwc)
         dwc = dwc[0]
         dbc = ops.colsum_h16(g)
@@ -312,6 +319,7 @@ class AttnLogProbFn(Function):
         return lp
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, G):
         fe, te, lp, lse, prior, x_len, m_len, f16 = ctx.saved_tensors
         B, Tm, C = fe.shape
@@ -338,6 +346,7 @@ class ForwardSumLossFn(Function):
         return per_sample.sum() / log_p_attn.shape[0]
 
     @staticmethod
+    @ops.pooled
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
         return grad * dloss, None, None, None

@@ -36,6 +36,66 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   }
 }
 
+// Multi-tensor gather: the step's gradient tensors (wherever autograd allocated them) -> the flat bucket, with the global
+// sum of squares and the non-finite flag accumulated on the way (stats may be null under data parallelism, where the norm is
+// taken after the all-reduce).  tab = [src pointer, destination offset, numel] per tensor; chunks = (tensor, chunk index),
+// GATHER_CHUNK floats each; a null source (no gradient this step) writes zeros.
+constexpr int GATHER_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+grad_gather_kernel(const long long* __restrict__ tab, const int2* __restrict__ chunks, long long n_chunks, float* __restrict__ flat,
+                   float* __restrict__ stats) {
+  float acc = 0.f;
+  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int2 ch = chunks[c];
+    const float* src = reinterpret_cast<const float*>(tab[3 * ch.x]);
+    const long long start = static_cast<long long>(ch.y) * GATHER_CHUNK;
+    const long long n = tab[3 * ch.x + 2];
+    const int len = static_cast<int>(n - start < GATHER_CHUNK ? n - start : GATHER_CHUNK);
+    float* dst = flat + tab[3 * ch.x + 1] + start;
+    if (src == nullptr) {
+      for (int i = threadIdx.x; i < len; i += 256) dst[i] = 0.f;
+      continue;
+    }
+    src += start;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {  // dst is 16-byte aligned by construction (offsets and chunks are multiples of 4)
+      const int len4 = len >> 2;
+      for (int i = threadIdx.x; i < len4; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        reinterpret_cast<float4*>(dst)[i] = v;
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+      for (int i = (len4 << 2) + threadIdx.x; i < len; i += 256) {
+        const float v = src[i];
+        dst[i] = v;
+        acc += v * v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < len; i += 256) {
+        const float v = src[i];
+        dst[i] = v;
+        acc += v * v;
+      }
+    }
+  }
+  if (stats == nullptr) return;
+  const bool bad = !isfinite(acc);
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  __shared__ int sbad;
+  if (threadIdx.x == 0) sbad = 0;
+  __syncthreads();
+  if (bad) sbad = 1;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(stats, s);
+    if (sbad || !isfinite(s)) stats[1] = 1.f;
+  }
+}
+
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, max_norm, inv_scale;
   const float* hyper;  // optional device [lr, bc1, bc2_sqrt] overriding the by-value fields (CUDA-graph replay)
@@ -84,6 +144,17 @@ extern "C" int osb_grad_sumsq(const float* g, int64_t n, float* stats, void* str
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, stats);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_grad_gather(const int64_t* table, const int32_t* chunks, int64_t n_chunks, float* flat_g, float* stats, void* stream) {
+  OSB_REQUIRE(table && chunks && flat_g, OSB_ERR_ARG);
+  OSB_REQUIRE(n_chunks > 0, OSB_ERR_SHAPE);
+  OSB_REQUIRE((reinterpret_cast<uintptr_t>(flat_g) & 15) == 0 && (reinterpret_cast<uintptr_t>(chunks) & 7) == 0, OSB_ERR_ALIGN);
+  long long blocks = n_chunks < 148 * 8 ? n_chunks : 148 * 8;
+  grad_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(table), reinterpret_cast<const int2*>(chunks), n_chunks, flat_g, stats);
   count_launch();
   return launch_status();
 }

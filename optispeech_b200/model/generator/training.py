@@ -154,6 +154,13 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
 
     log_p_attn = gen.alignment_module(text=h, feats=mel.transpose(1, 2), text_lengths=x_lengths, feats_lengths=mel_lengths,
                                       x_masks=in_pad)
+    # The forward-sum loss only meets the rest of the step at the final sum: its sequential recursion (one CTA per sample)
+    # runs on a side stream, next to the alignment search, the predictors and the decoder.
+    fs_side = ops.side_stream(dev) if log_p_attn.is_cuda else None
+    if fs_side is not None:
+        fs_side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(fs_side):
+            fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
     durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
     duration_hat = gen.duration_predictor(h.detach(), in_pad)
 
@@ -187,7 +194,10 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
             wav_hat = gen.vocoder.forward_train(segment)
 
     d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
-    fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
+    if fs_side is not None:
+        torch.cuda.current_stream().wait_stream(fs_side)
+    else:
+        fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
     align_loss = fs_loss + bin_loss
     lc = gen.loss_coeffs
     loss = align_loss * lc.lambda_align + d_loss * lc.lambda_duration + p_loss * lc.lambda_pitch + e_loss * lc.lambda_energy

@@ -37,6 +37,20 @@ def step_counter(device) -> torch.Tensor:
     return t
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device, slot: int = 0) -> "torch.cuda.Stream":
+    """A cached auxiliary stream per device: long single-wave kernels (the forward-sum recursion: 32 CTAs for 0.4 ms) run
+    there concurrently with the main stream's work.  Callers fork with wait_stream(current) and join before using results."""
+    key = (torch.device(device).index or 0, slot)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = s
+    return s
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -222,8 +236,57 @@ def to_h16(x: torch.Tensor, pad_to: Optional[int] = None, split: bool = False) -
 # ------------------------------------------------------------------------------------------------
 # backward kernels
 # ------------------------------------------------------------------------------------------------
-def _zeros(shape, like):
+class _ZeroPool:
+    """Zero-initialised fp32 scratch for one backward call: the many small accumulators the backward kernels add into
+    (bias / LayerNorm / weight gradients) are carved from one pre-zeroed block instead of one fill launch each."""
+
+    def __init__(self, device, block: int):
+        self.device, self.block = device, block
+        self.buf, self.pos = None, 0
+
+    def take(self, shape):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        n4 = (n + 3) // 4 * 4  # 16-byte aligned carve-outs
+        if self.buf is None or self.pos + n4 > self.buf.numel():
+            self.buf = torch.zeros(max(n4, self.block), device=self.device, dtype=torch.float32)
+            self.pos = 0
+        out = self.buf[self.pos:self.pos + n].view(shape)
+        self.pos += n4
+        return out
+
+
+_POOL: Optional[_ZeroPool] = None
+
+
+def pooled(fn):
+    """Decorator for autograd backward functions: zeros() inside the call share pre-zeroed blocks."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *grads):
+        global _POOL
+        dev = next((g.device for g in grads if g is not None), None)
+        if dev is None or dev.type != "cuda":
+            return fn(ctx, *grads)
+        prev, _POOL = _POOL, _ZeroPool(dev, 1 << 20)
+        try:
+            return fn(ctx, *grads)
+        finally:
+            _POOL = prev
+
+    return wrapper
+
+
+def zeros(shape, like):
+    shape = tuple(shape) if not isinstance(shape, int) else (shape,)
+    if _POOL is not None and _POOL.device == like.device:
+        return _POOL.take(shape)
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+_zeros = zeros
 
 
 def resid_bwd_prep(dout, z_h16, gamma, pad_mask, row_scale, T: int):

@@ -2,9 +2,10 @@
 
 `FlatAdamW` is a torch.optim.Optimizer (so `transformers.get_cosine_schedule_with_warmup` and any LR scheduler
 work on it unchanged) whose step is two kernel launches over ONE contiguous fp32 bucket per parameter group:
-osb_grad_sumsq (global norm + non-finite detection) and osb_adamw_step (unscale by the static loss scale, clip
-by global norm, decoupled-weight-decay Adam).  Under data parallelism the same bucket is what gets all-reduced
-(one NCCL call per optimizer per step).
+osb_grad_gather (multi-tensor copy of the step's gradients into the bucket, fused with the global norm and
+non-finite detection) and osb_adamw_step (unscale by the static loss scale, clip by global norm,
+decoupled-weight-decay Adam).  Under data parallelism the bucket is what gets all-reduced (one NCCL call per
+optimizer per step; the norm is then taken after the all-reduce by osb_grad_sumsq).
 
 Bucket membership is static per training phase: parameters that never receive a gradient (the decoder and the
 energy embedding at reference commit 3bdde20 — generator/__init__.py:161 feeds the vocoder `segment.detach()`)
@@ -22,6 +23,9 @@ from . import _lib
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+GATHER_CHUNK = 2048  # floats per work item of osb_grad_gather (csrc/osb_optim.cu)
 
 
 class _Bucket:
@@ -45,14 +49,52 @@ class _Bucket:
             for p, o in zip(params, offs):
                 n = p.numel()
                 self.flat_p[o:o + n].copy_(p.detach().reshape(-1))
-                if p.grad is not None:
-                    self.flat_g[o:o + n].copy_(p.grad.detach().reshape(-1))
                 p.data = self.flat_p[o:o + n].view(p.shape)
-                p.grad = self.flat_g[o:o + n].view(p.shape)
+        # work list of the gather kernel: (tensor, chunk) pairs; depends on the sizes only
+        chunks = [(t, c) for t, p in enumerate(params) for c in range((p.numel() + GATHER_CHUNK - 1) // GATHER_CHUNK)]
+        self.n_chunks = len(chunks)
+        self.chunks_dev = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        # pointer tables [src, dst offset, numel]: a ring of pinned host buffers for eager steps (each guarded by the event of
+        # its last upload), and one dedicated, never rewritten (host, device) pair per captured CUDA graph
+        self._ring = []
+        self._ring_pos = 0
+        self._graph_tables = []
 
     def view_of(self, flat: torch.Tensor, p: torch.nn.Parameter) -> torch.Tensor:
         o = self.offset_of[id(p)]
         return flat[o:o + p.numel()].view(p.shape)
+
+    def _fill_table(self, host: torch.Tensor) -> None:
+        rows = []
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                g = g.float().contiguous()
+                p.grad = g
+            rows.append((g.data_ptr() if g is not None else 0, o, p.numel()))
+        host.copy_(torch.tensor(rows, dtype=torch.int64))
+
+    def stage_table(self, for_graph: bool) -> torch.Tensor:
+        """Upload this step's gradient pointers; returns the device table the gather launch reads."""
+        dev = self.flat_p.device
+        n = len(self.params)
+        if for_graph:
+            host = torch.empty((n, 3), dtype=torch.int64).pin_memory()
+            table = torch.empty((n, 3), dtype=torch.int64, device=dev)
+            self._fill_table(host)
+            table.copy_(host, non_blocking=True)   # captured as a memcpy node: re-reads `host`, which is never rewritten
+            self._graph_tables.append((host, table))
+            return table
+        if len(self._ring) < 4:
+            self._ring.append((torch.empty((n, 3), dtype=torch.int64).pin_memory(),
+                               torch.empty((n, 3), dtype=torch.int64, device=dev), torch.cuda.Event()))
+        host, table, done = self._ring[self._ring_pos % len(self._ring)]
+        self._ring_pos += 1
+        done.synchronize()                          # the upload that last read this host buffer has finished
+        self._fill_table(host)
+        table.copy_(host, non_blocking=True)
+        done.record()
+        return table
 
 
 class FlatAdamW(torch.optim.Optimizer):
@@ -98,14 +140,12 @@ class FlatAdamW(torch.optim.Optimizer):
     def buckets(self) -> List[_Bucket]:
         return list(self._buckets.values())
 
-    def zero_grad(self, set_to_none: bool = False):
-        for gi, group in enumerate(self.param_groups):
-            b = self._buckets.get(gi)
-            if b is not None:
-                b.flat_g.zero_()
+    def zero_grad(self, set_to_none: bool = True):
+        """Gradients are dropped, not zero-filled: autograd then hands each parameter its gradient tensor as is (no
+        accumulate kernel per parameter), and step() gathers them into the flat bucket in one launch."""
+        for group in self.param_groups:
             for p in group["params"]:
-                if b is None or id(p) not in b.ids:
-                    p.grad = None
+                p.grad = None
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm: Optional[float] = None):
@@ -114,8 +154,11 @@ class FlatAdamW(torch.optim.Optimizer):
             b = self._bucket_for(gi, group)
             if b is None:
                 continue
+            b.stats.zero_()
+            self._gather_grads(b, fused_norm=self.world_size == 1)
             if self.world_size > 1:
                 torch.distributed.all_reduce(b.flat_g, group=self.process_group)
+                self._grad_norm(b)
             # the all-reduce SUMS the ranks' gradients; the 1/world factor is folded into the unscale factor
             inv_scale = 1.0 / (self.loss_scale * self.world_size)
             if self.graph_mode:
@@ -130,11 +173,19 @@ class FlatAdamW(torch.optim.Optimizer):
                 p._osb_epoch = getattr(p, "_osb_epoch", 0) + 1
         return None
 
-    def _kernel_step(self, b: _Bucket, group, step: int, max_norm: float, inv_scale: float) -> None:
-        """Two launches over the flat bucket: global norm (+ non-finite flag), then unscale + clip + AdamW."""
+    def _gather_grads(self, b: _Bucket, fused_norm: bool) -> None:
+        """One launch: every member's .grad -> b.flat_g (+ sum of squares / non-finite flag into b.stats when fused_norm)."""
         lib = _lib.load()
-        b.stats.zero_()
-        _lib.check(lib.osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
+        table = b.stage_table(for_graph=self.graph_mode and torch.cuda.is_current_stream_capturing())
+        _lib.check(lib.osb_grad_gather(table.data_ptr(), b.chunks_dev.data_ptr(), b.n_chunks, b.flat_g.data_ptr(),
+                                       b.stats.data_ptr() if fused_norm else None, _stream()), "osb_grad_gather")
+
+    def _grad_norm(self, b: _Bucket) -> None:
+        _lib.check(_lib.load().osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
+
+    def _kernel_step(self, b: _Bucket, group, step: int, max_norm: float, inv_scale: float) -> None:
+        """Unscale + clip by the global norm (b.stats) + AdamW over the flat bucket."""
+        lib = _lib.load()
         beta1, beta2 = group["betas"]
         _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
                                       b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
@@ -168,8 +219,6 @@ class FlatAdamW(torch.optim.Optimizer):
     def _kernel_step_dev(self, b: _Bucket, group, gi: int, max_norm: float, inv_scale: float) -> None:
         lib = _lib.load()
         self._ensure_hyper(b.flat_p.device)
-        b.stats.zero_()
-        _lib.check(lib.osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
         beta1, beta2 = group["betas"]
         _lib.check(lib.osb_adamw_step_dev(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
                                           b.stats.data_ptr(), self.hyper_dev[gi].data_ptr(), float(beta1), float(beta2),

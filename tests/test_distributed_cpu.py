@@ -1,9 +1,9 @@
 """Data-parallel plumbing with world_size 2 on the gloo backend (CPU): one flat gradient bucket per optimizer is
 all-reduced, and every rank ends up with the parameters a single process would get from the mean gradient.
 
-The CUDA update kernels cannot run here; the test substitutes a torch restatement of the two launches
-(`_kernel_step`) — test infrastructure only — so that bucket construction, static membership, the all-reduce and the
-1/world scaling are exercised exactly as on the GPU."""
+The CUDA kernels cannot run here; the test substitutes torch restatements of the three launches (`_gather_grads`,
+`_grad_norm`, `_kernel_step`) — test infrastructure only — so that bucket construction, static membership, the
+all-reduce and the 1/world scaling are exercised exactly as on the GPU."""
 import os
 
 import pytest
@@ -23,7 +23,17 @@ def _torch_kernel_step(self, b, group, step, max_norm, inv_scale):
     b.v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     b.flat_p.addcdiv_(b.m, (b.v.sqrt() / bc2 ** 0.5).add_(group["eps"]), value=-group["lr"] / bc1)
-    b.stats[0] = (b.flat_g ** 2).sum()
+
+
+def _torch_gather(self, b, fused_norm):
+    for p in b.params:
+        b.view_of(b.flat_g, p).copy_(p.grad if p.grad is not None else torch.zeros_like(p))
+    if fused_norm:
+        b.stats[0] += (b.flat_g ** 2).sum()
+
+
+def _torch_grad_norm(self, b):
+    b.stats[0] += (b.flat_g ** 2).sum()
 
 
 def _worker(rank, world, port, out_dir):
@@ -32,6 +42,8 @@ def _worker(rank, world, port, out_dir):
     from optispeech_b200.optim import FlatAdamW
 
     FlatAdamW._kernel_step = _torch_kernel_step
+    FlatAdamW._gather_grads = _torch_gather
+    FlatAdamW._grad_norm = _torch_grad_norm
     torch.manual_seed(0)
     params = [torch.nn.Parameter(torch.randn(17, 5)), torch.nn.Parameter(torch.randn(33)), torch.nn.Parameter(torch.randn(4, 4))]
     frozen = torch.nn.Parameter(torch.randn(6))  # never receives a gradient on any rank: static membership excludes it

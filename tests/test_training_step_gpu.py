@@ -48,6 +48,8 @@ def test_flat_adamw_matches_torch_adamw(cuda_device):
     # non-finite gradient: the step is skipped
     before = [p.detach().clone() for p in a]
     oa.zero_grad()
+    for p in a:
+        p.grad = torch.ones_like(p)
     a[0].grad.fill_(float("inf"))
     oa.step()
     for p, q in zip(a, before):
