@@ -138,7 +138,8 @@ int osb_gemm(const osb_gemm_desc* desc, void* stream);
 /* Weight-gradient contraction (split over rows, fp32 atomic accumulation into dw):
  *     dw[tap, n, k] += sum_{b,t} dy[b, t, n] * a[b, t + tap - pad, k]
  * dy: fp16 (B, T, ldy) ; a: fp16 (B, T, lda) ; dw: fp32 (taps, N, K) (must be zeroed or hold the
- * running accumulation).  Both operands are consumed MN-major straight from their
+ * running accumulation; 16-byte aligned, K a multiple of 4: the tile is flushed with vector reds,
+ * a warp per 512-byte row segment).  Both operands are consumed MN-major straight from their
  * channels-last layout (no transposes in HBM).
  * Replaces autograd's Conv1d/Linear weight gradient for the layers listed above. */
 int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,

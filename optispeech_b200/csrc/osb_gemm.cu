@@ -161,36 +161,61 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
     const int nvalid = static_cast<int>(p.col_len[b]) < ncols ? static_cast<int>(p.col_len[b]) : ncols;
     const float nf = valid ? p.row_stat[row] : 0.f;
     const float* ne = p.bias + static_cast<long long>(b) * ncols;
-    float mx = -INFINITY;
+    // pass 1: score = -distance, parked back in TMEM; running max / sum of exp (online softmax: one pass for both)
+    float mx = -INFINITY, sum = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
+      float cm = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int n = c0 + i;
-        if (n < nvalid) mx = fmaxf(mx, -sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)));
+        v[i] = n < nvalid ? -sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) : -INFINITY;
+        cm = fmaxf(cm, v[i]);
       }
-    }
-    float sum = 0.f;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      ld_chunk(taddr, c0, v);
+      if (cm > mx) {
+        sum *= __expf(mx - cm);  // exp(-inf) = 0 on the first chunk
+        mx = cm;
+      }
+      float cs = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int n = c0 + i;
-        if (n < nvalid) sum += expf(-sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) - mx);
-      }
+      for (int i = 0; i < 32; ++i) cs += v[i] > -INFINITY ? __expf(v[i] - mx) : 0.f;  // also keeps an all-masked row NaN-free
+      sum += cs;
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+      tmem_st_32x32(taddr + static_cast<uint32_t>(c0), r);
     }
+    tmem_st_wait();
     const float lse = mx + logf(sum);
     if (valid && p.out_dot != nullptr) p.out_dot[row] = lse;
+    // pass 2: log-probability + prior; 16-byte accesses when the row pitch allows (one thread = one row of the output)
+    const bool vec = (p.ldo & 3) == 0;
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (c0 >= ncols) break;
       ld_chunk(taddr, c0, v);
       if (valid) {
         float* orow = static_cast<float*>(p.out) + row * p.ldo;
         const float* prow = p.resid + row * p.ldo;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; i += 4) {
           const int n = c0 + i;
-          if (n < ncols)
-            orow[n] = n < nvalid ? (-sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) - lse) + prow[n] : -INFINITY;
+          if (vec && n + 3 < ncols) {
+            const float4 pr = *reinterpret_cast<const float4*>(prow + n);
+            float4 o;
+            o.x = (v[i] - lse) + pr.x;       // masked columns hold -inf already
+            o.y = (v[i + 1] - lse) + pr.y;
+            o.z = (v[i + 2] - lse) + pr.z;
+            o.w = (v[i + 3] - lse) + pr.w;
+            if (n >= nvalid) o.x = -INFINITY;
+            if (n + 1 >= nvalid) o.y = -INFINITY;
+            if (n + 2 >= nvalid) o.z = -INFINITY;
+            if (n + 3 >= nvalid) o.w = -INFINITY;
+            *reinterpret_cast<float4*>(orow + n) = o;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < ncols) orow[n + u] = n + u < nvalid ? (v[i + u] - lse) + prow[n + u] : -INFINITY;
+          }
         }
       }
     }
@@ -625,15 +650,28 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after_sync();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int n = n0 + q * 32 + lane;
+    // TMEM hands every thread one output row; the reduction into dw wants a warp on one row (512 contiguous bytes per
+    // vector red instead of 32 scattered 4-byte atomics).  Transpose the warp's 32 x 128 slab through the (now idle) pipeline
+    // stages: row stride 132 floats keeps both the float4 row writes and the float4 row reads conflict-free.
+    constexpr int LD = WG_TILE + 4;
+    float* slab = reinterpret_cast<float*>(smem) + q * 32 * LD;
     float v[32];
     for (int c0 = 0; c0 < WG_TILE; c0 += 32) {
       ld_chunk(taddr, c0, v);
-      if (n < p.N) {
-        float* dst = p.dw + (static_cast<long long>(zsel) * p.N + n) * p.K + k0 + c0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + c0 + i < p.K) atomicAdd(dst + i, v[i]);
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(slab + lane * LD + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    __syncwarp();
+    const int kc = k0 + lane * 4;
+    if (kc < p.K) {  // K is a multiple of 8: whole float4 groups are in or out
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const int n = n0 + q * 32 + r;
+        if (n >= p.N) break;
+        const float4 x = *reinterpret_cast<const float4*>(slab + r * LD + lane * 4);
+        float* dst = p.dw + (static_cast<long long>(zsel) * p.N + n) * p.K + kc;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
       }
     }
   }
@@ -869,6 +907,8 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
   OSB_REQUIRE(dy != nullptr && a != nullptr && dw != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0 && taps > 0, OSB_ERR_SHAPE);
   OSB_REQUIRE(ldy % 8 == 0 && lda % 8 == 0, OSB_ERR_ALIGN);
+  // the tile is reduced into dw with 16-byte vector reds
+  OSB_REQUIRE(K % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0, OSB_ERR_ALIGN);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUtensorMap tmDy, tmA;
   int rc = make_tmap_3d(&tmDy, dy, TMA_F16, N, T, B, ldy, static_cast<uint64_t>(T) * ldy, 64, WG_ROWS);
