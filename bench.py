@@ -248,7 +248,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             print(json.dumps({"metric": "mel_frames_per_sec_train_step", "value": frames_all / (ms * 1e-3), "unit": "mel-frames/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                               "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
-                              "note": "--quick run (possibly under a profiler): not a bench value"}))
+                              "note": "--quick run (possibly under a profiler): not a bench value"}), flush=True)
+        if model._graphed is not None:
+            model._graphed.release()
         return
     for i in range(2):
         step_e2e(i)
@@ -256,11 +258,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     # ---- per-kernel device times of one step (separate pass; event recording perturbs the step time) ----
     roofline, top = None, []
+    was_graphed, model.cuda_graph = model.cuda_graph, False  # per-launch events need the eager launches
     if rank == 0:
-        was_graphed, model.cuda_graph = model.cuda_graph, False  # per-launch events need the eager launches
         with _lib.LaunchProfiler() as prof:
             step_resident(0)
-        model.cuda_graph = was_graphed
+    else:
+        step_resident(0)  # the step holds a gradient all-reduce: every rank has to take it
+    model.cuda_graph = was_graphed
+    if rank == 0:
         summ = prof.summary()
         total_ms = sum(a["total_ms"] for a in summ) or 1.0
         top = [{"kernel": a["key"], "launches": a["launches"], "total_ms": round(a["total_ms"], 4), "share_of_lib_time": round(a["total_ms"] / total_ms, 4),
@@ -342,7 +347,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "top_kernels": top,
             "synthesis": synth,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if model._graphed is not None:  # every rank: graphs go before the process group does
+        model._graphed.release()
 
 
 def main():
@@ -369,7 +376,17 @@ def main():
         run_ours(args, rank, local_rank, world)
     finally:
         if world > 1:
+            # The captured step holds NCCL kernels: its graphs must be gone before the communicator is torn down, and a
+            # teardown that still blocks must not hold the launcher (the line is already printed): bounded by a watchdog.
+            import gc
+            import threading
+
+            gc.collect()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            threading.Timer(30.0, lambda: os._exit(0)).start()
             torch.distributed.destroy_process_group()
+            os._exit(0)
 
 
 if __name__ == "__main__":

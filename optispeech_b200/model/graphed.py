@@ -79,6 +79,16 @@ class GraphedTrainingStep:
         self._replay(entry, batch)
         return None
 
+    def release(self) -> None:
+        """Drop every captured graph (and its private memory pool).  Call before tearing down a process group whose
+        collectives were captured."""
+        for e in self._entries.values():
+            e.graph = None
+            e.keepalive = []
+            e.static = {}
+        self._entries.clear()
+        self.last_entry = None
+
     # ------------------------------------------------------------------------------------------------
     def _optimizers(self, train_discriminator: bool):
         opt_g, opt_d = self.module.optimizers()
