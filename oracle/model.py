@@ -75,6 +75,60 @@ def convnext_backbone(sd: SD, prefix: str, x: torch.Tensor, padding_mask: Option
 
 
 # ----------------------------------------------------------------------------------------------
+# Transformer backbone  (generator/modules/transformer.py:9-27; _transformer/encoder.py:271-313,
+# encoder_layer.py:60-116, attention.py:38-125, multi_layer_conv.py:52-62, embedding.py:57-124, layer_norm.py:11-36)
+# ----------------------------------------------------------------------------------------------
+def positional_encoding_table(T: int, d_model: int) -> torch.Tensor:
+    """embedding.py:57-73: pe[t, 2i] = sin(t * w_i), pe[t, 2i+1] = cos(t * w_i), w_i = exp(-2i ln(10000) / d)."""
+    position = torch.arange(0, T, dtype=torch.float32).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+    pe = torch.zeros(T, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def multi_head_attention(sd: SD, prefix: str, x: torch.Tensor, key_valid: torch.Tensor, heads: int) -> torch.Tensor:
+    """Self-attention of attention.py:107-125: softmax(masked_fill(QK^T / sqrt(d_k), finfo.min)).masked_fill(0) V, then
+    linear_out.  key_valid (B, T) True = real key; only KEYS are masked (query rows at pads are computed like any other)."""
+    B, T, D = x.shape
+    dk = D // heads
+    lin = lambda n, v: F.linear(v, sd[f"{prefix}.{n}.weight"], sd[f"{prefix}.{n}.bias"])  # noqa: E731
+    q = lin("linear_q", x).view(B, T, heads, dk).transpose(1, 2)
+    k = lin("linear_k", x).view(B, T, heads, dk).transpose(1, 2)
+    v = lin("linear_v", x).view(B, T, heads, dk).transpose(1, 2)
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+    masked = ~key_valid[:, None, None, :]
+    scores = scores.masked_fill(masked, torch.finfo(scores.dtype).min)
+    attn = torch.softmax(scores, dim=-1).masked_fill(masked, 0.0)
+    ctx = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, T, D)
+    return lin("linear_out", ctx)
+
+
+def transformer_backbone(sd: SD, prefix: str, x: torch.Tensor, padding_mask: torch.Tensor, blocks: int, heads: int) -> torch.Tensor:
+    """x (B,T,C), padding_mask (B,T) True = pad.  Eval mode (all dropouts are identity): x + alpha * pe, then `blocks`
+    pre-LN layers  x += MHA(LN(x));  x += w_2(relu(w_1(LN(x))))  (k=1 Conv1d = Linear), then after_norm.  LN eps 1e-12."""
+    t = f"{prefix}.transformer"
+    B, T, C = x.shape
+    x = x + sd[f"{t}.embed.0.alpha"] * positional_encoding_table(T, C)[None]
+    valid = ~padding_mask
+    ln = lambda v, n: F.layer_norm(v, (C,), sd[f"{n}.weight"], sd[f"{n}.bias"], 1e-12)  # noqa: E731
+    for i in range(blocks):
+        p = f"{t}.encoders.{i}"
+        x = x + multi_head_attention(sd, f"{p}.self_attn", ln(x, f"{p}.norm1"), valid, heads)
+        h = F.relu(F.linear(ln(x, f"{p}.norm2"), sd[f"{p}.feed_forward.w_1.weight"][:, :, 0], sd[f"{p}.feed_forward.w_1.bias"]))
+        x = x + F.linear(h, sd[f"{p}.feed_forward.w_2.weight"][:, :, 0], sd[f"{p}.feed_forward.w_2.bias"])
+    return ln(x, f"{t}.after_norm")
+
+
+def backbone(sd: SD, spec: ModelSpec, prefix: str, x: torch.Tensor, padding_mask: torch.Tensor, layers: int) -> torch.Tensor:
+    """encoder / decoder dispatch on spec.backbone (configs/model/optispeech.yaml vs configs/model/transformer.yaml)."""
+    if spec.backbone == "transformer":
+        return transformer_backbone(sd, prefix, x, padding_mask, spec.tf_blocks, spec.tf_heads)
+    return convnext_backbone(sd, prefix, x, padding_mask, layers)
+
+
+# ----------------------------------------------------------------------------------------------
 # variance predictors  (generator/modules/core.py:34-180, layers.py:26-45)
 # ----------------------------------------------------------------------------------------------
 def variance_predictor(sd: SD, prefix: str, x: torch.Tensor, padding_mask: torch.Tensor, ps: PredictorSpec):
@@ -340,7 +394,7 @@ def synthesise(sd: SD, spec: ModelSpec, x, x_lengths, d_factor=1.0, p_factor=1.0
     x_mask = sequence_mask(x_lengths, int(x_lengths.max()))
     pad = ~x_mask
     h, _ = text_embedding(sd, x, spec)
-    h = convnext_backbone(sd, "encoder", h, pad, spec.enc_layers)
+    h = backbone(sd, spec, "encoder", h, pad, spec.enc_layers)
     d_pred, log_d = duration_infer(sd, h, pad, spec.duration, d_factor)
     if durations is None:
         durations = d_pred
@@ -351,7 +405,7 @@ def synthesise(sd: SD, spec: ModelSpec, x, x_lengths, d_factor=1.0, p_factor=1.0
     y_lengths = durations.sum(dim=1)
     y_mask = sequence_mask(y_lengths, int(y_lengths.max()))
     y = gaussian_upsampling(h, durations, y_mask, x_mask)
-    y = convnext_backbone(sd, "decoder", y, ~y_mask, spec.dec_layers)
+    y = backbone(sd, spec, "decoder", y, ~y_mask, spec.dec_layers)
     f0_cond, _ = expand_by_duration(pitch.unsqueeze(-1), durations)
     wav = wavenext(sd, y, ~y_mask, spec)
     return dict(wav=wav, wav_lengths=y_lengths * spec.hop_length, durations=durations, pitch=pitch, energy=energy,
@@ -367,7 +421,7 @@ def generator_forward(sd: SD, spec: ModelSpec, x, x_lengths, mel, mel_lengths, p
     mel_mask = sequence_mask(mel_lengths, int(mel_lengths.max()))
     in_pad, tgt_pad = ~x_mask, ~mel_mask
     h, _ = text_embedding(sd, x, spec)
-    h = convnext_backbone(sd, "encoder", h, in_pad, spec.enc_layers)
+    h = backbone(sd, spec, "encoder", h, in_pad, spec.enc_layers)
     log_p_attn = alignment_log_p_attn(sd, h, mel.transpose(1, 2), x_lengths, mel_lengths, in_pad)
     durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
     duration_hat = variance_predictor(sd, "duration_predictor", h.detach(), in_pad, spec.duration)
@@ -378,7 +432,7 @@ def generator_forward(sd: SD, spec: ModelSpec, x, x_lengths, mel, mel_lengths, p
     energy_hat = variance_predictor(sd, "energy_predictor.predictor", h, in_pad, spec.energy)
     h = variance_embed(sd, "energy_predictor", h, in_pad, e_avg, spec.energy)
     y = gaussian_upsampling(h, durations, mel_mask, x_mask)
-    y = convnext_backbone(sd, "decoder", y, tgt_pad, spec.dec_layers)
+    y = backbone(sd, spec, "decoder", y, tgt_pad, spec.dec_layers)
     segment_size = min(spec.segment_size, y.shape[1])
     start_idx = segment_starts((mel_lengths - 4).to(y.dtype), segment_size, seg_rand)
     segment = get_segments(y, start_idx, segment_size)

@@ -59,6 +59,12 @@ class ModelSpec:
     lambda_mr_stft: float = 2.5
     num_speakers: int = 1
     num_languages: int = 1
+    # encoder/decoder backbone: "convnext" (configs/model/optispeech.yaml) or "transformer" (configs/model/transformer.yaml:
+    # attention_heads 2, linear_units 1024, num_blocks 4, pre-LN, conv1d k=1 position-wise layers, scaled positional encoding)
+    backbone: str = "convnext"
+    tf_heads: int = 2
+    tf_units: int = 1024
+    tf_blocks: int = 4
 
     def to_dict(self):
         return asdict(self)
@@ -92,6 +98,34 @@ def _convnext_shapes(prefix: str, dim: int, inter: int, layers: int) -> Dict[str
     return s
 
 
+def _transformer_shapes(prefix: str, dim: int, units: int, blocks: int) -> Dict[str, Tuple[int, ...]]:
+    """Transformer wrapper around the espnet Encoder (modules/transformer.py:9-27, _transformer/encoder.py:24-235):
+    embed = Sequential(ScaledPositionalEncoding) -> `embed.0.alpha` (0-d); the `pe` table is a plain attribute, not a buffer."""
+    t = f"{prefix}.transformer"
+    s: Dict[str, Tuple[int, ...]] = {f"{t}.embed.0.alpha": ()}
+    for i in range(blocks):
+        p = f"{t}.encoders.{i}"
+        for lin in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            s[f"{p}.self_attn.{lin}.weight"] = (dim, dim)
+            s[f"{p}.self_attn.{lin}.bias"] = (dim,)
+        s[f"{p}.feed_forward.w_1.weight"] = (units, dim, 1)
+        s[f"{p}.feed_forward.w_1.bias"] = (units,)
+        s[f"{p}.feed_forward.w_2.weight"] = (dim, units, 1)
+        s[f"{p}.feed_forward.w_2.bias"] = (dim,)
+        for n in ("norm1", "norm2"):
+            s[f"{p}.{n}.weight"] = (dim,)
+            s[f"{p}.{n}.bias"] = (dim,)
+    s[f"{t}.after_norm.weight"] = (dim,)
+    s[f"{t}.after_norm.bias"] = (dim,)
+    return s
+
+
+def _backbone_shapes(spec: "ModelSpec", prefix: str, inter: int, layers: int) -> Dict[str, Tuple[int, ...]]:
+    if spec.backbone == "transformer":
+        return _transformer_shapes(prefix, spec.dim, spec.tf_units, spec.tf_blocks)
+    return _convnext_shapes(prefix, spec.dim, inter, layers)
+
+
 def _predictor_shapes(prefix: str, dim: int, ps: PredictorSpec) -> Dict[str, Tuple[int, ...]]:
     s = {}
     for i in range(ps.num_layers):
@@ -111,7 +145,7 @@ def generator_shapes(spec: ModelSpec) -> Dict[str, Tuple[int, ...]]:
     s: Dict[str, Tuple[int, ...]] = {}
     s["text_embedding.embed_tokens.weight"] = (spec.n_vocab, d)
     s["text_embedding.embed_positions.scale"] = (1,)
-    s.update(_convnext_shapes("encoder", d, spec.enc_intermediate, spec.enc_layers))
+    s.update(_backbone_shapes(spec, "encoder", spec.enc_intermediate, spec.enc_layers))
     s.update(_predictor_shapes("duration_predictor", d, spec.duration))
     for name, cout, cin, k in (("t_conv1", d, d, 3), ("t_conv2", d, d, 1), ("f_conv1", d, spec.n_feats, 3),
                                ("f_conv2", d, d, 3), ("f_conv3", d, d, 1)):
@@ -121,7 +155,7 @@ def generator_shapes(spec: ModelSpec) -> Dict[str, Tuple[int, ...]]:
         s.update(_predictor_shapes(f"{nm}.predictor", d, ps))
         s[f"{nm}.embed.0.weight"] = (d, 1, ps.embed_kernel_size)
         s[f"{nm}.embed.0.bias"] = (d,)
-    s.update(_convnext_shapes("decoder", d, spec.dec_intermediate, spec.dec_layers))
+    s.update(_backbone_shapes(spec, "decoder", spec.dec_intermediate, spec.dec_layers))
     s["vocoder.embed.weight"] = (spec.voc_dim, d, 7)
     s["vocoder.embed.bias"] = (spec.voc_dim,)
     s["vocoder.norm.weight"] = (spec.voc_dim,)
@@ -152,9 +186,11 @@ def deterministic_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, 
         leaf = key.rsplit(".", 1)[-1]
         if key.endswith("embed_positions.scale"):
             v = torch.full(shape, 0.08)
+        elif leaf == "alpha":
+            v = 1.0 + 0.1 * r
         elif leaf == "gamma":
             v = 0.25 * (1.0 + 0.1 * r)
-        elif ".norm." in key or "layer_norm" in key or (leaf in ("weight", "bias") and len(shape) == 1 and ".2." in key):
+        elif ".norm." in key or "layer_norm" in key or ".norm1." in key or ".norm2." in key or ".after_norm." in key or (leaf in ("weight", "bias") and len(shape) == 1 and ".2." in key):
             v = (1.0 + 0.1 * r) if leaf == "weight" else 0.05 * r
         elif leaf == "bias":
             v = 0.05 * r

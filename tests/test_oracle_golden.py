@@ -142,3 +142,60 @@ def test_beta_binomial_prior():
     fx = _load("algorithms.npz")
     for T, N in [(5, 3), (31, 9), (110, 24)]:
         assert np.abs(O.beta_binomial_log_prior(T, N) - fx[f"prior_{T}_{N}"]).max() <= 1e-9
+
+
+# ---- Transformer backbone configuration (configs/model/transformer.yaml; tests/golden/make_golden_transformer.py) ----------
+def _tf_spec():
+    return ModelSpec(backbone="transformer")
+
+
+def test_transformer_state_dict_layout_matches_reference():
+    fx = _load("transformer.npz")
+    mine = generator_shapes(_tf_spec())
+    ref = {str(k): tuple(int(v) for v in str(s).split(",") if v) for k, s in zip(fx["state_dict_keys"], fx["state_dict_shapes"])}
+    assert {k: tuple(v) for k, v in mine.items()} == ref
+    total = sum(int(np.prod(v)) for v in mine.values())
+    align = sum(int(np.prod(v)) for k, v in mine.items() if k.startswith("alignment_module"))
+    assert total - align == 17_982_344  # README.md:168-170 parameter table
+
+
+def test_transformer_backbone_matches_reference():
+    fx = _load("transformer.npz")
+    spec = _tf_spec()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("encoder.")}
+    x = _t(fx["bb_x"]).requires_grad_(True)
+    lens = _t(fx["bb_lens"])
+    pad = ~(torch.arange(x.shape[1])[None] < lens[:, None])
+    out = O.transformer_backbone(sd, "encoder", x, pad, spec.tf_blocks, spec.tf_heads)
+    assert np.abs(out.detach().numpy() - fx["bb_out"]).max() <= 2e-5
+    (out * _t(fx["bb_w"])).sum().backward()
+    assert np.abs(x.grad.numpy() - fx["bb_dx"]).max() <= 2e-5 * max(1.0, np.abs(fx["bb_dx"]).max())
+    for k, ref_norm in zip(fx["bb_grad_keys"], fx["bb_grad_norms"]):
+        g = sd["encoder." + str(k)].grad
+        # linear_k.bias has a mathematically zero gradient (softmax is shift invariant): its norm is rounding noise ~1e-6
+        assert g is not None and abs(float(g.norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6) + 1e-5, k
+    assert abs(float(sd["encoder.transformer.embed.0.alpha"].grad) - float(fx["bb_grad_alpha"])) <= 1e-3 * abs(float(fx["bb_grad_alpha"])) + 1e-6
+
+
+def test_transformer_generator_matches_reference():
+    fx = _load("transformer.npz")
+    spec = _tf_spec()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    out = O.synthesise(sd, spec, _t(fx["synth_x"]), _t(fx["synth_x_lengths"]), 1.1, 1.6, 1.2)
+    assert np.array_equal(out["durations"].numpy(), fx["synth_durations"])
+    assert np.array_equal(out["wav_lengths"].numpy(), fx["synth_wav_lengths"])
+    assert np.abs(out["wav"].numpy() - fx["synth_wav"]).max() <= 2e-5
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.generator_forward(sdg, spec, _t(fx["train_x"]), _t(fx["train_x_lengths"]), _t(fx["train_mel"]), _t(fx["train_mel_lengths"]),
+                            _t(fx["train_pitches"]), _t(fx["train_energies"]), _t(fx["train_seg_rand"]))
+    for key in ("loss", "align_loss", "duration_loss", "pitch_loss", "energy_loss"):
+        assert abs(o[key].item() - float(fx[f"train_{key}"])) <= 2e-5 * max(1.0, abs(float(fx[f"train_{key}"]))), key
+    assert np.abs(o["wav_hat"].detach().numpy() - fx["train_wav_hat"]).max() <= 2e-5
+    o["loss"].backward()
+    for k, ref_norm in zip(fx["train_grad_keys"], fx["train_grad_norms"]):
+        g = sdg[str(k)].grad
+        if ref_norm < 0:
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            assert g is not None and abs(float(g.norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6) + 1e-5, k
