@@ -93,7 +93,8 @@ enum {
    * error instead of 2^-11).  Needed to hold the 1e-3 waveform tolerance at full-scale amplitude. */
   OSB_FLAG_SPLIT_IN = 32, /* a is (B,T,[hi K | lo K]) with lda >= 2K; w is (2, taps, N, ldw): [0] = hi parts, [1] = lo parts */
   OSB_FLAG_SPLIT_OUT = 64, /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                */
-  OSB_FLAG_RELU = 128      /* EPI_BIAS only: out = relu(acc + bias)                                                */
+  OSB_FLAG_RELU = 128,     /* EPI_BIAS only: out = relu(acc + bias)                                                */
+  OSB_FLAG_NO_F32 = 256    /* EPI_BIAS with OUT_H16: write only the fp16 copy (out may be NULL)                    */
 };
 
 typedef struct osb_gemm_desc {
@@ -123,7 +124,9 @@ typedef struct osb_gemm_desc {
   const void* aux_in_h16; /* *_BWD: fp16 (B*T, ldo) saved activation                                */
   const float* row_stat;  /* LN_BWD: (B*T) rstd saved by osb_dwconv_ln                              */
   /* Dropout after the LayerNorm of RELU_LN (VariancePredictor, core.py:78), element (row, n) keyed by
-   * dropout_seed: forward scales the LN output, RELU_LN_BWD scales the incoming gradient by the same mask. */
+   * dropout_seed: forward scales the LN output, RELU_LN_BWD scales the incoming gradient by the same mask.
+   * Also honoured by EPI_RELU (after the ReLU), EPI_RESID (on acc+bias, before the residual add) and EPI_RELU_BWD
+   * (multiplies by 1/(1-p); its aux_in must be the post-dropout ReLU output) — the Transformer layers' dropouts. */
   float dropout_p;        /* 0 disables                                                              */
   uint64_t dropout_seed;
   const uint64_t* dropout_seed_dev; /* optional device scalar added to dropout_seed (lets a captured CUDA graph draw a new
@@ -364,6 +367,47 @@ int osb_stft_loss(const float* x_hat, const float* y, const float* window, int32
 int osb_mel_loss(const float* x_hat, const float* y, const float* window, const float* fb, const int32_t* klo, const int32_t* khi,
                  const int32_t* jlo, const int32_t* jhi, int32_t n_mels, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t win,
                  float clamp_min, double* stats, const float* coef, float* dx_hat, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-head self-attention of the Transformer backbone (osb_mha.cu), d_k = 128.
+ * q, k, v: fp16 (B, T, ld_qkv) with head h in columns [h*128, +128) (typically three column slices of one fused
+ * (B, T, 3*H*128) projection output).  kv_len (B) or NULL: keys >= kv_len[b] are masked (their probability is exactly 0);
+ * query rows are never masked.  Counter-based dropout on the probabilities (element ((b*H+h)*T+t)*T+key of `seed`).
+ * Replaces MultiHeadedAttention.forward / forward_attention up to (not including) linear_out
+ * (optispeech/model/generator/modules/_transformer/attention.py:84-125).
+ * ------------------------------------------------------------------------------------- */
+
+/* ctx[b,t,h*128+d] = sum_key softmax_key(q.k * scale)[key] * D[key] * v[key,d]  as fp16 (ld_ctx); ctx_lo_off > 0 also writes the
+ * fp16 rounding residual at column offset ctx_lo_off (split-precision operand for linear_out).  row_max / row_inv_l (B,H,T)
+ * fp32, optional (both or neither): raw row maximum and 1/sum(exp) for the backward pass. */
+int osb_mha_fwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const int64_t* kv_len, void* ctx, int64_t ld_ctx,
+                int64_t ctx_lo_off, float* row_max, float* row_inv_l, int32_t B, int32_t T, int32_t H, int32_t d_k, float scale,
+                float dropout_p, uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* stream);
+
+/* Backward of osb_mha_fwd with respect to q (complete) and, as fp16 matrices for two further contractions, to k and v:
+ *   dq[b,t,h*128+d]       = sum_key dS[t,key] k[key,d]                       (fp16, ld_dq)
+ *   ds_out[b,t,h*Tp+key]  = dS = P o (dP o D - delta) * scale,  dP = d_ctx v^T, delta = <d_ctx_row, ctx_row>
+ *   pd_out[b,t,h*Tp+key]  = P o D                                            (both fp16, ld_p >= H*Tp, Tp >= T, Tp % 8 == 0;
+ *                                                                              columns [T, Tp) are zero)
+ * then dk_h = ds_out_h^T q_h and dv_h = pd_out_h^T d_ctx_h through osb_gemm_wgrad_batched. */
+int osb_mha_bwd(const void* q, const void* k, const void* v, int64_t ld_qkv, const int64_t* kv_len, const void* ctx, int64_t ld_ctx,
+                const void* d_ctx, int64_t ld_dctx, const float* row_max, const float* row_inv_l, void* dq, int64_t ld_dq,
+                void* ds_out, void* pd_out, int64_t ld_p, int32_t Tp, int32_t B, int32_t T, int32_t H, int32_t d_k, float scale,
+                float dropout_p, uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* stream);
+
+/* dst[b,t, h*128 + d] = fp16(src[h,b,t,d]): gathers per-head fp32 (H,B,T,128) gradients into a channels-last fp16 operand. */
+int osb_mha_pack_heads(const float* src, void* dst_h16, int64_t ld_dst, int32_t B, int32_t T, int32_t H, void* stream);
+
+/* dst[i] = fp16(src[i] * D(i)), i over rows*N elements, D the counter-based dropout scale of `seed` (p = 0: plain cast).
+ * The gradient entering a branch whose forward output was dropped out by OSB_EPI_RESID (same seed, same element order). */
+int osb_dropout_pack_h16(const float* src, void* dst_h16, int64_t rows, int32_t N, float dropout_p, uint64_t dropout_seed,
+                         const uint64_t* dropout_seed_dev, void* stream);
+
+/* out[b,t,:] = (x[b,t,:] + alpha[0] * pe[t,:]) * D : ScaledPositionalEncoding.forward and its dropout
+ * (modules/_transformer/embedding.py:111-124); pe (T, C) fp32 table, alpha device scalar.  pe = alpha = NULL applies the
+ * dropout mask only (the backward pass: dx = dout * D). */
+int osb_add_posenc(const float* x, const float* pe, const float* alpha, float* out, int32_t B, int32_t T, int32_t C, float dropout_p,
+                   uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* stream);
 
 #ifdef __cplusplus
 }

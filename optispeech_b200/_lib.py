@@ -16,7 +16,7 @@ OSB_OK = 0
 # osb_epilogue
 EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD, EPI_ATTN_LOGP, EPI_AXPY = range(12)
 # flags
-FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU = 1, 2, 4, 8, 16, 32, 64, 128
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU, FLAG_NO_F32 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 class GemmDesc(C.Structure):
@@ -124,6 +124,11 @@ def load() -> C.CDLL:
         "osb_adamw_step": [P, P, P, P, I64, P, F, F, F, F, F, I64, F, F, P],
         "osb_adamw_step_dev": [P, P, P, P, I64, P, P, F, F, F, F, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],
+        "osb_mha_fwd": [P, P, P, I64, P, P, I64, I64, P, P, I32, I32, I32, I32, F, F, C.c_uint64, P, P],
+        "osb_mha_bwd": [P, P, P, I64, P, P, I64, P, I64, P, P, P, I64, P, P, I64, I32, I32, I32, I32, I32, F, F, C.c_uint64, P, P],
+        "osb_mha_pack_heads": [P, P, I64, I32, I32, I32, P],
+        "osb_dropout_pack_h16": [P, P, I64, I32, F, C.c_uint64, P, P],
+        "osb_add_posenc": [P, P, P, P, I32, I32, I32, F, C.c_uint64, P, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

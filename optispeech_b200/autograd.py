@@ -350,3 +350,85 @@ class ForwardSumLossFn(Function):
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
         return grad * dloss, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# Transformer backbone (modules/transformer.py): scaled positional encoding and one pre-LN encoder layer
+# --------------------------------------------------------------------------------------------------
+class PosEncFn(Function):
+    """out = (x + alpha * pe[:T]) * D   (ScaledPositionalEncoding.forward, _transformer/embedding.py:111-124)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, pe, p, seed):
+        ctx.save_for_backward(pe)
+        ctx.p, ctx.seed, ctx.T = p, seed, x.shape[1]
+        return ops.add_posenc(x.contiguous(), pe, alpha.detach().reshape(1), p, seed)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (pe,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = ops.add_posenc(dout, None, None, ctx.p, ctx.seed) if ctx.p > 0.0 else dout
+        dalpha = (dx * pe[: ctx.T]).sum()  # one scalar: a reduction of the (B,T,C) gradient against the table
+        return dx, dalpha, None, None, None
+
+
+class TransformerLayerFn(Function):
+    """x1 = x + D1(linear_out(MHA(LN1 x)));  out = x1 + D3(w_2(D2(relu(w_1(LN2 x1)))))     (encoder_layer.py:88-116)
+
+    Seeds: attention dropout seed+0, D1 seed+1, D2 seed+2, D3 seed+3 (counter-based masks are regenerated in backward)."""
+
+    @staticmethod
+    def forward(ctx, x, kv_len, heads, p_drop, p_attn, p_ffn, seed, ones, n1w, n1b, wq, bq, wk, bk, wv, bv, wo, bo, n2w, n2b, w1, b1, w2, b2):
+        eps = 1e-12
+        x = x.contiguous()
+        _, xn = ops.layernorm(x, n1w, n1b, eps, f32=False, h16=True)
+        wqkv = torch.cat([wq, wk, wv], dim=0)
+        bqkv = torch.cat([bq, bk, bv])
+        _, qkv, _ = ops.gemm(xn, pack_nk(wqkv), epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, bias=bqkv)
+        att, rmax, rinv = ops.mha_fwd(qkv, heads, kv_len, save_stats=True, dropout_p=p_attn, dropout_seed=seed)
+        x1, _, _ = ops.gemm(att, pack_nk(wo), epi=ops.EPI_RESID, bias=bo, resid=x, gamma=ones, dropout_p=p_drop, dropout_seed=seed + 1)
+        _, xn2 = ops.layernorm(x1, n2w, n2b, eps, f32=False, h16=True)
+        h, _, _ = ops.gemm(xn2, pack_nk(w1[:, :, 0]), epi=ops.EPI_RELU, bias=b1, dropout_p=p_ffn, dropout_seed=seed + 2)
+        out, _, _ = ops.gemm(h, pack_nk(w2[:, :, 0]), epi=ops.EPI_RESID, bias=b2, resid=x1, gamma=ones, dropout_p=p_drop,
+                             dropout_seed=seed + 3)
+        ctx.save_for_backward(x, kv_len, n1w, wqkv, wo, n2w, w1, w2, xn, qkv, att, rmax, rinv, x1, xn2, h)
+        ctx.cfg = (heads, p_drop, p_attn, p_ffn, seed, eps)
+        return out
+
+    @staticmethod
+    @ops.pooled
+    def backward(ctx, dout):
+        x, kv_len, n1w, wqkv, wo, n2w, w1, w2, xn, qkv, att, rmax, rinv, x1, xn2, h = ctx.saved_tensors
+        heads, p_drop, p_attn, p_ffn, seed, eps = ctx.cfg
+        B, T, D = x.shape
+        U = w1.shape[0]
+        dout = dout.contiguous()
+        # ---- feed-forward branch ----
+        g2 = ops.dropout_pack_h16(dout, p_drop, seed + 3)                      # grad wrt (w_2 h + b2)
+        dw2 = ops.zeros((1, D, U), x)
+        ops.gemm_wgrad(g2, h, dw2)
+        db2 = ops.colsum_h16(g2)
+        dh, _, _ = ops.gemm(g2, pack_kn(w2[:, :, 0]), epi=ops.EPI_RELU_BWD, aux_in=h, dropout_p=p_ffn, dropout_seed=seed + 2)
+        dw1 = ops.zeros((1, U, D), x)
+        ops.gemm_wgrad(dh, xn2, dw1)
+        db1 = ops.colsum_h16(dh)
+        dxn2, _, _ = ops.gemm(dh, pack_kn(w1[:, :, 0]), epi=ops.EPI_BIAS)
+        dln2, dn2w, dn2b = ops.layernorm_bwd(dxn2, x1, n2w, eps)
+        dx1 = dout + dln2
+        # ---- attention branch ----
+        g1 = ops.dropout_pack_h16(dx1, p_drop, seed + 1)                       # grad wrt (linear_out att + bo)
+        dwo = ops.zeros((1, D, D), x)
+        ops.gemm_wgrad(g1, att, dwo)
+        dbo = ops.colsum_h16(g1)
+        _, datt, _ = ops.gemm(g1, pack_kn(wo), epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
+        dqkv = ops.mha_bwd(qkv, heads, kv_len, att, datt, rmax, rinv, dropout_p=p_attn, dropout_seed=seed)
+        dwqkv = ops.zeros((1, 3 * D, D), x)
+        ops.gemm_wgrad(dqkv, xn, dwqkv)
+        dbqkv = ops.colsum_h16(dqkv)
+        dxn, _, _ = ops.gemm(dqkv, pack_kn(wqkv), epi=ops.EPI_BIAS)
+        dln1, dn1w, dn1b = ops.layernorm_bwd(dxn, x, n1w, eps)
+        dx = dx1 + dln1
+        dwq, dwk, dwv = dwqkv[0, :D], dwqkv[0, D:2 * D], dwqkv[0, 2 * D:]
+        return (dx, None, None, None, None, None, None, None, dn1w, dn1b, dwq, dbqkv[:D], dwk, dbqkv[D:2 * D], dwv, dbqkv[2 * D:],
+                dwo[0], dbo, dn2w, dn2b, dw1.view(U, D, 1), db1, dw2.view(D, U, 1), db2)

@@ -247,8 +247,8 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if constexpr (EPI == OSB_EPI_GELU_BWD) v[i] *= gelu_erf_grad(pre[i]);
-          else v[i] = pre[i] > 0.f ? v[i] : 0.f;
-        }
+          else v[i] = pre[i] > 0.f ? v[i] * (p.drop_p > 0.f ? p.drop_inv_keep : 1.f) : 0.f;  // aux_in = relu output AFTER dropout:
+        }                                                                                      // dropped elements are 0 there
         st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + n, v);
       }
     }
@@ -350,7 +350,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
         if (valid) {
-          st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
+          if (!(p.flags & OSB_FLAG_NO_F32)) st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
           if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, n, v);
         }
       } else if constexpr (EPI == OSB_EPI_GELU) {
@@ -361,9 +361,19 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       } else if constexpr (EPI == OSB_EPI_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        if (p.drop_p > 0.f) {  // Dropout after the ReLU (MultiLayeredConv1d, multi_layer_conv.py:60-62)
+          const unsigned long long dbase = static_cast<unsigned long long>(row) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
+        }
         if (valid) store_h(p, p.out, row, n, v);
       } else {  // RESID
         if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
+        if (p.drop_p > 0.f) {  // element dropout on the branch before the residual add (EncoderLayer, encoder_layer.py:103,111)
+          const unsigned long long dbase = static_cast<unsigned long long>(row) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
+        }
         if (valid) {
           const float* rp = p.resid + row * p.ldo + n;
 #pragma unroll
@@ -842,7 +852,7 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
 
   switch (d->epi) {
     case OSB_EPI_BIAS:
-      OSB_REQUIRE(d->out != nullptr, OSB_ERR_ARG);
+      OSB_REQUIRE(d->out != nullptr || ((d->flags & OSB_FLAG_NO_F32) && (d->flags & OSB_FLAG_OUT_H16)), OSB_ERR_ARG);
       return dispatch_bn<OSB_EPI_BIAS>(bn, tmA, tmW, p, stream);
     case OSB_EPI_GELU:
       OSB_REQUIRE(d->out != nullptr, OSB_ERR_ARG);

@@ -9,7 +9,7 @@ from types import SimpleNamespace
 import torch
 
 from .model.generator import OptiSpeechGenerator
-from .model.generator.modules import ConvNeXtBackbone, DurationPredictor, EnergyPredictor, PitchPredictor, TextEmbedding
+from .model.generator.modules import ConvNeXtBackbone, DurationPredictor, EnergyPredictor, PitchPredictor, TextEmbedding, Transformer
 from .model.vocoder.wavenext import WaveNeXt
 
 DEFAULT_MODEL = dict(
@@ -29,6 +29,19 @@ DEFAULT_MODEL = dict(
     num_languages=1,
 )
 
+# configs/model/generator/{encoder,decoder}/transformer.yaml (selected by configs/model/transformer.yaml)
+TRANSFORMER_BACKBONE = dict(attention_heads=2, linear_units=1024, num_blocks=4, dropout_rate=0.2, positional_dropout_rate=0.2,
+                            attention_dropout_rate=0.2, normalize_before=True, concat_after=False, positionwise_layer_type="conv1d",
+                            positionwise_conv_kernel_size=1, use_scaled_pos_enc=True, init_alpha=1.0, init_type="xavier_uniform")
+
+
+def transformer_model_config() -> dict:
+    """DEFAULT_MODEL with `override generator/encoder: transformer` + `override generator/decoder: transformer`."""
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in DEFAULT_MODEL.items()}
+    cfg["encoder"] = dict(TRANSFORMER_BACKBONE, _backbone="transformer")
+    cfg["decoder"] = dict(TRANSFORMER_BACKBONE, _backbone="transformer")
+    return cfg
+
 
 def model_config_from_spec(spec) -> dict:
     """oracle.spec.ModelSpec (or anything with the same fields) -> factory config."""
@@ -36,8 +49,13 @@ def model_config_from_spec(spec) -> dict:
     cfg["dim"] = spec.dim
     cfg["segment_size"] = spec.segment_size
     cfg["text_embedding"].update(n_vocab=spec.n_vocab, max_source_positions=spec.max_source_positions)
-    cfg["encoder"].update(intermediate_dim=spec.enc_intermediate, num_layers=spec.enc_layers)
-    cfg["decoder"].update(intermediate_dim=spec.dec_intermediate, num_layers=spec.dec_layers)
+    if getattr(spec, "backbone", "convnext") == "transformer":
+        tf = dict(TRANSFORMER_BACKBONE, attention_heads=spec.tf_heads, linear_units=spec.tf_units, num_blocks=spec.tf_blocks,
+                  _backbone="transformer")
+        cfg["encoder"], cfg["decoder"] = dict(tf), dict(tf)
+    else:
+        cfg["encoder"].update(intermediate_dim=spec.enc_intermediate, num_layers=spec.enc_layers)
+        cfg["decoder"].update(intermediate_dim=spec.dec_intermediate, num_layers=spec.dec_layers)
     for name in ("duration", "pitch", "energy"):
         ps = getattr(spec, name)
         cfg[f"{name}_predictor"].update(num_layers=ps.num_layers, intermediate_dim=ps.intermediate_dim, kernel_size=ps.kernel_size)
@@ -53,6 +71,12 @@ def model_config_from_spec(spec) -> dict:
     return cfg
 
 
+def _backbone_partial(kw: dict):
+    kw = dict(kw)
+    kind = kw.pop("_backbone", "convnext")
+    return partial(Transformer if kind == "transformer" else ConvNeXtBackbone, **kw)
+
+
 def generator_partial(cfg: dict):
     """The `generator` partial of configs/model/generator/default.yaml."""
     conv = partial(torch.nn.Conv1d)
@@ -60,11 +84,11 @@ def generator_partial(cfg: dict):
         OptiSpeechGenerator,
         segment_size=cfg["segment_size"],
         text_embedding=partial(TextEmbedding, **cfg["text_embedding"]),
-        encoder=partial(ConvNeXtBackbone, **cfg["encoder"]),
+        encoder=_backbone_partial(cfg["encoder"]),
         duration_predictor=partial(DurationPredictor, conv_layer_class=conv, **cfg["duration_predictor"]),
         pitch_predictor=partial(PitchPredictor, conv_layer_class=conv, **cfg["pitch_predictor"]),
         energy_predictor=partial(EnergyPredictor, conv_layer_class=conv, **cfg["energy_predictor"]),
-        decoder=partial(ConvNeXtBackbone, **cfg["decoder"]),
+        decoder=_backbone_partial(cfg["decoder"]),
         loss_coeffs=SimpleNamespace(**cfg["loss_coeffs"]),
     )
 

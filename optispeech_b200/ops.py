@@ -96,7 +96,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
         K = K if K is not None else min(lda, ldw)
     f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN, EPI_LN_BWD, EPI_ATTN_LOGP, EPI_AXPY)
     hN = 2 * N if (flags & FLAG_SPLIT_OUT) else N
-    if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)):
+    if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)) and not (flags & _lib.FLAG_NO_F32):
         out = torch.empty((B, T, N if f32_out else hN), device=a.device, dtype=torch.float32 if f32_out else torch.float16)
     if (flags & FLAG_OUT_H16) and aux is None:
         aux = torch.empty((B, T, hN), device=a.device, dtype=torch.float16)
@@ -479,4 +479,77 @@ def convnext_block_fwd(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale
     _lib.check(_lib.load().osb_convnext_block_fwd(_ptr(_f32(x)), _ptr(_f32(dw_w)), _ptr(_f32(dw_b)), _ptr(w1f_h16), _ptr(_f32(b1f)),
                                                   _ptr(w2_h16), _ptr(_f32(b2)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask),
                                                   _ptr(out), B, T, Cc, I, float(eps), _stream()), "osb_convnext_block_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Transformer backbone: fused multi-head attention, positional encoding, dropout-pack
+# ------------------------------------------------------------------------------------------------
+FLAG_NO_F32 = _lib.FLAG_NO_F32
+MHA_DK = 128
+
+
+def _seed_dev(t, p):
+    return _ptr(step_counter(t.device)) if p > 0.0 else None
+
+
+def mha_fwd(qkv: torch.Tensor, heads: int, kv_len: Optional[torch.Tensor], *, split_out: bool = False, save_stats: bool = False,
+            dropout_p: float = 0.0, dropout_seed: int = 0):
+    """qkv fp16 (B, T, 3*D) = [q | k | v], D = heads*128 -> ctx fp16 (B, T, D) (or (B, T, [hi D | lo D]) with split_out),
+    and optionally (row_max, row_inv_l) fp32 (B, heads, T) for the backward pass."""
+    assert qkv.dtype == torch.float16 and qkv.dim() == 3
+    B, T, ld = qkv.shape
+    D = heads * MHA_DK
+    assert ld == 3 * D, (ld, D)
+    ctx = torch.empty((B, T, 2 * D if split_out else D), device=qkv.device, dtype=torch.float16)
+    rmax = rinv = None
+    if save_stats:
+        rmax = torch.empty((B, heads, T), device=qkv.device, dtype=torch.float32)
+        rinv = torch.empty((B, heads, T), device=qkv.device, dtype=torch.float32)
+    base = _ptr(qkv)
+    _lib.check(_lib.load().osb_mha_fwd(base, base + 2 * D, base + 4 * D, ld, _ptr(kv_len), _ptr(ctx), ctx.shape[2], D if split_out else 0,
+                                       _ptr(rmax), _ptr(rinv), B, T, heads, MHA_DK, MHA_DK ** -0.5, float(dropout_p), int(dropout_seed),
+                                       _seed_dev(qkv, dropout_p), _stream()), "osb_mha_fwd")
+    return ctx, rmax, rinv
+
+
+def mha_bwd(qkv: torch.Tensor, heads: int, kv_len, ctx: torch.Tensor, d_ctx: torch.Tensor, rmax, rinv, *, dropout_p: float = 0.0,
+            dropout_seed: int = 0) -> torch.Tensor:
+    """-> dqkv fp16 (B, T, 3*D): gradient of the loss w.r.t. [q | k | v] given d_ctx fp16 (B, T, D)."""
+    B, T, ld = qkv.shape
+    D = heads * MHA_DK
+    Tp = (T + 7) // 8 * 8
+    dqkv = torch.empty((B, T, 3 * D), device=qkv.device, dtype=torch.float16)
+    ds = torch.empty((B, T, heads * Tp), device=qkv.device, dtype=torch.float16)
+    pd = torch.empty((B, T, heads * Tp), device=qkv.device, dtype=torch.float16)
+    base = _ptr(qkv)
+    lib = _lib.load()
+    _lib.check(lib.osb_mha_bwd(base, base + 2 * D, base + 4 * D, ld, _ptr(kv_len), _ptr(ctx), ctx.shape[2], _ptr(d_ctx), d_ctx.shape[2],
+                               _ptr(rmax), _ptr(rinv), _ptr(dqkv), 3 * D, _ptr(ds), _ptr(pd), heads * Tp, Tp, B, T, heads, MHA_DK,
+                               MHA_DK ** -0.5, float(dropout_p), int(dropout_seed), _seed_dev(qkv, dropout_p), _stream()), "osb_mha_bwd")
+    # dK_h = dS_h^T Q_h, dV_h = (P o D)_h^T dO_h : contractions over the query rows, both operands MN-major in place
+    dkv = _zeros((2, heads, B, T, MHA_DK), qkv)
+    for h in range(heads):
+        _lib.check(lib.osb_gemm_wgrad_batched(_ptr(ds) + 2 * h * Tp, heads * Tp, base + 2 * h * MHA_DK, ld, _ptr(dkv[0, h]), B, T, T,
+                                              MHA_DK, _stream()), "osb_gemm_wgrad_batched")
+        _lib.check(lib.osb_gemm_wgrad_batched(_ptr(pd) + 2 * h * Tp, heads * Tp, _ptr(d_ctx) + 2 * h * MHA_DK, d_ctx.shape[2],
+                                              _ptr(dkv[1, h]), B, T, T, MHA_DK, _stream()), "osb_gemm_wgrad_batched")
+    for i in range(2):
+        _lib.check(lib.osb_mha_pack_heads(_ptr(dkv[i]), _ptr(dqkv) + 2 * (i + 1) * D, 3 * D, B, T, heads, _stream()), "osb_mha_pack_heads")
+    return dqkv
+
+
+def dropout_pack_h16(x: torch.Tensor, dropout_p: float = 0.0, dropout_seed: int = 0) -> torch.Tensor:
+    N = x.shape[-1]
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_dropout_pack_h16(_ptr(_f32(x)), _ptr(out), x.numel() // N, N, float(dropout_p), int(dropout_seed),
+                                                _seed_dev(x, dropout_p), _stream()), "osb_dropout_pack_h16")
+    return out
+
+
+def add_posenc(x: torch.Tensor, pe: Optional[torch.Tensor], alpha: Optional[torch.Tensor], dropout_p: float = 0.0, dropout_seed: int = 0):
+    B, T, Cc = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().osb_add_posenc(_ptr(_f32(x)), _ptr(pe), _ptr(alpha), _ptr(out), B, T, Cc, float(dropout_p), int(dropout_seed),
+                                          _seed_dev(x, dropout_p), _stream()), "osb_add_posenc")
     return out
