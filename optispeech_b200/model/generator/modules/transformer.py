@@ -56,13 +56,14 @@ class PositionalEncoding(nn.Module):
     def table(self, T: int, device) -> torch.Tensor:
         """pe[t, 2i] = sin(t w_i), pe[t, 2i+1] = cos(t w_i): built exactly as the reference does (fp32, CPU), cached on the device."""
         if self._pe is None or self._pe.shape[0] < T or self._pe.device != device:
-            n = max(T, 1024)
-            position = torch.arange(0, n, dtype=torch.float32).unsqueeze(1)
-            div_term = torch.exp(torch.arange(0, self.d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / self.d_model))
-            pe = torch.zeros(n, self.d_model)
-            pe[:, 0::2] = torch.sin(position * div_term)
-            pe[:, 1::2] = torch.cos(position * div_term)
-            self._pe = pe.to(device)
+            with torch.inference_mode(False):  # a cached constant: must stay usable by autograd after synthesise() built it
+                n = max(T, 1024)
+                position = torch.arange(0, n, dtype=torch.float32).unsqueeze(1)
+                div_term = torch.exp(torch.arange(0, self.d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / self.d_model))
+                pe = torch.zeros(n, self.d_model)
+                pe[:, 0::2] = torch.sin(position * div_term)
+                pe[:, 1::2] = torch.cos(position * div_term)
+                self._pe = pe.to(device)
         return self._pe
 
 
