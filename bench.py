@@ -115,6 +115,16 @@ def run_reference_arm(args, rank: int):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/summarize_ncu.py), or None."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return table.get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------------------
@@ -216,7 +226,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         frames_all = int(t.item())
     dev_batch = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
     pinned = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host_batch.items()}
-    h2d = batch_bytes(host_batch)
+    h2d = model.batch_h2d_bytes(model.stage_batch(pinned))  # what training_step really copies: the waveform crop is cut on the host
 
     def step_resident(i):
         model.training_step(dev_batch, i)
@@ -286,7 +296,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12  # algorithmic flops of all its launches / their summed duration
             roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": ncu_traffic(name),
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                         "launches_per_step": g["launches"], "avg_us": 1e3 * g["ms"] / g["launches"], "share_of_lib_time": g["ms"] / total_ms,
                         "per_shape": g["shapes"]}
@@ -313,6 +323,48 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             synth[name] = {"audio_samples_per_s_e2e": nsamp / dt, "rtf": dt / (nsamp / 22050.0), "ms": 1e3 * dt,
                            "frames": int(nsamp // 256), "precision": "fp16x3"}
         model.train()
+
+    # ---- BASELINE config 4: the same step and synthesis with the Transformer backbone (self-attention kernel path) ----
+    variants = {}
+    if rank == 0 and world == 1 and not args.no_variants:
+        try:
+            from optispeech_b200.factory import transformer_model_config
+
+            torch.manual_seed(SEED)
+            tmodel = build_model(transformer_model_config(), train_args=dict(pretraining_steps=10 ** 9)).to(dev).train()
+            tmodel.cuda_graph = True
+            for i in range(4 + 3):
+                tmodel.training_step(dev_batch, i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(10):
+                tmodel.training_step(dev_batch, i)
+            e1.record()
+            torch.cuda.synchronize()
+            tms = e0.elapsed_time(e1) / 10
+            tmodel.eval()
+            g = torch.Generator().manual_seed(SEED)
+            ids = torch.randint(1, 159, (8, 512), generator=g)
+            lens = torch.full((8,), 512, dtype=torch.int64)
+            durs = torch.randint(1, 4, (8, 512), generator=g)
+            for _ in range(3):
+                out = tmodel.generator.synthesise(ids.to(dev), lens, durations=durs)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                out = tmodel.generator.synthesise(ids.to(dev), lens, durations=durs)
+            dt = (time.perf_counter() - t0) / 5
+            nsamp = int(out["wav_lengths"].sum())
+            variants["transformer_backbone"] = {
+                "config": "configs/model/transformer.yaml (2 heads, d_k 128, 4+4 blocks), same batch, pre-training step, CUDA-graph replay",
+                "ms_per_step": tms, "mel_frames_per_s": frames_local / (tms * 1e-3),
+                "synthesis_long_B8_Tx512": {"audio_samples_per_s_e2e": nsamp / dt, "ms": 1e3 * dt, "frames": nsamp // 256}}
+            if tmodel._graphed is not None:
+                tmodel._graphed.release()
+            del tmodel
+        except Exception as exc:  # the headline line must not depend on a variant
+            variants["transformer_backbone"] = {"error": repr(exc)[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload through the oracle port ----
     cpu_baseline = None
@@ -346,6 +398,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu_baseline,
             "top_kernels": top,
             "synthesis": synth,
+            "variants": variants,
         }
         print(json.dumps(line), flush=True)
     if model._graphed is not None:  # every rank: graphs go before the process group does
@@ -359,6 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the Transformer-backbone variant (BASELINE config 4)")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying the step's CUDA graph")
     ap.add_argument("--quick", action="store_true", help="timed region only (for runs under ncu): no e2e / synthesis / roofline pass / cpu baseline")
     args = ap.parse_args()

@@ -37,6 +37,7 @@ struct FusedParams {
   const uint8_t* pad_mask;  // (B*T) or null
   float* out;            // (B, T, C)
   int B, T, m_tiles;
+  int nsplit;            // > 1: blockIdx.y owns a slice of the intermediate chunks and adds its partial result into `out` (pre-zeroed)
   float eps;
   long long* trace;      // optional (developer): clock64 timeline of CTA 0, [role][event] (see tools/probe_fused.py)
 };
@@ -94,6 +95,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.m_tiles;
   const int t0 = (blockIdx.x % p.m_tiles) * FB_M;
+  // Split of the intermediate dimension over blockIdx.y (small problems: fewer row tiles than SMs).  All pipeline indices
+  // below are relative to this CTA's first chunk; only weight / bias coordinates use the absolute chunk index.
+  const int split = blockIdx.y;
+  const int ch_begin = (NCH * split) / p.nsplit;
+  const int n_ch = (NCH * (split + 1)) / p.nsplit - ch_begin;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1);
@@ -118,21 +124,22 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   if (warp == 0) {
     // ===================== TMA producer: weight chunks =====================
     if (lane == 0) {
-      for (int j = 0; j < NCH; ++j) {
+      for (int j = 0; j < n_ch; ++j) {
         const int st = j % WS;
         const uint32_t ph = (j / WS) & 1;
+        const int ja = ch_begin + j;
         mbar_wait(&w1_empty[st], ph ^ 1);
         FB_TRACE(0, 2 * j);
         mbar_expect_tx(&w1_full[st], Cfg::W1_BYTES);
 #pragma unroll
         for (int kb = 0; kb < Cfg::KB; ++kb)
-          tma_load_3d(sW1 + st * Cfg::W1_BYTES + kb * (FB_NC * 128), &tmW1, &w1_full[st], kb * 64, j * FB_NC, 0);
+          tma_load_3d(sW1 + st * Cfg::W1_BYTES + kb * (FB_NC * 128), &tmW1, &w1_full[st], kb * 64, ja * FB_NC, 0);
         mbar_wait(&w2_empty[st], ph ^ 1);
         FB_TRACE(0, 2 * j + 1);
         mbar_expect_tx(&w2_full[st], Cfg::W2_BYTES);
 #pragma unroll
         for (int part = 0; part < Cfg::N2_PARTS; ++part)
-          tma_load_3d(sW2 + st * Cfg::W2_BYTES + part * (Cfg::N2 * 128), &tmW2, &w2_full[st], j * FB_NC, part * Cfg::N2, 0);
+          tma_load_3d(sW2 + st * Cfg::W2_BYTES + part * (Cfg::N2 * 128), &tmW2, &w2_full[st], ja * FB_NC, part * Cfg::N2, 0);
       }
     }
   } else if (warp == 1) {
@@ -153,8 +160,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       mbar_wait(a_ready, 0);
       if (lane == 0) FB_TRACE(1, 1);
       tc_fence_after_sync();
-      for (int j = 0; j <= NCH; ++j) {
-        if (j < NCH) {  // pwconv1 of chunk j -> acc1[j & 1]
+      for (int j = 0; j <= n_ch; ++j) {
+        if (j < n_ch) {  // pwconv1 of chunk j -> acc1[j & 1]
           const int buf = j & 1;
           const int st = j % WS;
           mbar_wait(&w1_full[st], (j / WS) & 1);
@@ -298,12 +305,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float bias_cur[32], bias_nxt[32];   // the folded pwconv1 bias of this thread's 32 columns, fetched one chunk ahead (L1 is tiny here)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) bias_cur[i] = __ldg(p.b1 + half * 32 + i);
-    for (int j = 0; j < NCH; ++j) {
+    for (int i = 0; i < 32; ++i) bias_cur[i] = __ldg(p.b1 + ch_begin * FB_NC + half * 32 + i);
+    for (int j = 0; j < n_ch; ++j) {
       const int buf = j & 1;
-      if (j + 1 < NCH) {
+      if (j + 1 < n_ch) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bias_nxt[i] = __ldg(p.b1 + (j + 1) * FB_NC + half * 32 + i);
+        for (int i = 0; i < 32; ++i) bias_nxt[i] = __ldg(p.b1 + (ch_begin + j + 1) * FB_NC + half * 32 + i);
       }
       mbar_wait(&acc1_full[buf], (j >> 1) & 1);
       if (ww == 0 && lane == 0) FB_TRACE(2, 1 + 5 * j);
@@ -361,7 +368,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + i));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + i));
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + i));
+        if (split != 0) b4 = make_float4(0.f, 0.f, 0.f, 0.f);   // the pwconv2 bias enters once
         float4 o;
         o.x = g4.x * (__uint_as_float(rr[i + 0]) + b4.x) * rs;
         o.y = g4.y * (__uint_as_float(rr[i + 1]) + b4.y) * rs;
@@ -379,11 +387,17 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int c = v * 128 + lane * 4;
-        const float4 x4 = *reinterpret_cast<const float4*>(p.x + grow * C + c);
+        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (split == 0) x4 = *reinterpret_cast<const float4*>(p.x + grow * C + c);   // so does the residual
         const float4 d4 = *reinterpret_cast<const float4*>(stile + r * OLD + c);
         float4 o;
         o.x = (x4.x + d4.x) * keep; o.y = (x4.y + d4.y) * keep; o.z = (x4.z + d4.z) * keep; o.w = (x4.w + d4.w) * keep;
-        *reinterpret_cast<float4*>(p.out + grow * C + c) = o;
+        if (p.nsplit == 1) {
+          *reinterpret_cast<float4*>(p.out + grow * C + c) = o;
+        } else {  // partial sums of the splits meet in L2: one 16-byte vector reduction per thread, 512 B per warp
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + grow * C + c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                       : "memory");
+        }
       }
     }
   }
@@ -409,7 +423,11 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
     if (e != cudaSuccess) return static_cast<int>(e);
     attr = true;
   }
-  convnext_fused_kernel<C, I><<<p.B * p.m_tiles, FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
+  if (p.nsplit > 1) {  // the splits accumulate into `out`
+    cudaError_t e = cudaMemsetAsync(p.out, 0, static_cast<size_t>(p.B) * p.T * C * sizeof(float), stream);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  convnext_fused_kernel<C, I><<<dim3(p.B * p.m_tiles, p.nsplit), FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
   count_launch();
   return launch_status();
 }
@@ -420,6 +438,9 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
 using namespace osb;
 
 static long long* g_fused_trace = nullptr;
+static int g_fused_nsplit = 0;
+/* developer hook (not in the public header): force the intermediate-dimension split of the fused block (0 = automatic) */
+extern "C" void osb_debug_set_fused_nsplit(int n) { g_fused_nsplit = n; }
 /* developer hook (not in the public header): device buffer of 3*256 int64 receiving a clock64 timeline of CTA 0 */
 extern "C" void osb_debug_set_fused_trace(long long* buf) { g_fused_trace = buf; }
 
@@ -432,6 +453,15 @@ extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const f
   FusedParams p;
   p.x = x; p.dw_w = dw_w; p.dw_b = dw_b; p.b1 = b1f; p.b2 = b2; p.gamma = gamma; p.row_scale = row_scale; p.pad_mask = pad_mask;
   p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps;
+  // Fewer row tiles than half the SMs: split the intermediate dimension so that the weight streaming (the per-CTA bound: every
+  // CTA walks all I/64 chunks) is spread over the machine; each split keeps at least two chunks.
+  {
+    const int tiles = B * p.m_tiles;
+    const int nch = I / FB_NC;
+    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles * 2 <= 148 ? 148 / tiles : 1);
+    if (ns > nch / 2) ns = nch / 2;
+    p.nsplit = ns < 1 ? 1 : ns;
+  }
   p.trace = g_fused_trace;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 256 && I == 1024) return launch_fused<256, 1024>(w1f_h16, w2_h16, p, s);

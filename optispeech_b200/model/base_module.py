@@ -113,14 +113,60 @@ class BaseModule(nn.Module):
         self.ckpt_loaded_epoch = checkpoint.get("epoch", -1)
 
     # -- reference training logic -------------------------------------------------------------------
+    def stage_batch(self, batch):
+        """Host half of the reference's `_process_batch` (base_lightning_module.py:38-43): when the collate function hands the
+        waveform and the lengths over in HOST memory — as the reference's does (`wav` is a numpy array,
+        text_wav_datamodule.py:253-266) — the segment start indices are drawn from the CPU generator exactly as
+        `get_random_segments` does (utils/segments.py:29-35: they depend on `mel_lengths` only) and the ground-truth crop is
+        cut on the host (`get_segments_numpy`, utils/segments.py:63-72).  Only the (B, segment*hop) crop and the (B,) draw
+        travel to the device instead of the whole (B, Tw) waveform (2 MB instead of 28 MB at B=32 x 864 frames); the device
+        recomputes the same start indices from the same fp32 draw.  Batches already on the device are returned unchanged."""
+        wav, ml = batch.get("wav"), batch.get("mel_lengths")
+        if wav is None or "wav_segment" in batch:
+            return batch
+        wav_on_host = isinstance(wav, np.ndarray) or (isinstance(wav, torch.Tensor) and not wav.is_cuda)
+        if not (wav_on_host and isinstance(ml, torch.Tensor) and not ml.is_cuda):
+            return batch
+        B = int(ml.shape[0])
+        seg = min(int(self.generator.segment_size), int(batch["mel"].shape[-1]))
+        rand = torch.rand(B)
+        start = (rand * (ml.to(torch.float32) - 4 - seg).clamp(min=0)).to(torch.long)
+        hop = int(self.hop_length)
+        n = seg * hop
+        pin = torch.cuda.is_available()
+        crop = torch.zeros((B, n), dtype=torch.float32, pin_memory=pin)
+        w = wav if isinstance(wav, np.ndarray) else wav.numpy()
+        if w.ndim == 3:
+            w = w[:, 0]
+        dst = crop.numpy()
+        for b, s in enumerate((start * hop).tolist()):
+            chunk = w[b, s: s + n]
+            dst[b, : chunk.shape[0]] = chunk
+        staged = {k: v for k, v in batch.items() if k != "wav"}
+        staged["wav_segment"] = crop
+        staged["seg_rand"] = rand.pin_memory() if pin else rand
+        return staged
+
+    @staticmethod
+    def batch_h2d_bytes(batch) -> int:
+        """Bytes a (staged) batch moves host -> device per step."""
+        return int(sum(v.numel() * v.element_size() if isinstance(v, torch.Tensor) else v.nbytes
+                       for v in batch.values() if isinstance(v, (torch.Tensor, np.ndarray)) and not (isinstance(v, torch.Tensor) and v.is_cuda)))
+
     def _process_batch(self, batch, vocoder_grad: bool = True):
         dev = self.device
         sids, lids = batch.get("sids"), batch.get("lids")
+        seg_rand = batch.get("seg_rand")
         gen_outputs = self.generator(
-            x=batch["x"].to(dev), x_lengths=batch["x_lengths"].to(dev), mel=batch["mel"].to(dev),
-            mel_lengths=batch["mel_lengths"].to(dev), pitches=batch["pitches"].to(dev), energies=batch["energies"].to(dev),
+            x=batch["x"].to(dev, non_blocking=True), x_lengths=batch["x_lengths"].to(dev, non_blocking=True),
+            mel=batch["mel"].to(dev, non_blocking=True), mel_lengths=batch["mel_lengths"].to(dev, non_blocking=True),
+            pitches=batch["pitches"].to(dev, non_blocking=True), energies=batch["energies"].to(dev, non_blocking=True),
             sids=sids.to(dev) if sids is not None else None, lids=lids.to(dev) if lids is not None else None,
+            **({"seg_rand": seg_rand.to(dev, non_blocking=True)} if seg_rand is not None else {}),
         )
+        if "wav_segment" in batch:  # host-staged crop (stage_batch)
+            gen_outputs["wav"] = batch["wav_segment"].to(dev, non_blocking=True).type_as(gen_outputs["wav_hat"])
+            return gen_outputs
         seg = gen_outputs["segment_size"] * self.hop_length
         wav = batch["wav"]
         wav = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
@@ -160,6 +206,8 @@ class BaseModule(nn.Module):
     def training_step(self, batch, batch_idx, **kwargs):
         """Reference base_lightning_module.py:86-130.  With `self.cuda_graph = True` the same step is captured once per
         batch shape and training phase and replayed afterwards (one graph launch instead of ~550 kernel launches)."""
+        if not self._capturing:
+            batch = self.stage_batch(batch)
         if self.cuda_graph and not self._capturing:
             if self._graphed is None:
                 from .graphed import GraphedTrainingStep

@@ -69,11 +69,12 @@ class OptiSpeechGenerator(nn.Module):
             x = x + self.lid_embed(lids.view(-1)).unsqueeze(1)
         return x
 
-    def forward(self, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids):
-        """Training forward (reference generator/__init__.py:72-192)."""
+    def forward(self, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
+        """Training forward (reference generator/__init__.py:72-192).  `seg_rand` (optional, (B,) in [0,1)) supplies the draw of
+        get_random_segments when the caller made it already (BaseModule.stage_batch cuts the waveform crop on the host)."""
         from .training import generator_training_forward
 
-        return generator_training_forward(self, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids)
+        return generator_training_forward(self, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=seg_rand)
 
     @torch.inference_mode()
     def synthesise(self, x, x_lengths, sids=None, lids=None, d_factor=1.0, p_factor=1.0, e_factor=1.0, durations=None):

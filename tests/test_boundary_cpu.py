@@ -96,7 +96,9 @@ def test_constructor_signatures_match_reference():
     assert names(TextEmbedding.__init__) == ["dim", "n_vocab", "dropout", "padding_idx", "max_source_positions"]
     assert names(VariancePredictor.__init__) == ["dim", "num_layers", "intermediate_dim", "kernel_size", "dropout", "conv_layer_class"]
     assert names(OptiSpeechGenerator.synthesise)[:7] == ["x", "x_lengths", "sids", "lids", "d_factor", "p_factor", "e_factor"]
-    assert names(OptiSpeechGenerator.forward) == ["x", "x_lengths", "mel", "mel_lengths", "pitches", "energies", "sids", "lids"]
+    # the reference's eight arguments, plus one optional trailing extra (the host-made segment draw, BaseModule.stage_batch)
+    assert names(OptiSpeechGenerator.forward) == ["x", "x_lengths", "mel", "mel_lengths", "pitches", "energies", "sids", "lids", "seg_rand"]
+    assert inspect.signature(OptiSpeechGenerator.forward).parameters["seg_rand"].default is None
 
 
 def test_reference_error_conventions():
@@ -163,3 +165,42 @@ def test_prior_table_matches_scipy_golden():
     fx = np.load(os.path.join(GOLD, "algorithms.npz"))
     for T, N in [(5, 3), (31, 9), (110, 24)]:
         assert np.abs(AlignmentModule._log_prior(T, N) - fx[f"prior_{T}_{N}"]).max() <= 1e-9
+
+
+def test_stage_batch_cuts_the_reference_crop_on_the_host(model):
+    """BaseModule.stage_batch = get_random_segments' start indices (CPU generator, utils/segments.py:29-35) + get_segments_numpy
+    (utils/segments.py:63-72) of the reference's _process_batch, for batches whose waveform is still in host memory."""
+    from oracle import model as O
+
+    g = torch.Generator().manual_seed(3)
+    B, Tm, hop = 4, 300, model.hop_length
+    ml = torch.tensor([300, 71, 68, 150])
+    wav = (torch.rand(B, Tm * hop, generator=g) * 2 - 1).numpy().astype(np.float32)
+    batch = dict(x=torch.zeros(B, 10, dtype=torch.long), x_lengths=torch.full((B,), 10), mel=torch.zeros(B, 100, Tm), mel_lengths=ml,
+                 pitches=torch.zeros(B, Tm), energies=torch.zeros(B, Tm), wav=wav, sids=None, lids=None)
+    torch.manual_seed(11)
+    staged = model.stage_batch(batch)
+    torch.manual_seed(11)
+    rand = torch.rand(B)   # the same CPU draw
+    assert "wav" not in staged and torch.equal(staged["seg_rand"], rand)
+    start = O.segment_starts((ml - 4).float(), 64, rand)
+    assert start[2] == 0 and (start <= (ml - 68).clamp(min=0)).all()
+    ref = O.crop_wav_segments(wav, start, 64, hop)
+    assert torch.equal(staged["wav_segment"], ref)
+    assert model.batch_h2d_bytes(staged) < model.batch_h2d_bytes(batch) - wav.nbytes + ref.numel() * 4 + 64
+    assert model.stage_batch(staged) is staged          # idempotent
+    as3d = dict(batch, wav=wav[:, None, :])             # (B, 1, Tw) layout of get_segments_numpy's input
+    torch.manual_seed(11)
+    assert torch.equal(model.stage_batch(as3d)["wav_segment"], ref)
+
+
+def test_transformer_config_instantiates_with_reference_layout():
+    from optispeech_b200.config import build_from_config
+    from optispeech_b200.model.generator.modules import Transformer
+
+    m = build_from_config("transformer")
+    assert isinstance(m.generator.encoder, Transformer) and isinstance(m.generator.decoder, Transformer)
+    fx = np.load(os.path.join(GOLD, "transformer.npz"))
+    ref = {str(k): tuple(int(v) for v in str(s).split(",") if v) for k, s in zip(fx["state_dict_keys"], fx["state_dict_shapes"])}
+    assert {k: tuple(v.shape) for k, v in m.generator.state_dict().items()} == ref
+    assert float(m.generator.encoder.transformer.embed[0].alpha) == 1.0

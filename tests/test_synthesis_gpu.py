@@ -118,6 +118,14 @@ def test_fused_convnext_block_kernel(cuda_device, C, I, T):
         blk.forward_cl(xc, mc, split=False)
         assert ops._lib.launch_count() - n0 == 1, "the non-split block must be a single kernel launch"
         three = blk.forward_cl(xc, mc, split=True)
+        # small problems split the intermediate dimension over CTAs (partial sums meet in L2): same result as one CTA per tile
+        lib = ops._lib.load()
+        lib.osb_debug_set_fused_nsplit(1)
+        try:
+            unsplit = blk.forward_cl(xc, mc, split=False)
+        finally:
+            lib.osb_debug_set_fused_nsplit(0)
+        assert (unsplit - fused).abs().max().item() <= 2e-5
     err_f = (fused.cpu() - ref).abs().max().item()
     err_3 = (three.cpu() - ref).abs().max().item()
     print(f"  C={C} T={T}: fused(fp16) max-abs err {err_f:.3e}; three-kernel fp16x3 {err_3:.3e}")

@@ -208,3 +208,41 @@ def test_transformer_training_forward_backward_matches_reference_golden(tf_gener
     errs.sort()
     print(f"  parameter-gradient norms: median err {errs[len(errs) // 2][0]:.3e}, worst {errs[-1][0]:.3e} ({errs[-1][1]})")
     assert errs[-1][0] <= 6e-2
+
+
+def test_transformer_training_step_eager_and_graphed(cuda_device):
+    """OptiSpeech.training_step with the Transformer configuration: train mode (all dropouts on), pre-training phase, eager and
+    CUDA-graph replay.  The encoder moves, the decoder (no gradient at the reference commit) does not."""
+    from optispeech_b200.factory import build_model, model_config_from_spec
+
+    spec = ModelSpec(backbone="transformer")
+    torch.manual_seed(1234)
+    model = build_model(model_config_from_spec(spec), train_args=dict(pretraining_steps=1000))
+    model.generator.load_state_dict(deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0))
+    model = model.to(cuda_device).train()
+    g = torch.Generator().manual_seed(3)
+    B, Tx, Tm = 2, 40, 170
+    xl = torch.tensor([40, 29])
+    x = torch.randint(1, 159, (B, Tx), generator=g) * (torch.arange(Tx)[None] < xl[:, None])
+    ml = torch.tensor([170, 123])
+    mm = torch.arange(Tm)[None] < ml[:, None]
+    batch = dict(x=x, x_lengths=xl, mel=torch.randn(B, spec.n_feats, Tm, generator=g) * mm[:, None, :], mel_lengths=ml,
+                 pitches=torch.randn(B, Tm, generator=g) * mm, energies=torch.randn(B, Tm, generator=g) * mm,
+                 wav=(torch.rand(B, Tm * spec.hop_length, generator=g) * 2 - 1).numpy().astype(np.float32), sids=None, lids=None)
+    enc = model.generator.encoder.transformer.encoders[0].self_attn.linear_q.weight
+    dec = model.generator.decoder.transformer.encoders[0].self_attn.linear_q.weight
+    enc0, dec0 = enc.detach().clone(), dec.detach().clone()
+    losses = []
+    for i in range(3):
+        model.training_step(batch, i)
+        losses.append(float(model.logged["total_loss/generator"]))
+    model.cuda_graph = True
+    for i in range(3, 9):   # 3 eager warm-up steps of the graphed wrapper, capture, 2 replays
+        model.training_step(batch, i)
+        losses.append(float(model.logged["total_loss/generator"]))
+    print("  losses:", [round(v, 3) for v in losses])
+    assert all(np.isfinite(v) for v in losses)
+    assert model._graphed is not None and model._graphed.replays >= 2
+    assert not torch.equal(enc0, enc.detach()) and torch.equal(dec0, dec.detach())
+    assert losses[-1] < losses[0]          # nine AdamW steps on one batch
+    model._graphed.release()

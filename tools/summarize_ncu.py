@@ -68,6 +68,25 @@ def full(path: str):
             except ValueError:
                 vals.append(v)
         print(f"| `{short(row[idx['Kernel Name']])}` | " + " | ".join(vals) + " |")
+    if "--json" in sys.argv:  # per C-ABI entry point: mean DRAM bytes (read + write) per launch -> bench.py roofline.traffic
+        import json
+
+        abi = {"gemm_nt_kernel": "osb_gemm", "convnext_fused_kernel": "osb_convnext_block_fwd", "gemm_wgrad_kernel": "osb_gemm_wgrad",
+               "mha_fwd_kernel": "osb_mha_fwd", "mha_bwd_kernel": "osb_mha_bwd"}
+        acc = {}
+        for row in r[2:]:
+            name = row[idx["Kernel Name"]]
+            for k, v in abi.items():
+                if k in name:
+                    mb = float(row[idx["dram__bytes_read.sum"]]) + float(row[idx["dram__bytes_write.sum"]])
+                    unit = r[1][idx["dram__bytes_read.sum"]]
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                    a = acc.setdefault(v, [0, 0.0])
+                    a[0] += 1
+                    a[1] += mb * scale
+        out_path = sys.argv[sys.argv.index("--json") + 1]
+        json.dump({k: {"launches_captured": n, "dram_bytes_per_launch": b / n, "source": path} for k, (n, b) in acc.items()},
+                  open(out_path, "w"), indent=1)
 
 
 if __name__ == "__main__":
