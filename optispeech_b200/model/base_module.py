@@ -133,8 +133,9 @@ class BaseModule(nn.Module):
         start = (rand * (ml.to(torch.float32) - 4 - seg).clamp(min=0)).to(torch.long)
         hop = int(self.hop_length)
         n = seg * hop
-        pin = torch.cuda.is_available()
-        crop = torch.zeros((B, n), dtype=torch.float32, pin_memory=pin)
+        slot = self._stage_slot(B, n)
+        crop, rand_buf = slot["crop"], slot["rand"]
+        rand_buf.copy_(rand)
         w = wav if isinstance(wav, np.ndarray) else wav.numpy()
         if w.ndim == 3:
             w = w[:, 0]
@@ -142,10 +143,35 @@ class BaseModule(nn.Module):
         for b, s in enumerate((start * hop).tolist()):
             chunk = w[b, s: s + n]
             dst[b, : chunk.shape[0]] = chunk
+            if chunk.shape[0] < n:
+                dst[b, chunk.shape[0]:] = 0.0
         staged = {k: v for k, v in batch.items() if k != "wav"}
         staged["wav_segment"] = crop
-        staged["seg_rand"] = rand.pin_memory() if pin else rand
+        staged["seg_rand"] = rand_buf
+        self._stage_live = slot
         return staged
+
+    def _stage_slot(self, B: int, n: int):
+        """Pinned staging buffers, a ring of four per (B, n): a slot is reused only after the step that copied from it has
+        passed the event recorded behind its copies (allocating pinned memory per step would cost more than the copy)."""
+        ring = self.__dict__.setdefault("_stage_rings", {}).setdefault((B, n), {"slots": [], "next": 0})
+        pin = torch.cuda.is_available()
+        if len(ring["slots"]) < 4:
+            slot = {"crop": torch.zeros((B, n), dtype=torch.float32, pin_memory=pin), "rand": torch.zeros(B, pin_memory=pin), "event": None}
+            ring["slots"].append(slot)
+            return slot
+        slot = ring["slots"][ring["next"] % 4]
+        ring["next"] += 1
+        if slot["event"] is not None:
+            slot["event"].synchronize()
+        return slot
+
+    def _stage_release(self):
+        slot = self.__dict__.pop("_stage_live", None)
+        if slot is not None and self.device.type == "cuda":
+            ev = slot["event"] or torch.cuda.Event()
+            ev.record()
+            slot["event"] = ev
 
     @staticmethod
     def batch_h2d_bytes(batch) -> int:
@@ -206,14 +232,18 @@ class BaseModule(nn.Module):
     def training_step(self, batch, batch_idx, **kwargs):
         """Reference base_lightning_module.py:86-130.  With `self.cuda_graph = True` the same step is captured once per
         batch shape and training phase and replayed afterwards (one graph launch instead of ~550 kernel launches)."""
-        if not self._capturing:
-            batch = self.stage_batch(batch)
-        if self.cuda_graph and not self._capturing:
-            if self._graphed is None:
-                from .graphed import GraphedTrainingStep
-                self._graphed = GraphedTrainingStep(self)
-            return self._graphed(batch, batch_idx)
-        return self._training_step_eager(batch, batch_idx, **kwargs)
+        if self._capturing:
+            return self._training_step_eager(batch, batch_idx, **kwargs)
+        batch = self.stage_batch(batch)
+        try:
+            if self.cuda_graph:
+                if self._graphed is None:
+                    from .graphed import GraphedTrainingStep
+                    self._graphed = GraphedTrainingStep(self)
+                return self._graphed(batch, batch_idx)
+            return self._training_step_eager(batch, batch_idx, **kwargs)
+        finally:
+            self._stage_release()
 
     def _training_step_eager(self, batch, batch_idx, **kwargs):
         acc = self.train_args.gradient_accumulate_batches
