@@ -50,7 +50,11 @@ struct GemmKParams {
   int w_lo_koff;    // K offset of the lo parts of W (split precision, batched weights stored [hi K | lo K])
   int w_batch;      // 1: slice index += batch (per-batch B operand)
   const long long* col_len;
+  long long* trace; // optional (developer): clock64 timeline of CTA (0,0), see tools/probe_gemm_trace.py
 };
+
+#define GT_TRACE(idx) \
+  do { if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.trace[(idx)] = clock64(); } while (0)
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -65,7 +69,10 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = cmin(6, (216 * 1024) / STAGE_BYTES);
   static constexpr int TMEM_COLS = pow2_cols(BN);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int VEC_BYTES = 4 * BN * 4;   // four per-column fp32 vectors (bias / gamma|ln_w / ln_b / dot_w) for the epilogue
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + VEC_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
   static_assert(NINST % 16 == 0 && NINST <= 256, "NINST");
   static_assert(STAGES >= 2, "stages");
 };
@@ -134,33 +141,218 @@ __device__ __forceinline__ void st_h16x32(__half* dst, const float (&v)[32]) {
   }
 }
 
-// fp16 destination row `row`, columns [n, n+32): plain (stride ldo) or split [hi ldo | lo ldo] (stride 2*ldo)
-__device__ __forceinline__ void store_h(const GemmKParams& p, void* base, long long row, int n, const float (&v)[32]) {
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative row I/O.  TMEM hands every thread one output ROW, but 32 threads storing 16 bytes each to 32 different
+// rows is 32 memory transactions per instruction (measured: 7-12 us of a ~10 us GEMM launch were these stores).  Each
+// epilogue warp therefore owns a small shared-memory slab (carved from the idle pipeline stages): a thread parks its
+// 32-column chunk there, and the warp moves the 32 x 32 block between the slab and global memory row-wise, 4 rows x 128 B
+// (fp32) or 8 rows x 64 B (fp16) per instruction.  All helpers are warp-collective; `nrows` = number of valid rows of
+// this warp (rows are consecutive, so validity is a prefix).
+// ------------------------------------------------------------------------------------------
+constexpr int SLAB_F32_LD = 36;                       // floats per slab row (32 + 4: conflict-free float4 columns)
+constexpr int SLAB_H16_LD = 40;                       // halves per slab row (fp16 view of the same slab)
+constexpr int SLAB_BYTES = 32 * SLAB_F32_LD * 4;      // 4608 B per warp
+
+__device__ __forceinline__ void warp_store_f32(float* sl, float* g, long long ld, int nrows, const float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  float* mine = sl + lane * SLAB_F32_LD;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, c = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rr;
+    if (r < nrows) *reinterpret_cast<float4*>(g + r * ld + c) = *reinterpret_cast<const float4*>(sl + r * SLAB_F32_LD + c);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void warp_load_f32(float* sl, const float* g, long long ld, int nrows, float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  const int rr = lane >> 3, c = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rr;
+    const float4 x = r < nrows ? *reinterpret_cast<const float4*>(g + r * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sl + r * SLAB_F32_LD + c) = x;
+  }
+  __syncwarp();
+  const float* mine = sl + lane * SLAB_F32_LD;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(mine + i);
+    v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void warp_store_h16(float* sl, __half* g, long long ld, int nrows, const float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  __half* sh = reinterpret_cast<__half*>(sl);
+  st_h16x32(sh + lane * SLAB_H16_LD, v);
+  __syncwarp();
+  const int rr = lane >> 2, c = (lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + rr;
+    if (r < nrows) *reinterpret_cast<uint4*>(g + r * ld + c) = *reinterpret_cast<const uint4*>(sh + r * SLAB_H16_LD + c);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void warp_load_h16(float* sl, const __half* g, long long ld, int nrows, float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  __half* sh = reinterpret_cast<__half*>(sl);
+  const int rr = lane >> 2, c = (lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + rr;
+    const uint4 x = r < nrows ? *reinterpret_cast<const uint4*>(g + r * ld + c) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sh + r * SLAB_H16_LD + c) = x;
+  }
+  __syncwarp();
+  ld_h16x32(sh + lane * SLAB_H16_LD, v);
+  __syncwarp();
+}
+
+// fp16 destination, this warp's rows, columns [n, n+32): plain (stride ldo) or split [hi ldo | lo ldo] (stride 2*ldo)
+__device__ __forceinline__ void warp_store_h(const GemmKParams& p, float* sl, void* base, long long row0, int n, int nrows,
+                                             const float (&v)[32]) {
   __half* hb = static_cast<__half*>(base);
   if (p.flags & OSB_FLAG_SPLIT_OUT) {
-    __half* r = hb + row * (2 * p.ldo);
-    st_h16x32(r + n, v);
-    st_h16x32_lo(r + p.ldo + n, v);
+    warp_store_h16(sl, hb + row0 * (2 * p.ldo) + n, 2 * p.ldo, nrows, v);
+    float r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = v[i] - __half2float(__float2half_rn(v[i]));   // residual after fp16 rounding
+    warp_store_h16(sl, hb + row0 * (2 * p.ldo) + p.ldo + n, 2 * p.ldo, nrows, r);
   } else {
-    st_h16x32(hb + row * p.ldo + n, v);
+    warp_store_h16(sl, hb + row0 * p.ldo + n, p.ldo, nrows, v);
   }
 }
 
+__device__ __forceinline__ void add_vec(const float* g, float (&v)[32]) {   // v[i] += g[i], 16-byte uniform loads
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(g + i));
+    v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+  }
+}
+__device__ __forceinline__ void ld_vec(const float* g, float (&w)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(g + i));
+    w[i] = x.x; w[i + 1] = x.y; w[i + 2] = x.z; w[i + 3] = x.w;
+  }
+}
+
+// Row-wise epilogue inputs (residual rows, saved activations): each warp bulk-loads ITS 32 rows x ncols into a warp-private
+// shared-memory tile with every load in flight at once (one exposed memory latency per tile instead of one per 32-column
+// chunk), then each thread reads its own row from shared memory.  Row pitch = ncols + 4 floats / ncols + 8 halves:
+// 16-byte row reads by 8 consecutive lanes hit 32 distinct banks.
+template <int NCOLS>
+__device__ __forceinline__ void warp_tile_load_f32(float* tile, const float* g, long long ld, int nrows) {
+  const int lane = threadIdx.x & 31;
+  constexpr int PER_ROW = NCOLS / 4;                // float4 per row
+  constexpr int ITERS = PER_ROW;                    // 32 rows * PER_ROW / 32 lanes
+  constexpr int BATCH = 8;                          // independent 16-byte loads in flight per lane
+  static_assert(ITERS % BATCH == 0, "tile width");
+#pragma unroll 1
+  for (int base = 0; base < ITERS; base += BATCH) {
+    float4 x[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = lane + 32 * (base + j);
+      const int r = i / PER_ROW, c = (i % PER_ROW) * 4;
+      x[j] = r < nrows ? *reinterpret_cast<const float4*>(g + r * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = lane + 32 * (base + j);
+      const int r = i / PER_ROW, c = (i % PER_ROW) * 4;
+      *reinterpret_cast<float4*>(tile + r * (NCOLS + 4) + c) = x[j];
+    }
+  }
+  __syncwarp();
+}
+template <int NCOLS>
+__device__ __forceinline__ void warp_tile_load_h16(__half* tile, const __half* g, long long ld, int nrows) {
+  const int lane = threadIdx.x & 31;
+  constexpr int PER_ROW = NCOLS / 8;                // uint4 (8 halves) per row
+  constexpr int ITERS = PER_ROW;
+  constexpr int BATCH = 8;
+  static_assert(ITERS % BATCH == 0, "tile width");
+#pragma unroll 1
+  for (int base = 0; base < ITERS; base += BATCH) {
+    uint4 x[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = lane + 32 * (base + j);
+      const int r = i / PER_ROW, c = (i % PER_ROW) * 8;
+      x[j] = r < nrows ? *reinterpret_cast<const uint4*>(g + r * ld + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      const int i = lane + 32 * (base + j);
+      const int r = i / PER_ROW, c = (i % PER_ROW) * 8;
+      *reinterpret_cast<uint4*>(tile + r * (NCOLS + 8) + c) = x[j];
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void ld_f32x32(const float* src, float (&v)[32]) {   // shared or global, 16-byte aligned
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(src + i);
+    v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+  }
+}
+__device__ __forceinline__ void add_f32x32(const float* src, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(src + i);
+    v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+  }
+}
+
+// `taddr`: this thread's TMEM lane, column 0.  `t`: this thread's row inside batch b; `tw`: first row of this warp;
+// `sl`: this warp's slab; `sv`: four per-column vectors of BN floats in shared memory (bias | gamma or ln_w | ln_b | dot_w,
+// preloaded while the main loop ran); `tile`: this warp's input-tile area.  Every branch is warp-uniform (the helpers are
+// warp-collective).  The accumulator is complete (and the pipeline memory free) once `acc_ready` has fired.
 template <int EPI, int BN>
-__device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t taddr, int b, int t, int n0) {
+__device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t taddr, int b, int t, int tw, int n0, float* sl,
+                                             const float* sv, uint8_t* tile, uint64_t* acc_ready) {
+  using Cfg = GemmCfg<BN>;
+  constexpr bool kTileF32 = 4 * SLAB_BYTES + 128 * (BN + 4) * 4 <= Cfg::PIPE_BYTES;
+  constexpr int TLD32 = BN + 4, TLD16 = BN + 8;
+  const int lane = threadIdx.x & 31;
   unsigned long long drop_seed = p.drop_seed;
   if (p.drop_p > 0.f && p.drop_seed_dev != nullptr) drop_seed += *p.drop_seed_dev;
   const bool valid = t < p.T;
+  const int nrows = p.T - tw < 0 ? 0 : (p.T - tw > 32 ? 32 : p.T - tw);
   const long long row = static_cast<long long>(b) * p.T + t;
+  const long long row0 = static_cast<long long>(b) * p.T + tw;
   const bool padded = (p.pad_mask != nullptr) && valid && (p.pad_mask[row] != 0);
+  const float* sv0 = sv;
+  const float* sv1 = sv + BN;
+  const float* sv2 = sv + 2 * BN;
+  const float* sv3 = sv + 3 * BN;
+  float* tile32 = reinterpret_cast<float*>(tile);
+  __half* tile16 = reinterpret_cast<__half*>(tile);
   float v[32];
+
+  mbar_wait(acc_ready, 0);
+  tc_fence_after_sync();
 
   if constexpr (EPI == OSB_EPI_ATTN_LOGP) {
     // the CTA owns whole rows of the (Tm x Tx) attention: distance, masked log-softmax and prior are thread-local
     const int ncols = p.N;                                              // true number of columns (<= BN)
     const int nvalid = static_cast<int>(p.col_len[b]) < ncols ? static_cast<int>(p.col_len[b]) : ncols;
     const float nf = valid ? p.row_stat[row] : 0.f;
-    const float* ne = p.bias + static_cast<long long>(b) * ncols;
+    const bool vec = (p.ldo & 3) == 0;
+    const int ntile = vec ? (ncols & ~31) : 0;                           // whole 32-column chunks of 16-byte aligned rows
+    const bool tiled = kTileF32 && ntile == BN;   // whole rows of BN columns (the usual case: Tx a multiple of 64)
+    if (tiled) warp_tile_load_f32<BN>(tile32, p.resid + row0 * p.ldo, p.ldo, nrows);
     // pass 1: score = -distance, parked back in TMEM; running max / sum of exp (online softmax: one pass for both)
     float mx = -INFINITY, sum = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -169,7 +361,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int n = c0 + i;
-        v[i] = n < nvalid ? -sqrtf(fmaxf(nf + __ldg(ne + n) - 2.f * v[i], 0.f)) : -INFINITY;
+        v[i] = n < nvalid ? -sqrtf(fmaxf(nf + sv0[n] - 2.f * v[i], 0.f)) : -INFINITY;
         cm = fmaxf(cm, v[i]);
       }
       if (cm > mx) {
@@ -188,75 +380,61 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
     tmem_st_wait();
     const float lse = mx + logf(sum);
     if (valid && p.out_dot != nullptr) p.out_dot[row] = lse;
-    // pass 2: log-probability + prior; 16-byte accesses when the row pitch allows (one thread = one row of the output)
-    const bool vec = (p.ldo & 3) == 0;
+    // pass 2: log-probability + prior
+    float pr[32];
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (c0 >= ncols) break;
       ld_chunk(taddr, c0, v);
-      if (valid) {
+      if (c0 + 32 <= ntile) {
+        if (tiled) ld_f32x32(tile32 + lane * TLD32 + c0, pr);
+        else warp_load_f32(sl, p.resid + row0 * p.ldo + c0, p.ldo, nrows, pr);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = c0 + i < nvalid ? (v[i] - lse) + pr[i] : -INFINITY;
+        warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
+      } else if (valid) {
         float* orow = static_cast<float*>(p.out) + row * p.ldo;
         const float* prow = p.resid + row * p.ldo;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < 32; ++i) {
           const int n = c0 + i;
-          if (vec && n + 3 < ncols) {
-            const float4 pr = *reinterpret_cast<const float4*>(prow + n);
-            float4 o;
-            o.x = (v[i] - lse) + pr.x;       // masked columns hold -inf already
-            o.y = (v[i + 1] - lse) + pr.y;
-            o.z = (v[i + 2] - lse) + pr.z;
-            o.w = (v[i + 3] - lse) + pr.w;
-            if (n >= nvalid) o.x = -INFINITY;
-            if (n + 1 >= nvalid) o.y = -INFINITY;
-            if (n + 2 >= nvalid) o.z = -INFINITY;
-            if (n + 3 >= nvalid) o.w = -INFINITY;
-            *reinterpret_cast<float4*>(orow + n) = o;
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n + u < ncols) orow[n + u] = n + u < nvalid ? (v[i + u] - lse) + prow[n + u] : -INFINITY;
-          }
+          if (n < ncols) orow[n] = n < nvalid ? (v[i] - lse) + prow[n] : -INFINITY;
         }
       }
     }
   } else if constexpr (EPI == OSB_EPI_AXPY) {
     const float alpha = valid ? p.row_stat[row] : 0.f;
+    float r[32];
+    if constexpr (kTileF32) warp_tile_load_f32<BN>(tile32, p.resid + row0 * p.ldo + n0, p.ldo, nrows);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
-      if (valid) {
-        const int n = n0 + c0;
-        const float* rp = p.resid + row * p.ldo + n;
+      const int n = n0 + c0;
+      if constexpr (kTileF32) ld_f32x32(tile32 + lane * TLD32 + c0, r);
+      else warp_load_f32(sl, p.resid + row0 * p.ldo + n, p.ldo, nrows, r);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-          v[i + 0] = fmaf(alpha, r4.x, v[i + 0]);
-          v[i + 1] = fmaf(alpha, r4.y, v[i + 1]);
-          v[i + 2] = fmaf(alpha, r4.z, v[i + 2]);
-          v[i + 3] = fmaf(alpha, r4.w, v[i + 3]);
-        }
-        st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
-      }
+      for (int i = 0; i < 32; ++i) v[i] = fmaf(alpha, r[i], v[i]);
+      warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_GELU_BWD || EPI == OSB_EPI_RELU_BWD) {
     float pre[32];
+    const float gate = p.drop_p > 0.f ? p.drop_inv_keep : 1.f;   // RELU_BWD: aux_in = relu output AFTER dropout (dropped = 0)
+    warp_tile_load_h16<BN>(tile16, static_cast<const __half*>(p.aux_in) + row0 * p.ldo + n0, p.ldo, nrows);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
-      if (valid) {
-        const int n = n0 + c0;
-        ld_h16x32(static_cast<const __half*>(p.aux_in) + row * p.ldo + n, pre);
+      const int n = n0 + c0;
+      ld_h16x32(tile16 + lane * TLD16 + c0, pre);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if constexpr (EPI == OSB_EPI_GELU_BWD) v[i] *= gelu_erf_grad(pre[i]);
-          else v[i] = pre[i] > 0.f ? v[i] * (p.drop_p > 0.f ? p.drop_inv_keep : 1.f) : 0.f;  // aux_in = relu output AFTER dropout:
-        }                                                                                      // dropped elements are 0 there
-        st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + n, v);
+      for (int i = 0; i < 32; ++i) {
+        if constexpr (EPI == OSB_EPI_GELU_BWD) v[i] *= gelu_erf_grad(pre[i]);
+        else v[i] = pre[i] > 0.f ? v[i] * gate : 0.f;
       }
+      warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_LN_BWD) {
     // acc = d(xhat); out = (acc - mean(acc) - xhat * mean(acc * xhat)) * rstd       (rows are independent)
     float xh[32];
     const float inv_n = 1.f / static_cast<float>(BN);
-    const __half* xrow = static_cast<const __half*>(p.aux_in) + (valid ? row : 0) * p.ldo;
+    warp_tile_load_h16<BN>(tile16, static_cast<const __half*>(p.aux_in) + row0 * p.ldo, p.ldo, nrows);
+    const __half* xrow = tile16 + lane * TLD16;
     float s1 = 0.f, s2 = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
@@ -274,13 +452,14 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       ld_h16x32(xrow + c0, xh);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = (v[i] - m1 - xh[i] * m2) * rstd;
-      if (valid) st_f32x32(static_cast<float*>(p.out) + row * p.ldo + c0, v);
+      warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_RELU_LN_BWD) {
     // recompute the forward LN statistics of r = relu(conv) (fp16-saved), then LN backward and the ReLU gate
     float r[32];
     const float inv_n = 1.f / static_cast<float>(BN);
-    const __half* rrow = static_cast<const __half*>(p.aux_in) + (valid ? row : 0) * p.ldo;
+    warp_tile_load_h16<BN>(tile16, static_cast<const __half*>(p.aux_in) + row0 * p.ldo, p.ldo, nrows);
+    const __half* rrow = tile16 + lane * TLD16;
     float s = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_h16x32(rrow + c0, r);
@@ -304,10 +483,12 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
       }
-      if (valid && (p.flags & OSB_FLAG_OUT_H16)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
+      if (p.flags & OSB_FLAG_OUT_H16) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + c0, p.ldo, nrows, v);
+      float lw[32];
+      ld_f32x32(sv1 + c0, lw);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float g = v[i] * __ldg(p.ln_w + c0 + i);
+        const float g = v[i] * lw[i];
         s1 += g;
         s2 = fmaf(g, (r[i] - mean) * rstd, s2);
       }
@@ -320,24 +501,24 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
       }
+      float lw[32];
+      ld_f32x32(sv1 + c0, lw);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float g = v[i] * __ldg(p.ln_w + c0 + i);
+        const float g = v[i] * lw[i];
         const float d = (g - m1 - (r[i] - mean) * rstd * m2) * rstd;
         v[i] = r[i] > 0.f ? d : 0.f;
       }
-      if (valid) st_h16x32(static_cast<__half*>(p.out) + row * p.ldo + c0, v);
+      warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_BIAS || EPI == OSB_EPI_GELU || EPI == OSB_EPI_RELU || EPI == OSB_EPI_RESID) {
     const float keep = ((p.flags & OSB_FLAG_KEEPMASK) && padded) ? 0.f : 1.f;
     const float rs = (EPI == OSB_EPI_RESID && p.row_scale != nullptr) ? p.row_scale[b] : 1.f;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      ld_chunk(taddr, c0, v);
+    if constexpr (EPI == OSB_EPI_RESID && kTileF32) warp_tile_load_f32<BN>(tile32, p.resid + row0 * p.ldo + n0, p.ldo, nrows);
+    // the TMEM load of chunk c+1 is in flight while chunk c is processed (two register buffers)
+    auto process = [&](int c0) {
       const int n = n0 + c0;
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + n + i);
-      }
+      add_f32x32(sv0 + c0, v);                      // bias (zeros when absent)
       if constexpr (EPI == OSB_EPI_BIAS) {
         if (p.flags & OSB_FLAG_CLIP) {
 #pragma unroll
@@ -349,15 +530,13 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
-        if (valid) {
-          if (!(p.flags & OSB_FLAG_NO_F32)) st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
-          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, n, v);
-        }
+        if (!(p.flags & OSB_FLAG_NO_F32)) warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
+        if (p.flags & OSB_FLAG_OUT_H16) warp_store_h(p, sl, p.aux, row0, n, nrows, v);
       } else if constexpr (EPI == OSB_EPI_GELU) {
-        if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
+        if (p.flags & OSB_FLAG_SAVE_PRE) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + n, p.ldo, nrows, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        if (valid) store_h(p, p.out, row, n, v);
+        warp_store_h(p, sl, p.out, row0, n, nrows, v);
       } else if constexpr (EPI == OSB_EPI_RELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -366,53 +545,84 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
         }
-        if (valid) store_h(p, p.out, row, n, v);
+        warp_store_h(p, sl, p.out, row0, n, nrows, v);
       } else {  // RESID
-        if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + n, v);
+        if (p.flags & OSB_FLAG_SAVE_PRE) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + n, p.ldo, nrows, v);
         if (p.drop_p > 0.f) {  // element dropout on the branch before the residual add (EncoderLayer, encoder_layer.py:103,111)
           const unsigned long long dbase = static_cast<unsigned long long>(row) * p.N + n;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
         }
-        if (valid) {
-          const float* rp = p.resid + row * p.ldo + n;
+        float r[32];
+        if constexpr (kTileF32) ld_f32x32(tile32 + lane * TLD32 + c0, r);
+        else warp_load_f32(sl, p.resid + row0 * p.ldo + n, p.ldo, nrows, r);
+        float gm[32];
+        ld_f32x32(sv1 + c0, gm);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
-            v[i + 0] = (r4.x + __ldg(p.gamma + n + i + 0) * v[i + 0] * rs) * keep;
-            v[i + 1] = (r4.y + __ldg(p.gamma + n + i + 1) * v[i + 1] * rs) * keep;
-            v[i + 2] = (r4.z + __ldg(p.gamma + n + i + 2) * v[i + 2] * rs) * keep;
-            v[i + 3] = (r4.w + __ldg(p.gamma + n + i + 3) * v[i + 3] * rs) * keep;
-          }
-          st_f32x32(static_cast<float*>(p.out) + row * p.ldo + n, v);
-          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, n, v);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = (r[i] + gm[i] * v[i] * rs) * keep;
+        warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
+        if (p.flags & OSB_FLAG_OUT_H16) warp_store_h(p, sl, p.aux, row0, n, nrows, v);
+      }
+    };
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+      tmem_ld_wait_regs(ra);
+      if (c0 + 32 < BN) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), rb);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+      process(c0);
+      if (c0 + 32 < BN) {
+        tmem_ld_wait_regs(rb);
+        if (c0 + 64 < BN) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 64), ra);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+        process(c0 + 32);
       }
     }
   } else {  // row-wise LayerNorm epilogues; the CTA owns the whole row (BN == N, n0 == 0)
     constexpr bool kRelu = (EPI == OSB_EPI_RELU_LN);
     const float inv_n = 1.f / static_cast<float>(BN);
+    // TMEM reads are 64 B/clk per SM (a 128 x 256 fp32 accumulator takes >= 2048 cycles per sweep): when the row fits, the
+    // pre-LN values are parked ONCE in this thread's row of the shared-memory tile and the later sweeps read them from there.
+    float* myrow = tile32 + lane * TLD32;
     // pass 1: mean
     float s = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       ld_chunk(taddr, c0, v);
+      add_f32x32(sv0 + c0, v);
+      if (kRelu) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-        if (kRelu) x = fmaxf(x, 0.f);
-        s += x;
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s += v[i];
+      if constexpr (kTileF32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(myrow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     }
     const float mean = s * inv_n;
+    auto load_pre = [&](int c0) {   // pre-LN values of this row, columns [c0, c0 + 32)
+      if constexpr (kTileF32) {
+        ld_f32x32(myrow + c0, v);
+      } else {
+        ld_chunk(taddr, c0, v);
+        add_f32x32(sv0 + c0, v);
+        if (kRelu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+      }
+    };
     // pass 2: biased variance around the mean (what at::layer_norm computes)
     float q = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      ld_chunk(taddr, c0, v);
+      load_pre(c0);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-        if (kRelu) x = fmaxf(x, 0.f);
-        const float d = x - mean;
+        const float d = v[i] - mean;
         q += d * d;
       }
     }
@@ -420,17 +630,14 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
     // pass 3: normalise, affine, store
     float dot = 0.f;
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      ld_chunk(taddr, c0, v);
+      load_pre(c0);
+      if (p.flags & OSB_FLAG_SAVE_PRE) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + c0, p.ldo, nrows, v);
+      {
+        float lw[32], lb[32];
+        ld_f32x32(sv1 + c0, lw);
+        ld_f32x32(sv2 + c0, lb);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-        if (kRelu) x = fmaxf(x, 0.f);
-        v[i] = x;
-      }
-      if (valid && (p.flags & OSB_FLAG_SAVE_PRE)) st_h16x32(static_cast<__half*>(p.aux) + row * p.ldo + c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = (v[i] - mean) * rstd * __ldg(p.ln_w + c0 + i) + __ldg(p.ln_b + c0 + i);
+        for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd * lw[i] + lb[i];
       }
       if (kRelu && p.drop_p > 0.f) {
         const unsigned long long base = static_cast<unsigned long long>(valid ? row : 0) * BN + c0;
@@ -438,16 +645,16 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, base + i, p.drop_p, p.drop_inv_keep);
       }
       if (p.flags & OSB_FLAG_DOT) {
+        float dw[32];
+        ld_f32x32(sv3 + c0, dw);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dot += v[i] * __ldg(p.dot_w + c0 + i);
+        for (int i = 0; i < 32; ++i) dot += v[i] * dw[i];
       }
-      if (valid) {
-        if constexpr (EPI == OSB_EPI_RELU_LN) {
-          if (p.out != nullptr) store_h(p, p.out, row, c0, v);
-        } else {
-          st_f32x32(static_cast<float*>(p.out) + row * p.ldo + c0, v);
-          if (p.flags & OSB_FLAG_OUT_H16) store_h(p, p.aux, row, c0, v);
-        }
+      if constexpr (EPI == OSB_EPI_RELU_LN) {
+        if (p.out != nullptr) warp_store_h(p, sl, p.out, row0, c0, nrows, v);
+      } else {
+        warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
+        if (p.flags & OSB_FLAG_OUT_H16) warp_store_h(p, sl, p.aux, row0, c0, nrows, v);
       }
     }
     if ((p.flags & OSB_FLAG_DOT) && valid) p.out_dot[row] = padded ? 0.f : (dot + (p.dot_b != nullptr ? __ldg(p.dot_b) : 0.f));
@@ -470,6 +677,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) GT_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -486,6 +694,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GT_TRACE(1);
 
   const int b = blockIdx.x / p.m_tiles;
   const int t0 = (blockIdx.x % p.m_tiles) * BM;
@@ -516,6 +725,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < Cfg::NCHUNK; ++c)
           tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], w_k, n0 + c * Cfg::NINST, w_slice);
+        if (it == 0) GT_TRACE(2);
+        if (it == iters - 1) GT_TRACE(3);
       }
     }
   } else if (warp == 1) {
@@ -527,6 +738,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (it / Cfg::STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after_sync();
+      if (it == 0 && lane == 0) GT_TRACE(4);
       if (elect_one()) {
         const uint64_t da0 = d0 + static_cast<uint64_t>((s * Cfg::STAGE_BYTES) >> 4);
         const uint64_t db0 = da0 + static_cast<uint64_t>(Cfg::A_BYTES >> 4);
@@ -545,17 +757,41 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (elect_one()) umma_commit(tmem_full_bar);  // accumulator complete
     __syncwarp();
+    if (lane == 0) GT_TRACE(5);
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
+    // While the main loop runs, the (otherwise idle) epilogue warps stage the per-column vectors in shared memory:
+    // [0] bias (ATTN: |e_n|^2 of this batch), [1] gamma / ln_w, [2] ln_b, [3] dot_w — zeros where absent.
+    float* sv = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + 256);
+    {
+      const int et = threadIdx.x - 64;   // 0..127
+      const float* v0 = p.bias;
+      int lim0 = BN;
+      if constexpr (EPI == OSB_EPI_ATTN_LOGP) { v0 = p.bias + static_cast<long long>(b) * p.N; lim0 = p.N; }
+      const float* v1 = (EPI == OSB_EPI_RESID) ? p.gamma : p.ln_w;
+      for (int i = et; i < BN; i += 128) {
+        sv[i] = (v0 != nullptr && i < lim0) ? __ldg(v0 + (EPI == OSB_EPI_ATTN_LOGP ? 0 : n0) + i) : 0.f;
+        sv[BN + i] = v1 != nullptr ? __ldg(v1 + n0 + i) : 0.f;
+        sv[2 * BN + i] = p.ln_b != nullptr ? __ldg(p.ln_b + n0 + i) : 0.f;
+        sv[3 * BN + i] = p.dot_w != nullptr ? __ldg(p.dot_w + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+    }
+    if (warp == 2 && lane == 0) GT_TRACE(6);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    run_epilogue<EPI, BN>(p, taddr, b, t0 + q * 32 + lane, n0);
+    // once the accumulator is complete every TMA stage has been consumed: the pipeline memory then holds the per-warp slabs
+    // and input tiles (run_epilogue waits on tmem_full_bar before touching either)
+    float* slab = reinterpret_cast<float*>(smem + q * SLAB_BYTES);
+    constexpr int TILE_WARP_BYTES = (Cfg::PIPE_BYTES - 4 * SLAB_BYTES) / 4 / 16 * 16;
+    uint8_t* tile = smem + 4 * SLAB_BYTES + q * TILE_WARP_BYTES;
+    run_epilogue<EPI, BN>(p, taddr, b, t0 + q * 32 + lane, t0 + q * 32, n0, slab, sv, tile, tmem_full_bar);
+    if (warp == 2 && lane == 0) GT_TRACE(7);
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) GT_TRACE(8);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -798,6 +1034,10 @@ int make_tmap_3d(CUtensorMap* out, const void* base, TmaDtype dt, uint64_t d0, u
 // ------------------------------------------------------------------------------------------
 using namespace osb;
 
+static long long* g_gemm_trace = nullptr;
+/* developer hook (not in the public header): device buffer of 16 int64 receiving a clock64 timeline of CTA (0,0) */
+extern "C" void osb_debug_set_gemm_trace(long long* buf) { g_gemm_trace = buf; }
+
 extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   OSB_REQUIRE(d != nullptr && d->a != nullptr && d->w != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->taps > 0, OSB_ERR_SHAPE);
@@ -843,10 +1083,17 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.w_lo_slice = w_batched ? 0 : d->taps;
   p.w_lo_koff = w_batched ? d->K : 0;
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
+  p.trace = g_gemm_trace;
   p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed; p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(d->dropout_seed_dev);
   p.drop_inv_keep = d->dropout_p > 0.f && d->dropout_p < 1.f ? 1.f / (1.f - d->dropout_p) : 0.f;
   OSB_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, OSB_ERR_ARG);
 
+  // the epilogues read per-column vectors and move row chunks with 16-byte accesses
+  for (const void* q : {static_cast<const void*>(d->gamma), static_cast<const void*>(d->ln_w), static_cast<const void*>(d->ln_b),
+                        static_cast<const void*>(d->dot_w), static_cast<const void*>(d->out), static_cast<const void*>(d->aux_h16),
+                        static_cast<const void*>(d->aux_in_h16), d->epi == OSB_EPI_ATTN_LOGP ? nullptr : static_cast<const void*>(d->bias),
+                        d->epi == OSB_EPI_ATTN_LOGP ? nullptr : static_cast<const void*>(d->resid)})
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return OSB_ERR_ALIGN;
   if ((d->flags & (OSB_FLAG_OUT_H16 | OSB_FLAG_SAVE_PRE)) && d->aux_h16 == nullptr) return OSB_ERR_ARG;
   if ((d->flags & OSB_FLAG_KEEPMASK) && d->pad_mask == nullptr) return OSB_ERR_ARG;
 
