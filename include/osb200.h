@@ -94,7 +94,9 @@ enum {
   OSB_FLAG_SPLIT_IN = 32, /* a is (B,T,[hi K | lo K]) with lda >= 2K; w is (2, taps, N, ldw): [0] = hi parts, [1] = lo parts */
   OSB_FLAG_SPLIT_OUT = 64, /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                */
   OSB_FLAG_RELU = 128,     /* EPI_BIAS only: out = relu(acc + bias)                                                */
-  OSB_FLAG_NO_F32 = 256    /* EPI_BIAS with OUT_H16: write only the fp16 copy (out may be NULL)                    */
+  OSB_FLAG_NO_F32 = 256,   /* EPI_BIAS with OUT_H16: write only the fp16 copy (out may be NULL)                    */
+  OSB_FLAG_COLSUM = 512    /* GELU_BWD / RELU_BWD / RELU_LN_BWD: out_colsum[n] += sum_rows out_h16[row, n] — the bias
+                              gradient of the layer this dgrad belongs to, taken from the tile while it is on chip   */
 };
 
 typedef struct osb_gemm_desc {
@@ -134,6 +136,7 @@ typedef struct osb_gemm_desc {
   /* per-batch B operand (batched matmul): w is (B, N, ldw) — with SPLIT_IN (B, N, [hi K | lo K]) — and taps == 1 */
   int32_t w_batched;
   const int64_t* col_len; /* ATTN_LOGP: (B) number of valid columns (text length)                    */
+  float* out_colsum;      /* COLSUM: (N) fp32, accumulated with atomics (caller zeroes it)            */
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);

@@ -16,7 +16,7 @@ OSB_OK = 0
 # osb_epilogue
 EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD, EPI_ATTN_LOGP, EPI_AXPY = range(12)
 # flags
-FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU, FLAG_NO_F32 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU, FLAG_NO_F32, FLAG_COLSUM = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 
 class GemmDesc(C.Structure):
@@ -56,6 +56,7 @@ class GemmDesc(C.Structure):
         ("dropout_seed_dev", C.c_void_p),
         ("w_batched", C.c_int32),
         ("col_len", C.c_void_p),
+        ("out_colsum", C.c_void_p),
     ]
 
 

@@ -113,10 +113,10 @@ class ConvNeXtBlockFn(Function):
         dout = dout.contiguous()
         dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
         # pwconv2: dgrad (with the GELU derivative fused) and wgrad
-        dpre, _, _ = ops.gemm(dyg, pack_kn(w2), epi=ops.EPI_GELU_BWD, aux_in=pre)
+        db1 = ops.zeros((I,), x)                                           # bias gradient: column sums taken in the dgrad epilogue
+        dpre, _, _ = ops.gemm(dyg, pack_kn(w2), epi=ops.EPI_GELU_BWD, aux_in=pre, colsum=db1)
         dw2 = ops.zeros((1, C, I), x)
         ops.gemm_wgrad(dyg, h, dw2)
-        db1 = ops.colsum_h16(dpre)
         # pwconv1: dgrad (LayerNorm backward fused: the CTA owns whole rows) and wgrad
         dd, _, _ = ops.gemm(dpre, pack_kn(w1f), epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd)
         dw1f = ops.zeros((1, I, C), x)
@@ -173,16 +173,17 @@ class VariancePredictorFn(Function):
                                                                  ctx.drop_p, ctx.drop_seed + L - 1)
         grads[4 * (L - 1) + 2], grads[4 * (L - 1) + 3] = dln_w, dln_b
         dx = None
+        grads[4 * (L - 1) + 1] = ops.colsum_h16(g)
         for l in range(L - 1, -1, -1):
             cw = layer_params[4 * l]
             N, Cin, _ = cw.shape
             grads[4 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
-            grads[4 * l + 1] = ops.colsum_h16(g)
             if l > 0:
                 lw_prev = layer_params[4 * (l - 1) + 2]
+                grads[4 * (l - 1) + 1] = ops.zeros((Cin,), g)             # conv bias gradient of layer l-1, summed in the epilogue
                 g_prev, gy, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, pad=k - 1 - pad,
                                          aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps, dropout_p=ctx.drop_p,
-                                         dropout_seed=ctx.drop_seed + l - 1)
+                                         dropout_seed=ctx.drop_seed + l - 1, colsum=grads[4 * (l - 1) + 1])
                 grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3] = ops.ln_param_grad(gy, pres[l - 1], lw_prev, eps)
                 g = g_prev
             elif ctx.x_needs_grad:
@@ -226,14 +227,16 @@ class ConvStackFn(Function):
         grads: List[Optional[torch.Tensor]] = [None] * (2 * L)
         g = ops.to_h16(dout.contiguous())
         dx = None
+        grads[2 * (L - 1) + 1] = ops.colsum_h16(g)
         for l in range(L - 1, -1, -1):
             cw = params[2 * l]
             N, Cin, k = cw.shape
             pad = (k - 1) // 2
             grads[2 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
-            grads[2 * l + 1] = ops.colsum_h16(g)
             if l > 0:
-                g, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l])
+                grads[2 * (l - 1) + 1] = ops.zeros((Cin,), g)             # bias gradient of layer l-1, summed in the epilogue
+                g, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l],
+                                   colsum=grads[2 * (l - 1) + 1])
             elif ctx.x_needs_grad:
                 dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
         return (dx, None, *grads)
@@ -409,10 +412,10 @@ class TransformerLayerFn(Function):
         dw2 = ops.zeros((1, D, U), x)
         ops.gemm_wgrad(g2, h, dw2)
         db2 = ops.colsum_h16(g2)
-        dh, _, _ = ops.gemm(g2, pack_kn(w2[:, :, 0]), epi=ops.EPI_RELU_BWD, aux_in=h, dropout_p=p_ffn, dropout_seed=seed + 2)
+        db1 = ops.zeros((U,), x)
+        dh, _, _ = ops.gemm(g2, pack_kn(w2[:, :, 0]), epi=ops.EPI_RELU_BWD, aux_in=h, dropout_p=p_ffn, dropout_seed=seed + 2, colsum=db1)
         dw1 = ops.zeros((1, U, D), x)
         ops.gemm_wgrad(dh, xn2, dw1)
-        db1 = ops.colsum_h16(dh)
         dxn2, _, _ = ops.gemm(dh, pack_kn(w1[:, :, 0]), epi=ops.EPI_BIAS)
         dln2, dn2w, dn2b = ops.layernorm_bwd(dxn2, x1, n2w, eps)
         dx1 = dout + dln2

@@ -35,6 +35,28 @@ __device__ __forceinline__ void atomic_add4(float* dst, const float4& v) {
 }
 __device__ __forceinline__ float sum4(const float4& v) { return (v.x + v.y) + (v.z + v.w); }
 
+// Per-column accumulators held by every warp of the block (column c = v*128 + lane*4) -> one vector reduction per column
+// group and block: the warps' partials are summed through shared memory first, so a launch issues blocks x C/4 reds
+// instead of warps x C scalar atomics on the same C addresses.  Block-collective (every warp calls it, also with zeros).
+template <int VPL>
+__device__ __forceinline__ void block_flush4(const float4 (&acc)[VPL], float* dst, float4* sred) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) sred[(w * VPL + v) * 32 + lane] = acc[v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < VPL * 32; i += WPB * 32) {
+    float4 t = sred[i];
+#pragma unroll
+    for (int ww = 1; ww < WPB; ++ww) {
+      const float4 u = sred[ww * VPL * 32 + i];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* d = dst + (i >> 5) * 128 + (i & 31) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  }
+  __syncthreads();
+}
+
 // rows [r0, r1) of this warp: contiguous slab so that neighbouring warps touch neighbouring memory
 __device__ __forceinline__ void warp_rows(long long rows, long long& r0, long long& r1) {
   const long long nw = static_cast<long long>(gridDim.x) * WPB;
@@ -89,13 +111,9 @@ resid_bwd_prep_kernel(const float* __restrict__ dout, const __half* __restrict__
       sth4(dyg + r * C + c, d.x, d.y, d.z, d.w);
     }
   }
-  if (r0 < r1) {
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      atomic_add4(dgamma + v * 128 + lane * 4, ag[v]);
-      atomic_add4(db2 + v * 128 + lane * 4, ab[v]);
-    }
-  }
+  __shared__ float4 sred[WPB * VPL * 32];
+  block_flush4<VPL>(ag, dgamma, sred);
+  block_flush4<VPL>(ab, db2, sred);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -294,13 +312,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       *reinterpret_cast<float4*>(dx + r * C + v * 128 + lane * 4) = o;
     }
   }
-  if (r0 < r1) {
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      atomic_add4(dw + v * 128 + lane * 4, aw[v]);
-      atomic_add4(db + v * 128 + lane * 4, ab[v]);
-    }
-  }
+  __shared__ float4 sred[WPB * VPL * 32];
+  block_flush4<VPL>(aw, dw, sred);
+  block_flush4<VPL>(ab, db, sred);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -392,15 +406,12 @@ predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restric
       }
     }
   }
-  if (r0 < r1) {
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c = v * 128 + lane * 4;
-      atomic_add4(dln_w + c, a_lnw[v]);
-      atomic_add4(dln_b + c, a_lnb[v]);
-      if (tail) atomic_add4(dlin_w + c, a_lin[v]);
-    }
-    if (tail && lane == 0) atomicAdd(dlin_b, a_linb);
+  __shared__ float4 sred[WPB * VPL * 32];
+  block_flush4<VPL>(a_lnw, dln_w, sred);
+  block_flush4<VPL>(a_lnb, dln_b, sred);
+  if (tail) {
+    block_flush4<VPL>(a_lin, dlin_w, sred);
+    if (lane == 0 && r0 < r1) atomicAdd(dlin_b, a_linb);
   }
 }
 
@@ -481,7 +492,7 @@ extern "C" int osb_resid_bwd_prep(const float* dout, const void* z_h16, const fl
                                   int32_t C, void* stream) {
   OSB_REQUIRE(dout && z_h16 && gamma && dyg_h16 && dgamma && db2, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && T > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
-  const int grid = grid_for_rows(rows, 16);
+  const int grid = grid_for_rows(rows, 6);   // short per-warp row runs: the row loop is a latency chain, parallelism hides it
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (resid_bwd_prep_kernel<VPL><<<grid, WPB * 32, 0, s>>>(dout, static_cast<const __half*>(z_h16), gamma, pad_mask,
                                                                           row_scale, static_cast<__half*>(dyg_h16), dgamma, db2,
@@ -530,7 +541,7 @@ extern "C" int osb_layernorm_bwd(const float* dy, const float* x, const float* w
                                  int32_t C, float eps, void* stream) {
   OSB_REQUIRE(dy && x && w && dx && dw && db, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
-  const int grid = grid_for_rows(rows, 16);
+  const int grid = grid_for_rows(rows, 6);   // short per-warp row runs: the row loop is a latency chain, parallelism hides it
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (layernorm_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(dy, x, w, dx, dw, db, rows, eps)));
   count_launch();
@@ -545,7 +556,7 @@ extern "C" int osb_predictor_tail_bwd(const float* d_out, const uint8_t* pad_mas
   OSB_REQUIRE(rows > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
   OSB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, OSB_ERR_ARG);
   const float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 0.f;
-  const int grid = grid_for_rows(rows, 16);
+  const int grid = grid_for_rows(rows, 6);   // short per-warp row runs: the row loop is a latency chain, parallelism hides it
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         d_out, nullptr, pad_mask, static_cast<const __half*>(r_h16), ln_w, ln_b, lin_w,
@@ -559,7 +570,7 @@ extern "C" int osb_ln_param_grad(const void* gy_h16, const void* r_h16, const fl
                                  int32_t C, float eps, void* stream) {
   OSB_REQUIRE(gy_h16 && r_h16 && ln_w && dln_w && dln_b, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && C % 128 == 0 && C <= 512, OSB_ERR_SHAPE);
-  const int grid = grid_for_rows(rows, 16);
+  const int grid = grid_for_rows(rows, 6);   // short per-warp row runs: the row loop is a latency chain, parallelism hides it
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSB_VPL_SWITCH(C, (predictor_ln_bwd_kernel<VPL><<<grid, WPB * 32, 0, s>>>(
                         nullptr, static_cast<const __half*>(gy_h16), nullptr, static_cast<const __half*>(r_h16), ln_w, nullptr,

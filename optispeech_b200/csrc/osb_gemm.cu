@@ -50,6 +50,7 @@ struct GemmKParams {
   int w_lo_koff;    // K offset of the lo parts of W (split precision, batched weights stored [hi K | lo K])
   int w_batch;      // 1: slice index += batch (per-batch B operand)
   const long long* col_len;
+  float* colsum;    // COLSUM: (N) column sums of the fp16 output
   long long* trace; // optional (developer): clock64 timeline of CTA (0,0), see tools/probe_gemm_trace.py
 };
 
@@ -213,6 +214,24 @@ __device__ __forceinline__ void warp_load_h16(float* sl, const __half* g, long l
   }
   __syncwarp();
   ld_h16x32(sh + lane * SLAB_H16_LD, v);
+  __syncwarp();
+}
+
+// warp_store_h16 that also adds the column sums of the (fp16-rounded, valid) rows into colsum[0..32): lane l owns column l.
+__device__ __forceinline__ void warp_store_h16_colsum(float* sl, __half* g, long long ld, int nrows, const float (&v)[32], float* colsum) {
+  const int lane = threadIdx.x & 31;
+  __half* sh = reinterpret_cast<__half*>(sl);
+  st_h16x32(sh + lane * SLAB_H16_LD, v);
+  __syncwarp();
+  const int rr = lane >> 2, c = (lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + rr;
+    if (r < nrows) *reinterpret_cast<uint4*>(g + r * ld + c) = *reinterpret_cast<const uint4*>(sh + r * SLAB_H16_LD + c);
+  }
+  float s = 0.f;
+  for (int r = 0; r < nrows; ++r) s += __half2float(sh[r * SLAB_H16_LD + lane]);
+  if (nrows > 0) atomicAdd(colsum + lane, s);
   __syncwarp();
 }
 
@@ -427,7 +446,8 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         if constexpr (EPI == OSB_EPI_GELU_BWD) v[i] *= gelu_erf_grad(pre[i]);
         else v[i] = pre[i] > 0.f ? v[i] * gate : 0.f;
       }
-      warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
+      if (p.colsum != nullptr) warp_store_h16_colsum(sl, static_cast<__half*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v, p.colsum + n);
+      else warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_LN_BWD) {
     // acc = d(xhat); out = (acc - mean(acc) - xhat * mean(acc * xhat)) * rstd       (rows are independent)
@@ -509,7 +529,8 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         const float d = (g - m1 - (r[i] - mean) * rstd * m2) * rstd;
         v[i] = r[i] > 0.f ? d : 0.f;
       }
-      warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
+      if (p.colsum != nullptr) warp_store_h16_colsum(sl, static_cast<__half*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v, p.colsum + c0);
+      else warp_store_h16(sl, static_cast<__half*>(p.out) + row0 * p.ldo + c0, p.ldo, nrows, v);
     }
   } else if constexpr (EPI == OSB_EPI_BIAS || EPI == OSB_EPI_GELU || EPI == OSB_EPI_RELU || EPI == OSB_EPI_RESID) {
     const float keep = ((p.flags & OSB_FLAG_KEEPMASK) && padded) ? 0.f : 1.f;
@@ -1083,6 +1104,9 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.w_lo_slice = w_batched ? 0 : d->taps;
   p.w_lo_koff = w_batched ? d->K : 0;
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
+  p.colsum = (d->flags & OSB_FLAG_COLSUM) ? d->out_colsum : nullptr;
+  if ((d->flags & OSB_FLAG_COLSUM) && (d->out_colsum == nullptr || !(d->epi == OSB_EPI_GELU_BWD || d->epi == OSB_EPI_RELU_BWD ||
+                                                                     d->epi == OSB_EPI_RELU_LN_BWD))) return OSB_ERR_ARG;
   p.trace = g_gemm_trace;
   p.drop_p = d->dropout_p; p.drop_seed = d->dropout_seed; p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(d->dropout_seed_dev);
   p.drop_inv_keep = d->dropout_p > 0.f && d->dropout_p < 1.f ? 1.f / (1.f - d->dropout_p) : 0.f;

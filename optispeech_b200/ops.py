@@ -72,7 +72,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -117,6 +117,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
     d.dropout_seed_dev = _ptr(step_counter(a.device)) if dropout_p > 0.0 else None
     d.w_batched, d.col_len = int(w_batched), _ptr(col_len)
+    if colsum is not None:  # bias gradient of the layer whose dgrad this is: column sums of the fp16 output, fused (pre-zeroed fp32 (N,))
+        assert epi in (EPI_GELU_BWD, EPI_RELU_BWD, EPI_RELU_LN_BWD) and colsum.dtype == torch.float32 and colsum.numel() == N
+        d.flags |= _lib.FLAG_COLSUM
+        d.out_colsum = _ptr(colsum)
     _lib.check(_lib.load().osb_gemm(C.byref(d), _stream()), "osb_gemm")
     return out, aux, out_dot
 
