@@ -272,6 +272,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     roofline, top = None, []
     was_graphed, model.cuda_graph = model.cuda_graph, False  # per-launch events need the eager launches
     if rank == 0:
+        # park the GPU behind a ~20 ms spin first: the host then runs ahead and the step's launches are all queued, so the
+        # event brackets measure device execution only (an idle GPU would make every bracket include the host's launch cost)
+        torch.cuda._sleep(40_000_000)
         with _lib.LaunchProfiler() as prof:
             step_resident(0)
     else:

@@ -95,8 +95,14 @@ enum {
   OSB_FLAG_SPLIT_OUT = 64, /* fp16 outputs are written as rows [hi ldo | lo ldo] (row stride 2*ldo)                */
   OSB_FLAG_RELU = 128,     /* EPI_BIAS only: out = relu(acc + bias)                                                */
   OSB_FLAG_NO_F32 = 256,   /* EPI_BIAS with OUT_H16: write only the fp16 copy (out may be NULL)                    */
-  OSB_FLAG_COLSUM = 512    /* GELU_BWD / RELU_BWD / RELU_LN_BWD: out_colsum[n] += sum_rows out_h16[row, n] — the bias
+  OSB_FLAG_COLSUM = 512,   /* GELU_BWD / RELU_BWD / RELU_LN_BWD: out_colsum[n] += sum_rows out_h16[row, n] — the bias
                               gradient of the layer this dgrad belongs to, taken from the tile while it is on chip   */
+  /* Data gradient on the FORWARD weight pack (no transposed copy): w is (taps, K, ldw >= N) with the output index n
+   * contiguous — i.e. the forward pack (taps, N_fwd, K_fwd) of the layer read as (taps, K = N_fwd, N = K_fwd) — and is fed
+   * to tcgen05.mma as an MN-major B operand:  acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] * w[tap', k, n],
+   * tap' = tap, or taps-1-tap with TAP_REVERSE (the transposed convolution of a Conv1d dgrad).  N % 64 == 0. */
+  OSB_FLAG_W_MN = 1024,
+  OSB_FLAG_TAP_REVERSE = 2048
 };
 
 typedef struct osb_gemm_desc {

@@ -101,24 +101,25 @@ class ConvNeXtBlockFn(Function):
         flags = ops.FLAG_SAVE_PRE | (ops.FLAG_KEEPMASK if pad_mask is not None else 0)
         out, z, _ = ops.gemm(h, w2_h, epi=ops.EPI_RESID, flags=flags, bias=b2, resid=x, gamma=gamma, row_scale=row_scale,
                              pad_mask=pad_mask)
-        ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale)
+        ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h)
         return out
 
     @staticmethod
     @ops.pooled
     def backward(ctx, dout):
-        x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale = ctx.saved_tensors
+        x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h = ctx.saved_tensors
         B, T, C = x.shape
         I = w1.shape[0]
         dout = dout.contiguous()
         dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
         # pwconv2: dgrad (with the GELU derivative fused) and wgrad
         db1 = ops.zeros((I,), x)                                           # bias gradient: column sums taken in the dgrad epilogue
-        dpre, _, _ = ops.gemm(dyg, pack_kn(w2), epi=ops.EPI_GELU_BWD, aux_in=pre, colsum=db1)
+        # data gradients run on the FORWARD weight packs (MN-major B operand): no transposed copies are made
+        dpre, _, _ = ops.gemm(dyg, w2_h, epi=ops.EPI_GELU_BWD, aux_in=pre, colsum=db1, w_mn=True)
         dw2 = ops.zeros((1, C, I), x)
         ops.gemm_wgrad(dyg, h, dw2)
         # pwconv1: dgrad (LayerNorm backward fused: the CTA owns whole rows) and wgrad
-        dd, _, _ = ops.gemm(dpre, pack_kn(w1f), epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd)
+        dd, _, _ = ops.gemm(dpre, w1f_h, epi=ops.EPI_LN_BWD, aux_in=xhat, row_stat=rstd, w_mn=True)
         dw1f = ops.zeros((1, I, C), x)
         ops.gemm_wgrad(dpre, xhat, dw1f)
         dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, ln_b, db1)
@@ -137,11 +138,12 @@ class VariancePredictorFn(Function):
         L = len(layer_params) // 4
         pad = (kernel_size - 1) // 2
         a = ops.to_h16(x.contiguous())
-        acts, pres = [a], []
+        acts, pres, wps = [a], [], []
         out = None
         for l in range(L):
             cw, cb, lw, lb = layer_params[4 * l: 4 * l + 4]
             wp = pack_conv_fwd(cw)
+            wps.append(wp)
             if l < L - 1:
                 y, r, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, pad=pad, bias=cb, ln_w=lw, ln_b=lb, ln_eps=eps,
                                    dropout_p=dropout_p, dropout_seed=dropout_seed + l)
@@ -151,7 +153,7 @@ class VariancePredictorFn(Function):
                                      ln_b=lb, ln_eps=eps, dot_w=lin_w.view(-1), dot_b=lin_b, pad_mask=pad_mask, dropout_p=dropout_p,
                                      dropout_seed=dropout_seed + l)
             pres.append(r)
-        ctx.save_for_backward(pad_mask, lin_w, *layer_params, *acts, *pres)
+        ctx.save_for_backward(pad_mask, lin_w, *layer_params, *acts, *pres, *wps)
         ctx.L, ctx.k, ctx.eps = L, kernel_size, eps
         ctx.drop_p, ctx.drop_seed = dropout_p, dropout_seed
         ctx.x_needs_grad = x.requires_grad
@@ -166,6 +168,7 @@ class VariancePredictorFn(Function):
         layer_params = saved[2: 2 + 4 * L]
         acts = saved[2 + 4 * L: 2 + 5 * L]
         pres = saved[2 + 5 * L: 2 + 6 * L]
+        wps = saved[2 + 6 * L: 2 + 7 * L]
         pad = (k - 1) // 2
         grads: List[Optional[torch.Tensor]] = [None] * (4 * L)
         cw, cb, lw, lb = layer_params[4 * (L - 1): 4 * L]
@@ -181,13 +184,14 @@ class VariancePredictorFn(Function):
             if l > 0:
                 lw_prev = layer_params[4 * (l - 1) + 2]
                 grads[4 * (l - 1) + 1] = ops.zeros((Cin,), g)             # conv bias gradient of layer l-1, summed in the epilogue
-                g_prev, gy, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, pad=k - 1 - pad,
+                g_prev, gy, _ = ops.gemm(g, wps[l], epi=ops.EPI_RELU_LN_BWD, flags=ops.FLAG_OUT_H16, pad=k - 1 - pad,
                                          aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps, dropout_p=ctx.drop_p,
-                                         dropout_seed=ctx.drop_seed + l - 1, colsum=grads[4 * (l - 1) + 1])
+                                         dropout_seed=ctx.drop_seed + l - 1, colsum=grads[4 * (l - 1) + 1], w_mn=True, tap_reverse=True,
+                                         N=Cin)
                 grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3] = ops.ln_param_grad(gy, pres[l - 1], lw_prev, eps)
                 g = g_prev
             elif ctx.x_needs_grad:
-                dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
+                dx, _, _ = ops.gemm(g, wps[0], epi=ops.EPI_BIAS, pad=k - 1 - pad, w_mn=True, tap_reverse=True, N=Cin)
         return (dx, None, None, None, None, None, dlin_w.view(1, -1), dlin_b, *grads)
 
 
@@ -201,18 +205,19 @@ class ConvStackFn(Function):
         x fp32 (B,T,Cin) -> fp32 (B,T,N_last).  k_pad: channel padding of the first operand (e.g. 100 mel bins -> 128)."""
         L = len(params) // 2
         a = ops.to_h16(x.contiguous(), pad_to=k_pad or None)
-        acts = [a]
+        acts, wps = [a], []
         out = None
         for l in range(L):
             cw, cb = params[2 * l], params[2 * l + 1]
             k = cw.shape[2]
             wp = pack_conv_fwd(cw, k_pad=acts[-1].shape[-1])
+            wps.append(wp)
             if l < L - 1:
                 y, _, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU, pad=(k - 1) // 2, bias=cb)
                 acts.append(y)
             else:
                 out, _, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_BIAS, pad=(k - 1) // 2, bias=cb)
-        ctx.save_for_backward(*params, *acts)
+        ctx.save_for_backward(*params, *acts, *wps)
         ctx.L = L
         ctx.x_needs_grad = x.requires_grad
         ctx.cin0 = x.shape[-1]
@@ -223,7 +228,7 @@ class ConvStackFn(Function):
     def backward(ctx, dout):
         L = ctx.L
         saved = ctx.saved_tensors
-        params, acts = saved[: 2 * L], saved[2 * L:]
+        params, acts, wps = saved[: 2 * L], saved[2 * L: 3 * L], saved[3 * L:]
         grads: List[Optional[torch.Tensor]] = [None] * (2 * L)
         g = ops.to_h16(dout.contiguous())
         dx = None
@@ -235,10 +240,10 @@ class ConvStackFn(Function):
             grads[2 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
             if l > 0:
                 grads[2 * (l - 1) + 1] = ops.zeros((Cin,), g)             # bias gradient of layer l-1, summed in the epilogue
-                g, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l],
-                                   colsum=grads[2 * (l - 1) + 1])
+                g, _, _ = ops.gemm(g, wps[l], epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l],
+                                   colsum=grads[2 * (l - 1) + 1], w_mn=True, tap_reverse=True, N=Cin)
             elif ctx.x_needs_grad:
-                dx, _, _ = ops.gemm(g, pack_conv_bwd(cw), epi=ops.EPI_BIAS, pad=k - 1 - pad)
+                dx, _, _ = ops.gemm(g, wps[0], epi=ops.EPI_BIAS, pad=k - 1 - pad, w_mn=True, tap_reverse=True, N=Cin)
         return (dx, None, *grads)
 
 
@@ -274,19 +279,20 @@ class WaveNeXtHeadFn(Function):
         wc = w2 @ w1                      # (hop, dim): no non-linearity between the two Linears (wavenext/__init__.py:43-45)
         bc = w2 @ b1
         a = ops.to_h16(x.contiguous())
-        out, _, _ = ops.gemm(a, pack_nk(wc), epi=ops.EPI_BIAS, flags=ops.FLAG_CLIP, bias=bc.contiguous())
-        ctx.save_for_backward(a, out, w1, b1, w2, wc)
+        wc_h = pack_nk(wc)
+        out, _, _ = ops.gemm(a, wc_h, epi=ops.EPI_BIAS, flags=ops.FLAG_CLIP, bias=bc.contiguous())
+        ctx.save_for_backward(a, out, w1, b1, w2, wc_h)
         return out.view(out.shape[0], -1)
 
     @staticmethod
     @ops.pooled
     def backward(ctx, dout):
-        a, out, w1, b1, w2, wc = ctx.saved_tensors
+        a, out, w1, b1, w2, wc_h = ctx.saved_tensors
         B, T, hop = out.shape
         # clip passes gradient only strictly inside (-1, 1)  (torch.clip backward)
         g32 = (dout.reshape(B, T, hop) * ((out > -1.0) & (out < 1.0))).contiguous()
         g = ops.to_h16(g32)
-        dx, _, _ = ops.gemm(g, pack_kn(wc), epi=ops.EPI_BIAS)
+        dx, _, _ = ops.gemm(g, wc_h, epi=ops.EPI_BIAS, w_mn=True)
         dwc = ops.zeros((1, hop, a.shape[-1]), a)
         ops.gemm_wgrad(g, a, dwc)
         dwc = dwc[0]
@@ -388,24 +394,24 @@ class TransformerLayerFn(Function):
         _, xn = ops.layernorm(x, n1w, n1b, eps, f32=False, h16=True)
         wqkv = torch.cat([wq, wk, wv], dim=0)
         bqkv = torch.cat([bq, bk, bv])
-        _, qkv, _ = ops.gemm(xn, pack_nk(wqkv), epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, bias=bqkv)
+        wqkv_h, wo_h, w1_h, w2_h = pack_nk(wqkv), pack_nk(wo), pack_nk(w1[:, :, 0]), pack_nk(w2[:, :, 0])
+        _, qkv, _ = ops.gemm(xn, wqkv_h, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, bias=bqkv)
         att, rmax, rinv = ops.mha_fwd(qkv, heads, kv_len, save_stats=True, dropout_p=p_attn, dropout_seed=seed)
-        x1, _, _ = ops.gemm(att, pack_nk(wo), epi=ops.EPI_RESID, bias=bo, resid=x, gamma=ones, dropout_p=p_drop, dropout_seed=seed + 1)
+        x1, _, _ = ops.gemm(att, wo_h, epi=ops.EPI_RESID, bias=bo, resid=x, gamma=ones, dropout_p=p_drop, dropout_seed=seed + 1)
         _, xn2 = ops.layernorm(x1, n2w, n2b, eps, f32=False, h16=True)
-        h, _, _ = ops.gemm(xn2, pack_nk(w1[:, :, 0]), epi=ops.EPI_RELU, bias=b1, dropout_p=p_ffn, dropout_seed=seed + 2)
-        out, _, _ = ops.gemm(h, pack_nk(w2[:, :, 0]), epi=ops.EPI_RESID, bias=b2, resid=x1, gamma=ones, dropout_p=p_drop,
-                             dropout_seed=seed + 3)
-        ctx.save_for_backward(x, kv_len, n1w, wqkv, wo, n2w, w1, w2, xn, qkv, att, rmax, rinv, x1, xn2, h)
+        h, _, _ = ops.gemm(xn2, w1_h, epi=ops.EPI_RELU, bias=b1, dropout_p=p_ffn, dropout_seed=seed + 2)
+        out, _, _ = ops.gemm(h, w2_h, epi=ops.EPI_RESID, bias=b2, resid=x1, gamma=ones, dropout_p=p_drop, dropout_seed=seed + 3)
+        ctx.save_for_backward(x, kv_len, n1w, wqkv_h, wo_h, n2w, w1_h, w2_h, xn, qkv, att, rmax, rinv, x1, xn2, h)
         ctx.cfg = (heads, p_drop, p_attn, p_ffn, seed, eps)
         return out
 
     @staticmethod
     @ops.pooled
     def backward(ctx, dout):
-        x, kv_len, n1w, wqkv, wo, n2w, w1, w2, xn, qkv, att, rmax, rinv, x1, xn2, h = ctx.saved_tensors
+        x, kv_len, n1w, wqkv_h, wo_h, n2w, w1_h, w2_h, xn, qkv, att, rmax, rinv, x1, xn2, h = ctx.saved_tensors
         heads, p_drop, p_attn, p_ffn, seed, eps = ctx.cfg
         B, T, D = x.shape
-        U = w1.shape[0]
+        U = w1_h.shape[1]
         dout = dout.contiguous()
         # ---- feed-forward branch ----
         g2 = ops.dropout_pack_h16(dout, p_drop, seed + 3)                      # grad wrt (w_2 h + b2)
@@ -413,10 +419,10 @@ class TransformerLayerFn(Function):
         ops.gemm_wgrad(g2, h, dw2)
         db2 = ops.colsum_h16(g2)
         db1 = ops.zeros((U,), x)
-        dh, _, _ = ops.gemm(g2, pack_kn(w2[:, :, 0]), epi=ops.EPI_RELU_BWD, aux_in=h, dropout_p=p_ffn, dropout_seed=seed + 2, colsum=db1)
+        dh, _, _ = ops.gemm(g2, w2_h, epi=ops.EPI_RELU_BWD, aux_in=h, dropout_p=p_ffn, dropout_seed=seed + 2, colsum=db1, w_mn=True)
         dw1 = ops.zeros((1, U, D), x)
         ops.gemm_wgrad(dh, xn2, dw1)
-        dxn2, _, _ = ops.gemm(dh, pack_kn(w1[:, :, 0]), epi=ops.EPI_BIAS)
+        dxn2, _, _ = ops.gemm(dh, w1_h, epi=ops.EPI_BIAS, w_mn=True)
         dln2, dn2w, dn2b = ops.layernorm_bwd(dxn2, x1, n2w, eps)
         dx1 = dout + dln2
         # ---- attention branch ----
@@ -424,12 +430,12 @@ class TransformerLayerFn(Function):
         dwo = ops.zeros((1, D, D), x)
         ops.gemm_wgrad(g1, att, dwo)
         dbo = ops.colsum_h16(g1)
-        _, datt, _ = ops.gemm(g1, pack_kn(wo), epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
+        _, datt, _ = ops.gemm(g1, wo_h, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, w_mn=True)
         dqkv = ops.mha_bwd(qkv, heads, kv_len, att, datt, rmax, rinv, dropout_p=p_attn, dropout_seed=seed)
         dwqkv = ops.zeros((1, 3 * D, D), x)
         ops.gemm_wgrad(dqkv, xn, dwqkv)
         dbqkv = ops.colsum_h16(dqkv)
-        dxn, _, _ = ops.gemm(dqkv, pack_kn(wqkv), epi=ops.EPI_BIAS)
+        dxn, _, _ = ops.gemm(dqkv, wqkv_h, epi=ops.EPI_BIAS, w_mn=True)
         dln1, dn1w, dn1b = ops.layernorm_bwd(dxn, x, n1w, eps)
         dx = dx1 + dln1
         dwq, dwk, dwv = dwqkv[0, :D], dwqkv[0, D:2 * D], dwqkv[0, 2 * D:]

@@ -51,6 +51,8 @@ struct GemmKParams {
   int w_batch;      // 1: slice index += batch (per-batch B operand)
   const long long* col_len;
   float* colsum;    // COLSUM: (N) column sums of the fp16 output
+  int w_mn;         // 1: W is (taps, K, ldw >= N) with the OUTPUT index contiguous (MN-major B operand): dgrad on the forward pack
+  int tap_rev;      // 1: tap t reads weight slice taps-1-t (transposed convolution)
   long long* trace; // optional (developer): clock64 timeline of CTA (0,0), see tools/probe_gemm_trace.py
 };
 
@@ -743,17 +745,25 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 + tap - p.pad, b);
+        if (p.w_mn) {
+          // MN-major B: 64 contraction rows x BN output columns, as BN/64 chunks of [64 rows x 128 B]
+          const int slice = p.tap_rev ? p.taps - 1 - tap : tap;
 #pragma unroll
-        for (int c = 0; c < Cfg::NCHUNK; ++c)
-          tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], w_k, n0 + c * Cfg::NINST, w_slice);
+          for (int c = 0; c < BN / 64; ++c) tma_load_3d(sB + c * (BKE * ROW_BYTES), &tmW, &full_bar[s], n0 + c * 64, kb * BKE, slice);
+        } else {
+#pragma unroll
+          for (int c = 0; c < Cfg::NCHUNK; ++c)
+            tma_load_3d(sB + c * Cfg::NINST * ROW_BYTES, &tmW, &full_bar[s], w_k, n0 + c * Cfg::NINST, w_slice);
+        }
         if (it == 0) GT_TRACE(2);
         if (it == iters - 1) GT_TRACE(3);
       }
     }
   } else if (warp == 1) {
     // whole warp, uniform control flow (descriptors live in uniform registers); one elected lane issues
-    constexpr uint32_t idesc = make_instr_desc(OSB_F16, BM, Cfg::NINST, 0, 0);
+    const uint32_t idesc = make_instr_desc(OSB_F16, BM, Cfg::NINST, 0, p.w_mn ? 1u : 0u);
     const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const uint64_t d0_mn = make_smem_desc_sw128(smem_u32(smem), BKE * ROW_BYTES, 1024);   // LBO = stride between 64-column chunks
     for (int it = 0; it < iters; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
@@ -763,13 +773,27 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (elect_one()) {
         const uint64_t da0 = d0 + static_cast<uint64_t>((s * Cfg::STAGE_BYTES) >> 4);
         const uint64_t db0 = da0 + static_cast<uint64_t>(Cfg::A_BYTES >> 4);
+        if (p.w_mn) {
+          const uint64_t db_mn = d0_mn + static_cast<uint64_t>((s * Cfg::STAGE_BYTES + Cfg::A_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
 #pragma unroll
-          for (int c = 0; c < Cfg::NCHUNK; ++c) {
-            umma_ss<false>(tmem_base + c * Cfg::NINST, da0 + static_cast<uint64_t>((k * UMMA_K_BYTES) >> 4),
-                           db0 + static_cast<uint64_t>((c * Cfg::NINST * ROW_BYTES + k * UMMA_K_BYTES) >> 4), idesc,
-                           (it | k) != 0 ? 1u : 0u);
+            for (int c = 0; c < Cfg::NCHUNK; ++c) {
+              // 16 contraction rows per MMA = 2048 B inside every chunk; instruction c starts NINST/64 chunks further
+              umma_ss<false>(tmem_base + c * Cfg::NINST, da0 + static_cast<uint64_t>((k * UMMA_K_BYTES) >> 4),
+                             db_mn + static_cast<uint64_t>((c * (Cfg::NINST / 64) * (BKE * ROW_BYTES) + k * 16 * ROW_BYTES) >> 4), idesc,
+                             (it | k) != 0 ? 1u : 0u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+#pragma unroll
+            for (int c = 0; c < Cfg::NCHUNK; ++c) {
+              umma_ss<false>(tmem_base + c * Cfg::NINST, da0 + static_cast<uint64_t>((k * UMMA_K_BYTES) >> 4),
+                             db0 + static_cast<uint64_t>((c * Cfg::NINST * ROW_BYTES + k * UMMA_K_BYTES) >> 4), idesc,
+                             (it | k) != 0 ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
@@ -1063,7 +1087,9 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   OSB_REQUIRE(d != nullptr && d->a != nullptr && d->w != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->K > 0 && d->taps > 0, OSB_ERR_SHAPE);
   OSB_REQUIRE(d->lda % 8 == 0 && d->ldw % 8 == 0 && (d->ldo % 8 == 0 || d->epi == OSB_EPI_ATTN_LOGP), OSB_ERR_ALIGN);
-  OSB_REQUIRE(d->lda >= d->K && d->ldw >= d->K && d->ldo >= d->N, OSB_ERR_SHAPE);
+  const bool w_mn = (d->flags & OSB_FLAG_W_MN) != 0;
+  OSB_REQUIRE(d->lda >= d->K && d->ldw >= (w_mn ? d->N : d->K) && d->ldo >= d->N, OSB_ERR_SHAPE);
+  if (w_mn) OSB_REQUIRE(!(d->flags & OSB_FLAG_SPLIT_IN) && d->w_batched == 0 && d->K % 8 == 0, OSB_ERR_SHAPE);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 
   const bool full_row = (d->epi == OSB_EPI_RELU_LN || d->epi == OSB_EPI_BIAS_LN || d->epi == OSB_EPI_LN_BWD ||
@@ -1081,7 +1107,11 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   int rc = make_tmap_3d(&tmA, d->a, TMA_F16, split_in ? 2 * d->K : d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda,
                         BKE, BM);
   if (rc != OSB_OK) return rc;
-  if (w_batched) {
+  if (w_mn) {
+    // (taps, K, ldw): contraction rows K, output columns N contiguous; box = 64 columns x 64 rows
+    OSB_REQUIRE(ninst % 64 == 0, OSB_ERR_SHAPE);
+    rc = make_tmap_3d(&tmW, d->w, TMA_F16, d->N, d->K, d->taps, d->ldw, static_cast<uint64_t>(d->K) * d->ldw, 64, BKE);
+  } else if (w_batched) {
     if (split_in) OSB_REQUIRE(d->ldw >= 2 * static_cast<int64_t>(d->K), OSB_ERR_SHAPE);
     rc = make_tmap_3d(&tmW, d->w, TMA_F16, split_in ? 2 * d->K : d->K, d->N, d->B, d->ldw, static_cast<uint64_t>(d->N) * d->ldw, BKE,
                       ninst);
@@ -1104,6 +1134,8 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.w_lo_slice = w_batched ? 0 : d->taps;
   p.w_lo_koff = w_batched ? d->K : 0;
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
+  p.w_mn = w_mn ? 1 : 0;
+  p.tap_rev = (d->flags & OSB_FLAG_TAP_REVERSE) ? 1 : 0;
   p.colsum = (d->flags & OSB_FLAG_COLSUM) ? d->out_colsum : nullptr;
   if ((d->flags & OSB_FLAG_COLSUM) && (d->out_colsum == nullptr || !(d->epi == OSB_EPI_GELU_BWD || d->epi == OSB_EPI_RELU_BWD ||
                                                                      d->epi == OSB_EPI_RELU_LN_BWD))) return OSB_ERR_ARG;

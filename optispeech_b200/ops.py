@@ -72,7 +72,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None, w_mn: bool = False, tap_reverse: bool = False):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -80,7 +80,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     Outputs are allocated when not given.  Returns (out, aux, out_dot)."""
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 3
     B, T, lda = a.shape
-    if w_batched:
+    if w_mn:
+        # dgrad on the forward pack: w (taps, K, ldw) with the output index contiguous (a layer's forward pack (taps, N_fwd, K_fwd))
+        if w.dim() == 4:
+            w = w[0]
+        taps, Kw, ldw = w.shape
+        K = K if K is not None else min(lda, Kw)
+        N = N if N is not None else ldw
+        flags |= _lib.FLAG_W_MN | (_lib.FLAG_TAP_REVERSE if tap_reverse else 0)
+    elif w_batched:
         assert w.dim() == 3 and w.shape[0] == B
         taps, ldw = 1, w.shape[2]
         N = N if N is not None else w.shape[1]
