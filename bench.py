@@ -371,6 +371,48 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception as exc:  # the headline line must not depend on a variant
             variants["transformer_backbone"] = {"error": repr(exc)[:300]}
 
+    # ---- SURVEY §8(d) step variants on the same batch: T2 = generator step with the spectral losses through the vocoder (every
+    #      kernel in this library), T3 = the full GAN-phase training_step (generator turn + discriminator turn; the MPD / MRD
+    #      discriminators run on stock PyTorch / cuDNN) ----
+    if rank == 0 and world == 1 and not args.no_variants:
+        def _time(fn, n=10, warm=3):
+            for i in range(warm):
+                fn(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        try:
+            torch.manual_seed(SEED)
+            gmodel = build_model(DEFAULT_MODEL, train_args=dict(pretraining_steps=0)).to(dev).train()
+            opt_g = gmodel.optimizers()[0]
+
+            def t2_step(i):   # eager: forward, AM + 45 mel + 2.5 MR-STFT losses, backward through vocoder and acoustic model, AdamW
+                out = gmodel._process_batch(dev_batch)
+                spec_loss, _ = gmodel.discriminator.forward_val(out["wav"], out["wav_hat"])
+                opt_g.zero_grad()
+                gmodel.manual_backward(out["loss"] + spec_loss)
+                gmodel.clip_gradients(opt_g, gradient_clip_val=10, gradient_clip_algorithm="norm")
+                opt_g.step()
+
+            t2 = _time(t2_step)
+            gmodel.cuda_graph = True
+            t3 = _time(lambda i: gmodel.training_step(dev_batch, i), n=10, warm=4 + 3)
+            variants["T2_generator_step_with_spectral_losses"] = {"ms_per_step": t2, "mel_frames_per_s": frames_local / (t2 * 1e-3),
+                                                                  "launch_mode": "eager"}
+            variants["T3_full_gan_training_step"] = {"ms_per_step": t3, "mel_frames_per_s": frames_local / (t3 * 1e-3),
+                                                     "launch_mode": "CUDA-graph replay", "note": "MPD/MRD discriminators on stock PyTorch/cuDNN"}
+            if gmodel._graphed is not None:
+                gmodel._graphed.release()
+            del gmodel
+        except Exception as exc:
+            variants["gan_phase"] = {"error": repr(exc)[:300]}
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload through the oracle port ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -377,6 +377,20 @@ int osb_mel_loss(const float* x_hat, const float* y, const float* window, const 
                  const int32_t* jlo, const int32_t* jhi, int32_t n_mels, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t win,
                  float clamp_min, double* stats, const float* coef, float* dx_hat, void* stream);
 
+/* Every fp32 -> fp16 weight pack of a training step in ONE launch (the weights change every step, so the packs are
+ * per-step work: 44 small launches otherwise).  jobs_dev: device array, sorted by first_elem (prefix sums of the
+ * destination element counts, first_elem[0] = 0); total_elems = sum of destination elements.
+ *   kind 0: src (rows, cols) fp32 row-major, optionally scaled per column -> dst (rows, dst_cols) fp16, zero padded
+ *   kind 1: src Conv1d weight (rows = N, cols = Cin, k) -> dst (k, N, dst_cols) fp16 (one K-major matrix per tap) */
+typedef struct osb_pack_job {
+  const void* src;
+  void* dst;
+  const void* col_scale;   /* kind 0: (cols) fp32 or NULL */
+  int64_t first_elem;
+  int32_t kind, rows, cols, k, dst_cols, reserved;
+} osb_pack_job;
+int osb_pack_multi(const osb_pack_job* jobs_dev, int32_t n_jobs, int64_t total_elems, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Multi-head self-attention of the Transformer backbone (osb_mha.cu), d_k = 128.
  * q, k, v: fp16 (B, T, ld_qkv) with head h in columns [h*128, +128) (typically three column slices of one fused

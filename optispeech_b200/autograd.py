@@ -23,6 +23,39 @@ def pack_nk(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     return ops.pack_h16(w.contiguous(), rows=N, cols=K, src_ld=K, dst_cols=Kp).view(1, N, Kp)
 
 
+def pack_params_nk(ws, col_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Parameters (N_i, K) fp32 (stacked along N), optionally scaled per column -> (1, sum N_i, K) fp16, served by the step
+    packer (model/packing.py: one launch for all the packs of a training step once the step has been seen)."""
+    from .model.packing import current_packer
+
+    ws = [w for w in ws]
+    K = ws[0].shape[1]
+    n_total = sum(w.shape[0] for w in ws)
+
+    def direct():
+        out = torch.empty((1, n_total, K), device=ws[0].device, dtype=torch.float16)
+        r = 0
+        for w in ws:
+            ops.pack_h16(w.detach().contiguous(), rows=w.shape[0], cols=K, src_ld=K, dst_cols=K, col_scale=col_scale, out=out[0, r: r + w.shape[0]])
+            r += w.shape[0]
+        return out
+
+    packer = current_packer()
+    if packer is None or any(not w.is_contiguous() for w in ws):
+        return direct()
+    return packer.request("nk", ws, col_scale, None, direct)
+
+
+def pack_param_conv(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
+    """Conv1d parameter (N, Cin, k) -> (k, N, Cin_pad) fp16 through the step packer."""
+    from .model.packing import current_packer
+
+    packer = current_packer()
+    if packer is None or not w.is_contiguous():
+        return ops.pack_conv_h16(w, k_pad=k_pad)
+    return packer.request("conv", [w], None, k_pad, lambda: ops.pack_conv_h16(w, k_pad=k_pad))
+
+
 def pack_kn(w: torch.Tensor) -> torch.Tensor:
     """(N, K) fp32 -> transposed (1, K, N) fp16 (the dgrad operand)."""
     N, K = w.shape
@@ -93,21 +126,20 @@ class ConvNeXtBlockFn(Function):
     @staticmethod
     def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, pad_mask, row_scale, eps):
         B, T, C = x.shape
-        w1f = w1 * ln_w                      # fold the LN affine into pwconv1 (packing-time glue on weights)
-        b1f = torch.addmv(b1, w1, ln_b)
-        w1f_h, w2_h = pack_nk(w1f), pack_nk(w2)
+        b1f = torch.addmv(b1, w1, ln_b)      # fold the LN affine into pwconv1: bias here, weight as a column scale of the pack
+        w1f_h, w2_h = pack_params_nk([w1], col_scale=ln_w), pack_params_nk([w2])
         xhat, rstd = ops.dwconv_ln(x, dw_w.view(C, 7), dw_b, eps, want_rstd=True)
         h, pre, _ = ops.gemm(xhat, w1f_h, epi=ops.EPI_GELU, flags=ops.FLAG_SAVE_PRE, bias=b1f)
         flags = ops.FLAG_SAVE_PRE | (ops.FLAG_KEEPMASK if pad_mask is not None else 0)
         out, z, _ = ops.gemm(h, w2_h, epi=ops.EPI_RESID, flags=flags, bias=b2, resid=x, gamma=gamma, row_scale=row_scale,
                              pad_mask=pad_mask)
-        ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h)
+        ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h)
         return out
 
     @staticmethod
     @ops.pooled
     def backward(ctx, dout):
-        x, dw_w, ln_w, ln_b, w1, w1f, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h = ctx.saved_tensors
+        x, dw_w, ln_w, ln_b, w1, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h = ctx.saved_tensors
         B, T, C = x.shape
         I = w1.shape[0]
         dout = dout.contiguous()
@@ -142,7 +174,7 @@ class VariancePredictorFn(Function):
         out = None
         for l in range(L):
             cw, cb, lw, lb = layer_params[4 * l: 4 * l + 4]
-            wp = pack_conv_fwd(cw)
+            wp = pack_param_conv(cw)
             wps.append(wp)
             if l < L - 1:
                 y, r, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU_LN, flags=ops.FLAG_SAVE_PRE, pad=pad, bias=cb, ln_w=lw, ln_b=lb, ln_eps=eps,
@@ -210,7 +242,7 @@ class ConvStackFn(Function):
         for l in range(L):
             cw, cb = params[2 * l], params[2 * l + 1]
             k = cw.shape[2]
-            wp = pack_conv_fwd(cw, k_pad=acts[-1].shape[-1])
+            wp = pack_param_conv(cw, k_pad=acts[-1].shape[-1])
             wps.append(wp)
             if l < L - 1:
                 y, _, _ = ops.gemm(acts[-1], wp, epi=ops.EPI_RELU, pad=(k - 1) // 2, bias=cb)
@@ -392,9 +424,9 @@ class TransformerLayerFn(Function):
         eps = 1e-12
         x = x.contiguous()
         _, xn = ops.layernorm(x, n1w, n1b, eps, f32=False, h16=True)
-        wqkv = torch.cat([wq, wk, wv], dim=0)
         bqkv = torch.cat([bq, bk, bv])
-        wqkv_h, wo_h, w1_h, w2_h = pack_nk(wqkv), pack_nk(wo), pack_nk(w1[:, :, 0]), pack_nk(w2[:, :, 0])
+        wqkv_h, wo_h = pack_params_nk([wq, wk, wv]), pack_params_nk([wo])
+        w1_h, w2_h = pack_params_nk([w1.view(w1.shape[0], -1)]), pack_params_nk([w2.view(w2.shape[0], -1)])
         _, qkv, _ = ops.gemm(xn, wqkv_h, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, bias=bqkv)
         att, rmax, rinv = ops.mha_fwd(qkv, heads, kv_len, save_stats=True, dropout_p=p_attn, dropout_seed=seed)
         x1, _, _ = ops.gemm(att, wo_h, epi=ops.EPI_RESID, bias=bo, resid=x, gamma=ones, dropout_p=p_drop, dropout_seed=seed + 1)

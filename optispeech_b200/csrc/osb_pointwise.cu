@@ -410,10 +410,50 @@ __global__ void pack_conv_h16_kernel(const float* __restrict__ w, __half* __rest
   if (dst_lo != nullptr) dst_lo[i] = __float2half_rn(v - __half2float(hi));
 }
 
+// Every weight pack of a training step in ONE launch: jobs[] (device) lists (source, destination, layout); a thread finds its
+// job by binary search over the prefix sums of the destination sizes.  kind 0: (rows, cols) fp32 row-major (optionally
+// scaled per column) -> (rows, dst_cols) fp16; kind 1: Conv1d weight (rows = N, cols = Cin, k) -> (k, N, dst_cols) fp16.
+__global__ void pack_multi_kernel(const osb_pack_job* __restrict__ jobs, int n_jobs, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_elem <= i) lo = mid; else hi = mid - 1;
+  }
+  const osb_pack_job j = jobs[lo];
+  const long long e = i - j.first_elem;
+  const float* src = static_cast<const float*>(j.src);
+  float v = 0.f;
+  if (j.kind == 0) {
+    const long long r = e / j.dst_cols;
+    const int c = static_cast<int>(e % j.dst_cols);
+    if (c < j.cols) {
+      v = src[r * j.cols + c];
+      if (j.col_scale != nullptr) v *= static_cast<const float*>(j.col_scale)[c];
+    }
+  } else {
+    const int c = static_cast<int>(e % j.dst_cols);
+    const int n = static_cast<int>((e / j.dst_cols) % j.rows);
+    const int tap = static_cast<int>(e / (static_cast<long long>(j.dst_cols) * j.rows));
+    if (c < j.cols) v = src[(static_cast<long long>(n) * j.cols + c) * j.k + tap];
+  }
+  static_cast<__half*>(j.dst)[e] = __float2half_rn(v);
+}
+
 }  // namespace
 }  // namespace osb
 
 using namespace osb;
+
+extern "C" int osb_pack_multi(const osb_pack_job* jobs_dev, int32_t n_jobs, int64_t total_elems, void* stream) {
+  OSB_REQUIRE(jobs_dev != nullptr, OSB_ERR_ARG);
+  OSB_REQUIRE(n_jobs > 0 && total_elems > 0, OSB_ERR_SHAPE);
+  pack_multi_kernel<<<static_cast<unsigned>((total_elems + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, n_jobs,
+                                                                                                                   total_elems);
+  count_launch();
+  return launch_status();
+}
 
 extern "C" int osb_pack_conv_h16(const float* w, void* dst, void* dst_lo, int32_t N, int32_t Cin, int32_t k, int32_t Kp,
                                  int32_t transpose_reverse, void* stream) {

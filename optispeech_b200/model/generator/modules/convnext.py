@@ -32,6 +32,9 @@ class DropPath(nn.Module):
     def sample_scale(self, batch: int, device) -> Optional[torch.Tensor]:
         if self.drop_prob == 0.0 or not self.training:
             return None
+        pre = self.__dict__.pop("_presampled", None)   # drawn for all blocks of the step at once (presample_drop_paths)
+        if pre is not None and pre.shape[0] == batch and pre.device == device:
+            return pre
         keep = 1.0 - self.drop_prob
         scale = torch.empty(batch, device=device, dtype=torch.float32).bernoulli_(keep)
         if keep > 0.0 and self.scale_by_keep:
@@ -44,6 +47,28 @@ class DropPath(nn.Module):
 
     def extra_repr(self):
         return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+def presample_drop_paths(root: nn.Module, batch: int, device) -> None:
+    """Draw the per-sample stochastic-depth scales of every DropPath under `root` for one forward with three kernels instead
+    of two per block (same distribution: Bernoulli(keep_l) / keep_l per sample and block; reference convnext.py:121-129)."""
+    mods = root.__dict__.get("_drop_path_mods")
+    if mods is None:
+        mods = [m for m in root.modules() if isinstance(m, DropPath) and m.drop_prob > 0.0 and m.scale_by_keep]
+        root.__dict__["_drop_path_mods"] = mods
+        root.__dict__["_drop_path_keep"] = {}
+    active = [m for m in mods if m.training]
+    if not active:
+        return
+    cache = root.__dict__["_drop_path_keep"]
+    key = (tuple(id(m) for m in active), str(device))
+    keep = cache.get(key)
+    if keep is None:
+        keep = torch.tensor([1.0 - m.drop_prob for m in active], dtype=torch.float32).to(device).view(-1, 1)
+        cache[key] = keep
+    scales = torch.bernoulli(keep.expand(len(active), batch)) / keep
+    for i, m in enumerate(active):
+        m.__dict__["_presampled"] = scales[i]
 
 
 class ConvNeXtBlock(nn.Module):

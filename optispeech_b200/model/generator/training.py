@@ -143,6 +143,16 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
     """Reference generator/__init__.py:72-192.  `seg_rand` (B,) in [0,1) replaces the CPU `torch.rand` draw of
     get_random_segments (utils/segments.py:32) when given (parity tests); otherwise it is drawn the same way."""
     dev = x.device
+    from ..packing import step_packs
+    if gen.training:
+        from .modules.convnext import presample_drop_paths
+        presample_drop_paths(gen, x.shape[0], dev)   # all DropPath draws of the step at once
+    with step_packs(gen, dev):   # every weight pack of this forward in one launch (once the step has been recorded)
+        return _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand)
+
+
+def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
+    dev = x.device
     f0_real = pitches
     x_mask = sequence_mask(x_lengths, x.shape[1])
     mel_mask = sequence_mask(mel_lengths, mel.shape[-1])

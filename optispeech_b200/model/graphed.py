@@ -134,6 +134,9 @@ class GraphedTrainingStep:
         e.graph = graph
         from .packing import live_packs
         e.keepalive = live_packs()
+        packer = getattr(m.generator, "_step_packer", None)
+        if packer is not None and packer.plan is not None:
+            e.keepalive.append(packer.plan)   # the graph replays osb_pack_multi on this plan's job table and buffers
         return e
 
     def _replay(self, e: _Entry, batch) -> None:

@@ -65,3 +65,129 @@ def pack_conv(weight: torch.Tensor, k_pad: int | None = None) -> torch.Tensor:
     from .. import ops
 
     return ops.pack_conv_h16(weight.detach(), k_pad=k_pad, split=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# per-step weight packs of the training path, batched into one launch
+# --------------------------------------------------------------------------------------------------
+class StepPacker:
+    """Trainable weights change every step, so their fp16 tensor-core copies are per-step work: ~44 small pack launches in
+    the ConvNeXt pre-training step.  The packer records the sequence of pack requests of one training forward (source
+    parameter, layout, column scale), then serves the same sequence on later steps from ONE `osb_pack_multi` launch at the
+    start of the forward: the job table (device) and the destination buffers are built once, the sources are parameter
+    storage (stable addresses: views into the optimizer's flat bucket).  Any deviation from the recorded sequence (another
+    training phase, other shapes, re-allocated parameters) drops the plan; the requests of that step fall back to one
+    launch each and the next step records again.  Requests are served in order, so the plan is also what a captured CUDA
+    graph replays."""
+
+    def __init__(self):
+        self.plan = None          # dict(specs, outs, table, total)
+        self.recording = None     # list of (spec, out) while recording
+        self.cursor = 0
+        self.active = False
+
+    @staticmethod
+    def _spec(kind, srcs, col_scale, k_pad):
+        return (kind, tuple((s.data_ptr(), tuple(s.shape)) for s in srcs), col_scale.data_ptr() if col_scale is not None else 0, k_pad or 0)
+
+    def begin(self, device):
+        from .. import _lib, ops
+
+        self.cursor = 0
+        if self.plan is not None:
+            if self.plan["device"] != device:
+                self.plan = None
+            else:
+                _lib.check(_lib.load().osb_pack_multi(self.plan["table"].data_ptr(), self.plan["n_jobs"], self.plan["total"], ops._stream()),
+                           "osb_pack_multi")
+                self.active = True
+                self.recording = None
+                return
+        self.active = False
+        self.recording = []
+
+    def end(self):
+        if self.recording:
+            self._build(self.recording)
+        self.recording = None
+        self.active = False
+
+    def drop(self):
+        self.plan, self.recording, self.active = None, None, False
+
+    def request(self, kind, srcs, col_scale, k_pad, direct):
+        """-> packed tensor for (kind, srcs, col_scale, k_pad); `direct()` packs it with one launch (fallback / recording)."""
+        if self.active:
+            spec = self._spec(kind, srcs, col_scale, k_pad)
+            if self.cursor < len(self.plan["specs"]) and self.plan["specs"][self.cursor] == spec:
+                out = self.plan["outs"][self.cursor]
+                self.cursor += 1
+                return out
+            self.drop()                       # the step deviates from the recorded one
+            return direct()
+        out = direct()
+        if self.recording is not None:
+            self.recording.append((self._spec(kind, srcs, col_scale, k_pad), kind, list(srcs), col_scale, k_pad, out))
+        return out
+
+    def _build(self, rec):
+        import ctypes as C
+
+        from .. import _lib
+
+        jobs, outs, specs, first = [], [], [], 0
+        for spec, kind, srcs, col_scale, k_pad, sample in rec:
+            out = torch.empty_like(sample)
+            flat = out.view(-1)
+            off = 0
+            for s in srcs:
+                j = _lib.PackJob()
+                j.src, j.col_scale = s.data_ptr(), (col_scale.data_ptr() if col_scale is not None else None)
+                j.dst = flat.data_ptr() + 2 * off
+                j.first_elem = first
+                if kind == "nk":
+                    rows, cols = s.shape
+                    j.kind, j.rows, j.cols, j.k, j.dst_cols = 0, rows, cols, 1, (k_pad or cols)
+                    n = rows * j.dst_cols
+                else:
+                    N, Cin, k = s.shape
+                    j.kind, j.rows, j.cols, j.k, j.dst_cols = 1, N, Cin, k, (k_pad or Cin)
+                    n = k * N * j.dst_cols
+                jobs.append(j)
+                first += n
+                off += n
+            assert off == flat.numel(), (off, flat.numel(), kind)
+            outs.append(out)
+            specs.append(spec)
+        arr = (_lib.PackJob * len(jobs))(*jobs)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = rec[0][5].device
+        self.plan = dict(specs=specs, outs=outs, table=raw.to(dev), n_jobs=len(jobs), total=first, device=dev,
+                         keepalive=[(srcs, cs) for _, _, srcs, cs, _, _ in rec])
+
+
+_CURRENT: "StepPacker | None" = None   # the packer of the training forward in progress (set by generator_training_forward)
+
+
+def current_packer() -> "StepPacker | None":
+    return _CURRENT
+
+
+class step_packs:
+    """Context of one training forward: `with step_packs(generator, device): ...` routes the pack requests of the autograd
+    Functions to the generator's own StepPacker (one plan per model: two models in one process do not disturb each other)."""
+
+    def __init__(self, owner, device):
+        self.packer = owner.__dict__.setdefault("_step_packer", StepPacker())
+        self.device = device
+
+    def __enter__(self):
+        global _CURRENT
+        self.prev, _CURRENT = _CURRENT, self.packer
+        self.packer.begin(self.device)
+        return self.packer
+
+    def __exit__(self, *exc):
+        global _CURRENT
+        self.packer.end()
+        _CURRENT = self.prev
