@@ -274,11 +274,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if rank == 0:
         # park the GPU behind a ~20 ms spin first: the host then runs ahead and the step's launches are all queued, so the
         # event brackets measure device execution only (an idle GPU would make every bracket include the host's launch cost)
+        from optispeech_b200 import ops as _ops
         torch.cuda._sleep(40_000_000)
-        with _lib.LaunchProfiler() as prof:
-            step_resident(0)
+        _ops.SIDE_STREAMS_ENABLED = False   # serial execution: a bracket must hold one kernel, not its concurrent neighbours
+        try:
+            with _lib.LaunchProfiler() as prof:
+                step_resident(0)
+        finally:
+            _ops.SIDE_STREAMS_ENABLED = True
     else:
-        step_resident(0)  # the step holds a gradient all-reduce: every rank has to take it
+        step_resident(0)  # the step holds a gradient all-reduce: every rank has to take it (rank 0 takes it serially, see above)
     model.cuda_graph = was_graphed
     if rank == 0:
         summ = prof.summary()

@@ -271,6 +271,9 @@ class BaseModule(nn.Module):
             if not self._capturing:  # host bookkeeping of a captured step is done per replay (model/graphed.py)
                 sched_g.step()
         self.untoggle_optimizer(opt_g)
+        for s in self.__dict__.pop("_pending_streams", []):   # branches the generator turn left running (see training_step_g)
+            torch.cuda.current_stream().wait_stream(s)
+        self.__dict__.pop("_pending_keepalive", None)
         if not self._capturing:
             self._fit.total_batch_idx += 1
         if not train_discriminator:
@@ -295,12 +298,17 @@ class BaseModule(nn.Module):
         if train_discriminator:
             gen_outputs = self._process_batch(batch)
         else:
-            # pre-training: the vocoder output feeds no loss, so its autograd graph is not built
+            # pre-training: the vocoder output feeds no loss, so its autograd graph is not built and its stream is only joined
+            # at the end of the step (the decoder / vocoder forward overlaps the backward pass)
             self.generator.vocoder_needs_grad = False
+            self.generator.defer_vocoder_join = True
             try:
                 gen_outputs = self._process_batch(batch)
             finally:
                 self.generator.vocoder_needs_grad = True
+                self.generator.defer_vocoder_join = False
+        self._pending_streams = list(gen_outputs.pop("_pending_streams", []) or [])
+        self._pending_keepalive = gen_outputs.pop("_pending_keepalive", [])
         gen_am_loss = gen_outputs["loss"]
         log_outputs.update({
             "total_loss/train_am_loss": gen_am_loss,

@@ -141,13 +141,20 @@ class PitchPredictor(nn.Module):
         return ops.variance_embed(x.contiguous(), values.contiguous(), conv.weight.view(self.dim, -1), conv.bias, mask_u8,
                                   f32=True, h16=want_h16, split=split)
 
-    def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor):
-        """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics."""
+    def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor, side_stream=None):
+        """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics.
+        The prediction only meets the rest of the step at the loss (the embedding is driven by `target`), so with
+        `side_stream` it is enqueued there, forked from the current stream; the CALLER joins (`wait_stream`) before using it."""
         mask_u8 = padding_mask.to(torch.uint8).contiguous()
         if torch.is_grad_enabled():
             from ....autograd import VarianceEmbedFn
 
-            preds = self.predictor(x, padding_mask)
+            if side_stream is not None and x.is_cuda:
+                side_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side_stream):
+                    preds = self.predictor(x, padding_mask)
+            else:
+                preds = self.predictor(x, padding_mask)
             conv, drop = self.embed[0], self.embed[1]
             emb_scale = None
             if self.training and drop.p > 0.0:  # Dropout on the embedding branch (core.py:143-150)

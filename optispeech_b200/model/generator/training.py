@@ -5,6 +5,7 @@ generator/__init__.py:72-192 (reference @ 3bdde20).
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import numpy as np
@@ -33,15 +34,24 @@ class AlignmentModule(nn.Module):
         self.f_conv2 = nn.Conv1d(adim, adim, kernel_size=3, padding=1)
         self.f_conv3 = nn.Conv1d(adim, adim, kernel_size=1, padding=0)
 
-    def forward(self, text, feats, text_lengths, feats_lengths, x_masks=None):
-        """text (B,Tx,adim), feats (B,Tm,odim) -> log_p_attn (B,Tm,Tx) with the beta-binomial prior added."""
-        te = ConvStackFn.apply(text, 0, self.t_conv1.weight, self.t_conv1.bias, self.t_conv2.weight, self.t_conv2.bias)
+    def encode_text(self, text):
+        """t_conv1 -> ReLU -> t_conv2 (reference alignments.py:55-58)."""
+        return ConvStackFn.apply(text, 0, self.t_conv1.weight, self.t_conv1.bias, self.t_conv2.weight, self.t_conv2.bias)
+
+    def encode_feats(self, feats):
+        """f_conv1 -> ReLU -> f_conv2 -> ReLU -> f_conv3 (reference alignments.py:60-64); depends on the mel input only."""
         odim = feats.shape[-1]
-        fe = ConvStackFn.apply(feats, ((odim + 63) // 64) * 64, self.f_conv1.weight, self.f_conv1.bias, self.f_conv2.weight,
-                               self.f_conv2.bias, self.f_conv3.weight, self.f_conv3.bias)
-        prior = self._generate_prior(text_lengths, feats_lengths, text.shape[1], feats.shape[1])
+        return ConvStackFn.apply(feats, ((odim + 63) // 64) * 64, self.f_conv1.weight, self.f_conv1.bias, self.f_conv2.weight,
+                                 self.f_conv2.bias, self.f_conv3.weight, self.f_conv3.bias)
+
+    def attend(self, fe, te, text_lengths, feats_lengths):
+        prior = self._generate_prior(text_lengths, feats_lengths, te.shape[1], fe.shape[1])
         # x_masks is the prefix mask of text_lengths in every reference call site (generator/__init__.py:120-126)
         return AttnLogProbFn.apply(fe, te, prior, text_lengths.contiguous(), feats_lengths.contiguous())
+
+    def forward(self, text, feats, text_lengths, feats_lengths, x_masks=None):
+        """text (B,Tx,adim), feats (B,Tm,odim) -> log_p_attn (B,Tm,Tx) with the beta-binomial prior added."""
+        return self.attend(self.encode_feats(feats), self.encode_text(text), text_lengths, feats_lengths)
 
     @staticmethod
     def _log_prior(T: int, N: int) -> np.ndarray:
@@ -158,12 +168,31 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     mel_mask = sequence_mask(mel_lengths, mel.shape[-1])
     in_pad, tgt_pad = ~x_mask, ~mel_mask
 
+    # Independent branches run on side streams (forked from / joined to the current stream, so a CUDA-graph capture records
+    # them as parallel branches and autograd replays their backward on the same streams): the 6144-row encoder-side kernels
+    # fill 64 of 148 SMs, the 27 648-row mel-side kernels of the alignment module's feature encoder take the rest.
+    cuda = x.is_cuda
+    main = torch.cuda.current_stream() if cuda else None
+    am = gen.alignment_module
+    if cuda:
+        s_feat = ops.side_stream(dev, 1)
+        s_feat.wait_stream(main)
+        with torch.cuda.stream(s_feat):
+            fe = am.encode_feats(mel.transpose(1, 2))     # depends on the mel input only
     h, _ = gen.text_embedding(x)
     h = gen.encoder(h, in_pad)
     h = gen._speaker_language(h, sids, lids)
-
-    log_p_attn = gen.alignment_module(text=h, feats=mel.transpose(1, 2), text_lengths=x_lengths, feats_lengths=mel_lengths,
-                                      x_masks=in_pad)
+    if cuda:
+        s_dur = ops.side_stream(dev, 2)
+        s_dur.wait_stream(main)
+        with torch.cuda.stream(s_dur):
+            duration_hat = gen.duration_predictor(h.detach(), in_pad)   # detached input: meets the rest only at the loss
+        te = am.encode_text(h)
+        main.wait_stream(s_feat)
+        log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
+    else:
+        duration_hat = gen.duration_predictor(h.detach(), in_pad)
+        log_p_attn = am(text=h, feats=mel.transpose(1, 2), text_lengths=x_lengths, feats_lengths=mel_lengths, x_masks=in_pad)
     # The forward-sum loss only meets the rest of the step at the final sum: its sequential recursion (one CTA per sample)
     # runs on a side stream, next to the alignment search, the predictors and the decoder.
     fs_side = ops.side_stream(dev) if log_p_attn.is_cuda else None
@@ -172,37 +201,56 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
         with torch.cuda.stream(fs_side):
             fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
     durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
-    duration_hat = gen.duration_predictor(h.detach(), in_pad)
 
     p_avg = average_by_duration(durations, pitches, x_lengths, mel_lengths)
     e_avg = average_by_duration(durations, energies, x_lengths, mel_lengths)
 
-    h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg)
-    h, energy_hat = gen.energy_predictor(h, in_pad, e_avg)
+    # teacher forcing: the embeddings are driven by the targets, the predictions only feed the loss -> side streams
+    s_pitch = ops.side_stream(dev, 3) if cuda else None
+    s_energy = ops.side_stream(dev, 4) if cuda else None
+    h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg, side_stream=s_pitch)
+    h, energy_hat = gen.energy_predictor(h, in_pad, e_avg, side_stream=s_energy)
 
     # Upsampler, decoder and vocoder input carry no gradient in the reference (the vocoder is fed segment.detach(),
-    # generator/__init__.py:161, and nothing else consumes the decoder output), so they run on the inference kernels.
-    with torch.no_grad():
-        y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
-                                  y_lengths=mel_lengths)
-        y = gen.decoder(y, tgt_pad, split=False)
-        segment_size = min(gen.segment_size, y.shape[1])
-        num_frames = (mel_lengths - 4).to(y.dtype)
-        max_start = (num_frames - segment_size).clamp(min=0)
-        if seg_rand is None:
-            # inside a CUDA-graph capture the draw has to live on the device (a pageable H2D copy cannot be captured)
-            capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
-            seg_rand = torch.rand([x.shape[0]], device=dev) if capturing else torch.rand([x.shape[0]])
-        start_idx = (seg_rand.to(dev) * max_start).to(torch.long)
-        segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
-        _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt
-
-    if getattr(gen, "vocoder_needs_grad", True):
-        wav_hat = gen.vocoder.forward_train(segment)
-    else:
+    # generator/__init__.py:161, and nothing else consumes the decoder output), so they run on the inference kernels — and on
+    # their own stream: the acoustic-model losses do not depend on them.  In the pre-training phase nothing in the step
+    # consumes wav_hat at all, so the caller may defer the join to the end of the step (`gen.defer_vocoder_join`): the
+    # decoder / vocoder forward then overlaps the backward pass.
+    s_voc = ops.side_stream(dev, 5) if cuda else None
+    if s_voc is not None:
+        s_voc.wait_stream(main)
+    with (torch.cuda.stream(s_voc) if s_voc is not None else contextlib.nullcontext()):
         with torch.no_grad():
-            wav_hat = gen.vocoder.forward_train(segment)
+            y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
+                                      y_lengths=mel_lengths)
+            y = gen.decoder(y, tgt_pad, split=False)
+            segment_size = min(gen.segment_size, y.shape[1])
+            num_frames = (mel_lengths - 4).to(y.dtype)
+            max_start = (num_frames - segment_size).clamp(min=0)
+            if seg_rand is None:
+                # inside a CUDA-graph capture the draw has to live on the device (a pageable H2D copy cannot be captured)
+                capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+                seg_rand = torch.rand([x.shape[0]], device=dev) if capturing else torch.rand([x.shape[0]])
+            start_idx = (seg_rand.to(dev) * max_start).to(torch.long)
+            segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
+            _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt
 
+        if getattr(gen, "vocoder_needs_grad", True):
+            wav_hat = gen.vocoder.forward_train(segment)
+        else:
+            with torch.no_grad():
+                wav_hat = gen.vocoder.forward_train(segment)
+    pending = []
+    if s_voc is not None:
+        if getattr(gen, "defer_vocoder_join", False) and not getattr(gen, "vocoder_needs_grad", True):
+            pending.append(s_voc)
+        else:
+            main.wait_stream(s_voc)
+
+    if cuda:
+        main.wait_stream(s_dur)
+        main.wait_stream(s_pitch)
+        main.wait_stream(s_energy)
     d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
     if fs_side is not None:
         torch.cuda.current_stream().wait_stream(fs_side)
@@ -212,6 +260,9 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     lc = gen.loss_coeffs
     loss = align_loss * lc.lambda_align + d_loss * lc.lambda_duration + p_loss * lc.lambda_pitch + e_loss * lc.lambda_energy
     return {
+        "_pending_streams": pending,   # streams the caller has to join before the step ends (pre-training: the vocoder branch)
+        # main-stream tensors that branch reads: they must not be freed (and their memory re-used by this stream) before the join
+        "_pending_keepalive": [h, durations, mel_mask, x_mask, tgt_pad, in_pad, seg_rand] if pending else [],
         "wav_hat": wav_hat,
         "start_idx": start_idx,
         "segment_size": segment_size,

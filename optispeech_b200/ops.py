@@ -38,11 +38,14 @@ def step_counter(device) -> torch.Tensor:
 
 
 _SIDE_STREAMS = {}
+SIDE_STREAMS_ENABLED = True   # False: every branch stays on the current stream (per-kernel timing passes want serial execution)
 
 
 def side_stream(device, slot: int = 0) -> "torch.cuda.Stream":
     """A cached auxiliary stream per device: long single-wave kernels (the forward-sum recursion: 32 CTAs for 0.4 ms) run
     there concurrently with the main stream's work.  Callers fork with wait_stream(current) and join before using results."""
+    if not SIDE_STREAMS_ENABLED:
+        return torch.cuda.current_stream(device)
     key = (torch.device(device).index or 0, slot)
     s = _SIDE_STREAMS.get(key)
     if s is None:
