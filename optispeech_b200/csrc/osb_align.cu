@@ -530,17 +530,22 @@ __global__ void fs_lse_kernel(const float* __restrict__ lpa, const long long* __
 
 constexpr int FS_G = 8;  // emissions are fetched FS_G frames ahead (registers) so that L2 latency stays off the serial chain
 
-// The serial part: alpha (t = 1 .. T-1) and beta (t = T-2 .. 0) advance in the SAME iteration (independent chains: half
-// the barrier steps).  One CTA per sample; thread k owns blank state 2k and token state 2k+1.
+// The serial part: alpha (t = 1 .. T-1) and beta (t = T-2 .. 0) advance in the SAME iteration, on two halves of the CTA
+// (threads [0, nthr) own the alpha chain, threads [nthr, 2 nthr) the beta chain: a thread carries ONE dependency chain of
+// exp / log per step, the two recursions only share the barrier).  One CTA per sample; within a half, thread k owns blank
+// state 2k and token state 2k+1.
 __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                                    float blank_logit, const float* __restrict__ lse_ws, float* __restrict__ aw_all,
-                                   float* __restrict__ bw_all, float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx) {
+                                   float* __restrict__ bw_all, float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx,
+                                   int nsplit_halves) {
   extern __shared__ float fs_smem[];
   const int b = blockIdx.x;
   const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
   const int S = 2 * N + 1;
   const int Smax = 2 * Tx + 1;
-  const int k = threadIdx.x;
+  // split = 1 (2 (Tx + 1) threads fit a CTA): the two chains run side by side; otherwise every thread walks alpha, then beta
+  const int split = nsplit_halves;
+  const int half = split ? (blockDim.x >> 1) : blockDim.x;
   float* abuf0 = fs_smem;
   float* abuf1 = abuf0 + Smax;
   float* bbuf0 = abuf1 + Smax;
@@ -551,84 +556,98 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
   float* bw = bw_all + static_cast<long long>(b) * Tm * Tx;
   const float NEG = -INFINITY;
   if (N <= 0 || T <= 0) {
-    if (k == 0) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
+    if (threadIdx.x == 0) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
     return;
   }
-  for (int t = k; t < T; t += blockDim.x) lse[t] = lse_ws[static_cast<long long>(b) * Tm + t];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) lse[t] = lse_ws[static_cast<long long>(b) * Tm + t];
   __syncthreads();
 
+  for (int pass = 0; pass < (split ? 1 : 2); ++pass) {
+  const bool is_beta = split ? (static_cast<int>(threadIdx.x) >= half) : (pass == 1);
+  const int k = static_cast<int>(threadIdx.x) - ((split && is_beta) ? half : 0);
   const bool has_tok = k < N;
   const bool active = k <= N;
-  float* ap = abuf0; float* ac = abuf1;
-  float* bp = bbuf0; float* bc = bbuf1;
+  // this half's state buffers: cp = previous step, cc = current step
+  float* cp = is_beta ? bbuf0 : abuf0;
+  float* cc = is_beta ? bbuf1 : abuf1;
+  float* ws = is_beta ? bw : aw;
   {
     const float l0 = lse[0], lT = lse[T - 1];
     if (active) {
-      ap[2 * k] = (k == 0) ? blank_logit - l0 : NEG;
-      bp[2 * k] = (k == N) ? blank_logit - lT : NEG;
-      if (has_tok) {
-        const float at = (k == 0) ? lp[0] - l0 : NEG;
-        const float bt = (k == N - 1) ? lp[static_cast<long long>(T - 1) * Tx + k] - lT : NEG;
-        ap[2 * k + 1] = at;
-        bp[2 * k + 1] = bt;
-        aw[k] = at;
-        bw[static_cast<long long>(T - 1) * Tx + k] = bt;
+      if (!is_beta) {
+        cp[2 * k] = (k == 0) ? blank_logit - l0 : NEG;
+        if (has_tok) {
+          const float at = (k == 0) ? lp[0] - l0 : NEG;
+          cp[2 * k + 1] = at;
+          ws[k] = at;
+        }
+      } else {
+        cp[2 * k] = (k == N) ? blank_logit - lT : NEG;
+        if (has_tok) {
+          const float bt = (k == N - 1) ? lp[static_cast<long long>(T - 1) * Tx + k] - lT : NEG;
+          cp[2 * k + 1] = bt;
+          ws[static_cast<long long>(T - 1) * Tx + k] = bt;
+        }
       }
     }
   }
   __syncthreads();
-  float ea[FS_G], eb[FS_G], ea_n[FS_G], eb_n[FS_G];
+  // frame visited at step i: alpha walks forward, beta backward
+  auto frame = [&](int i) { return is_beta ? T - 1 - i : i; };
+  float e[FS_G], e_n[FS_G];
 #pragma unroll
   for (int g = 0; g < FS_G; ++g) {
     const int i = 1 + g;
-    const bool ok = has_tok && i < T;
-    ea[g] = ok ? lp[static_cast<long long>(i) * Tx + k] : 0.f;
-    eb[g] = ok ? lp[static_cast<long long>(T - 1 - i) * Tx + k] : 0.f;
+    e[g] = (has_tok && i < T) ? lp[static_cast<long long>(frame(i)) * Tx + k] : 0.f;
   }
   for (int base = 1; base < T; base += FS_G) {
 #pragma unroll
     for (int g = 0; g < FS_G; ++g) {
       const int i = base + FS_G + g;
-      const bool ok = has_tok && i < T;
-      ea_n[g] = ok ? lp[static_cast<long long>(i) * Tx + k] : 0.f;
-      eb_n[g] = ok ? lp[static_cast<long long>(T - 1 - i) * Tx + k] : 0.f;
+      e_n[g] = (has_tok && i < T) ? lp[static_cast<long long>(frame(i)) * Tx + k] : 0.f;
     }
 #pragma unroll
     for (int g = 0; g < FS_G; ++g) {
       const int i = base + g;
       if (i < T) {  // uniform across the block
-        const int ta = i, tb = T - 1 - i;
-        const float la = lse[ta], lb = lse[tb];
+        const int tf = frame(i);
+        const float lf = lse[tf];
         if (active) {
-          const float pb = ap[2 * k];
-          const float pm1 = k > 0 ? ap[2 * k - 1] : NEG;
-          ac[2 * k] = lse2(pb, pm1) + (blank_logit - la);
-          const float qb = bp[2 * k];
-          const float qt = has_tok ? bp[2 * k + 1] : NEG;
-          bc[2 * k] = lse2(qb, qt) + (blank_logit - lb);
-          if (has_tok) {
-            const float nt = lse3(ap[2 * k + 1], pb, pm1) + (ea[g] - la);
-            ac[2 * k + 1] = nt;
-            aw[static_cast<long long>(ta) * Tx + k] = nt;
-            const float mt = lse3(qt, bp[2 * k + 2], (k + 1 < N) ? bp[2 * k + 3] : NEG) + (eb[g] - lb);
-            bc[2 * k + 1] = mt;
-            bw[static_cast<long long>(tb) * Tx + k] = mt;
+          if (!is_beta) {
+            const float pb = cp[2 * k];
+            const float pm1 = k > 0 ? cp[2 * k - 1] : NEG;
+            cc[2 * k] = lse2(pb, pm1) + (blank_logit - lf);
+            if (has_tok) {
+              const float nt = lse3(cp[2 * k + 1], pb, pm1) + (e[g] - lf);
+              cc[2 * k + 1] = nt;
+              ws[static_cast<long long>(tf) * Tx + k] = nt;
+            }
+          } else {
+            const float qb = cp[2 * k];
+            const float qt = has_tok ? cp[2 * k + 1] : NEG;
+            cc[2 * k] = lse2(qb, qt) + (blank_logit - lf);
+            if (has_tok) {
+              const float mt = lse3(qt, cp[2 * k + 2], (k + 1 < N) ? cp[2 * k + 3] : NEG) + (e[g] - lf);
+              cc[2 * k + 1] = mt;
+              ws[static_cast<long long>(tf) * Tx + k] = mt;
+            }
           }
         }
         __syncthreads();
-        float* t0 = ap; ap = ac; ac = t0;
-        float* t1 = bp; bp = bc; bc = t1;
+        float* t0 = cp; cp = cc; cc = t0;
       }
     }
 #pragma unroll
-    for (int g = 0; g < FS_G; ++g) { ea[g] = ea_n[g]; eb[g] = eb_n[g]; }
+    for (int g = 0; g < FS_G; ++g) e[g] = e_n[g];
   }
-  if (k == 0) {
-    const float ll = lse2(ap[S - 1], S >= 2 ? ap[S - 2] : NEG);
+  if (threadIdx.x == 0 && !is_beta) {   // alpha chain, k = 0: cp is the last alpha column
+    const float ll = lse2(cp[S - 1], S >= 2 ? cp[S - 2] : NEG);
     const bool finite = ll > -INFINITY && ll < INFINITY;
     loss[b] = finite ? -ll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
     nll_ws[b] = finite ? -ll : INFINITY;
   }
+  __syncthreads();
+  }  // pass
 }
 
 // gradient, fully parallel over (b, t, n): softmax minus posterior occupancy, with the per-sample 1/N and the batch 1/B
@@ -658,6 +677,7 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   OSB_REQUIRE(log_p_attn && x_len && m_len && alpha_ws && loss && grad, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && Tm > 0 && Tx > 0 && Tx <= 1023, OSB_ERR_SHAPE);
   const int nthr = ((Tx + 1 + 31) / 32) * 32;
+  const int halves = 2 * nthr <= 1024 ? 1 : 0;   // alpha and beta chains side by side when both fit one CTA
   const size_t smem = sizeof(float) * (4 * static_cast<size_t>(2 * Tx + 1) + Tm);
   OSB_REQUIRE(smem <= 200 * 1024, OSB_ERR_SHAPE);
   static size_t configured = 0;
@@ -676,7 +696,8 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   const long long* ml = reinterpret_cast<const long long*>(m_len);
   const long long rows = static_cast<long long>(B) * Tm;
   osb::fs_lse_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, B, Tm, Tx);
-  osb::forward_sum_kernel<<<B, nthr, smem, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+  osb::forward_sum_kernel<<<B, halves ? 2 * nthr : nthr, smem, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx,
+                                                                   halves);
   osb::fs_grad_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
   osb::count_launch(3);
   return osb::launch_status();

@@ -312,3 +312,25 @@ def test_forward_sum_loss_fn(cuda_device):
     lp2 = torch.log_softmax(torch.randn(1, 12, 10, generator=g), dim=-1)
     l2 = ForwardSumLossFn.apply(lp2.to(dev).requires_grad_(True), tl2.to(dev), fl2.to(dev), -1.0)
     assert float(l2) == 0.0
+
+
+def test_forward_sum_long_text_takes_the_sequential_fallback(cuda_device):
+    """More than 511 tokens: the alpha and beta chains no longer fit one CTA side by side and are walked one after the other."""
+    from optispeech_b200.autograd import ForwardSumLossFn
+
+    g = torch.Generator().manual_seed(12)
+    dev = cuda_device
+    B, Tm, Tx = 2, 640, 530
+    tl, fl = torch.tensor([530, 300]), torch.tensor([640, 333])
+    lp = torch.log_softmax(torch.randn(B, Tm, Tx, generator=g) * 2, dim=-1)
+    for b in range(B):
+        lp[b, fl[b]:, :] = -float("inf")
+        lp[b, :, tl[b]:] = -float("inf")
+    ref_in = lp.clone().requires_grad_(True)
+    ref = O.forward_sum_loss(ref_in, tl, fl)
+    (rg,) = torch.autograd.grad(ref, ref_in)
+    x = lp.to(dev).requires_grad_(True)
+    loss = ForwardSumLossFn.apply(x, tl.to(dev), fl.to(dev), -1.0)
+    (gg,) = torch.autograd.grad(loss, x)
+    assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
+    _check([("dlogp", gg.cpu(), torch.nan_to_num(rg, nan=0.0))], 1e-3)
