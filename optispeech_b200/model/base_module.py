@@ -113,7 +113,27 @@ class BaseModule(nn.Module):
         self.ckpt_loaded_epoch = checkpoint.get("epoch", -1)
 
     # -- reference training logic -------------------------------------------------------------------
-    def stage_batch(self, batch):
+    def _upload_early(self, batch):
+        """Enqueue the host -> device copies of the batch's (pinned) host tensors NOW, into persistent device buffers, and return
+        the batch with those entries replaced: the DMA transfers then run while the host cuts the waveform crop."""
+        dev = self.device
+        if dev.type != "cuda":
+            return batch
+        bufs = self.__dict__.setdefault("_upload_bufs", {})
+        out = dict(batch)
+        for k, v in batch.items():
+            if k == "wav" or not isinstance(v, torch.Tensor) or v.is_cuda:
+                continue
+            key = (k, tuple(v.shape), v.dtype)
+            buf = bufs.get(key)
+            if buf is None:
+                buf = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                bufs[key] = buf
+            buf.copy_(v, non_blocking=True)
+            out[k] = buf
+        return out
+
+    def stage_batch(self, batch, upload: bool = False):
         """Host half of the reference's `_process_batch` (base_lightning_module.py:38-43): when the collate function hands the
         waveform and the lengths over in HOST memory — as the reference's does (`wav` is a numpy array,
         text_wav_datamodule.py:253-266) — the segment start indices are drawn from the CPU generator exactly as
@@ -129,6 +149,8 @@ class BaseModule(nn.Module):
             return batch
         B = int(ml.shape[0])
         seg = min(int(self.generator.segment_size), int(batch["mel"].shape[-1]))
+        if upload:   # (training_step) start the transfers of the other tensors before the host-side work below
+            batch = self._upload_early(batch)
         rand = torch.rand(B)
         start = (rand * (ml.to(torch.float32) - 4 - seg).clamp(min=0)).to(torch.long)
         hop = int(self.hop_length)
@@ -234,7 +256,7 @@ class BaseModule(nn.Module):
         batch shape and training phase and replayed afterwards (one graph launch instead of ~550 kernel launches)."""
         if self._capturing:
             return self._training_step_eager(batch, batch_idx, **kwargs)
-        batch = self.stage_batch(batch)
+        batch = self.stage_batch(batch, upload=True)
         try:
             if self.cuda_graph:
                 if self._graphed is None:

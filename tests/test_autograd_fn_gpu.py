@@ -208,12 +208,14 @@ def test_predictor_dropout_mask_is_consistent_between_forward_and_backward(cuda_
     assert rel(y, y_eval) > 0.1, "dropout had no effect"
     assert torch.equal(y, f()), "same seed must give the same mask"
     grads = torch.autograd.grad(y, [lin_w] + params, dy)
-    # exact linearity in lin_w
-    v = torch.randn_like(lin_w)
+    # exact linearity in lin_w.  The direction comes from the seeded CPU generator (the device generator's state depends on
+    # the tests that ran before); the backward recomputes the LayerNorm statistics from the fp16-saved activations, so the
+    # two sides agree to the fp16 rounding level (2^-11 = 4.9e-4 per element), not to fp32.
+    v = torch.randn(lin_w.shape, generator=g).to(dev)
     fd = ((f(lw=lin_w + v) - y) * dy).sum()
     an = (grads[0] * v).sum()
     print(f"  lin_w directional: fd {float(fd):.5f} analytic {float(an):.5f}")
-    assert abs(float(fd - an)) <= 2e-3 * max(1.0, abs(float(an)))
+    assert abs(float(fd - an)) <= 5e-3 * max(1.0, abs(float(an)))
 
 
 def test_inner_dropout_mask_matches_between_relu_ln_forward_and_backward_epilogues(cuda_device):
