@@ -14,7 +14,8 @@ from . import ops
 
 
 # --------------------------------------------------------------------------------------------------
-# weight packing helpers (fp32 master -> fp16 operands), forward and transposed (dgrad) forms
+# weight packing helpers (fp32 master -> fp16 operands).  Only forward packs exist: data gradients read the same pack as an
+# MN-major B operand (ops.gemm(..., w_mn=True[, tap_reverse=True])).
 # --------------------------------------------------------------------------------------------------
 def pack_nk(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     """(N, K) fp32 -> (1, N, Kp) fp16."""
@@ -54,23 +55,6 @@ def pack_param_conv(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tenso
     if packer is None or not w.is_contiguous():
         return ops.pack_conv_h16(w, k_pad=k_pad)
     return packer.request("conv", [w], None, k_pad, lambda: ops.pack_conv_h16(w, k_pad=k_pad))
-
-
-def pack_kn(w: torch.Tensor) -> torch.Tensor:
-    """(N, K) fp32 -> transposed (1, K, N) fp16 (the dgrad operand)."""
-    N, K = w.shape
-    return ops.pack_h16(w.contiguous(), rows=K, cols=N, src_ld=1, src_cs=K).view(1, K, N)
-
-
-def pack_conv_fwd(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
-    """Conv1d weight (N, Cin, k) -> (k, N, Cin_pad) fp16."""
-    return ops.pack_conv_h16(w, k_pad=k_pad)
-
-
-def pack_conv_bwd(w: torch.Tensor) -> torch.Tensor:
-    """Conv1d weight (N, Cin, k) -> dgrad operand (k, Cin, N) fp16 with the taps reversed:
-    out[tap', c, n] = w[n, c, k-1-tap']."""
-    return ops.pack_conv_h16(w, transpose_reverse=True)
 
 
 def _conv_wgrad(g_h16: torch.Tensor, a_h16: torch.Tensor, N: int, Cin: int, k: int, pad: int) -> torch.Tensor:
