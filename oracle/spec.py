@@ -186,6 +186,8 @@ def deterministic_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 0, 
         leaf = key.rsplit(".", 1)[-1]
         if key.endswith("embed_positions.scale"):
             v = torch.full(shape, 0.08)
+        elif leaf == "weight_g":        # weight_norm magnitude (discriminators): positive, O(1)
+            v = 0.75 + 0.5 * r.abs()
         elif leaf == "alpha":
             v = 1.0 + 0.1 * r
         elif leaf == "gamma":

@@ -199,3 +199,65 @@ def test_transformer_generator_matches_reference():
             assert g is None or float(g.abs().max()) == 0.0, k
         else:
             assert g is not None and abs(float(g.norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6) + 1e-5, k
+
+
+# ---- GAN-phase discriminators and losses (tests/golden/make_golden_disc.py) ---------------------------------
+def _disc_sd():
+    from oracle.discriminators import discriminator_shapes
+
+    return deterministic_state_dict(discriminator_shapes(), seed=0)
+
+
+def test_discriminator_oracle_matches_reference():
+    from oracle import discriminators as D
+
+    fx = _load("discriminator.npz")
+    sd = _disc_sd()
+    assert sum(int(np.prod(v.shape)) for v in sd.values()) == 41_705_968
+    wav, wav_hat = _t(fx["wav"]), _t(fx["wav_hat"]).requires_grad_(True)
+    spec = ModelSpec()
+    with torch.no_grad():
+        loss_d, log_d = D.forward_disc(sd, wav, wav_hat.detach())
+    assert abs(float(loss_d) - float(fx["loss_disc"])) <= 2e-5 * abs(float(fx["loss_disc"]))
+    for k, v in log_d.items():
+        assert abs(float(v) - float(fx[f"disc_{k}"])) <= 2e-5 * max(1.0, abs(float(fx[f"disc_{k}"]))), k
+    loss_g, log_g = D.forward_gen(sd, wav, wav_hat, spec)
+    for k, v in log_g.items():
+        assert abs(float(v) - float(fx[f"gen_{k}"])) <= 5e-5 * max(1.0, abs(float(fx[f"gen_{k}"]))), k
+    assert abs(float(loss_g) - float(fx["loss_gen"])) <= 5e-5 * abs(float(fx["loss_gen"]))
+    loss_g.backward()
+    assert abs(float(wav_hat.grad.norm()) - float(fx["dwav_hat_norm"])) <= 1e-3 * float(fx["dwav_hat_norm"])
+    assert np.abs(wav_hat.grad[:, ::64].numpy() - fx["dwav_hat_slice"]).max() <= 1e-3 * np.abs(fx["dwav_hat_slice"]).max()
+    with torch.no_grad():
+        outs, _, fr, _ = D._multi(sd, wav, wav_hat.detach(), "mpd")
+        assert [o.shape[1] for o in outs] == fx["mpd_out_sizes"].tolist()
+        assert np.allclose([[float(f.mean()) for f in fm] for fm in fr], fx["mpd_fmap_means"], rtol=1e-4, atol=1e-6)
+        outs, _, fr, _ = D._multi(sd, wav, wav_hat.detach(), "mrd")
+        assert [o.shape[1] for o in outs] == fx["mrd_out_sizes"].tolist()
+        assert np.allclose([[float(f.mean()) for f in fm] for fm in fr], fx["mrd_fmap_means"], rtol=1e-4, atol=1e-6)
+
+
+def test_discriminator_host_modules_match_reference():
+    """The product's MPD / MRD modules (stock PyTorch this round, reference module tree) and its hinge / feature-matching
+    losses against the same goldens, on the CPU."""
+    from optispeech_b200.model.vocoder.wavenext.disc._discriminators import MultiPeriodDiscriminator, MultiResolutionDiscriminator
+    from optispeech_b200.model.vocoder.wavenext.disc.loss import DiscriminatorLoss, FeatureMatchingLoss, GeneratorLoss
+
+    fx = _load("discriminator.npz")
+    sd = _disc_sd()
+    mpd, mrd = MultiPeriodDiscriminator(), MultiResolutionDiscriminator()
+    mpd.load_state_dict({k[len("multiperioddisc."):]: v for k, v in sd.items() if k.startswith("multiperioddisc.")}, strict=True)
+    mrd.load_state_dict({k[len("multiresddisc."):]: v for k, v in sd.items() if k.startswith("multiresddisc.")}, strict=True)
+    wav, wav_hat = _t(fx["wav"]), _t(fx["wav_hat"])
+    with torch.no_grad():
+        r_mp, g_mp, fr_mp, fg_mp = mpd(y=wav, y_hat=wav_hat)
+        r_mr, g_mr, fr_mr, fg_mr = mrd(y=wav, y_hat=wav_hat)
+        l_mp, parts_mp, _ = DiscriminatorLoss()(disc_real_outputs=r_mp, disc_generated_outputs=g_mp)
+        l_mr, parts_mr, _ = DiscriminatorLoss()(disc_real_outputs=r_mr, disc_generated_outputs=g_mr)
+        assert abs(float(l_mp / len(parts_mp)) - float(fx["disc_loss_mp"])) <= 2e-5 * max(1.0, float(fx["disc_loss_mp"]))
+        assert abs(float(l_mr / len(parts_mr)) - float(fx["disc_loss_mrd"])) <= 2e-5 * max(1.0, float(fx["disc_loss_mrd"]))
+        lg_mp, pg = GeneratorLoss()(disc_outputs=g_mp)
+        assert abs(float(lg_mp / len(pg)) - float(fx["gen_loss_gen_mp"])) <= 2e-5 * max(1.0, float(fx["gen_loss_gen_mp"]))
+        fm_mr = FeatureMatchingLoss()(fmap_r=fr_mr, fmap_g=fg_mr) / len(fr_mr)
+        assert abs(float(fm_mr) - float(fx["gen_loss_fm_mrd"])) <= 5e-5 * max(1.0, float(fx["gen_loss_fm_mrd"]))
+        assert [o.shape[1] for o in r_mp] == fx["mpd_out_sizes"].tolist() and [o.shape[1] for o in r_mr] == fx["mrd_out_sizes"].tolist()
