@@ -377,6 +377,13 @@ int osb_mel_loss(const float* x_hat, const float* y, const float* window, const 
                  const int32_t* jlo, const int32_t* jhi, int32_t n_mels, int32_t B, int32_t L, int32_t n_fft, int32_t hop, int32_t win,
                  float clamp_min, double* stats, const float* coef, float* dx_hat, void* stream);
 
+/* FastSpeech2Loss (optispeech/model/generator/loss.py:83-140) as the reference evaluates it (its masks broadcast inside
+ * masked_select: see osb_loss.cu) and its gradients in one launch.  All inputs fp32 (B, Tx); x_len (B) int64.
+ *   losses[0] = duration MSE in the log domain, losses[1] = pitch SmoothL1, losses[2] = energy SmoothL1 (weighted means)
+ *   g_d / g_p / g_e (B, Tx) = d losses[0] / d d_hat, d losses[1] / d p_hat, d losses[2] / d e_hat */
+int osb_fs2_losses(const float* d_hat, const float* p_hat, const float* e_hat, const float* ds, const float* p_tgt, const float* e_tgt,
+                   const int64_t* x_len, float* losses, float* g_d, float* g_p, float* g_e, int32_t B, int32_t Tx, void* stream);
+
 /* Every fp32 -> fp16 weight pack of a training step in ONE launch (the weights change every step, so the packs are
  * per-step work: 44 small launches otherwise).  jobs_dev: device array, sorted by first_elem (prefix sums of the
  * destination element counts, first_elem[0] = 0); total_elems = sum of destination elements.

@@ -457,3 +457,20 @@ class TransformerLayerFn(Function):
         dwq, dwk, dwv = dwqkv[0, :D], dwqkv[0, D:2 * D], dwqkv[0, 2 * D:]
         return (dx, None, None, None, None, None, None, None, dn1w, dn1b, dwq, dbqkv[:D], dwk, dbqkv[D:2 * D], dwv, dbqkv[2 * D:],
                 dwo[0], dbo, dn2w, dn2b, dw1.view(U, D, 1), db1, dw2.view(D, U, 1), db2)
+
+
+# --------------------------------------------------------------------------------------------------
+# FastSpeech2 variance losses (duration / pitch / energy), one kernel for the three losses and their gradients
+# --------------------------------------------------------------------------------------------------
+class FastSpeech2LossFn(Function):
+    @staticmethod
+    def forward(ctx, d_hat, p_hat, e_hat, ds, p_tgt, e_tgt, x_len):
+        losses, gd, gp, ge = ops.fs2_losses(d_hat.contiguous(), p_hat.contiguous(), e_hat.contiguous(), ds.float().contiguous(),
+                                            p_tgt.float().contiguous(), e_tgt.float().contiguous(), x_len.contiguous())
+        ctx.save_for_backward(gd, gp, ge)
+        return losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, dl_d, dl_p, dl_e):
+        gd, gp, ge = ctx.saved_tensors
+        return gd * dl_d, gp * dl_p, ge * dl_e, None, None, None, None

@@ -1,0 +1,98 @@
+// osb_loss.cu — the FastSpeech2 variance losses of the training step and their gradients in one launch.
+//
+// Replaces FastSpeech2Loss.forward (optispeech/model/generator/loss.py:83-140) AS THE REFERENCE EVALUATES IT: its masks carry a
+// stray singleton axis, so `masked_select` broadcasts — the duration term takes element (b,i) len_b times for EVERY i < Tx
+// (padded positions included, target log(0 + 1e-8)), the pitch / energy terms take element (b,i) once per sample whose length
+// exceeds i — followed by 'mean' reductions:
+//     d_loss = sum_b len_b * sum_i (d_hat[b,i] - log(ds[b,i] + 1e-8))^2 / (sum_b len_b * Tx)
+//     w[i]   = #{b : len_b > i};   p_loss = sum_{b,i} smooth_l1(p_hat[b,i] - p_tgt[b,i]) * w[i] / (B * sum_i w[i])   (same for e)
+// The ~25 small reductions / elementwise kernels of the PyTorch formulation (and as many in its backward) sit on the critical
+// path between the joins of the prediction branches and the start of the backward pass; here they are one CTA.
+#include "osb_host.h"
+#include "osb_ptx.cuh"
+
+namespace osb {
+namespace {
+
+constexpr int FL_THREADS = 1024;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < (FL_THREADS / 32) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) t = warp_sum(t);
+  __syncthreads();
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(FL_THREADS)
+fs2_losses_kernel(const float* __restrict__ d_hat, const float* __restrict__ p_hat, const float* __restrict__ e_hat,
+                  const float* __restrict__ ds, const float* __restrict__ p_tgt, const float* __restrict__ e_tgt,
+                  const long long* __restrict__ x_len, float* __restrict__ losses, float* __restrict__ g_d, float* __restrict__ g_p,
+                  float* __restrict__ g_e, int B, int Tx) {
+  extern __shared__ float fl_smem[];
+  float* w = fl_smem;            // [Tx] samples longer than i
+  float* lens = w + Tx;          // [B]
+  float* red = lens + B;         // [32]
+  for (int b = threadIdx.x; b < B; b += FL_THREADS) lens[b] = static_cast<float>(x_len[b]);
+  __syncthreads();
+  float wsum_part = 0.f;
+  for (int i = threadIdx.x; i < Tx; i += FL_THREADS) {
+    int c = 0;
+    for (int b = 0; b < B; ++b) c += (lens[b] > static_cast<float>(i)) ? 1 : 0;
+    w[i] = static_cast<float>(c);
+    wsum_part += static_cast<float>(c);
+  }
+  float len_part = 0.f;
+  for (int b = threadIdx.x; b < B; b += FL_THREADS) len_part += lens[b];
+  const float wsum = block_sum(wsum_part, red);
+  const float lsum = block_sum(len_part, red);
+  const float d_den = lsum * static_cast<float>(Tx);
+  const float pe_den = wsum * static_cast<float>(B);
+  const float inv_d = d_den > 0.f ? 1.f / d_den : 0.f;
+  const float inv_pe = pe_den > 0.f ? 1.f / pe_den : 0.f;
+  float sd = 0.f, sp = 0.f, se = 0.f;
+  const int n = B * Tx;
+  for (int idx = threadIdx.x; idx < n; idx += FL_THREADS) {
+    const int b = idx / Tx, i = idx - b * Tx;
+    const float dd = d_hat[idx] - logf(ds[idx] + 1e-8f);
+    sd = fmaf(dd * dd, lens[b], sd);
+    g_d[idx] = 2.f * dd * lens[b] * inv_d;
+    const float wi = w[i];
+    const float dp = p_hat[idx] - p_tgt[idx];
+    const float ap = fabsf(dp);
+    sp = fmaf(ap < 1.f ? 0.5f * dp * dp : ap - 0.5f, wi, sp);          // SmoothL1, beta = 1 (loss.py:77-78)
+    g_p[idx] = fminf(fmaxf(dp, -1.f), 1.f) * wi * inv_pe;
+    const float de = e_hat[idx] - e_tgt[idx];
+    const float ae = fabsf(de);
+    se = fmaf(ae < 1.f ? 0.5f * de * de : ae - 0.5f, wi, se);
+    g_e[idx] = fminf(fmaxf(de, -1.f), 1.f) * wi * inv_pe;
+  }
+  sd = block_sum(sd, red);
+  sp = block_sum(sp, red);
+  se = block_sum(se, red);
+  if (threadIdx.x == 0) {
+    losses[0] = sd * inv_d;
+    losses[1] = sp * inv_pe;
+    losses[2] = se * inv_pe;
+  }
+}
+
+}  // namespace
+}  // namespace osb
+
+extern "C" int osb_fs2_losses(const float* d_hat, const float* p_hat, const float* e_hat, const float* ds, const float* p_tgt,
+                              const float* e_tgt, const int64_t* x_len, float* losses, float* g_d, float* g_p, float* g_e, int32_t B,
+                              int32_t Tx, void* stream) {
+  OSB_REQUIRE(d_hat && p_hat && e_hat && ds && p_tgt && e_tgt && x_len && losses && g_d && g_p && g_e, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tx > 0 && (static_cast<size_t>(Tx) + B + 32) * sizeof(float) <= 48 * 1024, OSB_ERR_SHAPE);
+  const size_t smem = (static_cast<size_t>(Tx) + B + 32) * sizeof(float);
+  osb::fs2_losses_kernel<<<1, osb::FL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_hat, p_hat, e_hat, ds, p_tgt, e_tgt, reinterpret_cast<const long long*>(x_len), losses, g_d, g_p, g_e, B, Tx);
+  osb::count_launch();
+  return osb::launch_status();
+}

@@ -138,6 +138,10 @@ def fastspeech2_losses(d_outs, p_outs, e_outs, ds, ps, es, ilens):
     axis, so masked_select broadcasts: the duration term takes element (b,i) len_b times for EVERY i < Tx (padded
     positions included, target log(0 + 1e-8)); the pitch / energy terms take element (b,i) once per sample whose
     length exceeds i.  'mean' reduction over those multisets."""
+    if d_outs.is_cuda:   # one kernel for the three losses and their gradients (osb_loss.cu)
+        from ...autograd import FastSpeech2LossFn
+
+        return FastSpeech2LossFn.apply(d_outs, p_outs, e_outs, ds, ps, es, ilens)
     B, Tx = d_outs.shape
     lens = ilens.to(d_outs.dtype)
     d_err = (d_outs - torch.log(ds.float() + 1e-8)) ** 2

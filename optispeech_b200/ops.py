@@ -568,3 +568,14 @@ def add_posenc(x: torch.Tensor, pe: Optional[torch.Tensor], alpha: Optional[torc
     _lib.check(_lib.load().osb_add_posenc(_ptr(_f32(x)), _ptr(pe), _ptr(alpha), _ptr(out), B, T, Cc, float(dropout_p), int(dropout_seed),
                                           _seed_dev(x, dropout_p), _stream()), "osb_add_posenc")
     return out
+
+
+def fs2_losses(d_hat, p_hat, e_hat, ds, p_tgt, e_tgt, x_len):
+    """-> (losses (3,) fp32 = [duration, pitch, energy], g_d, g_p, g_e (B,Tx) = gradients of the respective loss)."""
+    B, Tx = d_hat.shape
+    losses = torch.empty(3, device=d_hat.device, dtype=torch.float32)
+    g = [torch.empty((B, Tx), device=d_hat.device, dtype=torch.float32) for _ in range(3)]
+    _lib.check(_lib.load().osb_fs2_losses(_ptr(_f32(d_hat)), _ptr(_f32(p_hat)), _ptr(_f32(e_hat)), _ptr(_f32(ds)), _ptr(_f32(p_tgt)),
+                                          _ptr(_f32(e_tgt)), _ptr(x_len), _ptr(losses), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), B, Tx,
+                                          _stream()), "osb_fs2_losses")
+    return losses, g[0], g[1], g[2]
