@@ -384,6 +384,13 @@ int osb_mel_loss(const float* x_hat, const float* y, const float* window, const 
 int osb_fs2_losses(const float* d_hat, const float* p_hat, const float* e_hat, const float* ds, const float* p_tgt, const float* e_tgt,
                    const int64_t* x_len, float* losses, float* g_d, float* g_p, float* g_e, int32_t B, int32_t Tx, void* stream);
 
+/* align_loss = forward-sum loss + bin loss (generator/__init__.py:174-175; bin loss: alignments.py:236-238) from the outputs
+ * of osb_forward_sum (per-sample losses, gradient) and osb_mas (path):  out[0] = align_loss, out[1] = forward-sum part,
+ * out[2] = bin part = -(1/B) sum_b mean_t log_p_attn[b,t,path[b,t]];  fs_grad (B,Tm,Tx) receives the bin-loss gradient
+ * in place, so it becomes d(align_loss)/d(log_p_attn). */
+int osb_align_loss_fold(const float* log_p_attn, const int32_t* path, const int64_t* m_len, const float* per_sample_fs, float* fs_grad,
+                        float* out /*(3)*/, int32_t B, int32_t Tm, int32_t Tx, void* stream);
+
 /* Every fp32 -> fp16 weight pack of a training step in ONE launch (the weights change every step, so the packs are
  * per-step work: 44 small launches otherwise).  jobs_dev: device array, sorted by first_elem (prefix sums of the
  * destination element counts, first_elem[0] = 0); total_elems = sum of destination elements.

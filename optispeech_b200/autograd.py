@@ -474,3 +474,21 @@ class FastSpeech2LossFn(Function):
     def backward(ctx, dl_d, dl_p, dl_e):
         gd, gp, ge = ctx.saved_tensors
         return gd * dl_d, gp * dl_p, ge * dl_e, None, None, None, None
+
+
+class AlignLossFn(Function):
+    """align_loss = ForwardSumLoss + bin loss (generator/__init__.py:174-175).  `per_sample_fs` / `fs_grad` come from
+    ops.forward_sum (run on a side stream), `path` from ops.mas; the bin-loss gradient is folded into fs_grad in place."""
+
+    @staticmethod
+    def forward(ctx, log_p_attn, per_sample_fs, fs_grad, path, m_len):
+        out = ops.align_loss_fold(log_p_attn.contiguous(), path, m_len.contiguous(), per_sample_fs, fs_grad)
+        ctx.save_for_backward(fs_grad)
+        fs_part, bin_part = out[1], out[2]
+        ctx.mark_non_differentiable(fs_part, bin_part)
+        return out[0], fs_part, bin_part
+
+    @staticmethod
+    def backward(ctx, g, _g1, _g2):
+        (fs_grad,) = ctx.saved_tensors
+        return fs_grad * g, None, None, None, None

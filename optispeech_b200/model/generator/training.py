@@ -202,9 +202,11 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     fs_side = ops.side_stream(dev) if log_p_attn.is_cuda else None
     if fs_side is not None:
         fs_side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(fs_side):
-            fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
-    durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
+        with torch.cuda.stream(fs_side):   # per-sample losses and d(fs_loss)/d(log_p_attn); joined with the bin loss below
+            fs_per_sample, fs_grad = ops.forward_sum(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous(), -1.0)
+        mas_path, durations = ops.mas(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous())
+    else:
+        durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
 
     p_avg = average_by_duration(durations, pitches, x_lengths, mel_lengths)
     e_avg = average_by_duration(durations, energies, x_lengths, mel_lengths)
@@ -257,10 +259,13 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
         main.wait_stream(s_energy)
     d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
     if fs_side is not None:
+        from ...autograd import AlignLossFn
+
         torch.cuda.current_stream().wait_stream(fs_side)
+        align_loss, fs_loss, bin_loss = AlignLossFn.apply(log_p_attn, fs_per_sample, fs_grad, mas_path, mel_lengths)
     else:
         fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
-    align_loss = fs_loss + bin_loss
+        align_loss = fs_loss + bin_loss
     lc = gen.loss_coeffs
     loss = align_loss * lc.lambda_align + d_loss * lc.lambda_duration + p_loss * lc.lambda_pitch + e_loss * lc.lambda_energy
     return {

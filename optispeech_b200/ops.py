@@ -579,3 +579,12 @@ def fs2_losses(d_hat, p_hat, e_hat, ds, p_tgt, e_tgt, x_len):
                                           _ptr(_f32(e_tgt)), _ptr(x_len), _ptr(losses), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), B, Tx,
                                           _stream()), "osb_fs2_losses")
     return losses, g[0], g[1], g[2]
+
+
+def align_loss_fold(log_p_attn, path, m_len, per_sample_fs, fs_grad):
+    """-> (3,) fp32 = [align_loss, forward-sum part, bin part]; adds the bin-loss gradient into `fs_grad` in place."""
+    B, Tm, Tx = log_p_attn.shape
+    out = torch.empty(3, device=log_p_attn.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_align_loss_fold(_ptr(_f32(log_p_attn)), _ptr(path), _ptr(m_len), _ptr(per_sample_fs), _ptr(fs_grad), _ptr(out),
+                                               B, Tm, Tx, _stream()), "osb_align_loss_fold")
+    return out
