@@ -204,3 +204,105 @@ def test_transformer_config_instantiates_with_reference_layout():
     ref = {str(k): tuple(int(v) for v in str(s).split(",") if v) for k, s in zip(fx["state_dict_keys"], fx["state_dict_shapes"])}
     assert {k: tuple(v.shape) for k, v in m.generator.state_dict().items()} == ref
     assert float(m.generator.encoder.transformer.embed[0].alpha) == 1.0
+
+
+def test_step_packer_plan_and_job_table(monkeypatch):
+    """model/packing.StepPacker on the CPU: record the pack requests of one forward, serve the same sequence from the plan
+    afterwards (the single osb_pack_multi launch is replaced by an interpreter of its job table), drop the plan on deviation."""
+    import ctypes as C
+
+    from optispeech_b200 import _lib
+    from optispeech_b200.model.packing import StepPacker
+
+    g = torch.Generator().manual_seed(4)
+    w_a, w_b = torch.randn(6, 8, generator=g), torch.randn(10, 8, generator=g)      # two Linear weights stacked along N
+    scale = torch.rand(8, generator=g) + 0.5
+    w_c = torch.randn(5, 3, 7, generator=g)                                          # Conv1d (N, Cin, k)
+
+    def nk_direct(ws, cs):
+        w = torch.cat(ws, 0) * (cs if cs is not None else 1.0)
+        return w.half().view(1, -1, 8)
+
+    def conv_direct(w, kp):
+        out = torch.zeros(w.shape[2], w.shape[0], kp)
+        out[:, :, : w.shape[1]] = w.permute(2, 0, 1)
+        return out.half()
+
+    launches = []
+
+    class FakeLib:
+        @staticmethod
+        def osb_pack_multi(table_ptr, n_jobs, total, stream):
+            jobs = (_lib.PackJob * n_jobs).from_address(table_ptr)
+            done = 0
+            for j in jobs:
+                n = j.rows * j.dst_cols * (j.k if j.kind == 1 else 1)
+                assert j.first_elem == done
+                src_n = j.rows * j.cols * (j.k if j.kind == 1 else 1)
+                src = np.ctypeslib.as_array((C.c_float * src_n).from_address(j.src))
+                dst = np.ctypeslib.as_array((C.c_uint16 * n).from_address(j.dst)).view(np.float16)
+                if j.kind == 0:
+                    m = src.reshape(j.rows, j.cols).copy()
+                    if j.col_scale:
+                        m *= np.ctypeslib.as_array((C.c_float * j.cols).from_address(j.col_scale))[None, :]
+                    buf = np.zeros((j.rows, j.dst_cols), np.float32)
+                    buf[:, : j.cols] = m
+                else:
+                    buf = np.zeros((j.k, j.rows, j.dst_cols), np.float32)
+                    buf[:, :, : j.cols] = src.reshape(j.rows, j.cols, j.k).transpose(2, 0, 1)
+                dst[:] = buf.astype(np.float16).reshape(-1)
+                done += n
+            assert done == total
+            launches.append(n_jobs)
+            return 0
+
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib)
+    from optispeech_b200 import ops
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+
+    pk = StepPacker()
+    dev = torch.device("cpu")
+
+    def forward(third_shape_change=False):
+        pk.begin(dev)
+        a = pk.request("nk", [w_a, w_b], scale, None, lambda: nk_direct([w_a, w_b], scale))
+        b = pk.request("nk", [w_b], None, None, lambda: nk_direct([w_b], None))
+        src = w_c[:4].contiguous() if third_shape_change else w_c
+        c = pk.request("conv", [src], None, 8, lambda: conv_direct(src, 8))
+        pk.end()
+        return a, b, c
+
+    a0, b0, c0 = forward()                                   # recording step: direct packs, plan built at end()
+    assert pk.plan is not None and pk.plan["n_jobs"] == 4 and not launches
+    w_a.mul_(2.0); w_c.add_(1.0)                             # "optimizer step": same storage, new values
+    a1, b1, c1 = forward()                                   # served from ONE launch of the job table
+    assert launches == [4]
+    assert torch.equal(a1, nk_direct([w_a, w_b], scale)) and torch.equal(b1, nk_direct([w_b], None)) and torch.equal(c1, conv_direct(w_c, 8))
+    assert a1.data_ptr() == pk.plan["outs"][0].data_ptr() and a1.shape == a0.shape
+    forward(third_shape_change=True)                         # the step deviates: plan dropped, that request packed directly
+    assert pk.plan is None
+    forward()                                                # records again
+    assert pk.plan is not None and launches == [4, 4]
+
+
+def test_presampled_drop_paths_follow_the_reference_distribution():
+    """presample_drop_paths draws Bernoulli(keep_l) / keep_l per sample and block (reference convnext.py:121-129) for all blocks
+    at once; every DropPath then consumes its own row exactly once."""
+    from optispeech_b200.model.generator.modules.convnext import ConvNeXtBackbone, DropPath, presample_drop_paths
+
+    torch.manual_seed(0)
+    bb = ConvNeXtBackbone(dim=256, intermediate_dim=1024, num_layers=4, drop_path=0.2).train()
+    mods = [m for m in bb.modules() if isinstance(m, DropPath)]
+    assert [round(m.drop_prob, 4) for m in mods] == [0.0667, 0.1333, 0.2]          # linspace(0, 0.2, 4) without the zero rate
+    B = 4096
+    presample_drop_paths(bb, B, torch.device("cpu"))
+    for m in mods:
+        keep = 1.0 - m.drop_prob
+        s = m.sample_scale(B, torch.device("cpu"))
+        vals = set(torch.unique(s).tolist())
+        assert vals <= {0.0, float(torch.tensor(1.0) / torch.tensor(keep))} or all(abs(v) < 1e-6 or abs(v - 1 / keep) < 1e-5 for v in vals)
+        assert abs(float((s > 0).float().mean()) - keep) < 0.03
+        assert "_presampled" not in m.__dict__                                      # consumed
+    bb.eval()
+    presample_drop_paths(bb, B, torch.device("cpu"))
+    assert all(m.sample_scale(B, torch.device("cpu")) is None for m in mods)          # eval: identity
