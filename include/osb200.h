@@ -102,7 +102,8 @@ enum {
    * to tcgen05.mma as an MN-major B operand:  acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] * w[tap', k, n],
    * tap' = tap, or taps-1-tap with TAP_REVERSE (the transposed convolution of a Conv1d dgrad).  N % 64 == 0. */
   OSB_FLAG_W_MN = 1024,
-  OSB_FLAG_TAP_REVERSE = 2048
+  OSB_FLAG_TAP_REVERSE = 2048,
+  OSB_FLAG_LRELU = 4096    /* EPI_BIAS only: out = leaky_relu(acc + bias, lrelu_slope)                              */
 };
 
 typedef struct osb_gemm_desc {
@@ -143,6 +144,13 @@ typedef struct osb_gemm_desc {
   int32_t w_batched;
   const int64_t* col_len; /* ATTN_LOGP: (B) number of valid columns (text length)                    */
   float* out_colsum;      /* COLSUM: (N) fp32, accumulated with atomics (caller zeroes it)            */
+  /* Strided convolution (row_stride > 1; groundwork for the period discriminators' (5,1)/stride-3 convs,
+   * vocoder/wavenext/disc/_discriminators.py:52-60): output row t reads input rows t*row_stride + tap - pad of an input with
+   * T_in rows per batch (a is (B, T_in, lda)); T is the number of OUTPUT rows.  The stride is a TMA traversal stride
+   * (elementStrides) — no im2col copy.  0 / 1 = dense rows (T_in ignored). */
+  int32_t row_stride;
+  int32_t T_in;
+  float lrelu_slope;      /* OSB_FLAG_LRELU: negative slope                                          */
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);

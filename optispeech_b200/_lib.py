@@ -16,7 +16,7 @@ OSB_OK = 0
 # osb_epilogue
 EPI_BIAS, EPI_GELU, EPI_RESID, EPI_RELU_LN, EPI_BIAS_LN, EPI_RELU, EPI_GELU_BWD, EPI_LN_BWD, EPI_RELU_LN_BWD, EPI_RELU_BWD, EPI_ATTN_LOGP, EPI_AXPY = range(12)
 # flags
-FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU, FLAG_NO_F32, FLAG_COLSUM, FLAG_W_MN, FLAG_TAP_REVERSE = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
+FLAG_CLIP, FLAG_KEEPMASK, FLAG_OUT_H16, FLAG_SAVE_PRE, FLAG_DOT, FLAG_SPLIT_IN, FLAG_SPLIT_OUT, FLAG_RELU, FLAG_NO_F32, FLAG_COLSUM, FLAG_W_MN, FLAG_TAP_REVERSE, FLAG_LRELU = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096
 
 
 class GemmDesc(C.Structure):
@@ -57,6 +57,9 @@ class GemmDesc(C.Structure):
         ("w_batched", C.c_int32),
         ("col_len", C.c_void_p),
         ("out_colsum", C.c_void_p),
+        ("row_stride", C.c_int32),
+        ("T_in", C.c_int32),
+        ("lrelu_slope", C.c_float),
     ]
 
 

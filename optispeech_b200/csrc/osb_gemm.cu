@@ -51,6 +51,8 @@ struct GemmKParams {
   int w_batch;      // 1: slice index += batch (per-batch B operand)
   const long long* col_len;
   float* colsum;    // COLSUM: (N) column sums of the fp16 output
+  int row_stride;   // > 1: strided convolution, output row t reads input row t*row_stride + tap - pad
+  float lrelu;      // OSB_FLAG_LRELU slope
   int w_mn;         // 1: W is (taps, K, ldw >= N) with the OUTPUT index contiguous (MN-major B operand): dgrad on the forward pack
   int tap_rev;      // 1: tap t reads weight slice taps-1-t (transposed convolution)
   long long* trace; // optional (developer): clock64 timeline of CTA (0,0), see tools/probe_gemm_trace.py
@@ -551,6 +553,10 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
+        if (p.flags & OSB_FLAG_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * p.lrelu;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= keep;
         if (!(p.flags & OSB_FLAG_NO_F32)) warp_store_f32(sl, static_cast<float*>(p.out) + row0 * p.ldo + n, p.ldo, nrows, v);
@@ -744,7 +750,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w_k = kb * BKE + (sub == 2 ? p.w_lo_koff : 0);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
-        tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 + tap - p.pad, b);
+        if (p.row_stride > 1) {
+          // strided rows: a TMA box is at most 256 SOURCE rows, i.e. 64 loaded rows at stride <= 4: two boxes per 128-row tile
+          tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 * p.row_stride + tap - p.pad, b);
+          tma_load_3d(sA + 64 * ROW_BYTES, &tmA, &full_bar[s], a_k, (t0 + 64) * p.row_stride + tap - p.pad, b);
+        } else {
+          tma_load_3d(sA, &tmA, &full_bar[s], a_k, t0 + tap - p.pad, b);
+        }
         if (p.w_mn) {
           // MN-major B: 64 contraction rows x BN output columns, as BN/64 chunks of [64 rows x 128 B]
           const int slice = p.tap_rev ? p.taps - 1 - tap : tap;
@@ -1054,7 +1066,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap_3d(CUtensorMap* out, const void* base, TmaDtype dt, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+                 uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1, uint32_t elem_stride1) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return OSB_ERR_DRIVER;
   const uint64_t es = (dt == TMA_F32) ? 4 : 2;
@@ -1066,7 +1078,8 @@ int make_tmap_3d(CUtensorMap* out, const void* base, TmaDtype dt, uint64_t d0, u
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_elems * es, stride2_elems * es};
   cuuint32_t box[3] = {box0, box1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
+  if (elem_stride1 < 1 || elem_stride1 > 8 || box1 > 256) return OSB_ERR_SHAPE;
+  cuuint32_t estr[3] = {1, elem_stride1, 1};
   CUresult r = fn(out, cdt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? OSB_OK : OSB_ERR_DRIVER;
@@ -1104,8 +1117,17 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   const bool split_in = (d->flags & OSB_FLAG_SPLIT_IN) != 0;
   if (split_in) OSB_REQUIRE(d->K % BKE == 0 && d->lda >= 2 * static_cast<int64_t>(d->K), OSB_ERR_SHAPE);
   CUtensorMap tmA, tmW;
-  int rc = make_tmap_3d(&tmA, d->a, TMA_F16, split_in ? 2 * d->K : d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda,
-                        BKE, BM);
+  const int row_stride = d->row_stride > 1 ? d->row_stride : 1;
+  int rc;
+  if (row_stride > 1) {
+    // strided convolution: the tensor map walks the INPUT rows with a traversal stride; 64 loaded rows per box
+    OSB_REQUIRE(row_stride <= 4 && d->T_in > 0 && !split_in && d->epi == OSB_EPI_BIAS, OSB_ERR_SHAPE);
+    OSB_REQUIRE(static_cast<int64_t>(d->T - 1) * row_stride + d->taps - 1 - d->pad < d->T_in + d->taps, OSB_ERR_SHAPE);
+    rc = make_tmap_3d(&tmA, d->a, TMA_F16, d->K, d->T_in, d->B, d->lda, static_cast<uint64_t>(d->T_in) * d->lda, BKE, 64 * row_stride,
+                      row_stride);
+  } else {
+    rc = make_tmap_3d(&tmA, d->a, TMA_F16, split_in ? 2 * d->K : d->K, d->T, d->B, d->lda, static_cast<uint64_t>(d->T) * d->lda, BKE, BM);
+  }
   if (rc != OSB_OK) return rc;
   if (w_mn) {
     // (taps, K, ldw): contraction rows K, output columns N contiguous; box = 64 columns x 64 rows
@@ -1134,6 +1156,8 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.w_lo_slice = w_batched ? 0 : d->taps;
   p.w_lo_koff = w_batched ? d->K : 0;
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
+  p.row_stride = row_stride;
+  p.lrelu = d->lrelu_slope;
   p.w_mn = w_mn ? 1 : 0;
   p.tap_rev = (d->flags & OSB_FLAG_TAP_REVERSE) ? 1 : 0;
   p.colsum = (d->flags & OSB_FLAG_COLSUM) ? d->out_colsum : nullptr;

@@ -75,7 +75,8 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
-         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None, w_mn: bool = False, tap_reverse: bool = False):
+         ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None, w_mn: bool = False, tap_reverse: bool = False,
+         row_stride: int = 1, lrelu: Optional[float] = None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -105,6 +106,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
             w = w[0]
         taps, N, ldw = w.shape
         K = K if K is not None else min(lda, ldw)
+    T_in = T
+    if row_stride > 1:   # strided convolution: T becomes the number of OUTPUT rows
+        T = (T_in + 2 * pad - taps) // row_stride + 1
+    if lrelu is not None:
+        flags |= _lib.FLAG_LRELU
     f32_out = epi in (EPI_BIAS, EPI_RESID, EPI_BIAS_LN, EPI_LN_BWD, EPI_ATTN_LOGP, EPI_AXPY)
     hN = 2 * N if (flags & FLAG_SPLIT_OUT) else N
     if out is None and not (epi == EPI_RELU_LN and (flags & FLAG_DOT) and not (flags & FLAG_OUT_H16)) and not (flags & _lib.FLAG_NO_F32):
@@ -128,6 +134,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.dropout_p, d.dropout_seed = float(dropout_p), int(dropout_seed)
     d.dropout_seed_dev = _ptr(step_counter(a.device)) if dropout_p > 0.0 else None
     d.w_batched, d.col_len = int(w_batched), _ptr(col_len)
+    d.row_stride, d.T_in, d.lrelu_slope = int(row_stride), int(T_in), float(lrelu or 0.0)
     if colsum is not None:  # bias gradient of the layer whose dgrad this is: column sums of the fp16 output, fused (pre-zeroed fp32 (N,))
         assert epi in (EPI_GELU_BWD, EPI_RELU_BWD, EPI_RELU_LN_BWD) and colsum.dtype == torch.float32 and colsum.numel() == N
         d.flags |= _lib.FLAG_COLSUM

@@ -336,3 +336,24 @@ def test_forward_sum_long_text_takes_the_sequential_fallback(cuda_device):
     (gg,) = torch.autograd.grad(loss, x)
     assert abs(float(loss) - float(ref)) <= 1e-4 * abs(float(ref))
     _check([("dlogp", gg.cpu(), torch.nan_to_num(rg, nan=0.0))], 1e-3)
+
+
+@pytest.mark.parametrize("B,T_in,Cin,Cout,stride", [(3, 200, 128, 128, 3), (2, 1366, 32, 128, 3), (2, 97, 64, 64, 2)])
+def test_strided_conv_gemm_with_leaky_relu(cuda_device, B, T_in, Cin, Cout, stride):
+    """Conv1d(k=5, stride, padding=2) + LeakyReLU(0.1) as an implicit GEMM whose row stride is a TMA traversal stride (the shape
+    of the period discriminators' (5,1)/stride-3 convolutions, reference disc/_discriminators.py:52-60), against F.conv1d."""
+    from optispeech_b200 import ops
+
+    g = torch.Generator().manual_seed(B * T_in)
+    dev = cuda_device
+    k, pad = 5, 2
+    x = torch.randn(B, T_in, Cin, generator=g).to(dev).half()
+    w = (torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    wp = ops.pack_conv_h16(w.to(dev))                                              # (k, Cout, Cin)
+    out, _, _ = ops.gemm(x, wp, epi=ops.EPI_BIAS, pad=pad, bias=bias.to(dev), row_stride=stride, lrelu=0.1)
+    ref = F.leaky_relu(F.conv1d(x.float().cpu().transpose(1, 2), w.half().float(), bias, stride=stride, padding=pad), 0.1).transpose(1, 2)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    err = float((out.cpu() - ref).abs().max())
+    print(f"  stride {stride} T_in {T_in} -> {out.shape[1]} rows: max-abs err {err:.3e}")
+    assert err <= 2e-3
