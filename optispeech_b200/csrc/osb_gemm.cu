@@ -1281,7 +1281,8 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
   return launch_status();
 }
 
-extern "C" int osb_version(void) { return 2;  // v2: osb_gemm_desc grew (out_colsum, row_stride, T_in, lrelu_slope), new entry points (mha, pack_multi, losses) }
+// v2: osb_gemm_desc grew (out_colsum, row_stride, T_in, lrelu_slope), new entry points (mha, pack_multi, losses)
+extern "C" int osb_version(void) { return 2; }
 extern "C" unsigned long long osb_launch_count(void) { return osb::g_launch_count; }
 extern "C" const char* osb_strerror(int s) {
   switch (s) {
