@@ -454,6 +454,23 @@ int osb_dropout_pack_h16(const float* src, void* dst_h16, int64_t rows, int32_t 
 int osb_add_posenc(const float* x, const float* pe, const float* alpha, float* out, int32_t B, int32_t T, int32_t C, float dropout_p,
                    uint64_t dropout_seed, const uint64_t* dropout_seed_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Index / mask glue (osb_glue.cu)
+ * ------------------------------------------------------------------------------------- */
+/* valid[b,t] = t < lengths[b], pad[b,t] = !valid (bytes; either output may be NULL).
+ * Replaces sequence_mask / make_non_pad_mask / make_pad_mask (optispeech/utils/model.py:12-21). */
+int osb_sequence_mask(const int64_t* lengths, uint8_t* valid, uint8_t* pad, int32_t B, int32_t T, void* stream);
+
+/* start[b] = (int64) (rand[b] * max((float)(lengths[b] - margin) - S, 0)): the segment start draw of
+ * get_random_segments (optispeech/utils/segments.py:29-35; margin = 4 at generator/__init__.py:147-153). */
+int osb_segment_starts(const float* rand, const int64_t* lengths, int64_t* start, int32_t B, int32_t margin, int32_t S, void* stream);
+
+/* out[b,s,:] = x[b, start[b]*scale + s, :] for s < S (zero outside [0,T)); x (B,T,C) fp32 channels-last, C = 1 for waveforms.
+ * Replaces get_segments / get_segments_numpy (optispeech/utils/segments.py:38-72; scale = hop_length for the ground-truth
+ * waveform crop of base_lightning_module.py:38-43). */
+int osb_gather_segments(const float* x, const int64_t* start, float* out, int32_t B, int64_t T, int32_t C, int32_t S, int32_t scale,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,6 +143,9 @@ def load() -> C.CDLL:
         "osb_mha_pack_heads": [P, P, I64, I32, I32, I32, P],
         "osb_dropout_pack_h16": [P, P, I64, I32, F, C.c_uint64, P, P],
         "osb_add_posenc": [P, P, P, P, I32, I32, I32, F, C.c_uint64, P, P],
+        "osb_sequence_mask": [P, P, P, I32, I32, P],
+        "osb_segment_starts": [P, P, P, I32, I32, I32, P],
+        "osb_gather_segments": [P, P, P, I32, I64, I32, I32, I32, P],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -88,14 +88,21 @@ class BaseModule(nn.Module):
         (loss * self.loss_scale).backward(**kwargs)
 
     def clip_gradients(self, opt, gradient_clip_val=None, gradient_clip_algorithm="norm"):
-        """Recorded and applied inside the fused optimizer step (osb_adamw_step clips by the global norm)."""
+        """FlatAdamW: recorded and applied inside the fused optimizer step (osb_adamw_step unscales and clips by the global
+        norm).  Any other optimizer (configure_optimizers then runs with loss_scale = 1, so there is nothing to unscale):
+        data-parallel mean of the gradients, then torch's clip_grad_norm_ — what Lightning's DDP strategy + clip_gradients do
+        (reference base_lightning_module.py:100-105)."""
         assert gradient_clip_algorithm == "norm"
         if isinstance(opt, FlatAdamW):
             opt.max_grad_norm = float(gradient_clip_val or 0.0)
-        elif gradient_clip_val:
-            params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
+            return
+        params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            ws = torch.distributed.get_world_size()
             for p in params:
-                p.grad.div_(self.loss_scale)
+                torch.distributed.all_reduce(p.grad)
+                p.grad.div_(ws)
+        if gradient_clip_val:
             torch.nn.utils.clip_grad_norm_(params, gradient_clip_val)
 
     def log_dict(self, values: Dict[str, Any], **kwargs):
@@ -218,10 +225,13 @@ class BaseModule(nn.Module):
         seg = gen_outputs["segment_size"] * self.hop_length
         wav = batch["wav"]
         wav = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
-        wav = wav.to(dev, non_blocking=True)
-        start = gen_outputs["start_idx"] * self.hop_length
-        pos = start.view(-1, 1) + torch.arange(seg, device=dev).view(1, -1)
-        gen_outputs["wav"] = torch.gather(wav, 1, pos.clamp(max=wav.shape[1] - 1)).type_as(gen_outputs["wav_hat"])
+        if wav.dim() == 3:      # (B, 1, Tw) as the reference's collate function hands it over (text_wav_datamodule.py:253-266)
+            wav = wav[:, 0]
+        wav = wav.to(dev, non_blocking=True).to(torch.float32).contiguous()
+        from .. import ops
+        # ground-truth crop wav[b, start*hop : start*hop + seg], zero-filled past the end like get_segments_numpy's pre-zeroed
+        # array (utils/segments.py:63-72) and the host path (stage_batch)
+        gen_outputs["wav"] = ops.crop_segments(wav, gen_outputs["start_idx"], seg, self.hop_length).type_as(gen_outputs["wav_hat"])
         return gen_outputs
 
     def configure_optimizers(self):
@@ -236,6 +246,8 @@ class BaseModule(nn.Module):
             opt_gen = FlatAdamW(gen_params, loss_scale=self.loss_scale, world_size=ws, **kw)
             opt_disc = FlatAdamW(disc_params, loss_scale=self.loss_scale, world_size=ws, **kw)
         else:
+            # stock optimizers see plain gradients: the static loss scale is a FlatAdamW service (it unscales in its fused step)
+            self.loss_scale = 1.0
             opt_gen, opt_disc = make(gen_params), make(disc_params)
         max_steps = (self.trainer.max_steps if self.trainer is not None else getattr(self, "max_steps", 2_000_000)) // 2
         acc = self.train_args.gradient_accumulate_batches

@@ -167,7 +167,10 @@ class ConvNeXtBackbone(nn.Module):
                 split: Optional[bool] = None):
         """x (B,T,C) fp32, padding_mask (B,T) bool True = pad -> (B,T,C) fp32 [, fp16 operand copy]."""
         x = x.contiguous()
-        mask_u8 = None if padding_mask is None else padding_mask.to(torch.uint8).contiguous()
+        mask_u8 = None
+        if padding_mask is not None:   # a contiguous bool mask IS the byte mask the kernels read: no cast launch
+            mask_u8 = (padding_mask.view(torch.uint8) if padding_mask.dtype == torch.bool and padding_mask.is_contiguous()
+                       else padding_mask.to(torch.uint8).contiguous())
         if torch.is_grad_enabled():
             from ....autograd import LayerNormFn
 

@@ -23,6 +23,14 @@ from .layers import LayerNorm, ScaledSinusoidalEmbedding
 DEFAULT_MAX_SOURCE_POSITIONS = 2000
 
 
+
+def _as_u8(mask: torch.Tensor) -> torch.Tensor:
+    """Byte view of a boolean mask (no cast launch when it is already a contiguous bool tensor)."""
+    if mask.dtype == torch.bool and mask.is_contiguous():
+        return mask.view(torch.uint8)
+    return mask.to(torch.uint8).contiguous()
+
+
 class TextEmbedding(nn.Module):
     def __init__(self, dim: int, n_vocab: int, dropout: float = 0.0, padding_idx: int = 0,
                  max_source_positions: int = DEFAULT_MAX_SOURCE_POSITIONS):
@@ -94,7 +102,7 @@ class VariancePredictor(nn.Module):
 
     def forward(self, x: torch.Tensor, padding_mask) -> torch.Tensor:
         """Reference signature: x (B,T,dim) fp32, padding_mask (B,T) bool -> (B,T)."""
-        mask_u8 = padding_mask.to(torch.uint8).contiguous()
+        mask_u8 = _as_u8(padding_mask)
         if torch.is_grad_enabled():
             from ....autograd import VariancePredictorFn
 
@@ -118,7 +126,7 @@ class DurationPredictor(VariancePredictor):
     def infer(self, x, mask, factor=1.0, x_h16=None):
         """-> (durations int64 (B,T), lengths int64 (B,)); reference returns durations only (core.py:115-133).
         `x_h16`, when given, must be in the current inference operand format (see precision.use_split)."""
-        mask_u8 = mask.to(torch.uint8).contiguous()
+        mask_u8 = _as_u8(mask)
         split = precision.use_split(False)
         log_d = self.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         return ops.durations(log_d, mask_u8, factor, self.clip_val)
@@ -145,7 +153,7 @@ class PitchPredictor(nn.Module):
         """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics.
         The prediction only meets the rest of the step at the loss (the embedding is driven by `target`), so with
         `side_stream` it is enqueued there, forked from the current stream; the CALLER joins (`wait_stream`) before using it."""
-        mask_u8 = padding_mask.to(torch.uint8).contiguous()
+        mask_u8 = _as_u8(padding_mask)
         if torch.is_grad_enabled():
             from ....autograd import VarianceEmbedFn
 
@@ -168,7 +176,7 @@ class PitchPredictor(nn.Module):
 
     @torch.inference_mode()
     def infer(self, x, padding_mask, factor=1.0, x_h16=None, want_h16=False):
-        mask_u8 = padding_mask.to(torch.uint8).contiguous()
+        mask_u8 = _as_u8(padding_mask)
         split = precision.use_split(False)
         preds = self.predictor.forward_h16(x_h16 if x_h16 is not None else ops.to_h16(x.contiguous(), split=split), mask_u8, split)
         preds = preds * factor

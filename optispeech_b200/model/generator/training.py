@@ -5,18 +5,14 @@ generator/__init__.py:72-192 (reference @ 3bdde20).
 """
 from __future__ import annotations
 
-import contextlib
 import math
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from ... import ops
 from ...autograd import AttnLogProbFn, ConvStackFn, ForwardSumLossFn
-from ...utils import sequence_mask
-from ...utils.segments import get_segments
 
 
 class AlignmentModule(nn.Module):
@@ -63,42 +59,32 @@ class AlignmentModule(nn.Module):
         return (lf[N] - lf[k] - lf[N - k] + lf[k + t - 1] + lf[N - k + T - t] - lf[N + T] - lf[t - 1] - lf[T - t] + lf[T])
 
     def _generate_prior(self, text_lengths, feats_lengths, T_text=None, T_feats=None, w=1) -> torch.Tensor:
-        if text_lengths.is_cuda:
-            # device path: no host round trip for the lengths (the reference loops over .item() per sample, :104-106)
-            T_text = T_text or int(text_lengths.max())
-            T_feats = T_feats or int(feats_lengths.max())
-            need = T_text + T_feats + 2
-            lf = self._cache.get("lf")
-            if lf is None or lf.numel() < need or lf.device != text_lengths.device:
-                tab = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, max(need, 4096), dtype=np.float64)))])
-                lf = torch.from_numpy(tab).to(text_lengths.device)
-                self._cache["lf"] = lf
-            return ops.beta_binomial_prior(lf, text_lengths.contiguous(), feats_lengths.contiguous(), T_feats, T_text)
-        tl, fl = text_lengths.tolist(), feats_lengths.tolist()
-        T_text = T_text or max(tl)
-        T_feats = T_feats or max(fl)
-        key_all = (tuple(tl), tuple(fl), T_text, T_feats)
-        hit = self._cache.get("batch")
-        if self.cache_prior and hit is not None and hit[0] == key_all:
-            return hit[1]
-        prior = torch.full((len(tl), T_feats, T_text), fill_value=-np.inf)
-        for b, (N, T) in enumerate(zip(tl, fl)):
-            key = f"{T},{N}"
-            prob = self._cache.get(key) if self.cache_prior else None
-            if prob is None:
-                prob = torch.from_numpy(self._log_prior(T, N)).float()
-                if self.cache_prior:
-                    self._cache[key] = prob
-            prior[b, :T, :N] = prob
-        prior = prior.to(self.t_conv1.weight.device)
-        if self.cache_prior:
-            self._cache["batch"] = (key_all, prior)
-        return prior
+        """(B, T_feats, T_text) log-prior on the device (osb_beta_binomial_prior): no host round trip for the lengths (the
+        reference loops over .item() per sample and calls scipy, :104-114)."""
+        _require_cuda(text_lengths, "AlignmentModule._generate_prior")
+        T_text = T_text or int(text_lengths.max())
+        T_feats = T_feats or int(feats_lengths.max())
+        need = T_text + T_feats + 2
+        lf = self._cache.get("lf")
+        if lf is None or lf.numel() < need or lf.device != text_lengths.device:
+            tab = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, max(need, 4096), dtype=np.float64)))])
+            lf = torch.from_numpy(tab).to(text_lengths.device)
+            self._cache["lf"] = lf
+        return ops.beta_binomial_prior(lf, text_lengths.contiguous(), feats_lengths.contiguous(), T_feats, T_text)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        from ... import _lib
+
+        raise _lib.OsbError(f"{what}: the training path runs on libosb200 kernels only (CUDA tensors required; no CPU fallback)")
 
 
 def viterbi_decode(log_p_attn, text_lengths, feats_lengths):
     """-> (durations (B,Tx) fp32, bin_loss).  Reference alignments.py:210-239; the search itself runs on the device
-    (osb_mas, bit-exact with the reference's float64 numba code) instead of one host round trip per sample."""
+    (osb_mas, bit-exact with the reference's float64 numba code) instead of one host round trip per sample.  The training
+    forward below uses the fused form (AlignLossFn: bin loss + forward-sum loss and their gradients in one kernel)."""
+    _require_cuda(log_p_attn, "viterbi_decode")
     B, Tm, Tx = log_p_attn.shape
     path, ds = ops.mas(log_p_attn.detach().contiguous(), text_lengths.contiguous(), feats_lengths.contiguous())
     valid = path >= 0
@@ -118,39 +104,22 @@ def average_by_duration(ds, xs, text_lengths, feats_lengths):
 
 def forward_sum_loss(log_p_attn, ilens, olens, blank_logprob: float = -1.0):
     """ForwardSumLoss (reference loss.py:150-194): blank column log(e^-1), per-sample log_softmax over its own
-    (N_b + 1) columns, CTC with targets 1..N_b, 'mean' reduction (divide by N_b), zero_infinity, mean over batch."""
-    if log_p_attn.is_cuda:
-        return ForwardSumLossFn.apply(log_p_attn, ilens.contiguous(), olens.contiguous(), blank_logprob)
-    B, Tm, Tx = log_p_attn.shape
-    padded = F.pad(log_p_attn, (1, 0), value=blank_logprob)                       # (B, Tm, Tx+1)
-    col_ok = torch.arange(Tx + 1, device=padded.device)[None, :] <= ilens[:, None]  # blank + the sample's own tokens
-    # columns past the sample's own tokens (and the -inf prior of padded frames) are pushed to a large finite negative:
-    # exp() of it is exactly 0 in fp32, so the normalisation is unchanged, and the CTC backward stays NaN-free
-    padded = padded.masked_fill(~col_ok[:, None, :], -1.0e4).clamp(min=-1.0e4)
-    lp = F.log_softmax(padded, dim=-1).transpose(0, 1)                            # (Tm, B, Tx+1)
-    targets = torch.arange(1, Tx + 1, device=padded.device)[None, :].expand(B, -1)
-    per_sample = F.ctc_loss(lp, targets, olens, ilens, blank=0, reduction="none", zero_infinity=True)
-    return (per_sample / ilens.to(per_sample.dtype)).sum() / B
+    (N_b + 1) columns, CTC with targets 1..N_b, 'mean' reduction (divide by N_b), zero_infinity, mean over batch —
+    forward and gradient by the osb_forward_sum kernels."""
+    _require_cuda(log_p_attn, "forward_sum_loss")
+    return ForwardSumLossFn.apply(log_p_attn, ilens.contiguous(), olens.contiguous(), blank_logprob)
 
 
 def fastspeech2_losses(d_outs, p_outs, e_outs, ds, ps, es, ilens):
     """FastSpeech2Loss exactly as the reference evaluates it (loss.py:83-140).  Its masks carry a stray singleton
     axis, so masked_select broadcasts: the duration term takes element (b,i) len_b times for EVERY i < Tx (padded
     positions included, target log(0 + 1e-8)); the pitch / energy terms take element (b,i) once per sample whose
-    length exceeds i.  'mean' reduction over those multisets."""
-    if d_outs.is_cuda:   # one kernel for the three losses and their gradients (osb_loss.cu)
-        from ...autograd import FastSpeech2LossFn
+    length exceeds i.  'mean' reduction over those multisets.  One kernel for the three losses and their gradients
+    (osb_loss.cu)."""
+    from ...autograd import FastSpeech2LossFn
 
-        return FastSpeech2LossFn.apply(d_outs, p_outs, e_outs, ds, ps, es, ilens)
-    B, Tx = d_outs.shape
-    lens = ilens.to(d_outs.dtype)
-    d_err = (d_outs - torch.log(ds.float() + 1e-8)) ** 2
-    d_loss = (d_err.sum(dim=1) * lens).sum() / (lens.sum() * Tx)
-    w = (torch.arange(Tx, device=d_outs.device)[None, :] < ilens[:, None]).to(d_outs.dtype).sum(dim=0)
-    denom = w.sum() * B
-    p_loss = (F.smooth_l1_loss(p_outs, ps, reduction="none") * w[None, :]).sum() / denom
-    e_loss = (F.smooth_l1_loss(e_outs, es, reduction="none") * w[None, :]).sum() / denom
-    return d_loss, p_loss, e_loss
+    _require_cuda(d_outs, "fastspeech2_losses")
+    return FastSpeech2LossFn.apply(d_outs, p_outs, e_outs, ds, ps, es, ilens)
 
 
 def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
@@ -167,53 +136,44 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
 
 def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
     dev = x.device
-    f0_real = pitches
-    x_mask = sequence_mask(x_lengths, x.shape[1])
-    mel_mask = sequence_mask(mel_lengths, mel.shape[-1])
-    in_pad, tgt_pad = ~x_mask, ~mel_mask
+    _require_cuda(x, "OptiSpeechGenerator.forward")
+    # valid + padding masks of a length vector in one launch each (osb_sequence_mask)
+    x_mask, in_pad = ops.sequence_masks(x_lengths, x.shape[1])
+    mel_mask, tgt_pad = ops.sequence_masks(mel_lengths, mel.shape[-1])
 
     # Independent branches run on side streams (forked from / joined to the current stream, so a CUDA-graph capture records
     # them as parallel branches and autograd replays their backward on the same streams): the 6144-row encoder-side kernels
     # fill 64 of 148 SMs, the 27 648-row mel-side kernels of the alignment module's feature encoder take the rest.
-    cuda = x.is_cuda
-    main = torch.cuda.current_stream() if cuda else None
+    main = torch.cuda.current_stream()
     am = gen.alignment_module
-    if cuda:
-        s_feat = ops.side_stream(dev, 1)
-        s_feat.wait_stream(main)
-        with torch.cuda.stream(s_feat):
-            fe = am.encode_feats(mel.transpose(1, 2))     # depends on the mel input only
+    s_feat = ops.side_stream(dev, 1)
+    s_feat.wait_stream(main)
+    with torch.cuda.stream(s_feat):
+        fe = am.encode_feats(mel.transpose(1, 2))     # depends on the mel input only
     h, _ = gen.text_embedding(x)
     h = gen.encoder(h, in_pad)
     h = gen._speaker_language(h, sids, lids)
-    if cuda:
-        s_dur = ops.side_stream(dev, 2)
-        s_dur.wait_stream(main)
-        with torch.cuda.stream(s_dur):
-            duration_hat = gen.duration_predictor(h.detach(), in_pad)   # detached input: meets the rest only at the loss
-        te = am.encode_text(h)
-        main.wait_stream(s_feat)
-        log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
-    else:
-        duration_hat = gen.duration_predictor(h.detach(), in_pad)
-        log_p_attn = am(text=h, feats=mel.transpose(1, 2), text_lengths=x_lengths, feats_lengths=mel_lengths, x_masks=in_pad)
+    s_dur = ops.side_stream(dev, 2)
+    s_dur.wait_stream(main)
+    with torch.cuda.stream(s_dur):
+        duration_hat = gen.duration_predictor(h.detach(), in_pad)   # detached input: meets the rest only at the loss
+    te = am.encode_text(h)
+    main.wait_stream(s_feat)
+    log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
     # The forward-sum loss only meets the rest of the step at the final sum: its sequential recursion (one CTA per sample)
     # runs on a side stream, next to the alignment search, the predictors and the decoder.
-    fs_side = ops.side_stream(dev) if log_p_attn.is_cuda else None
-    if fs_side is not None:
-        fs_side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(fs_side):   # per-sample losses and d(fs_loss)/d(log_p_attn); joined with the bin loss below
-            fs_per_sample, fs_grad = ops.forward_sum(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous(), -1.0)
-        mas_path, durations = ops.mas(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous())
-    else:
-        durations, bin_loss = viterbi_decode(log_p_attn, x_lengths, mel_lengths)
+    fs_side = ops.side_stream(dev)
+    fs_side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(fs_side):   # per-sample losses and d(fs_loss)/d(log_p_attn); joined with the bin loss below
+        fs_per_sample, fs_grad = ops.forward_sum(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous(), -1.0)
+    mas_path, durations = ops.mas(log_p_attn.detach().contiguous(), x_lengths.contiguous(), mel_lengths.contiguous())
 
     p_avg = average_by_duration(durations, pitches, x_lengths, mel_lengths)
     e_avg = average_by_duration(durations, energies, x_lengths, mel_lengths)
 
     # teacher forcing: the embeddings are driven by the targets, the predictions only feed the loss -> side streams
-    s_pitch = ops.side_stream(dev, 3) if cuda else None
-    s_energy = ops.side_stream(dev, 4) if cuda else None
+    s_pitch = ops.side_stream(dev, 3)
+    s_energy = ops.side_stream(dev, 4)
     h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg, side_stream=s_pitch)
     h, energy_hat = gen.energy_predictor(h, in_pad, e_avg, side_stream=s_energy)
 
@@ -222,24 +182,22 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     # their own stream: the acoustic-model losses do not depend on them.  In the pre-training phase nothing in the step
     # consumes wav_hat at all, so the caller may defer the join to the end of the step (`gen.defer_vocoder_join`): the
     # decoder / vocoder forward then overlaps the backward pass.
-    s_voc = ops.side_stream(dev, 5) if cuda else None
-    if s_voc is not None:
-        s_voc.wait_stream(main)
-    with (torch.cuda.stream(s_voc) if s_voc is not None else contextlib.nullcontext()):
+    s_voc = ops.side_stream(dev, 5)
+    s_voc.wait_stream(main)
+    with torch.cuda.stream(s_voc):
         with torch.no_grad():
             y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
                                       y_lengths=mel_lengths)
             y = gen.decoder(y, tgt_pad, split=False)
             segment_size = min(gen.segment_size, y.shape[1])
-            num_frames = (mel_lengths - 4).to(y.dtype)
-            max_start = (num_frames - segment_size).clamp(min=0)
             if seg_rand is None:
                 # inside a CUDA-graph capture the draw has to live on the device (a pageable H2D copy cannot be captured)
                 capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
                 seg_rand = torch.rand([x.shape[0]], device=dev) if capturing else torch.rand([x.shape[0]])
-            start_idx = (seg_rand.to(dev) * max_start).to(torch.long)
-            segment = get_segments(y.transpose(1, 2), start_idx, segment_size).transpose(1, 2).contiguous()  # (B, S, C)
-            _ = get_segments(f0_real.unsqueeze(1), start_idx, segment_size)  # f0_cond: accepted and ignored by WaveNeXt
+            # start = floor(rand * max(len - 4 - S, 0)) and the (B, S, C) crop: two launches (osb_glue.cu); the f0_cond crop
+            # of generator/__init__.py:156-158 is not taken: WaveNeXt ignores it (wavenext/__init__.py:82)
+            start_idx = ops.segment_starts(seg_rand.to(dev, non_blocking=True).float(), mel_lengths, segment_size, margin=4)
+            segment = ops.gather_segments(y.contiguous(), start_idx, segment_size)
 
         if getattr(gen, "vocoder_needs_grad", True):
             wav_hat = gen.vocoder.forward_train(segment)
@@ -247,25 +205,19 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
             with torch.no_grad():
                 wav_hat = gen.vocoder.forward_train(segment)
     pending = []
-    if s_voc is not None:
-        if getattr(gen, "defer_vocoder_join", False) and not getattr(gen, "vocoder_needs_grad", True):
-            pending.append(s_voc)
-        else:
-            main.wait_stream(s_voc)
-
-    if cuda:
-        main.wait_stream(s_dur)
-        main.wait_stream(s_pitch)
-        main.wait_stream(s_energy)
-    d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
-    if fs_side is not None:
-        from ...autograd import AlignLossFn
-
-        torch.cuda.current_stream().wait_stream(fs_side)
-        align_loss, fs_loss, bin_loss = AlignLossFn.apply(log_p_attn, fs_per_sample, fs_grad, mas_path, mel_lengths)
+    if getattr(gen, "defer_vocoder_join", False) and not getattr(gen, "vocoder_needs_grad", True):
+        pending.append(s_voc)
     else:
-        fs_loss = forward_sum_loss(log_p_attn, x_lengths, mel_lengths)
-        align_loss = fs_loss + bin_loss
+        main.wait_stream(s_voc)
+
+    main.wait_stream(s_dur)
+    main.wait_stream(s_pitch)
+    main.wait_stream(s_energy)
+    d_loss, p_loss, e_loss = fastspeech2_losses(duration_hat, pitch_hat, energy_hat, durations, p_avg, e_avg, x_lengths)
+    from ...autograd import AlignLossFn
+
+    torch.cuda.current_stream().wait_stream(fs_side)
+    align_loss, fs_loss, bin_loss = AlignLossFn.apply(log_p_attn, fs_per_sample, fs_grad, mas_path, mel_lengths)
     lc = gen.loss_coeffs
     loss = align_loss * lc.lambda_align + d_loss * lc.lambda_duration + p_loss * lc.lambda_pitch + e_loss * lc.lambda_energy
     return {

@@ -15,6 +15,12 @@ What makes the captured step reusable:
     capture); packs of frozen parameters the graph reads are kept alive by the entry.
 
 Gradient accumulation (`gradient_accumulate_batches` > 1) alternates two different steps and stays eager.
+
+Graph mode needs a BOUNDED set of batch shapes: one graph (and its private memory pool) is kept per distinct
+(shapes, phase) key, least-recently-used entries beyond `max_entries` are dropped, and every key costs `warmup` eager
+steps plus a capture.  Pad or bucket variable-length batches (e.g. to multiples of 64 frames) before enabling it.
+Steps that run eagerly while graphs exist (warm-up of a new key, the phase switch) are ordinary optimizer steps:
+FlatAdamW takes its device-side hyper-parameter path only while a capture is in progress.
 """
 from __future__ import annotations
 
@@ -42,10 +48,11 @@ def _as_tensor(v):
 
 
 class GraphedTrainingStep:
-    def __init__(self, module, warmup: int = 3):
+    def __init__(self, module, warmup: int = 3, max_entries: int = 8):
         self.module = module
         self.warmup = int(warmup)
-        self._entries: Dict[tuple, _Entry] = {}
+        self.max_entries = int(max_entries)
+        self._entries: Dict[tuple, _Entry] = {}   # insertion order = recency (re-inserted on every hit)
         self._warm: Dict[tuple, int] = {}
         self.replays = 0
         self.last_entry: _Entry = None
@@ -75,7 +82,12 @@ class GraphedTrainingStep:
                 self._warm[key] = seen + 1
                 return m._training_step_eager(batch, batch_idx)
             entry = self._capture(batch, batch_idx, train_discriminator)
-            self._entries[key] = entry
+            while len(self._entries) >= self.max_entries:   # LRU: drop the stalest graph and its memory pool
+                old = self._entries.pop(next(iter(self._entries)))
+                old.graph, old.keepalive, old.static = None, [], {}
+        else:
+            self._entries.pop(key)
+        self._entries[key] = entry
         self._replay(entry, batch)
         return None
 
@@ -88,6 +100,10 @@ class GraphedTrainingStep:
             e.static = {}
         self._entries.clear()
         self.last_entry = None
+        if self.module._optimizers is not None:
+            for opt in self.module._optimizers:
+                if isinstance(opt, FlatAdamW):
+                    opt.graph_mode = False
 
     # ------------------------------------------------------------------------------------------------
     def _optimizers(self, train_discriminator: bool):

@@ -595,3 +595,43 @@ def align_loss_fold(log_p_attn, path, m_len, per_sample_fs, fs_grad):
     _lib.check(_lib.load().osb_align_loss_fold(_ptr(_f32(log_p_attn)), _ptr(path), _ptr(m_len), _ptr(per_sample_fs), _ptr(fs_grad), _ptr(out),
                                                B, Tm, Tx, _stream()), "osb_align_loss_fold")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# index / mask glue (osb_glue.cu)
+# ------------------------------------------------------------------------------------------------
+def sequence_masks(lengths: torch.Tensor, T: int, valid: bool = True, pad: bool = True):
+    """-> (valid (B,T) bool | None, pad (B,T) bool | None) from one launch (utils/model.py:12-21)."""
+    B = lengths.shape[0]
+    lengths = lengths.to(torch.int64).contiguous()
+    v = torch.empty((B, T), device=lengths.device, dtype=torch.bool) if valid else None
+    p = torch.empty((B, T), device=lengths.device, dtype=torch.bool) if pad else None
+    _lib.check(_lib.load().osb_sequence_mask(_ptr(lengths), _ptr(v), _ptr(p), B, T, _stream()), "osb_sequence_mask")
+    return v, p
+
+
+def segment_starts(rand: torch.Tensor, lengths: torch.Tensor, segment_size: int, margin: int = 4) -> torch.Tensor:
+    """start = floor(rand * max(len - margin - S, 0)) as int64 (utils/segments.py:29-35)."""
+    B = lengths.shape[0]
+    out = torch.empty((B,), device=lengths.device, dtype=torch.int64)
+    _lib.check(_lib.load().osb_segment_starts(_ptr(_f32(rand.contiguous())), _ptr(lengths.to(torch.int64).contiguous()), _ptr(out), B,
+                                              int(margin), int(segment_size), _stream()), "osb_segment_starts")
+    return out
+
+
+def gather_segments(x: torch.Tensor, start: torch.Tensor, segment_size: int, scale: int = 1) -> torch.Tensor:
+    """x (B,T,C) fp32 channels-last -> (B,S,C): rows start*scale .. +S of every sample, zero past T (utils/segments.py:38-60)."""
+    B, T, Cc = x.shape
+    out = torch.empty((B, segment_size, Cc), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_gather_segments(_ptr(_f32(x)), _ptr(start), _ptr(out), B, T, Cc, int(segment_size), int(scale), _stream()),
+               "osb_gather_segments")
+    return out
+
+
+def crop_segments(wav: torch.Tensor, start_frames: torch.Tensor, n: int, hop: int) -> torch.Tensor:
+    """wav (B,Tw) fp32 -> (B,n): samples start*hop .. +n, zero past the end (utils/segments.py:63-72)."""
+    B, Tw = wav.shape
+    out = torch.empty((B, n), device=wav.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_gather_segments(_ptr(_f32(wav)), _ptr(start_frames.to(torch.int64).contiguous()), _ptr(out), B, Tw, 1, int(n),
+                                               int(hop), _stream()), "osb_gather_segments")
+    return out

@@ -29,7 +29,12 @@ GATHER_CHUNK = 2048  # floats per work item of osb_grad_gather (csrc/osb_optim.c
 
 
 class _Bucket:
-    def __init__(self, params: List[torch.nn.Parameter]):
+    """`cohorts` = [(n_params, first_step)]: consecutive runs of `params` that joined the bucket together.  `first_step` is the
+    group's step count when the run's first update happened minus one, so the run's own Adam step (bias correction) is
+    `group_step - first_step` — what torch.optim.AdamW keeps per parameter (parameters that start receiving gradients later,
+    e.g. the vocoder after `pretraining_steps`, begin at step 1)."""
+
+    def __init__(self, params: List[torch.nn.Parameter], cohorts=None):
         dev = params[0].device
         offs, total = [], 0
         for p in params:
@@ -40,6 +45,23 @@ class _Bucket:
         self.offsets = offs
         self.offset_of = {id(p): o for p, o in zip(params, offs)}
         self.numel = total
+        self.cohorts = []   # (element start, element end, first_step)
+        cohorts = cohorts or [(len(params), 0)]
+        assert sum(n for n, _ in cohorts) == len(params)
+        i = 0
+        for n, first in cohorts:
+            if n == 0:
+                continue
+            start = offs[i]
+            end = offs[i + n] if i + n < len(params) else total
+            self.cohorts.append((start, end, int(first)))
+            i += n
+        self.cohort_of = {}
+        i = 0
+        for ci, (n, _) in enumerate([c for c in cohorts if c[0] > 0]):
+            for p in params[i:i + n]:
+                self.cohort_of[id(p)] = ci
+            i += n
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.m = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -108,6 +130,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self.world_size = int(world_size)
         self._buckets: Dict[int, _Bucket] = {}
         self._steps: Dict[int, int] = {}
+        self._pending_state: Dict[int, tuple] = {}   # id(param) -> (exp_avg, exp_avg_sq, step) from load_state_dict
         self.last_stats: Optional[torch.Tensor] = None
         # CUDA-graph mode (model/graphed.py): lr and the bias corrections are read from `hyper_dev`, which the host refreshes
         # with stage_hyper() before every replay; step() then has no per-step host value baked into its launches.
@@ -121,19 +144,38 @@ class FlatAdamW(torch.optim.Optimizer):
         if not live:
             return None
         b = self._buckets.get(gi)
-        if b is not None and b.ids == {id(p) for p in live}:
+        live_ids = {id(p) for p in live}
+        if b is not None and b.ids == live_ids:
             return b
-        # (re)build, carrying Adam moments over for parameters that were already tracked
+        # (re)build: parameters already tracked keep their order, run ("cohort") and Adam moments; newcomers form new runs whose
+        # bias-correction step starts at 1 (or continues from a loaded state_dict)
         old = b
-        saved = {}
+        gstep = self._steps.get(gi, 0)
+        params, cohorts, saved = [], [], {}
         if old is not None:
-            for p in old.params:
-                saved[id(p)] = (old.view_of(old.m, p).clone(), old.view_of(old.v, p).clone())
-        b = _Bucket(live)
-        for p in live:
+            for ci, (_, _, first) in enumerate(old.cohorts):
+                keep = [p for p in old.params if old.cohort_of[id(p)] == ci and id(p) in live_ids]
+                for p in keep:
+                    saved[id(p)] = (old.view_of(old.m, p).clone(), old.view_of(old.v, p).clone())
+                params += keep
+                cohorts.append((len(keep), first))
+        new = [p for p in live if id(p) not in saved]
+        by_first: Dict[int, list] = {}
+        for p in new:
+            pend = self._pending_state.pop(id(p), None)
+            first = gstep
+            if pend is not None:
+                saved[id(p)] = (pend[0], pend[1])
+                first = gstep - int(pend[2])
+            by_first.setdefault(first, []).append(p)
+        for first in sorted(by_first):
+            params += by_first[first]
+            cohorts.append((len(by_first[first]), first))
+        b = _Bucket(params, cohorts)
+        for p in params:
             if id(p) in saved:
-                b.view_of(b.m, p).copy_(saved[id(p)][0])
-                b.view_of(b.v, p).copy_(saved[id(p)][1])
+                b.view_of(b.m, p).copy_(saved[id(p)][0].to(b.m.device).reshape(p.shape))
+                b.view_of(b.v, p).copy_(saved[id(p)][1].to(b.v.device).reshape(p.shape))
         self._buckets[gi] = b
         return b
 
@@ -150,6 +192,11 @@ class FlatAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm: Optional[float] = None):
         max_norm = self.max_grad_norm if max_grad_norm is None else float(max_grad_norm)
+        # The device-side hyper-parameter path is for launches that are being CAPTURED (their lr / bias corrections must not be
+        # baked into the graph; stage_hyper() refreshes them and advances the counters once per replay).  Every other step —
+        # warm-up steps of a new batch shape, accumulation, the phase switch, cuda_graph=False — is a normal eager step even
+        # after a capture has happened: it reads lr from the param group, advances the step counter and the weight epochs.
+        capturing = self.graph_mode and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         for gi, group in enumerate(self.param_groups):
             b = self._bucket_for(gi, group)
             if b is None:
@@ -161,7 +208,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 self._grad_norm(b)
             # the all-reduce SUMS the ranks' gradients; the 1/world factor is folded into the unscale factor
             inv_scale = 1.0 / (self.loss_scale * self.world_size)
-            if self.graph_mode:
+            if capturing:
                 self._kernel_step_dev(b, group, gi, max_norm, inv_scale)
                 self.last_stats = b.stats
                 continue  # step counters and weight epochs are advanced by stage_hyper(), once per replay
@@ -184,21 +231,38 @@ class FlatAdamW(torch.optim.Optimizer):
         _lib.check(_lib.load().osb_grad_sumsq(b.flat_g.data_ptr(), b.numel, b.stats.data_ptr(), _stream()), "osb_grad_sumsq")
 
     def _kernel_step(self, b: _Bucket, group, step: int, max_norm: float, inv_scale: float) -> None:
-        """Unscale + clip by the global norm (b.stats) + AdamW over the flat bucket."""
+        """Unscale + clip by the global norm (b.stats) + AdamW over the flat bucket, one launch per cohort (its own Adam step)."""
         lib = _lib.load()
         beta1, beta2 = group["betas"]
-        _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
-                                      b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                                      float(group["weight_decay"]), step, max_norm, inv_scale, _stream()), "osb_adamw_step")
+        for start, end, first in b.cohorts:
+            o = 4 * start
+            _lib.check(lib.osb_adamw_step(b.flat_p.data_ptr() + o, b.flat_g.data_ptr() + o, b.m.data_ptr() + o, b.v.data_ptr() + o,
+                                          end - start, b.stats.data_ptr(), float(group["lr"]), float(beta1), float(beta2),
+                                          float(group["eps"]), float(group["weight_decay"]), max(step - first, 1), max_norm, inv_scale,
+                                          _stream()), "osb_adamw_step")
+
+    HYPER_ROWS = 32
 
     def _ensure_hyper(self, device) -> None:
         if self.hyper_dev is None:
-            n = len(self.param_groups)
-            self.hyper_host = torch.zeros(n, 4, dtype=torch.float32).pin_memory()
-            self.hyper_dev = torch.zeros(n, 4, dtype=torch.float32, device=device)
+            self.hyper_host = torch.zeros(self.HYPER_ROWS, 4, dtype=torch.float32)
+            if torch.cuda.is_available():
+                self.hyper_host = self.hyper_host.pin_memory()
+            self.hyper_dev = torch.zeros(self.HYPER_ROWS, 4, dtype=torch.float32, device=device)
+
+    def _hyper_row(self, gi: int, ci: int) -> int:
+        """Row of the device hyper-parameter table for cohort `ci` of group `gi` (stable for the life of a captured graph:
+        rows are only ever appended)."""
+        rows = self.__dict__.setdefault("_hyper_row_ids", {})
+        key = (gi, ci)
+        if key not in rows:
+            if len(rows) >= self.HYPER_ROWS:
+                raise RuntimeError("FlatAdamW: too many (group, cohort) pairs for the device hyper-parameter table")
+            rows[key] = len(rows)
+        return rows[key]
 
     def stage_hyper(self) -> None:
-        """Host side of one graph-mode step: advance the step counters, stage [lr, 1-b1^t, sqrt(1-b2^t)] of every group
+        """Host side of one graph-mode step: advance the step counters, stage [lr, 1-b1^t, sqrt(1-b2^t)] of every cohort
         for the captured osb_adamw_step_dev launches (async copy on the current stream) and invalidate packed weights."""
         for gi, group in enumerate(self.param_groups):
             b = self._buckets.get(gi)
@@ -208,9 +272,12 @@ class FlatAdamW(torch.optim.Optimizer):
             step = self._steps.get(gi, 0) + 1
             self._steps[gi] = step
             beta1, beta2 = group["betas"]
-            self.hyper_host[gi, 0] = float(group["lr"])
-            self.hyper_host[gi, 1] = 1.0 - beta1 ** step
-            self.hyper_host[gi, 2] = (1.0 - beta2 ** step) ** 0.5
+            for ci, (_, _, first) in enumerate(b.cohorts):
+                r = self._hyper_row(gi, ci)
+                t = max(step - first, 1)
+                self.hyper_host[r, 0] = float(group["lr"])
+                self.hyper_host[r, 1] = 1.0 - beta1 ** t
+                self.hyper_host[r, 2] = (1.0 - beta2 ** t) ** 0.5
             for p in b.params:
                 p._osb_epoch = getattr(p, "_osb_epoch", 0) + 1
         if self.hyper_dev is not None:
@@ -220,10 +287,60 @@ class FlatAdamW(torch.optim.Optimizer):
         lib = _lib.load()
         self._ensure_hyper(b.flat_p.device)
         beta1, beta2 = group["betas"]
-        _lib.check(lib.osb_adamw_step_dev(b.flat_p.data_ptr(), b.flat_g.data_ptr(), b.m.data_ptr(), b.v.data_ptr(), b.numel,
-                                          b.stats.data_ptr(), self.hyper_dev[gi].data_ptr(), float(beta1), float(beta2),
-                                          float(group["eps"]), float(group["weight_decay"]), max_norm, inv_scale, _stream()),
-                   "osb_adamw_step_dev")
+        for ci, (start, end, _) in enumerate(b.cohorts):
+            o = 4 * start
+            _lib.check(lib.osb_adamw_step_dev(b.flat_p.data_ptr() + o, b.flat_g.data_ptr() + o, b.m.data_ptr() + o, b.v.data_ptr() + o,
+                                              end - start, b.stats.data_ptr(), self.hyper_dev[self._hyper_row(gi, ci)].data_ptr(),
+                                              float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]), max_norm,
+                                              inv_scale, _stream()), "osb_adamw_step_dev")
+
+    # -- checkpointing: torch.optim.AdamW layout ------------------------------------------------------
+    def state_dict(self):
+        """Same layout as torch.optim.AdamW.state_dict(): per-parameter `step`, `exp_avg`, `exp_avg_sq` (copies of the bucket
+        views) for every parameter that has been updated, plus the param groups — what Lightning stores under
+        `optimizer_states` (reference checkpoints; base_lightning_module.py relies on torch.optim.AdamW round-tripping)."""
+        self.state.clear()
+        for gi, group in enumerate(self.param_groups):
+            b = self._buckets.get(gi)
+            gstep = self._steps.get(gi, 0)
+            for p in group["params"]:
+                if b is not None and id(p) in b.ids:
+                    first = b.cohorts[b.cohort_of[id(p)]][2]
+                    self.state[p] = {"step": torch.tensor(float(max(gstep - first, 0))), "exp_avg": b.view_of(b.m, p).clone(),
+                                     "exp_avg_sq": b.view_of(b.v, p).clone()}
+                elif id(p) in self._pending_state:
+                    m, v, st = self._pending_state[id(p)]
+                    self.state[p] = {"step": torch.tensor(float(st)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        try:
+            sd = super().state_dict()
+        finally:
+            self.state.clear()
+        sd["osb_group_steps"] = {int(k): int(v) for k, v in self._steps.items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """Accepts FlatAdamW.state_dict() and torch.optim.AdamW.state_dict() alike.  The moments are parked until the buckets
+        are (re)built on the next step (bucket membership depends on which parameters receive gradients)."""
+        sd = dict(state_dict)
+        group_steps = sd.pop("osb_group_steps", None)
+        super().load_state_dict(sd)
+        self._pending_state = {}
+        self._buckets = {}
+        self._steps = {}
+        for gi, group in enumerate(self.param_groups):
+            best = 0
+            for p in group["params"]:
+                st = self.state.get(p)
+                if not st or "exp_avg" not in st:
+                    continue
+                step = int(float(st["step"]))
+                self._pending_state[id(p)] = (st["exp_avg"].detach().clone(), st["exp_avg_sq"].detach().clone(), step)
+                best = max(best, step)
+            if group_steps is not None and (gi in group_steps or str(gi) in group_steps):
+                best = int(group_steps.get(gi, group_steps.get(str(gi))))
+            if best:
+                self._steps[gi] = best
+        self.state.clear()
 
     def grad_norm(self) -> float:
         """Unscaled global gradient norm of the last step (reads a device scalar: call outside the hot loop)."""

@@ -9,6 +9,10 @@ def sequence_mask(length, max_length=None):
     """(B,) lengths -> (B, max_length) bool, True inside the sequence (utils/model.py:12-16)."""
     if max_length is None:
         max_length = length.max()
+    if length.is_cuda and length.dim() == 1:   # one launch (osb_sequence_mask) instead of arange + compare
+        from .. import ops
+
+        return ops.sequence_masks(length, int(max_length), valid=True, pad=False)[0]
     x = torch.arange(int(max_length), dtype=length.dtype, device=length.device)
     return x.unsqueeze(0) < length.unsqueeze(1)
 
@@ -19,6 +23,10 @@ def make_non_pad_mask(lengths):
 
 def make_pad_mask(lengths, max_len=None):
     max_length = max_len if max_len is not None else lengths.max()
+    if lengths.is_cuda and lengths.dim() == 1:
+        from .. import ops
+
+        return ops.sequence_masks(lengths, int(max_length), valid=False, pad=True)[1]
     return ~sequence_mask(lengths, max_length).bool()
 
 

@@ -26,70 +26,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 
 
-def _stub(name, **attrs):
-    m = types.ModuleType(name)
-    m.__path__ = []
-    m.__spec__ = importlib.machinery.ModuleSpec(name, None, is_package=True)
-    for k, v in attrs.items():
-        setattr(m, k, v)
-    sys.modules[name] = m
-    return m
-
-
-def install_stubs():
-    _stub("matplotlib", use=lambda *a, **k: None)
-    _stub("matplotlib.pyplot", Figure=object)
-    _stub("omegaconf", DictConfig=dict, OmegaConf=object, open_dict=lambda *a, **k: None)
-    _stub("hydra")
-    _stub("hydra.core")
-    _stub("hydra.core.hydra_config", HydraConfig=object)
-    _stub("lightning", LightningModule=torch.nn.Module, Callback=object, LightningDataModule=object, Trainer=object)
-    _stub("lightning.pytorch")
-    _stub("lightning.pytorch.loggers", Logger=object)
-    _stub("lightning.pytorch.utilities", rank_zero_only=lambda f: f, grad_norm=lambda *a, **k: {})
-
-
-def build_reference_generator(spec):
-    from optispeech.model.generator import OptiSpeechGenerator
-    from optispeech.model.generator.modules import (ConvNeXtBackbone, DurationPredictor, EnergyPredictor, PitchPredictor,
-                                                    TextEmbedding)
-    from optispeech.model.vocoder.wavenext import WaveNeXt
-
-    conv = partial(torch.nn.Conv1d)
-    fe = SimpleNamespace(n_feats=spec.n_feats, n_fft=spec.n_fft, hop_length=spec.hop_length, win_length=spec.win_length,
-                         sample_rate=spec.sample_rate, f_min=spec.f_min, f_max=spec.f_max)
-    gen = OptiSpeechGenerator(
-        dim=spec.dim,
-        segment_size=spec.segment_size,
-        text_embedding=partial(TextEmbedding, n_vocab=spec.n_vocab, dropout=0.1, padding_idx=0,
-                               max_source_positions=spec.max_source_positions),
-        encoder=partial(ConvNeXtBackbone, intermediate_dim=spec.enc_intermediate, num_layers=spec.enc_layers, drop_path=0.2),
-        duration_predictor=partial(DurationPredictor, num_layers=spec.duration.num_layers,
-                                   intermediate_dim=spec.duration.intermediate_dim, kernel_size=spec.duration.kernel_size,
-                                   dropout=0.1, conv_layer_class=conv),
-        pitch_predictor=partial(PitchPredictor, num_layers=spec.pitch.num_layers, intermediate_dim=spec.pitch.intermediate_dim,
-                                kernel_size=spec.pitch.kernel_size, dropout=0.5, embed_kernel_size=spec.pitch.embed_kernel_size,
-                                embed_dropout=0.2, conv_layer_class=conv),
-        energy_predictor=partial(EnergyPredictor, num_layers=spec.energy.num_layers, intermediate_dim=spec.energy.intermediate_dim,
-                                 kernel_size=spec.energy.kernel_size, dropout=0.5, embed_kernel_size=spec.energy.embed_kernel_size,
-                                 embed_dropout=0.5, conv_layer_class=conv),
-        decoder=partial(ConvNeXtBackbone, intermediate_dim=spec.dec_intermediate, num_layers=spec.dec_layers, drop_path=0.2),
-        vocoder=partial(WaveNeXt, dim=spec.voc_dim, intermediate_dim=spec.voc_intermediate, num_layers=spec.voc_layers, drop_path=0.1),
-        loss_coeffs=SimpleNamespace(lambda_align=spec.lambda_align, lambda_duration=spec.lambda_duration,
-                                    lambda_pitch=spec.lambda_pitch, lambda_energy=spec.lambda_energy),
-        feature_extractor=fe,
-        num_speakers=spec.num_speakers,
-        num_languages=spec.num_languages,
-        data_statistics=None,
-    )
-    return gen, fe
-
-
-def build_reference_discriminator(spec, fe):
-    from optispeech.model.vocoder.wavenext.disc import VocosDiscriminator
-
-    return VocosDiscriminator(feature_extractor=fe, loss_coeffs=SimpleNamespace(lambda_mrd=spec.lambda_mrd, lambda_mel=spec.lambda_mel,
-                                                                               lambda_mr_stft=spec.lambda_mr_stft))
+sys.path.insert(0, ROOT)
+from oracle.ref_harness import (build_reference_discriminator, build_reference_generator, install_stubs,  # noqa: E402,F401
+                                run_reference_forward)
+sys.path.remove(ROOT)
 
 
 def train_batch(spec, B, Tx, Tm, seed):
@@ -108,20 +48,6 @@ def train_batch(spec, B, Tx, Tm, seed):
     seg_rand = torch.rand(B, generator=g)
     return dict(x=x, x_lengths=x_lengths, mel=mel, mel_lengths=mel_lengths, pitches=pitches, energies=energies, wav=wav,
                 seg_rand=seg_rand)
-
-
-def run_reference_forward(gen, batch):
-    """generator.forward with torch.rand patched to return the batch's seg_rand (reference draws on the CPU generator)."""
-    import optispeech.utils.segments as seg
-
-    orig = torch.rand
-    seg.torch.rand = lambda shape, *a, **k: batch["seg_rand"].clone()
-    try:
-        out = gen(x=batch["x"], x_lengths=batch["x_lengths"], mel=batch["mel"], mel_lengths=batch["mel_lengths"],
-                  pitches=batch["pitches"], energies=batch["energies"], sids=None, lids=None)
-    finally:
-        seg.torch.rand = orig
-    return out
 
 
 def main():
