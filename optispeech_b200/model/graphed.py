@@ -48,8 +48,13 @@ def _as_tensor(v):
 
 
 class GraphedTrainingStep:
-    def __init__(self, module, warmup: int = 3, max_entries: int = 8):
+    def __init__(self, module, warmup: int = 3, max_entries: int = 8, step_fn=None, train_discriminator=None):
+        """`step_fn(batch, batch_idx)` (default: the module's `_training_step_eager`) is what gets captured; a custom step must
+        do its optimizer steps through the module's FlatAdamW optimizers.  `train_discriminator` pins the phase (and with it
+        the optimizers whose hyper-parameters are staged per replay) instead of reading it from `global_step`."""
         self.module = module
+        self.step_fn = step_fn
+        self.force_phase = train_discriminator
         self.warmup = int(warmup)
         self.max_entries = int(max_entries)
         self._entries: Dict[tuple, _Entry] = {}   # insertion order = recency (re-inserted on every hit)
@@ -71,16 +76,17 @@ class GraphedTrainingStep:
     def __call__(self, batch, batch_idx):
         m = self.module
         acc = m.train_args.gradient_accumulate_batches
+        step_fn = self.step_fn or m._training_step_eager
         if m.device.type != "cuda" or (acc is not None and acc != 1):
-            return m._training_step_eager(batch, batch_idx)
-        train_discriminator = m.global_step >= m.train_args.pretraining_steps
+            return step_fn(batch, batch_idx)
+        train_discriminator = (m.global_step >= m.train_args.pretraining_steps) if self.force_phase is None else bool(self.force_phase)
         key = self._key(batch, train_discriminator)
         entry = self._entries.get(key)
         if entry is None:
             seen = self._warm.get(key, 0)
             if seen < self.warmup:  # eager steps build the flat buckets, tables and kernel attributes the capture relies on
                 self._warm[key] = seen + 1
-                return m._training_step_eager(batch, batch_idx)
+                return step_fn(batch, batch_idx)
             entry = self._capture(batch, batch_idx, train_discriminator)
             while len(self._entries) >= self.max_entries:   # LRU: drop the stalest graph and its memory pool
                 old = self._entries.pop(next(iter(self._entries)))
@@ -143,7 +149,7 @@ class GraphedTrainingStep:
         try:
             # the NCCL watchdog thread polls events while we capture: only this thread's calls may invalidate the capture
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
-                m._training_step_eager(static_batch, batch_idx)
+                (self.step_fn or m._training_step_eager)(static_batch, batch_idx)
         finally:
             m._capturing = False
         e.launches = int(lib.osb_launch_count() - n0)

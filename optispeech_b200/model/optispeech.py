@@ -99,21 +99,47 @@ class OptiSpeech(BaseModule):
         return inputs.as_torch().to(self.device)
 
     @classmethod
-    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict: bool = True, **overrides) -> "OptiSpeech":
-        """Lightning-style checkpoint: {'state_dict', 'hyper_parameters', 'epoch', ...} (reference optispeech/infer.py:38).
-        Checkpoints written by the reference pickle partials of `optispeech.*` classes; the `optispeech` alias package at
-        the repository root resolves those names to this implementation."""
-        ckpt: Dict[str, Any] = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
-        hparams = dict(ckpt["hyper_parameters"])
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict: bool = True, resume_training: bool = False,
+                             **overrides) -> "OptiSpeech":
+        """Lightning-style checkpoint: {'state_dict', 'hyper_parameters', 'epoch', 'global_step', 'optimizer_states',
+        'lr_schedulers', ...} (reference optispeech/infer.py:38, optispeech/train.py:84-91).  Checkpoints written by the
+        reference itself pickle OmegaConf containers and live text-processor / feature-extractor objects in
+        `hyper_parameters`; they are read through `optispeech_b200.checkpoint.load_checkpoint_file`, which resolves the
+        `optispeech.*` class paths to this implementation and OmegaConf containers to plain dict / list / namespace objects
+        (OmegaConf is not a dependency).  `resume_training=True` also restores optimizer, scheduler and step counters — what
+        `Trainer.fit(ckpt_path=...)` does for the reference."""
+        from ..checkpoint import hyper_parameters_from_checkpoint, load_checkpoint_file
+
+        ckpt: Dict[str, Any] = load_checkpoint_file(checkpoint_path, map_location=map_location or "cpu")
+        hparams = hyper_parameters_from_checkpoint(ckpt)
         hparams.update(overrides)
         model = cls(**hparams)
         model.load_state_dict(ckpt["state_dict"], strict=strict)
         model.on_load_checkpoint(ckpt)
         if map_location is not None and str(map_location) != "cpu":
             model = model.to(map_location)
+        if resume_training:
+            model.load_training_state(ckpt)
         return model
 
-    def save_checkpoint(self, path, epoch: int = 0, global_step: int = 0):
-        """Writes the same dictionary layout `load_from_checkpoint` (and Lightning) reads."""
-        torch.save({"state_dict": self.state_dict(), "hyper_parameters": vars(self.hparams), "epoch": epoch,
-                    "global_step": global_step}, path)
+    def load_training_state(self, ckpt: Dict[str, Any]) -> None:
+        """Optimizer moments / step counts (torch.optim.AdamW layout, so the reference's own `optimizer_states` load as well),
+        LR schedulers and the batch counter behind `global_step` (base_lightning_module.py:294-303)."""
+        opts, scheds = self.optimizers(), self.lr_schedulers()
+        for opt, sd in zip(opts, ckpt.get("optimizer_states") or []):
+            opt.load_state_dict(sd)
+        for sched, sd in zip(scheds, ckpt.get("lr_schedulers") or []):
+            sched.load_state_dict(sd)
+            for group, lr in zip(sched.optimizer.param_groups, sched.get_last_lr()):
+                group["lr"] = lr
+        acc = self.train_args.gradient_accumulate_batches or 1
+        self._fit.total_batch_idx = int(ckpt.get("global_step", 0)) * int(acc)
+
+    def save_checkpoint(self, path, epoch: int = 0, global_step: int | None = None):
+        """Writes the dictionary layout `load_from_checkpoint` (and Lightning) reads, optimizer and scheduler state included."""
+        ckpt = {"state_dict": self.state_dict(), "hyper_parameters": vars(self.hparams), "epoch": epoch,
+                "global_step": self.global_step if global_step is None else global_step}
+        if self._optimizers is not None:
+            ckpt["optimizer_states"] = [o.state_dict() for o in self._optimizers]
+            ckpt["lr_schedulers"] = [s.state_dict() for s in self._schedulers]
+        torch.save(ckpt, path)

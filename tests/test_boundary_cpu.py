@@ -306,3 +306,100 @@ def test_presampled_drop_paths_follow_the_reference_distribution():
     bb.eval()
     presample_drop_paths(bb, B, torch.device("cpu"))
     assert all(m.sample_scale(B, torch.device("cpu")) is None for m in mods)          # eval: identity
+
+
+def test_reference_style_checkpoint_loads_without_omegaconf(tmp_path):
+    """A checkpoint laid out like the reference's (Lightning dict; `hyper_parameters` = partials of `optispeech.*` classes,
+    OmegaConf DictConfig / ListConfig containers with *Node leaves, live text-processor / feature-extractor objects;
+    optispeech/model/optispeech.py:26) loads through optispeech_b200.checkpoint without omegaconf / lightning / the text
+    front-end being importable.  OmegaConf is not installed here, so the containers are written by stand-in classes with
+    OmegaConf's module paths and pickled `__dict__` layout (`_content`, `_metadata`, `_parent`, `_flags_cache`; nodes: `_val`)."""
+    import importlib.machinery
+    import sys
+    import types
+    from functools import partial
+
+    from optispeech_b200.checkpoint import AttrDict, Placeholder
+    from optispeech_b200.factory import DEFAULT_MODEL, build_model
+    from optispeech_b200.model import OptiSpeech
+
+    fake = {}
+
+    def mod(name):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        fake[name] = m
+        return m
+
+    base, dictconfig, listconfig, nodes = mod("omegaconf.base"), mod("omegaconf.dictconfig"), mod("omegaconf.listconfig"), mod("omegaconf.nodes")
+    mod("omegaconf")
+    text_mod, fe_mod = mod("optispeech.text"), mod("optispeech.dataset.feature_extractors")
+
+    def cls(m, name):
+        c = type(name, (), {})
+        c.__module__ = m.__name__
+        c.__qualname__ = name
+        setattr(m, name, c)
+        return c
+
+    Meta, CMeta = cls(base, "Metadata"), cls(base, "ContainerMetadata")
+    DictConfig, ListConfig = cls(dictconfig, "DictConfig"), cls(listconfig, "ListConfig")
+    AnyNode, IntegerNode, FloatNode, BooleanNode = (cls(nodes, n) for n in ("AnyNode", "IntegerNode", "FloatNode", "BooleanNode"))
+    TextProcessor, FeatureExtractor = cls(text_mod, "TextProcessor"), cls(fe_mod, "CommonFeatureExtractor")
+
+    def wrap(v, parent=None):
+        if isinstance(v, dict):
+            d = DictConfig()
+            d.__dict__.update(_metadata=CMeta(), _parent=parent, _flags_cache=None, _content={})
+            d._metadata.__dict__.update(ref_type=object, object_type=dict, optional=True, key=None, flags={"allow_objects": True})
+            for k, x in v.items():
+                d._content[k] = wrap(x, d)
+            return d
+        if isinstance(v, (list, tuple)):
+            l = ListConfig()
+            l.__dict__.update(_metadata=CMeta(), _parent=parent, _flags_cache=None, _content=[])
+            l._content.extend(wrap(x, l) for x in v)
+            return l
+        node = {bool: BooleanNode, int: IntegerNode, float: FloatNode}.get(type(v), AnyNode)()
+        node.__dict__.update(_metadata=Meta(), _parent=parent, _flags_cache=None, _val=v)
+        return node
+
+    src = build_model(DEFAULT_MODEL)
+    hp = vars(src.hparams)
+    tp = TextProcessor()
+    tp.__dict__.update(languages=["en-us"], num_languages=1, is_multi_language=False, default_language="en-us", add_blank=True)
+    fe = FeatureExtractor()
+    fe.__dict__.update(vars(hp["data_args"].feature_extractor), center=False, pitch_extractor=None)
+    data_args = dict(vars(hp["data_args"]), text_processor=tp, feature_extractor=fe)
+    gen = hp["generator"]
+    gen_kw = dict(gen.keywords, loss_coeffs=wrap(vars(gen.keywords["loss_coeffs"])))          # nested DictConfig keyword
+    disc_kw = dict(hp["discriminator"].keywords, loss_coeffs=wrap(vars(hp["discriminator"].keywords["loss_coeffs"])))
+    upstream = dict(dim=hp["dim"], generator=partial(gen.func, **gen_kw), vocoder=hp["vocoder"],
+                    discriminator=partial(hp["discriminator"].func, **disc_kw),
+                    train_args=wrap(vars(hp["train_args"])), data_args=wrap(data_args), inference_args=wrap(vars(hp["inference_args"])),
+                    optimizer=partial(torch.optim.AdamW, lr=2e-4, betas=wrap([0.8, 0.99]), weight_decay=1e-2), scheduler=hp["scheduler"])
+    path = tmp_path / "upstream.ckpt"
+    saved = {k: sys.modules.get(k) for k in fake}
+    sys.modules.update(fake)
+    try:
+        torch.save({"state_dict": src.state_dict(), "hyper_parameters": upstream, "epoch": 11, "global_step": 5000,
+                    "pytorch-lightning_version": "2.4.0", "optimizer_states": [], "lr_schedulers": []}, str(path))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert "omegaconf" not in sys.modules
+    loaded = OptiSpeech.load_from_checkpoint(str(path), map_location="cpu")
+    assert loaded.ckpt_loaded_epoch == 11
+    assert isinstance(loaded.train_args, AttrDict) and loaded.train_args.gradient_clip_val == 10 and loaded.train_args.pretraining_steps == 1000
+    assert loaded.sample_rate == 22050 and loaded.hop_length == 256 and loaded.inference_args.d_factor == 1.1
+    assert isinstance(loaded.text_processor, Placeholder) and loaded.text_processor.languages == ["en-us"]
+    assert loaded.generator.loss_coeffs.lambda_align == 5.0
+    with pytest.raises(RuntimeError, match="attribute bag"):
+        loaded.prepare_input("hello")            # the phonemiser itself is outside this package
+    a, b = src.state_dict(), loaded.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    opts, _ = loaded.configure_optimizers()
+    assert opts[0].defaults["betas"] == (0.8, 0.99)

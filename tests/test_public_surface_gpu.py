@@ -1,0 +1,214 @@
+"""The public surface on the GPU, end to end:
+
+  * `OptiSpeech.prepare_input` (stub text processor) -> `OptiSpeech.synthesise(InferenceInputs)` -> `InferenceOutputs`
+    against the oracle (reference optispeech/model/optispeech.py:58-154);
+  * `VocosDiscriminator.forward_disc / forward_gen` on the device against the goldens of the real reference
+    (tests/golden/discriminator.npz; reference disc/__init__.py:44-96): every loss term and d loss / d wav_hat;
+  * optimizer state: CUDA-graph replays interleaved with eager steps of another batch shape equal a pure-eager run
+    (lr, step counters, parameters), and a checkpoint round trip (`state_dict` in torch.optim.AdamW layout) resumes
+    identically.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as O
+from oracle.spec import ModelSpec, deterministic_state_dict, generator_shapes
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class StubTextProcessor:
+    """The TextProcessor interface OptiSpeech.prepare_input relies on (reference optispeech/text/processor.py): ids per
+    sentence from a fixed table, no phonemiser."""
+
+    languages = ["en-us"]
+    is_multi_language = False
+    num_languages = 1
+
+    def __call__(self, text, lang=None, split_sentences=True):
+        sents = [s.strip() for s in text.split(".") if s.strip()] if split_sentences else [text]
+        ids = [[1 + (ord(c) * 7 + i) % 158 for i, c in enumerate(s)] for s in sents]
+        return (ids, sents) if split_sentences else (ids[0], text)
+
+
+def test_optispeech_synthesise_end_to_end(cuda_device):
+    from optispeech_b200.factory import build_model, model_config_from_spec
+    from optispeech_b200.values import InferenceInputs, InferenceOutputs
+
+    spec = ModelSpec()
+    sd = deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0)
+    model = build_model(model_config_from_spec(spec), text_processor=StubTextProcessor())
+    model.generator.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).eval()
+    text = "the quick brown fox jumps over the lazy dog. pack my box with five dozen liquor jugs. sphinx of black quartz"
+    inputs = model.prepare_input(text, d_factor=1.0, p_factor=1.0, e_factor=1.0)
+    assert isinstance(inputs, InferenceInputs) and inputs.x.shape[0] == 3 and inputs.x.is_cuda
+    out = model.synthesise(inputs)
+    assert isinstance(out, InferenceOutputs)
+    x, xl = inputs.x.cpu(), inputs.x_lengths.cpu()
+    ref = O.synthesise(sd, spec, x, xl, 1.0, 1.0, 1.0)
+    wav, wl, dur = torch.as_tensor(out.wav), torch.as_tensor(out.wav_lengths), torch.as_tensor(out.durations)
+    assert wl.dtype == torch.int64 or wl.dtype == torch.int32
+    flips = int((dur.cpu() != ref["durations"]).sum())
+    print(f"durations differing from the oracle: {flips} of {dur.numel()}")
+    assert flips <= max(1, dur.numel() // 50)       # ceil() of a predictor output may flip by one frame at ULP level
+    compared = 0
+    for b in range(x.shape[0]):
+        if not torch.equal(dur[b].cpu(), ref["durations"][b]):
+            continue
+        n = int(ref["wav_lengths"][b])
+        assert int(wl[b]) == n
+        err = float((wav[b, :n].cpu() - ref["wav"][b, :n]).abs().max())
+        print(f"utterance {b}: {n} samples, waveform max-abs diff {err:.3e}")
+        assert err <= 1e-3
+        compared += 1
+    assert compared >= 1
+    assert out.rtf > 0 and out.latency > 0
+    assert len(out.unbatched_wavs()) == 3
+    # the same call through the README spelling and without a text processor
+    out2 = model.synthesize(InferenceInputs.from_ids_and_lengths(ids=[x[0, : int(xl[0])].tolist()], lengths=[int(xl[0])], d_factor=1.0,
+                                                                p_factor=1.0, e_factor=1.0))
+    n0 = int(torch.as_tensor(out2.wav_lengths)[0])
+    if n0 == int(wl[0]):
+        assert float((torch.as_tensor(out2.wav)[0, :n0].cpu() - wav[0, :n0].cpu()).abs().max()) <= 1e-3   # batch-vs-single invariance
+
+
+def test_vocos_discriminator_terms_on_device(cuda_device):
+    from types import SimpleNamespace
+
+    from optispeech_b200.model.vocoder.wavenext.disc import VocosDiscriminator
+    from oracle.discriminators import discriminator_shapes
+
+    fx = np.load(os.path.join(GOLD, "discriminator.npz"))
+    spec = ModelSpec()
+    fe = SimpleNamespace(n_feats=spec.n_feats, n_fft=spec.n_fft, hop_length=spec.hop_length, win_length=spec.win_length,
+                         sample_rate=spec.sample_rate, f_min=spec.f_min, f_max=spec.f_max)
+    disc = VocosDiscriminator(feature_extractor=fe, loss_coeffs=SimpleNamespace(lambda_mrd=spec.lambda_mrd, lambda_mel=spec.lambda_mel,
+                                                                                lambda_mr_stft=spec.lambda_mr_stft))
+    missing, unexpected = disc.load_state_dict(deterministic_state_dict(discriminator_shapes(), seed=0), strict=False)
+    assert not unexpected and all(k.startswith(("melspec_loss", "mr_stft_loss")) for k in missing), (missing, unexpected)
+    disc = disc.to(cuda_device).eval()
+    wav = torch.from_numpy(fx["wav"]).to(cuda_device)
+    wav_hat = torch.from_numpy(fx["wav_hat"]).to(cuda_device).requires_grad_(True)
+    # fp16 / TF32 tensor-core operands in the convolution stacks: 1e-2 relative on every term (measured values are printed)
+    tol = 1e-2
+    loss_d, log_d = disc.forward_disc(wav, wav_hat.detach())
+    print("forward_disc", float(loss_d), float(fx["loss_disc"]))
+    assert abs(float(loss_d) - float(fx["loss_disc"])) <= tol * abs(float(fx["loss_disc"]))
+    for k, v in log_d.items():
+        assert abs(float(v) - float(fx[f"disc_{k}"])) <= tol * max(1.0, abs(float(fx[f"disc_{k}"]))), k
+    loss_g, log_g = disc.forward_gen(wav, wav_hat)
+    for k, v in log_g.items():
+        print(f"forward_gen {k}: {float(v):.6f} reference {float(fx[f'gen_{k}']):.6f}")
+        assert abs(float(v) - float(fx[f"gen_{k}"])) <= tol * max(1.0, abs(float(fx[f"gen_{k}"]))), k
+    assert abs(float(loss_g) - float(fx["loss_gen"])) <= tol * abs(float(fx["loss_gen"]))
+    loss_g.backward()
+    g = wav_hat.grad.detach().cpu()
+    rel_norm = abs(float(g.norm()) - float(fx["dwav_hat_norm"])) / float(fx["dwav_hat_norm"])
+    sl = g[:, ::64].numpy()
+    rel = float(np.linalg.norm(sl - fx["dwav_hat_slice"]) / np.linalg.norm(fx["dwav_hat_slice"]))
+    print(f"d loss_gen / d wav_hat: norm rel err {rel_norm:.3e}, slice rel L2 err {rel:.3e}")
+    assert rel_norm <= 3e-2 and rel <= 5e-2
+
+
+def _small_batch(spec, B, Tx, Tm, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    xl = torch.randint(Tx // 2, Tx + 1, (B,), generator=g); xl[0] = Tx
+    x = torch.randint(1, 159, (B, Tx), generator=g) * (torch.arange(Tx)[None] < xl[:, None])
+    ml = torch.clamp((xl.float() * (Tm / Tx)).round().long(), max=Tm); ml[0] = Tm
+    mm = torch.arange(Tm)[None] < ml[:, None]
+    b = dict(x=x, x_lengths=xl, mel=torch.randn(B, spec.n_feats, Tm, generator=g) * mm[:, None, :], mel_lengths=ml,
+             pitches=torch.randn(B, Tm, generator=g) * mm, energies=torch.randn(B, Tm, generator=g) * mm,
+             wav=torch.rand(B, Tm * spec.hop_length, generator=g) * 2 - 1, seg_rand=torch.rand(B, generator=g))
+    return {k: v.to(dev) for k, v in b.items()} | dict(sids=None, lids=None)
+
+
+def _fresh_model(spec, dev, warmup=4):
+    from functools import partial
+
+    from transformers import get_cosine_schedule_with_warmup
+
+    from optispeech_b200.factory import build_model, model_config_from_spec
+
+    model = build_model(model_config_from_spec(spec), train_args=dict(pretraining_steps=10 ** 9))
+    model.hparams.scheduler = partial(get_cosine_schedule_with_warmup, num_warmup_steps=warmup, num_training_steps=-1)
+    model.generator.load_state_dict(deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0), strict=True)
+    return model.to(dev).eval()
+
+
+def test_eager_steps_between_graph_replays_are_real_steps(cuda_device):
+    """Advisor finding (round 1): after a capture, eager steps (a new batch shape warming up) used the replay's stale lr and
+    did not advance the optimizer step.  Sequence A A A A(capture) A(replay) B(eager) A(replay) must equal the same sequence run
+    fully eagerly: same lr trajectory, same step counter, same parameters (eval mode: no dropout; segment draw pinned)."""
+    spec = ModelSpec()
+    A = _small_batch(spec, 2, 40, 170, seed=1, dev=cuda_device)
+    Bb = _small_batch(spec, 2, 32, 140, seed=2, dev=cuda_device)
+    seq = [A, A, A, A, A, Bb, A]
+    results = []
+    for graph in (False, True):
+        model = _fresh_model(spec, cuda_device)
+        model.cuda_graph = graph
+        lrs = []
+        for i, b in enumerate(seq):
+            model.training_step(b, i)
+            lrs.append(model.optimizers()[0].param_groups[0]["lr"])
+        torch.cuda.synchronize()
+        if graph:
+            assert model._graphed is not None and model._graphed.replays >= 2
+        opt = model.optimizers()[0]
+        results.append((lrs, dict(opt._steps), {k: p.detach().clone() for k, p in model.generator.named_parameters()}))
+        if model._graphed is not None:
+            model._graphed.release()
+            assert opt.graph_mode is False
+    (lr_e, st_e, p_e), (lr_g, st_g, p_g) = results
+    assert lr_e == lr_g and st_e == st_g and st_e[0] == len(seq)
+    worst = 0.0
+    for k in p_e:
+        d = float((p_e[k] - p_g[k]).abs().max())
+        worst = max(worst, d / (float(p_e[k].abs().max()) + 1e-12))
+    print(f"eager vs graph+eager parameters: worst relative max-abs difference {worst:.3e}")
+    assert worst <= 2e-3    # atomics in the weight-gradient reductions make runs differ in the last fp32 bits only
+
+
+def test_checkpoint_round_trip_resumes_optimizer_state(cuda_device, tmp_path):
+    """save_checkpoint -> load_from_checkpoint(resume_training=True) -> step equals the uninterrupted run (the optimizer
+    `state_dict` has torch.optim.AdamW's layout: per-parameter step / exp_avg / exp_avg_sq)."""
+    from optispeech_b200.model import OptiSpeech
+
+    spec = ModelSpec()
+    A = _small_batch(spec, 2, 40, 170, seed=1, dev=cuda_device)
+    model = _fresh_model(spec, cuda_device)
+    for i in range(3):
+        model.training_step(A, i)
+    osd = model.optimizers()[0].state_dict()
+    assert osd["state"] and all({"step", "exp_avg", "exp_avg_sq"} <= set(s) for s in osd["state"].values())
+    assert all(float(s["step"]) == 3.0 for s in osd["state"].values())
+    path = tmp_path / "ckpt.pt"
+    model.save_checkpoint(str(path), epoch=0, global_step=model.global_step)
+    model.training_step(A, 3)
+    torch.cuda.synchronize()
+    want = {k: p.detach().clone() for k, p in model.generator.named_parameters()}
+
+    resumed = OptiSpeech.load_from_checkpoint(str(path), map_location=cuda_device, resume_training=True).eval()
+    assert resumed.global_step == 3
+    resumed.training_step(A, 3)
+    torch.cuda.synchronize()
+    assert resumed.optimizers()[0]._steps[0] == 4
+    assert abs(resumed.lr_schedulers()[0].get_last_lr()[0] - model.lr_schedulers()[0].get_last_lr()[0]) <= 1e-12
+    worst = 0.0
+    for k, p in resumed.generator.named_parameters():
+        worst = max(worst, float((p.detach() - want[k]).abs().max()) / (float(want[k].abs().max()) + 1e-12))
+    print(f"resumed vs uninterrupted step: worst relative max-abs difference {worst:.3e}")
+    assert worst <= 2e-3
+    # a torch.optim.AdamW state_dict (what a reference checkpoint holds) loads too
+    ref_opt = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in resumed.generator.parameters()], lr=2e-4, betas=(0.8, 0.99))
+    for p in ref_opt.param_groups[0]["params"]:
+        p.grad = torch.zeros_like(p)
+    ref_opt.step()
+    resumed.optimizers()[0].load_state_dict(ref_opt.state_dict())
+    assert resumed.optimizers()[0]._steps[0] == 1
