@@ -343,7 +343,7 @@ int osb_beta_binomial_prior(const double* log_factorial, int64_t table_len, cons
 /* Forward-sum alignment loss and its gradient in one launch: per sample, CTC over the frames t < m_len of
  * log_softmax([blank_logit | log_p_attn[b,t,:x_len]]) with target 1..x_len, nll / x_len ('mean' reduction), 0 when infinite
  * (zero_infinity).  loss (B) holds the per-sample values (ForwardSumLoss = sum / B); grad (B,Tm,Tx) = d(sum/B)/d(log_p_attn);
- * alpha_ws is an fp32 workspace of 2*B*Tm*Tx + B*Tm + B values (token-state alpha and beta, per-frame normalisers, nll).  Replaces ForwardSumLoss.forward (generator/loss.py:150-194: a Python loop of
+ * alpha_ws is an fp32 workspace of 2*B*Tm*Tx + 3*B*Tm + B values (token-state alpha and beta, per-frame normalisers, nll, per-frame log-scales of the two recursions).  Replaces ForwardSumLoss.forward (generator/loss.py:150-194: a Python loop of
  * F.ctc_loss calls) and its autograd. */
 int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len, float blank_logit, float* alpha_ws,
                     float* loss, float* grad, int32_t B, int32_t Tm, int32_t Tx, void* stream);

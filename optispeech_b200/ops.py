@@ -468,7 +468,7 @@ def beta_binomial_prior(log_factorial, x_len, m_len, Tm: int, Tx: int):
 def forward_sum(log_p_attn, x_len, m_len, blank_logit: float = -1.0):
     """-> (per-sample loss (B,), grad (B,Tm,Tx) of sum(loss)/B w.r.t. log_p_attn)."""
     B, Tm, Tx = log_p_attn.shape
-    ws = torch.empty((2 * B * Tm * Tx + B * Tm + B,), device=log_p_attn.device, dtype=torch.float32)
+    ws = torch.empty((2 * B * Tm * Tx + 3 * B * Tm + B,), device=log_p_attn.device, dtype=torch.float32)
     loss = torch.empty((B,), device=log_p_attn.device, dtype=torch.float32)
     grad = torch.empty((B, Tm, Tx), device=log_p_attn.device, dtype=torch.float32)
     _lib.check(_lib.load().osb_forward_sum(_ptr(_f32(log_p_attn)), _ptr(x_len), _ptr(m_len), float(blank_logit), _ptr(ws), _ptr(loss),

@@ -338,6 +338,44 @@ def test_forward_sum_long_text_takes_the_sequential_fallback(cuda_device):
     _check([("dlogp", gg.cpu(), torch.nan_to_num(rg, nan=0.0))], 1e-3)
 
 
+@pytest.mark.parametrize("Tx,Tm,sharp", [(192, 864, 2.0), (192, 864, 12.0), (300, 700, 3.0), (100, 333, 6.0)])
+def test_forward_sum_warp_recursion_matches_oracle_and_legacy(cuda_device, Tx, Tm, sharp):
+    """The warp-synchronous linear-domain recursion (registers + shuffles, exact power-of-two rescaling per frame) against the
+    oracle's F.ctc_loss formulation and against the shared-memory log-domain kernel it replaces, at the training shape and with
+    sharply peaked rows (per-frame probabilities down to e^-60: the rescaling has to carry the range)."""
+    import ctypes
+
+    from optispeech_b200 import _lib, ops
+
+    g = torch.Generator().manual_seed(21)
+    dev = cuda_device
+    B = 3
+    tl = torch.tensor([Tx, Tx // 2 + 3, 1])
+    fl = torch.tensor([Tm, Tm // 2 + 11, 7])
+    lp = torch.log_softmax(torch.randn(B, Tm, Tx, generator=g) * sharp, dim=-1)
+    for b in range(B):
+        lp[b, fl[b]:, :] = -float("inf")
+        lp[b, :, tl[b]:] = -float("inf")
+    ref_in = lp.clone().requires_grad_(True)
+    ref = O.forward_sum_loss(ref_in, tl, fl)
+    (rg,) = torch.autograd.grad(ref, ref_in)
+    rg = torch.nan_to_num(rg, nan=0.0)
+    x = lp.to(dev)
+    loss_w, grad_w = ops.forward_sum(x, tl.to(dev), fl.to(dev), -1.0)
+    lib = _lib.load()
+    lib.osb_debug_forward_sum_legacy.argtypes = [ctypes.c_int]
+    lib.osb_debug_forward_sum_legacy(1)
+    try:
+        loss_l, grad_l = ops.forward_sum(x, tl.to(dev), fl.to(dev), -1.0)
+    finally:
+        lib.osb_debug_forward_sum_legacy(0)
+    total = float(loss_w.sum()) / B
+    print(f"  Tx={Tx} Tm={Tm} sharp={sharp}: warp {total:.6f} legacy {float(loss_l.sum()) / B:.6f} oracle {float(ref):.6f}")
+    assert abs(total - float(ref)) <= 2e-5 * abs(float(ref))
+    assert torch.allclose(loss_w, loss_l, rtol=2e-5, atol=1e-6)
+    _check([("dlogp vs oracle", grad_w.cpu(), rg), ("dlogp vs legacy", grad_w.cpu(), grad_l.cpu())], 1e-3)
+
+
 @pytest.mark.parametrize("B,T_in,Cin,Cout,stride", [(3, 200, 128, 128, 3), (2, 1366, 32, 128, 3), (2, 97, 64, 64, 2)])
 def test_strided_conv_gemm_with_leaky_relu(cuda_device, B, T_in, Cin, Cout, stride):
     """Conv1d(k=5, stride, padding=2) + LeakyReLU(0.1) as an implicit GEMM whose row stride is a TMA traversal stride (the shape

@@ -47,11 +47,16 @@ def _named(fx, prefix):
     return keys, {k: float(n) for k, n in zip(keys, fx[f"{prefix}_norms"])}
 
 
+def _family(k):
+    return k.split(".")[0]
+
+
 def _compare_packed(fx, prefix, tensors, scale, tol_full, tol_norm, what):
-    """tensors: name -> CUDA tensor (already divided by `scale` here).  Checks norms for all, values for the stored ones."""
+    """tensors: name -> CUDA tensor (divided by `scale` here).  Checks norms for all, values for the stored ones.
+    `tol_full` is a float or a dict family -> tolerance (key "" = default)."""
     keys, norms = _named(fx, prefix)
     stride = 127
-    bad, worst = [], 0.0
+    bad, worst, fam_worst = [], 0.0, {}
     for k in keys:
         ref_norm = norms[k]
         t = tensors.get(k)
@@ -67,9 +72,12 @@ def _compare_packed(fx, prefix, tensors, scale, tol_full, tol_norm, what):
             ref, flat = fx[f"{prefix}_slice/{k}"], flat[::stride]
         rel = float(np.linalg.norm(flat - ref) / (np.linalg.norm(ref) + 1e-30))
         worst = max(worst, rel)
-        if not (rel <= tol_full and rel_norm <= tol_norm):
+        fam_worst[_family(k)] = max(fam_worst.get(_family(k), 0.0), rel)
+        tol = tol_full.get(_family(k), tol_full[""]) if isinstance(tol_full, dict) else tol_full
+        if not (rel <= tol and rel_norm <= tol_norm):
             bad.append((k, rel, rel_norm))
-    print(f"{what}: {len(keys)} tensors, worst relative error {worst:.3e}")
+    print(f"{what}: {len(keys)} tensors, worst relative error {worst:.3e}; per family: "
+          + ", ".join(f"{f} {v:.2e}" for f, v in sorted(fam_worst.items())))
     for k, rel, rn in bad:
         print(f"BAD {what} {k}: rel {rel:.3e} norm-rel {rn:.3e}")
     assert not bad
@@ -111,9 +119,10 @@ def test_training_forward_backward_fullsize_vs_reference(cuda_device, fx, batch)
     gen.zero_grad(set_to_none=True)
     (out["loss"] * 1024.0).backward()
     grads = {k: p.grad for k, p in gen.named_parameters()}
-    # 5e-2: ReLU gates of the 5-layer pitch predictor flip between an fp16-operand forward and the fp32 reference; every
-    # other family is far below (printed)
-    _compare_packed(fx, "grad", grads, 1024.0, tol_full=5e-2, tol_norm=3e-2, what="gradient")
+    # per layer family: ReLU gates of the 5-layer pitch predictor flip between an fp16-operand forward and the fp32 reference
+    # (error grows with depth); smooth GELU blocks and the alignment convolutions agree far better (worst values are printed)
+    tol = {"": 3e-2, "pitch_predictor": 7e-2, "duration_predictor": 4e-2, "energy_predictor": 4e-2}
+    _compare_packed(fx, "grad", grads, 1024.0, tol_full=tol, tol_norm=3e-2, what="gradient")
 
 
 def test_three_training_steps_fullsize_vs_reference(cuda_device, fx, batch):

@@ -71,7 +71,7 @@ def test_optispeech_synthesise_end_to_end(cuda_device):
     assert out.rtf > 0 and out.latency > 0
     assert len(out.unbatched_wavs()) == 3
     # the same call through the README spelling and without a text processor
-    out2 = model.synthesize(InferenceInputs.from_ids_and_lengths(ids=[x[0, : int(xl[0])].tolist()], lengths=[int(xl[0])], d_factor=1.0,
+    out2 = model.synthesize(InferenceInputs.from_ids_and_lengths(ids=[x[0, : int(xl[0])].tolist()], lengths=[int(xl[0])], clean_text="", d_factor=1.0,
                                                                 p_factor=1.0, e_factor=1.0))
     n0 = int(torch.as_tensor(out2.wav_lengths)[0])
     if n0 == int(wl[0]):
@@ -144,13 +144,14 @@ def _fresh_model(spec, dev, warmup=4):
 def test_eager_steps_between_graph_replays_are_real_steps(cuda_device):
     """Advisor finding (round 1): after a capture, eager steps (a new batch shape warming up) used the replay's stale lr and
     did not advance the optimizer step.  Sequence A A A A(capture) A(replay) B(eager) A(replay) must equal the same sequence run
-    fully eagerly: same lr trajectory, same step counter, same parameters (eval mode: no dropout; segment draw pinned)."""
+    fully eagerly: same lr trajectory, same step counter, same parameters (eval mode: no dropout; segment draw pinned).  Two
+    eager runs give the run-to-run floor (fp32 atomics in the weight-gradient reductions + Adam's sign-like first updates)."""
     spec = ModelSpec()
     A = _small_batch(spec, 2, 40, 170, seed=1, dev=cuda_device)
     Bb = _small_batch(spec, 2, 32, 140, seed=2, dev=cuda_device)
     seq = [A, A, A, A, A, Bb, A]
     results = []
-    for graph in (False, True):
+    for graph in (False, False, True):
         model = _fresh_model(spec, cuda_device)
         model.cuda_graph = graph
         lrs = []
@@ -165,14 +166,18 @@ def test_eager_steps_between_graph_replays_are_real_steps(cuda_device):
         if model._graphed is not None:
             model._graphed.release()
             assert opt.graph_mode is False
-    (lr_e, st_e, p_e), (lr_g, st_g, p_g) = results
-    assert lr_e == lr_g and st_e == st_g and st_e[0] == len(seq)
-    worst = 0.0
-    for k in p_e:
-        d = float((p_e[k] - p_g[k]).abs().max())
-        worst = max(worst, d / (float(p_e[k].abs().max()) + 1e-12))
-    print(f"eager vs graph+eager parameters: worst relative max-abs difference {worst:.3e}")
-    assert worst <= 2e-3    # atomics in the weight-gradient reductions make runs differ in the last fp32 bits only
+
+    def dist(pa, pb):   # relative L2 distance over all parameters
+        num = sum(float((pa[k] - pb[k]).double().pow(2).sum()) for k in pa)
+        den = sum(float(pa[k].double().pow(2).sum()) for k in pa)
+        return (num / den) ** 0.5
+
+    (lr_e, st_e, p_e), (lr_e2, st_e2, p_e2), (lr_g, st_g, p_g) = results
+    assert lr_e == lr_g == lr_e2 and st_e == st_g and st_e[0] == len(seq)
+    floor, got = dist(p_e, p_e2), dist(p_e, p_g)
+    print(f"eager vs eager (run-to-run floor) {floor:.3e}; eager vs graph+eager {got:.3e}")
+    # a stale learning rate or a skipped step moves every parameter by ~lr per step: orders of magnitude above the floor
+    assert got <= 3.0 * floor + 2e-5
 
 
 def test_checkpoint_round_trip_resumes_optimizer_state(cuda_device, tmp_path):

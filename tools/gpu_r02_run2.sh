@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, run 2: fixed tests + warp forward-sum
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "forward_sum" -s > gpurun_out/pytest_fs.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_fs.log
+tail -30 gpurun_out/pytest_fs.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -12 gpurun_out/pytest_gpu.log
+grep -n "per family\|MAS durations\|eager vs eager\|step losses\|wav_hat max\|durations differing\|utterance\|forward_gen\|d loss_gen" gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-variants --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_quick.json'))
+print(d['ms_per_step'], d['e2e']['ms_per_step'], d['gpu_launches_per_step'])
+for t in d['top_kernels']: print(t)
+PY
