@@ -343,7 +343,7 @@ int osb_beta_binomial_prior(const double* log_factorial, int64_t table_len, cons
 /* Forward-sum alignment loss and its gradient in one launch: per sample, CTC over the frames t < m_len of
  * log_softmax([blank_logit | log_p_attn[b,t,:x_len]]) with target 1..x_len, nll / x_len ('mean' reduction), 0 when infinite
  * (zero_infinity).  loss (B) holds the per-sample values (ForwardSumLoss = sum / B); grad (B,Tm,Tx) = d(sum/B)/d(log_p_attn);
- * alpha_ws is an fp32 workspace of 2*B*Tm*Tx + 3*B*Tm + B values (token-state alpha and beta, per-frame normalisers, nll, per-frame log-scales of the two recursions).  Replaces ForwardSumLoss.forward (generator/loss.py:150-194: a Python loop of
+ * alpha_ws is an fp32 workspace of 2*B*Tm*Tx + B*Tm + B values (token-state alpha and beta, per-frame normalisers, nll).  Replaces ForwardSumLoss.forward (generator/loss.py:150-194: a Python loop of
  * F.ctc_loss calls) and its autograd. */
 int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, const int64_t* m_len, float blank_logit, float* alpha_ws,
                     float* loss, float* grad, int32_t B, int32_t Tm, int32_t Tx, void* stream);
@@ -470,6 +470,37 @@ int osb_segment_starts(const float* rand, const int64_t* lengths, int64_t* start
  * waveform crop of base_lightning_module.py:38-43). */
 int osb_gather_segments(const float* x, const int64_t* start, float* out, int32_t B, int64_t T, int32_t C, int32_t S, int32_t scale,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ConvNeXt block, training path (osb_convnext.cu / osb_convnext_bwd.cu)
+ * ------------------------------------------------------------------------------------- */
+/* osb_convnext_block_fwd that also emits what the backward needs while it is on chip: xhat (fp16 normalised dwconv output,
+ * the A operand of pwconv1), rstd (fp32 per position), pre (fp16 GELU argument) and h (fp16 GELU output).  Same arguments and
+ * result otherwise.  Replaces ConvNeXtBlock.forward under autograd (modules/convnext.py:34-47). */
+int osb_convnext_block_fwd_train(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
+                                 const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
+                                 const uint8_t* pad_mask, float* out, void* xhat_h16, float* rstd, void* pre_h16, void* h_h16, int32_t B,
+                                 int32_t T, int32_t C, int32_t I, float eps, void* stream);
+
+/* Both data-gradient contractions of a ConvNeXt block in one tcgen05 kernel (the autograd of modules/convnext.py:39-46):
+ *   dyg   = fp16(dout * gamma * keep * row_scale[b])                     (B,T,C)  dy of the pwconv2 weight gradient
+ *   dh    = fp16((dyg . W2) * gelu_erf'(pre))                            (B,T,I)  dy of the pwconv1 weight gradient
+ *   dxhat = dh . W1f   (fp32)                                            (B,T,C)  gradient wrt the normalised dwconv output
+ * w2_h16 (C, I) and w1f_h16 (I, C) are the FORWARD fp16 packs (read as MN-major B operands).  (C, I) = (256,1024) or (384,1152). */
+int osb_convnext_block_bwd(const float* dout, const float* gamma, const float* row_scale, const uint8_t* pad_mask, const void* pre_h16,
+                           const void* w2_h16, const void* w1f_h16, void* dyg_h16, void* dh_h16, float* dxhat, int32_t B, int32_t T,
+                           int32_t C, int32_t I, void* stream);
+
+/* LayerNorm backward (affine folded away) + depthwise conv7 backward + residual path + depthwise parameter gradients in one pass:
+ *   dd = LN_bwd(dxhat; xhat, rstd);  dx[t] = dout[t] * keep[t] + sum_j w[:,j] * dd[t-j+3];  ddw (C,7) += ..., ddb (C) += ...
+ * (ddw / ddb are accumulated: zero them first).  Autograd of nn.Conv1d(groups=C) + nn.LayerNorm (modules/convnext.py:36-38). */
+int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const float* rstd, const float* dout, const float* x, const float* dw_w,
+                      const uint8_t* pad_mask, float* dx, float* ddw, float* ddb, int32_t B, int32_t T, int32_t C, void* stream);
+
+/* Layer-scale and pwconv2-bias gradients from the block's input x and output out (gamma * z * rs = out - x on unmasked rows):
+ *   dgamma += sum_rows dout * keep * (out - x) / gamma ;  db2 += sum_rows dout * keep * rs * gamma   (modules/convnext.py:42-46) */
+int osb_resid_param_grad(const float* dout, const float* out, const float* x, const float* gamma, const uint8_t* pad_mask,
+                         const float* row_scale, float* dgamma, float* db2, int64_t rows, int32_t T, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -143,6 +143,10 @@ def load() -> C.CDLL:
         "osb_mha_pack_heads": [P, P, I64, I32, I32, I32, P],
         "osb_dropout_pack_h16": [P, P, I64, I32, F, C.c_uint64, P, P],
         "osb_add_posenc": [P, P, P, P, I32, I32, I32, F, C.c_uint64, P, P],
+        "osb_convnext_block_fwd_train": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, F, P],
+        "osb_convnext_block_bwd": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
+        "osb_ln_dwconv_bwd": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
+        "osb_resid_param_grad": [P, P, P, P, P, P, P, P, I64, I32, I32, P],
         "osb_sequence_mask": [P, P, P, I32, I32, P],
         "osb_segment_starts": [P, P, P, I32, I32, I32, P],
         "osb_gather_segments": [P, P, P, I32, I64, I32, I32, I32, P],
@@ -211,6 +215,14 @@ class LaunchProfiler:
                         B, T, Cc, I = args[11], args[12], args[13], args[14]
                         key = f"osb_convnext_block_fwd[rows={B * T},C={Cc},I={I}]"
                         flops = 2.0 * B * T * (2 * Cc * I + 7 * Cc)
+                    elif name == "osb_convnext_block_fwd_train":
+                        B, T, Cc, I = args[15], args[16], args[17], args[18]
+                        key = f"osb_convnext_block_fwd_train[rows={B * T},C={Cc},I={I}]"
+                        flops = 2.0 * B * T * (2 * Cc * I + 7 * Cc)
+                    elif name == "osb_convnext_block_bwd":
+                        B, T, Cc, I = args[10], args[11], args[12], args[13]
+                        key = f"osb_convnext_block_bwd[rows={B * T},C={Cc},I={I}]"
+                        flops = 2.0 * B * T * (2 * Cc * I)
                     elif name == "osb_gemm_wgrad":
                         B, T, N, K, taps = args[5], args[6], args[7], args[8], args[9]
                         key = f"osb_gemm_wgrad[rows={B * T},N={N},K={K},taps={taps}]"

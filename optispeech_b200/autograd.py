@@ -105,13 +105,28 @@ class LayerNormFn(Function):
 # ConvNeXt block
 # --------------------------------------------------------------------------------------------------
 class ConvNeXtBlockFn(Function):
-    """out = (x + gamma * pw2(gelu(pw1(LN(dwconv7(x))))) * row_scale[b]) * keep      (channels-last)"""
+    """out = (x + gamma * pw2(gelu(pw1(LN(dwconv7(x))))) * row_scale[b]) * keep      (channels-last)
+
+    Supported shapes ((C, I) = (256, 1024), (384, 1152)) run ONE fused tcgen05 kernel forward (osb_convnext_block_fwd_train:
+    dwconv + LN prologue, both pointwise convolutions, GELU, layer scale, DropPath, residual, mask; it also emits xhat / rstd /
+    pre-GELU / GELU activations for the backward) and, backward, one fused kernel for both data-gradient contractions
+    (osb_convnext_block_bwd) followed by one LayerNorm + depthwise-conv backward pass (osb_ln_dwconv_bwd).  The weight / bias /
+    layer-scale gradients only meet the optimizer: they run on a side stream (ops.grad_side)."""
+
+    FUSED = True   # tests flip this to compare the fused path with the three-kernel path below
 
     @staticmethod
     def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, pad_mask, row_scale, eps):
         B, T, C = x.shape
+        I = w1.shape[0]
         b1f = torch.addmv(b1, w1, ln_b)      # fold the LN affine into pwconv1: bias here, weight as a column scale of the pack
         w1f_h, w2_h = pack_params_nk([w1], col_scale=ln_w), pack_params_nk([w2])
+        ctx.fused = ConvNeXtBlockFn.FUSED and (C, I) in ops.FUSED_BLOCK_SHAPES
+        if ctx.fused:
+            out, xhat, rstd, pre, h = ops.convnext_block_fwd_train(x, dw_w.view(C, 7), dw_b, w1f_h[0], b1f, w2_h[0], b2, gamma, row_scale,
+                                                                   pad_mask, eps)
+            ctx.save_for_backward(x, dw_w, ln_w, ln_b, w1, w2, gamma, xhat, rstd, pre, h, out, pad_mask, row_scale, w1f_h, w2_h)
+            return out
         xhat, rstd = ops.dwconv_ln(x, dw_w.view(C, 7), dw_b, eps, want_rstd=True)
         h, pre, _ = ops.gemm(xhat, w1f_h, epi=ops.EPI_GELU, flags=ops.FLAG_SAVE_PRE, bias=b1f)
         flags = ops.FLAG_SAVE_PRE | (ops.FLAG_KEEPMASK if pad_mask is not None else 0)
@@ -123,10 +138,25 @@ class ConvNeXtBlockFn(Function):
     @staticmethod
     @ops.pooled
     def backward(ctx, dout):
-        x, dw_w, ln_w, ln_b, w1, w2, gamma, xhat, rstd, pre, h, z, pad_mask, row_scale, w1f_h, w2_h = ctx.saved_tensors
+        x, dw_w, ln_w, ln_b, w1, w2, gamma, xhat, rstd, pre, h, z_or_out, pad_mask, row_scale, w1f_h, w2_h = ctx.saved_tensors
         B, T, C = x.shape
         I = w1.shape[0]
         dout = dout.contiguous()
+        if ctx.fused:
+            out = z_or_out
+            dyg, dh, dxh = ops.convnext_block_bwd(dout, gamma, row_scale, pad_mask, pre, w2_h[0], w1f_h[0])
+            dx, ddw, ddb = ops.ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w.view(C, 7), pad_mask)
+            with ops.grad_side(x, dout, dyg, dh, h, xhat, out, x) as side:     # parameter gradients: off the critical path
+                dgamma, db2 = ops.resid_param_grad(dout, out, x, gamma, pad_mask, row_scale)
+                dw2 = ops.zeros((1, C, I), x)
+                ops.gemm_wgrad(dyg, h, dw2)
+                dw1f = ops.zeros((1, I, C), x)
+                ops.gemm_wgrad(dh, xhat, dw1f)
+                db1 = ops.colsum_h16(dh)
+                dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, ln_b, db1)
+                side.keepalive(dgamma, db2, dw2, dw1f, db1, dln_w, dln_b)
+            return dx, ddw.view(C, 1, 7), ddb, dln_w, dln_b, dw1, db1, dw2.view(C, I), db2, dgamma, None, None, None
+        z = z_or_out
         dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
         # pwconv2: dgrad (with the GELU derivative fused) and wgrad
         db1 = ops.zeros((I,), x)                                           # bias gradient: column sums taken in the dgrad epilogue

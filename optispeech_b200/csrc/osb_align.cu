@@ -654,22 +654,44 @@ __global__ void forward_sum_kernel(const float* __restrict__ lpa, const long lon
 // Warp-synchronous forward-sum recursion (round 2).  The 2N+1 states of the extended target live in REGISTERS: lane L owns the
 // SPL consecutive states s = SPL*L + j (SPL even, so register j is a blank state for even j and a token state for odd j, known
 // at compile time); a step needs one neighbour value from lane L-1 (alpha) or two from lane L+1 (beta): shuffles, no shared
-// memory, no __syncthreads.  The recursion runs in the LINEAR domain,
-//     alpha_t(s) = (alpha_{t-1}(s) + alpha_{t-1}(s-1) [+ alpha_{t-1}(s-2) for token states]) * p_t(s),
-// and every step the whole state vector is rescaled by an exact power of two (the exponent of the warp-wide maximum, one
-// REDUX on the float bit patterns), the exponents being accumulated in an integer: no exp / log on the dependency chain, and the
-// scaled values are bit-identical to an unscaled recursion of unbounded range.  Warp 0 walks alpha forward, warp 1 walks beta
-// backward (same CTA, no communication).  Workspaces receive the SCALED token-state values and, per frame, the accumulated
-// log-scale: log alpha_t(2k+1) = log(aw[t,k]) + ca[t].
+// memory, no __syncthreads.  The recursion stays in the LOG domain (base 2; a linear-domain recursion with a shared scale loses
+// states that are small against the frame's maximum but are the only ones able to finish, e.g. T = N), with the sorted form
+//     log2(2^a + 2^b + 2^c) = m + lg2(1 + 2^(mid - m) + 2^(lo - m)),
+// i.e. three MUFU operations per token state and two per blank state, all of a lane's SPL states independent of each other
+// within a step.  "Impossible" is a large finite negative number, so no branch guards a (-inf) - (-inf).
+// Warp 0 walks alpha forward, warp 1 walks beta backward (same CTA, no communication).  The workspaces receive the natural-log
+// alpha / beta of the token states, as the shared-memory kernel writes them (fs_grad_kernel reads either).
 // ------------------------------------------------------------------------------------------
-constexpr int FSW_G = 4;   // frames of emissions in flight per lane (register ring, two groups)
+constexpr int FSW_G = 4;               // frames of emissions in flight per lane (register ring, two groups)
+constexpr float FSW_NEG = -1.0e30f;    // log2 of an impossible state
+constexpr float FSW_LOG2E = 1.4426950408889634f;
+constexpr float FSW_LN2 = 0.69314718055994530942f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float l2add2(float a, float b) {          // log2(2^a + 2^b)
+  const float m = fmaxf(a, b);
+  return m + lg2_approx(1.f + ex2_approx(fminf(a, b) - m));
+}
+__device__ __forceinline__ float l2add3(float a, float b, float c) { // log2(2^a + 2^b + 2^c)
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);
+  return m + lg2_approx(1.f + ex2_approx(mid - m) + ex2_approx(lo - m));
+}
 
 template <int SPL>
 __global__ void __launch_bounds__(64)
 forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                         float blank_logit, const float* __restrict__ lse_ws, float* __restrict__ aw_all, float* __restrict__ bw_all,
-                        float* __restrict__ ca_all, float* __restrict__ cb_all, float* __restrict__ nll_ws, float* __restrict__ loss,
-                        int B, int Tm, int Tx) {
+                        float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx) {
   constexpr int TPL = SPL / 2;                 // token states per lane
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -683,35 +705,31 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
   const float* lp = lpa + static_cast<long long>(b) * Tm * Tx;
   const float* lse = lse_ws + static_cast<long long>(b) * Tm;
   float* ws = (is_beta ? bw_all : aw_all) + static_cast<long long>(b) * Tm * Tx;
-  float* cs = (is_beta ? cb_all : ca_all) + static_cast<long long>(b) * Tm;
-  const int k0 = TPL * lane;                   // first token of this lane; blank slot of register 2i is k0 + i
-  // validity of this lane's states: token k < N, blank slot k <= N
-  bool tok_ok[TPL], blk_ok[TPL];
+  const int k0 = TPL * lane;                   // first token of this lane; the blank state of register 2i belongs to slot k0 + i
+  bool tok_ok[TPL], blk_ok[TPL];               // token k < N, blank slot k <= N
 #pragma unroll
   for (int i = 0; i < TPL; ++i) { tok_ok[i] = k0 + i < N; blk_ok[i] = k0 + i <= N; }
   auto frame = [&](int i) { return is_beta ? T - 1 - i : i; };   // frame visited at step i
 
-  float a[SPL];
+  float a[SPL];                                // log2 of the state values
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) a[j] = 0.f;
-  int E = 0;   // accumulated binary exponent of the scale factors: true value = a * 2^E
+  for (int j = 0; j < SPL; ++j) a[j] = FSW_NEG;
   {
     const int f0 = frame(0);
     const float l0 = lse[f0];
-    const float pb = __expf(blank_logit - l0);
+    const float eb = (blank_logit - l0) * FSW_LOG2E;
     if (!is_beta) {          // alpha_0: blank state 0 and token state 1
-      if (lane == 0) { a[0] = pb; a[1] = __expf(lp[static_cast<long long>(f0) * Tx] - l0); }
+      if (lane == 0) { a[0] = eb; a[1] = (lp[static_cast<long long>(f0) * Tx] - l0) * FSW_LOG2E; }
     } else {                 // beta_{T-1}: last blank state 2N and last token state 2N-1
 #pragma unroll
       for (int i = 0; i < TPL; ++i) {
-        if (k0 + i == N) a[2 * i] = pb;
-        if (k0 + i == N - 1) a[2 * i + 1] = __expf(lp[static_cast<long long>(f0) * Tx + N - 1] - l0);
+        if (k0 + i == N) a[2 * i] = eb;
+        if (k0 + i == N - 1) a[2 * i + 1] = (lp[static_cast<long long>(f0) * Tx + N - 1] - l0) * FSW_LOG2E;
       }
     }
 #pragma unroll
     for (int i = 0; i < TPL; ++i)
-      if (tok_ok[i]) ws[static_cast<long long>(f0) * Tx + k0 + i] = a[2 * i + 1];
-    if (lane == 0) cs[f0] = 0.f;
+      if (tok_ok[i]) ws[static_cast<long long>(f0) * Tx + k0 + i] = a[2 * i + 1] > 0.5f * FSW_NEG ? a[2 * i + 1] * FSW_LN2 : -INFINITY;
   }
 
   // emissions of the next frames, fetched FSW_G steps ahead (two register groups)
@@ -740,50 +758,38 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
       if (step < T) {   // warp-uniform
         const int f = frame(step);
         const float l = lf[g];
-        const float pb = __expf(blank_logit - l);
-        float p[TPL];
+        const float eb = (blank_logit - l) * FSW_LOG2E;
+        float em[TPL];                                                   // log2 emission of this lane's tokens (impossible: FSW_NEG)
 #pragma unroll
-        for (int i = 0; i < TPL; ++i) p[i] = __expf(e[g][i] - l);      // exp(-inf) = 0 for invalid tokens
+        for (int i = 0; i < TPL; ++i) em[i] = fmaxf((e[g][i] - l) * FSW_LOG2E, FSW_NEG);
         float n[SPL];
         if (!is_beta) {
           float pm = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);        // state SPL*L - 1
-          if (lane == 0) pm = 0.f;
-          n[0] = blk_ok[0] ? (a[0] + pm) * pb : 0.f;
-          n[1] = (a[1] + a[0] + pm) * p[0];
+          if (lane == 0) pm = FSW_NEG;
+          n[0] = blk_ok[0] ? l2add2(a[0], pm) + eb : FSW_NEG;
+          n[1] = l2add3(a[1], a[0], pm) + em[0];
 #pragma unroll
           for (int i = 1; i < TPL; ++i) {
-            n[2 * i] = blk_ok[i] ? (a[2 * i] + a[2 * i - 1]) * pb : 0.f;
-            n[2 * i + 1] = (a[2 * i + 1] + a[2 * i] + a[2 * i - 1]) * p[i];
+            n[2 * i] = blk_ok[i] ? l2add2(a[2 * i], a[2 * i - 1]) + eb : FSW_NEG;
+            n[2 * i + 1] = l2add3(a[2 * i + 1], a[2 * i], a[2 * i - 1]) + em[i];
           }
         } else {
           float nx0 = __shfl_down_sync(0xffffffffu, a[0], 1);            // states SPL*(L+1), SPL*(L+1) + 1
           float nx1 = __shfl_down_sync(0xffffffffu, a[1], 1);
-          if (lane == 31) { nx0 = 0.f; nx1 = 0.f; }
+          if (lane == 31) { nx0 = FSW_NEG; nx1 = FSW_NEG; }
 #pragma unroll
           for (int i = 0; i < TPL - 1; ++i) {
-            n[2 * i] = blk_ok[i] ? (a[2 * i] + a[2 * i + 1]) * pb : 0.f;
-            n[2 * i + 1] = (a[2 * i + 1] + a[2 * i + 2] + a[2 * i + 3]) * p[i];
+            n[2 * i] = blk_ok[i] ? l2add2(a[2 * i], a[2 * i + 1]) + eb : FSW_NEG;
+            n[2 * i + 1] = l2add3(a[2 * i + 1], a[2 * i + 2], a[2 * i + 3]) + em[i];
           }
-          n[SPL - 2] = blk_ok[TPL - 1] ? (a[SPL - 2] + a[SPL - 1]) * pb : 0.f;
-          n[SPL - 1] = (a[SPL - 1] + nx0 + nx1) * p[TPL - 1];
-        }
-        // rescale by the exponent of the warp-wide maximum (non-negative floats order like their bit patterns)
-        float m = n[0];
-#pragma unroll
-        for (int j = 1; j < SPL; ++j) m = fmaxf(m, n[j]);
-        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-        float scale = 1.f;
-        if (wm != 0u && wm < 0x7f800000u) {
-          const int ex = static_cast<int>(wm >> 23) - 127;               // max in [2^ex, 2^(ex+1)); subnormal max: ex = -127
-          scale = __uint_as_float(static_cast<unsigned>(127 - ex) << 23);
-          E += ex;
+          n[SPL - 2] = blk_ok[TPL - 1] ? l2add2(a[SPL - 2], a[SPL - 1]) + eb : FSW_NEG;
+          n[SPL - 1] = l2add3(a[SPL - 1], nx0, nx1) + em[TPL - 1];
         }
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) a[j] = n[j] * scale;
+        for (int j = 0; j < SPL; ++j) a[j] = fmaxf(n[j], FSW_NEG);      // impossible states stay at the sentinel
 #pragma unroll
         for (int i = 0; i < TPL; ++i)
-          if (tok_ok[i]) ws[static_cast<long long>(f) * Tx + k0 + i] = a[2 * i + 1];
-        if (lane == 0) cs[f] = static_cast<float>(E) * 0.69314718055994530942f;
+          if (tok_ok[i]) ws[static_cast<long long>(f) * Tx + k0 + i] = a[2 * i + 1] > 0.5f * FSW_NEG ? a[2 * i + 1] * FSW_LN2 : -INFINITY;
       }
     }
 #pragma unroll
@@ -793,43 +799,23 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
       for (int i = 0; i < TPL; ++i) e[g][i] = en[g][i];
     }
   }
-  if (!is_beta) {   // log-likelihood = log(alpha_{T-1}(S-1) + alpha_{T-1}(S-2)) + E ln 2
-    float v = 0.f;
+  if (!is_beta) {   // log-likelihood = log(alpha_{T-1}(S-1) + alpha_{T-1}(S-2))
+    float v1 = FSW_NEG, v2 = FSW_NEG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const int s = SPL * lane + j;
-      if (s == S - 1 || s == S - 2) v += a[j];
+      if (s == S - 1) v1 = a[j];
+      if (s == S - 2) v2 = a[j];
     }
-    v = warp_sum(v);
+    v1 = warp_max(v1);
+    v2 = warp_max(v2);
     if (lane == 0) {
-      const float ll = logf(v) + static_cast<float>(E) * 0.69314718055994530942f;
-      const bool finite = ll > -INFINITY && ll < INFINITY;
+      const float ll = l2add2(v1, v2) * FSW_LN2;
+      const bool finite = ll > 0.5f * FSW_NEG && ll < INFINITY;
       loss[b] = finite ? -ll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
       nll_ws[b] = finite ? -ll : INFINITY;
     }
   }
-}
-
-// gradient for the scaled linear-domain workspaces: posterior = exp(log aw + log bw + ca + cb - e + nll)
-__global__ void fs_grad_scaled_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
-                                      const float* __restrict__ lse_ws, const float* __restrict__ aw, const float* __restrict__ bw,
-                                      const float* __restrict__ ca, const float* __restrict__ cb, const float* __restrict__ nll_ws,
-                                      float* __restrict__ grad, int B, int Tm, int Tx) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(B) * Tm * Tx) return;
-  const int n = static_cast<int>(idx % Tx);
-  const long long row = idx / Tx;
-  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
-  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
-  float g = 0.f;
-  const float nll = nll_ws[b];
-  if (t < T && n < N && nll < INFINITY) {
-    const float e = lpa[idx] - lse_ws[row];
-    const float av = aw[idx], bv = bw[idx];
-    const float post = (av > 0.f && bv > 0.f) ? expf(logf(av) + logf(bv) + ((ca[row] + cb[row]) + nll) - e) : 0.f;
-    g = (expf(e) - post) / (static_cast<float>(N) * static_cast<float>(B));
-  }
-  grad[idx] = g;
 }
 
 // gradient, fully parallel over (b, t, n): softmax minus posterior occupancy, with the per-sample 1/N and the batch 1/B
@@ -885,12 +871,10 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   // warp-synchronous register recursion when the 2 Tx + 1 states fit 32 lanes x SPL registers; else the shared-memory kernel
   const int S_max = 2 * Tx + 1;
   if (S_max <= 32 * 26 && !g_fs_force_legacy) {
-    float* ca = nll_ws + B;
-    float* cb = ca + rows;
-    if (S_max <= 32 * 8) osb::forward_sum_warp_kernel<8><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, ca, cb, nll_ws, loss, B, Tm, Tx);
-    else if (S_max <= 32 * 14) osb::forward_sum_warp_kernel<14><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, ca, cb, nll_ws, loss, B, Tm, Tx);
-    else osb::forward_sum_warp_kernel<26><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, ca, cb, nll_ws, loss, B, Tm, Tx);
-    osb::fs_grad_scaled_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, ca, cb, nll_ws, grad, B, Tm, Tx);
+    if (S_max <= 32 * 8) osb::forward_sum_warp_kernel<8><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    else if (S_max <= 32 * 14) osb::forward_sum_warp_kernel<14><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    else osb::forward_sum_warp_kernel<26><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    osb::fs_grad_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
     osb::count_launch(3);
     return osb::launch_status();
   }

@@ -36,6 +36,12 @@ struct FusedParams {
   const float* row_scale;   // (B) or null
   const uint8_t* pad_mask;  // (B*T) or null
   float* out;            // (B, T, C)
+  // training mode (kTrain): activations the hand-written backward needs, written while they are on chip
+  __half* xhat_out;      // (B, T, C) fp16 normalised dwconv output (A operand of pwconv1, LN affine folded into W1f)
+  float* rstd_out;       // (B, T)
+  __half* pre_out;       // (B, T, I) fp16 pwconv1 output + bias (GELU argument)
+  __half* h_out;         // (B, T, I) fp16 GELU output (A operand of pwconv2)
+  int I;
   int B, T, m_tiles;
   int nsplit;            // > 1: blockIdx.y owns a slice of the intermediate chunks and adds its partial result into `out` (pre-zeroed)
   float eps;
@@ -65,7 +71,7 @@ struct FusedCfg {
 // 16-byte chunk `c16` (0..7) of row `r` inside a [rows x 128 B] tile with the 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) { return static_cast<uint32_t>(r * 128 + ((c16 ^ (r & 7)) << 4)); }
 
-template <int C, int I>
+template <int C, int I, bool kTrain>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FusedParams p) {
   using Cfg = FusedCfg<C>;
@@ -291,6 +297,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           u.x = *reinterpret_cast<uint32_t*>(&h0);
           u.y = *reinterpret_cast<uint32_t*>(&h1);
           *reinterpret_cast<uint2*>(sA + kb * (FB_M * 128) + sw128_offset(r, cc >> 3) + (cc & 7) * 2) = u;
+          if constexpr (kTrain) {
+            if (split == 0 && t < p.T) *reinterpret_cast<uint2*>(p.xhat_out + (static_cast<long long>(b) * p.T + t) * C + c) = u;
+          }
+        }
+        if constexpr (kTrain) {
+          if (split == 0 && t < p.T && lane == 0) p.rstd_out[static_cast<long long>(b) * p.T + t] = rstd;
         }
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -323,6 +335,24 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       if (lane == 0) mbar_arrive(&acc1_empty[buf]);
       if (ww == 0 && lane == 0) FB_TRACE(2, 2 + 5 * j);
       float v[32];
+      if constexpr (kTrain) {
+        // pre-activation (fp16) -> HBM: this thread's 32 columns of its row are 64 contiguous bytes
+        const int t = t0 + row;
+        if (t < p.T) {
+          __half* dst = p.pre_out + (static_cast<long long>(b) * p.T + t) * p.I + (ch_begin + j) * FB_NC + half * 32;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 u;
+            __half2 h0 = __floats2half2_rn(__uint_as_float(rr[c4 * 8 + 0]) + bias_cur[c4 * 8 + 0], __uint_as_float(rr[c4 * 8 + 1]) + bias_cur[c4 * 8 + 1]);
+            __half2 h1 = __floats2half2_rn(__uint_as_float(rr[c4 * 8 + 2]) + bias_cur[c4 * 8 + 2], __uint_as_float(rr[c4 * 8 + 3]) + bias_cur[c4 * 8 + 3]);
+            __half2 h2 = __floats2half2_rn(__uint_as_float(rr[c4 * 8 + 4]) + bias_cur[c4 * 8 + 4], __uint_as_float(rr[c4 * 8 + 5]) + bias_cur[c4 * 8 + 5]);
+            __half2 h3 = __floats2half2_rn(__uint_as_float(rr[c4 * 8 + 6]) + bias_cur[c4 * 8 + 6], __uint_as_float(rr[c4 * 8 + 7]) + bias_cur[c4 * 8 + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + c4 * 8) = u;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(__uint_as_float(rr[i]) + bias_cur[i]);
 #pragma unroll
@@ -343,6 +373,11 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
         u.z = *reinterpret_cast<uint32_t*>(&h2);
         u.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(hrow + sw128_offset(row, half * 4 + c4)) = u;
+        if constexpr (kTrain) {
+          const int t = t0 + row;
+          if (t < p.T)
+            *reinterpret_cast<uint4*>(p.h_out + (static_cast<long long>(b) * p.T + t) * p.I + (ch_begin + j) * FB_NC + half * 32 + c4 * 8) = u;
+        }
       }
       if (ww == 0 && lane == 0 && j < 8) FB_TRACE(2, 210 + j);
       fence_proxy_async_smem();
@@ -408,7 +443,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-template <int C, int I>
+template <int C, int I, bool kTrain>
 int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, cudaStream_t stream) {
   using Cfg = FusedCfg<C>;
   CUtensorMap tmW1, tmW2;
@@ -419,7 +454,7 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
   if (rc != OSB_OK) return rc;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C, I, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr = true;
   }
@@ -427,7 +462,7 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
     cudaError_t e = cudaMemsetAsync(p.out, 0, static_cast<size_t>(p.B) * p.T * C * sizeof(float), stream);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  convnext_fused_kernel<C, I><<<dim3(p.B * p.m_tiles, p.nsplit), FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
+  convnext_fused_kernel<C, I, kTrain><<<dim3(p.B * p.m_tiles, p.nsplit), FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
   count_launch();
   return launch_status();
 }
@@ -444,15 +479,18 @@ extern "C" void osb_debug_set_fused_nsplit(int n) { g_fused_nsplit = n; }
 /* developer hook (not in the public header): device buffer of 3*256 int64 receiving a clock64 timeline of CTA 0 */
 extern "C" void osb_debug_set_fused_trace(long long* buf) { g_fused_trace = buf; }
 
-extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
-                                      const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
-                                      const uint8_t* pad_mask, float* out, int32_t B, int32_t T, int32_t C, int32_t I, float eps,
-                                      void* stream) {
+static int fused_fwd_impl(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f, const void* w2_h16,
+                          const float* b2, const float* gamma, const float* row_scale, const uint8_t* pad_mask, float* out, void* xhat_out,
+                          float* rstd_out, void* pre_out, void* h_out, int32_t B, int32_t T, int32_t C, int32_t I, float eps, void* stream) {
   OSB_REQUIRE(x && dw_w && dw_b && w1f_h16 && b1f && w2_h16 && b2 && gamma && out, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0, OSB_ERR_SHAPE);
+  const bool train = xhat_out != nullptr;
+  if (train) OSB_REQUIRE(rstd_out && pre_out && h_out, OSB_ERR_ARG);
   FusedParams p;
   p.x = x; p.dw_w = dw_w; p.dw_b = dw_b; p.b1 = b1f; p.b2 = b2; p.gamma = gamma; p.row_scale = row_scale; p.pad_mask = pad_mask;
-  p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps;
+  p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps; p.I = I;
+  p.xhat_out = static_cast<__half*>(xhat_out); p.rstd_out = rstd_out; p.pre_out = static_cast<__half*>(pre_out);
+  p.h_out = static_cast<__half*>(h_out);
   // Fewer row tiles than half the SMs: split the intermediate dimension so that the weight streaming (the per-CTA bound: every
   // CTA walks all I/64 chunks) is spread over the machine; each split keeps at least two chunks.
   {
@@ -464,7 +502,24 @@ extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const f
   }
   p.trace = g_fused_trace;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (C == 256 && I == 1024) return launch_fused<256, 1024>(w1f_h16, w2_h16, p, s);
-  if (C == 384 && I == 1152) return launch_fused<384, 1152>(w1f_h16, w2_h16, p, s);
+  if (C == 256 && I == 1024) return train ? launch_fused<256, 1024, true>(w1f_h16, w2_h16, p, s) : launch_fused<256, 1024, false>(w1f_h16, w2_h16, p, s);
+  if (C == 384 && I == 1152) return train ? launch_fused<384, 1152, true>(w1f_h16, w2_h16, p, s) : launch_fused<384, 1152, false>(w1f_h16, w2_h16, p, s);
   return OSB_ERR_SHAPE;
+}
+
+extern "C" int osb_convnext_block_fwd(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
+                                      const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
+                                      const uint8_t* pad_mask, float* out, int32_t B, int32_t T, int32_t C, int32_t I, float eps,
+                                      void* stream) {
+  return fused_fwd_impl(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale, pad_mask, out, nullptr, nullptr, nullptr, nullptr, B, T, C,
+                        I, eps, stream);
+}
+
+extern "C" int osb_convnext_block_fwd_train(const float* x, const float* dw_w, const float* dw_b, const void* w1f_h16, const float* b1f,
+                                            const void* w2_h16, const float* b2, const float* gamma, const float* row_scale,
+                                            const uint8_t* pad_mask, float* out, void* xhat_h16, float* rstd, void* pre_h16, void* h_h16,
+                                            int32_t B, int32_t T, int32_t C, int32_t I, float eps, void* stream) {
+  OSB_REQUIRE(xhat_h16 && rstd && pre_h16 && h_h16, OSB_ERR_ARG);
+  return fused_fwd_impl(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale, pad_mask, out, xhat_h16, rstd, pre_h16, h_h16, B, T, C, I,
+                        eps, stream);
 }

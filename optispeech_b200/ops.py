@@ -468,7 +468,7 @@ def beta_binomial_prior(log_factorial, x_len, m_len, Tm: int, Tx: int):
 def forward_sum(log_p_attn, x_len, m_len, blank_logit: float = -1.0):
     """-> (per-sample loss (B,), grad (B,Tm,Tx) of sum(loss)/B w.r.t. log_p_attn)."""
     B, Tm, Tx = log_p_attn.shape
-    ws = torch.empty((2 * B * Tm * Tx + 3 * B * Tm + B,), device=log_p_attn.device, dtype=torch.float32)
+    ws = torch.empty((2 * B * Tm * Tx + B * Tm + B,), device=log_p_attn.device, dtype=torch.float32)
     loss = torch.empty((B,), device=log_p_attn.device, dtype=torch.float32)
     grad = torch.empty((B, Tm, Tx), device=log_p_attn.device, dtype=torch.float32)
     _lib.check(_lib.load().osb_forward_sum(_ptr(_f32(log_p_attn)), _ptr(x_len), _ptr(m_len), float(blank_logit), _ptr(ws), _ptr(loss),
@@ -502,6 +502,117 @@ def convnext_block_fwd(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale
                                                   _ptr(w2_h16), _ptr(_f32(b2)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask),
                                                   _ptr(out), B, T, Cc, I, float(eps), _stream()), "osb_convnext_block_fwd")
     return out
+
+
+def convnext_block_fwd_train(x, dw_w, dw_b, w1f_h16, b1f, w2_h16, b2, gamma, row_scale=None, pad_mask=None, eps: float = 1e-6):
+    """Fused ConvNeXt block forward that also emits the activations the backward needs (one launch).
+    -> (out fp32 (B,T,C), xhat fp16 (B,T,C), rstd fp32 (B,T), pre fp16 (B,T,I), h fp16 (B,T,I))."""
+    B, T, Cc = x.shape
+    I = w1f_h16.shape[-2]
+    out = torch.empty_like(x)
+    xhat = torch.empty((B, T, Cc), device=x.device, dtype=torch.float16)
+    rstd = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    pre = torch.empty((B, T, I), device=x.device, dtype=torch.float16)
+    h = torch.empty((B, T, I), device=x.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_convnext_block_fwd_train(_ptr(_f32(x)), _ptr(_f32(dw_w)), _ptr(_f32(dw_b)), _ptr(w1f_h16), _ptr(_f32(b1f)),
+                                                        _ptr(w2_h16), _ptr(_f32(b2)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask),
+                                                        _ptr(out), _ptr(xhat), _ptr(rstd), _ptr(pre), _ptr(h), B, T, Cc, I, float(eps),
+                                                        _stream()), "osb_convnext_block_fwd_train")
+    return out, xhat, rstd, pre, h
+
+
+def convnext_block_bwd(dout, gamma, row_scale, pad_mask, pre, w2_h16, w1f_h16):
+    """Both data-gradient contractions of a ConvNeXt block in one launch.
+    -> (dyg fp16 (B,T,C), dh fp16 (B,T,I), dxhat fp32 (B,T,C))."""
+    B, T, Cc = dout.shape
+    I = pre.shape[-1]
+    dyg = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float16)
+    dh = torch.empty((B, T, I), device=dout.device, dtype=torch.float16)
+    dxh = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_convnext_block_bwd(_ptr(_f32(dout)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask), _ptr(pre), _ptr(w2_h16),
+                                                  _ptr(w1f_h16), _ptr(dyg), _ptr(dh), _ptr(dxh), B, T, Cc, I, _stream()),
+               "osb_convnext_block_bwd")
+    return dyg, dh, dxh
+
+
+def ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w, pad_mask):
+    """LayerNorm backward + depthwise conv backward + residual path -> (dx, ddw (C,7), ddb (C))."""
+    B, T, Cc = x.shape
+    dx = torch.empty_like(x)
+    ddw, ddb = _zeros((Cc, 7), x), _zeros((Cc,), x)
+    _lib.check(_lib.load().osb_ln_dwconv_bwd(_ptr(_f32(dxh)), _ptr(xhat), _ptr(_f32(rstd)), _ptr(_f32(dout)), _ptr(_f32(x)), _ptr(_f32(dw_w)),
+                                             _ptr(pad_mask), _ptr(dx), _ptr(ddw), _ptr(ddb), B, T, Cc, _stream()), "osb_ln_dwconv_bwd")
+    return dx, ddw, ddb
+
+
+def resid_param_grad(dout, out, x, gamma, pad_mask, row_scale):
+    """-> (dgamma (C), db2 (C)) of the residual epilogue from the block's input and output (no saved pwconv2 output)."""
+    B, T, Cc = x.shape
+    dgamma, db2 = _zeros((Cc,), x), _zeros((Cc,), x)
+    _lib.check(_lib.load().osb_resid_param_grad(_ptr(_f32(dout)), _ptr(_f32(out)), _ptr(_f32(x)), _ptr(_f32(gamma)), _ptr(pad_mask),
+                                                _ptr(row_scale), _ptr(dgamma), _ptr(db2), B * T, T, Cc, _stream()), "osb_resid_param_grad")
+    return dgamma, db2
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-gradient side streams: parameter gradients are only consumed by the optimizer at the end of the step, so the
+# contractions / reductions that produce them leave the critical path (data gradients) of the backward pass
+# ------------------------------------------------------------------------------------------------
+_GRAD_PENDING = {"streams": [], "keep": [], "hooked": False, "rr": 0}
+GRAD_SIDE_SLOTS = (6, 7)
+
+
+class grad_side:
+    """Context manager: run the enclosed weight-gradient work on a side stream forked from the current one.  The side stream
+    is joined (and the tensors it reads released) when the running backward pass finishes — a callback queued on the autograd
+    engine — or explicitly by join_grad_streams().  Inside a CUDA-graph capture the fork / join become graph dependencies."""
+
+    def __init__(self, like: torch.Tensor, *keep):
+        self.dev = like.device
+        self.keep = keep
+        self.enabled = SIDE_STREAMS_ENABLED and like.is_cuda
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        st = _GRAD_PENDING
+        slot = GRAD_SIDE_SLOTS[st["rr"] % len(GRAD_SIDE_SLOTS)]
+        st["rr"] += 1
+        self.side = side_stream(self.dev, slot)
+        self.side.wait_stream(torch.cuda.current_stream(self.dev))
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def keepalive(self, *tensors):
+        """Tensors allocated on the main stream that the side stream reads / writes: held until the join."""
+        if self.enabled:
+            _GRAD_PENDING["keep"].extend(t for t in tensors if t is not None)
+
+    def __exit__(self, *exc):
+        if not self.enabled:
+            return False
+        self.ctx.__exit__(*exc)
+        st = _GRAD_PENDING
+        if self.side not in st["streams"]:
+            st["streams"].append(self.side)
+        st["keep"].extend(t for t in self.keep if t is not None)
+        if not st["hooked"]:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(join_grad_streams)
+                st["hooked"] = True
+            except RuntimeError:     # not inside a backward pass: the caller joins
+                pass
+        return False
+
+
+def join_grad_streams():
+    st = _GRAD_PENDING
+    if st["streams"]:
+        cur = torch.cuda.current_stream(st["streams"][0].device)
+        for s_ in st["streams"]:
+            cur.wait_stream(s_)
+    st["streams"], st["keep"], st["hooked"] = [], [], False
 
 
 # ------------------------------------------------------------------------------------------------

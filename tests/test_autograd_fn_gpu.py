@@ -36,9 +36,22 @@ def test_layernorm_fn(cuda_device):
     _check([("y", y, yr), ("dx", gx, rx), ("dw", gw, rw), ("db", gb, rb)], 1e-5)
 
 
-@pytest.mark.parametrize("C,I,T", [(256, 1024, 77), (384, 1152, 64)])
-def test_convnext_block_fn(cuda_device, C, I, T):
+@pytest.mark.parametrize("C,I,T,nsplit,fused", [(256, 1024, 77, 0, True), (384, 1152, 64, 0, True), (256, 1024, 300, 1, True),
+                                                 (256, 1024, 300, 3, True), (384, 1152, 200, 1, True), (256, 1024, 77, 0, False)])
+def test_convnext_block_fn(cuda_device, C, I, T, nsplit, fused):
+    """ConvNeXtBlockFn forward + every gradient against the oracle block under torch autograd: the fused tcgen05 forward /
+    backward kernels (intermediate dimension split over CTAs automatically, not at all, or 3-way) and the three-kernel path."""
+    import ctypes
+
+    from optispeech_b200 import _lib
     from optispeech_b200.autograd import ConvNeXtBlockFn
+
+    lib = _lib.load()
+    for fn in (lib.osb_debug_set_fused_nsplit, lib.osb_debug_set_bwd_nsplit):
+        fn.argtypes = [ctypes.c_int]
+        fn.restype = None
+        fn(nsplit)
+    ConvNeXtBlockFn.FUSED = fused
 
     g = torch.Generator().manual_seed(1)
     B = 3
@@ -58,8 +71,14 @@ def test_convnext_block_fn(cuda_device, C, I, T):
     names = ["dwconv.weight", "dwconv.bias", "norm.weight", "norm.bias", "pwconv1.weight", "pwconv1.bias", "pwconv2.weight",
              "pwconv2.bias", "gamma"]
     params = [sd[f"b.{n}"] for n in names]
-    y = ConvNeXtBlockFn.apply(x, *params, pad.to(torch.uint8), rs, 1e-6)
-    grads = torch.autograd.grad(y, (x, *params), dy)
+    try:
+        y = ConvNeXtBlockFn.apply(x, *params, pad.to(torch.uint8), rs, 1e-6)
+        grads = torch.autograd.grad(y, (x, *params), dy)
+        torch.cuda.synchronize()
+    finally:
+        ConvNeXtBlockFn.FUSED = True
+        lib.osb_debug_set_fused_nsplit(0)
+        lib.osb_debug_set_bwd_nsplit(0)
     yr = O.convnext_block(sd, "b", x, drop_scale=rs) * (1 - pad.float())[..., None]
     rgrads = torch.autograd.grad(yr, (x, *params), dy)
     _check([("y", y, yr)] + [(n, a, b) for n, a, b in zip(["dx"] + names, grads, rgrads)], 4e-3)
