@@ -492,10 +492,11 @@ int osb_convnext_block_bwd(const float* dout, const float* gamma, const float* r
                            int32_t C, int32_t I, void* stream);
 
 /* LayerNorm backward (affine folded away) + depthwise conv7 backward + residual path + depthwise parameter gradients in one pass:
- *   dd = LN_bwd(dxhat; xhat, rstd);  dx[t] = dout[t] * keep[t] + sum_j w[:,j] * dd[t-j+3];  ddw (C,7) += ..., ddb (C) += ...
- * (ddw / ddb are accumulated: zero them first).  Autograd of nn.Conv1d(groups=C) + nn.LayerNorm (modules/convnext.py:36-38). */
+ *   dd = LN_bwd(dxhat; xhat, rstd);  dx[t] = dout[t] * keep[t] + sum_j w[:,j] * dd[t-j+3]
+ *   dparam (8, C) fp32 += [ddw[:,0] | ... | ddw[:,6] | ddb]   (tap-major; accumulated: zero it first)
+ * Autograd of nn.Conv1d(groups=C) + nn.LayerNorm (modules/convnext.py:36-38). */
 int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const float* rstd, const float* dout, const float* x, const float* dw_w,
-                      const uint8_t* pad_mask, float* dx, float* ddw, float* ddb, int32_t B, int32_t T, int32_t C, void* stream);
+                      const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T, int32_t C, void* stream);
 
 /* Layer-scale and pwconv2-bias gradients from the block's input x and output out (gamma * z * rs = out - x on unmasked rows):
  *   dgamma += sum_rows dout * keep * (out - x) / gamma ;  db2 += sum_rows dout * keep * rs * gamma   (modules/convnext.py:42-46) */

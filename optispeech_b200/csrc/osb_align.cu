@@ -687,15 +687,22 @@ __device__ __forceinline__ float l2add3(float a, float b, float c) { // log2(2^a
   return m + lg2_approx(1.f + ex2_approx(mid - m) + ex2_approx(lo - m));
 }
 
-template <int SPL>
-__global__ void __launch_bounds__(64)
+// W warps per recursion (a single warp issues at ~0.45 instructions / cycle: the recursion is issue bound, not latency bound —
+// ncu, round 2): the chain of a sample is spread over W warps; the one value (alpha) / two values (beta) that cross a warp
+// boundary go through a double-buffered shared-memory mailbox and ONE named barrier per step and chain.
+template <int SPL, int W>
+__global__ void __launch_bounds__(64 * W)
 forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                         float blank_logit, const float* __restrict__ lse_ws, float* __restrict__ aw_all, float* __restrict__ bw_all,
                         float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx) {
   constexpr int TPL = SPL / 2;                 // token states per lane
+  __shared__ float mbox[2][2][W][2];           // [chain][slot][warp][value]
+  __shared__ float fin[2];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool is_beta = (threadIdx.x >> 5) != 0;
+  const bool is_beta = threadIdx.x >= 32 * W;
+  const int wc = (threadIdx.x >> 5) - (is_beta ? W : 0);      // warp index inside its chain
+  const int gl = wc * 32 + lane;                               // lane index inside the chain
   const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
   if (N <= 0 || T <= 0) {
     if (threadIdx.x == 0) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
@@ -705,11 +712,16 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
   const float* lp = lpa + static_cast<long long>(b) * Tm * Tx;
   const float* lse = lse_ws + static_cast<long long>(b) * Tm;
   float* ws = (is_beta ? bw_all : aw_all) + static_cast<long long>(b) * Tm * Tx;
-  const int k0 = TPL * lane;                   // first token of this lane; the blank state of register 2i belongs to slot k0 + i
+  const int k0 = TPL * gl;                     // first token of this lane; the blank state of register 2i belongs to slot k0 + i
   bool tok_ok[TPL], blk_ok[TPL];               // token k < N, blank slot k <= N
 #pragma unroll
   for (int i = 0; i < TPL; ++i) { tok_ok[i] = k0 + i < N; blk_ok[i] = k0 + i <= N; }
   auto frame = [&](int i) { return is_beta ? T - 1 - i : i; };   // frame visited at step i
+  auto chain_barrier = [&]() {
+    if (is_beta) asm volatile("bar.sync 2, %0;" ::"n"(32 * W) : "memory");
+    else asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory");
+  };
+  const int ch = is_beta ? 1 : 0;
 
   float a[SPL];                                // log2 of the state values
 #pragma unroll
@@ -719,7 +731,7 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
     const float l0 = lse[f0];
     const float eb = (blank_logit - l0) * FSW_LOG2E;
     if (!is_beta) {          // alpha_0: blank state 0 and token state 1
-      if (lane == 0) { a[0] = eb; a[1] = (lp[static_cast<long long>(f0) * Tx] - l0) * FSW_LOG2E; }
+      if (gl == 0) { a[0] = eb; a[1] = (lp[static_cast<long long>(f0) * Tx] - l0) * FSW_LOG2E; }
     } else {                 // beta_{T-1}: last blank state 2N and last token state 2N-1
 #pragma unroll
       for (int i = 0; i < TPL; ++i) {
@@ -729,8 +741,11 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
     }
 #pragma unroll
     for (int i = 0; i < TPL; ++i)
-      if (tok_ok[i]) ws[static_cast<long long>(f0) * Tx + k0 + i] = a[2 * i + 1] > 0.5f * FSW_NEG ? a[2 * i + 1] * FSW_LN2 : -INFINITY;
+      if (tok_ok[i]) ws[static_cast<long long>(f0) * Tx + k0 + i] = a[2 * i + 1];
+    if (!is_beta && lane == 31) mbox[0][0][wc][0] = a[SPL - 1];
+    if (is_beta && lane == 0) { mbox[1][0][wc][0] = a[0]; mbox[1][0][wc][1] = a[1]; }
   }
+  chain_barrier();
 
   // emissions of the next frames, fetched FSW_G steps ahead (two register groups)
   float e[FSW_G][TPL], en[FSW_G][TPL], lf[FSW_G], lfn[FSW_G];
@@ -755,17 +770,18 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
 #pragma unroll
     for (int g = 0; g < FSW_G; ++g) {
       const int step = base + g;
-      if (step < T) {   // warp-uniform
+      if (step < T) {   // uniform across the CTA
         const int f = frame(step);
-        const float l = lf[g];
-        const float eb = (blank_logit - l) * FSW_LOG2E;
+        const int rs = (step - 1) & 1, wsl = step & 1;                   // mailbox slots: read the previous step's, write this step's
+        const float nl2 = -lf[g] * FSW_LOG2E;
+        const float eb = fmaf(blank_logit, FSW_LOG2E, nl2);
         float em[TPL];                                                   // log2 emission of this lane's tokens (impossible: FSW_NEG)
 #pragma unroll
-        for (int i = 0; i < TPL; ++i) em[i] = fmaxf((e[g][i] - l) * FSW_LOG2E, FSW_NEG);
+        for (int i = 0; i < TPL; ++i) em[i] = fmaxf(fmaf(e[g][i], FSW_LOG2E, nl2), FSW_NEG);
         float n[SPL];
         if (!is_beta) {
-          float pm = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);        // state SPL*L - 1
-          if (lane == 0) pm = FSW_NEG;
+          float pm = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);        // state SPL*gl - 1
+          if (lane == 0) pm = wc > 0 ? mbox[0][rs][wc - 1][0] : FSW_NEG;
           n[0] = blk_ok[0] ? l2add2(a[0], pm) + eb : FSW_NEG;
           n[1] = l2add3(a[1], a[0], pm) + em[0];
 #pragma unroll
@@ -774,9 +790,12 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
             n[2 * i + 1] = l2add3(a[2 * i + 1], a[2 * i], a[2 * i - 1]) + em[i];
           }
         } else {
-          float nx0 = __shfl_down_sync(0xffffffffu, a[0], 1);            // states SPL*(L+1), SPL*(L+1) + 1
+          float nx0 = __shfl_down_sync(0xffffffffu, a[0], 1);            // states SPL*(gl+1), SPL*(gl+1) + 1
           float nx1 = __shfl_down_sync(0xffffffffu, a[1], 1);
-          if (lane == 31) { nx0 = FSW_NEG; nx1 = FSW_NEG; }
+          if (lane == 31) {
+            nx0 = wc + 1 < W ? mbox[1][rs][wc + 1][0] : FSW_NEG;
+            nx1 = wc + 1 < W ? mbox[1][rs][wc + 1][1] : FSW_NEG;
+          }
 #pragma unroll
           for (int i = 0; i < TPL - 1; ++i) {
             n[2 * i] = blk_ok[i] ? l2add2(a[2 * i], a[2 * i + 1]) + eb : FSW_NEG;
@@ -785,11 +804,15 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
           n[SPL - 2] = blk_ok[TPL - 1] ? l2add2(a[SPL - 2], a[SPL - 1]) + eb : FSW_NEG;
           n[SPL - 1] = l2add3(a[SPL - 1], nx0, nx1) + em[TPL - 1];
         }
+        // impossible states drift below the sentinel by one sentinel per step at most (-1e30 * T: far from the fp32 range)
 #pragma unroll
-        for (int j = 0; j < SPL; ++j) a[j] = fmaxf(n[j], FSW_NEG);      // impossible states stay at the sentinel
+        for (int j = 0; j < SPL; ++j) a[j] = n[j];
+        if (!is_beta && lane == 31) mbox[0][wsl][wc][0] = a[SPL - 1];
+        if (is_beta && lane == 0) { mbox[1][wsl][wc][0] = a[0]; mbox[1][wsl][wc][1] = a[1]; }
 #pragma unroll
         for (int i = 0; i < TPL; ++i)
-          if (tok_ok[i]) ws[static_cast<long long>(f) * Tx + k0 + i] = a[2 * i + 1] > 0.5f * FSW_NEG ? a[2 * i + 1] * FSW_LN2 : -INFINITY;
+          if (tok_ok[i]) ws[static_cast<long long>(f) * Tx + k0 + i] = a[2 * i + 1];    // log2 units; impossible <= FSW_NEG
+        chain_barrier();
       }
     }
 #pragma unroll
@@ -800,22 +823,41 @@ forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restri
     }
   }
   if (!is_beta) {   // log-likelihood = log(alpha_{T-1}(S-1) + alpha_{T-1}(S-2))
-    float v1 = FSW_NEG, v2 = FSW_NEG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
-      const int s = SPL * lane + j;
-      if (s == S - 1) v1 = a[j];
-      if (s == S - 2) v2 = a[j];
+      const int s_ = SPL * gl + j;
+      if (s_ == S - 1) fin[0] = a[j];
+      if (s_ == S - 2) fin[1] = a[j];
     }
-    v1 = warp_max(v1);
-    v2 = warp_max(v2);
-    if (lane == 0) {
-      const float ll = l2add2(v1, v2) * FSW_LN2;
+    chain_barrier();
+    if (gl == 0) {
+      const float ll = l2add2(fin[0], S >= 2 ? fin[1] : FSW_NEG) * FSW_LN2;
       const bool finite = ll > 0.5f * FSW_NEG && ll < INFINITY;
       loss[b] = finite ? -ll / static_cast<float>(N) : 0.f;   // reduction='mean' (target length), zero_infinity
       nll_ws[b] = finite ? -ll : INFINITY;
     }
   }
+}
+
+// gradient for the log2-domain workspaces of the warp kernel: posterior = exp((aw + bw) ln 2 - e + nll), 0 for impossible states
+__global__ void fs_grad_log2_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
+                                    const float* __restrict__ lse_ws, const float* __restrict__ aw, const float* __restrict__ bw,
+                                    const float* __restrict__ nll_ws, float* __restrict__ grad, int B, int Tm, int Tx) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Tm * Tx) return;
+  const int n = static_cast<int>(idx % Tx);
+  const long long row = idx / Tx;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  float g = 0.f;
+  const float nll = nll_ws[b];
+  if (t < T && n < N && nll < INFINITY) {
+    const float e = lpa[idx] - lse_ws[row];
+    const float av = aw[idx], bv = bw[idx];
+    const float post = (av > 0.5f * FSW_NEG && bv > 0.5f * FSW_NEG) ? expf((av + bv) * FSW_LN2 - e + nll) : 0.f;
+    g = (expf(e) - post) / (static_cast<float>(N) * static_cast<float>(B));
+  }
+  grad[idx] = g;
 }
 
 // gradient, fully parallel over (b, t, n): softmax minus posterior occupancy, with the per-sample 1/N and the batch 1/B
@@ -870,11 +912,11 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   osb::fs_lse_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, B, Tm, Tx);
   // warp-synchronous register recursion when the 2 Tx + 1 states fit 32 lanes x SPL registers; else the shared-memory kernel
   const int S_max = 2 * Tx + 1;
-  if (S_max <= 32 * 26 && !g_fs_force_legacy) {
-    if (S_max <= 32 * 8) osb::forward_sum_warp_kernel<8><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    else if (S_max <= 32 * 14) osb::forward_sum_warp_kernel<14><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    else osb::forward_sum_warp_kernel<26><<<B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    osb::fs_grad_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
+  if (S_max <= 1024 && !g_fs_force_legacy) {
+    if (S_max <= 256) osb::forward_sum_warp_kernel<4, 2><<<B, 128, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    else if (S_max <= 512) osb::forward_sum_warp_kernel<4, 4><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    else osb::forward_sum_warp_kernel<8, 4><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    osb::fs_grad_log2_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
     osb::count_launch(3);
     return osb::launch_status();
   }

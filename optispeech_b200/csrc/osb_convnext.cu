@@ -24,7 +24,8 @@ namespace {
 constexpr int FB_M = 128;      // rows per CTA
 constexpr int FB_NC = 64;      // intermediate columns per chunk (= one 128-byte swizzle row of fp16)
 constexpr int FB_WORKERS = 8;  // worker warps (prologue + epilogues)
-constexpr int FB_THREADS = 64 + FB_WORKERS * 32;
+constexpr int FB_CTRL = 3;      // control warps: TMA producer, pwconv1 MMA issuer, pwconv2 MMA issuer
+constexpr int FB_THREADS = FB_CTRL * 32 + FB_WORKERS * 32;
 
 struct FusedParams {
   const float* x;        // (B, T, C) fp32 residual stream
@@ -66,6 +67,17 @@ struct FusedCfg {
   static constexpr int N2 = C <= 256 ? C : C / 2;          // N of one pwconv2 MMA
   static constexpr int N2_PARTS = C / N2;
   static constexpr uint32_t ACC1_COL = C;                  // TMEM: [0, C) pwconv2 accumulator, then 2 x 64 for pwconv1
+  // prologue input staging: the (rows + 6 halo) x C fp32 input tile is brought in by TMA as C/32 boxes of [rows x 128 B]
+  // (128B swizzle, zero fill outside [0, T) = the convolution's zero padding) into the weight / GELU buffers, which are idle
+  // until the prologue is done; C = 384 takes two passes of 64 rows
+  static constexpr int NXB = C / 32;
+  static constexpr int NPASS = C <= 256 ? 1 : 2;
+  static constexpr int RP = FB_M / NPASS;                  // output rows per pass
+  static constexpr int XR = RP + 6;                        // staged input rows per pass
+  static constexpr int XB_STRIDE = (XR * 128 + 1023) / 1024 * 1024;
+  static constexpr int X_BYTES = NXB * XB_STRIDE;
+  static constexpr int TAP_BYTES = 8 * C * 4;              // 7 taps + bias, tap-major
+  static_assert(X_BYTES + TAP_BYTES <= WS * (W1_BYTES + W2_BYTES) + 2 * H_BYTES, "input tile must fit the idle buffers");
 };
 
 // 16-byte chunk `c16` (0..7) of row `r` inside a [rows x 128 B] tile with the 128-byte swizzle
@@ -73,7 +85,8 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) { return static
 
 template <int C, int I, bool kTrain>
 __global__ void __launch_bounds__(FB_THREADS, 1)
-convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FusedParams p) {
+convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                      const FusedParams p) {
   using Cfg = FusedCfg<C>;
   constexpr int NCH = I / FB_NC;
   constexpr int VPL = C / 128;
@@ -84,6 +97,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   uint8_t* sW1 = sA + Cfg::A_BYTES;                 // [WS]
   uint8_t* sW2 = sW1 + WS * Cfg::W1_BYTES;          // [WS]
   uint8_t* sH = sW2 + WS * Cfg::W2_BYTES;           // [2]
+  uint8_t* sX = sW1;                                // prologue only: staged input tile, then the taps
   uint64_t* bars = reinterpret_cast<uint64_t*>(sH + 2 * Cfg::H_BYTES);
   uint64_t* w1_full = bars + 0;     // [2]
   uint64_t* w1_empty = bars + 2;    // [2]
@@ -95,7 +109,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   uint64_t* h_empty = bars + 14;    // [2]
   uint64_t* a_ready = bars + 16;
   uint64_t* acc2_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* x_full = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +125,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1);
       mbar_init(&acc1_full[i], 1);
@@ -119,6 +135,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     }
     mbar_init(a_ready, FB_WORKERS);
     mbar_init(acc2_full, 1);
+    mbar_init(x_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -128,8 +145,12 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer: weight chunks =====================
+    // ===================== TMA producer: input tile (pass 0), then the weight chunks =====================
     if (lane == 0) {
+      mbar_expect_tx(x_full, Cfg::NXB * Cfg::XR * 128);
+#pragma unroll
+      for (int i = 0; i < Cfg::NXB; ++i) tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, t0 - 3, b);
+      mbar_wait(a_ready, 0);   // the weight ring overlays the staged input tile: the prologue has to be done with it
       for (int j = 0; j < n_ch; ++j) {
         const int st = j % WS;
         const uint32_t ph = (j / WS) & 1;
@@ -149,168 +170,154 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the loop with uniform control flow (operands stay in uniform registers); one elected lane
-    // issues tcgen05.mma / tcgen05.commit.
-    {
-      constexpr uint32_t idesc1 = make_instr_desc(OSB_F16, FB_M, FB_NC, 0, 0);
-      constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, FB_M, Cfg::N2, 0, 0);
-      const uint32_t a_addr = smem_u32(sA), w1_addr = smem_u32(sW1), w2_addr = smem_u32(sW2), h_addr = smem_u32(sH);
-      // Descriptors are loop invariant up to a byte offset: build them once and advance the 14-bit start-address field
-      // (units of 16 B) with one integer add per MMA — the single issuing thread is latency bound on its scalar stream.
-      const uint64_t dA0 = make_smem_desc_sw128(a_addr, 16, 1024);
-      const uint64_t dW10 = make_smem_desc_sw128(w1_addr, 16, 1024);
-      const uint64_t dW20 = make_smem_desc_sw128(w2_addr, 16, 1024);
-      const uint64_t dH0 = make_smem_desc_sw128(h_addr, 16, 1024);
-      if (lane == 0) FB_TRACE(1, 0);
-      mbar_wait(a_ready, 0);
-      if (lane == 0) FB_TRACE(1, 1);
+    // ===================== MMA issuer 1: pwconv1 of every chunk -> acc1[j & 1] =====================
+    // Two issuing warps: with a single one, pwconv1 of chunk j+1 queued behind the wait for the GELU of chunk j-1 (the
+    // operand of pwconv2), and the ~60 cycles of scalar work per tcgen05.mma made the issuing thread itself the bound
+    // (clock64 timeline, round 2).  The whole warp walks the loop with uniform control flow; one elected lane issues.
+    constexpr uint32_t idesc1 = make_instr_desc(OSB_F16, FB_M, FB_NC, 0, 0);
+    const uint64_t dA0 = make_smem_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t dW10 = make_smem_desc_sw128(smem_u32(sW1), 16, 1024);
+    if (lane == 0) FB_TRACE(1, 0);
+    mbar_wait(a_ready, 0);
+    if (lane == 0) FB_TRACE(1, 1);
+    tc_fence_after_sync();
+    for (int j = 0; j < n_ch; ++j) {
+      const int buf = j & 1;
+      const int st = j % WS;
+      mbar_wait(&w1_full[st], (j / WS) & 1);
+      if (lane == 0) FB_TRACE(1, 2 + 6 * j);
+      mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
+      if (lane == 0) FB_TRACE(1, 3 + 6 * j);
       tc_fence_after_sync();
-      for (int j = 0; j <= n_ch; ++j) {
-        if (j < n_ch) {  // pwconv1 of chunk j -> acc1[j & 1]
-          const int buf = j & 1;
-          const int st = j % WS;
-          mbar_wait(&w1_full[st], (j / WS) & 1);
-          if (lane == 0) FB_TRACE(1, 2 + 6 * j);
-          mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
-          if (lane == 0) FB_TRACE(1, 3 + 6 * j);
-          tc_fence_after_sync();
-          const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * FB_NC;
-          if (elect_one()) {
+      const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * FB_NC;
+      if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < Cfg::KB; ++kb)
+        for (int kb = 0; kb < Cfg::KB; ++kb)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = dA0 + static_cast<uint64_t>((kb * (FB_M * 128) + k * 32) >> 4);
-                const uint64_t db = dW10 + static_cast<uint64_t>((st * Cfg::W1_BYTES + kb * (FB_NC * 128) + k * 32) >> 4);
-                umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
-              }
-            umma_commit(&w1_empty[st]);
-            umma_commit(&acc1_full[buf]);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = dA0 + static_cast<uint64_t>((kb * (FB_M * 128) + k * 32) >> 4);
+            const uint64_t db = dW10 + static_cast<uint64_t>((st * Cfg::W1_BYTES + kb * (FB_NC * 128) + k * 32) >> 4);
+            umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
           }
-          __syncwarp();
-          if (lane == 0) FB_TRACE(1, 4 + 6 * j);
-        }
-        if (j >= 1) {   // pwconv2 of chunk j-1: acc2 += gelu_chunk . W2[:, chunk]^T
-          const int jj = j - 1, buf = jj & 1;
-          const int st = jj % WS;
-          mbar_wait(&w2_full[st], (jj / WS) & 1);
-          if (lane == 0) FB_TRACE(1, 5 + 6 * jj);
-          mbar_wait(&h_full[buf], (jj >> 1) & 1);
-          if (lane == 0) FB_TRACE(1, 6 + 6 * jj);
-          tc_fence_after_sync();
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = dH0 + static_cast<uint64_t>((buf * Cfg::H_BYTES + k * 32) >> 4);
-#pragma unroll
-              for (int part = 0; part < Cfg::N2_PARTS; ++part) {
-                const uint64_t db = dW20 + static_cast<uint64_t>((st * Cfg::W2_BYTES + part * (Cfg::N2 * 128) + k * 32) >> 4);
-                umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
-              }
-            }
-            umma_commit(&w2_empty[st]);
-            umma_commit(&h_empty[buf]);
-          }
-          __syncwarp();
-          if (lane == 0) FB_TRACE(1, 7 + 6 * jj);
-        }
+        umma_commit(&w1_empty[st]);
+        umma_commit(&acc1_full[buf]);
       }
-      if (elect_one()) umma_commit(acc2_full);
       __syncwarp();
+      if (lane == 0) FB_TRACE(1, 4 + 6 * j);
     }
+  } else if (warp == 2) {
+    // ===================== MMA issuer 2: pwconv2, acc2 += gelu_chunk . W2[:, chunk]^T =====================
+    constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, FB_M, Cfg::N2, 0, 0);
+    const uint64_t dW20 = make_smem_desc_sw128(smem_u32(sW2), 16, 1024);
+    const uint64_t dH0 = make_smem_desc_sw128(smem_u32(sH), 16, 1024);
+    for (int jj = 0; jj < n_ch; ++jj) {
+      const int buf = jj & 1;
+      const int st = jj % WS;
+      mbar_wait(&w2_full[st], (jj / WS) & 1);
+      if (lane == 0) FB_TRACE(1, 5 + 6 * jj);
+      mbar_wait(&h_full[buf], (jj >> 1) & 1);
+      if (lane == 0) FB_TRACE(1, 6 + 6 * jj);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = dH0 + static_cast<uint64_t>((buf * Cfg::H_BYTES + k * 32) >> 4);
+#pragma unroll
+          for (int part = 0; part < Cfg::N2_PARTS; ++part) {
+            const uint64_t db = dW20 + static_cast<uint64_t>((st * Cfg::W2_BYTES + part * (Cfg::N2 * 128) + k * 32) >> 4);
+            umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&w2_empty[st]);
+        umma_commit(&h_empty[buf]);
+      }
+      __syncwarp();
+      if (lane == 0) FB_TRACE(1, 7 + 6 * jj);
+    }
+    if (elect_one()) umma_commit(acc2_full);
+    __syncwarp();
   } else {
     // ===================== worker warps =====================
-    const int ww = warp - 2;          // 0..7
+    const int ww = warp - FB_CTRL;    // 0..7
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (ww >> 2);       // which 32-column half of a 64-column chunk / which half of C in the last epilogue
-    // ---- prologue: dwconv7 + LayerNorm statistics -> fp16 xhat in swizzled smem (rows ww*16 .. +16) ----
+    // ---- prologue: dwconv7 + LayerNorm statistics -> fp16 xhat in swizzled smem ----
     {
-      // With ~224 KB of shared memory carved out, L1D is only a few KB: the 7 x C filter taps would be re-fetched from L2 for
-      // every row.  The GELU staging buffers are idle until the first chunk, so the taps (tap-major) and the bias live there.
-      float* s_dw = reinterpret_cast<float*>(sH);          // [7][C]
-      float* s_db = s_dw + 7 * C;                          // [C]
-      const int wt = threadIdx.x - 64;                     // 0 .. 255
+      float* s_dw = reinterpret_cast<float*>(sX + Cfg::X_BYTES);   // [7][C] taps (tap-major), then [C] bias
+      float* s_db = s_dw + 7 * C;
+      const int wt = threadIdx.x - FB_CTRL * 32;                    // 0 .. 255
       for (int i = wt; i < 7 * C; i += FB_WORKERS * 32) s_dw[(i % 7) * C + i / 7] = p.dw_w[i];
       for (int i = wt; i < C; i += FB_WORKERS * 32) s_db[i] = p.dw_b[i];
       asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");   // worker warps only
-      const float* xb = p.x + static_cast<long long>(b) * p.T * C;
-      float4 win[7][VPL];
-      auto load_row = [&](int t, float4 (&dst)[VPL]) {
-        if (t >= 0 && t < p.T) {
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) dst[v] = *reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * C + v * 128 + lane * 4);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      const int r_begin = ww * 16;
-#pragma unroll
-      for (int jx = 0; jx < 6; ++jx) load_row(t0 + r_begin + jx - 3, win[jx + 1]);
-      // rows are requested two iterations before they are needed (the loop is otherwise one DRAM latency per row)
-      float4 q0[VPL], q1[VPL];
-      load_row(t0 + r_begin + 3, q0);
-      load_row(t0 + r_begin + 4, q1);
+      // this lane's 4 channels of every 128-channel group v live in box v*4 + lane/8, 16-byte chunk lane%8 of the box row
+      const int xbox = lane >> 3, xchunk = lane & 7;
+      constexpr int ROWS_PER_WARP = Cfg::RP / FB_WORKERS;
 #pragma unroll 1
-      for (int r = r_begin; r < r_begin + 16; ++r) {
-        const int t = t0 + r;
+      for (int pass = 0; pass < Cfg::NPASS; ++pass) {
+        if (pass > 0) {   // the next 64 rows: every worker is done with the previous pass's tile
+          asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");
+          if (ww == 0 && lane == 0) {
+            mbar_expect_tx(x_full, Cfg::NXB * Cfg::XR * 128);
 #pragma unroll
-        for (int jx = 0; jx < 6; ++jx)
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) win[jx][v] = win[jx + 1][v];
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) { win[6][v] = q0[v]; q0[v] = q1[v]; }
-        if (r + 2 < r_begin + 16) load_row(t + 5, q1);
-        float4 d[VPL];
-        float s = 0.f;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = v * 128 + lane * 4;
-          float4 acc = *reinterpret_cast<const float4*>(s_db + c);
-#pragma unroll
-          for (int jx = 0; jx < 7; ++jx) {
-            const float4 wj = *reinterpret_cast<const float4*>(s_dw + jx * C + c);
-            acc.x = fmaf(wj.x, win[jx][v].x, acc.x);
-            acc.y = fmaf(wj.y, win[jx][v].y, acc.y);
-            acc.z = fmaf(wj.z, win[jx][v].z, acc.z);
-            acc.w = fmaf(wj.w, win[jx][v].w, acc.w);
+            for (int i = 0; i < Cfg::NXB; ++i) tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, t0 + pass * Cfg::RP - 3, b);
           }
-          d[v] = acc;
-          s += (acc.x + acc.y) + (acc.z + acc.w);
         }
-        const float mean = warp_sum(s) * (1.f / C);
-        float qv = 0.f;
+        mbar_wait(x_full, pass & 1);
+#pragma unroll 2
+        for (int rl = ww * ROWS_PER_WARP; rl < (ww + 1) * ROWS_PER_WARP; ++rl) {   // rl: row inside the pass; staged rows rl .. rl+6
+          const int r = pass * Cfg::RP + rl;
+          const int t = t0 + r;
+          float4 d[VPL];
+          float s = 0.f;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
-          qv += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
-        }
-        const float rstd = (t < p.T) ? rsqrtf(warp_sum(qv) * (1.f / C) + p.eps) : 0.f;
+          for (int v = 0; v < VPL; ++v) {
+            const int c = v * 128 + lane * 4;
+            const uint8_t* xb = sX + (v * 4 + xbox) * Cfg::XB_STRIDE;
+            float4 acc = *reinterpret_cast<const float4*>(s_db + c);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = v * 128 + lane * 4;
-          const int kb = c >> 6, cc = c & 63;
-          __half2 h0 = __floats2half2_rn(d[v].x * rstd, d[v].y * rstd);
-          __half2 h1 = __floats2half2_rn(d[v].z * rstd, d[v].w * rstd);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(sA + kb * (FB_M * 128) + sw128_offset(r, cc >> 3) + (cc & 7) * 2) = u;
+            for (int jx = 0; jx < 7; ++jx) {
+              const int rr = rl + jx;
+              const float4 xv = *reinterpret_cast<const float4*>(xb + rr * 128 + ((xchunk ^ (rr & 7)) << 4));
+              const float4 wj = *reinterpret_cast<const float4*>(s_dw + jx * C + c);
+              acc.x = fmaf(wj.x, xv.x, acc.x);
+              acc.y = fmaf(wj.y, xv.y, acc.y);
+              acc.z = fmaf(wj.z, xv.z, acc.z);
+              acc.w = fmaf(wj.w, xv.w, acc.w);
+            }
+            d[v] = acc;
+            s += (acc.x + acc.y) + (acc.z + acc.w);
+          }
+          const float mean = warp_sum(s) * (1.f / C);
+          float qv = 0.f;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
+            qv += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
+          }
+          const float rstd = (t < p.T) ? rsqrtf(warp_sum(qv) * (1.f / C) + p.eps) : 0.f;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int c = v * 128 + lane * 4;
+            const int kb = c >> 6, cc = c & 63;
+            __half2 h0 = __floats2half2_rn(d[v].x * rstd, d[v].y * rstd);
+            __half2 h1 = __floats2half2_rn(d[v].z * rstd, d[v].w * rstd);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(sA + kb * (FB_M * 128) + sw128_offset(r, cc >> 3) + (cc & 7) * 2) = u;
+            if constexpr (kTrain) {
+              if (split == 0 && t < p.T) *reinterpret_cast<uint2*>(p.xhat_out + (static_cast<long long>(b) * p.T + t) * C + c) = u;
+            }
+          }
           if constexpr (kTrain) {
-            if (split == 0 && t < p.T) *reinterpret_cast<uint2*>(p.xhat_out + (static_cast<long long>(b) * p.T + t) * C + c) = u;
+            if (split == 0 && t < p.T && lane == 0) p.rstd_out[static_cast<long long>(b) * p.T + t] = rstd;
           }
-        }
-        if constexpr (kTrain) {
-          if (split == 0 && t < p.T && lane == 0) p.rstd_out[static_cast<long long>(b) * p.T + t] = rstd;
         }
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
       if (ww == 0 && lane == 0) FB_TRACE(2, 0);
-      // all workers must be done with the filter taps before the first GELU chunk overwrites the staging buffer
-      asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");
     }
     // ---- per chunk: acc1 -> +bias -> GELU -> fp16 -> swizzled smem (A operand of pwconv2) ----
     const int row = q * 32 + lane;
@@ -388,6 +395,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     }
     // ---- final epilogue: bias, layer scale, DropPath -> fp32 tile staged in shared memory (all MMA operands are dead
     //      now), then residual add + pad mask with fully coalesced row-wise global reads / writes ----
+    // the residual rows of this warp are requested before the accumulator is awaited (their latency hides behind the tail)
+    constexpr int EPR = FB_M / FB_WORKERS;    // rows per warp in the coalesced pass: r = ww + FB_WORKERS * i
     mbar_wait(acc2_full, 0);
     if (ww == 0 && lane == 0) FB_TRACE(2, 200);
     tc_fence_after_sync();
@@ -414,30 +423,48 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");   // worker warps only
-    for (int r = ww; r < FB_M; r += FB_WORKERS) {          // one warp per row: 512-byte coalesced accesses
-      const int t = t0 + r;
-      if (t >= p.T) break;
-      const long long grow = static_cast<long long>(b) * p.T + t;
-      const float keep = (p.pad_mask != nullptr && p.pad_mask[grow]) ? 0.f : 1.f;
+    constexpr int EB = 4;                                    // rows in flight per warp (independent 512-byte loads)
+#pragma unroll 1
+    for (int i0 = 0; i0 < EPR; i0 += EB) {                   // one warp per row: 512-byte coalesced accesses
+      float4 x4[EB][VPL];
+      float keep[EB];
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = v * 128 + lane * 4;
-        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (split == 0) x4 = *reinterpret_cast<const float4*>(p.x + grow * C + c);   // so does the residual
-        const float4 d4 = *reinterpret_cast<const float4*>(stile + r * OLD + c);
-        float4 o;
-        o.x = (x4.x + d4.x) * keep; o.y = (x4.y + d4.y) * keep; o.z = (x4.z + d4.z) * keep; o.w = (x4.w + d4.w) * keep;
-        if (p.nsplit == 1) {
-          *reinterpret_cast<float4*>(p.out + grow * C + c) = o;
-        } else {  // partial sums of the splits meet in L2: one 16-byte vector reduction per thread, 512 B per warp
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + grow * C + c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                       : "memory");
+      for (int e = 0; e < EB; ++e) {
+        const int r = ww + FB_WORKERS * (i0 + e);
+        const int t = t0 + r;
+        const long long grow = static_cast<long long>(b) * p.T + t;
+        keep[e] = (t < p.T && !(p.pad_mask != nullptr && p.pad_mask[grow])) ? 1.f : 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          x4[e][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (split == 0 && t < p.T) x4[e][v] = *reinterpret_cast<const float4*>(p.x + grow * C + v * 128 + lane * 4);   // so does the residual
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EB; ++e) {
+        const int r = ww + FB_WORKERS * (i0 + e);
+        const int t = t0 + r;
+        if (t >= p.T) continue;
+        const long long grow = static_cast<long long>(b) * p.T + t;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          const float4 d4 = *reinterpret_cast<const float4*>(stile + r * OLD + c);
+          float4 o;
+          o.x = (x4[e][v].x + d4.x) * keep[e]; o.y = (x4[e][v].y + d4.y) * keep[e];
+          o.z = (x4[e][v].z + d4.z) * keep[e]; o.w = (x4[e][v].w + d4.w) * keep[e];
+          if (p.nsplit == 1) {
+            *reinterpret_cast<float4*>(p.out + grow * C + c) = o;
+          } else {  // partial sums of the splits meet in L2: one 16-byte vector reduction per thread, 512 B per warp
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + grow * C + c), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
         }
       }
     }
   }
 
-  if (threadIdx.x == 64) FB_TRACE(2, 201);
+  if (threadIdx.x == FB_CTRL * 32) FB_TRACE(2, 201);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
@@ -452,6 +479,10 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
   if (rc != OSB_OK) return rc;
   rc = make_tmap_3d(&tmW2, w2_h16, TMA_F16, I, C, 1, I, static_cast<uint64_t>(C) * I, 64, Cfg::N2);
   if (rc != OSB_OK) return rc;
+  // input (B, T, C) fp32: boxes of 32 channels (128 B) x XR rows; rows outside [0, T) read as zero (Conv1d zero padding)
+  CUtensorMap tmX;
+  rc = make_tmap_3d(&tmX, p.x, TMA_F32, C, p.T, p.B, C, static_cast<uint64_t>(p.T) * C, 32, Cfg::XR);
+  if (rc != OSB_OK) return rc;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(convnext_fused_kernel<C, I, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -462,7 +493,7 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
     cudaError_t e = cudaMemsetAsync(p.out, 0, static_cast<size_t>(p.B) * p.T * C * sizeof(float), stream);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  convnext_fused_kernel<C, I, kTrain><<<dim3(p.B * p.m_tiles, p.nsplit), FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, p);
+  convnext_fused_kernel<C, I, kTrain><<<dim3(p.B * p.m_tiles, p.nsplit), FB_THREADS, Cfg::SMEM, stream>>>(tmW1, tmW2, tmX, p);
   count_launch();
   return launch_status();
 }
@@ -491,12 +522,14 @@ static int fused_fwd_impl(const float* x, const float* dw_w, const float* dw_b, 
   p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps; p.I = I;
   p.xhat_out = static_cast<__half*>(xhat_out); p.rstd_out = rstd_out; p.pre_out = static_cast<__half*>(pre_out);
   p.h_out = static_cast<__half*>(h_out);
-  // Fewer row tiles than half the SMs: split the intermediate dimension so that the weight streaming (the per-CTA bound: every
-  // CTA walks all I/64 chunks) is spread over the machine; each split keeps at least two chunks.
+  // Few row tiles: split the intermediate dimension over blockIdx.y so that more SMs share the chunk loop — but no further
+  // than ~100 CTAs and 4 splits: beyond that the prologue (replicated per split) and the L2 reductions cost more than the
+  // shorter loops save (measured: 48 tiles: 2 splits 42 us, 3 splits 66 us; 16 tiles: 4 splits = 9 splits), and the SMs left
+  // free run the other branches of the step.
   {
     const int tiles = B * p.m_tiles;
     const int nch = I / FB_NC;
-    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles * 2 <= 148 ? 148 / tiles : 1);
+    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles >= 100 ? 1 : (100 / tiles > 4 ? 4 : 100 / tiles));
     if (ns > nch / 2) ns = nch / 2;
     p.nsplit = ns < 1 ? 1 : ns;
   }

@@ -28,7 +28,8 @@ namespace {
 constexpr int BB_M = 128;      // rows per CTA
 constexpr int BB_NC = 64;      // intermediate columns per chunk
 constexpr int BB_WORKERS = 8;
-constexpr int BB_THREADS = 64 + BB_WORKERS * 32;
+constexpr int BB_CTRL = 3;      // control warps: TMA producer, GEMM 1 issuer, GEMM 2 issuer
+constexpr int BB_THREADS = BB_CTRL * 32 + BB_WORKERS * 32;
 
 struct BwdParams {
   const float* dout;        // (B, T, C) fp32 gradient of the block output (carries the static loss scale)
@@ -136,66 +137,67 @@ convnext_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer 1: dG chunk = dyg (128 x C) . W2[:, chunk]  (K = C) -> acc1[j & 1] =====================
+    // (two issuing warps, as in the forward kernel: GEMM 1 of chunk j+1 does not queue behind the wait for dH of chunk j-1)
     constexpr uint32_t idesc1 = make_instr_desc(OSB_F16, BB_M, BB_NC, 0, 1);
-    constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, BB_M, Cfg::N2, 0, 1);
     const uint64_t dA0 = make_smem_desc_sw128(smem_u32(sA), 16, 1024);
-    const uint64_t dH0 = make_smem_desc_sw128(smem_u32(sH), 16, 1024);
     // MN-major B: 64-column chunks are 64 * 128 B apart (LBO), 8-row groups 1024 B apart (SBO)
     const uint64_t dWA0 = make_smem_desc_sw128(smem_u32(sWA), 64 * 128, 1024);
-    const uint64_t dWB0 = make_smem_desc_sw128(smem_u32(sWB), 64 * 128, 1024);
     mbar_wait(a_ready, 0);
     tc_fence_after_sync();
-    for (int j = 0; j <= n_ch; ++j) {
-      if (j < n_ch) {  // GEMM 1 of chunk j: acc1[j & 1] = dyg (128 x C) . W2[:, chunk]  (K = C)
-        const int buf = j & 1;
-        const int st = j % WS;
-        mbar_wait(&wa_full[st], (j / WS) & 1);
-        mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * BB_NC;
-        if (elect_one()) {
+    for (int j = 0; j < n_ch; ++j) {
+      const int buf = j & 1;
+      const int st = j % WS;
+      mbar_wait(&wa_full[st], (j / WS) & 1);
+      mbar_wait(&acc1_empty[buf], ((j >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d = tmem_base + Cfg::ACC1_COL + buf * BB_NC;
+      if (elect_one()) {
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = dA0 + static_cast<uint64_t>((kb * (BB_M * 128) + k * 32) >> 4);
-              // 16 contraction rows per MMA = 2048 B inside the k-block's [64 rows x 128 B] box
-              const uint64_t db = dWA0 + static_cast<uint64_t>((st * Cfg::WA_BYTES + kb * (64 * 128) + k * (16 * 128)) >> 4);
-              umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
-            }
-          umma_commit(&wa_empty[st]);
-          umma_commit(&acc1_full[buf]);
-        }
-        __syncwarp();
-      }
-      if (j >= 1) {   // GEMM 2 of chunk j-1: acc2 += dH chunk (128 x 64) . W1f[chunk, :]  (K = 64)
-        const int jj = j - 1, buf = jj & 1;
-        const int st = jj % WS;
-        mbar_wait(&wb_full[st], (jj / WS) & 1);
-        mbar_wait(&h_full[buf], (jj >> 1) & 1);
-        tc_fence_after_sync();
-        if (elect_one()) {
+        for (int kb = 0; kb < Cfg::KB; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = dH0 + static_cast<uint64_t>((buf * Cfg::H_BYTES + k * 32) >> 4);
-#pragma unroll
-            for (int part = 0; part < Cfg::N2_PARTS; ++part) {
-              const uint64_t db = dWB0 + static_cast<uint64_t>((st * Cfg::WB_BYTES + part * (Cfg::N2 / 64) * (64 * 128) + k * (16 * 128)) >> 4);
-              umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
-            }
+            const uint64_t da = dA0 + static_cast<uint64_t>((kb * (BB_M * 128) + k * 32) >> 4);
+            // 16 contraction rows per MMA = 2048 B inside the k-block's [64 rows x 128 B] box
+            const uint64_t db = dWA0 + static_cast<uint64_t>((st * Cfg::WA_BYTES + kb * (64 * 128) + k * (16 * 128)) >> 4);
+            umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&wb_empty[st]);
-          umma_commit(&h_empty[buf]);
-        }
-        __syncwarp();
+        umma_commit(&wa_empty[st]);
+        umma_commit(&acc1_full[buf]);
       }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer 2: acc2 += dH chunk (128 x 64) . W1f[chunk, :]  (K = 64) =====================
+    constexpr uint32_t idesc2 = make_instr_desc(OSB_F16, BB_M, Cfg::N2, 0, 1);
+    const uint64_t dH0 = make_smem_desc_sw128(smem_u32(sH), 16, 1024);
+    const uint64_t dWB0 = make_smem_desc_sw128(smem_u32(sWB), 64 * 128, 1024);
+    for (int jj = 0; jj < n_ch; ++jj) {
+      const int buf = jj & 1;
+      const int st = jj % WS;
+      mbar_wait(&wb_full[st], (jj / WS) & 1);
+      mbar_wait(&h_full[buf], (jj >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = dH0 + static_cast<uint64_t>((buf * Cfg::H_BYTES + k * 32) >> 4);
+#pragma unroll
+          for (int part = 0; part < Cfg::N2_PARTS; ++part) {
+            const uint64_t db = dWB0 + static_cast<uint64_t>((st * Cfg::WB_BYTES + part * (Cfg::N2 / 64) * (64 * 128) + k * (16 * 128)) >> 4);
+            umma_ss<false>(tmem_base + part * Cfg::N2, da, db, idesc2, (jj | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&wb_empty[st]);
+        umma_commit(&h_empty[buf]);
+      }
+      __syncwarp();
     }
     if (elect_one()) umma_commit(acc2_full);
     __syncwarp();
   } else {
     // ===================== worker warps =====================
-    const int ww = warp - 2;          // 0..7
+    const int ww = warp - BB_CTRL;    // 0..7
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (ww >> 2);       // which 32-column half of a chunk / which half of C in the last epilogue
     // ---- prologue: dyg = dout * gamma * keep * rs -> fp16, swizzled smem (rows ww*16 .. +16) and HBM ----
@@ -363,28 +365,27 @@ int launch_bwd(const void* w2_h16, const void* w1f_h16, const BwdParams& p, cuda
 // A warp owns a run of RUN consecutive positions of one sequence (lanes own 4 channels per 128-channel group) and slides a
 // 7-row register window of dd over it; the 6 halo rows of dd are recomputed by the neighbouring runs.
 // ------------------------------------------------------------------------------------------
-constexpr int LDB_RUN = 16;
-constexpr int LDB_WARPS = 4;
+constexpr int LDB_TT = 32;              // positions per tile
+constexpr int LDB_HR = LDB_TT + 6;      // staged rows of dd (3 halo rows each side)
+constexpr int LDB_WARPS = 8;
 
+// A block owns tiles of LDB_TT consecutive positions of one sequence (grid-stride over tiles).  Phase 1: the warps compute
+// the LayerNorm backward of the tile's LDB_HR rows (independent rows: all loads of a warp's rows are in flight together)
+// into a shared-memory tile; phase 2: every output row reads its 7 neighbours from that tile.  The 6 halo rows per tile
+// are recomputed by the neighbouring tiles (19 % extra LayerNorm work, no dd round trip through HBM).  Parameter gradients
+// are accumulated in registers over all tiles of the block and flushed once: (8, C) fp32, rows 0-6 = taps, row 7 = bias.
 template <int VPL>
 __global__ void __launch_bounds__(LDB_WARPS * 32)
 ln_dwconv_bwd_kernel(const float* __restrict__ dxh, const __half* __restrict__ xhat, const float* __restrict__ rstd,
                      const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w /*(C,7)*/,
-                     const uint8_t* __restrict__ pad_mask, float* __restrict__ dx, float* __restrict__ ddw, float* __restrict__ ddb,
-                     int B, int T, int runs_per_seq) {
+                     const uint8_t* __restrict__ pad_mask, float* __restrict__ dx, float* __restrict__ dparam /*(8,C)*/, int B, int T,
+                     int tiles_per_seq, int ntiles) {
   constexpr int C = 128 * VPL;
+  extern __shared__ float ldb_smem[];
+  float* sdd = ldb_smem;                 // [LDB_HR][C]
+  float* stw = sdd + LDB_HR * C;         // [7][C] taps, tap-major
   const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
-  const int run = blockIdx.x * LDB_WARPS + wip;
-  const bool active = run < B * runs_per_seq;
-  const int b = active ? run / runs_per_seq : 0;
-  const int t_begin = active ? (run % runs_per_seq) * LDB_RUN : 0;
-  const int t_end = active ? min(T, t_begin + LDB_RUN) : 0;
-  const long long base = static_cast<long long>(b) * T;
-  __shared__ float s_w[7 * C];          // taps, tap-major: s_w[j * C + c]
-  for (int i = threadIdx.x; i < 7 * C; i += LDB_WARPS * 32) s_w[(i % 7) * C + i / 7] = w[i];
-  __syncthreads();
-
-  float4 win[7][VPL];                    // dd rows t-3 .. t+3 of the current centre t (index j <-> position t + j - 3)
+  for (int i = threadIdx.x; i < 7 * C; i += LDB_WARPS * 32) stw[(i % 7) * C + i / 7] = w[i];
   float4 aw[7][VPL], ab[VPL];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
@@ -392,70 +393,108 @@ ln_dwconv_bwd_kernel(const float* __restrict__ dxh, const __half* __restrict__ x
 #pragma unroll
     for (int j = 0; j < 7; ++j) aw[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  auto dd_row = [&](int t, float4 (&dst)[VPL]) {     // LayerNorm backward of one position (zero outside [0, T))
-    if (t < 0 || t >= T) {
+  __syncthreads();
+  constexpr int RPW = (LDB_HR + LDB_WARPS - 1) / LDB_WARPS;   // dd rows per warp (5)
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_seq;
+    const int tbeg = (tile % tiles_per_seq) * LDB_TT;
+    const long long base = static_cast<long long>(b) * T;
+    // ---- phase 1: dd rows tbeg-3 .. tbeg+LDB_TT+2 -> shared memory ----
+    {
+      float4 g[RPW][VPL];
+      uint2 xh[RPW][VPL];
+      float rs[RPW];
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      return;
-    }
-    float4 g[VPL], xh[VPL];
-    float s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < RPW; ++i) {
+        const int rr = wip + LDB_WARPS * i;
+        const int t = tbeg + rr - 3;
+        const bool ok = rr < LDB_HR && t >= 0 && t < T;
+        rs[i] = ok ? rstd[base + t] : 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int c = v * 128 + lane * 4;
-      g[v] = *reinterpret_cast<const float4*>(dxh + (base + t) * C + c);
-      const uint2 u = *reinterpret_cast<const uint2*>(xhat + (base + t) * C + c);
-      const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-      const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      xh[v] = make_float4(a0.x, a0.y, a1.x, a1.y);
-      s1 += (g[v].x + g[v].y) + (g[v].z + g[v].w);
-      s2 += (g[v].x * xh[v].x + g[v].y * xh[v].y) + (g[v].z * xh[v].z + g[v].w * xh[v].w);
-    }
-    const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
-    const float rs = rstd[base + t];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      dst[v].x = (g[v].x - m1 - xh[v].x * m2) * rs;
-      dst[v].y = (g[v].y - m1 - xh[v].y * m2) * rs;
-      dst[v].z = (g[v].z - m1 - xh[v].z * m2) * rs;
-      dst[v].w = (g[v].w - m1 - xh[v].w * m2) * rs;
-    }
-  };
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) dd_row(t_begin + j - 3, win[j + 1]);
-    for (int t = t_begin; t < t_end; ++t) {
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) win[j][v] = win[j + 1][v];
-      dd_row(t + 3, win[6]);
-      const float keep = (pad_mask != nullptr && pad_mask[base + t]) ? 0.f : 1.f;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int c = v * 128 + lane * 4;
-        const float4 xo = *reinterpret_cast<const float4*>(x + (base + t) * C + c);
-        const float4 go = *reinterpret_cast<const float4*>(dout + (base + t) * C + c);
-        float4 acc = make_float4(go.x * keep, go.y * keep, go.z * keep, go.w * keep);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const float4 wj = *reinterpret_cast<const float4*>(s_w + j * C + c);
-          const float4 d = win[6 - j][v];                  // dd[t - j + 3]
-          acc.x = fmaf(wj.x, d.x, acc.x); acc.y = fmaf(wj.y, d.y, acc.y);
-          acc.z = fmaf(wj.z, d.z, acc.z); acc.w = fmaf(wj.w, d.w, acc.w);
-          aw[j][v].x = fmaf(d.x, xo.x, aw[j][v].x); aw[j][v].y = fmaf(d.y, xo.y, aw[j][v].y);   // ddw[c,j] += dd[u-j+3] x[u]
-          aw[j][v].z = fmaf(d.z, xo.z, aw[j][v].z); aw[j][v].w = fmaf(d.w, xo.w, aw[j][v].w);
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          g[i][v] = ok ? *reinterpret_cast<const float4*>(dxh + (base + t) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xh[i][v] = ok ? *reinterpret_cast<const uint2*>(xhat + (base + t) * C + c) : make_uint2(0u, 0u);
         }
-        *reinterpret_cast<float4*>(dx + (base + t) * C + c) = acc;
-        const float4 dc = win[3][v];
-        ab[v].x += dc.x; ab[v].y += dc.y; ab[v].z += dc.z; ab[v].w += dc.w;
+      }
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int rr = wip + LDB_WARPS * i;
+        if (rr >= LDB_HR) continue;
+        float4 xf[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&xh[i][v].x));
+          const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&xh[i][v].y));
+          xf[v] = make_float4(a0.x, a0.y, a1.x, a1.y);
+          s1 += (g[i][v].x + g[i][v].y) + (g[i][v].z + g[i][v].w);
+          s2 += (g[i][v].x * xf[v].x + g[i][v].y * xf[v].y) + (g[i][v].z * xf[v].z + g[i][v].w * xf[v].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {     // the two row sums travel together
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float m1 = s1 * (1.f / C), m2 = s2 * (1.f / C);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          float4 d;
+          d.x = (g[i][v].x - m1 - xf[v].x * m2) * rs[i];
+          d.y = (g[i][v].y - m1 - xf[v].y * m2) * rs[i];
+          d.z = (g[i][v].z - m1 - xf[v].z * m2) * rs[i];
+          d.w = (g[i][v].w - m1 - xf[v].w * m2) * rs[i];
+          *reinterpret_cast<float4*>(sdd + rr * C + v * 128 + lane * 4) = d;
+        }
       }
     }
+    __syncthreads();
+    // ---- phase 2: dx and the parameter-gradient partial sums; rows wip, wip + 8, ... of the tile ----
+    {
+      constexpr int OPW = LDB_TT / LDB_WARPS;   // output rows per warp (4)
+      float4 xo[OPW][VPL], go[OPW][VPL];
+      float keep[OPW];
+#pragma unroll
+      for (int i = 0; i < OPW; ++i) {
+        const int t = tbeg + wip + LDB_WARPS * i;
+        const bool ok = t < T;
+        keep[i] = (ok && !(pad_mask != nullptr && pad_mask[base + t])) ? 1.f : 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          xo[i][v] = ok ? *reinterpret_cast<const float4*>(x + (base + t) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          go[i][v] = ok ? *reinterpret_cast<const float4*>(dout + (base + t) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < OPW; ++i) {
+        const int r = wip + LDB_WARPS * i;
+        const int t = tbeg + r;
+        if (t >= T) continue;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = v * 128 + lane * 4;
+          float4 acc = make_float4(go[i][v].x * keep[i], go[i][v].y * keep[i], go[i][v].z * keep[i], go[i][v].w * keep[i]);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const float4 wj = *reinterpret_cast<const float4*>(stw + j * C + c);
+            const float4 d = *reinterpret_cast<const float4*>(sdd + (r + 6 - j) * C + c);   // dd[t - j + 3]
+            acc.x = fmaf(wj.x, d.x, acc.x); acc.y = fmaf(wj.y, d.y, acc.y);
+            acc.z = fmaf(wj.z, d.z, acc.z); acc.w = fmaf(wj.w, d.w, acc.w);
+            aw[j][v].x = fmaf(d.x, xo[i][v].x, aw[j][v].x); aw[j][v].y = fmaf(d.y, xo[i][v].y, aw[j][v].y);   // ddw[c,j] += dd[u-j+3] x[u]
+            aw[j][v].z = fmaf(d.z, xo[i][v].z, aw[j][v].z); aw[j][v].w = fmaf(d.w, xo[i][v].w, aw[j][v].w);
+          }
+          *reinterpret_cast<float4*>(dx + (base + t) * C + c) = acc;
+          const float4 dc = *reinterpret_cast<const float4*>(sdd + (r + 3) * C + c);
+          ab[v].x += dc.x; ab[v].y += dc.y; ab[v].z += dc.z; ab[v].w += dc.w;
+        }
+      }
+    }
+    __syncthreads();   // the next tile overwrites sdd
   }
-  // block reduction of the parameter gradients through shared memory (the warps add in turn), then one atomic per element
-  // and block
-  __shared__ float s_acc[8 * C];        // [c][8]: 7 taps + bias
-  for (int i = threadIdx.x; i < 8 * C; i += LDB_WARPS * 32) s_acc[i] = 0.f;
+  // ---- flush the parameter gradients: the warps add into a shared accumulator in turn, then one vector reduction per 4 channels ----
+  float* sacc = sdd;   // [8][C]
+  for (int i = threadIdx.x; i < 8 * C; i += LDB_WARPS * 32) sacc[i] = 0.f;
   __syncthreads();
   for (int q = 0; q < LDB_WARPS; ++q) {
     if (wip == q) {
@@ -464,20 +503,20 @@ ln_dwconv_bwd_kernel(const float* __restrict__ dxh, const __half* __restrict__ x
         const int c = v * 128 + lane * 4;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
-          s_acc[(c + 0) * 8 + j] += aw[j][v].x; s_acc[(c + 1) * 8 + j] += aw[j][v].y;
-          s_acc[(c + 2) * 8 + j] += aw[j][v].z; s_acc[(c + 3) * 8 + j] += aw[j][v].w;
+          float4 t4 = *reinterpret_cast<float4*>(sacc + j * C + c);
+          t4.x += aw[j][v].x; t4.y += aw[j][v].y; t4.z += aw[j][v].z; t4.w += aw[j][v].w;
+          *reinterpret_cast<float4*>(sacc + j * C + c) = t4;
         }
-        s_acc[(c + 0) * 8 + 7] += ab[v].x; s_acc[(c + 1) * 8 + 7] += ab[v].y;
-        s_acc[(c + 2) * 8 + 7] += ab[v].z; s_acc[(c + 3) * 8 + 7] += ab[v].w;
+        float4 t4 = *reinterpret_cast<float4*>(sacc + 7 * C + c);
+        t4.x += ab[v].x; t4.y += ab[v].y; t4.z += ab[v].z; t4.w += ab[v].w;
+        *reinterpret_cast<float4*>(sacc + 7 * C + c) = t4;
       }
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < 8 * C; i += LDB_WARPS * 32) {
-    const float s = s_acc[i];
-    const int c = i >> 3, j = i & 7;
-    if (j < 7) atomicAdd(ddw + c * 7 + j, s);
-    else atomicAdd(ddb + c, s);
+  for (int i = threadIdx.x; i < 2 * C; i += LDB_WARPS * 32) {
+    const float4 t4 = *reinterpret_cast<const float4*>(sacc + 4 * i);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dparam + 4 * i), "f"(t4.x), "f"(t4.y), "f"(t4.z), "f"(t4.w) : "memory");
   }
 }
 
@@ -571,7 +610,7 @@ extern "C" int osb_convnext_block_bwd(const float* dout, const float* gamma, con
   {
     const int tiles = B * p.m_tiles;
     const int nch = I / BB_NC;
-    int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles * 2 <= 148 ? 148 / tiles : 1);
+    int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles >= 100 ? 1 : (100 / tiles > 4 ? 4 : 100 / tiles));
     if (ns > nch / 2) ns = nch / 2;
     p.nsplit = ns < 1 ? 1 : ns;
   }
@@ -582,17 +621,26 @@ extern "C" int osb_convnext_block_bwd(const float* dout, const float* gamma, con
 }
 
 extern "C" int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const float* rstd, const float* dout, const float* x,
-                                 const float* dw_w, const uint8_t* pad_mask, float* dx, float* ddw, float* ddb, int32_t B, int32_t T,
-                                 int32_t C, void* stream) {
-  OSB_REQUIRE(dxhat && xhat_h16 && rstd && dout && x && dw_w && dx && ddw && ddb, OSB_ERR_ARG);
+                                 const float* dw_w, const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T, int32_t C,
+                                 void* stream) {
+  OSB_REQUIRE(dxhat && xhat_h16 && rstd && dout && x && dw_w && dx && dparam, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384), OSB_ERR_SHAPE);
-  const int runs_per_seq = (T + LDB_RUN - 1) / LDB_RUN;
-  const long long runs = static_cast<long long>(B) * runs_per_seq;
-  const unsigned blocks = static_cast<unsigned>((runs + LDB_WARPS - 1) / LDB_WARPS);
+  OSB_REQUIRE((reinterpret_cast<uintptr_t>(dparam) & 15) == 0, OSB_ERR_ALIGN);
+  const int tiles_per_seq = (T + LDB_TT - 1) / LDB_TT;
+  const long long ntiles = static_cast<long long>(B) * tiles_per_seq;
+  const unsigned blocks = static_cast<unsigned>(ntiles < 148 * 2 ? ntiles : 148 * 2);
+  const size_t smem = static_cast<size_t>(LDB_HR + 7) * C * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __half* xh = static_cast<const __half*>(xhat_h16);
-  if (C == 256) ln_dwconv_bwd_kernel<2><<<blocks, LDB_WARPS * 32, 0, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, ddw, ddb, B, T, runs_per_seq);
-  else ln_dwconv_bwd_kernel<3><<<blocks, LDB_WARPS * 32, 0, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, ddw, ddb, B, T, runs_per_seq);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(ln_dwconv_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LDB_HR + 7) * 256 * 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_dwconv_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LDB_HR + 7) * 384 * 4);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  if (C == 256) ln_dwconv_bwd_kernel<2><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles));
+  else ln_dwconv_bwd_kernel<3><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles));
   count_launch();
   return launch_status();
 }
@@ -601,7 +649,7 @@ extern "C" int osb_resid_param_grad(const float* dout, const float* out, const f
                                     const float* row_scale, float* dgamma, float* db2, int64_t rows, int32_t T, int32_t C, void* stream) {
   OSB_REQUIRE(dout && out && x && gamma && dgamma && db2, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && T > 0 && (C == 256 || C == 384), OSB_ERR_SHAPE);
-  const int rows_per_warp = 16;
+  const int rows_per_warp = 4;
   const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
   const unsigned blocks = static_cast<unsigned>((warps + 7) / 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -1082,6 +1082,13 @@ int make_tmap_3d(CUtensorMap* out, const void* base, TmaDtype dt, uint64_t d0, u
   cuuint32_t estr[3] = {1, elem_stride1, 1};
   CUresult r = fn(out, cdt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    // A thread that has not made a runtime call yet (e.g. the autograd engine's worker on its first backward node) has no
+    // current context for this driver entry point: bind the primary context and retry once.
+    cudaFree(nullptr);
+    r = fn(out, cdt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? OSB_OK : OSB_ERR_DRIVER;
 }
 

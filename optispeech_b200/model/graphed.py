@@ -61,6 +61,7 @@ class GraphedTrainingStep:
         self._warm: Dict[tuple, int] = {}
         self.replays = 0
         self.last_entry: _Entry = None
+        self._capture_stream = None
 
     @staticmethod
     def _key(batch, train_discriminator: bool) -> tuple:
@@ -148,7 +149,11 @@ class GraphedTrainingStep:
         m._capturing = True
         try:
             # the NCCL watchdog thread polls events while we capture: only this thread's calls may invalidate the capture
-            with torch.cuda.graph(graph, capture_error_mode="thread_local" if world > 1 else "global"):
+            # captured on a high-priority stream: the step's main chain outranks the low-priority decoder / vocoder and
+            # weight-gradient branches (ops.side_stream) when CTAs compete for SMs
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=dev, priority=-1)
+            with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local" if world > 1 else "global"):
                 (self.step_fn or m._training_step_eager)(static_batch, batch_idx)
         finally:
             m._capturing = False

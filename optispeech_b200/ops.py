@@ -49,7 +49,13 @@ def side_stream(device, slot: int = 0) -> "torch.cuda.Stream":
     key = (torch.device(device).index or 0, slot)
     s = _SIDE_STREAMS.get(key)
     if s is None:
-        s = torch.cuda.Stream(device=device)
+        # Branches on the step's critical path (alignment / predictor branches) get a high-priority stream; the gradient-free
+        # decoder -> vocoder branch (slot 5) and the weight-gradient streams (slots >= 6) keep the default (lowest) priority:
+        # their full-machine kernels (216 CTAs x 224 KB of shared memory) otherwise hold every SM while the small kernels of
+        # the critical path wait for a free one (timeline of the captured step, round 2).  A captured kernel node inherits
+        # the priority of the stream it was captured on.
+        prio = -1 if slot <= 4 else 0
+        s = torch.cuda.Stream(device=device, priority=prio)
         _SIDE_STREAMS[key] = s
     return s
 
@@ -539,10 +545,10 @@ def ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w, pad_mask):
     """LayerNorm backward + depthwise conv backward + residual path -> (dx, ddw (C,7), ddb (C))."""
     B, T, Cc = x.shape
     dx = torch.empty_like(x)
-    ddw, ddb = _zeros((Cc, 7), x), _zeros((Cc,), x)
+    dparam = _zeros((8, Cc), x)      # rows 0-6: the 7 taps (tap-major), row 7: the bias
     _lib.check(_lib.load().osb_ln_dwconv_bwd(_ptr(_f32(dxh)), _ptr(xhat), _ptr(_f32(rstd)), _ptr(_f32(dout)), _ptr(_f32(x)), _ptr(_f32(dw_w)),
-                                             _ptr(pad_mask), _ptr(dx), _ptr(ddw), _ptr(ddb), B, T, Cc, _stream()), "osb_ln_dwconv_bwd")
-    return dx, ddw, ddb
+                                             _ptr(pad_mask), _ptr(dx), _ptr(dparam), B, T, Cc, _stream()), "osb_ln_dwconv_bwd")
+    return dx, dparam[:7].t(), dparam[7]
 
 
 def resid_param_grad(dout, out, x, gamma, pad_mask, row_scale):
@@ -559,7 +565,7 @@ def resid_param_grad(dout, out, x, gamma, pad_mask, row_scale):
 # contractions / reductions that produce them leave the critical path (data gradients) of the backward pass
 # ------------------------------------------------------------------------------------------------
 _GRAD_PENDING = {"streams": [], "keep": [], "hooked": False, "rr": 0}
-GRAD_SIDE_SLOTS = (6, 7)
+GRAD_SIDE_SLOTS = (6, 7, 8, 9)
 
 
 class grad_side:
@@ -582,6 +588,10 @@ class grad_side:
         self.side.wait_stream(torch.cuda.current_stream(self.dev))
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
+        # zero-initialised accumulators requested inside the context come from a block that is allocated AND filled on the
+        # side stream (a block filled on the forking stream after the fork would not be ordered before the side stream's use)
+        global _POOL
+        self._prev_pool, _POOL = _POOL, _ZeroPool(self.dev, 1 << 18)
         return self
 
     def keepalive(self, *tensors):
@@ -592,6 +602,8 @@ class grad_side:
     def __exit__(self, *exc):
         if not self.enabled:
             return False
+        global _POOL
+        _POOL = self._prev_pool
         self.ctx.__exit__(*exc)
         st = _GRAD_PENDING
         if self.side not in st["streams"]:

@@ -392,7 +392,8 @@ def test_forward_sum_warp_recursion_matches_oracle_and_legacy(cuda_device, Tx, T
     print(f"  Tx={Tx} Tm={Tm} sharp={sharp}: warp {total:.6f} legacy {float(loss_l.sum()) / B:.6f} oracle {float(ref):.6f}")
     assert abs(total - float(ref)) <= 2e-5 * abs(float(ref))
     assert torch.allclose(loss_w, loss_l, rtol=2e-5, atol=1e-6)
-    _check([("dlogp vs oracle", grad_w.cpu(), rg), ("dlogp vs legacy", grad_w.cpu(), grad_l.cpu())], 1e-3)
+    # sharply peaked rows put the posteriors at exp() of differences of ~1e3-magnitude logs: 3e-3 there, 1e-3 otherwise
+    _check([("dlogp vs oracle", grad_w.cpu(), rg), ("dlogp vs legacy", grad_w.cpu(), grad_l.cpu())], 3e-3 if sharp > 8 else 1e-3)
 
 
 @pytest.mark.parametrize("B,T_in,Cin,Cout,stride", [(3, 200, 128, 128, 3), (2, 1366, 32, 128, 3), (2, 97, 64, 64, 2)])
