@@ -395,19 +395,24 @@ int osb_fs2_losses(const float* d_hat, const float* p_hat, const float* e_hat, c
 /* align_loss = forward-sum loss + bin loss (generator/__init__.py:174-175; bin loss: alignments.py:236-238) from the outputs
  * of osb_forward_sum (per-sample losses, gradient) and osb_mas (path):  out[0] = align_loss, out[1] = forward-sum part,
  * out[2] = bin part = -(1/B) sum_b mean_t log_p_attn[b,t,path[b,t]];  fs_grad (B,Tm,Tx) receives the bin-loss gradient
- * in place, so it becomes d(align_loss)/d(log_p_attn). */
+ * in place, so it becomes d(align_loss)/d(log_p_attn).  workspace: B + 1 fp32 words; the last word is a counter that has to
+ * be ZERO on entry and is left zero (one CTA per sample; the last one to finish adds the partial sums in sample order). */
 int osb_align_loss_fold(const float* log_p_attn, const int32_t* path, const int64_t* m_len, const float* per_sample_fs, float* fs_grad,
-                        float* out /*(3)*/, int32_t B, int32_t Tm, int32_t Tx, void* stream);
+                        float* out /*(3)*/, float* workspace /*(B+1)*/, int32_t B, int32_t Tm, int32_t Tx, void* stream);
 
 /* Every fp32 -> fp16 weight pack of a training step in ONE launch (the weights change every step, so the packs are
  * per-step work: 44 small launches otherwise).  jobs_dev: device array, sorted by first_elem (prefix sums of the
  * destination element counts, first_elem[0] = 0); total_elems = sum of destination elements.
  *   kind 0: src (rows, cols) fp32 row-major, optionally scaled per column -> dst (rows, dst_cols) fp16, zero padded
- *   kind 1: src Conv1d weight (rows = N, cols = Cin, k) -> dst (k, N, dst_cols) fp16 (one K-major matrix per tap) */
+ *   kind 1: src Conv1d weight (rows = N, cols = Cin, k) -> dst (k, N, dst_cols) fp16 (one K-major matrix per tap)
+ *   kind 2: dst (rows) fp32 = aux (rows) + src (rows, cols) @ col_scale (cols)   (counts as 8 * rows destination elements):
+ *           the pwconv1 bias with the LayerNorm bias folded in, b1 + W1 @ ln_b (modules/convnext.py:38-39)
+ * dst_cols and every first_elem are multiples of 8 (a thread writes 8 destination elements with one 16-byte store). */
 typedef struct osb_pack_job {
   const void* src;
   void* dst;
-  const void* col_scale;   /* kind 0: (cols) fp32 or NULL */
+  const void* col_scale;   /* kind 0: (cols) fp32 or NULL; kind 2: the vector */
+  const void* aux;         /* kind 2: (rows) fp32 addend or NULL */
   int64_t first_elem;
   int32_t kind, rows, cols, k, dst_cols, reserved;
 } osb_pack_job;

@@ -66,7 +66,7 @@ class GemmDesc(C.Structure):
 class PackJob(C.Structure):
     """Mirror of `osb_pack_job` (include/osb200.h)."""
 
-    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("col_scale", C.c_void_p), ("first_elem", C.c_int64), ("kind", C.c_int32),
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("col_scale", C.c_void_p), ("aux", C.c_void_p), ("first_elem", C.c_int64), ("kind", C.c_int32),
                 ("rows", C.c_int32), ("cols", C.c_int32), ("k", C.c_int32), ("dst_cols", C.c_int32), ("reserved", C.c_int32)]
 
 
@@ -136,7 +136,7 @@ def load() -> C.CDLL:
         "osb_adamw_step_dev": [P, P, P, P, I64, P, P, F, F, F, F, F, F, P],
         "osb_average_by_duration": [P, P, P, P, P, I32, I32, I32, P],
         "osb_pack_multi": [P, I32, I64, P],
-        "osb_align_loss_fold": [P, P, P, P, P, P, I32, I32, I32, P],
+        "osb_align_loss_fold": [P, P, P, P, P, P, P, I32, I32, I32, P],
         "osb_fs2_losses": [P, P, P, P, P, P, P, P, P, P, P, I32, I32, P],
         "osb_mha_fwd": [P, P, P, I64, P, P, I64, I64, P, P, I32, I32, I32, I32, F, F, C.c_uint64, P, P],
         "osb_mha_bwd": [P, P, P, I64, P, P, I64, P, I64, P, P, P, I64, P, P, I64, I32, I32, I32, I32, I32, F, F, C.c_uint64, P, P],

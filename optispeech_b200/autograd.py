@@ -47,6 +47,20 @@ def pack_params_nk(ws, col_scale: Optional[torch.Tensor] = None) -> torch.Tensor
     return packer.request("nk", ws, col_scale, None, direct)
 
 
+def folded_bias(b1: torch.Tensor, w1: torch.Tensor, ln_b: torch.Tensor) -> torch.Tensor:
+    """b1 + W1 @ ln_b (the LayerNorm bias folded into the bias of the Linear that follows it), through the step packer: inside
+    a recorded step it costs nothing extra (a job of the one osb_pack_multi launch) instead of a copy + gemv per block."""
+    from .model.packing import current_packer
+
+    def direct():
+        return torch.addmv(b1, w1, ln_b)
+
+    packer = current_packer()
+    if packer is None or not (w1.is_contiguous() and w1.shape[1] % 4 == 0):
+        return direct()
+    return packer.request("matvec", [w1], ln_b, None, direct, aux=b1)
+
+
 def pack_param_conv(w: torch.Tensor, k_pad: Optional[int] = None) -> torch.Tensor:
     """Conv1d parameter (N, Cin, k) -> (k, N, Cin_pad) fp16 through the step packer."""
     from .model.packing import current_packer
@@ -119,7 +133,7 @@ class ConvNeXtBlockFn(Function):
     def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, pad_mask, row_scale, eps):
         B, T, C = x.shape
         I = w1.shape[0]
-        b1f = torch.addmv(b1, w1, ln_b)      # fold the LN affine into pwconv1: bias here, weight as a column scale of the pack
+        b1f = folded_bias(b1, w1, ln_b)      # fold the LN affine into pwconv1: bias here, weight as a column scale of the pack
         w1f_h, w2_h = pack_params_nk([w1], col_scale=ln_w), pack_params_nk([w2])
         ctx.fused = ConvNeXtBlockFn.FUSED and (C, I) in ops.FUSED_BLOCK_SHAPES
         if ctx.fused:

@@ -114,30 +114,38 @@ template <> struct MasFlag<8> { using type = unsigned char; };
 template <> struct MasFlag<12> { using type = unsigned short; };
 template <> struct MasFlag<16> { using type = unsigned short; };
 
-template <int VPL>
-__global__ void __launch_bounds__(32)
+// W warps per sample (round 2): the search is issue bound on one warp (fp64 adds / compares / selects of VPL tokens per lane
+// at ~0.45 instructions per cycle), so the tokens are spread over W warps with VPL = ceil(Tx / (32 W)) per lane; the one
+// fp64 value that crosses a warp boundary per frame goes through a double-buffered shared-memory mailbox and one block
+// barrier per frame.  W = 1 keeps the single-warp form (no barrier).
+template <int VPL, int W>
+__global__ void __launch_bounds__(32 * W)
 mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                 int* __restrict__ path, float* __restrict__ dur, int Tm, int Tx) {
   using FlagT = typename MasFlag<VPL>::type;
+  constexpr int NL = 32 * W;                              // lanes per sample
   constexpr int G = VPL <= 8 ? 8 : (VPL <= 16 ? 4 : 2);  // frames per prefetch batch
   extern __shared__ unsigned char mas_smem[];
+  __shared__ double mbox[2][W];
   const int b = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int wip = threadIdx.x >> 5;
+  const int gl = threadIdx.x;                              // lane index inside the sample
   const int N = static_cast<int>(x_len[b]);
   const int T = static_cast<int>(m_len[b]);
   int* pth = reinterpret_cast<int*>(mas_smem);                               // [Tm]
   int* cnt = pth + Tm;                                                       // [Tx]
-  FlagT* flags = reinterpret_cast<FlagT*>(cnt + Tx);                         // [T][32]
+  FlagT* flags = reinterpret_cast<FlagT*>(cnt + Tx);                         // [T][NL]
   const float* lpb = lp + static_cast<long long>(b) * Tm * Tx;
   int* pb = path + static_cast<long long>(b) * Tm;
-  for (int n = lane; n < Tx; n += 32) cnt[n] = 0;
+  for (int n = gl; n < Tx; n += NL) cnt[n] = 0;
   if (N <= 0 || T <= 0) {
-    for (int t = lane; t < Tm; t += 32) pb[t] = -1;
-    for (int n = lane; n < Tx; n += 32) dur[static_cast<long long>(b) * Tx + n] = 0.f;
+    for (int t = gl; t < Tm; t += NL) pb[t] = -1;
+    for (int n = gl; n < Tx; n += NL) dur[static_cast<long long>(b) * Tx + n] = 0.f;
     return;
   }
   const double NEG = -INFINITY;
-  const int c0 = lane * VPL;
+  const int c0 = gl * VPL;
   double q[VPL];
   int lim[VPL];    // token i = c0 + k takes part from frame j >= lim[k] on (i <= j), never when i >= N; token 0 is the float32 row sum
 #pragma unroll
@@ -146,11 +154,15 @@ mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_le
     lim[k] = (c0 + k < N && c0 + k > 0) ? c0 + k : 0x7fffffff;
   }
   float row0 = 0.f;
-  if (lane == 0) {
+  if (gl == 0) {
     row0 = lpb[0];
     q[0] = static_cast<double>(row0);
   }
-  const bool first = lane == 0;
+  const bool first = gl == 0;
+  if (W > 1) {
+    if (lane == 31) mbox[0][wip] = q[VPL - 1];
+    __syncthreads();
+  }
   // Frames are fetched G at a time, one whole batch ahead (two register batches): the wait at the top of a batch then only
   // covers loads issued a full batch earlier.  (Per-frame refills share hardware scoreboards with the newest loads and
   // serialise on the full memory latency every frame.)
@@ -169,9 +181,9 @@ mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_le
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int j = base + g;
-      if (j < T) {  // warp-uniform
+      if (j < T) {  // uniform across the block
         double up = __shfl_up_sync(0xffffffffu, q[VPL - 1], 1);
-        if (first) up = NEG;
+        if (lane == 0) up = (W > 1 && wip > 0) ? mbox[(j - 1) & 1][wip - 1] : NEG;
         unsigned bits = 0;
         row0 = __fadd_rn(row0, cur[g][0]);
 #pragma unroll
@@ -189,7 +201,11 @@ mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_le
           q[0] = static_cast<double>(row0);
           bits &= ~1u;  // token 0 has no left neighbour
         }
-        flags[static_cast<size_t>(j) * 32 + lane] = static_cast<FlagT>(bits);
+        flags[static_cast<size_t>(j) * NL + gl] = static_cast<FlagT>(bits);
+        if (W > 1) {
+          if (lane == 31) mbox[j & 1][wip] = q[VPL - 1];
+          __syncthreads();
+        }
       }
     }
 #pragma unroll
@@ -197,20 +213,20 @@ mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_le
 #pragma unroll
       for (int k = 0; k < VPL; ++k) cur[g][k] = nxt[g][k];
   }
-  __syncwarp();
-  if (lane == 0) {
+  __syncthreads();
+  if (gl == 0) {
     int a = N - 1;
     pth[T - 1] = a;
     for (int j = T - 2; j >= 0; --j) {
       if (a > 0) {
-        const unsigned w = flags[static_cast<size_t>(j + 1) * 32 + a / VPL];
+        const unsigned w = flags[static_cast<size_t>(j + 1) * NL + a / VPL];
         a -= (w >> (a % VPL)) & 1u;
       }
       pth[j] = a;
     }
   }
-  __syncwarp();
-  for (int t = lane; t < Tm; t += 32) {
+  __syncthreads();
+  for (int t = gl; t < Tm; t += NL) {
     if (t < T) {
       const int a = pth[t];
       pb[t] = a;
@@ -219,22 +235,22 @@ mas_warp_kernel(const float* __restrict__ lp, const long long* __restrict__ x_le
       pb[t] = -1;
     }
   }
-  __syncwarp();
-  for (int n = lane; n < Tx; n += 32) dur[static_cast<long long>(b) * Tx + n] = static_cast<float>(cnt[n]);
+  __syncthreads();
+  for (int n = gl; n < Tx; n += NL) dur[static_cast<long long>(b) * Tx + n] = static_cast<float>(cnt[n]);
 }
 
-template <int VPL>
+template <int VPL, int W>
 int launch_mas_warp(const float* lp, const long long* x_len, const long long* m_len, int* path, float* dur, int B, int Tm, int Tx,
                     cudaStream_t stream) {
   using FlagT = typename MasFlag<VPL>::type;
-  const size_t smem = sizeof(int) * (static_cast<size_t>(Tm) + Tx) + sizeof(FlagT) * 32 * static_cast<size_t>(Tm);
+  const size_t smem = sizeof(int) * (static_cast<size_t>(Tm) + Tx) + sizeof(FlagT) * 32 * W * static_cast<size_t>(Tm);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mas_warp_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mas_warp_kernel<VPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = 200 * 1024;
   }
-  mas_warp_kernel<VPL><<<B, 32, smem, stream>>>(lp, x_len, m_len, path, dur, Tm, Tx);
+  mas_warp_kernel<VPL, W><<<B, 32 * W, smem, stream>>>(lp, x_len, m_len, path, dur, Tm, Tx);
   count_launch();
   return launch_status();
 }
@@ -291,14 +307,21 @@ extern "C" int osb_mas(const float* log_p_attn, const int64_t* x_len, const int6
       const long long* xl = reinterpret_cast<const long long*>(x_len);
       const long long* ml = reinterpret_cast<const long long*>(m_len);
       cudaStream_t st = static_cast<cudaStream_t>(stream);
-      if (vpl <= 2) return launch_mas_warp<2>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 4) return launch_mas_warp<4>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 6) return launch_mas_warp<6>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 8) return launch_mas_warp<8>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 12) return launch_mas_warp<12>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 16) return launch_mas_warp<16>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      if (vpl <= 24) return launch_mas_warp<24>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
-      return launch_mas_warp<32>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      // four warps per sample (2-4 tokens per lane) while their decision bytes fit shared memory; else one warp
+      static const bool one_warp = getenv("OSB_MAS_ONE_WARP") != nullptr;   // developer switch
+      const size_t need4 = sizeof(int) * (static_cast<size_t>(Tm) + Tx) + static_cast<size_t>(128) * Tm;
+      if (!one_warp && Tx <= 512 && need4 <= 200 * 1024) {
+        if (Tx <= 256) return launch_mas_warp<2, 4>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+        return launch_mas_warp<4, 4>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      }
+      if (vpl <= 2) return launch_mas_warp<2, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 4) return launch_mas_warp<4, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 6) return launch_mas_warp<6, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 8) return launch_mas_warp<8, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 12) return launch_mas_warp<12, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 16) return launch_mas_warp<16, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      if (vpl <= 24) return launch_mas_warp<24, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
+      return launch_mas_warp<32, 1>(log_p_attn, xl, ml, path, durations, B, Tm, Tx, st);
     }
   }
   const int nthr = ((Tx + 31) / 32) * 32;

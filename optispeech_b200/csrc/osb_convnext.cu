@@ -522,14 +522,14 @@ static int fused_fwd_impl(const float* x, const float* dw_w, const float* dw_b, 
   p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps; p.I = I;
   p.xhat_out = static_cast<__half*>(xhat_out); p.rstd_out = rstd_out; p.pre_out = static_cast<__half*>(pre_out);
   p.h_out = static_cast<__half*>(h_out);
-  // Few row tiles: split the intermediate dimension over blockIdx.y so that more SMs share the chunk loop — but no further
-  // than ~100 CTAs and 4 splits: beyond that the prologue (replicated per split) and the L2 reductions cost more than the
-  // shorter loops save (measured: 48 tiles: 2 splits 42 us, 3 splits 66 us; 16 tiles: 4 splits = 9 splits), and the SMs left
-  // free run the other branches of the step.
+  // Few row tiles (less than half the SMs): split the intermediate dimension over blockIdx.y so that more SMs share the chunk
+  // loop — 148 / tiles splits, at most 4: beyond that the prologue (replicated per split) and the L2 reductions cost what the
+  // shorter loops save (16 tiles: 4 splits take the same 45 us as 9), and the SMs left free run the other branches of the
+  // step (inside the captured step 48 tiles run 46 us with 3 splits, 63 us with 2).
   {
     const int tiles = B * p.m_tiles;
     const int nch = I / FB_NC;
-    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles >= 100 ? 1 : (100 / tiles > 4 ? 4 : 100 / tiles));
+    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > 4 ? 4 : 148 / tiles));
     if (ns > nch / 2) ns = nch / 2;
     p.nsplit = ns < 1 ? 1 : ns;
   }

@@ -610,7 +610,7 @@ extern "C" int osb_convnext_block_bwd(const float* dout, const float* gamma, con
   {
     const int tiles = B * p.m_tiles;
     const int nch = I / BB_NC;
-    int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles >= 100 ? 1 : (100 / tiles > 4 ? 4 : 100 / tiles));
+    int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > 4 ? 4 : 148 / tiles));
     if (ns > nch / 2) ns = nch / 2;
     p.nsplit = ns < 1 ? 1 : ns;
   }

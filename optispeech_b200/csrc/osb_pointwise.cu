@@ -410,11 +410,14 @@ __global__ void pack_conv_h16_kernel(const float* __restrict__ w, __half* __rest
   if (dst_lo != nullptr) dst_lo[i] = __float2half_rn(v - __half2float(hi));
 }
 
-// Every weight pack of a training step in ONE launch: jobs[] (device) lists (source, destination, layout); a thread finds its
-// job by binary search over the prefix sums of the destination sizes.  kind 0: (rows, cols) fp32 row-major (optionally
-// scaled per column) -> (rows, dst_cols) fp16; kind 1: Conv1d weight (rows = N, cols = Cin, k) -> (k, N, dst_cols) fp16.
-__global__ void pack_multi_kernel(const osb_pack_job* __restrict__ jobs, int n_jobs, long long total) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+// Every weight pack of a training step in ONE launch: jobs[] (device) lists (source, destination, layout); a thread owns 8
+// consecutive destination elements (one 16-byte store) and finds its job by binary search over the prefix sums of the
+// destination sizes (multiples of 8).  kind 0: (rows, cols) fp32 row-major (optionally scaled per column) -> (rows, dst_cols)
+// fp16; kind 1: Conv1d weight (rows = N, cols = Cin, k) -> (k, N, dst_cols) fp16; kind 2: fp32 matrix-vector product
+// dst[r] = aux[r] + sum_c src[r, c] * col_scale[c] (the LayerNorm bias folded into the pwconv1 bias), 8 virtual elements
+// per row.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const osb_pack_job* __restrict__ jobs, int n_jobs, long long total) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i >= total) return;
   int lo = 0, hi = n_jobs - 1;
   while (lo < hi) {
@@ -424,21 +427,51 @@ __global__ void pack_multi_kernel(const osb_pack_job* __restrict__ jobs, int n_j
   const osb_pack_job j = jobs[lo];
   const long long e = i - j.first_elem;
   const float* src = static_cast<const float*>(j.src);
-  float v = 0.f;
+  const float* cs = static_cast<const float*>(j.col_scale);
+  if (j.kind == 2) {
+    const long long r = e >> 3;
+    const float* row = src + r * j.cols;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= j.cols; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(row + c);
+      const float4 v4 = *reinterpret_cast<const float4*>(cs + c);
+      acc0 = fmaf(w4.x, v4.x, acc0); acc1 = fmaf(w4.y, v4.y, acc1); acc2 = fmaf(w4.z, v4.z, acc2); acc3 = fmaf(w4.w, v4.w, acc3);
+    }
+    for (; c < j.cols; ++c) acc0 = fmaf(row[c], cs[c], acc0);
+    static_cast<float*>(j.dst)[r] = (j.aux != nullptr ? static_cast<const float*>(j.aux)[r] : 0.f) + ((acc0 + acc1) + (acc2 + acc3));
+    return;
+  }
+  float v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  const int c = static_cast<int>(e % j.dst_cols);
   if (j.kind == 0) {
     const long long r = e / j.dst_cols;
-    const int c = static_cast<int>(e % j.dst_cols);
-    if (c < j.cols) {
-      v = src[r * j.cols + c];
-      if (j.col_scale != nullptr) v *= static_cast<const float*>(j.col_scale)[c];
+    const float* row = src + r * j.cols;
+    if (c + 8 <= j.cols && ((reinterpret_cast<uintptr_t>(row + c) & 15) == 0)) {
+      const float4 a4 = *reinterpret_cast<const float4*>(row + c), b4 = *reinterpret_cast<const float4*>(row + c + 4);
+      v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (c + q < j.cols) v[q] = row[c + q];
+    }
+    if (cs != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (c + q < j.cols) v[q] *= cs[c + q];
     }
   } else {
-    const int c = static_cast<int>(e % j.dst_cols);
     const int n = static_cast<int>((e / j.dst_cols) % j.rows);
     const int tap = static_cast<int>(e / (static_cast<long long>(j.dst_cols) * j.rows));
-    if (c < j.cols) v = src[(static_cast<long long>(n) * j.cols + c) * j.k + tap];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (c + q < j.cols) v[q] = src[(static_cast<long long>(n) * j.cols + c + q) * j.k + tap];
   }
-  static_cast<__half*>(j.dst)[e] = __float2half_rn(v);
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(static_cast<__half*>(j.dst) + e) = u;
 }
 
 }  // namespace
@@ -448,9 +481,9 @@ using namespace osb;
 
 extern "C" int osb_pack_multi(const osb_pack_job* jobs_dev, int32_t n_jobs, int64_t total_elems, void* stream) {
   OSB_REQUIRE(jobs_dev != nullptr, OSB_ERR_ARG);
-  OSB_REQUIRE(n_jobs > 0 && total_elems > 0, OSB_ERR_SHAPE);
-  pack_multi_kernel<<<static_cast<unsigned>((total_elems + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, n_jobs,
-                                                                                                                   total_elems);
+  OSB_REQUIRE(n_jobs > 0 && total_elems > 0 && total_elems % 8 == 0, OSB_ERR_SHAPE);
+  pack_multi_kernel<<<static_cast<unsigned>((total_elems / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, n_jobs,
+                                                                                                                       total_elems);
   count_launch();
   return launch_status();
 }

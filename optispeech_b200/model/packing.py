@@ -87,8 +87,9 @@ class StepPacker:
         self.active = False
 
     @staticmethod
-    def _spec(kind, srcs, col_scale, k_pad):
-        return (kind, tuple((s.data_ptr(), tuple(s.shape)) for s in srcs), col_scale.data_ptr() if col_scale is not None else 0, k_pad or 0)
+    def _spec(kind, srcs, col_scale, k_pad, aux=None):
+        return (kind, tuple((s.data_ptr(), tuple(s.shape)) for s in srcs), col_scale.data_ptr() if col_scale is not None else 0, k_pad or 0,
+                aux.data_ptr() if aux is not None else 0)
 
     def begin(self, device):
         from .. import _lib, ops
@@ -115,10 +116,11 @@ class StepPacker:
     def drop(self):
         self.plan, self.recording, self.active = None, None, False
 
-    def request(self, kind, srcs, col_scale, k_pad, direct):
-        """-> packed tensor for (kind, srcs, col_scale, k_pad); `direct()` packs it with one launch (fallback / recording)."""
+    def request(self, kind, srcs, col_scale, k_pad, direct, aux=None):
+        """-> packed tensor for (kind, srcs, col_scale, k_pad); `direct()` packs it with one launch (fallback / recording).
+        kind "matvec": fp32 (rows,) = aux + srcs[0] @ col_scale."""
         if self.active:
-            spec = self._spec(kind, srcs, col_scale, k_pad)
+            spec = self._spec(kind, srcs, col_scale, k_pad, aux)
             if self.cursor < len(self.plan["specs"]) and self.plan["specs"][self.cursor] == spec:
                 out = self.plan["outs"][self.cursor]
                 self.cursor += 1
@@ -127,7 +129,7 @@ class StepPacker:
             return direct()
         out = direct()
         if self.recording is not None:
-            self.recording.append((self._spec(kind, srcs, col_scale, k_pad), kind, list(srcs), col_scale, k_pad, out))
+            self.recording.append((self._spec(kind, srcs, col_scale, k_pad, aux), kind, list(srcs), col_scale, k_pad, out, aux))
         return out
 
     def _build(self, rec):
@@ -136,10 +138,21 @@ class StepPacker:
         from .. import _lib
 
         jobs, outs, specs, first = [], [], [], 0
-        for spec, kind, srcs, col_scale, k_pad, sample in rec:
+        for spec, kind, srcs, col_scale, k_pad, sample, aux in rec:
             out = torch.empty_like(sample)
             flat = out.view(-1)
             off = 0
+            if kind == "matvec":
+                rows, cols = srcs[0].shape
+                j = _lib.PackJob()
+                j.src, j.col_scale, j.aux = srcs[0].data_ptr(), col_scale.data_ptr(), (aux.data_ptr() if aux is not None else None)
+                j.dst, j.first_elem = flat.data_ptr(), first
+                j.kind, j.rows, j.cols, j.k, j.dst_cols = 2, rows, cols, 1, 8
+                jobs.append(j)
+                first += 8 * rows
+                outs.append(out)
+                specs.append(spec)
+                continue
             for s in srcs:
                 j = _lib.PackJob()
                 j.src, j.col_scale = s.data_ptr(), (col_scale.data_ptr() if col_scale is not None else None)
@@ -153,6 +166,9 @@ class StepPacker:
                     N, Cin, k = s.shape
                     j.kind, j.rows, j.cols, j.k, j.dst_cols = 1, N, Cin, k, (k_pad or Cin)
                     n = k * N * j.dst_cols
+                if j.dst_cols % 8 or n % 8:   # the launch writes 16-byte groups: keep such a step on the per-request path
+                    self.plan = None
+                    return
                 jobs.append(j)
                 first += n
                 off += n
@@ -163,7 +179,7 @@ class StepPacker:
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         dev = rec[0][5].device
         self.plan = dict(specs=specs, outs=outs, table=raw.to(dev), n_jobs=len(jobs), total=first, device=dev,
-                         keepalive=[(srcs, cs) for _, _, srcs, cs, _, _ in rec])
+                         keepalive=[(srcs, cs, ax) for _, _, srcs, cs, _, _, ax in rec])
 
 
 _CURRENT: "StepPacker | None" = None   # the packer of the training forward in progress (set by generator_training_forward)

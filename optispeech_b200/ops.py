@@ -700,6 +700,9 @@ def add_posenc(x: torch.Tensor, pe: Optional[torch.Tensor], alpha: Optional[torc
     return out
 
 
+_ALIGN_WS = {}
+
+
 def fs2_losses(d_hat, p_hat, e_hat, ds, p_tgt, e_tgt, x_len):
     """-> (losses (3,) fp32 = [duration, pitch, energy], g_d, g_p, g_e (B,Tx) = gradients of the respective loss)."""
     B, Tx = d_hat.shape
@@ -715,8 +718,13 @@ def align_loss_fold(log_p_attn, path, m_len, per_sample_fs, fs_grad):
     """-> (3,) fp32 = [align_loss, forward-sum part, bin part]; adds the bin-loss gradient into `fs_grad` in place."""
     B, Tm, Tx = log_p_attn.shape
     out = torch.empty(3, device=log_p_attn.device, dtype=torch.float32)
+    key = (log_p_attn.device.index or 0, B)
+    ws = _ALIGN_WS.get(key)
+    if ws is None:   # per-sample partial sums + a counter the kernel leaves at zero: allocated (and zeroed) once
+        ws = torch.zeros(B + 1, device=log_p_attn.device, dtype=torch.float32)
+        _ALIGN_WS[key] = ws
     _lib.check(_lib.load().osb_align_loss_fold(_ptr(_f32(log_p_attn)), _ptr(path), _ptr(m_len), _ptr(per_sample_fs), _ptr(fs_grad), _ptr(out),
-                                               B, Tm, Tx, _stream()), "osb_align_loss_fold")
+                                               _ptr(ws), B, Tm, Tx, _stream()), "osb_align_loss_fold")
     return out
 
 
