@@ -490,8 +490,11 @@ int osb_convnext_block_fwd_train(const float* x, const float* dw_w, const float*
 /* Both data-gradient contractions of a ConvNeXt block in one tcgen05 kernel (the autograd of modules/convnext.py:39-46):
  *   dyg   = fp16(dout * gamma * keep * row_scale[b])                     (B,T,C)  dy of the pwconv2 weight gradient
  *   dh    = fp16((dyg . W2) * gelu_erf'(pre))                            (B,T,I)  dy of the pwconv1 weight gradient
- *   dxhat = dh . W1f   (fp32)                                            (B,T,C)  gradient wrt the normalised dwconv output
+ *   dxhat = dh . W1f   (fp32)                                      (parts,B,T,C)  gradient wrt the normalised dwconv output, as
+ *           `parts` = osb_convnext_block_bwd_parts(B, T, I) partial sums (the intermediate dimension is split over CTAs when
+ *           there are few row tiles; osb_ln_dwconv_bwd adds them up)
  * w2_h16 (C, I) and w1f_h16 (I, C) are the FORWARD fp16 packs (read as MN-major B operands).  (C, I) = (256,1024) or (384,1152). */
+int osb_convnext_block_bwd_parts(int32_t B, int32_t T, int32_t I);
 int osb_convnext_block_bwd(const float* dout, const float* gamma, const float* row_scale, const uint8_t* pad_mask, const void* pre_h16,
                            const void* w2_h16, const void* w1f_h16, void* dyg_h16, void* dh_h16, float* dxhat, int32_t B, int32_t T,
                            int32_t C, int32_t I, void* stream);
@@ -500,8 +503,9 @@ int osb_convnext_block_bwd(const float* dout, const float* gamma, const float* r
  *   dd = LN_bwd(dxhat; xhat, rstd);  dx[t] = dout[t] * keep[t] + sum_j w[:,j] * dd[t-j+3]
  *   dparam (8, C) fp32 += [ddw[:,0] | ... | ddw[:,6] | ddb]   (tap-major; accumulated: zero it first)
  * Autograd of nn.Conv1d(groups=C) + nn.LayerNorm (modules/convnext.py:36-38). */
-int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const float* rstd, const float* dout, const float* x, const float* dw_w,
-                      const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T, int32_t C, void* stream);
+int osb_ln_dwconv_bwd(const float* dxhat /*(nparts,B,T,C)*/, int32_t nparts, const void* xhat_h16, const float* rstd, const float* dout,
+                      const float* x, const float* dw_w, const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T,
+                      int32_t C, void* stream);
 
 /* Layer-scale and pwconv2-bias gradients from the block's input x and output out (gamma * z * rs = out - x on unmasked rows):
  *   dgamma += sum_rows dout * keep * (out - x) / gamma ;  db2 += sum_rows dout * keep * rs * gamma   (modules/convnext.py:42-46) */

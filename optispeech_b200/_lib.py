@@ -145,7 +145,8 @@ def load() -> C.CDLL:
         "osb_add_posenc": [P, P, P, P, I32, I32, I32, F, C.c_uint64, P, P],
         "osb_convnext_block_fwd_train": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, F, P],
         "osb_convnext_block_bwd": [P, P, P, P, P, P, P, P, P, P, I32, I32, I32, I32, P],
-        "osb_ln_dwconv_bwd": [P, P, P, P, P, P, P, P, P, I32, I32, I32, P],
+        "osb_ln_dwconv_bwd": [P, I32, P, P, P, P, P, P, P, P, I32, I32, I32, P],
+        "osb_convnext_block_bwd_parts": [I32, I32, I32],
         "osb_resid_param_grad": [P, P, P, P, P, P, P, P, I64, I32, I32, P],
         "osb_sequence_mask": [P, P, P, I32, I32, P],
         "osb_segment_starts": [P, P, P, I32, I32, I32, P],

@@ -160,7 +160,7 @@ class ConvNeXtBlockFn(Function):
             out = z_or_out
             dyg, dh, dxh = ops.convnext_block_bwd(dout, gamma, row_scale, pad_mask, pre, w2_h[0], w1f_h[0])
             dx, ddw, ddb = ops.ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w.view(C, 7), pad_mask)
-            with ops.grad_side(x, dout, dyg, dh, h, xhat, out, x) as side:     # parameter gradients: off the critical path
+            with ops.grad_side(x, dout, dyg, dh, h, xhat, out, x):     # parameter gradients: off the critical path
                 dgamma, db2 = ops.resid_param_grad(dout, out, x, gamma, pad_mask, row_scale)
                 dw2 = ops.zeros((1, C, I), x)
                 ops.gemm_wgrad(dyg, h, dw2)
@@ -168,7 +168,6 @@ class ConvNeXtBlockFn(Function):
                 ops.gemm_wgrad(dh, xhat, dw1f)
                 db1 = ops.colsum_h16(dh)
                 dw1, dln_w, dln_b = ops.ln_fold_bwd(dw1f.view(I, C), w1, ln_w, ln_b, db1)
-                side.keepalive(dgamma, db2, dw2, dw1f, db1, dln_w, dln_b)
             return dx, ddw.reshape(C, 1, 7), ddb, dln_w, dln_b, dw1, db1, dw2.view(C, I), db2, dgamma, None, None, None
         z = z_or_out
         dyg, dgamma, db2 = ops.resid_bwd_prep(dout, z, gamma, pad_mask, row_scale, T)
@@ -236,15 +235,13 @@ class VariancePredictorFn(Function):
                                                                  ctx.drop_p, ctx.drop_seed + L - 1)
         grads[4 * (L - 1) + 2], grads[4 * (L - 1) + 3] = dln_w, dln_b
         dx = None
-        with ops.grad_side(g, g) as side:   # parameter gradients leave the critical path (the data-gradient chain g -> g_prev)
+        with ops.grad_side(g, g):   # parameter gradients leave the critical path (the data-gradient chain g -> g_prev)
             grads[4 * (L - 1) + 1] = ops.colsum_h16(g)
-            side.keepalive(grads[4 * (L - 1) + 1])
         for l in range(L - 1, -1, -1):
             cw = layer_params[4 * l]
             N, Cin, _ = cw.shape
-            with ops.grad_side(g, g, acts[l]) as side:
+            with ops.grad_side(g, g, acts[l]):
                 grads[4 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
-                side.keepalive(grads[4 * l])
             if l > 0:
                 lw_prev = layer_params[4 * (l - 1) + 2]
                 grads[4 * (l - 1) + 1] = ops.zeros((Cin,), g)             # conv bias gradient of layer l-1, summed in the epilogue
@@ -252,9 +249,8 @@ class VariancePredictorFn(Function):
                                          aux_in=pres[l - 1], ln_w=lw_prev, ln_eps=eps, dropout_p=ctx.drop_p,
                                          dropout_seed=ctx.drop_seed + l - 1, colsum=grads[4 * (l - 1) + 1], w_mn=True, tap_reverse=True,
                                          N=Cin)
-                with ops.grad_side(gy, gy, pres[l - 1]) as side:
+                with ops.grad_side(gy, gy, pres[l - 1]):
                     grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3] = ops.ln_param_grad(gy, pres[l - 1], lw_prev, eps)
-                    side.keepalive(grads[4 * (l - 1) + 2], grads[4 * (l - 1) + 3])
                 g = g_prev
             elif ctx.x_needs_grad:
                 dx, _, _ = ops.gemm(g, wps[0], epi=ops.EPI_BIAS, pad=k - 1 - pad, w_mn=True, tap_reverse=True, N=Cin)
@@ -298,16 +294,14 @@ class ConvStackFn(Function):
         grads: List[Optional[torch.Tensor]] = [None] * (2 * L)
         g = ops.to_h16(dout.contiguous())
         dx = None
-        with ops.grad_side(g, g) as side:
+        with ops.grad_side(g, g):
             grads[2 * (L - 1) + 1] = ops.colsum_h16(g)
-            side.keepalive(grads[2 * (L - 1) + 1])
         for l in range(L - 1, -1, -1):
             cw = params[2 * l]
             N, Cin, k = cw.shape
             pad = (k - 1) // 2
-            with ops.grad_side(g, g, acts[l]) as side:
+            with ops.grad_side(g, g, acts[l]):
                 grads[2 * l] = _conv_wgrad(g, acts[l], N, Cin, k, pad)
-                side.keepalive(grads[2 * l])
             if l > 0:
                 grads[2 * (l - 1) + 1] = ops.zeros((Cin,), g)             # bias gradient of layer l-1, summed in the epilogue
                 g, _, _ = ops.gemm(g, wps[l], epi=ops.EPI_RELU_BWD, pad=k - 1 - pad, aux_in=acts[l],

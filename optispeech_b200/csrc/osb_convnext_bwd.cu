@@ -39,7 +39,7 @@ struct BwdParams {
   const __half* pre;        // (B, T, I) saved GELU argument
   __half* dyg_out;          // (B, T, C)
   __half* dh_out;           // (B, T, I)
-  float* dxh_out;           // (B, T, C) gradient wrt the normalised dwconv output (pre-zeroed when nsplit > 1)
+  float* dxh_out;           // (nsplit, B, T, C) gradient wrt the normalised dwconv output: one partial sum per split
   int B, T, m_tiles, nsplit;
 };
 
@@ -317,13 +317,8 @@ convnext_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmW2, const __grid
       for (int v = 0; v < VPL; ++v) {
         const int c = v * 128 + lane * 4;
         const float4 d4 = *reinterpret_cast<const float4*>(stile + r * OLD + c);
-        if (p.nsplit == 1) {
-          *reinterpret_cast<float4*>(p.dxh_out + grow * C + c) = d4;
-        } else {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dxh_out + grow * C + c), "f"(d4.x), "f"(d4.y), "f"(d4.z),
-                       "f"(d4.w)
-                       : "memory");
-        }
+        // each split writes its own partial sum (plain stores: no zero fill, no atomics); osb_ln_dwconv_bwd adds them up
+        *reinterpret_cast<float4*>(p.dxh_out + (static_cast<long long>(split) * p.B * p.T + grow) * C + c) = d4;
       }
     }
   }
@@ -347,10 +342,6 @@ int launch_bwd(const void* w2_h16, const void* w1f_h16, const BwdParams& p, cuda
     cudaError_t e = cudaFuncSetAttribute(convnext_bwd_fused_kernel<C, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr = true;
-  }
-  if (p.nsplit > 1) {
-    cudaError_t e = cudaMemsetAsync(p.dxh_out, 0, static_cast<size_t>(p.B) * p.T * C * sizeof(float), stream);
-    if (e != cudaSuccess) return static_cast<int>(e);
   }
   convnext_bwd_fused_kernel<C, I><<<dim3(p.B * p.m_tiles, p.nsplit), BB_THREADS, Cfg::SMEM, stream>>>(tmW2, tmW1, p);
   count_launch();
@@ -379,7 +370,7 @@ __global__ void __launch_bounds__(LDB_WARPS * 32)
 ln_dwconv_bwd_kernel(const float* __restrict__ dxh, const __half* __restrict__ xhat, const float* __restrict__ rstd,
                      const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w /*(C,7)*/,
                      const uint8_t* __restrict__ pad_mask, float* __restrict__ dx, float* __restrict__ dparam /*(8,C)*/, int B, int T,
-                     int tiles_per_seq, int ntiles) {
+                     int tiles_per_seq, int ntiles, int nparts) {
   constexpr int C = 128 * VPL;
   extern __shared__ float ldb_smem[];
   float* sdd = ldb_smem;                 // [LDB_HR][C]
@@ -414,6 +405,10 @@ ln_dwconv_bwd_kernel(const float* __restrict__ dxh, const __half* __restrict__ x
         for (int v = 0; v < VPL; ++v) {
           const int c = v * 128 + lane * 4;
           g[i][v] = ok ? *reinterpret_cast<const float4*>(dxh + (base + t) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int part = 1; part < nparts && ok; ++part) {   // partial sums of the fused backward kernel's splits
+            const float4 e4 = *reinterpret_cast<const float4*>(dxh + (static_cast<long long>(part) * B * T + base + t) * C + c);
+            g[i][v].x += e4.x; g[i][v].y += e4.y; g[i][v].z += e4.z; g[i][v].w += e4.w;
+          }
           xh[i][v] = ok ? *reinterpret_cast<const uint2*>(xhat + (base + t) * C + c) : make_uint2(0u, 0u);
         }
       }
@@ -594,6 +589,15 @@ static int g_bwd_nsplit = 0;
 /* developer hook (not in the public header): force the intermediate-dimension split of the fused backward (0 = automatic) */
 extern "C" void osb_debug_set_bwd_nsplit(int n) { g_bwd_nsplit = n; }
 
+/* number of partial buffers osb_convnext_block_bwd writes for this shape (the caller sizes dxhat with it) */
+extern "C" int osb_convnext_block_bwd_parts(int32_t B, int32_t T, int32_t I) {
+  const int tiles = B * ((T + BB_M - 1) / BB_M);
+  const int nch = I / BB_NC;
+  int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > 4 ? 4 : 148 / tiles));
+  if (ns > nch / 2) ns = nch / 2;
+  return ns < 1 ? 1 : ns;
+}
+
 extern "C" int osb_convnext_block_bwd(const float* dout, const float* gamma, const float* row_scale, const uint8_t* pad_mask,
                                       const void* pre_h16, const void* w2_h16, const void* w1f_h16, void* dyg_h16, void* dh_h16,
                                       float* dxhat, int32_t B, int32_t T, int32_t C, int32_t I, void* stream) {
@@ -607,24 +611,18 @@ extern "C" int osb_convnext_block_bwd(const float* dout, const float* gamma, con
   p.pre = static_cast<const __half*>(pre_h16);
   p.dyg_out = static_cast<__half*>(dyg_h16); p.dh_out = static_cast<__half*>(dh_h16); p.dxh_out = dxhat;
   p.B = B; p.T = T; p.m_tiles = (T + BB_M - 1) / BB_M;
-  {
-    const int tiles = B * p.m_tiles;
-    const int nch = I / BB_NC;
-    int ns = g_bwd_nsplit > 0 ? g_bwd_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > 4 ? 4 : 148 / tiles));
-    if (ns > nch / 2) ns = nch / 2;
-    p.nsplit = ns < 1 ? 1 : ns;
-  }
+  p.nsplit = osb_convnext_block_bwd_parts(B, T, I);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (C == 256 && I == 1024) return launch_bwd<256, 1024>(w2_h16, w1f_h16, p, s);
   if (C == 384 && I == 1152) return launch_bwd<384, 1152>(w2_h16, w1f_h16, p, s);
   return OSB_ERR_SHAPE;
 }
 
-extern "C" int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const float* rstd, const float* dout, const float* x,
-                                 const float* dw_w, const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T, int32_t C,
-                                 void* stream) {
+extern "C" int osb_ln_dwconv_bwd(const float* dxhat, int32_t nparts, const void* xhat_h16, const float* rstd, const float* dout,
+                                 const float* x, const float* dw_w, const uint8_t* pad_mask, float* dx, float* dparam, int32_t B, int32_t T,
+                                 int32_t C, void* stream) {
   OSB_REQUIRE(dxhat && xhat_h16 && rstd && dout && x && dw_w && dx && dparam, OSB_ERR_ARG);
-  OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384), OSB_ERR_SHAPE);
+  OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384) && nparts >= 1 && nparts <= 16, OSB_ERR_SHAPE);
   OSB_REQUIRE((reinterpret_cast<uintptr_t>(dparam) & 15) == 0, OSB_ERR_ALIGN);
   const int tiles_per_seq = (T + LDB_TT - 1) / LDB_TT;
   const long long ntiles = static_cast<long long>(B) * tiles_per_seq;
@@ -639,8 +637,8 @@ extern "C" int osb_ln_dwconv_bwd(const float* dxhat, const void* xhat_h16, const
     if (e != cudaSuccess) return static_cast<int>(e);
     attr = true;
   }
-  if (C == 256) ln_dwconv_bwd_kernel<2><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles));
-  else ln_dwconv_bwd_kernel<3><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles));
+  if (C == 256) ln_dwconv_bwd_kernel<2><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles), nparts);
+  else ln_dwconv_bwd_kernel<3><<<blocks, LDB_WARPS * 32, smem, s>>>(dxhat, xh, rstd, dout, x, dw_w, pad_mask, dx, dparam, B, T, tiles_per_seq, static_cast<int>(ntiles), nparts);
   count_launch();
   return launch_status();
 }

@@ -157,9 +157,15 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     s_dur.wait_stream(main)
     with torch.cuda.stream(s_dur):
         duration_hat = gen.duration_predictor(h.detach(), in_pad)   # detached input: meets the rest only at the loss
-    te = am.encode_text(h)
-    main.wait_stream(s_feat)
-    log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
+    # text-side alignment convs + attention on their own stream: in the backward pass (autograd replays a node on its forward
+    # stream) the attention gradient chain then runs next to the predictors' instead of queueing behind them on the main stream
+    s_attn = ops.side_stream(dev, ops.ATTN_SLOT)
+    s_attn.wait_stream(main)
+    s_attn.wait_stream(s_feat)
+    with torch.cuda.stream(s_attn):
+        te = am.encode_text(h)
+        log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
+    main.wait_stream(s_attn)
     # The forward-sum loss only meets the rest of the step at the final sum: its sequential recursion (one CTA per sample)
     # runs on a side stream, next to the alignment search, the predictors and the decoder.
     fs_side = ops.side_stream(dev)

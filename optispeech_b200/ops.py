@@ -38,6 +38,7 @@ def step_counter(device) -> torch.Tensor:
 
 
 _SIDE_STREAMS = {}
+ATTN_SLOT = 10   # text-side alignment convs + attention: own high-priority stream (its backward then overlaps the predictors')
 SIDE_STREAMS_ENABLED = True   # False: every branch stays on the current stream (per-kernel timing passes want serial execution)
 
 
@@ -54,7 +55,7 @@ def side_stream(device, slot: int = 0) -> "torch.cuda.Stream":
         # their full-machine kernels (216 CTAs x 224 KB of shared memory) otherwise hold every SM while the small kernels of
         # the critical path wait for a free one (timeline of the captured step, round 2).  A captured kernel node inherits
         # the priority of the stream it was captured on.
-        prio = -1 if slot <= 4 else 0
+        prio = -1 if (slot <= 4 or slot == ATTN_SLOT) else 0
         s = torch.cuda.Stream(device=device, priority=prio)
         _SIDE_STREAMS[key] = s
     return s
@@ -534,7 +535,8 @@ def convnext_block_bwd(dout, gamma, row_scale, pad_mask, pre, w2_h16, w1f_h16):
     I = pre.shape[-1]
     dyg = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float16)
     dh = torch.empty((B, T, I), device=dout.device, dtype=torch.float16)
-    dxh = torch.empty((B, T, Cc), device=dout.device, dtype=torch.float32)
+    parts = int(_lib.load().osb_convnext_block_bwd_parts(B, T, I))
+    dxh = torch.empty((parts, B, T, Cc), device=dout.device, dtype=torch.float32)   # one partial sum per split of I
     _lib.check(_lib.load().osb_convnext_block_bwd(_ptr(_f32(dout)), _ptr(_f32(gamma)), _ptr(row_scale), _ptr(pad_mask), _ptr(pre), _ptr(w2_h16),
                                                   _ptr(w1f_h16), _ptr(dyg), _ptr(dh), _ptr(dxh), B, T, Cc, I, _stream()),
                "osb_convnext_block_bwd")
@@ -546,7 +548,8 @@ def ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w, pad_mask):
     B, T, Cc = x.shape
     dx = torch.empty_like(x)
     dparam = _zeros((8, Cc), x)      # rows 0-6: the 7 taps (tap-major), row 7: the bias
-    _lib.check(_lib.load().osb_ln_dwconv_bwd(_ptr(_f32(dxh)), _ptr(xhat), _ptr(_f32(rstd)), _ptr(_f32(dout)), _ptr(_f32(x)), _ptr(_f32(dw_w)),
+    nparts = dxh.shape[0] if dxh.dim() == 4 else 1
+    _lib.check(_lib.load().osb_ln_dwconv_bwd(_ptr(_f32(dxh)), nparts, _ptr(xhat), _ptr(_f32(rstd)), _ptr(_f32(dout)), _ptr(_f32(x)), _ptr(_f32(dw_w)),
                                              _ptr(pad_mask), _ptr(dx), _ptr(dparam), B, T, Cc, _stream()), "osb_ln_dwconv_bwd")
     return dx, dparam[:7].t(), dparam[7]
 
@@ -571,7 +574,11 @@ GRAD_SIDE_SLOTS = (6, 7, 8, 9)
 class grad_side:
     """Context manager: run the enclosed weight-gradient work on a side stream forked from the current one.  The side stream
     is joined (and the tensors it reads released) when the running backward pass finishes — a callback queued on the autograd
-    engine — or explicitly by join_grad_streams().  Inside a CUDA-graph capture the fork / join become graph dependencies."""
+    engine — or explicitly by join_grad_streams().  Inside a CUDA-graph capture the fork / join become graph dependencies.
+
+    Pass the INPUT tensors of the enclosed work (allocated on the forking stream) to be kept alive until the join.  Do NOT
+    hold extra references to the gradients it produces: autograd's AccumulateGrad then takes them over as they are; with
+    another reference alive it would clone them — on the forking stream, unordered with the side stream that writes them."""
 
     def __init__(self, like: torch.Tensor, *keep):
         self.dev = like.device
