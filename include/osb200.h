@@ -289,6 +289,12 @@ int osb_variance_embed_bwd(const float* dout, const float* val, const uint8_t* p
 int osb_embed_text_bwd(const float* dout, const int64_t* ids, const float* inv_freq, float* dtable, float* dscale, int32_t B,
                        int32_t T, int32_t dim, int32_t n_vocab, int32_t padding_idx, void* stream);
 
+/* osb_gemm_wgrad for a strided convolution (stride <= 4): dw[tap,n,k] += sum_{b,t<T} dy[b,t,n] * a[b, t*stride + tap - pad, k]
+ * with a fp16 (B, T_in, lda).  The strided rows are a TMA traversal stride (no im2col copy).  Weight gradient of the period
+ * discriminators' (5,1)/(3,1) convolutions (vocoder/wavenext/disc/_discriminators.py:52-58). */
+int osb_gemm_wgrad_strided(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t T_in,
+                           int32_t N, int32_t K, int32_t taps, int32_t pad, int32_t stride, void* stream);
+
 /* Batched form of osb_gemm_wgrad: dw[b, n, k] += sum_t dy[b, t, n] * a[b, t, k]  (A^T B per batch; dw is (B, N, K)). */
 int osb_gemm_wgrad_batched(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N,
                            int32_t K, void* stream);

@@ -122,6 +122,7 @@ def load() -> C.CDLL:
         "osb_embed_text_bwd": [P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_mas": [P, P, P, P, P, I32, I32, I32, P],
         "osb_gemm_wgrad_batched": [P, I64, P, I64, P, I32, I32, I32, I32, P],
+        "osb_gemm_wgrad_strided": [P, I64, P, I64, P, I32, I32, I32, I32, I32, I32, I32, I32, P],
         "osb_rownorm_sq": [P, P, I64, I32, P],
         "osb_forward_sum": [P, P, P, F, P, P, P, I32, I32, I32, P],
         "osb_beta_binomial_prior": [P, I64, P, P, P, I32, I32, I32, P],

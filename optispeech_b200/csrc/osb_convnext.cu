@@ -263,8 +263,33 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           }
         }
         mbar_wait(x_full, pass & 1);
-#pragma unroll 2
-        for (int rl = ww * ROWS_PER_WARP; rl < (ww + 1) * ROWS_PER_WARP; ++rl) {   // rl: row inside the pass; staged rows rl .. rl+6
+        // The staged rows are read ONCE each into a 7-row register window (fully unrolled: the window rotates at compile time);
+        // for C = 256 the 7 x C taps of this lane's channels also live in registers — re-reading taps and rows from shared
+        // memory for every output row made the prologue shared-memory-bandwidth bound (28 LDS.128 per row and warp, 8 warps:
+        // ~14k cycles per tile, clock64 timeline round 2).
+        constexpr bool kTapsInRegs = VPL <= 2;
+        float4 tw[kTapsInRegs ? 7 : 1][VPL], tb[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          tb[v] = *reinterpret_cast<const float4*>(s_db + v * 128 + lane * 4);
+          if constexpr (kTapsInRegs) {
+#pragma unroll
+            for (int jx = 0; jx < 7; ++jx) tw[jx][v] = *reinterpret_cast<const float4*>(s_dw + jx * C + v * 128 + lane * 4);
+          }
+        }
+        auto ld_row = [&](int rr, float4 (&dst)[VPL]) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            dst[v] = *reinterpret_cast<const float4*>(sX + (v * 4 + xbox) * Cfg::XB_STRIDE + rr * 128 + ((xchunk ^ (rr & 7)) << 4));
+        };
+        const int rl0 = ww * ROWS_PER_WARP;
+        float4 win[7][VPL];           // slot (rl + jx) % 7 holds staged row rl + jx
+#pragma unroll
+        for (int jx = 0; jx < 6; ++jx) ld_row(rl0 + jx, win[jx]);
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_WARP; ++i) {
+          const int rl = rl0 + i;      // row inside the pass; staged rows rl .. rl+6
+          ld_row(rl + 6, win[(i + 6) % 7]);
           const int r = pass * Cfg::RP + rl;
           const int t = t0 + r;
           float4 d[VPL];
@@ -272,13 +297,13 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             const int c = v * 128 + lane * 4;
-            const uint8_t* xb = sX + (v * 4 + xbox) * Cfg::XB_STRIDE;
-            float4 acc = *reinterpret_cast<const float4*>(s_db + c);
+            float4 acc = tb[v];
 #pragma unroll
             for (int jx = 0; jx < 7; ++jx) {
-              const int rr = rl + jx;
-              const float4 xv = *reinterpret_cast<const float4*>(xb + rr * 128 + ((xchunk ^ (rr & 7)) << 4));
-              const float4 wj = *reinterpret_cast<const float4*>(s_dw + jx * C + c);
+              const float4 xv = win[(i + jx) % 7][v];
+              float4 wj;
+              if constexpr (kTapsInRegs) wj = tw[jx][v];
+              else wj = *reinterpret_cast<const float4*>(s_dw + jx * C + c);
               acc.x = fmaf(wj.x, xv.x, acc.x);
               acc.y = fmaf(wj.y, xv.y, acc.y);
               acc.z = fmaf(wj.z, xv.z, acc.z);

@@ -1,0 +1,435 @@
+// osb_disc.cu — the non-GEMM kernels of the multi-period discriminators (reference vocoder/wavenext/disc/_discriminators.py:41-97):
+//
+//   A period discriminator views the waveform (reflect-padded at the tail to a multiple of the period p) as p interleaved
+//   sequences x_j[l] = wav[l*p + j] and runs (5,1)/(3,1) convolutions along l.  On this path every (signal, phase) pair is
+//   one channels-last sequence: activations are fp16 (NS*p, L, C), the layers with C_in >= 32 are tcgen05 implicit GEMMs
+//   (osb_gemm with a row stride, LeakyReLU epilogue), and this file holds what is left:
+//     mpd_first_*      layer 1 (C_in = 1): period split + reflect padding + 5-tap FIR + bias + LeakyReLU, and its backward
+//     mpd_post_*       conv_post (C_out = 1): 3-tap dot product over 1024 channels, and its backward
+//     lrelu_bwd        gradient gate of a LeakyReLU from the saved OUTPUT (the slope is positive: the sign survives)
+//     col2im_k5        data gradient of a strided convolution: gathers the per-tap products of one GEMM (rows_out x 5*C_in)
+//     l1_pair_*        feature-matching term mean|f_real - f_fake| and its gradient with respect to f_fake
+//   fp16 gradient tensors carry the caller's loss scale times DISC_GRAD_SCALE (the 1/numel factors of the hinge / feature-
+//   matching means would otherwise sit in the fp16 subnormal range); the kernels that produce fp32 results take the factor
+//   back out (`inv_scale`).
+#include "osb_host.h"
+#include "osb_ptx.cuh"
+
+namespace osb {
+namespace {
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+__device__ __forceinline__ void st_h8(__half* dst, const float (&v)[8]) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void ld_h8(const __half* src, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(src);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+// sample index of element l of phase j of the reflect-padded signal (F.pad(x, (0, n_pad), "reflect"): padded[T + i] = x[T - 2 - i])
+__device__ __forceinline__ long long wav_index(int l, int j, int p, int T) {
+  const long long w = static_cast<long long>(l) * p + j;
+  return w < T ? w : 2LL * T - 2 - w;
+}
+
+// ------------------------------------------------------------------------------------------
+// layer 1: out[(n*p + j), lo, c] = lrelu(b[c] + sum_k w[c,k] * x_j[3*lo + k - 2]),  c < 32 (columns 32..CP-1 are zero padding
+// so that the next layer's contraction is a whole 64-element k-block).  One thread = 8 channels of one output row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mpd_first_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ w /*(32,5)*/, const float* __restrict__ bias,
+                     __half* __restrict__ out, int NS, int T, int p, int L0, int L1, int CP, int stride, float slope) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = CP / 8;
+  const long long rows = static_cast<long long>(NS) * p * L1;
+  if (i >= rows * groups) return;
+  const int cg = static_cast<int>(i % groups);
+  const long long row = i / groups;
+  const int lo = static_cast<int>(row % L1);
+  const int seq = static_cast<int>(row / L1);
+  const int n = seq / p, j = seq % p;
+  float v[8];
+  if (cg * 8 >= 32) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  } else {
+    float x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int l = stride * lo + k - 2;
+      x[k] = (l >= 0 && l < L0) ? wav[static_cast<long long>(n) * T + wav_index(l, j, p, T)] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = cg * 8 + q;
+      float acc = bias[c];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc = fmaf(w[c * 5 + k], x[k], acc);
+      v[q] = lrelu(acc, slope);
+    }
+  }
+  st_h8(out + row * CP + cg * 8, v);
+}
+
+// d wav[n, widx] += inv_scale * sum_{k, lo: 3 lo + k - 2 = l} sum_c w[c,k] * g[(n*p+j), lo, c]     (g already gated)
+// one thread per (seq, l); at most two (k, lo) pairs hit an input position; reflected positions fold onto T-2-i: atomics.
+__global__ void __launch_bounds__(256)
+mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, float* __restrict__ dwav, int NS, int n_first, int T, int p,
+                    int L0, int L1, int CP, int stride, float inv_scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NS - n_first) * p * L0;
+  if (i >= total) return;
+  const int l = static_cast<int>(i % L0);
+  const int seq = static_cast<int>(i / L0) + n_first * p;
+  const int n = seq / p, j = seq % p;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int num = l + 2 - k;
+    if (num < 0 || num % stride != 0) continue;
+    const int lo = num / stride;
+    if (lo >= L1) continue;
+    const __half* gr = g + (static_cast<long long>(seq) * L1 + lo) * CP;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      float gv[8];
+      ld_h8(gr + c0, gv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(w[(c0 + q) * 5 + k], gv[q], acc);
+    }
+  }
+  if (acc != 0.f) atomicAdd(dwav + static_cast<long long>(n) * T + wav_index(l, j, p, T), acc * inv_scale);
+}
+
+// dW1[c,k] += inv_scale * sum g[row, c] * x_j[3 lo + k - 2] ; db1[c] += inv_scale * sum g[row, c].  Block partial sums in
+// shared memory (32 channels x 6), one atomic per element and block.
+__global__ void __launch_bounds__(256)
+mpd_first_dw_kernel(const __half* __restrict__ g, const float* __restrict__ wav, float* __restrict__ dw /*(32,5)*/, float* __restrict__ db,
+                    int NS, int T, int p, int L0, int L1, int CP, int stride, float inv_scale, long long rows_per_block) {
+  __shared__ float part[8][32 * 6];
+  const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;   // lane = channel
+  const long long rows = static_cast<long long>(NS) * p * L1;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float aw[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, ab = 0.f;
+  for (long long row = r0 + wip; row < r1; row += 8) {
+    const int lo = static_cast<int>(row % L1);
+    const int seq = static_cast<int>(row / L1);
+    const int n = seq / p, j = seq % p;
+    const float gv = __half2float(g[row * CP + lane]);
+    ab += gv;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int l = stride * lo + k - 2;
+      const float x = (l >= 0 && l < L0) ? wav[static_cast<long long>(n) * T + wav_index(l, j, p, T)] : 0.f;   // warp-uniform address
+      aw[k] = fmaf(gv, x, aw[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) part[wip][lane * 6 + k] = aw[k];
+  part[wip][lane * 6 + 5] = ab;
+  __syncthreads();
+  if (threadIdx.x < 32 * 6) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q][threadIdx.x];
+    const int c = threadIdx.x / 6, k = threadIdx.x % 6;
+    if (k < 5) atomicAdd(dw + c * 5 + k, s * inv_scale);
+    else atomicAdd(db + c, s * inv_scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv_post: out[seq, l] = b + sum_k sum_c w[c,k] * x[seq, l + k - 1, c]     (C = 1024, k = 3).  One warp per output.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mpd_post_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ w /*(C,3)*/, const float* __restrict__ bias, float* __restrict__ out,
+                    int NSEQ, int L, int C) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(NSEQ) * L) return;
+  const int lane = threadIdx.x & 31;
+  const int l = static_cast<int>(row % L);
+  const long long seq = row / L;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int li = l + k - 1;
+    if (li < 0 || li >= L) continue;
+    const __half* xr = x + (seq * L + li) * C;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float xv[8];
+      ld_h8(xr + c0, xv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(w[(c0 + q) * 3 + k], xv[q], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + bias[0];
+}
+
+// dx[seq, l, c] = scale * sum_k w[c,k] * dout[seq, l - k + 1]   (fp16);  one thread = 8 channels of one row
+__global__ void __launch_bounds__(256)
+mpd_post_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w, __half* __restrict__ dx, int NSEQ, int L, int C, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = C / 8;
+  if (i >= static_cast<long long>(NSEQ) * L * groups) return;
+  const int cg = static_cast<int>(i % groups);
+  const long long row = i / groups;
+  const int l = static_cast<int>(row % L);
+  const long long seq = row / L;
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int lo = l - k + 1;
+    d[k] = (lo >= 0 && lo < L) ? dout[seq * L + lo] * scale : 0.f;
+  }
+  float v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = cg * 8 + q;
+    v[q] = w[c * 3 + 0] * d[0] + w[c * 3 + 1] * d[1] + w[c * 3 + 2] * d[2];
+  }
+  st_h8(dx + row * C + cg * 8, v);
+}
+
+// dw[c,k] += sum_{seq,l} dout[seq,l] * x[seq, l+k-1, c] ; db += sum dout.   Thread = 8 channels; rows strided over blocks.
+__global__ void __launch_bounds__(128)
+mpd_post_dw_kernel(const float* __restrict__ dout, const __half* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int NSEQ, int L,
+                   int C, long long rows_per_block) {
+  const int cg = threadIdx.x;             // C / 8 == blockDim.x == 128
+  const long long rows = static_cast<long long>(NSEQ) * L;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float aw[8][3];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) aw[q][0] = aw[q][1] = aw[q][2] = 0.f;
+  float ab = 0.f;
+  for (long long row = r0; row < r1; ++row) {   // row = the INPUT row (seq, li); it meets dout at l = li - k + 1
+    const int li = static_cast<int>(row % L);
+    const long long seq = row / L;
+    float xv[8];
+    ld_h8(x + row * C + cg * 8, xv);
+    ab += dout[row];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int l = li - k + 1;
+      const float d = (l >= 0 && l < L) ? dout[seq * L + l] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) aw[q][k] = fmaf(d, xv[q], aw[q][k]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) atomicAdd(dw + (cg * 8 + q) * 3 + k, aw[q][k]);
+  if (cg == 0) atomicAdd(db, ab);
+}
+
+// g = dy * (y > 0 ? 1 : slope)      (fp16, 8 elements per thread)
+__global__ void __launch_bounds__(256)
+lrelu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, __half* __restrict__ g, long long n8, float slope) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float a[8], b[8];
+  ld_h8(dy + i * 8, a);
+  ld_h8(y + i * 8, b);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a[q] = b[q] > 0.f ? a[q] : a[q] * slope;
+  st_h8(g + i * 8, a);
+}
+
+// dx[seq, l, c] = sum_{k: (l + pad - k) % stride == 0, lo = (l + pad - k) / stride < L_out} col[seq, lo, k*C + c]     (k < taps)
+__global__ void __launch_bounds__(256)
+col2im_kernel(const __half* __restrict__ col, __half* __restrict__ dx, int NSEQ, int L_in, int L_out, int C, int taps, int pad, int stride) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = C / 8;
+  if (i >= static_cast<long long>(NSEQ) * L_in * groups) return;
+  const int cg = static_cast<int>(i % groups);
+  const long long row = i / groups;
+  const int l = static_cast<int>(row % L_in);
+  const long long seq = row / L_in;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  for (int k = 0; k < taps; ++k) {
+    const int num = l + pad - k;
+    if (num < 0 || num % stride != 0) continue;
+    const int lo = num / stride;
+    if (lo >= L_out) continue;
+    float v[8];
+    ld_h8(col + ((seq * L_out + lo) * taps + k) * C + cg * 8, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += v[q];
+  }
+  st_h8(dx + row * C + cg * 8, acc);
+}
+
+// sum |a - b| over n8*8 fp16 elements -> out[0] (atomic, one per block)
+__global__ void __launch_bounds__(256)
+l1_pair_fwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, float* __restrict__ out, long long n8) {
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    ld_h8(a + i * 8, x);
+    ld_h8(b + i * 8, y);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += fabsf(x[q] - y[q]);
+  }
+  s = warp_sum(s);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q];
+    atomicAdd(out, t);
+  }
+}
+
+// d b = coef[0] * sign(b - a)   (gradient of coef * sum|a - b| with respect to b), fp16
+__global__ void __launch_bounds__(256)
+l1_pair_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const float* __restrict__ coef, float scale, __half* __restrict__ db,
+                   long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float c = coef[0] * scale;
+  float x[8], y[8];
+  ld_h8(a + i * 8, x);
+  ld_h8(b + i * 8, y);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) x[q] = y[q] > x[q] ? c : (y[q] < x[q] ? -c : 0.f);
+  st_h8(db + i * 8, x);
+}
+
+inline unsigned grid_for(long long n, int block) { return static_cast<unsigned>((n + block - 1) / block); }
+
+}  // namespace
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" int osb_mpd_first_fwd(const float* wav, const float* w, const float* bias, void* out_h16, int32_t NS, int32_t T, int32_t period,
+                                 int32_t L1, int32_t CP, int32_t stride, float slope, void* stream) {
+  OSB_REQUIRE(wav && w && bias && out_h16, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && T > 1 && period > 0 && L1 > 0 && CP >= 32 && CP % 8 == 0 && stride >= 1, OSB_ERR_SHAPE);
+  const int L0 = (T + period - 1) / period;
+  OSB_REQUIRE(L0 * period - T < T - 1, OSB_ERR_SHAPE);   // reflect padding needs n_pad < T
+  const long long n = static_cast<long long>(NS) * period * L1 * (CP / 8);
+  mpd_first_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(wav, w, bias, static_cast<__half*>(out_h16), NS, T, period, L0,
+                                                                                       L1, CP, stride, slope);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mpd_first_bwd(const void* g_h16, const float* wav, const float* w, float* dwav, float* dw, float* db, int32_t NS,
+                                 int32_t n_first, int32_t T, int32_t period, int32_t L1, int32_t CP, int32_t stride, float inv_scale,
+                                 void* stream) {
+  OSB_REQUIRE(g_h16 && wav && w, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && n_first >= 0 && n_first <= NS && T > 1 && period > 0 && L1 > 0, OSB_ERR_SHAPE);
+  const int L0 = (T + period - 1) / period;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __half* g = static_cast<const __half*>(g_h16);
+  int launched = 0;
+  if (dwav != nullptr && n_first < NS) {   // signals [n_first, NS) receive a waveform gradient (the generated half)
+    const long long n = static_cast<long long>(NS - n_first) * period * L0;
+    mpd_first_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(g, w, dwav, NS, n_first, T, period, L0, L1, CP, stride, inv_scale);
+    ++launched;
+  }
+  if (dw != nullptr && db != nullptr) {
+    const long long rows = static_cast<long long>(NS) * period * L1;
+    long long blocks = (rows + 2047) / 2048;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    mpd_first_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(g, wav, dw, db, NS, T, period, L0, L1, CP, stride, inv_scale, rpb);
+    ++launched;
+  }
+  count_launch(launched);
+  return launch_status();
+}
+
+extern "C" int osb_mpd_post_fwd(const void* x_h16, const float* w, const float* bias, float* out, int32_t NSEQ, int32_t L, int32_t C,
+                                void* stream) {
+  OSB_REQUIRE(x_h16 && w && bias && out, OSB_ERR_ARG);
+  OSB_REQUIRE(NSEQ > 0 && L > 0 && C % 256 == 0, OSB_ERR_SHAPE);
+  const long long rows = static_cast<long long>(NSEQ) * L;
+  mpd_post_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), w, bias, out, NSEQ, L, C);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mpd_post_bwd(const float* dout, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NSEQ,
+                                int32_t L, int32_t C, float scale, void* stream) {
+  OSB_REQUIRE(dout && w, OSB_ERR_ARG);
+  OSB_REQUIRE(NSEQ > 0 && L > 0 && C == 1024, OSB_ERR_SHAPE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int launched = 0;
+  if (dx_h16 != nullptr) {
+    const long long n = static_cast<long long>(NSEQ) * L * (C / 8);
+    mpd_post_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(dout, w, static_cast<__half*>(dx_h16), NSEQ, L, C, scale);
+    ++launched;
+  }
+  if (dw != nullptr && db != nullptr && x_h16 != nullptr) {
+    const long long rows = static_cast<long long>(NSEQ) * L;
+    long long blocks = (rows + 63) / 64;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    mpd_post_dw_kernel<<<static_cast<unsigned>(blocks), 128, 0, s>>>(dout, static_cast<const __half*>(x_h16), dw, db, NSEQ, L, C, rpb);
+    ++launched;
+  }
+  count_launch(launched);
+  return launch_status();
+}
+
+extern "C" int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t n, float slope, void* stream) {
+  OSB_REQUIRE(dy && y && g, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0 && n % 8 == 0, OSB_ERR_SHAPE);
+  lrelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                                    static_cast<__half*>(g), n / 8, slope);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_col2im_h16(const void* col, void* dx, int32_t NSEQ, int32_t L_in, int32_t L_out, int32_t C, int32_t taps, int32_t pad,
+                              int32_t stride, void* stream) {
+  OSB_REQUIRE(col && dx, OSB_ERR_ARG);
+  OSB_REQUIRE(NSEQ > 0 && L_in > 0 && L_out > 0 && C % 8 == 0 && taps > 0 && stride >= 1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NSEQ) * L_in * (C / 8);
+  col2im_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(col), static_cast<__half*>(dx), NSEQ, L_in,
+                                                                              L_out, C, taps, pad, stride);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_l1_pair_fwd(const void* a_h16, const void* b_h16, float* out_sum, int64_t n, void* stream) {
+  OSB_REQUIRE(a_h16 && b_h16 && out_sum, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0 && n % 8 == 0, OSB_ERR_SHAPE);
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  l1_pair_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(a_h16),
+                                                                                                static_cast<const __half*>(b_h16), out_sum, n / 8);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_l1_pair_bwd(const void* a_h16, const void* b_h16, const float* coef, float scale, void* db_h16, int64_t n, void* stream) {
+  OSB_REQUIRE(a_h16 && b_h16 && coef && db_h16, OSB_ERR_ARG);
+  OSB_REQUIRE(n > 0 && n % 8 == 0, OSB_ERR_SHAPE);
+  l1_pair_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(a_h16), static_cast<const __half*>(b_h16),
+                                                                                      coef, scale, static_cast<__half*>(db_h16), n / 8);
+  count_launch();
+  return launch_status();
+}

@@ -866,6 +866,7 @@ struct WgradParams {
   int row_blocks_per_batch;  // ceil(T / 64)
   int splits;
   int per_batch;             // 1: one (N, K) output per batch (batched matmul A^T B), taps == 1
+  int a_stride;              // > 1: strided convolution — output row t pairs with input row t * a_stride + tap - pad
   float* dw;
 };
 
@@ -922,7 +923,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           tma_load_3d(sDy + c * (WG_ROWS * ROW_BYTES), &tmDy, &full_bar[s], n0 + c * 64, t0, b);
-          tma_load_3d(sA + c * (WG_ROWS * ROW_BYTES), &tmA, &full_bar[s], k0 + c * 64, t0 + tap - p.pad, b);
+          tma_load_3d(sA + c * (WG_ROWS * ROW_BYTES), &tmA, &full_bar[s], k0 + c * 64, t0 * p.a_stride + tap - p.pad, b);
         }
       }
     }
@@ -1234,7 +1235,7 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
 }
 
 static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N, int32_t K,
-                      int32_t taps, int32_t pad, int per_batch, void* stream_);
+                      int32_t taps, int32_t pad, int per_batch, void* stream_, int32_t a_stride = 1, int32_t T_in = 0);
 
 extern "C" int osb_gemm_wgrad(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
                               int32_t N, int32_t K, int32_t taps, int32_t pad, void* stream_) {
@@ -1246,8 +1247,14 @@ extern "C" int osb_gemm_wgrad_batched(const void* dy, int64_t ldy, const void* a
   return wgrad_impl(dy, ldy, a, lda, dw, B, T, N, K, 1, 0, 1, stream_);
 }
 
+extern "C" int osb_gemm_wgrad_strided(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T,
+                                      int32_t T_in, int32_t N, int32_t K, int32_t taps, int32_t pad, int32_t stride, void* stream_) {
+  OSB_REQUIRE(stride >= 1 && stride <= 4 && T_in > 0, OSB_ERR_SHAPE);
+  return wgrad_impl(dy, ldy, a, lda, dw, B, T, N, K, taps, pad, 0, stream_, stride, T_in);
+}
+
 static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, float* dw, int32_t B, int32_t T, int32_t N, int32_t K,
-                      int32_t taps, int32_t pad, int per_batch, void* stream_) {
+                      int32_t taps, int32_t pad, int per_batch, void* stream_, int32_t a_stride, int32_t T_in) {
   OSB_REQUIRE(dy != nullptr && a != nullptr && dw != nullptr, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0 && taps > 0, OSB_ERR_SHAPE);
   OSB_REQUIRE(ldy % 8 == 0 && lda % 8 == 0, OSB_ERR_ALIGN);
@@ -1257,10 +1264,14 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
   CUtensorMap tmDy, tmA;
   int rc = make_tmap_3d(&tmDy, dy, TMA_F16, N, T, B, ldy, static_cast<uint64_t>(T) * ldy, 64, WG_ROWS);
   if (rc != OSB_OK) return rc;
-  rc = make_tmap_3d(&tmA, a, TMA_F16, K, T, B, lda, static_cast<uint64_t>(T) * lda, 64, WG_ROWS);
+  if (a_stride > 1)   // the tensor map walks the INPUT rows (T_in per batch) with a traversal stride: 64 loaded rows per box
+    rc = make_tmap_3d(&tmA, a, TMA_F16, K, T_in, B, lda, static_cast<uint64_t>(T_in) * lda, 64, WG_ROWS * a_stride, a_stride);
+  else
+    rc = make_tmap_3d(&tmA, a, TMA_F16, K, T, B, lda, static_cast<uint64_t>(T) * lda, 64, WG_ROWS);
   if (rc != OSB_OK) return rc;
 
   WgradParams p;
+  p.a_stride = a_stride > 1 ? a_stride : 1;
   p.T = T; p.B = B; p.N = N; p.K = K; p.taps = taps; p.pad = pad;
   p.row_blocks_per_batch = (T + WG_ROWS - 1) / WG_ROWS;
   const int n_tiles = (N + WG_TILE - 1) / WG_TILE;

@@ -189,7 +189,7 @@ def test_graph_replay_gradients_equal_eager_gradients(cuda_device):
     spec = ModelSpec()
     A = _small_batch(spec, 3, 48, 200, seed=7, dev=cuda_device)
     buckets = []
-    for graph in (False, True):
+    for graph in (False, False, True):
         model = _fresh_model(spec, cuda_device)
         model.hparams.optimizer = partial(torch.optim.AdamW, lr=0.0, betas=[0.8, 0.99], weight_decay=0.0)
         model.cuda_graph = graph
@@ -199,20 +199,29 @@ def test_graph_replay_gradients_equal_eager_gradients(cuda_device):
         if graph:
             assert model._graphed is not None and model._graphed.replays >= 2
         b = model.optimizers()[0].buckets()[0]
-        buckets.append((b.flat_g.clone(), [tuple(p.shape) for p in b.params], list(b.offsets)))
+        names = {id(p): n for n, p in model.generator.named_parameters()}
+        buckets.append((b.flat_g.clone(), [(names[id(p)], tuple(p.shape)) for p in b.params], list(b.offsets)))
         if model._graphed is not None:
             model._graphed.release()
-    (ge, shapes, offs), (gg, shapes2, offs2) = buckets
+    (ge, shapes, offs), (ge2, _, _), (gg, shapes2, offs2) = buckets
     assert shapes == shapes2 and offs == offs2
-    worst, worst_at = 0.0, None
-    for shp, o in zip(shapes, offs):
-        n = int(np.prod(shp))
-        a, b = ge[o:o + n], gg[o:o + n]
-        rel = float((a - b).norm() / (a.norm() + 1e-20))
-        if rel > worst:
-            worst, worst_at = rel, shp
-    print(f"graph-replay vs eager gradient bucket: worst per-tensor relative difference {worst:.3e} at {worst_at}")
-    assert worst <= 2e-3   # fp32 atomics reorder the sums inside the weight-gradient kernels; a stale or missing gradient is O(1)
+
+    def worst_of(x, y):
+        worst, at = 0.0, None
+        for (name, shp), o in zip(shapes, offs):
+            n = int(np.prod(shp))
+            a, b = x[o:o + n], y[o:o + n]
+            rel = float((a - b).norm() / (a.norm() + 1e-20))
+            if rel > worst:
+                worst, at = rel, name
+        return worst, at
+
+    floor, floor_at = worst_of(ge, ge2)
+    worst, worst_at = worst_of(ge, gg)
+    print(f"gradient bucket, worst per-tensor relative difference: eager vs eager {floor:.3e} ({floor_at}); "
+          f"graph replay vs eager {worst:.3e} ({worst_at})")
+    # fp32 atomics reorder the sums inside the weight-gradient kernels (the run-to-run floor); a stale or missing gradient is O(1)
+    assert worst <= max(3.0 * floor, 2e-3) and worst < 0.05
 
 
 def test_checkpoint_round_trip_resumes_optimizer_state(cuda_device, tmp_path):
