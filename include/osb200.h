@@ -518,6 +518,41 @@ int osb_ln_dwconv_bwd(const float* dxhat /*(nparts,B,T,C)*/, int32_t nparts, con
 int osb_resid_param_grad(const float* dout, const float* out, const float* x, const float* gamma, const uint8_t* pad_mask,
                          const float* row_scale, float* dgamma, float* db2, int64_t rows, int32_t T, int32_t C, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-period discriminator (osb_disc.cu) — reference vocoder/wavenext/disc/_discriminators.py:41-97
+ *
+ * Layout.  A period discriminator sees the waveform as `period` interleaved sequences x_j[l] = wav[l*period + j] (after the
+ * reflect padding of the tail to a multiple of the period, :66-70).  All NSEQ = NS*period sequences of a layer share one flat
+ * fp16 matrix (NSEQ * P rows, C columns): a sequence owns P consecutive rows, its L valid rows first, zeros after.  With
+ * P_5 = P_4 = L_4 + 2 and P_i = 3 * P_(i+1) the zero tail doubles as convolution padding and a layer is one osb_gemm call with
+ * row_stride 3 (or 1), OSB_FLAG_LRELU and a keep mask on the gap rows.
+ * fp16 gradient tensors carry the caller's loss scale times an extra power of two; entry points producing fp32 gradients take
+ * `inv_scale` to remove it.
+ * ------------------------------------------------------------------------------------- */
+/* Layer 1 (Conv2d(1, 32, (5,1), (stride,1), padding (2,0)) + LeakyReLU, :52): out (NS*period*P1, CP) fp16, columns >= 32 zero. */
+int osb_mpd_first_fwd(const float* wav /*(NS,T)*/, const float* w /*(32,5)*/, const float* bias, void* out_h16, int32_t NS, int32_t T,
+                      int32_t period, int32_t L1, int32_t P1, int32_t CP, int32_t stride, float slope, void* stream);
+/* Its backward from the gated gradient g (same layout as out): dwav (NS,T) += (reflected positions fold back), dw (32,5) +=,
+ * db (32) +=; any of dwav / (dw, db) may be NULL. */
+int osb_mpd_first_bwd(const void* g_h16, const float* wav, const float* w, float* dwav, float* dw, float* db, int32_t NS, int32_t T,
+                      int32_t period, int32_t L1, int32_t P1, int32_t CP, int32_t stride, float inv_scale, void* stream);
+/* conv_post (Conv2d(1024, 1, (3,1), padding (1,0)), :62): score (NS, L*period) fp32 in the reference's flatten order l*period + j. */
+int osb_mpd_post_fwd(const void* x_h16, const float* w /*(C,3)*/, const float* bias, float* score, int32_t NSEQ, int32_t period, int32_t L,
+                     int32_t P, int32_t C, void* stream);
+/* dx (NSEQ*P, C) fp16 = scale * conv_post^T(dscore); dw (C,3) +=, db (1) += (unscaled; NULL to skip either part). */
+int osb_mpd_post_bwd(const float* dscore, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NSEQ,
+                     int32_t period, int32_t L, int32_t P, int32_t C, float scale, void* stream);
+/* g = dy * (y > 0 ? 1 : slope) on the valid rows (row % P < L), 0 on the gap rows — LeakyReLU backward from the saved output. */
+int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t rows, int32_t C, int32_t P, int32_t L, float slope, void* stream);
+/* Data gradient of a strided convolution from the per-tap products of one GEMM: col (rows_out, taps*C) -> dx (rows_in, C),
+ * dx[r] = sum_{tap: (r + pad - tap) % stride == 0} col[(r + pad - tap) / stride, j(tap)*C : +C], j(tap) = taps-1-tap if `reversed`. */
+int osb_col2im_h16(const void* col, void* dx, int64_t rows_in, int64_t rows_out, int32_t C, int32_t taps, int32_t pad, int32_t stride,
+                   int32_t reversed, void* stream);
+/* Feature-matching term (disc/loss.py:67-85): out_sum[0] += sum |a - b| over n fp16 elements; and its gradient with respect
+ * to b: db = coef[0] * scale * sign(b - a). */
+int osb_l1_pair_fwd(const void* a_h16, const void* b_h16, float* out_sum, int64_t n, void* stream);
+int osb_l1_pair_bwd(const void* a_h16, const void* b_h16, const float* coef, float scale, void* db_h16, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

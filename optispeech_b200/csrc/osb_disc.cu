@@ -2,8 +2,11 @@
 //
 //   A period discriminator views the waveform (reflect-padded at the tail to a multiple of the period p) as p interleaved
 //   sequences x_j[l] = wav[l*p + j] and runs (5,1)/(3,1) convolutions along l.  On this path every (signal, phase) pair is
-//   one channels-last sequence: activations are fp16 (NS*p, L, C), the layers with C_in >= 32 are tcgen05 implicit GEMMs
-//   (osb_gemm with a row stride, LeakyReLU epilogue), and this file holds what is left:
+//   one channels-last sequence and ALL sequences of a layer live in one flat fp16 matrix (NSEQ * P_i rows, C_i columns): a
+//   sequence owns P_i consecutive rows, its L_i valid rows first, the rest zero.  With P_5 = P_4 = L_4 + 2 and P_i = 3 P_{i+1}
+//   for the stride-3 layers, the zero tail of one sequence is the convolution padding of the next, and every layer is ONE
+//   implicit GEMM over the flat matrix (osb_gemm with a row stride, LeakyReLU epilogue, gap rows re-zeroed by the keep mask)
+//   with full 128-row tiles, whatever the period.  This file holds what is left:
 //     mpd_first_*      layer 1 (C_in = 1): period split + reflect padding + 5-tap FIR + bias + LeakyReLU, and its backward
 //     mpd_post_*       conv_post (C_out = 1): 3-tap dot product over 1024 channels, and its backward
 //     lrelu_bwd        gradient gate of a LeakyReLU from the saved OUTPUT (the slope is positive: the sign survives)
@@ -51,18 +54,18 @@ __device__ __forceinline__ long long wav_index(int l, int j, int p, int T) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mpd_first_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ w /*(32,5)*/, const float* __restrict__ bias,
-                     __half* __restrict__ out, int NS, int T, int p, int L0, int L1, int CP, int stride, float slope) {
+                     __half* __restrict__ out, int NS, int T, int p, int L0, int L1, int P1, int CP, int stride, float slope) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int groups = CP / 8;
-  const long long rows = static_cast<long long>(NS) * p * L1;
+  const long long rows = static_cast<long long>(NS) * p * P1;
   if (i >= rows * groups) return;
   const int cg = static_cast<int>(i % groups);
   const long long row = i / groups;
-  const int lo = static_cast<int>(row % L1);
-  const int seq = static_cast<int>(row / L1);
+  const int lo = static_cast<int>(row % P1);
+  const int seq = static_cast<int>(row / P1);
   const int n = seq / p, j = seq % p;
   float v[8];
-  if (cg * 8 >= 32) {
+  if (cg * 8 >= 32 || lo >= L1) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = 0.f;
   } else {
@@ -87,13 +90,13 @@ mpd_first_fwd_kernel(const float* __restrict__ wav, const float* __restrict__ w 
 // d wav[n, widx] += inv_scale * sum_{k, lo: 3 lo + k - 2 = l} sum_c w[c,k] * g[(n*p+j), lo, c]     (g already gated)
 // one thread per (seq, l); at most two (k, lo) pairs hit an input position; reflected positions fold onto T-2-i: atomics.
 __global__ void __launch_bounds__(256)
-mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, float* __restrict__ dwav, int NS, int n_first, int T, int p,
-                    int L0, int L1, int CP, int stride, float inv_scale) {
+mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, float* __restrict__ dwav, int NS, int T, int p,
+                    int L0, int L1, int P1, int CP, int stride, float inv_scale) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(NS - n_first) * p * L0;
+  const long long total = static_cast<long long>(NS) * p * L0;
   if (i >= total) return;
   const int l = static_cast<int>(i % L0);
-  const int seq = static_cast<int>(i / L0) + n_first * p;
+  const int seq = static_cast<int>(i / L0);
   const int n = seq / p, j = seq % p;
   float acc = 0.f;
 #pragma unroll
@@ -102,7 +105,7 @@ mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, f
     if (num < 0 || num % stride != 0) continue;
     const int lo = num / stride;
     if (lo >= L1) continue;
-    const __half* gr = g + (static_cast<long long>(seq) * L1 + lo) * CP;
+    const __half* gr = g + (static_cast<long long>(seq) * P1 + lo) * CP;
 #pragma unroll
     for (int c0 = 0; c0 < 32; c0 += 8) {
       float gv[8];
@@ -118,16 +121,17 @@ mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, f
 // shared memory (32 channels x 6), one atomic per element and block.
 __global__ void __launch_bounds__(256)
 mpd_first_dw_kernel(const __half* __restrict__ g, const float* __restrict__ wav, float* __restrict__ dw /*(32,5)*/, float* __restrict__ db,
-                    int NS, int T, int p, int L0, int L1, int CP, int stride, float inv_scale, long long rows_per_block) {
+                    int NS, int T, int p, int L0, int L1, int P1, int CP, int stride, float inv_scale, long long rows_per_block) {
   __shared__ float part[8][32 * 6];
   const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;   // lane = channel
-  const long long rows = static_cast<long long>(NS) * p * L1;
+  const long long rows = static_cast<long long>(NS) * p * P1;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float aw[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, ab = 0.f;
   for (long long row = r0 + wip; row < r1; row += 8) {
-    const int lo = static_cast<int>(row % L1);
-    const int seq = static_cast<int>(row / L1);
+    const int lo = static_cast<int>(row % P1);
+    if (lo >= L1) continue;
+    const int seq = static_cast<int>(row / P1);
     const int n = seq / p, j = seq % p;
     const float gv = __half2float(g[row * CP + lane]);
     ab += gv;
@@ -153,22 +157,23 @@ mpd_first_dw_kernel(const __half* __restrict__ g, const float* __restrict__ wav,
 }
 
 // ------------------------------------------------------------------------------------------
-// conv_post: out[seq, l] = b + sum_k sum_c w[c,k] * x[seq, l + k - 1, c]     (C = 1024, k = 3).  One warp per output.
+// conv_post: score[n, l*p + j] = b + sum_k sum_c w[c,k] * x[seq*P + l + k - 1, c]   (seq = n*p + j, C = 1024, k = 3; the rows
+// before / after a sequence are zero or out of range).  One warp per output.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mpd_post_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ w /*(C,3)*/, const float* __restrict__ bias, float* __restrict__ out,
-                    int NSEQ, int L, int C) {
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= static_cast<long long>(NSEQ) * L) return;
+                    int NSEQ, int p, int L, int P, int C) {
+  const long long o = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (o >= static_cast<long long>(NSEQ) * L) return;
   const int lane = threadIdx.x & 31;
-  const int l = static_cast<int>(row % L);
-  const long long seq = row / L;
+  const int l = static_cast<int>(o % L);
+  const long long seq = o / L;
   float acc = 0.f;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int li = l + k - 1;
     if (li < 0 || li >= L) continue;
-    const __half* xr = x + (seq * L + li) * C;
+    const __half* xr = x + (seq * P + li) * C;
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
       float xv[8];
       ld_h8(xr + c0, xv);
@@ -177,56 +182,66 @@ mpd_post_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ w /*
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[row] = acc + bias[0];
+  if (lane == 0) out[(seq / p) * (static_cast<long long>(L) * p) + static_cast<long long>(l) * p + (seq % p)] = acc + bias[0];
 }
 
-// dx[seq, l, c] = scale * sum_k w[c,k] * dout[seq, l - k + 1]   (fp16);  one thread = 8 channels of one row
+__device__ __forceinline__ float score_grad(const float* dout, long long seq, int l, int p, int L) {
+  return dout[(seq / p) * (static_cast<long long>(L) * p) + static_cast<long long>(l) * p + (seq % p)];
+}
+
+// dx[seq*P + l, c] = scale * sum_k w[c,k] * dscore[seq, l - k + 1]   (fp16, zero on the gap rows);  one thread = 8 channels of one row
 __global__ void __launch_bounds__(256)
-mpd_post_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w, __half* __restrict__ dx, int NSEQ, int L, int C, float scale) {
+mpd_post_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w, __half* __restrict__ dx, int NSEQ, int p, int L, int P, int C,
+                   float scale) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int groups = C / 8;
-  if (i >= static_cast<long long>(NSEQ) * L * groups) return;
+  if (i >= static_cast<long long>(NSEQ) * P * groups) return;
   const int cg = static_cast<int>(i % groups);
   const long long row = i / groups;
-  const int l = static_cast<int>(row % L);
-  const long long seq = row / L;
-  float d[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int lo = l - k + 1;
-    d[k] = (lo >= 0 && lo < L) ? dout[seq * L + lo] * scale : 0.f;
-  }
+  const int l = static_cast<int>(row % P);
+  const long long seq = row / P;
   float v[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int c = cg * 8 + q;
-    v[q] = w[c * 3 + 0] * d[0] + w[c * 3 + 1] * d[1] + w[c * 3 + 2] * d[2];
+  for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  if (l < L) {
+    float d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int lo = l - k + 1;
+      d[k] = (lo >= 0 && lo < L) ? score_grad(dout, seq, lo, p, L) * scale : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = cg * 8 + q;
+      v[q] = w[c * 3 + 0] * d[0] + w[c * 3 + 1] * d[1] + w[c * 3 + 2] * d[2];
+    }
   }
   st_h8(dx + row * C + cg * 8, v);
 }
 
-// dw[c,k] += sum_{seq,l} dout[seq,l] * x[seq, l+k-1, c] ; db += sum dout.   Thread = 8 channels; rows strided over blocks.
+// dw[c,k] += sum dscore[seq, l] * x[seq*P + l + k - 1, c] ; db += sum dscore.   Thread = 8 channels; a block owns a row range.
 __global__ void __launch_bounds__(128)
-mpd_post_dw_kernel(const float* __restrict__ dout, const __half* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int NSEQ, int L,
-                   int C, long long rows_per_block) {
+mpd_post_dw_kernel(const float* __restrict__ dout, const __half* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int NSEQ, int p,
+                   int L, int P, int C, long long rows_per_block) {
   const int cg = threadIdx.x;             // C / 8 == blockDim.x == 128
-  const long long rows = static_cast<long long>(NSEQ) * L;
+  const long long rows = static_cast<long long>(NSEQ) * P;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float aw[8][3];
 #pragma unroll
   for (int q = 0; q < 8; ++q) aw[q][0] = aw[q][1] = aw[q][2] = 0.f;
   float ab = 0.f;
-  for (long long row = r0; row < r1; ++row) {   // row = the INPUT row (seq, li); it meets dout at l = li - k + 1
-    const int li = static_cast<int>(row % L);
-    const long long seq = row / L;
+  for (long long row = r0; row < r1; ++row) {   // row = the INPUT row (seq, li); it meets dscore at l = li - k + 1
+    const int li = static_cast<int>(row % P);
+    if (li >= L) continue;
+    const long long seq = row / P;
     float xv[8];
     ld_h8(x + row * C + cg * 8, xv);
-    ab += dout[row];
+    ab += score_grad(dout, seq, li, p, L);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int l = li - k + 1;
-      const float d = (l >= 0 && l < L) ? dout[seq * L + l] : 0.f;
+      const float d = (l >= 0 && l < L) ? score_grad(dout, seq, l, p, L) : 0.f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) aw[q][k] = fmaf(d, xv[q], aw[q][k]);
     }
@@ -238,39 +253,47 @@ mpd_post_dw_kernel(const float* __restrict__ dout, const __half* __restrict__ x,
   if (cg == 0) atomicAdd(db, ab);
 }
 
-// g = dy * (y > 0 ? 1 : slope)      (fp16, 8 elements per thread)
+// g = dy * (y > 0 ? 1 : slope) on the valid rows (row % P < L), 0 on the gap rows      (fp16, 8 elements per thread)
 __global__ void __launch_bounds__(256)
-lrelu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, __half* __restrict__ g, long long n8, float slope) {
+lrelu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, __half* __restrict__ g, long long n8, int C8, int P, int L,
+                 float slope) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float a[8], b[8];
-  ld_h8(dy + i * 8, a);
-  ld_h8(y + i * 8, b);
+  const bool valid = static_cast<int>((i / C8) % P) < L;
+  if (valid) {
+    ld_h8(dy + i * 8, a);
+    ld_h8(y + i * 8, b);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) a[q] = b[q] > 0.f ? a[q] : a[q] * slope;
+    for (int q = 0; q < 8; ++q) a[q] = b[q] > 0.f ? a[q] : a[q] * slope;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+  }
   st_h8(g + i * 8, a);
 }
 
-// dx[seq, l, c] = sum_{k: (l + pad - k) % stride == 0, lo = (l + pad - k) / stride < L_out} col[seq, lo, k*C + c]     (k < taps)
+// data gradient of a strided convolution from the per-tap products of ONE GEMM: col (rows_out, taps*C) holds, at column block j,
+// sum_n g[r, n] W[n, :, tap(j)] with tap(j) = j or taps-1-j (`reversed`: the tap-reversed weight pack); the input row
+// r_in = stride*r + tap - pad collects it:   dx[r_in, c] = sum_{tap: (r_in + pad - tap) % stride == 0} col[(r_in + pad - tap)/stride, j(tap)*C + c]
 __global__ void __launch_bounds__(256)
-col2im_kernel(const __half* __restrict__ col, __half* __restrict__ dx, int NSEQ, int L_in, int L_out, int C, int taps, int pad, int stride) {
+col2im_kernel(const __half* __restrict__ col, __half* __restrict__ dx, long long rows_in, long long rows_out, int C, int taps, int pad, int stride,
+              int reversed) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int groups = C / 8;
-  if (i >= static_cast<long long>(NSEQ) * L_in * groups) return;
+  if (i >= rows_in * groups) return;
   const int cg = static_cast<int>(i % groups);
   const long long row = i / groups;
-  const int l = static_cast<int>(row % L_in);
-  const long long seq = row / L_in;
   float acc[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
   for (int k = 0; k < taps; ++k) {
-    const int num = l + pad - k;
+    const long long num = row + pad - k;
     if (num < 0 || num % stride != 0) continue;
-    const int lo = num / stride;
-    if (lo >= L_out) continue;
+    const long long ro = num / stride;
+    if (ro >= rows_out) continue;
     float v[8];
-    ld_h8(col + ((seq * L_out + lo) * taps + k) * C + cg * 8, v);
+    ld_h8(col + (ro * taps + (reversed ? taps - 1 - k : k)) * C + cg * 8, v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] += v[q];
   }
@@ -300,7 +323,7 @@ l1_pair_fwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, f
   }
 }
 
-// d b = coef[0] * sign(b - a)   (gradient of coef * sum|a - b| with respect to b), fp16
+// d b = coef[0] * scale * sign(b - a)   (gradient of coef * sum|a - b| with respect to b), fp16
 __global__ void __launch_bounds__(256)
 l1_pair_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const float* __restrict__ coef, float scale, __half* __restrict__ db,
                    long long n8) {
@@ -323,93 +346,95 @@ inline unsigned grid_for(long long n, int block) { return static_cast<unsigned>(
 using namespace osb;
 
 extern "C" int osb_mpd_first_fwd(const float* wav, const float* w, const float* bias, void* out_h16, int32_t NS, int32_t T, int32_t period,
-                                 int32_t L1, int32_t CP, int32_t stride, float slope, void* stream) {
+                                 int32_t L1, int32_t P1, int32_t CP, int32_t stride, float slope, void* stream) {
   OSB_REQUIRE(wav && w && bias && out_h16, OSB_ERR_ARG);
-  OSB_REQUIRE(NS > 0 && T > 1 && period > 0 && L1 > 0 && CP >= 32 && CP % 8 == 0 && stride >= 1, OSB_ERR_SHAPE);
+  OSB_REQUIRE(NS > 0 && T > 1 && period > 0 && L1 > 0 && P1 >= L1 && CP >= 32 && CP % 8 == 0 && stride >= 1, OSB_ERR_SHAPE);
   const int L0 = (T + period - 1) / period;
   OSB_REQUIRE(L0 * period - T < T - 1, OSB_ERR_SHAPE);   // reflect padding needs n_pad < T
-  const long long n = static_cast<long long>(NS) * period * L1 * (CP / 8);
+  const long long n = static_cast<long long>(NS) * period * P1 * (CP / 8);
   mpd_first_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(wav, w, bias, static_cast<__half*>(out_h16), NS, T, period, L0,
-                                                                                       L1, CP, stride, slope);
+                                                                                       L1, P1, CP, stride, slope);
   count_launch();
   return launch_status();
 }
 
-extern "C" int osb_mpd_first_bwd(const void* g_h16, const float* wav, const float* w, float* dwav, float* dw, float* db, int32_t NS,
-                                 int32_t n_first, int32_t T, int32_t period, int32_t L1, int32_t CP, int32_t stride, float inv_scale,
-                                 void* stream) {
+extern "C" int osb_mpd_first_bwd(const void* g_h16, const float* wav, const float* w, float* dwav, float* dw, float* db, int32_t NS, int32_t T,
+                                 int32_t period, int32_t L1, int32_t P1, int32_t CP, int32_t stride, float inv_scale, void* stream) {
   OSB_REQUIRE(g_h16 && wav && w, OSB_ERR_ARG);
-  OSB_REQUIRE(NS > 0 && n_first >= 0 && n_first <= NS && T > 1 && period > 0 && L1 > 0, OSB_ERR_SHAPE);
+  OSB_REQUIRE(NS > 0 && T > 1 && period > 0 && L1 > 0 && P1 >= L1, OSB_ERR_SHAPE);
   const int L0 = (T + period - 1) / period;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __half* g = static_cast<const __half*>(g_h16);
   int launched = 0;
-  if (dwav != nullptr && n_first < NS) {   // signals [n_first, NS) receive a waveform gradient (the generated half)
-    const long long n = static_cast<long long>(NS - n_first) * period * L0;
-    mpd_first_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(g, w, dwav, NS, n_first, T, period, L0, L1, CP, stride, inv_scale);
+  if (dwav != nullptr) {   // accumulated (+=): the caller zeroes it
+    const long long n = static_cast<long long>(NS) * period * L0;
+    mpd_first_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(g, w, dwav, NS, T, period, L0, L1, P1, CP, stride, inv_scale);
     ++launched;
   }
   if (dw != nullptr && db != nullptr) {
-    const long long rows = static_cast<long long>(NS) * period * L1;
+    const long long rows = static_cast<long long>(NS) * period * P1;
     long long blocks = (rows + 2047) / 2048;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const long long rpb = (rows + blocks - 1) / blocks;
-    mpd_first_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(g, wav, dw, db, NS, T, period, L0, L1, CP, stride, inv_scale, rpb);
+    mpd_first_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(g, wav, dw, db, NS, T, period, L0, L1, P1, CP, stride, inv_scale, rpb);
     ++launched;
   }
   count_launch(launched);
   return launch_status();
 }
 
-extern "C" int osb_mpd_post_fwd(const void* x_h16, const float* w, const float* bias, float* out, int32_t NSEQ, int32_t L, int32_t C,
-                                void* stream) {
+extern "C" int osb_mpd_post_fwd(const void* x_h16, const float* w, const float* bias, float* out, int32_t NSEQ, int32_t period, int32_t L,
+                                int32_t P, int32_t C, void* stream) {
   OSB_REQUIRE(x_h16 && w && bias && out, OSB_ERR_ARG);
-  OSB_REQUIRE(NSEQ > 0 && L > 0 && C % 256 == 0, OSB_ERR_SHAPE);
+  OSB_REQUIRE(NSEQ > 0 && period > 0 && NSEQ % period == 0 && L > 0 && P >= L && C % 256 == 0, OSB_ERR_SHAPE);
   const long long rows = static_cast<long long>(NSEQ) * L;
-  mpd_post_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), w, bias, out, NSEQ, L, C);
+  mpd_post_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), w, bias, out, NSEQ, period,
+                                                                                       L, P, C);
   count_launch();
   return launch_status();
 }
 
 extern "C" int osb_mpd_post_bwd(const float* dout, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NSEQ,
-                                int32_t L, int32_t C, float scale, void* stream) {
+                                int32_t period, int32_t L, int32_t P, int32_t C, float scale, void* stream) {
   OSB_REQUIRE(dout && w, OSB_ERR_ARG);
-  OSB_REQUIRE(NSEQ > 0 && L > 0 && C == 1024, OSB_ERR_SHAPE);
+  OSB_REQUIRE(NSEQ > 0 && period > 0 && NSEQ % period == 0 && L > 0 && P >= L && C == 1024, OSB_ERR_SHAPE);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int launched = 0;
   if (dx_h16 != nullptr) {
-    const long long n = static_cast<long long>(NSEQ) * L * (C / 8);
-    mpd_post_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(dout, w, static_cast<__half*>(dx_h16), NSEQ, L, C, scale);
+    const long long n = static_cast<long long>(NSEQ) * P * (C / 8);
+    mpd_post_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(dout, w, static_cast<__half*>(dx_h16), NSEQ, period, L, P, C, scale);
     ++launched;
   }
-  if (dw != nullptr && db != nullptr && x_h16 != nullptr) {
-    const long long rows = static_cast<long long>(NSEQ) * L;
+  if (dw != nullptr && db != nullptr && x_h16 != nullptr) {   // accumulated (+=): the caller zeroes them
+    const long long rows = static_cast<long long>(NSEQ) * P;
     long long blocks = (rows + 63) / 64;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const long long rpb = (rows + blocks - 1) / blocks;
-    mpd_post_dw_kernel<<<static_cast<unsigned>(blocks), 128, 0, s>>>(dout, static_cast<const __half*>(x_h16), dw, db, NSEQ, L, C, rpb);
+    mpd_post_dw_kernel<<<static_cast<unsigned>(blocks), 128, 0, s>>>(dout, static_cast<const __half*>(x_h16), dw, db, NSEQ, period, L, P, C, rpb);
     ++launched;
   }
   count_launch(launched);
   return launch_status();
 }
 
-extern "C" int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t n, float slope, void* stream) {
+extern "C" int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t rows, int32_t C, int32_t P, int32_t L, float slope,
+                                 void* stream) {
   OSB_REQUIRE(dy && y && g, OSB_ERR_ARG);
-  OSB_REQUIRE(n > 0 && n % 8 == 0, OSB_ERR_SHAPE);
-  lrelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
-                                                                                    static_cast<__half*>(g), n / 8, slope);
+  OSB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && P > 0 && L > 0 && L <= P, OSB_ERR_SHAPE);
+  const long long n8 = rows * (C / 8);
+  lrelu_bwd_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                                    static_cast<__half*>(g), n8, C / 8, P, L, slope);
   count_launch();
   return launch_status();
 }
 
-extern "C" int osb_col2im_h16(const void* col, void* dx, int32_t NSEQ, int32_t L_in, int32_t L_out, int32_t C, int32_t taps, int32_t pad,
-                              int32_t stride, void* stream) {
+extern "C" int osb_col2im_h16(const void* col, void* dx, int64_t rows_in, int64_t rows_out, int32_t C, int32_t taps, int32_t pad,
+                              int32_t stride, int32_t reversed, void* stream) {
   OSB_REQUIRE(col && dx, OSB_ERR_ARG);
-  OSB_REQUIRE(NSEQ > 0 && L_in > 0 && L_out > 0 && C % 8 == 0 && taps > 0 && stride >= 1, OSB_ERR_SHAPE);
-  const long long n = static_cast<long long>(NSEQ) * L_in * (C / 8);
-  col2im_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(col), static_cast<__half*>(dx), NSEQ, L_in,
-                                                                              L_out, C, taps, pad, stride);
+  OSB_REQUIRE(rows_in > 0 && rows_out > 0 && C % 8 == 0 && taps > 0 && stride >= 1, OSB_ERR_SHAPE);
+  const long long n = rows_in * (C / 8);
+  col2im_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(col), static_cast<__half*>(dx), rows_in,
+                                                                              rows_out, C, taps, pad, stride, reversed);
   count_launch();
   return launch_status();
 }

@@ -1,8 +1,9 @@
 """Multi-period and multi-resolution discriminators (reference: disc/_discriminators.py:10-216).
 
-These Conv2d stacks are NOT part of the B200 hot-path scope of this round: they run
-on stock PyTorch / cuDNN, with the reference's module tree so that `state_dict` keys (weight-norm `weight_g` /
-`weight_v` included) are interchangeable.
+The module tree is the reference's, so that `state_dict` keys (weight-norm `weight_g` / `weight_v` included) are
+interchangeable.  On CUDA tensors the period discriminators run on this package's kernels (disc/native.py: tcgen05 implicit
+GEMMs over a flat fp16 sequence layout; feature maps come back as `native.FlatMap`, `.dense()` gives the reference's
+(B, C, L, period) tensor).  The resolution discriminators (Conv2d over spectrograms) run on stock PyTorch / cuDNN.
 """
 from __future__ import annotations
 
@@ -12,6 +13,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 from torch.nn.utils import weight_norm
+
+
+NATIVE_MPD = True   # False: the period discriminators run on cuDNN as well (A/B comparisons in tests and bench.py)
 
 
 def _wn_conv(cin, cout, kernel, stride, padding):
@@ -33,6 +37,9 @@ class DiscriminatorP(nn.Module):
         self.lrelu_slope = lrelu_slope
 
     def forward(self, x: torch.Tensor):
+        if x.is_cuda and NATIVE_MPD:
+            from . import native
+            return native.period_forward(self, x)
         x = x.unsqueeze(1)
         b, c, t = x.shape
         rem = t % self.period
@@ -98,6 +105,16 @@ class MultiPeriodDiscriminator(_Multi):
     def __init__(self, periods: Tuple[int, ...] = (2, 3, 5, 7, 11)):
         super().__init__()
         self.discriminators = nn.ModuleList([DiscriminatorP(period=p) for p in periods])
+
+    def forward(self, y: torch.Tensor, y_hat: torch.Tensor):
+        if not (y.is_cuda and NATIVE_MPD):
+            return super().forward(y, y_hat)
+        from . import native
+        real, fake, fr, ff = [], [], [], []
+        for d in self.discriminators:
+            a, b, fa, fb = native.period_forward_pair(d, y, y_hat)
+            real.append(a); fr.append(fa); fake.append(b); ff.append(fb)
+        return real, fake, fr, ff
 
 
 class MultiResolutionDiscriminator(_Multi):

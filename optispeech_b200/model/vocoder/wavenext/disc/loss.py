@@ -38,7 +38,9 @@ class FeatureMatchingLoss(nn.Module):
     """L1 between real / generated feature maps, summed over layers and sub-discriminators (reference :67-85)."""
 
     def forward(self, fmap_r, fmap_g) -> Tensor:
-        return sum((rl - gl).abs().mean() for dr, dg in zip(fmap_r, fmap_g) for rl, gl in zip(dr, dg))
+        from .native import feature_l1  # flat fp16 maps of the native period discriminators, or plain tensors
+
+        return sum(feature_l1(rl, gl) for dr, dg in zip(fmap_r, fmap_g) for rl, gl in zip(dr, dg))
 
 
 class _Spectrogram(nn.Module):

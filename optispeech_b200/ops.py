@@ -773,3 +773,81 @@ def crop_segments(wav: torch.Tensor, start_frames: torch.Tensor, n: int, hop: in
     _lib.check(_lib.load().osb_gather_segments(_ptr(_f32(wav)), _ptr(start_frames.to(torch.int64).contiguous()), _ptr(out), B, Tw, 1, int(n),
                                                int(hop), _stream()), "osb_gather_segments")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# period discriminators (osb_disc.cu): flat fp16 sequence matrices, see include/osb200.h
+# ------------------------------------------------------------------------------------------------
+def gemm_wgrad_strided(dy: torch.Tensor, a: torch.Tensor, dw: torch.Tensor, *, taps: int, pad: int, stride: int):
+    """dw[tap,n,k] += sum_t dy[t,n] a[t*stride + tap - pad, k]; dy (T,N), a (T_in,K) fp16 flat matrices; dw fp32 (taps,N,K)."""
+    assert dy.dtype == torch.float16 and a.dtype == torch.float16 and dw.dtype == torch.float32 and dy.dim() == 2 and a.dim() == 2
+    T, N = dy.shape
+    T_in, K = a.shape
+    _lib.check(_lib.load().osb_gemm_wgrad_strided(_ptr(dy), N, _ptr(a), K, _ptr(dw), 1, T, T_in, N, K, taps, pad, stride, _stream()),
+               "osb_gemm_wgrad_strided")
+    return dw
+
+
+def mpd_first_fwd(wav, w, bias, period: int, L1: int, P1: int, CP: int, stride: int, slope: float):
+    NS, T = wav.shape
+    out = torch.empty((NS * period * P1, CP), device=wav.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_mpd_first_fwd(_ptr(_f32(wav)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(out), NS, T, period, L1, P1, CP, stride,
+                                             slope, _stream()), "osb_mpd_first_fwd")
+    return out
+
+
+def mpd_first_bwd(g, wav, w, period: int, L1: int, P1: int, stride: int, inv_scale: float, want_dwav: bool, want_dw: bool):
+    NS, T = wav.shape
+    dwav = torch.zeros_like(wav) if want_dwav else None
+    dwb = torch.zeros((32 * 5 + 32,), device=wav.device, dtype=torch.float32) if want_dw else None
+    _lib.check(_lib.load().osb_mpd_first_bwd(_ptr(g), _ptr(_f32(wav)), _ptr(_f32(w)), _ptr(dwav), _ptr(dwb),
+                                             (dwb.data_ptr() + 4 * 160) if want_dw else None, NS, T, period, L1, P1, g.shape[1], stride,
+                                             inv_scale, _stream()), "osb_mpd_first_bwd")
+    return dwav, (dwb[:160].view(32, 5) if want_dw else None), (dwb[160:] if want_dw else None)
+
+
+def mpd_post_fwd(x, w, bias, period: int, L: int, P: int):
+    rows, Cc = x.shape
+    NSEQ = rows // P
+    out = torch.empty((NSEQ // period, L * period), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_mpd_post_fwd(_ptr(x), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(out), NSEQ, period, L, P, Cc, _stream()),
+               "osb_mpd_post_fwd")
+    return out
+
+
+def mpd_post_bwd(dscore, x, w, period: int, L: int, P: int, scale: float, want_dx: bool, want_dw: bool):
+    rows, Cc = x.shape
+    NSEQ = rows // P
+    dx = torch.empty_like(x) if want_dx else None
+    dwb = torch.zeros((Cc * 3 + 4,), device=x.device, dtype=torch.float32) if want_dw else None
+    _lib.check(_lib.load().osb_mpd_post_bwd(_ptr(_f32(dscore.contiguous())), _ptr(x), _ptr(_f32(w)), _ptr(dx), _ptr(dwb),
+                                            (dwb.data_ptr() + 4 * Cc * 3) if want_dw else None, NSEQ, period, L, P, Cc, scale, _stream()),
+               "osb_mpd_post_bwd")
+    return dx, (dwb[:Cc * 3].view(Cc, 3) if want_dw else None), (dwb[Cc * 3:Cc * 3 + 1] if want_dw else None)
+
+
+def lrelu_bwd_h16(dy, y, P: int, L: int, slope: float):
+    rows, Cc = y.shape
+    g = torch.empty_like(y)
+    _lib.check(_lib.load().osb_lrelu_bwd_h16(_ptr(dy), _ptr(y), _ptr(g), rows, Cc, P, L, slope, _stream()), "osb_lrelu_bwd_h16")
+    return g
+
+
+def col2im_h16(col, rows_in: int, Cc: int, taps: int, pad: int, stride: int, reversed_taps: bool):
+    rows_out = col.shape[0]
+    dx = torch.empty((rows_in, Cc), device=col.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_col2im_h16(_ptr(col), _ptr(dx), rows_in, rows_out, Cc, taps, pad, stride, int(reversed_taps), _stream()),
+               "osb_col2im_h16")
+    return dx
+
+
+def l1_pair_fwd(a, b):
+    out = torch.zeros((1,), device=a.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_l1_pair_fwd(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "osb_l1_pair_fwd")
+    return out
+
+
+def l1_pair_bwd(a, b, coef, scale: float):
+    db = torch.empty_like(b)
+    _lib.check(_lib.load().osb_l1_pair_bwd(_ptr(a), _ptr(b), _ptr(_f32(coef)), scale, _ptr(db), a.numel(), _stream()), "osb_l1_pair_bwd")
+    return db
