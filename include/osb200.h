@@ -151,6 +151,11 @@ typedef struct osb_gemm_desc {
   int32_t row_stride;
   int32_t T_in;
   float lrelu_slope;      /* OSB_FLAG_LRELU: negative slope                                          */
+  /* OSB_FLAG_KEEPMASK without a pad_mask: rows are grouped in sequences of seq_pitch rows whose first seq_valid rows are
+   * kept and the rest zeroed (the flat sequence layout of the period discriminators: the zero tail of one sequence is the
+   * convolution padding of the next).  0 = unused. */
+  int32_t seq_pitch;
+  int32_t seq_valid;
 } osb_gemm_desc;
 
 int osb_gemm(const osb_gemm_desc* desc, void* stream);

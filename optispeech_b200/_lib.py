@@ -60,6 +60,8 @@ class GemmDesc(C.Structure):
         ("row_stride", C.c_int32),
         ("T_in", C.c_int32),
         ("lrelu_slope", C.c_float),
+        ("seq_pitch", C.c_int32),
+        ("seq_valid", C.c_int32),
     ]
 
 

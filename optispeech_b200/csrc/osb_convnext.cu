@@ -67,6 +67,11 @@ struct FusedCfg {
   static constexpr int N2 = C <= 256 ? C : C / 2;          // N of one pwconv2 MMA
   static constexpr int N2_PARTS = C / N2;
   static constexpr uint32_t ACC1_COL = C;                  // TMEM: [0, C) pwconv2 accumulator, then 2 x 64 for pwconv1
+  // C = 256 leaves 128 TMEM columns: exactly the fp16 xhat tile (128 rows x 256 channels, two per column).  pwconv1 then takes
+  // its A operand from tensor memory: the tile is read by all I/64 chunks, and as a shared-memory operand those re-reads
+  // (64 KB per chunk) were the largest share of the shared-memory traffic that bounded the chunk loop (clock64 timeline, r2).
+  static constexpr bool A_TMEM = (C == 256);
+  static constexpr uint32_t A_COL = C + 2 * FB_NC;
   // prologue input staging: the (rows + 6 halo) x C fp32 input tile is brought in by TMA as C/32 boxes of [rows x 128 B]
   // (128B swizzle, zero fill outside [0, T) = the convolution's zero padding) into the weight / GELU buffers, which are idle
   // until the prologue is done; C = 384 takes two passes of 64 rows
@@ -197,7 +202,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = dA0 + static_cast<uint64_t>((kb * (FB_M * 128) + k * 32) >> 4);
             const uint64_t db = dW10 + static_cast<uint64_t>((st * Cfg::W1_BYTES + kb * (FB_NC * 128) + k * 32) >> 4);
-            umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (Cfg::A_TMEM) umma_ts_f16(d, tmem_base + Cfg::A_COL + kb * 32 + k * 8, db, idesc1, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss<false>(d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
           }
         umma_commit(&w1_empty[st]);
         umma_commit(&acc1_full[buf]);
@@ -339,7 +345,27 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           }
         }
       }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+      if constexpr (Cfg::A_TMEM) {
+        // xhat tile: shared memory -> tensor memory.  A thread owns one row (TMEM lane) and two of the four 64-channel
+        // k-blocks; the tile was written by other warps (rows are dealt differently in the prologue).
+        asm volatile("bar.sync 1, %0;" ::"n"(FB_WORKERS * 32) : "memory");
+        const int arow = q * 32 + lane;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KB / 2; ++kk) {
+          const int kb = half * (Cfg::KB / 2) + kk;
+          uint32_t ar[32];
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sA + kb * (FB_M * 128) + sw128_offset(arow, c16));
+            ar[c16 * 4 + 0] = u.x; ar[c16 * 4 + 1] = u.y; ar[c16 * 4 + 2] = u.z; ar[c16 * 4 + 3] = u.w;
+          }
+          tmem_st_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + Cfg::A_COL + kb * 32, ar);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+      } else {
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor-core (async) proxy
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
       if (ww == 0 && lane == 0) FB_TRACE(2, 0);

@@ -117,34 +117,56 @@ mpd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, f
   if (acc != 0.f) atomicAdd(dwav + static_cast<long long>(n) * T + wav_index(l, j, p, T), acc * inv_scale);
 }
 
-// dW1[c,k] += inv_scale * sum g[row, c] * x_j[3 lo + k - 2] ; db1[c] += inv_scale * sum g[row, c].  Block partial sums in
-// shared memory (32 channels x 6), one atomic per element and block.
+// dW1[c,k] += inv_scale * sum g[row, c] * x_j[3 lo + k - 2] ; db1[c] += inv_scale * sum g[row, c].  A thread owns 8 channels of
+// a row (one 16-byte load; 4 threads cover the 32 real channels, a warp 8 rows per trip); partial sums are folded across the
+// warp by shuffles, across the block in shared memory, and leave with one atomic per element and block.
 __global__ void __launch_bounds__(256)
 mpd_first_dw_kernel(const __half* __restrict__ g, const float* __restrict__ wav, float* __restrict__ dw /*(32,5)*/, float* __restrict__ db,
                     int NS, int T, int p, int L0, int L1, int P1, int CP, int stride, float inv_scale, long long rows_per_block) {
   __shared__ float part[8][32 * 6];
-  const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;   // lane = channel
+  const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
+  const int cg = lane & 3, rsub = lane >> 2;             // channel group (8 channels), row within the warp's 8-row trip
   const long long rows = static_cast<long long>(NS) * p * P1;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float aw[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, ab = 0.f;
-  for (long long row = r0 + wip; row < r1; row += 8) {
+  float aw[8][5], ab[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    ab[q] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) aw[q][k] = 0.f;
+  }
+  for (long long row = r0 + wip * 8 + rsub; row < r1; row += 64) {
     const int lo = static_cast<int>(row % P1);
     if (lo >= L1) continue;
     const int seq = static_cast<int>(row / P1);
     const int n = seq / p, j = seq % p;
-    const float gv = __half2float(g[row * CP + lane]);
-    ab += gv;
+    float gv[8], x[5];
+    ld_h8(g + row * CP + cg * 8, gv);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const int l = stride * lo + k - 2;
-      const float x = (l >= 0 && l < L0) ? wav[static_cast<long long>(n) * T + wav_index(l, j, p, T)] : 0.f;   // warp-uniform address
-      aw[k] = fmaf(gv, x, aw[k]);
+      x[k] = (l >= 0 && l < L0) ? wav[static_cast<long long>(n) * T + wav_index(l, j, p, T)] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ab[q] += gv[q];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) aw[q][k] = fmaf(gv[q], x[k], aw[q][k]);
     }
   }
+  // fold the 8 row slots of the warp (lanes with equal cg), then the 8 warps
 #pragma unroll
-  for (int k = 0; k < 5; ++k) part[wip][lane * 6 + k] = aw[k];
-  part[wip][lane * 6 + 5] = ab;
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float v = k < 5 ? aw[q][k] : ab[q];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (rsub == 0) part[wip][(cg * 8 + q) * 6 + k] = v;
+    }
+  }
   __syncthreads();
   if (threadIdx.x < 32 * 6) {
     float s = 0.f;

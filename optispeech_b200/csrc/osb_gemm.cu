@@ -53,6 +53,8 @@ struct GemmKParams {
   float* colsum;    // COLSUM: (N) column sums of the fp16 output
   int row_stride;   // > 1: strided convolution, output row t reads input row t*row_stride + tap - pad
   float lrelu;      // OSB_FLAG_LRELU slope
+  int seq_pitch;    // > 0: rows t with t % seq_pitch >= seq_valid count as padded (KEEPMASK without a mask array)
+  int seq_valid;
   int w_mn;         // 1: W is (taps, K, ldw >= N) with the OUTPUT index contiguous (MN-major B operand): dgrad on the forward pack
   int tap_rev;      // 1: tap t reads weight slice taps-1-t (transposed convolution)
   long long* trace; // optional (developer): clock64 timeline of CTA (0,0), see tools/probe_gemm_trace.py
@@ -355,7 +357,8 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
   const int nrows = p.T - tw < 0 ? 0 : (p.T - tw > 32 ? 32 : p.T - tw);
   const long long row = static_cast<long long>(b) * p.T + t;
   const long long row0 = static_cast<long long>(b) * p.T + tw;
-  const bool padded = (p.pad_mask != nullptr) && valid && (p.pad_mask[row] != 0);
+  const bool padded = valid && (p.pad_mask != nullptr ? (p.pad_mask[row] != 0)
+                                                      : (p.seq_pitch > 0 && static_cast<int>(row % p.seq_pitch) >= p.seq_valid));
   const float* sv0 = sv;
   const float* sv1 = sv + BN;
   const float* sv2 = sv + 2 * BN;
@@ -1166,6 +1169,8 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   p.col_len = reinterpret_cast<const long long*>(d->col_len);
   p.row_stride = row_stride;
   p.lrelu = d->lrelu_slope;
+  p.seq_pitch = d->seq_pitch > 0 ? d->seq_pitch : 0;
+  p.seq_valid = d->seq_valid;
   p.w_mn = w_mn ? 1 : 0;
   p.tap_rev = (d->flags & OSB_FLAG_TAP_REVERSE) ? 1 : 0;
   p.colsum = (d->flags & OSB_FLAG_COLSUM) ? d->out_colsum : nullptr;
@@ -1183,7 +1188,7 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
                         d->epi == OSB_EPI_ATTN_LOGP ? nullptr : static_cast<const void*>(d->resid)})
     if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return OSB_ERR_ALIGN;
   if ((d->flags & (OSB_FLAG_OUT_H16 | OSB_FLAG_SAVE_PRE)) && d->aux_h16 == nullptr) return OSB_ERR_ARG;
-  if ((d->flags & OSB_FLAG_KEEPMASK) && d->pad_mask == nullptr) return OSB_ERR_ARG;
+  if ((d->flags & OSB_FLAG_KEEPMASK) && d->pad_mask == nullptr && d->seq_pitch <= 0) return OSB_ERR_ARG;
 
   switch (d->epi) {
     case OSB_EPI_BIAS:
@@ -1300,7 +1305,9 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
 }
 
 // v2: osb_gemm_desc grew (out_colsum, row_stride, T_in, lrelu_slope), new entry points (mha, pack_multi, losses)
-extern "C" int osb_version(void) { return 2; }
+// v3: osb_gemm_desc grew (seq_pitch, seq_valid), osb_pack_job grew (aux), osb_align_loss_fold / osb_ln_dwconv_bwd signatures,
+//     new entry points (fused ConvNeXt training kernels, period discriminators, glue kernels)
+extern "C" int osb_version(void) { return 3; }
 extern "C" unsigned long long osb_launch_count(void) { return osb::g_launch_count; }
 extern "C" const char* osb_strerror(int s) {
   switch (s) {

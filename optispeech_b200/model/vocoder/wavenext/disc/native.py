@@ -86,21 +86,6 @@ class _DenseFn(torch.autograd.Function):
         return flat, None, None, None
 
 
-_MASKS = {}
-
-
-def _gap_mask(rows: int, P: int, L: int, device) -> torch.Tensor:
-    """uint8 (rows,): 1 on the rows past a sequence's valid length (the GEMM epilogue zeroes them)."""
-    key = (rows, P, L, str(device))
-    m = _MASKS.get(key)
-    if m is None:
-        if len(_MASKS) > 64:
-            _MASKS.clear()
-        m = ((torch.arange(rows, device=device) % P) >= L).to(torch.uint8)
-        _MASKS[key] = m
-    return m
-
-
 class _FirstFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wav, w, bias, geom: Geometry, stride: int, slope: float):
@@ -127,9 +112,8 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, wp, stride: int, P_out: int, L_out: int, slope: float):
         rows_in, cin_p = x.shape
         rows_out = rows_in // stride
-        mask = _gap_mask(rows_out, P_out, L_out, x.device)
         _, y, _ = ops.gemm(x.view(1, rows_in, cin_p), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
-                           pad=PAD, bias=bias, pad_mask=mask, row_stride=stride, lrelu=slope)
+                           pad=PAD, bias=bias, seq_rows=(P_out, L_out), row_stride=stride, lrelu=slope)
         y = y.view(rows_out, -1)
         ctx.save_for_backward(x, w, wp, y)
         ctx.stride, ctx.P_out, ctx.L_out, ctx.slope = stride, P_out, L_out, slope

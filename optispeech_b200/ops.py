@@ -83,7 +83,7 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int = 0, K: Optional[int] = None,
          bias=None, out=None, aux=None, resid=None, gamma=None, row_scale=None, pad_mask=None, ln_w=None, ln_b=None,
          ln_eps: float = 0.0, dot_w=None, dot_b=None, out_dot=None, aux_in=None, row_stat=None, dropout_p: float = 0.0, dropout_seed: int = 0, w_batched: bool = False, col_len=None, N: Optional[int] = None, colsum=None, w_mn: bool = False, tap_reverse: bool = False,
-         row_stride: int = 1, lrelu: Optional[float] = None):
+         row_stride: int = 1, lrelu: Optional[float] = None, seq_rows: Optional[Tuple[int, int]] = None):
     """acc[b,t,n] = sum_tap sum_k a[b,t+tap-pad,k] w[tap,n,k]; then the fused epilogue `epi`.
 
     a: fp16 (B,T,lda); w: fp16 (taps,N,ldw) — or, with FLAG_SPLIT_IN, a = (B,T,[hi K|lo K]) and
@@ -142,6 +142,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epi: int, flags: int = 0, pad: int
     d.dropout_seed_dev = _ptr(step_counter(a.device)) if dropout_p > 0.0 else None
     d.w_batched, d.col_len = int(w_batched), _ptr(col_len)
     d.row_stride, d.T_in, d.lrelu_slope = int(row_stride), int(T_in), float(lrelu or 0.0)
+    if seq_rows is not None:   # KEEPMASK by arithmetic: (pitch, valid rows) of the flat sequence layout
+        d.seq_pitch, d.seq_valid = int(seq_rows[0]), int(seq_rows[1])
     if colsum is not None:  # bias gradient of the layer whose dgrad this is: column sums of the fp16 output, fused (pre-zeroed fp32 (N,))
         assert epi in (EPI_GELU_BWD, EPI_RELU_BWD, EPI_RELU_LN_BWD) and colsum.dtype == torch.float32 and colsum.numel() == N
         d.flags |= _lib.FLAG_COLSUM
