@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -479,9 +480,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def step_resident(i):
         model.training_step(dev_batch, i)
 
-    def step_e2e(i):
+    # Every step's loss is read on the host inside the timed region, one step late: the 4-byte device->host copy of step i is
+    # enqueued behind step i and waited for after step i+1 has been enqueued (the last step's is waited for at once), so the
+    # host stages / uploads batch i+1 while the device still computes step i.
+    loss_pin = [torch.zeros(1, pin_memory=True) for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"n": 0, "losses": []}
+
+    def step_e2e(i, last=False):
         model.training_step(pinned, i)  # the batch is staged and copied host->device inside the step
-        return float(model.logged["total_loss/generator"])  # 4-byte device->host read of the step's loss
+        n = e2e_state["n"]
+        loss_pin[n % 2].copy_(model.logged["total_loss/generator"].reshape(1), non_blocking=True)
+        loss_ev[n % 2].record()
+        if n > 0:
+            loss_ev[(n - 1) % 2].synchronize()
+            e2e_state["losses"].append(float(loss_pin[(n - 1) % 2]))
+        if last:
+            loss_ev[n % 2].synchronize()
+            e2e_state["losses"].append(float(loss_pin[n % 2]))
+            e2e_state["n"] = 0
+        else:
+            e2e_state["n"] = n + 1
 
     model.cuda_graph = not args.eager
     sampler.load_start = time.perf_counter()
@@ -511,8 +530,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # untimed: a host batch is staged (the waveform crop is cut on the host), i.e. it has its own tensor signature and its own
     # captured graph: 3 eager steps + the capture + replays
     for i in range(4 + args.warmup):
-        step_e2e(i)
-    ms_e2e = timed_steps(step_e2e, args.steps, world, dev)
+        step_e2e(i, last=(i == 3 + args.warmup))
+    e2e_state["losses"].clear()
+    ms_e2e = timed_steps(lambda i: step_e2e(i, last=(i == args.steps - 1)), args.steps, world, dev)
+    assert len(e2e_state["losses"]) == args.steps and all(math.isfinite(v) for v in e2e_state["losses"]), e2e_state["losses"]
 
     # ---- per-kernel device times of one step (separate pass; event recording perturbs the step time) ----
     roofline, top = None, []
@@ -658,7 +679,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "algorithmic_tflop": (78.8e9 + 124.4e9) * B_PER_GPU / 1e12,
                 "achieved_tflops": (78.8e9 + 124.4e9) * B_PER_GPU / (t3 * 1e-3) / 1e12,
                 "frac_of_sustained_peak": (78.8e9 + 124.4e9) * B_PER_GPU / (t3 * 1e-3) / 1e12 / float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                "discriminators": getattr(gmodel.discriminator, "backend", "stock PyTorch / cuDNN")}
+                "discriminators": "period (MPD): this package's kernels (disc/native.py: tcgen05 implicit GEMMs over the flat sequence "
+                                  "layout); resolution (MRD): stock PyTorch / cuDNN fp32"}
             if gmodel._graphed is not None:
                 gmodel._graphed.release()
             variants["spectral_loss_kernels"] = spectral_kernel_bench(gmodel, dev, peaks)
@@ -686,6 +708,26 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         gpu_library_baseline = {k: gpu_line.get(k) for k in ("value", "ms_per_step", "variants", "note", "error") if k in gpu_line}
         gpu_library_baseline["unit"] = UNIT
 
+    # ---- the gradient all-reduce on its own (N > 1): device time of the captured collective's payload, max over ranks ----
+    allreduce = None
+    if world > 1:
+        bucket = model.optimizers()[0].buckets()[0]
+        payload = torch.zeros_like(bucket.flat_g)
+        for _ in range(3):
+            torch.distributed.all_reduce(payload)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            torch.distributed.all_reduce(payload)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = max_over_ranks(a0.elapsed_time(a1), world, dev) / 10
+        nbytes = payload.numel() * 4
+        allreduce = {"bytes": nbytes, "ms": ar_ms, "bus_GBps": 2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                     "note": "fp32 flat gradient bucket of the generator optimizer, one NCCL all-reduce per step inside the captured graph"}
+
     if rank == 0:
         value = frames_all / (ms * 1e-3)
         e2e_value = frames_all / (ms_e2e * 1e-3)
@@ -701,6 +743,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "launch_mode": "one CUDA-graph replay per step (graph holds the step's library + torch kernels)" if model.cuda_graph else "eager",
             "clocks": clocks,
+            "allreduce": allreduce,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "gpu_library_baseline": gpu_library_baseline,

@@ -558,6 +558,50 @@ int osb_col2im_h16(const void* col, void* dx, int64_t rows_in, int64_t rows_out,
 int osb_l1_pair_fwd(const void* a_h16, const void* b_h16, float* out_sum, int64_t n, void* stream);
 int osb_l1_pair_bwd(const void* a_h16, const void* b_h16, const float* coef, float scale, void* db_h16, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-resolution discriminator (osb_disc.cu) — reference vocoder/wavenext/disc/_discriminators.py:139-216
+ *
+ * Conv2d stacks over magnitude spectrograms (NS, F, W).  Same flat fp16 layout as the period discriminators with the
+ * (signal, frame) pairs as sequences and frequency along the rows: row = (n*W_i + w)*P_i + h, h < H_i valid, 64 channels;
+ * P_5 = H_5 + 2, P_i = 2*P_(i+1).  The kw taps along the frame axis are gathered into the contraction (osb_wim2col_h16,
+ * K = kw*64), the kh taps along frequency are implicit-GEMM taps of osb_gemm with row_stride 2.
+ * ------------------------------------------------------------------------------------- */
+/* Layer 1 (Conv2d(1, 64, (7,5), (2,2), (3,2)) + LeakyReLU, :154): spec (NS, F, W) fp32 -> (NS*W1*P1, 64) fp16. */
+int osb_mrd_first_fwd(const float* spec, const float* w /*(64,35)*/, const float* bias, void* out_h16, int32_t NS, int32_t F, int32_t W,
+                      int32_t H1, int32_t W1, int32_t P1, float slope, void* stream);
+/* Backward from the gated gradient: dspec (NS,F,W) written; dw (64,35) +=, db (64) +=; either part may be NULL. */
+int osb_mrd_first_bwd(const void* g_h16, const float* spec, const float* w, float* dspec, float* dw, float* db, int32_t NS, int32_t F,
+                      int32_t W, int32_t H1, int32_t W1, int32_t P1, float inv_scale, void* stream);
+/* Layer 1 as a GEMM (the path the host takes): xcol (NS*W1*P1, 64) fp16 with xcol[(n, w1, h1), kh*5 + kw] =
+ * spec[n, 2 h1 + kh - 3, 2 w1 + kw - 2] (taps 35..63, out-of-range positions and gap rows zero); and the adjoint gather
+ * dspec[n, f, t] = inv_scale * sum col[(n, w1, h1), kh*5 + kw] over the taps that touch (f, t), col = g . W1 (fp16). */
+int osb_spec_im2col_h16(const float* spec, void* xcol, int32_t NS, int32_t F, int32_t W, int32_t H1, int32_t W1, int32_t P1, void* stream);
+int osb_spec_col2im(const void* col_h16, float* dspec, int32_t NS, int32_t F, int32_t W, int32_t H1, int32_t W1, int32_t P1,
+                    float inv_scale, void* stream);
+/* xcol[(n, wo, h), kw*C + c] = x[(n, wo*sw + kw - pw, h), c] (zero outside [0, W_in)), and its adjoint. */
+int osb_wim2col_h16(const void* x, void* xcol, int32_t NS, int32_t W_in, int32_t W_out, int32_t P, int32_t C, int32_t KW, int32_t pw,
+                    int32_t sw, void* stream);
+int osb_wcol2im_h16(const void* dxcol, void* dx, int32_t NS, int32_t W_in, int32_t W_out, int32_t P, int32_t C, int32_t KW, int32_t pw,
+                    int32_t sw, void* stream);
+/* conv_post (Conv2d(64, 1, (3,3), padding 1), :163): score (NS, H*W) fp32 in the reference's flatten order h*W + w; backward:
+ * dx (NS*W*P, 64) fp16 = scale * conv_post^T(dscore); dw (64,9) +=, db (1) += (unscaled). */
+int osb_mrd_post_fwd(const void* x_h16, const float* w /*(64,9)*/, const float* bias, float* score, int32_t NS, int32_t W, int32_t H,
+                     int32_t P, void* stream);
+int osb_mrd_post_bwd(const float* dscore, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NS, int32_t W,
+                     int32_t H, int32_t P, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Feature extraction of the data path (osb_spectral.cu) — reference dataset/feature_extractors/__init__.py:110-200
+ * ------------------------------------------------------------------------------------- */
+/* log-mel spectrogram and frame energy of a ragged batch of waveforms, one launch: reflect padding by (n_fft - hop)/2 with
+ * every utterance's OWN length, no centring, Hann `window`, mag = sqrt(re^2 + im^2 + mag_eps);
+ *   mel[b, j, f] = log(max(sum_k fb[j, k] mag[f, k], clip_val)),  energy[b, f] = ||mag[f, :]||_2,  f < lengths[b] / hop, else 0.
+ * fb is (n_mels, n_fft/2+1) row-major with the non-zero bin range [klo[j], khi[j]] of every filter.  n_fft in {512, 1024, 2048}.
+ * Replaces CommonFeatureExtractor.get_mel (:151-200) and FeatureExtractor.get_energy (:114-146), which run per utterance. */
+int osb_mel_energy(const float* wav, const int64_t* lengths, const float* window, const float* fb, const int32_t* klo, const int32_t* khi,
+                   float* mel, float* energy, int32_t B, int32_t Lmax, int32_t Fmax, int32_t n_mels, int32_t n_fft, int32_t hop,
+                   int32_t win, float mag_eps, float clip_val, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -154,6 +154,15 @@ def load() -> C.CDLL:
         "osb_sequence_mask": [P, P, P, I32, I32, P],
         "osb_segment_starts": [P, P, P, I32, I32, I32, P],
         "osb_gather_segments": [P, P, P, I32, I64, I32, I32, I32, P],
+        "osb_mrd_first_fwd": [P, P, P, P, I32, I32, I32, I32, I32, I32, F, P],
+        "osb_mrd_first_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F, P],
+        "osb_spec_im2col_h16": [P, P, I32, I32, I32, I32, I32, I32, P],
+        "osb_spec_col2im": [P, P, I32, I32, I32, I32, I32, I32, F, P],
+        "osb_wim2col_h16": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, P],
+        "osb_wcol2im_h16": [P, P, I32, I32, I32, I32, I32, I32, I32, I32, P],
+        "osb_mrd_post_fwd": [P, P, P, P, I32, I32, I32, I32, P],
+        "osb_mrd_post_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
+        "osb_mel_energy": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, F, F, P],
         "osb_mpd_first_fwd": [P, P, P, P, I32, I32, I32, I32, I32, I32, I32, F, P],
         "osb_mpd_first_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, F, P],
         "osb_mpd_post_fwd": [P, P, P, P, I32, I32, I32, I32, I32, P],

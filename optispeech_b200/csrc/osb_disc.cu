@@ -360,6 +360,357 @@ l1_pair_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, c
   st_h8(db + i * 8, x);
 }
 
+// ------------------------------------------------------------------------------------------
+// Resolution discriminators (reference _discriminators.py:139-216): Conv2d stacks over magnitude spectrograms (NS, F, W).
+// Same flat layout, with the (signal, frame) pairs as the sequences and the frequency axis along the rows:
+//   row = (n * W_i + w) * P_i + h,  h < H_i valid, 64 channels per row;  P_5 = H_5 + 2, P_i = 2 P_(i+1) (every layer has
+//   stride 2 along frequency).  The kw taps along the frame axis are folded into the contraction by a small gather
+//   (wim2col: K = kw * 64), the kh taps along frequency are the implicit-GEMM taps with row stride 2.
+// ------------------------------------------------------------------------------------------
+constexpr int R1_KH = 7, R1_KW = 5, R1_TAPS = R1_KH * R1_KW;
+
+// layer 1 (Conv2d(1, 64, (7,5), (2,2), (3,2)) + LeakyReLU): one thread = 8 channels of one output row
+__global__ void __launch_bounds__(256)
+mrd_first_fwd_kernel(const float* __restrict__ spec, const float* __restrict__ w /*(64,35)*/, const float* __restrict__ bias,
+                     __half* __restrict__ out, int NS, int F, int W, int H1, int W1, int P1, float slope) {
+  __shared__ float sw[R1_TAPS][64];   // tap-major
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 64 * R1_TAPS; i += blockDim.x) sw[i % R1_TAPS][i / R1_TAPS] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rows = static_cast<long long>(NS) * W1 * P1;
+  if (i >= rows * 8) return;
+  const int cg = static_cast<int>(i & 7);
+  const long long row = i >> 3;
+  const int h = static_cast<int>(row % P1);
+  const int w1 = static_cast<int>((row / P1) % W1);
+  const int n = static_cast<int>(row / (static_cast<long long>(P1) * W1));
+  float v[8];
+  if (h >= H1) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sb[cg * 8 + q];
+    const float* sp = spec + static_cast<long long>(n) * F * W;
+    for (int kh = 0; kh < R1_KH; ++kh) {
+      const int f = 2 * h + kh - 3;
+      if (f < 0 || f >= F) continue;
+#pragma unroll
+      for (int kw = 0; kw < R1_KW; ++kw) {
+        const int t = 2 * w1 + kw - 2;
+        if (t < 0 || t >= W) continue;
+        const float x = sp[static_cast<long long>(f) * W + t];
+        const float* wt = &sw[kh * R1_KW + kw][cg * 8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaf(wt[q], x, v[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = lrelu(v[q], slope);
+  }
+  st_h8(out + row * 64 + cg * 8, v);
+}
+
+// d spec[n, f, t] = inv_scale * sum_{kh, kw: parity ok} sum_c w[c, kh, kw] * g[(n, w1, h1), c]   (g gated); one thread per input
+__global__ void __launch_bounds__(256)
+mrd_first_dx_kernel(const __half* __restrict__ g, const float* __restrict__ w, float* __restrict__ dspec, int NS, int F, int W, int H1,
+                    int W1, int P1, float inv_scale) {
+  __shared__ float sw[R1_TAPS][64];
+  for (int i = threadIdx.x; i < 64 * R1_TAPS; i += blockDim.x) sw[i % R1_TAPS][i / R1_TAPS] = w[i];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(NS) * F * W) return;
+  const int t = static_cast<int>(i % W);
+  const int f = static_cast<int>((i / W) % F);
+  const int n = static_cast<int>(i / (static_cast<long long>(W) * F));
+  float acc = 0.f;
+  for (int kh = 0; kh < R1_KH; ++kh) {
+    const int nh = f + 3 - kh;
+    if (nh < 0 || (nh & 1)) continue;
+    const int h1 = nh >> 1;
+    if (h1 >= H1) continue;
+    for (int kw = 0; kw < R1_KW; ++kw) {
+      const int nw = t + 2 - kw;
+      if (nw < 0 || (nw & 1)) continue;
+      const int w1 = nw >> 1;
+      if (w1 >= W1) continue;
+      const __half* gr = g + ((static_cast<long long>(n) * W1 + w1) * P1 + h1) * 64;
+      const float* wt = sw[kh * R1_KW + kw];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        float gv[8];
+        ld_h8(gr + c0, gv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fmaf(wt[c0 + q], gv[q], acc);
+      }
+    }
+  }
+  dspec[i] = acc * inv_scale;
+}
+
+// dW1[c, tap] += inv_scale * sum g[row, c] * spec[...];  db1[c] += inv_scale * sum g[row, c].  A lane owns 2 channels, a warp walks
+// rows (the 35 spectrogram values of a row are warp-uniform loads); block partials in shared memory, one atomic per element.
+__global__ void __launch_bounds__(256)
+mrd_first_dw_kernel(const __half* __restrict__ g, const float* __restrict__ spec, float* __restrict__ dw /*(64,35)*/, float* __restrict__ db,
+                    int NS, int F, int W, int H1, int W1, int P1, float inv_scale, long long rows_per_block) {
+  __shared__ float part[64 * (R1_TAPS + 1)];
+  for (int i = threadIdx.x; i < 64 * (R1_TAPS + 1); i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
+  const long long rows = static_cast<long long>(NS) * W1 * P1;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float a0[R1_TAPS + 1], a1[R1_TAPS + 1];
+#pragma unroll
+  for (int k = 0; k <= R1_TAPS; ++k) a0[k] = a1[k] = 0.f;
+  for (long long row = r0 + wip; row < r1; row += 8) {
+    const int h = static_cast<int>(row % P1);
+    if (h >= H1) continue;
+    const int w1 = static_cast<int>((row / P1) % W1);
+    const int n = static_cast<int>(row / (static_cast<long long>(P1) * W1));
+    const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(g + row * 64 + lane * 2));
+    const float* sp = spec + static_cast<long long>(n) * F * W;
+    a0[R1_TAPS] += gv.x;
+    a1[R1_TAPS] += gv.y;
+#pragma unroll
+    for (int kh = 0; kh < R1_KH; ++kh) {
+      const int f = 2 * h + kh - 3;
+#pragma unroll
+      for (int kw = 0; kw < R1_KW; ++kw) {
+        const int t = 2 * w1 + kw - 2;
+        const float x = (f >= 0 && f < F && t >= 0 && t < W) ? sp[static_cast<long long>(f) * W + t] : 0.f;
+        a0[kh * R1_KW + kw] = fmaf(gv.x, x, a0[kh * R1_KW + kw]);
+        a1[kh * R1_KW + kw] = fmaf(gv.y, x, a1[kh * R1_KW + kw]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k <= R1_TAPS; ++k) {
+    atomicAdd(&part[(lane * 2) * (R1_TAPS + 1) + k], a0[k]);
+    atomicAdd(&part[(lane * 2 + 1) * (R1_TAPS + 1) + k], a1[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * (R1_TAPS + 1); i += blockDim.x) {
+    const int c = i / (R1_TAPS + 1), k = i % (R1_TAPS + 1);
+    if (k < R1_TAPS) atomicAdd(dw + c * R1_TAPS + k, part[i] * inv_scale);
+    else atomicAdd(db + c, part[i] * inv_scale);
+  }
+}
+
+// xcol[(n, wo, h), kw*C + c] = x[(n, wo*sw + kw - pw, h), c]  (zero outside [0, W_in)); 8 channels per thread
+__global__ void __launch_bounds__(256)
+wim2col_kernel(const __half* __restrict__ x, __half* __restrict__ xcol, int NS, int W_in, int W_out, int P, int C, int KW, int pw, int sw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = KW * C / 8;
+  const long long rows = static_cast<long long>(NS) * W_out * P;
+  if (i >= rows * groups) return;
+  const int gidx = static_cast<int>(i % groups);
+  const long long row = i / groups;
+  const int kw = gidx / (C / 8), cg = gidx % (C / 8);
+  const int h = static_cast<int>(row % P);
+  const int wo = static_cast<int>((row / P) % W_out);
+  const long long n = row / (static_cast<long long>(P) * W_out);
+  const int wi = wo * sw + kw - pw;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (wi >= 0 && wi < W_in) v = *reinterpret_cast<const uint4*>(x + ((n * W_in + wi) * P + h) * C + cg * 8);
+  *reinterpret_cast<uint4*>(xcol + row * (KW * C) + kw * C + cg * 8) = v;
+}
+
+// dx[(n, w, h), c] = sum_{kw: (w + pw - kw) % sw == 0, wo in range} dxcol[(n, wo, h), kw*C + c]
+__global__ void __launch_bounds__(256)
+wcol2im_kernel(const __half* __restrict__ dxcol, __half* __restrict__ dx, int NS, int W_in, int W_out, int P, int C, int KW, int pw, int sw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = C / 8;
+  const long long rows = static_cast<long long>(NS) * W_in * P;
+  if (i >= rows * groups) return;
+  const int cg = static_cast<int>(i % groups);
+  const long long row = i / groups;
+  const int h = static_cast<int>(row % P);
+  const int wi = static_cast<int>((row / P) % W_in);
+  const long long n = row / (static_cast<long long>(P) * W_in);
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  for (int kw = 0; kw < KW; ++kw) {
+    const int num = wi + pw - kw;
+    if (num < 0 || num % sw != 0) continue;
+    const int wo = num / sw;
+    if (wo >= W_out) continue;
+    float v[8];
+    ld_h8(dxcol + ((n * W_out + wo) * P + h) * (KW * C) + kw * C + cg * 8, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += v[q];
+  }
+  st_h8(dx + row * C + cg * 8, acc);
+}
+
+// conv_post (Conv2d(64, 1, (3,3), padding 1)): score[n, h*W + w] = b + sum_{kh,kw,c} w[c,kh,kw] x[(n, w+kw-1, h+kh-1), c]; 8 lanes per output
+__global__ void __launch_bounds__(256)
+mrd_post_fwd_kernel(const __half* __restrict__ x, const float* __restrict__ w /*(64,9)*/, const float* __restrict__ bias, float* __restrict__ out,
+                    int NS, int W, int H, int P) {
+  __shared__ float sw9[9][64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw9[i % 9][i / 9] = w[i];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long o = i >> 3;
+  const int cg = static_cast<int>(i & 7);
+  const bool live = o < static_cast<long long>(NS) * W * H;
+  float acc = 0.f;
+  int h = 0, wv = 0;
+  long long n = 0;
+  if (live) {
+    h = static_cast<int>(o % H);
+    wv = static_cast<int>((o / H) % W);
+    n = o / (static_cast<long long>(H) * W);
+    for (int kw = 0; kw < 3; ++kw) {
+      const int wi = wv + kw - 1;
+      if (wi < 0 || wi >= W) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hi = h + kh - 1;
+        if (hi < 0 || hi >= H) continue;
+        float xv[8];
+        ld_h8(x + ((n * W + wi) * P + hi) * 64 + cg * 8, xv);
+        const float* wt = &sw9[kh * 3 + kw][cg * 8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fmaf(wt[q], xv[q], acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && cg == 0) out[n * (static_cast<long long>(H) * W) + static_cast<long long>(h) * W + wv] = acc + bias[0];
+}
+
+// dx[(n, w, h), c] = scale * sum_{kh,kw} w[c,kh,kw] dscore[n, (h-kh+1)*W + (w-kw+1)]   (fp16; zero on the gap rows)
+__global__ void __launch_bounds__(256)
+mrd_post_dx_kernel(const float* __restrict__ dscore, const float* __restrict__ w, __half* __restrict__ dx, int NS, int W, int H, int P, float scale) {
+  __shared__ float sw9[9][64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw9[i % 9][i / 9] = w[i];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rows = static_cast<long long>(NS) * W * P;
+  if (i >= rows * 8) return;
+  const int cg = static_cast<int>(i & 7);
+  const long long row = i >> 3;
+  const int h = static_cast<int>(row % P);
+  const int wv = static_cast<int>((row / P) % W);
+  const long long n = row / (static_cast<long long>(P) * W);
+  float v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  if (h < H) {
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ho = h - kh + 1;
+      if (ho < 0 || ho >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wo = wv - kw + 1;
+        if (wo < 0 || wo >= W) continue;
+        const float d = dscore[n * (static_cast<long long>(H) * W) + static_cast<long long>(ho) * W + wo] * scale;
+        const float* wt = &sw9[kh * 3 + kw][cg * 8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaf(wt[q], d, v[q]);
+      }
+    }
+  }
+  st_h8(dx + row * 64 + cg * 8, v);
+}
+
+// dw[c, kh, kw] += sum dscore[n, ho, wo] x[(n, wo+kw-1, ho+kh-1), c];  db += sum dscore.  Thread = 8 channels of an INPUT row.
+__global__ void __launch_bounds__(256)
+mrd_post_dw_kernel(const float* __restrict__ dscore, const __half* __restrict__ x, float* __restrict__ dw /*(64,9)*/, float* __restrict__ db,
+                   int NS, int W, int H, int P, long long rows_per_block) {
+  __shared__ float part[64 * 9 + 1];
+  for (int i = threadIdx.x; i < 64 * 9 + 1; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7, rsub = threadIdx.x >> 3;   // 32 rows per trip
+  const long long rows = static_cast<long long>(NS) * W * P;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float aw[8][9];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) aw[q][k] = 0.f;
+  float ab = 0.f;
+  for (long long row = r0 + rsub; row < r1; row += 32) {
+    const int hi = static_cast<int>(row % P);
+    if (hi >= H) continue;
+    const int wi = static_cast<int>((row / P) % W);
+    const long long n = row / (static_cast<long long>(P) * W);
+    float xv[8];
+    ld_h8(x + row * 64 + cg * 8, xv);
+    const float* ds = dscore + n * (static_cast<long long>(H) * W);
+    if (cg == 0) ab += ds[static_cast<long long>(hi) * W + wi];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ho = hi - kh + 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wo = wi - kw + 1;
+        const float d = (ho >= 0 && ho < H && wo >= 0 && wo < W) ? ds[static_cast<long long>(ho) * W + wo] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) aw[q][kh * 3 + kw] = fmaf(d, xv[q], aw[q][kh * 3 + kw]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(&part[(cg * 8 + q) * 9 + k], aw[q][k]);
+  if (cg == 0) atomicAdd(&part[64 * 9], ab);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) atomicAdd(dw + i, part[i]);
+  if (threadIdx.x == 0) atomicAdd(db, part[64 * 9]);
+}
+
+// Layer 1 of a resolution discriminator as a GEMM: xcol[(n, w1, h1), tap] = spec[n, 2 h1 + kh - 3, 2 w1 + kw - 2], tap = kh*5 + kw < 35,
+// zero for taps 35..63, outside the spectrogram and on the gap rows (h1 >= H1).  8 columns per thread.
+__global__ void __launch_bounds__(256)
+spec_im2col_kernel(const float* __restrict__ spec, __half* __restrict__ xcol, int NS, int F, int W, int H1, int W1, int P1) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long rows = static_cast<long long>(NS) * W1 * P1;
+  if (i >= rows * 8) return;
+  const int cg = static_cast<int>(i & 7);
+  const long long row = i >> 3;
+  const int h = static_cast<int>(row % P1);
+  const int w1 = static_cast<int>((row / P1) % W1);
+  const int n = static_cast<int>(row / (static_cast<long long>(P1) * W1));
+  float v[8];
+  const float* sp = spec + static_cast<long long>(n) * F * W;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int tap = cg * 8 + q;
+    const int kh = tap / R1_KW, kw = tap % R1_KW;
+    const int f = 2 * h + kh - 3, t = 2 * w1 + kw - 2;
+    v[q] = (tap < R1_TAPS && h < H1 && f >= 0 && f < F && t >= 0 && t < W) ? sp[static_cast<long long>(f) * W + t] : 0.f;
+  }
+  st_h8(xcol + row * 64 + cg * 8, v);
+}
+
+// adjoint: dspec[n, f, t] = inv_scale * sum_{kh, kw with matching parity} col[(n, w1, h1), kh*5 + kw]   (col = g . W1, fp16)
+__global__ void __launch_bounds__(256)
+spec_col2im_kernel(const __half* __restrict__ col, float* __restrict__ dspec, int NS, int F, int W, int H1, int W1, int P1, float inv_scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(NS) * F * W) return;
+  const int t = static_cast<int>(i % W);
+  const int f = static_cast<int>((i / W) % F);
+  const int n = static_cast<int>(i / (static_cast<long long>(W) * F));
+  float acc = 0.f;
+  for (int kh = (f + 3) & 1; kh < R1_KH; kh += 2) {
+    const int h1 = (f + 3 - kh) >> 1;
+    if (f + 3 - kh < 0 || h1 >= H1) continue;
+    for (int kw = (t + 2) & 1; kw < R1_KW; kw += 2) {
+      const int w1 = (t + 2 - kw) >> 1;
+      if (t + 2 - kw < 0 || w1 >= W1) continue;
+      acc += __half2float(col[((static_cast<long long>(n) * W1 + w1) * P1 + h1) * 64 + kh * R1_KW + kw]);
+    }
+  }
+  dspec[i] = acc * inv_scale;
+}
+
 inline unsigned grid_for(long long n, int block) { return static_cast<unsigned>((n + block - 1) / block); }
 
 }  // namespace
@@ -477,6 +828,117 @@ extern "C" int osb_l1_pair_bwd(const void* a_h16, const void* b_h16, const float
   OSB_REQUIRE(n > 0 && n % 8 == 0, OSB_ERR_SHAPE);
   l1_pair_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(a_h16), static_cast<const __half*>(b_h16),
                                                                                       coef, scale, static_cast<__half*>(db_h16), n / 8);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mrd_first_fwd(const float* spec, const float* w, const float* bias, void* out_h16, int32_t NS, int32_t F, int32_t W,
+                                 int32_t H1, int32_t W1, int32_t P1, float slope, void* stream) {
+  OSB_REQUIRE(spec && w && bias && out_h16, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && F > 0 && W > 0 && H1 > 0 && W1 > 0 && P1 >= H1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * W1 * P1 * 8;
+  mrd_first_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(spec, w, bias, static_cast<__half*>(out_h16), NS, F, W, H1, W1,
+                                                                                       P1, slope);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mrd_first_bwd(const void* g_h16, const float* spec, const float* w, float* dspec, float* dw, float* db, int32_t NS, int32_t F,
+                                 int32_t W, int32_t H1, int32_t W1, int32_t P1, float inv_scale, void* stream) {
+  OSB_REQUIRE(g_h16 && spec && w, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && F > 0 && W > 0 && H1 > 0 && W1 > 0 && P1 >= H1, OSB_ERR_SHAPE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __half* g = static_cast<const __half*>(g_h16);
+  int launched = 0;
+  if (dspec != nullptr) {   // written (not accumulated)
+    const long long n = static_cast<long long>(NS) * F * W;
+    mrd_first_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(g, w, dspec, NS, F, W, H1, W1, P1, inv_scale);
+    ++launched;
+  }
+  if (dw != nullptr && db != nullptr) {   // accumulated (+=): the caller zeroes them
+    const long long rows = static_cast<long long>(NS) * W1 * P1;
+    long long blocks = (rows + 511) / 512;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    mrd_first_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(g, spec, dw, db, NS, F, W, H1, W1, P1, inv_scale, rpb);
+    ++launched;
+  }
+  count_launch(launched);
+  return launch_status();
+}
+
+extern "C" int osb_wim2col_h16(const void* x, void* xcol, int32_t NS, int32_t W_in, int32_t W_out, int32_t P, int32_t C, int32_t KW, int32_t pw,
+                               int32_t sw, void* stream) {
+  OSB_REQUIRE(x && xcol, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && W_in > 0 && W_out > 0 && P > 0 && C % 8 == 0 && KW > 0 && sw >= 1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * W_out * P * (KW * C / 8);
+  wim2col_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x), static_cast<__half*>(xcol), NS, W_in,
+                                                                               W_out, P, C, KW, pw, sw);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_wcol2im_h16(const void* dxcol, void* dx, int32_t NS, int32_t W_in, int32_t W_out, int32_t P, int32_t C, int32_t KW, int32_t pw,
+                               int32_t sw, void* stream) {
+  OSB_REQUIRE(dxcol && dx, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && W_in > 0 && W_out > 0 && P > 0 && C % 8 == 0 && KW > 0 && sw >= 1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * W_in * P * (C / 8);
+  wcol2im_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dxcol), static_cast<__half*>(dx), NS, W_in,
+                                                                               W_out, P, C, KW, pw, sw);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mrd_post_fwd(const void* x_h16, const float* w, const float* bias, float* score, int32_t NS, int32_t W, int32_t H, int32_t P,
+                                void* stream) {
+  OSB_REQUIRE(x_h16 && w && bias && score, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && W > 0 && H > 0 && P >= H, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * W * H * 8;
+  mrd_post_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x_h16), w, bias, score, NS, W, H, P);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_mrd_post_bwd(const float* dscore, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NS, int32_t W,
+                                int32_t H, int32_t P, float scale, void* stream) {
+  OSB_REQUIRE(dscore && w, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && W > 0 && H > 0 && P >= H, OSB_ERR_SHAPE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int launched = 0;
+  if (dx_h16 != nullptr) {
+    const long long n = static_cast<long long>(NS) * W * P * 8;
+    mrd_post_dx_kernel<<<grid_for(n, 256), 256, 0, s>>>(dscore, w, static_cast<__half*>(dx_h16), NS, W, H, P, scale);
+    ++launched;
+  }
+  if (dw != nullptr && db != nullptr && x_h16 != nullptr) {   // accumulated (+=)
+    const long long rows = static_cast<long long>(NS) * W * P;
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    const long long rpb = (rows + blocks - 1) / blocks;
+    mrd_post_dw_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(dscore, static_cast<const __half*>(x_h16), dw, db, NS, W, H, P, rpb);
+    ++launched;
+  }
+  count_launch(launched);
+  return launch_status();
+}
+
+extern "C" int osb_spec_im2col_h16(const float* spec, void* xcol, int32_t NS, int32_t F, int32_t W, int32_t H1, int32_t W1, int32_t P1,
+                                   void* stream) {
+  OSB_REQUIRE(spec && xcol, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && F > 0 && W > 0 && H1 > 0 && W1 > 0 && P1 >= H1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * W1 * P1 * 8;
+  spec_im2col_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(spec, static_cast<__half*>(xcol), NS, F, W, H1, W1, P1);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_spec_col2im(const void* col_h16, float* dspec, int32_t NS, int32_t F, int32_t W, int32_t H1, int32_t W1, int32_t P1,
+                               float inv_scale, void* stream) {
+  OSB_REQUIRE(col_h16 && dspec, OSB_ERR_ARG);
+  OSB_REQUIRE(NS > 0 && F > 0 && W > 0 && H1 > 0 && W1 > 0 && P1 >= H1, OSB_ERR_SHAPE);
+  const long long n = static_cast<long long>(NS) * F * W;
+  spec_col2im_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(col_h16), dspec, NS, F, W, H1, W1,
+                                                                                     P1, inv_scale);
   count_launch();
   return launch_status();
 }

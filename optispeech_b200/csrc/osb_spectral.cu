@@ -244,6 +244,118 @@ int dispatch_spec(int n_fft, const SpecParams& p, cudaStream_t stream) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Feature extraction (reference dataset/feature_extractors/__init__.py:110-200, `CommonFeatureExtractor.get_mel` and
+// `FeatureExtractor.get_energy`): reflect padding by (n_fft - hop)/2 on both sides, framing WITHOUT centring, Hann window,
+// magnitude sqrt(re^2 + im^2 + 1e-9), then   energy[f] = || mag[f, :] ||_2   and   mel[j, f] = log(max(sum_k fb[j,k] mag[f,k], 1e-5)).
+// One CTA transforms two consecutive frames of one utterance with ONE complex FFT (z = frame_a + i*frame_b); every utterance
+// is padded by its OWN length (a batch of ragged utterances gives what the per-utterance reference loop gives).
+// ------------------------------------------------------------------------------------------
+struct FeatParams {
+  const float* wav;           // (B, Lmax)
+  const long long* lengths;   // (B) samples
+  const float* window;        // (win)
+  const float* fb;            // (n_mels, N/2+1) row-major (librosa layout)
+  const int* klo; const int* khi;   // (n_mels) non-zero bin range of every filter
+  float* mel;                 // (B, n_mels, Fmax), zero for frames >= length/hop
+  float* energy;              // (B, Fmax)
+  int B, Lmax, hop, win, Fmax, n_mels;
+  float mag_eps, clip_val;
+};
+
+template <int N>
+__global__ void __launch_bounds__(FFT_THREADS) mel_energy_kernel(const FeatParams p) {
+  extern __shared__ float2 sp_smem[];
+  float2* s = sp_smem;
+  float2* tw = s + N;
+  constexpr int NB = N / 2 + 1;
+  float* maga = reinterpret_cast<float*>(tw + N / 2);   // [NB]
+  float* magb = maga + NB;                              // [NB]
+  __shared__ float red[2][FFT_THREADS / 32];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int fa = 2 * blockIdx.x, fb_ = fa + 1;
+  const int L = static_cast<int>(p.lengths[b]);
+  const int frames = L / p.hop;
+  const int pad = (N - p.hop) / 2;
+  const int off = (N - p.win) / 2;
+  const float* w = p.wav + static_cast<long long>(b) * p.Lmax;
+  const bool va = fa < frames, vb = fb_ < frames;
+  if (!va) {   // both frames past the utterance: zeros
+    for (int j = tid; j < p.n_mels; j += FFT_THREADS) {
+      if (fa < p.Fmax) p.mel[(static_cast<long long>(b) * p.n_mels + j) * p.Fmax + fa] = 0.f;
+      if (fb_ < p.Fmax) p.mel[(static_cast<long long>(b) * p.n_mels + j) * p.Fmax + fb_] = 0.f;
+    }
+    if (tid == 0) {
+      if (fa < p.Fmax) p.energy[static_cast<long long>(b) * p.Fmax + fa] = 0.f;
+      if (fb_ < p.Fmax) p.energy[static_cast<long long>(b) * p.Fmax + fb_] = 0.f;
+    }
+    return;
+  }
+  for (int k = tid; k < N / 2; k += FFT_THREADS) {
+    float sn, cs;
+    sincospif(-2.0f * static_cast<float>(k) / static_cast<float>(N), &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+  }
+  for (int n = tid; n < N; n += FFT_THREADS) {
+    float2 v = make_float2(0.f, 0.f);
+    const int m = n - off;
+    if (m >= 0 && m < p.win) {
+      const float wn = p.window[m];
+      v.x = wn * w[reflect_index(fa * p.hop + n - pad, L)];
+      if (vb) v.y = wn * w[reflect_index(fb_ * p.hop + n - pad, L)];
+    }
+    s[bitrev<N>(n)] = v;
+  }
+  __syncthreads();
+  fft_inplace<N, false>(s, tw);
+  float ea = 0.f, eb = 0.f;
+  for (int k = tid; k < NB; k += FFT_THREADS) {
+    const float2 zk = s[k], zn = s[(N - k) & (N - 1)];
+    const float xr = 0.5f * (zk.x + zn.x), xi = 0.5f * (zk.y - zn.y);
+    const float yr = 0.5f * (zk.y + zn.y), yi = -0.5f * (zk.x - zn.x);
+    const float pa = xr * xr + xi * xi + p.mag_eps, pb = yr * yr + yi * yi + p.mag_eps;
+    maga[k] = sqrtf(pa);
+    magb[k] = sqrtf(pb);
+    ea += pa;
+    eb += pb;
+  }
+  ea = warp_sum(ea); eb = warp_sum(eb);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = ea; red[1][tid >> 5] = eb; }
+  __syncthreads();
+  if (tid == 0) {
+    float ra = 0.f, rb = 0.f;
+    for (int i = 0; i < FFT_THREADS / 32; ++i) { ra += red[0][i]; rb += red[1][i]; }
+    p.energy[static_cast<long long>(b) * p.Fmax + fa] = sqrtf(ra);
+    if (fb_ < p.Fmax) p.energy[static_cast<long long>(b) * p.Fmax + fb_] = vb ? sqrtf(rb) : 0.f;
+  }
+  for (int j = tid; j < p.n_mels; j += FFT_THREADS) {
+    float ma = 0.f, mb = 0.f;
+    const float* frow = p.fb + static_cast<long long>(j) * NB;
+    for (int k = p.klo[j]; k <= p.khi[j]; ++k) {
+      const float wk = frow[k];
+      ma = fmaf(wk, maga[k], ma);
+      mb = fmaf(wk, magb[k], mb);
+    }
+    float* mrow = p.mel + (static_cast<long long>(b) * p.n_mels + j) * p.Fmax;
+    mrow[fa] = logf(fmaxf(ma, p.clip_val));
+    if (fb_ < p.Fmax) mrow[fb_] = vb ? logf(fmaxf(mb, p.clip_val)) : 0.f;
+  }
+}
+
+template <int N>
+int launch_feat(const FeatParams& p, cudaStream_t stream) {
+  const size_t smem = sizeof(float2) * (N + N / 2) + sizeof(float) * 2 * (N / 2 + 1);
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mel_energy_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  mel_energy_kernel<N><<<dim3((p.Fmax + 1) / 2, p.B), FFT_THREADS, smem, stream>>>(p);
+  count_launch();
+  return launch_status();
+}
+
 }  // namespace
 }  // namespace osb
 
@@ -280,4 +392,22 @@ extern "C" int osb_mel_loss(const float* x_hat, const float* y, const float* win
     return dispatch_spec<true, true>(n_fft, p, s);
   }
   return dispatch_spec<true, false>(n_fft, p, s);
+}
+
+extern "C" int osb_mel_energy(const float* wav, const int64_t* lengths, const float* window, const float* fb, const int32_t* klo,
+                              const int32_t* khi, float* mel, float* energy, int32_t B, int32_t Lmax, int32_t Fmax, int32_t n_mels,
+                              int32_t n_fft, int32_t hop, int32_t win, float mag_eps, float clip_val, void* stream) {
+  OSB_REQUIRE(wav && lengths && window && fb && klo && khi && mel && energy, OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Lmax > n_fft / 2 && hop > 0 && hop <= n_fft && win > 0 && win <= n_fft && Fmax > 0 && n_mels > 0, OSB_ERR_SHAPE);
+  FeatParams p{};
+  p.wav = wav; p.lengths = reinterpret_cast<const long long*>(lengths); p.window = window; p.fb = fb; p.klo = klo; p.khi = khi;
+  p.mel = mel; p.energy = energy; p.B = B; p.Lmax = Lmax; p.hop = hop; p.win = win; p.Fmax = Fmax; p.n_mels = n_mels;
+  p.mag_eps = mag_eps; p.clip_val = clip_val;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (n_fft) {
+    case 512: return launch_feat<512>(p, s);
+    case 1024: return launch_feat<1024>(p, s);
+    case 2048: return launch_feat<2048>(p, s);
+    default: return OSB_ERR_SHAPE;
+  }
 }

@@ -121,23 +121,37 @@ class BaseModule(nn.Module):
 
     # -- reference training logic -------------------------------------------------------------------
     def _upload_early(self, batch):
-        """Enqueue the host -> device copies of the batch's (pinned) host tensors NOW, into persistent device buffers, and return
-        the batch with those entries replaced: the DMA transfers then run while the host cuts the waveform crop."""
+        """Enqueue the host -> device copies of the batch's (pinned) host tensors NOW, on a copy stream, into a ring of
+        persistent device buffers, and return the batch with those entries replaced.  The DMA transfers run while the host
+        cuts the waveform crop — and while the PREVIOUS step still computes: the compute stream only waits for the copy
+        event, and a buffer set is overwritten only after the step that read it has passed its release event."""
         dev = self.device
         if dev.type != "cuda":
             return batch
-        bufs = self.__dict__.setdefault("_upload_bufs", {})
+        st = self.__dict__.setdefault("_upload_state", {"stream": torch.cuda.Stream(device=dev), "sets": {}, "turn": 0})
+        copy_stream = st["stream"]
+        turn = st["turn"] % 3
+        st["turn"] += 1
         out = dict(batch)
-        for k, v in batch.items():
-            if k == "wav" or not isinstance(v, torch.Tensor) or v.is_cuda:
-                continue
-            key = (k, tuple(v.shape), v.dtype)
-            buf = bufs.get(key)
-            if buf is None:
-                buf = torch.empty(v.shape, dtype=v.dtype, device=dev)
-                bufs[key] = buf
-            buf.copy_(v, non_blocking=True)
-            out[k] = buf
+        main = torch.cuda.current_stream(dev)
+        rel = st.get(("released", turn))
+        if rel is not None:
+            copy_stream.wait_event(rel)           # the step that last read this buffer set has been enqueued and passed
+        with torch.cuda.stream(copy_stream):
+            for k, v in batch.items():
+                if k == "wav" or not isinstance(v, torch.Tensor) or v.is_cuda:
+                    continue
+                key = (turn, k, tuple(v.shape), v.dtype)
+                buf = st["sets"].get(key)
+                if buf is None:
+                    buf = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                    st["sets"][key] = buf
+                buf.copy_(v, non_blocking=True)
+                out[k] = buf
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        main.wait_event(ev)
+        self._upload_turn = turn
         return out
 
     def stage_batch(self, batch, upload: bool = False):
@@ -201,6 +215,12 @@ class BaseModule(nn.Module):
             ev = slot["event"] or torch.cuda.Event()
             ev.record()
             slot["event"] = ev
+        turn = self.__dict__.pop("_upload_turn", None)
+        if turn is not None and self.device.type == "cuda":   # the uploaded buffer set may be overwritten once this point has passed
+            st = self._upload_state
+            ev = st.get(("released", turn)) or torch.cuda.Event()
+            ev.record()
+            st[("released", turn)] = ev
 
     @staticmethod
     def batch_h2d_bytes(batch) -> int:

@@ -3,7 +3,8 @@
 The module tree is the reference's, so that `state_dict` keys (weight-norm `weight_g` / `weight_v` included) are
 interchangeable.  On CUDA tensors the period discriminators run on this package's kernels (disc/native.py: tcgen05 implicit
 GEMMs over a flat fp16 sequence layout; feature maps come back as `native.FlatMap`, `.dense()` gives the reference's
-(B, C, L, period) tensor).  The resolution discriminators (Conv2d over spectrograms) run on stock PyTorch / cuDNN.
+(B, C, L, period) tensor), and so do the resolution discriminators (rectangular-window |STFT| by torch.stft / cuFFT, then the
+Conv2d stack as gathers + tcgen05 implicit GEMMs).  CPU tensors take the stock PyTorch path (module-tree / state_dict tests).
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ from torch.nn.utils import weight_norm
 
 
 NATIVE_MPD = True   # False: the period discriminators run on cuDNN as well (A/B comparisons in tests and bench.py)
+NATIVE_MRD = True   # likewise for the resolution discriminators
 
 
 def _wn_conv(cin, cout, kernel, stride, padding):
@@ -81,6 +83,9 @@ class DiscriminatorR(nn.Module):
                           return_complex=True).abs()
 
     def forward(self, x: torch.Tensor):
+        if x.is_cuda and NATIVE_MRD:
+            from . import native
+            return native.resolution_forward(self, x)
         x = self.spectrogram(x).unsqueeze(1)
         fmap = []
         for conv in self.convs:
@@ -121,3 +126,13 @@ class MultiResolutionDiscriminator(_Multi):
     def __init__(self, resolutions=((1024, 256, 1024), (2048, 512, 2048), (512, 128, 512))):
         super().__init__()
         self.discriminators = nn.ModuleList([DiscriminatorR(resolution=r) for r in resolutions])
+
+    def forward(self, y: torch.Tensor, y_hat: torch.Tensor):
+        if not (y.is_cuda and NATIVE_MRD):
+            return super().forward(y, y_hat)
+        from . import native
+        real, fake, fr, ff = [], [], [], []
+        for d in self.discriminators:
+            a, b, fa, fb = native.resolution_forward_pair(d, y, y_hat)
+            real.append(a); fr.append(fa); fake.append(b); ff.append(fb)
+        return real, fake, fr, ff

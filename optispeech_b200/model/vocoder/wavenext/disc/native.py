@@ -139,13 +139,13 @@ class _ConvFn(torch.autograd.Function):
                                     pad=KSIZE - 1 - PAD, w_mn=True, tap_reverse=True, N=cin_p)
                 dx = dx.view(rows_in, cin_p)
             else:
-                # per-tap products in one GEMM (N = 5 * Cin_p), gathered by col2im: row r of g meets input row 3r + tap - 2
-                w3 = w.reshape(cout, cin, KSIZE)
+                # phase decomposition: one stride-1 GEMM over g writes the three interleaved input-row phases side by side
+                w4 = w.detach().reshape(cout, cin, KSIZE, 1)
                 if cin_p != cin:
-                    w3 = F.pad(w3, (0, 0, 0, cin_p - cin))
-                wt = ops.pack_conv_h16(w3, transpose_reverse=True).view(1, KSIZE * cin_p, cout)
-                _, col, _ = ops.gemm(g.view(1, rows_out, cout), wt, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
-                dx = ops.col2im_h16(col.view(rows_out, KSIZE * cin_p), rows_in, cin_p, KSIZE, PAD, stride, reversed_taps=True)
+                    w4 = F.pad(w4, (0, 0, 0, 0, 0, cin_p - cin))
+                wd, dpad = _phase_dgrad_pack(w4, PAD, stride)
+                _, dxp, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=dpad)
+                dx = dxp.view(rows_in, cin_p)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -238,6 +238,175 @@ def period_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
         return sr, sg, fr, fg
     B = y.shape[0]
     s, f = period_forward(disc, torch.cat((y.float(), y_hat.float()), dim=0), layers)
+    fr = [m.half(0) if isinstance(m, FlatMap) else m[:B] for m in f]
+    fg = [m.half(1) if isinstance(m, FlatMap) else m[B:] for m in f]
+    return s[:B], s[B:], fr, fg
+
+
+# --------------------------------------------------------------------------------------------------
+# Resolution discriminators (reference _discriminators.py:139-216) on the same flat layout: sequences are (signal, frame)
+# pairs, rows run along frequency.  `FlatMap(data, period=W, L=H, P)` and its `dense()` -> (N, 64, H, W) apply unchanged.
+# --------------------------------------------------------------------------------------------------
+MRD_LAYERS = ((7, 5, 2, 2, 3, 2), (5, 3, 2, 1, 2, 1), (5, 3, 2, 2, 2, 1), (3, 3, 2, 1, 1, 1), (3, 3, 2, 2, 1, 1))  # kh, kw, sh, sw, ph, pw
+
+
+@dataclass(frozen=True)
+class GeometryR:
+    H: Tuple[int, ...]   # valid frequency rows: H[0] = bins of the spectrogram, H[1..5] layer outputs
+    W: Tuple[int, ...]   # frames
+    P: Tuple[int, ...]   # rows a (signal, frame) sequence owns in layer i's matrix (P[0] unused)
+
+    @staticmethod
+    def make(F_bins: int, frames: int) -> "GeometryR":
+        H, W = [F_bins], [frames]
+        for kh, kw, sh, sw, ph, pw in MRD_LAYERS:
+            H.append((H[-1] + 2 * ph - kh) // sh + 1)
+            W.append((W[-1] + 2 * pw - kw) // sw + 1)
+        p5 = H[5] + 2
+        P = (0, p5 * 16, p5 * 8, p5 * 4, p5 * 2, p5)
+        for i in range(1, 5):
+            assert P[i] >= H[i] + 2, (P, H)
+        return GeometryR(tuple(H), tuple(W), P)
+
+
+class _RFirstFn(torch.autograd.Function):
+    """Layer 1 (Conv2d(1, 64, (7,5), (2,2), (3,2)) + LeakyReLU) as a GEMM: the 35 taps of every output position are gathered
+    into a 64-wide fp16 row (osb_spec_im2col_h16), which is also the operand of the weight gradient."""
+
+    @staticmethod
+    def forward(ctx, spec, w, bias, geom: GeometryR, slope: float):
+        xcol = ops.spec_im2col_h16(spec, geom.H[1], geom.W[1], geom.P[1])
+        rows = xcol.shape[0]
+        wp = F.pad(w.detach().reshape(64, 35), (0, 29)).to(torch.float16).view(1, 64, 64)
+        _, y, _ = ops.gemm(xcol.view(1, rows, 64), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
+                           bias=bias, seq_rows=(geom.P[1], geom.H[1]), lrelu=slope)
+        y = y.view(rows, 64)
+        ctx.save_for_backward(xcol, w, y)
+        ctx.geom, ctx.slope, ctx.spec_shape = geom, slope, tuple(spec.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xcol, w, y = ctx.saved_tensors
+        geom = ctx.geom
+        rows = y.shape[0]
+        g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
+        dspec = dw = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dwp = torch.zeros((1, 64, 64), device=g.device, dtype=torch.float32)
+            ops.gemm_wgrad(g.view(1, rows, 64), xcol.view(1, rows, 64), dwp)
+            dw = (dwp[0, :, :35] * (1.0 / GRAD_SCALE)).reshape(w.shape)
+            db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
+        if ctx.needs_input_grad[0]:
+            wd = F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64)   # [tap][cout]
+            _, col, _ = ops.gemm(g.view(1, rows, 64), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
+            dspec = ops.spec_col2im(col.view(rows, 64), ctx.spec_shape, geom.H[1], geom.W[1], geom.P[1], 1.0 / GRAD_SCALE)
+        return dspec, dw, db, None, None
+
+
+def _phase_dgrad_pack(w: torch.Tensor, ph: int, stride: int = 2):
+    """Data gradient of a strided convolution along the rows as ONE stride-1 GEMM over the output-gradient rows: input row
+    stride*m + phi collects g[m + d] . W[kh] for the taps with phi + ph - kh = stride*d.  All phases share the tap offsets d
+    and sit side by side in the N dimension, so the (rows_out, stride*K) result IS the (stride*rows_out, K) input-gradient
+    matrix — no per-tap product buffer, no scatter.   w (cout, cin, kh, kw) -> (fp16 (taps, stride*kw*cin, cout), pad)."""
+    cout, cin, kh, kw = w.shape
+    terms = [(phi, k, (phi + ph - k) // stride) for phi in range(stride) for k in range(kh) if (phi + ph - k) % stride == 0]
+    d_min, d_max = min(t[2] for t in terms), max(t[2] for t in terms)
+    wd = torch.zeros((d_max - d_min + 1, stride, kw, cin, cout), device=w.device, dtype=torch.float32)
+    for phi, k, d in terms:
+        wd[d - d_min, phi] = w[:, :, k, :].permute(2, 1, 0)
+    return wd.reshape(d_max - d_min + 1, stride * kw * cin, cout).to(torch.float16).contiguous(), -d_min
+
+
+class _RConvFn(torch.autograd.Function):
+    """One Conv2d(64, 64, (kh, kw), (2, sw)) + LeakyReLU: x (NS*W_in*P_in, 64) -> y (NS*W_out*P_out, 64)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, NS: int, W_in: int, W_out: int, P_in: int, P_out: int, H_out: int, layer, slope: float):
+        kh, kw, _sh, sw, ph, pw = layer
+        xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)
+        cout, cin = w.shape[0], w.shape[1]
+        wp = w.detach().permute(2, 0, 3, 1).reshape(kh, cout, kw * cin).to(torch.float16).contiguous()     # [kh][cout][(kw, cin)]
+        rows_in = xcol.shape[0]
+        _, y, _ = ops.gemm(xcol.view(1, rows_in, kw * cin), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
+                           pad=ph, bias=bias, seq_rows=(P_out, H_out), row_stride=2, lrelu=slope)
+        y = y.view(rows_in // 2, cout)
+        ctx.save_for_backward(x, w, y)
+        ctx.geo = (NS, W_in, W_out, P_in, P_out, H_out, layer, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        NS, W_in, W_out, P_in, P_out, H_out, layer, slope = ctx.geo
+        kh, kw, _sh, sw, ph, pw = layer
+        cout, cin = w.shape[0], w.shape[1]
+        g = ops.lrelu_bwd_h16(gy.contiguous(), y, P_out, H_out, slope)
+        rows_out = y.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)      # recomputed: cheaper than keeping 3x the activation
+            dwp = torch.zeros((kh, cout, kw * cin), device=x.device, dtype=torch.float32)
+            ops.gemm_wgrad_strided(g, xcol, dwp, taps=kh, pad=ph, stride=2)
+            dw = (dwp.view(kh, cout, kw, cin).permute(1, 3, 0, 2) * (1.0 / GRAD_SCALE)).contiguous()
+            db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
+        if ctx.needs_input_grad[0]:
+            wd, pad = _phase_dgrad_pack(w.detach(), ph)
+            _, dxcol, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=pad)
+            dx = ops.wcol2im_h16(dxcol.view(2 * rows_out, kw * cin), NS, W_in, W_out, P_in, cin, kw, pw, sw)
+        return (dx, dw, db) + (None,) * 8
+
+
+class _RPostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, NS: int, W: int, H: int, P: int):
+        w2 = w.reshape(64, 9).contiguous()
+        score = ops.mrd_post_fwd(x, w2, bias, NS, W, H, P)
+        ctx.save_for_backward(x, w2)
+        ctx.geo, ctx.w_shape = (NS, W, H, P), w.shape
+        return score
+
+    @staticmethod
+    def backward(ctx, dscore):
+        x, w2 = ctx.saved_tensors
+        NS, W, H, P = ctx.geo
+        want_dw = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx, dw, db = ops.mrd_post_bwd(dscore, x, w2, NS, W, H, P, GRAD_SCALE, ctx.needs_input_grad[0], want_dw)
+        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None
+
+
+def resolution_forward(disc, wav: torch.Tensor, weights=None):
+    """Native forward of one DiscriminatorR on (NS, T) signals: (score (NS, H5*W5) fp32, [FlatMap x 5, score map])."""
+    if not wav.is_cuda:
+        raise RuntimeError("the resolution discriminators run on the CUDA kernels only (no CPU path)")
+    spec = disc.spectrogram(wav.float()).contiguous()          # rectangular-window |STFT| (torch.stft / cuFFT), (NS, F, W)
+    NS, F_bins, frames = spec.shape
+    geom = GeometryR.make(F_bins, frames)
+    if weights is None:
+        weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
+    slope = float(disc.lrelu_slope)
+    x = _RFirstFn.apply(spec, weights[0][0], weights[0][1], geom, slope)
+    fmap: List[object] = [FlatMap(x, geom.W[1], geom.H[1], geom.P[1])]
+    for i in range(2, 6):
+        w, b = weights[i - 1]
+        x = _RConvFn.apply(x, w, b, NS, geom.W[i - 1], geom.W[i], geom.P[i - 1], geom.P[i], geom.H[i], MRD_LAYERS[i - 1], slope)
+        fmap.append(FlatMap(x, geom.W[i], geom.H[i], geom.P[i]))
+    wpost, bpost = weights[5]
+    score = _RPostFn.apply(x, wpost, bpost, NS, geom.W[5], geom.H[5], geom.P[5])
+    fmap.append(score.view(NS, 1, geom.H[5], geom.W[5]))
+    return score, fmap
+
+
+def resolution_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
+    """As period_forward_pair, for one resolution discriminator."""
+    weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
+    if torch.is_grad_enabled() and y_hat.requires_grad:
+        with torch.no_grad():
+            sr, fr = resolution_forward(disc, y, [(w.detach(), b.detach()) for w, b in weights])
+        sg, fg = resolution_forward(disc, y_hat, weights)
+        return sr, sg, fr, fg
+    B = y.shape[0]
+    s, f = resolution_forward(disc, torch.cat((y.float(), y_hat.float()), dim=0), weights)
     fr = [m.half(0) if isinstance(m, FlatMap) else m[:B] for m in f]
     fg = [m.half(1) if isinstance(m, FlatMap) else m[B:] for m in f]
     return s[:B], s[B:], fr, fg

@@ -853,3 +853,66 @@ def l1_pair_bwd(a, b, coef, scale: float):
     db = torch.empty_like(b)
     _lib.check(_lib.load().osb_l1_pair_bwd(_ptr(a), _ptr(b), _ptr(_f32(coef)), scale, _ptr(db), a.numel(), _stream()), "osb_l1_pair_bwd")
     return db
+
+
+# ------------------------------------------------------------------------------------------------
+# resolution discriminators (osb_disc.cu)
+# ------------------------------------------------------------------------------------------------
+def mrd_first_fwd(spec, w, bias, H1: int, W1: int, P1: int, slope: float):
+    NS, Fq, W = spec.shape
+    out = torch.empty((NS * W1 * P1, 64), device=spec.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_mrd_first_fwd(_ptr(_f32(spec)), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(out), NS, Fq, W, H1, W1, P1, slope, _stream()),
+               "osb_mrd_first_fwd")
+    return out
+
+
+def mrd_first_bwd(g, spec, w, H1: int, W1: int, P1: int, inv_scale: float, want_dspec: bool, want_dw: bool):
+    NS, Fq, W = spec.shape
+    dspec = torch.empty_like(spec) if want_dspec else None
+    dwb = torch.zeros((64 * 35 + 64,), device=spec.device, dtype=torch.float32) if want_dw else None
+    _lib.check(_lib.load().osb_mrd_first_bwd(_ptr(g), _ptr(_f32(spec)), _ptr(_f32(w)), _ptr(dspec), _ptr(dwb),
+                                             (dwb.data_ptr() + 4 * 64 * 35) if want_dw else None, NS, Fq, W, H1, W1, P1, inv_scale, _stream()),
+               "osb_mrd_first_bwd")
+    return dspec, (dwb[:64 * 35].view(64, 35) if want_dw else None), (dwb[64 * 35:] if want_dw else None)
+
+
+def wim2col_h16(x, NS: int, W_in: int, W_out: int, P: int, KW: int, pw: int, sw: int):
+    Cc = x.shape[1]
+    xcol = torch.empty((NS * W_out * P, KW * Cc), device=x.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_wim2col_h16(_ptr(x), _ptr(xcol), NS, W_in, W_out, P, Cc, KW, pw, sw, _stream()), "osb_wim2col_h16")
+    return xcol
+
+
+def wcol2im_h16(dxcol, NS: int, W_in: int, W_out: int, P: int, Cc: int, KW: int, pw: int, sw: int):
+    dx = torch.empty((NS * W_in * P, Cc), device=dxcol.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_wcol2im_h16(_ptr(dxcol), _ptr(dx), NS, W_in, W_out, P, Cc, KW, pw, sw, _stream()), "osb_wcol2im_h16")
+    return dx
+
+
+def mrd_post_fwd(x, w, bias, NS: int, W: int, H: int, P: int):
+    out = torch.empty((NS, H * W), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_mrd_post_fwd(_ptr(x), _ptr(_f32(w)), _ptr(_f32(bias)), _ptr(out), NS, W, H, P, _stream()), "osb_mrd_post_fwd")
+    return out
+
+
+def mrd_post_bwd(dscore, x, w, NS: int, W: int, H: int, P: int, scale: float, want_dx: bool, want_dw: bool):
+    dx = torch.empty_like(x) if want_dx else None
+    dwb = torch.zeros((64 * 9 + 4,), device=x.device, dtype=torch.float32) if want_dw else None
+    _lib.check(_lib.load().osb_mrd_post_bwd(_ptr(_f32(dscore.contiguous())), _ptr(x), _ptr(_f32(w)), _ptr(dx), _ptr(dwb),
+                                            (dwb.data_ptr() + 4 * 64 * 9) if want_dw else None, NS, W, H, P, scale, _stream()),
+               "osb_mrd_post_bwd")
+    return dx, (dwb[:64 * 9].view(64, 9) if want_dw else None), (dwb[64 * 9:64 * 9 + 1] if want_dw else None)
+
+
+def spec_im2col_h16(spec, H1: int, W1: int, P1: int):
+    NS, Fq, W = spec.shape
+    xcol = torch.empty((NS * W1 * P1, 64), device=spec.device, dtype=torch.float16)
+    _lib.check(_lib.load().osb_spec_im2col_h16(_ptr(_f32(spec)), _ptr(xcol), NS, Fq, W, H1, W1, P1, _stream()), "osb_spec_im2col_h16")
+    return xcol
+
+
+def spec_col2im(col, shape, H1: int, W1: int, P1: int, inv_scale: float):
+    NS, Fq, W = shape
+    dspec = torch.empty((NS, Fq, W), device=col.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_spec_col2im(_ptr(col), _ptr(dspec), NS, Fq, W, H1, W1, P1, inv_scale, _stream()), "osb_spec_col2im")
+    return dspec

@@ -1,0 +1,86 @@
+"""Data parallelism on two GPUs over NCCL (needs >= 2 devices; skipped otherwise): the flat gradient bucket of the training
+step is all-reduced, eagerly and inside the captured CUDA graph, every rank ends with bit-identical parameters, and the
+reduced bucket is the mean of the ranks' local gradients (reference: Lightning DDP around base_lightning_module.py:86-130)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir, graph):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from functools import partial
+
+    from test_public_surface_gpu import ModelSpec, _fresh_model, _small_batch
+
+    spec = ModelSpec()
+    batch = _small_batch(spec, 3, 48, 200, seed=7, dev=dev)
+    if rank == 1:   # same shapes and lengths, different content
+        batch = dict(batch)
+        batch["mel"], batch["pitches"], batch["energies"] = batch["mel"] * 0.7, -batch["pitches"], batch["energies"] * 0.5
+    out = {}
+    # (a) lr = 0: the bucket after the step is the all-reduced mean gradient (times the loss scale)
+    model = _fresh_model(spec, dev)
+    model.hparams.optimizer = partial(torch.optim.AdamW, lr=0.0, betas=[0.8, 0.99], weight_decay=0.0)
+    model.cuda_graph = graph
+    for i in range(6):
+        model.training_step(batch, i)
+    torch.cuda.synchronize()
+    bucket = model.optimizers()[0].buckets()[0]
+    reduced = bucket.flat_g.clone()
+    if model._graphed is not None:
+        model._graphed.release()
+    # local gradient of this rank through plain autograd, in bucket order
+    for p in model.generator.parameters():
+        p.grad = None
+    o = model._process_batch(batch)
+    (o["loss"] * model.loss_scale).backward()
+    from optispeech_b200 import ops
+    ops.join_grad_streams()
+    local = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket.params])
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean_local = sum(gathered) / world
+    n = min(mean_local.numel(), reduced.numel())
+    out["mean_rel"] = float((reduced[:n] - mean_local[:n]).norm() / mean_local[:n].norm())
+    out["own_rel"] = float((reduced[:n] - local[:n]).norm() / local[:n].norm())
+    # (b) real steps: ranks stay bit-identical
+    model2 = _fresh_model(spec, dev)
+    model2.cuda_graph = graph
+    for i in range(6):
+        model2.training_step(batch, i)
+    torch.cuda.synchronize()
+    out["params"] = [p.detach().cpu().clone() for p in model2.generator.parameters()]
+    if model2._graphed is not None:
+        model2._graphed.release()
+    torch.save(out, os.path.join(out_dir, f"rank{rank}_{int(graph)}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_rank_training_step_over_nccl(tmp_path, graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = 29700 + (os.getpid() % 200) + int(graph)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), graph), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / f"rank0_{int(graph)}.pt")
+    r1 = torch.load(tmp_path / f"rank1_{int(graph)}.pt")
+    print(f"graph={graph}: |reduced - mean(local)| / |mean(local)| = {r0['mean_rel']:.3e}; "
+          f"|reduced - own local| / |own local| = {r0['own_rel']:.3e} (rank 0), {r1['own_rel']:.3e} (rank 1)")
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b), "ranks diverged"
+    # run-to-run floor of one gradient evaluation is a few percent on the predictors (fp32 atomics + fp16 roundings); the
+    # ranks' own gradients differ from the mean by O(1)
+    assert r0["mean_rel"] <= 5e-2 and r1["mean_rel"] <= 5e-2
+    assert r0["own_rel"] >= 4 * r0["mean_rel"] and r1["own_rel"] >= 4 * r1["mean_rel"]

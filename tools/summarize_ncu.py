@@ -48,7 +48,10 @@ def launches(path: str, last: int | None):
 
 
 def full(path: str):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):   # already exported on the GPU box (`ncu -i rep --page raw --csv`): the report itself was too big to travel
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(out.splitlines()))
     h = r[0]
     idx = {n: i for i, n in enumerate(h)}
@@ -72,7 +75,7 @@ def full(path: str):
         import json
 
         abi = {"gemm_nt_kernel": "osb_gemm", "convnext_fused_kernel": "osb_convnext_block_fwd", "gemm_wgrad_kernel": "osb_gemm_wgrad",
-               "mha_fwd_kernel": "osb_mha_fwd", "mha_bwd_kernel": "osb_mha_bwd"}
+               "convnext_bwd_fused_kernel": "osb_convnext_block_bwd", "mha_fwd_kernel": "osb_mha_fwd", "mha_bwd_kernel": "osb_mha_bwd"}
         acc = {}
         for row in r[2:]:
             name = row[idx["Kernel Name"]]
