@@ -679,8 +679,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 "algorithmic_tflop": (78.8e9 + 124.4e9) * B_PER_GPU / 1e12,
                 "achieved_tflops": (78.8e9 + 124.4e9) * B_PER_GPU / (t3 * 1e-3) / 1e12,
                 "frac_of_sustained_peak": (78.8e9 + 124.4e9) * B_PER_GPU / (t3 * 1e-3) / 1e12 / float(peaks.get("bf16_tflops_sustained", 1400.0)),
-                "discriminators": "period (MPD): this package's kernels (disc/native.py: tcgen05 implicit GEMMs over the flat sequence "
-                                  "layout); resolution (MRD): stock PyTorch / cuDNN fp32"}
+                "discriminators": "period (MPD) and resolution (MRD) stacks on this package's kernels (disc/native.py: tcgen05 implicit "
+                                  "GEMMs over the flat sequence layout); the MRD's rectangular-window |STFT| is torch.stft (cuFFT)"}
             if gmodel._graphed is not None:
                 gmodel._graphed.release()
             variants["spectral_loss_kernels"] = spectral_kernel_bench(gmodel, dev, peaks)
@@ -752,7 +752,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "synthesis": synth,
             "variants": variants,
         }
+        if _STDOUT_FD is not None:
+            sys.stdout.flush()
+            os.dup2(_STDOUT_FD, 1)
         print(json.dumps(line), flush=True)
+
+
+_STDOUT_FD = None
 
 
 def main():
@@ -778,9 +784,23 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner to file descriptor 1 at communicator creation; stdout carries ONE JSON line, so fd 1
+        # points at stderr until the line is printed (run_ours restores it)
+        global _STDOUT_FD
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, local_rank, world)
+    except BaseException:
+        import traceback
+
+        traceback.print_exc()      # the multi-rank teardown below leaves through os._exit: the traceback has to be out first
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(1)
+        raise
     finally:
         if world > 1:
             # The captured step holds NCCL kernels: its graphs must be gone before the communicator is torn down, and a

@@ -8,6 +8,14 @@ namespace osb {
 namespace {
 
 // stats[0] += sum g^2 ; stats[1] = 1 if any element is non-finite
+// Sum of squares of the (all-reduced) flat gradient, DETERMINISTIC: block partials are combined by the last block in index
+// order, so every rank of a data-parallel job derives bit-identical clip coefficients from its bit-identical copy of the
+// reduced bucket (an atomic accumulation order would let the ranks' parameters drift apart by an ulp per step).
+constexpr int SUMSQ_MAX_BLOCKS = 148 * 4;
+__device__ float g_sumsq_partial[SUMSQ_MAX_BLOCKS];
+__device__ int g_sumsq_bad[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ stats) {
   float acc = 0.f;
   bool bad = false;
@@ -23,6 +31,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   acc = warp_sum(acc);
   __shared__ float red[8];
   __shared__ int sbad;
+  __shared__ bool last;
   if (threadIdx.x == 0) sbad = 0;
   __syncthreads();
   if (bad) sbad = 1;
@@ -31,8 +40,28 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < 8; ++i) s += red[i];
-    atomicAdd(stats, s);
-    if (sbad || !isfinite(s)) stats[1] = 1.f;
+    g_sumsq_partial[blockIdx.x] = s;
+    g_sumsq_bad[blockIdx.x] = (sbad || !isfinite(s)) ? 1 : 0;
+    __threadfence();
+    last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {   // one warp, fixed order: lane l takes partials l, l+32, ...; then a fixed shuffle tree
+    float s = 0.f;
+    int b = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) {
+      s += *(volatile float*)&g_sumsq_partial[i];
+      b |= *(volatile int*)&g_sumsq_bad[i];
+    }
+    s = warp_sum(s);
+    b = __any_sync(0xffffffffu, b != 0);
+    if (threadIdx.x == 0) {
+      stats[0] += s;
+      if (b) stats[1] = 1.f;
+      g_sumsq_ticket = 0;
+    }
   }
 }
 

@@ -47,20 +47,22 @@ def _worker(rank, world, port, out_dir, graph):
     (o["loss"] * model.loss_scale).backward()
     from optispeech_b200 import ops
     ops.join_grad_streams()
-    local = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket.params])
+    local = torch.zeros_like(reduced)          # members sit at 16-byte aligned offsets of the bucket
+    for p, o in zip(bucket.params, bucket.offsets):
+        if p.grad is not None:
+            local[o:o + p.numel()] = p.grad.reshape(-1).float()
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
-    mean_local = sum(gathered) / world
-    n = min(mean_local.numel(), reduced.numel())
-    out["mean_rel"] = float((reduced[:n] - mean_local[:n]).norm() / mean_local[:n].norm())
-    out["own_rel"] = float((reduced[:n] - local[:n]).norm() / local[:n].norm())
+    sum_local = sum(gathered)                  # the all-reduce SUMS; 1/world is folded into the optimizer's unscale factor
+    out["mean_rel"] = float((reduced - sum_local).norm() / sum_local.norm())
+    out["own_rel"] = float((reduced - local).norm() / local.norm())
     # (b) real steps: ranks stay bit-identical
     model2 = _fresh_model(spec, dev)
     model2.cuda_graph = graph
     for i in range(6):
         model2.training_step(batch, i)
     torch.cuda.synchronize()
-    out["params"] = [p.detach().cpu().clone() for p in model2.generator.parameters()]
+    out["params"] = {n: p.detach().cpu().clone() for n, p in model2.generator.named_parameters()}
     if model2._graphed is not None:
         model2._graphed.release()
     torch.save(out, os.path.join(out_dir, f"rank{rank}_{int(graph)}.pt"))
@@ -76,11 +78,11 @@ def test_two_rank_training_step_over_nccl(tmp_path, graph):
     mp.spawn(_worker, args=(2, port, str(tmp_path), graph), nprocs=2, join=True)
     r0 = torch.load(tmp_path / f"rank0_{int(graph)}.pt")
     r1 = torch.load(tmp_path / f"rank1_{int(graph)}.pt")
-    print(f"graph={graph}: |reduced - mean(local)| / |mean(local)| = {r0['mean_rel']:.3e}; "
+    print(f"graph={graph}: |reduced - sum(local)| / |sum(local)| = {r0['mean_rel']:.3e}; "
           f"|reduced - own local| / |own local| = {r0['own_rel']:.3e} (rank 0), {r1['own_rel']:.3e} (rank 1)")
-    for a, b in zip(r0["params"], r1["params"]):
-        assert torch.equal(a, b), "ranks diverged"
-    # run-to-run floor of one gradient evaluation is a few percent on the predictors (fp32 atomics + fp16 roundings); the
-    # ranks' own gradients differ from the mean by O(1)
+    diverged = [(n, float((a - r1["params"][n]).abs().max())) for n, a in r0["params"].items() if not torch.equal(a, r1["params"][n])]
+    assert not diverged, f"ranks diverged on {len(diverged)} of {len(r0['params'])} tensors, e.g. {diverged[:6]}"
+    # run-to-run floor of one gradient evaluation is a few percent on the predictors (fp32 atomics + fp16 roundings); a
+    # rank's own gradient differs from the sum by O(1)
     assert r0["mean_rel"] <= 5e-2 and r1["mean_rel"] <= 5e-2
     assert r0["own_rel"] >= 4 * r0["mean_rel"] and r1["own_rel"] >= 4 * r1["mean_rel"]
