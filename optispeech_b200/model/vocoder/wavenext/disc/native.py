@@ -88,9 +88,9 @@ class _DenseFn(torch.autograd.Function):
 
 class _FirstFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, wav, w, bias, geom: Geometry, stride: int, slope: float):
+    def forward(ctx, wav, w, bias, geom: Geometry, stride: int, slope: float, y_pre=None):
         w2 = w.reshape(32, KSIZE).contiguous()
-        y = ops.mpd_first_fwd(wav, w2, bias, geom.period, geom.L[1], geom.P[1], C1_PAD, stride, slope)
+        y = y_pre if y_pre is not None else ops.mpd_first_fwd(wav, w2, bias, geom.period, geom.L[1], geom.P[1], C1_PAD, stride, slope)
         ctx.save_for_backward(wav, w2, y)
         ctx.geom, ctx.stride, ctx.slope, ctx.w_shape = geom, stride, slope, w.shape
         return y
@@ -102,19 +102,22 @@ class _FirstFn(torch.autograd.Function):
         g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.L[1], ctx.slope)
         want_dwav, want_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dwav, dw, db = ops.mpd_first_bwd(g, wav, w2, geom.period, geom.L[1], geom.P[1], ctx.stride, 1.0 / GRAD_SCALE, want_dwav, want_dw)
-        return dwav, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None
+        return dwav, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None
 
 
 class _ConvFn(torch.autograd.Function):
     """One (5,1) convolution + LeakyReLU on the flat layout: x (rows_in, Cin_p) fp16 -> y (rows_out, Cout) fp16."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, wp, stride: int, P_out: int, L_out: int, slope: float):
+    def forward(ctx, x, w, bias, wp, stride: int, P_out: int, L_out: int, slope: float, y_pre=None):
         rows_in, cin_p = x.shape
         rows_out = rows_in // stride
-        _, y, _ = ops.gemm(x.view(1, rows_in, cin_p), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
-                           pad=PAD, bias=bias, seq_rows=(P_out, L_out), row_stride=stride, lrelu=slope)
-        y = y.view(rows_out, -1)
+        if y_pre is not None:
+            y = y_pre
+        else:
+            _, y, _ = ops.gemm(x.view(1, rows_in, cin_p), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
+                               pad=PAD, bias=bias, seq_rows=(P_out, L_out), row_stride=stride, lrelu=slope)
+            y = y.view(rows_out, -1)
         ctx.save_for_backward(x, w, wp, y)
         ctx.stride, ctx.P_out, ctx.L_out, ctx.slope = stride, P_out, L_out, slope
         return y
@@ -146,14 +149,14 @@ class _ConvFn(torch.autograd.Function):
                 wd, dpad = _phase_dgrad_pack(w4, PAD, stride)
                 _, dxp, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=dpad)
                 dx = dxp.view(rows_in, cin_p)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class _PostFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, period: int, L: int, P: int):
+    def forward(ctx, x, w, bias, period: int, L: int, P: int, s_pre=None):
         w2 = w.reshape(-1, 3).contiguous()
-        score = ops.mpd_post_fwd(x, w2, bias, period, L, P)
+        score = s_pre if s_pre is not None else ops.mpd_post_fwd(x, w2, bias, period, L, P)
         ctx.save_for_backward(x, w2)
         ctx.geo, ctx.w_shape = (period, L, P), w.shape
         return score
@@ -164,7 +167,7 @@ class _PostFn(torch.autograd.Function):
         period, L, P = ctx.geo
         want_dw = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx, dw, db = ops.mpd_post_bwd(dscore, x, w2, period, L, P, GRAD_SCALE, ctx.needs_input_grad[0], want_dw)
-        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None
+        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None
 
 
 class L1PairFn(torch.autograd.Function):
@@ -204,8 +207,10 @@ def effective_weights(disc):
     return layers
 
 
-def period_forward(disc, wav: torch.Tensor, layers=None):
-    """Native forward of one DiscriminatorP on (NS, T) fp32 signals: (score (NS, L5*period) fp32, [FlatMap x 4, score map])."""
+def period_forward(disc, wav: torch.Tensor, layers=None, pre=None, record=None):
+    """Native forward of one DiscriminatorP on (NS, T) fp32 signals: (score (NS, L5*period) fp32, [FlatMap x 4, score map]).
+    `pre` = the six layer outputs computed earlier for the same signals and weights (the kernels are skipped, the autograd
+    graph is built around them); `record` = a list that receives the six layer outputs."""
     if not wav.is_cuda:
         raise RuntimeError("the period discriminators run on the CUDA kernels only (no CPU path)")
     wav = wav.float().contiguous()
@@ -214,33 +219,66 @@ def period_forward(disc, wav: torch.Tensor, layers=None):
     layers = layers if layers is not None else effective_weights(disc)
     slope = float(disc.lrelu_slope)
     (w1, b1, _), rest = layers[0], layers[1:5]
-    x = _FirstFn.apply(wav, w1, b1, geom, 3, slope)
+    x = _FirstFn.apply(wav, w1, b1, geom, 3, slope, pre[0] if pre else None)
+    outs = [x]
     fmap: List[object] = []
     for i, (w, b, wp) in enumerate(rest, start=2):
         stride = 3 if i <= 4 else 1
-        x = _ConvFn.apply(x, w, b, wp, stride, geom.P[i], geom.L[i], slope)
+        x = _ConvFn.apply(x, w, b, wp, stride, geom.P[i], geom.L[i], slope, pre[i - 1] if pre else None)
+        outs.append(x)
         fmap.append(FlatMap(x, disc.period, geom.L[i], geom.P[i]))
     wpost, bpost, _ = layers[5]
-    score = _PostFn.apply(x, wpost, bpost, disc.period, geom.L[5], geom.P[5])
+    score = _PostFn.apply(x, wpost, bpost, disc.period, geom.L[5], geom.P[5], pre[5] if pre else None)
+    outs.append(score)
+    if record is not None:
+        record.extend(t.detach() for t in outs)
     fmap.append(score.view(NS, 1, geom.L[5], disc.period))
     return score, fmap
 
 
-def period_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
-    """(score_real, score_fake, fmap_real, fmap_fake) of one period discriminator.  Generator turn (y_hat carries a graph):
-    the real signals run without a graph and the generated ones alone are differentiated; otherwise both halves share one
-    pass (one GEMM per layer over 2B signals)."""
-    layers = effective_weights(disc)
-    if torch.is_grad_enabled() and y_hat.requires_grad:
+REUSE_GENERATOR_TURN = True   # the discriminator turn reuses the layer outputs of the generator turn (see _pair below)
+LAST_PAIR_REUSED = False      # whether the latest discriminator-turn call hit that cache (tests)
+
+
+def _reuse_key(disc, y, y_hat):
+    return (y.data_ptr(), y._version, tuple(y.shape), y_hat.data_ptr(), y_hat._version,
+            tuple((p._version, getattr(p, "_osb_epoch", 0)) for p in disc.parameters()))
+
+
+def _pair(disc, y, y_hat, forward, weights, detach):
+    """(score_real, score_fake, fmap_real, fmap_fake) of one discriminator.
+
+    Generator turn (y_hat carries a graph, the discriminator weights are frozen): the real signals run without a graph, the
+    generated ones alone are differentiated.  Discriminator turn: both halves share one pass over 2B signals.  With
+    `cache_generator_outputs` (the reference default) the discriminator turn sees the SAME waveforms and the SAME weights as the
+    generator turn of the step (the discriminator optimizer steps afterwards), so its forward values are the ones the
+    generator turn already produced: they are kept (keyed by the tensors' storage, versions and every parameter version) and the
+    discriminator turn only builds its autograd graph around them — one of the step's three discriminator forwards is not
+    recomputed.  The reference recomputes it; the values are identical."""
+    gen_turn = torch.is_grad_enabled() and y_hat.requires_grad
+    if gen_turn:
+        rec_r, rec_g = [], []
         with torch.no_grad():
-            sr, fr = period_forward(disc, y, [(w.detach(), b.detach(), wp) for w, b, wp in layers])
-        sg, fg = period_forward(disc, y_hat, layers)
+            sr, fr = forward(disc, y, detach(weights), record=rec_r)
+        sg, fg = forward(disc, y_hat, weights, record=rec_g)
+        if REUSE_GENERATOR_TURN:
+            disc.__dict__["_turn_cache"] = (_reuse_key(disc, y, y_hat), rec_r, rec_g)
         return sr, sg, fr, fg
+    global LAST_PAIR_REUSED
     B = y.shape[0]
-    s, f = period_forward(disc, torch.cat((y.float(), y_hat.float()), dim=0), layers)
+    pre = None
+    cached = disc.__dict__.pop("_turn_cache", None)
+    if cached is not None and REUSE_GENERATOR_TURN and cached[0] == _reuse_key(disc, y, y_hat):
+        pre = [tuple(torch.cat((a, b)) for a, b in zip(r, g)) if isinstance(r, tuple) else torch.cat((r, g)) for r, g in zip(cached[1], cached[2])]
+    LAST_PAIR_REUSED = pre is not None
+    s, f = forward(disc, torch.cat((y.float(), y_hat.float()), dim=0), weights, pre=pre)
     fr = [m.half(0) if isinstance(m, FlatMap) else m[:B] for m in f]
     fg = [m.half(1) if isinstance(m, FlatMap) else m[B:] for m in f]
     return s[:B], s[B:], fr, fg
+
+
+def period_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
+    return _pair(disc, y, y_hat, period_forward, effective_weights(disc), lambda ws: [(w.detach(), b.detach(), wp) for w, b, wp in ws])
 
 
 # --------------------------------------------------------------------------------------------------
@@ -274,15 +312,18 @@ class _RFirstFn(torch.autograd.Function):
     into a 64-wide fp16 row (osb_spec_im2col_h16), which is also the operand of the weight gradient."""
 
     @staticmethod
-    def forward(ctx, spec, w, bias, geom: GeometryR, slope: float):
-        xcol = ops.spec_im2col_h16(spec, geom.H[1], geom.W[1], geom.P[1])
+    def forward(ctx, spec, xcol, w, bias, geom: GeometryR, slope: float, y_pre=None):
+        """`spec` only routes the gradient (it may be None when nothing upstream needs one); `xcol` is its tap gather."""
         rows = xcol.shape[0]
-        wp = F.pad(w.detach().reshape(64, 35), (0, 29)).to(torch.float16).view(1, 64, 64)
-        _, y, _ = ops.gemm(xcol.view(1, rows, 64), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
-                           bias=bias, seq_rows=(geom.P[1], geom.H[1]), lrelu=slope)
-        y = y.view(rows, 64)
+        if y_pre is not None:
+            y = y_pre
+        else:
+            wp = F.pad(w.detach().reshape(64, 35), (0, 29)).to(torch.float16).view(1, 64, 64)
+            _, y, _ = ops.gemm(xcol.view(1, rows, 64), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
+                               bias=bias, seq_rows=(geom.P[1], geom.H[1]), lrelu=slope)
+            y = y.view(rows, 64)
         ctx.save_for_backward(xcol, w, y)
-        ctx.geom, ctx.slope, ctx.spec_shape = geom, slope, tuple(spec.shape)
+        ctx.geom, ctx.slope, ctx.spec_shape = geom, slope, (tuple(spec.shape) if spec is not None else None)
         return y
 
     @staticmethod
@@ -292,16 +333,16 @@ class _RFirstFn(torch.autograd.Function):
         rows = y.shape[0]
         g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
         dspec = dw = db = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dwp = torch.zeros((1, 64, 64), device=g.device, dtype=torch.float32)
             ops.gemm_wgrad(g.view(1, rows, 64), xcol.view(1, rows, 64), dwp)
             dw = (dwp[0, :, :35] * (1.0 / GRAD_SCALE)).reshape(w.shape)
             db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.spec_shape is not None:
             wd = F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64)   # [tap][cout]
             _, col, _ = ops.gemm(g.view(1, rows, 64), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
             dspec = ops.spec_col2im(col.view(rows, 64), ctx.spec_shape, geom.H[1], geom.W[1], geom.P[1], 1.0 / GRAD_SCALE)
-        return dspec, dw, db, None, None
+        return dspec, None, dw, db, None, None, None
 
 
 def _phase_dgrad_pack(w: torch.Tensor, ph: int, stride: int = 2):
@@ -322,15 +363,18 @@ class _RConvFn(torch.autograd.Function):
     """One Conv2d(64, 64, (kh, kw), (2, sw)) + LeakyReLU: x (NS*W_in*P_in, 64) -> y (NS*W_out*P_out, 64)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, NS: int, W_in: int, W_out: int, P_in: int, P_out: int, H_out: int, layer, slope: float):
+    def forward(ctx, x, w, bias, NS: int, W_in: int, W_out: int, P_in: int, P_out: int, H_out: int, layer, slope: float, y_pre=None):
         kh, kw, _sh, sw, ph, pw = layer
-        xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)
-        cout, cin = w.shape[0], w.shape[1]
-        wp = w.detach().permute(2, 0, 3, 1).reshape(kh, cout, kw * cin).to(torch.float16).contiguous()     # [kh][cout][(kw, cin)]
-        rows_in = xcol.shape[0]
-        _, y, _ = ops.gemm(xcol.view(1, rows_in, kw * cin), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
-                           pad=ph, bias=bias, seq_rows=(P_out, H_out), row_stride=2, lrelu=slope)
-        y = y.view(rows_in // 2, cout)
+        if y_pre is not None:
+            y = y_pre
+        else:
+            xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)
+            cout, cin = w.shape[0], w.shape[1]
+            wp = w.detach().permute(2, 0, 3, 1).reshape(kh, cout, kw * cin).to(torch.float16).contiguous()     # [kh][cout][(kw, cin)]
+            rows_in = xcol.shape[0]
+            _, y, _ = ops.gemm(xcol.view(1, rows_in, kw * cin), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
+                               pad=ph, bias=bias, seq_rows=(P_out, H_out), row_stride=2, lrelu=slope)
+            y = y.view(rows_in // 2, cout)
         ctx.save_for_backward(x, w, y)
         ctx.geo = (NS, W_in, W_out, P_in, P_out, H_out, layer, slope)
         return y
@@ -354,14 +398,14 @@ class _RConvFn(torch.autograd.Function):
             wd, pad = _phase_dgrad_pack(w.detach(), ph)
             _, dxcol, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=pad)
             dx = ops.wcol2im_h16(dxcol.view(2 * rows_out, kw * cin), NS, W_in, W_out, P_in, cin, kw, pw, sw)
-        return (dx, dw, db) + (None,) * 8
+        return (dx, dw, db) + (None,) * 9
 
 
 class _RPostFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, bias, NS: int, W: int, H: int, P: int):
+    def forward(ctx, x, w, bias, NS: int, W: int, H: int, P: int, s_pre=None):
         w2 = w.reshape(64, 9).contiguous()
-        score = ops.mrd_post_fwd(x, w2, bias, NS, W, H, P)
+        score = s_pre if s_pre is not None else ops.mrd_post_fwd(x, w2, bias, NS, W, H, P)
         ctx.save_for_backward(x, w2)
         ctx.geo, ctx.w_shape = (NS, W, H, P), w.shape
         return score
@@ -372,27 +416,46 @@ class _RPostFn(torch.autograd.Function):
         NS, W, H, P = ctx.geo
         want_dw = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx, dw, db = ops.mrd_post_bwd(dscore, x, w2, NS, W, H, P, GRAD_SCALE, ctx.needs_input_grad[0], want_dw)
-        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None
+        return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None, None
 
 
-def resolution_forward(disc, wav: torch.Tensor, weights=None):
-    """Native forward of one DiscriminatorR on (NS, T) signals: (score (NS, H5*W5) fp32, [FlatMap x 5, score map])."""
+def _stft_frames(T: int, hop: int) -> int:
+    return T // hop + 1      # torch.stft(center=True)
+
+
+def resolution_forward(disc, wav: torch.Tensor, weights=None, pre=None, record=None):
+    """Native forward of one DiscriminatorR on (NS, T) signals: (score (NS, H5*W5) fp32, [FlatMap x 5, score map]).
+    `pre` / `record` as in period_forward (the first entry is the pair (tap gather, layer-1 output))."""
     if not wav.is_cuda:
         raise RuntimeError("the resolution discriminators run on the CUDA kernels only (no CPU path)")
-    spec = disc.spectrogram(wav.float()).contiguous()          # rectangular-window |STFT| (torch.stft / cuFFT), (NS, F, W)
-    NS, F_bins, frames = spec.shape
+    NS = wav.shape[0]
+    if pre is None:
+        spec = disc.spectrogram(wav.float()).contiguous()          # rectangular-window |STFT| (torch.stft / cuFFT), (NS, F, W)
+        F_bins, frames = spec.shape[1], spec.shape[2]
+    else:
+        spec = None
+        n_fft, hop, _win = disc.resolution
+        F_bins, frames = n_fft // 2 + 1, _stft_frames(wav.shape[1], hop)
     geom = GeometryR.make(F_bins, frames)
     if weights is None:
         weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
     slope = float(disc.lrelu_slope)
-    x = _RFirstFn.apply(spec, weights[0][0], weights[0][1], geom, slope)
+    xcol1 = pre[0][0] if pre else ops.spec_im2col_h16(spec, geom.H[1], geom.W[1], geom.P[1])
+    x = _RFirstFn.apply(spec, xcol1, weights[0][0], weights[0][1], geom, slope, pre[0][1] if pre else None)
+    outs = [x]
     fmap: List[object] = [FlatMap(x, geom.W[1], geom.H[1], geom.P[1])]
     for i in range(2, 6):
         w, b = weights[i - 1]
-        x = _RConvFn.apply(x, w, b, NS, geom.W[i - 1], geom.W[i], geom.P[i - 1], geom.P[i], geom.H[i], MRD_LAYERS[i - 1], slope)
+        x = _RConvFn.apply(x, w, b, NS, geom.W[i - 1], geom.W[i], geom.P[i - 1], geom.P[i], geom.H[i], MRD_LAYERS[i - 1], slope,
+                           pre[i - 1] if pre else None)
+        outs.append(x)
         fmap.append(FlatMap(x, geom.W[i], geom.H[i], geom.P[i]))
     wpost, bpost = weights[5]
-    score = _RPostFn.apply(x, wpost, bpost, NS, geom.W[5], geom.H[5], geom.P[5])
+    score = _RPostFn.apply(x, wpost, bpost, NS, geom.W[5], geom.H[5], geom.P[5], pre[5] if pre else None)
+    outs.append(score)
+    if record is not None:
+        record.append((xcol1.detach(), outs[0].detach()))
+        record.extend(t.detach() for t in outs[1:])
     fmap.append(score.view(NS, 1, geom.H[5], geom.W[5]))
     return score, fmap
 
@@ -400,13 +463,4 @@ def resolution_forward(disc, wav: torch.Tensor, weights=None):
 def resolution_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
     """As period_forward_pair, for one resolution discriminator."""
     weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
-    if torch.is_grad_enabled() and y_hat.requires_grad:
-        with torch.no_grad():
-            sr, fr = resolution_forward(disc, y, [(w.detach(), b.detach()) for w, b in weights])
-        sg, fg = resolution_forward(disc, y_hat, weights)
-        return sr, sg, fr, fg
-    B = y.shape[0]
-    s, f = resolution_forward(disc, torch.cat((y.float(), y_hat.float()), dim=0), weights)
-    fr = [m.half(0) if isinstance(m, FlatMap) else m[:B] for m in f]
-    fg = [m.half(1) if isinstance(m, FlatMap) else m[B:] for m in f]
-    return s[:B], s[B:], fr, fg
+    return _pair(disc, y, y_hat, resolution_forward, weights, lambda ws: [(w.detach(), b.detach()) for w, b in ws])

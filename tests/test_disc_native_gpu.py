@@ -256,3 +256,55 @@ def test_resolution_gradients(cuda_device, resolution):
         report.append(f"{n} {r:.2e}")
         assert r <= 3e-2, (n, r, report)
     print(f"  resolution {resolution}: discriminator turn loss {ln:.6f} vs {lr:.6f}; parameter-gradient relative L2 differences: " + ", ".join(report))
+
+
+@pytest.mark.parametrize("kind", ["period", "resolution"])
+def test_discriminator_turn_reuses_generator_turn_activations(cuda_device, kind):
+    """With `cache_generator_outputs` the discriminator turn sees the waveforms and weights of the generator turn; the layer
+    outputs computed there are reused (native._pair).  Same loss and same weight gradients as a recomputed forward; a changed
+    input or weight must NOT hit the cache."""
+    from optispeech_b200.model.vocoder.wavenext.disc import native
+    from optispeech_b200.model.vocoder.wavenext.disc.loss import DiscriminatorLoss, FeatureMatchingLoss, GeneratorLoss
+
+    d = _disc(5, cuda_device) if kind == "period" else _disc_r((1024, 256, 1024), cuda_device)
+    pair = native.period_forward_pair if kind == "period" else native.resolution_forward_pair
+    g = torch.Generator().manual_seed(11)
+    wav = (torch.rand(2, 16384, generator=g) * 2 - 1).to(cuda_device)
+    wav_hat = (0.6 * wav.cpu() + 0.4 * (torch.rand(2, 16384, generator=g) * 2 - 1)).to(cuda_device).requires_grad_(True)
+
+    def step(reuse):
+        native.REUSE_GENERATOR_TURN = reuse
+        try:
+            d.requires_grad_(False)                          # generator turn: weights frozen (toggle_optimizer)
+            _, sg, fr, fg = pair(d, wav, wav_hat)
+            (GeneratorLoss()([sg])[0] + FeatureMatchingLoss()([fr], [fg])).backward()
+            d.requires_grad_(True)
+            d.zero_grad(set_to_none=True)
+            sr, sg2, _, _ = pair(d, wav, wav_hat.detach())   # discriminator turn on the cached waveforms
+            hit = native.LAST_PAIR_REUSED
+            loss = DiscriminatorLoss()([sr], [sg2])[0] + 0.75 * torch.clamp(1 - sr, min=0).mean()
+            (loss * 1024.0).backward()
+            return float(loss), {n: p.grad.detach().clone() for n, p in d.named_parameters()}, hit
+        finally:
+            native.REUSE_GENERATOR_TURN = True
+
+    l0, g0, hit0 = step(False)
+    l1, g1, hit1 = step(True)
+    assert not hit0 and hit1
+    assert l0 == l1                                           # the very same forward values
+    worst = max(_param_rel(g1[n], g0[n]) for n in g0)
+    print(f"  {kind}: discriminator-turn loss {l1:.6f}; worst weight-gradient difference reuse vs recompute {worst:.3e}")
+    assert worst <= 1e-3                                      # atomics in the weight-gradient kernels reorder sums
+    # a different generated waveform (new storage) or a changed weight: no reuse
+    d.requires_grad_(False)
+    pair(d, wav, wav_hat)
+    d.requires_grad_(True)
+    pair(d, wav, wav_hat.detach().clone())
+    assert not native.LAST_PAIR_REUSED
+    d.requires_grad_(False)
+    pair(d, wav, wav_hat)
+    d.requires_grad_(True)
+    with torch.no_grad():
+        next(d.parameters()).mul_(1.0)                        # in-place write bumps the version counter
+    pair(d, wav, wav_hat.detach())
+    assert not native.LAST_PAIR_REUSED
