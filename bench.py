@@ -83,7 +83,7 @@ def synth_inputs(name: str):
 class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.01):
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
         self.gpu, self.period = gpu_index, period_s
         self.samples = []          # (t, sm_mhz, reasons bitmask, power_w)
         self.sm_max = None
@@ -132,7 +132,7 @@ class ClockSampler:
         if self._thread is not None:
             self._thread.join(timeout=2)
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "samples_in_timed_region": 0, "power_w_max": None,
-               "how": "NVML polled every 10 ms from before the warm-up to the end of the timed region; sm_mhz = median over the samples "
+               "how": "NVML polled every 4 ms from before the warm-up to the end of the timed region; sm_mhz = median over the samples "
                       "taken under load (timed region, else warm-up + timed region)"}
         if not self.samples:
             return out

@@ -547,8 +547,10 @@ int osb_mpd_post_fwd(const void* x_h16, const float* w /*(C,3)*/, const float* b
 /* dx (NSEQ*P, C) fp16 = scale * conv_post^T(dscore); dw (C,3) +=, db (1) += (unscaled; NULL to skip either part). */
 int osb_mpd_post_bwd(const float* dscore, const void* x_h16, const float* w, void* dx_h16, float* dw, float* db, int32_t NSEQ,
                      int32_t period, int32_t L, int32_t P, int32_t C, float scale, void* stream);
-/* g = dy * (y > 0 ? 1 : slope) on the valid rows (row % P < L), 0 on the gap rows — LeakyReLU backward from the saved output. */
-int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t rows, int32_t C, int32_t P, int32_t L, float slope, void* stream);
+/* g = dy * (y > 0 ? 1 : slope) on the valid rows (row % P < L), 0 on the gap rows — LeakyReLU backward from the saved output.
+ * colsum (optional, (C) fp32, accumulated): += colsum_scale * column sums of g = the layer's bias gradient. */
+int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t rows, int32_t C, int32_t P, int32_t L, float slope, float* colsum,
+                      float colsum_scale, void* stream);
 /* Data gradient of a strided convolution from the per-tap products of one GEMM: col (rows_out, taps*C) -> dx (rows_in, C),
  * dx[r] = sum_{tap: (r + pad - tap) % stride == 0} col[(r + pad - tap) / stride, j(tap)*C : +C], j(tap) = taps-1-tap if `reversed`. */
 int osb_col2im_h16(const void* col, void* dx, int64_t rows_in, int64_t rows_out, int32_t C, int32_t taps, int32_t pad, int32_t stride,

@@ -167,7 +167,7 @@ def load() -> C.CDLL:
         "osb_mpd_first_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, I32, F, P],
         "osb_mpd_post_fwd": [P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_mpd_post_bwd": [P, P, P, P, P, P, I32, I32, I32, I32, I32, F, P],
-        "osb_lrelu_bwd_h16": [P, P, P, I64, I32, I32, I32, F, P],
+        "osb_lrelu_bwd_h16": [P, P, P, I64, I32, I32, I32, F, P, F, P],
         "osb_col2im_h16": [P, P, I64, I64, I32, I32, I32, I32, I32, P],
         "osb_l1_pair_fwd": [P, P, P, I64, P],
         "osb_l1_pair_bwd": [P, P, P, F, P, I64, P],

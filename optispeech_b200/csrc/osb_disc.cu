@@ -276,23 +276,73 @@ mpd_post_dw_kernel(const float* __restrict__ dout, const __half* __restrict__ x,
 }
 
 // g = dy * (y > 0 ? 1 : slope) on the valid rows (row % P < L), 0 on the gap rows      (fp16, 8 elements per thread)
+// A thread owns 8 channels and walks LB_ROWS rows; with `colsum` it also accumulates the column sums of g (the bias gradient of
+// the layer, scaled) and leaves with 8 atomics — the separate column-sum pass re-read every gradient row from HBM.
+constexpr int LB_ROWS = 8;
 __global__ void __launch_bounds__(256)
-lrelu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, __half* __restrict__ g, long long n8, int C8, int P, int L,
-                 float slope) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  float a[8], b[8];
-  const bool valid = static_cast<int>((i / C8) % P) < L;
-  if (valid) {
-    ld_h8(dy + i * 8, a);
-    ld_h8(y + i * 8, b);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = b[q] > 0.f ? a[q] : a[q] * slope;
-  } else {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+lrelu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, __half* __restrict__ g, long long rows, int C8, int P, int L,
+                 float slope, float* __restrict__ colsum, float colsum_scale) {
+  // column sums: threads of a block that own the same channel group meet in shared memory first (256 % C8 == 0: the group of
+  // a thread is threadIdx.x % C8), so every address sees one global atomic per block instead of one per 8-row slab
+  __shared__ float sacc[256 * 8];
+  const bool block_reduce = colsum != nullptr && C8 <= 256 && 256 % C8 == 0;
+  if (block_reduce) {
+    for (int k = threadIdx.x; k < C8 * 8; k += blockDim.x) sacc[k] = 0.f;
+    __syncthreads();
   }
-  st_h8(g + i * 8, a);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long slabs = (rows + LB_ROWS - 1) / LB_ROWS;
+  const bool active = i < slabs * C8;
+  const int cg = active ? static_cast<int>(i % C8) : 0;
+  const long long r0 = active ? (i / C8) * LB_ROWS : rows;
+  uint4 a4[LB_ROWS], b4[LB_ROWS];
+  bool live[LB_ROWS];
+#pragma unroll
+  for (int j = 0; j < LB_ROWS; ++j) {     // all loads of the slab in flight before the first use
+    const long long r = r0 + j;
+    live[j] = r < rows && static_cast<int>(r % P) < L;
+    if (live[j]) {
+      const long long off = (r * C8 + cg) * 8;
+      a4[j] = *reinterpret_cast<const uint4*>(dy + off);
+      b4[j] = *reinterpret_cast<const uint4*>(y + off);
+    }
+  }
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+  for (int j = 0; j < LB_ROWS; ++j) {
+    const long long r = r0 + j;
+    if (r >= rows) break;
+    float a[8];
+    if (live[j]) {
+      const __half2* ah = reinterpret_cast<const __half2*>(&a4[j]);
+      const __half2* bh = reinterpret_cast<const __half2*>(&b4[j]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 av = __half22float2(ah[q]), bv = __half22float2(bh[q]);
+        a[2 * q] = bv.x > 0.f ? av.x : av.x * slope;
+        a[2 * q + 1] = bv.y > 0.f ? av.y : av.y * slope;
+        acc[2 * q] += a[2 * q];
+        acc[2 * q + 1] += a[2 * q + 1];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = 0.f;
+    }
+    st_h8(g + (r * C8 + cg) * 8, a);
+  }
+  if (block_reduce) {
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) atomicAdd(&sacc[cg * 8 + q], acc[q]);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < C8 * 8; k += blockDim.x) atomicAdd(colsum + k, sacc[k] * colsum_scale);
+  } else if (colsum != nullptr && active) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(colsum + cg * 8 + q, acc[q] * colsum_scale);
+  }
 }
 
 // data gradient of a strided convolution from the per-tap products of ONE GEMM: col (rows_out, taps*C) holds, at column block j,
@@ -791,12 +841,13 @@ extern "C" int osb_mpd_post_bwd(const float* dout, const void* x_h16, const floa
 }
 
 extern "C" int osb_lrelu_bwd_h16(const void* dy, const void* y, void* g, int64_t rows, int32_t C, int32_t P, int32_t L, float slope,
-                                 void* stream) {
+                                 float* colsum, float colsum_scale, void* stream) {
   OSB_REQUIRE(dy && y && g, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && P > 0 && L > 0 && L <= P, OSB_ERR_SHAPE);
-  const long long n8 = rows * (C / 8);
-  lrelu_bwd_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
-                                                                                    static_cast<__half*>(g), n8, C / 8, P, L, slope);
+  const long long n = ((rows + LB_ROWS - 1) / LB_ROWS) * (C / 8);
+  lrelu_bwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                                  static_cast<__half*>(g), rows, C / 8, P, L, slope, colsum,
+                                                                                  colsum_scale);
   count_launch();
   return launch_status();
 }

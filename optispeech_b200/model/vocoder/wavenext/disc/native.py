@@ -129,13 +129,15 @@ class _ConvFn(torch.autograd.Function):
         rows_in, cin_p = x.shape
         rows_out, cout = y.shape
         cin = w.shape[1]
-        g = ops.lrelu_bwd_h16(gy.contiguous(), y, ctx.P_out, ctx.L_out, ctx.slope)
+        want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx = dw = db = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if want_w:    # the bias gradient (column sums of g) comes out of the gate kernel
+            g, db = ops.lrelu_bwd_h16(gy.contiguous(), y, ctx.P_out, ctx.L_out, ctx.slope, colsum_scale=1.0 / GRAD_SCALE)
             dwp = torch.zeros((KSIZE, cout, cin_p), device=x.device, dtype=torch.float32)
             ops.gemm_wgrad_strided(g, x, dwp, taps=KSIZE, pad=PAD, stride=stride)
             dw = (dwp[:, :, :cin].permute(1, 2, 0) * (1.0 / GRAD_SCALE)).contiguous().view(w.shape)
-            db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
+        else:
+            g = ops.lrelu_bwd_h16(gy.contiguous(), y, ctx.P_out, ctx.L_out, ctx.slope)
         if ctx.needs_input_grad[0]:
             if stride == 1:   # the forward pack read as an MN-major operand, taps reversed
                 _, dx, _ = ops.gemm(g.view(1, rows_out, cout), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32,
@@ -331,13 +333,14 @@ class _RFirstFn(torch.autograd.Function):
         xcol, w, y = ctx.saved_tensors
         geom = ctx.geom
         rows = y.shape[0]
-        g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
         dspec = dw = db = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            g, db = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope, colsum_scale=1.0 / GRAD_SCALE)
             dwp = torch.zeros((1, 64, 64), device=g.device, dtype=torch.float32)
             ops.gemm_wgrad(g.view(1, rows, 64), xcol.view(1, rows, 64), dwp)
             dw = (dwp[0, :, :35] * (1.0 / GRAD_SCALE)).reshape(w.shape)
-            db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
+        else:
+            g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
         if ctx.needs_input_grad[0] and ctx.spec_shape is not None:
             wd = F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64)   # [tap][cout]
             _, col, _ = ops.gemm(g.view(1, rows, 64), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
@@ -385,15 +388,16 @@ class _RConvFn(torch.autograd.Function):
         NS, W_in, W_out, P_in, P_out, H_out, layer, slope = ctx.geo
         kh, kw, _sh, sw, ph, pw = layer
         cout, cin = w.shape[0], w.shape[1]
-        g = ops.lrelu_bwd_h16(gy.contiguous(), y, P_out, H_out, slope)
         rows_out = y.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            g, db = ops.lrelu_bwd_h16(gy.contiguous(), y, P_out, H_out, slope, colsum_scale=1.0 / GRAD_SCALE)
             xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)      # recomputed: cheaper than keeping 3x the activation
             dwp = torch.zeros((kh, cout, kw * cin), device=x.device, dtype=torch.float32)
             ops.gemm_wgrad_strided(g, xcol, dwp, taps=kh, pad=ph, stride=2)
             dw = (dwp.view(kh, cout, kw, cin).permute(1, 3, 0, 2) * (1.0 / GRAD_SCALE)).contiguous()
-            db = ops.colsum_h16(g) * (1.0 / GRAD_SCALE)
+        else:
+            g = ops.lrelu_bwd_h16(gy.contiguous(), y, P_out, H_out, slope)
         if ctx.needs_input_grad[0]:
             wd, pad = _phase_dgrad_pack(w.detach(), ph)
             _, dxcol, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=pad)

@@ -828,11 +828,14 @@ def mpd_post_bwd(dscore, x, w, period: int, L: int, P: int, scale: float, want_d
     return dx, (dwb[:Cc * 3].view(Cc, 3) if want_dw else None), (dwb[Cc * 3:Cc * 3 + 1] if want_dw else None)
 
 
-def lrelu_bwd_h16(dy, y, P: int, L: int, slope: float):
+def lrelu_bwd_h16(dy, y, P: int, L: int, slope: float, colsum_scale: Optional[float] = None):
+    """Gated gradient g; with `colsum_scale` also returns colsum_scale * column sums of g (the bias gradient), same launch."""
     rows, Cc = y.shape
     g = torch.empty_like(y)
-    _lib.check(_lib.load().osb_lrelu_bwd_h16(_ptr(dy), _ptr(y), _ptr(g), rows, Cc, P, L, slope, _stream()), "osb_lrelu_bwd_h16")
-    return g
+    cs = torch.zeros((Cc,), device=y.device, dtype=torch.float32) if colsum_scale is not None else None
+    _lib.check(_lib.load().osb_lrelu_bwd_h16(_ptr(dy), _ptr(y), _ptr(g), rows, Cc, P, L, slope, _ptr(cs), float(colsum_scale or 0.0), _stream()),
+               "osb_lrelu_bwd_h16")
+    return g if colsum_scale is None else (g, cs)
 
 
 def col2im_h16(col, rows_in: int, Cc: int, taps: int, pad: int, stride: int, reversed_taps: bool):
