@@ -35,6 +35,9 @@ class VocosDiscriminator(BaseVocoderDiscriminator):
         return loss, dict(loss_mp=loss_mp.detach(), loss_mrd=loss_mrd.detach())
 
     def forward_gen(self, wav, wav_hat):
+        if wav.is_cuda:   # weight packs are shared between this turn and the discriminator turn of the same step only
+            from . import native
+            native.reset_pack_memo()
         _, gen_mp, fr_mp, fg_mp = self.multiperioddisc(y=wav, y_hat=wav_hat)
         _, gen_mrd, fr_mrd, fg_mrd = self.multiresddisc(y=wav, y_hat=wav_hat)
         loss_gen_mp, parts_mp = self.gen_loss(disc_outputs=gen_mp)

@@ -18,6 +18,7 @@ feature-matching means would otherwise sit in fp16's subnormal range); it is rem
 """
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -29,6 +30,39 @@ from ..... import ops
 GRAD_SCALE = 256.0
 KSIZE, PAD = 5, 2
 C1_PAD = 64          # layer 1 has 32 channels; its output is stored 64 wide (one 64-element k-block of the next GEMM)
+
+# fp16 operand packs of the discriminator weights, shared by the generator turn and the discriminator turn of one step (the
+# weights do not change in between).  Keyed by the layer and its parameters' versions (torch in-place updates bump `_version`,
+# FlatAdamW bumps `_osb_epoch`); emptied at the start of every generator turn (VocosDiscriminator.forward_gen), so an entry never
+# outlives a step — inside a captured step the pack kernels of the generator turn are part of the graph and replayed with it.
+_PACK_MEMO = {}
+
+
+def reset_pack_memo() -> None:
+    _PACK_MEMO.clear()
+
+
+def _memo(key, make):
+    if key is None:
+        return make()
+    hit = _PACK_MEMO.get(key)
+    if hit is None:
+        if len(_PACK_MEMO) > 512:
+            _PACK_MEMO.clear()
+        hit = make()
+        _PACK_MEMO[key] = hit
+    return hit
+
+
+_UIDS = itertools.count(1)
+
+
+def _layer_key(conv):
+    uid = conv.__dict__.get("_osb_uid")
+    if uid is None:          # id() of a collected module can come back for a new one; this token cannot
+        uid = conv.__dict__["_osb_uid"] = next(_UIDS)
+    return (uid, conv.weight_v._version, conv.weight_g._version, getattr(conv.weight_v, "_osb_epoch", 0),
+            getattr(conv.weight_g, "_osb_epoch", 0))
 
 
 @dataclass(frozen=True)
@@ -109,7 +143,8 @@ class _ConvFn(torch.autograd.Function):
     """One (5,1) convolution + LeakyReLU on the flat layout: x (rows_in, Cin_p) fp16 -> y (rows_out, Cout) fp16."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, wp, stride: int, P_out: int, L_out: int, slope: float, y_pre=None):
+    def forward(ctx, x, w, bias, wp, stride: int, P_out: int, L_out: int, slope: float, y_pre=None, pkey=None):
+        ctx.pkey = pkey
         rows_in, cin_p = x.shape
         rows_out = rows_in // stride
         if y_pre is not None:
@@ -145,13 +180,16 @@ class _ConvFn(torch.autograd.Function):
                 dx = dx.view(rows_in, cin_p)
             else:
                 # phase decomposition: one stride-1 GEMM over g writes the three interleaved input-row phases side by side
-                w4 = w.detach().reshape(cout, cin, KSIZE, 1)
-                if cin_p != cin:
-                    w4 = F.pad(w4, (0, 0, 0, 0, 0, cin_p - cin))
-                wd, dpad = _phase_dgrad_pack(w4, PAD, stride)
+                def make():
+                    w4 = w.detach().reshape(cout, cin, KSIZE, 1)
+                    if cin_p != cin:
+                        w4 = F.pad(w4, (0, 0, 0, 0, 0, cin_p - cin))
+                    return _phase_dgrad_pack(w4, PAD, stride)
+
+                wd, dpad = _memo(("dgrad",) + ctx.pkey if ctx.pkey else None, make)
                 _, dxp, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=dpad)
                 dx = dxp.view(rows_in, cin_p)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 class _PostFn(torch.autograd.Function):
@@ -201,11 +239,11 @@ def effective_weights(disc):
     layers = []
     for i, conv in enumerate(list(disc.convs) + [disc.conv_post]):
         w = torch._weight_norm(conv.weight_v, conv.weight_g, 0)
-        wp = None
+        wp, key = None, _layer_key(conv)
         if 1 <= i <= 4:
             cout, cin = w.shape[0], w.shape[1]
-            wp = ops.pack_conv_h16(w.detach().reshape(cout, cin, KSIZE), k_pad=max(cin, C1_PAD))
-        layers.append((w, conv.bias, wp))
+            wp = _memo(("fwd",) + key, lambda: ops.pack_conv_h16(w.detach().reshape(cout, cin, KSIZE), k_pad=max(cin, C1_PAD)))
+        layers.append((w, conv.bias, wp, key))
     return layers
 
 
@@ -220,16 +258,16 @@ def period_forward(disc, wav: torch.Tensor, layers=None, pre=None, record=None):
     geom = Geometry.make(T, disc.period)
     layers = layers if layers is not None else effective_weights(disc)
     slope = float(disc.lrelu_slope)
-    (w1, b1, _), rest = layers[0], layers[1:5]
+    (w1, b1, _, _), rest = layers[0], layers[1:5]
     x = _FirstFn.apply(wav, w1, b1, geom, 3, slope, pre[0] if pre else None)
     outs = [x]
     fmap: List[object] = []
-    for i, (w, b, wp) in enumerate(rest, start=2):
+    for i, (w, b, wp, key) in enumerate(rest, start=2):
         stride = 3 if i <= 4 else 1
-        x = _ConvFn.apply(x, w, b, wp, stride, geom.P[i], geom.L[i], slope, pre[i - 1] if pre else None)
+        x = _ConvFn.apply(x, w, b, wp, stride, geom.P[i], geom.L[i], slope, pre[i - 1] if pre else None, key)
         outs.append(x)
         fmap.append(FlatMap(x, disc.period, geom.L[i], geom.P[i]))
-    wpost, bpost, _ = layers[5]
+    wpost, bpost = layers[5][0], layers[5][1]
     score = _PostFn.apply(x, wpost, bpost, disc.period, geom.L[5], geom.P[5], pre[5] if pre else None)
     outs.append(score)
     if record is not None:
@@ -280,7 +318,7 @@ def _pair(disc, y, y_hat, forward, weights, detach):
 
 
 def period_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
-    return _pair(disc, y, y_hat, period_forward, effective_weights(disc), lambda ws: [(w.detach(), b.detach(), wp) for w, b, wp in ws])
+    return _pair(disc, y, y_hat, period_forward, effective_weights(disc), lambda ws: [(w.detach(), b.detach(), wp, k) for w, b, wp, k in ws])
 
 
 # --------------------------------------------------------------------------------------------------
@@ -314,13 +352,14 @@ class _RFirstFn(torch.autograd.Function):
     into a 64-wide fp16 row (osb_spec_im2col_h16), which is also the operand of the weight gradient."""
 
     @staticmethod
-    def forward(ctx, spec, xcol, w, bias, geom: GeometryR, slope: float, y_pre=None):
+    def forward(ctx, spec, xcol, w, bias, geom: GeometryR, slope: float, y_pre=None, pkey=None):
         """`spec` only routes the gradient (it may be None when nothing upstream needs one); `xcol` is its tap gather."""
+        ctx.pkey = pkey
         rows = xcol.shape[0]
         if y_pre is not None:
             y = y_pre
         else:
-            wp = F.pad(w.detach().reshape(64, 35), (0, 29)).to(torch.float16).view(1, 64, 64)
+            wp = _memo(("fwd",) + pkey if pkey else None, lambda: F.pad(w.detach().reshape(64, 35), (0, 29)).to(torch.float16).view(1, 64, 64))
             _, y, _ = ops.gemm(xcol.view(1, rows, 64), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
                                bias=bias, seq_rows=(geom.P[1], geom.H[1]), lrelu=slope)
             y = y.view(rows, 64)
@@ -342,10 +381,11 @@ class _RFirstFn(torch.autograd.Function):
         else:
             g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
         if ctx.needs_input_grad[0] and ctx.spec_shape is not None:
-            wd = F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64)   # [tap][cout]
+            wd = _memo(("dgrad",) + ctx.pkey if ctx.pkey else None,
+                       lambda: F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64))   # [tap][cout]
             _, col, _ = ops.gemm(g.view(1, rows, 64), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
             dspec = ops.spec_col2im(col.view(rows, 64), ctx.spec_shape, geom.H[1], geom.W[1], geom.P[1], 1.0 / GRAD_SCALE)
-        return dspec, None, dw, db, None, None, None
+        return dspec, None, dw, db, None, None, None, None
 
 
 def _phase_dgrad_pack(w: torch.Tensor, ph: int, stride: int = 2):
@@ -366,14 +406,17 @@ class _RConvFn(torch.autograd.Function):
     """One Conv2d(64, 64, (kh, kw), (2, sw)) + LeakyReLU: x (NS*W_in*P_in, 64) -> y (NS*W_out*P_out, 64)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, NS: int, W_in: int, W_out: int, P_in: int, P_out: int, H_out: int, layer, slope: float, y_pre=None):
+    def forward(ctx, x, w, bias, NS: int, W_in: int, W_out: int, P_in: int, P_out: int, H_out: int, layer, slope: float, y_pre=None,
+                pkey=None):
         kh, kw, _sh, sw, ph, pw = layer
+        ctx.pkey = pkey
         if y_pre is not None:
             y = y_pre
         else:
             xcol = ops.wim2col_h16(x, NS, W_in, W_out, P_in, kw, pw, sw)
             cout, cin = w.shape[0], w.shape[1]
-            wp = w.detach().permute(2, 0, 3, 1).reshape(kh, cout, kw * cin).to(torch.float16).contiguous()     # [kh][cout][(kw, cin)]
+            wp = _memo(("fwd",) + pkey if pkey else None,
+                       lambda: w.detach().permute(2, 0, 3, 1).reshape(kh, cout, kw * cin).to(torch.float16).contiguous())   # [kh][cout][(kw, cin)]
             rows_in = xcol.shape[0]
             _, y, _ = ops.gemm(xcol.view(1, rows_in, kw * cin), wp, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32 | ops.FLAG_KEEPMASK,
                                pad=ph, bias=bias, seq_rows=(P_out, H_out), row_stride=2, lrelu=slope)
@@ -399,10 +442,10 @@ class _RConvFn(torch.autograd.Function):
         else:
             g = ops.lrelu_bwd_h16(gy.contiguous(), y, P_out, H_out, slope)
         if ctx.needs_input_grad[0]:
-            wd, pad = _phase_dgrad_pack(w.detach(), ph)
+            wd, pad = _memo(("dgrad",) + ctx.pkey if ctx.pkey else None, lambda: _phase_dgrad_pack(w.detach(), ph))
             _, dxcol, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=pad)
             dx = ops.wcol2im_h16(dxcol.view(2 * rows_out, kw * cin), NS, W_in, W_out, P_in, cin, kw, pw, sw)
-        return (dx, dw, db) + (None,) * 9
+        return (dx, dw, db) + (None,) * 10
 
 
 class _RPostFn(torch.autograd.Function):
@@ -421,6 +464,10 @@ class _RPostFn(torch.autograd.Function):
         want_dw = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dx, dw, db = ops.mrd_post_bwd(dscore, x, w2, NS, W, H, P, GRAD_SCALE, ctx.needs_input_grad[0], want_dw)
         return dx, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None, None
+
+
+def _resolution_weights(disc):
+    return [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias, _layer_key(c)) for c in list(disc.convs) + [disc.conv_post]]
 
 
 def _stft_frames(T: int, hop: int) -> int:
@@ -442,19 +489,19 @@ def resolution_forward(disc, wav: torch.Tensor, weights=None, pre=None, record=N
         F_bins, frames = n_fft // 2 + 1, _stft_frames(wav.shape[1], hop)
     geom = GeometryR.make(F_bins, frames)
     if weights is None:
-        weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
+        weights = _resolution_weights(disc)
     slope = float(disc.lrelu_slope)
     xcol1 = pre[0][0] if pre else ops.spec_im2col_h16(spec, geom.H[1], geom.W[1], geom.P[1])
-    x = _RFirstFn.apply(spec, xcol1, weights[0][0], weights[0][1], geom, slope, pre[0][1] if pre else None)
+    x = _RFirstFn.apply(spec, xcol1, weights[0][0], weights[0][1], geom, slope, pre[0][1] if pre else None, weights[0][2])
     outs = [x]
     fmap: List[object] = [FlatMap(x, geom.W[1], geom.H[1], geom.P[1])]
     for i in range(2, 6):
-        w, b = weights[i - 1]
+        w, b, key = weights[i - 1]
         x = _RConvFn.apply(x, w, b, NS, geom.W[i - 1], geom.W[i], geom.P[i - 1], geom.P[i], geom.H[i], MRD_LAYERS[i - 1], slope,
-                           pre[i - 1] if pre else None)
+                           pre[i - 1] if pre else None, key)
         outs.append(x)
         fmap.append(FlatMap(x, geom.W[i], geom.H[i], geom.P[i]))
-    wpost, bpost = weights[5]
+    wpost, bpost = weights[5][0], weights[5][1]
     score = _RPostFn.apply(x, wpost, bpost, NS, geom.W[5], geom.H[5], geom.P[5], pre[5] if pre else None)
     outs.append(score)
     if record is not None:
@@ -466,5 +513,4 @@ def resolution_forward(disc, wav: torch.Tensor, weights=None, pre=None, record=N
 
 def resolution_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
     """As period_forward_pair, for one resolution discriminator."""
-    weights = [(torch._weight_norm(c.weight_v, c.weight_g, 0), c.bias) for c in list(disc.convs) + [disc.conv_post]]
-    return _pair(disc, y, y_hat, resolution_forward, weights, lambda ws: [(w.detach(), b.detach()) for w, b in ws])
+    return _pair(disc, y, y_hat, resolution_forward, _resolution_weights(disc), lambda ws: [(w.detach(), b.detach(), k) for w, b, k in ws])
