@@ -22,23 +22,42 @@ __device__ __forceinline__ int reflect_index(int p, int L) {
   return p;
 }
 
-// In-place radix-2 decimation-in-time FFT over shared memory; input must already be in bit-reversed order.
+// In-place decimation-in-time FFT over shared memory; input must already be in bit-reversed order.
 // tw[k] = exp(-2*pi*i*k/N), k < N/2; INVERSE uses the conjugate twiddles (no 1/N normalisation).
+// Two radix-2 stages (lengths len and 2*len) are fused per pass: the four elements i0, i0+len/2, i0+len, i0+len+len/2 form a
+// closed set under both, so a thread carries them in registers — half the block-wide barriers and half the shared-memory
+// round trips of the stage-per-pass loop (5 passes instead of 10 for N = 1024).  An odd log2(N) starts with one radix-2 stage.
 template <int N, bool INVERSE>
 __device__ __forceinline__ void fft_inplace(float2* s, const float2* tw) {
+  constexpr int LOG2N = (N == 512) ? 9 : (N == 1024) ? 10 : 11;
+  int len = 2;
+  if constexpr (LOG2N & 1) {
+    for (int j = threadIdx.x; j < N / 2; j += FFT_THREADS) {   // len = 2: twiddle 1
+      const float2 a = s[2 * j], b = s[2 * j + 1];
+      s[2 * j] = make_float2(a.x + b.x, a.y + b.y);
+      s[2 * j + 1] = make_float2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+    len = 4;
+  }
 #pragma unroll 1
-  for (int len = 2; len <= N; len <<= 1) {
+  for (; len <= N / 2; len <<= 2) {
     const int half = len >> 1;
-    const int tstep = N / len;
-    for (int j = threadIdx.x; j < N / 2; j += FFT_THREADS) {
+    const int t1 = N / len, t2 = N / (2 * len);
+    for (int j = threadIdx.x; j < N / 4; j += FFT_THREADS) {
       const int grp = j / half, pos = j - grp * half;
-      const int i0 = grp * len + pos, i1 = i0 + half;
-      float2 w = tw[pos * tstep];
-      if (INVERSE) w.y = -w.y;
-      const float2 t = cmul(w, s[i1]);
-      const float2 a = s[i0];
-      s[i0] = make_float2(a.x + t.x, a.y + t.y);
-      s[i1] = make_float2(a.x - t.x, a.y - t.y);
+      const int i0 = grp * (2 * len) + pos;
+      float2 w1 = tw[pos * t1], w2 = tw[pos * t2], w3 = tw[(pos + half) * t2];
+      if (INVERSE) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      const float2 a = s[i0], b = s[i0 + half], c = s[i0 + len], d = s[i0 + len + half];
+      const float2 tb = cmul(w1, b), td = cmul(w1, d);
+      const float2 a1 = make_float2(a.x + tb.x, a.y + tb.y), b1 = make_float2(a.x - tb.x, a.y - tb.y);
+      const float2 c1 = make_float2(c.x + td.x, c.y + td.y), d1 = make_float2(c.x - td.x, c.y - td.y);
+      const float2 u = cmul(w2, c1), v = cmul(w3, d1);
+      s[i0] = make_float2(a1.x + u.x, a1.y + u.y);
+      s[i0 + len] = make_float2(a1.x - u.x, a1.y - u.y);
+      s[i0 + half] = make_float2(b1.x + v.x, b1.y + v.y);
+      s[i0 + len + half] = make_float2(b1.x - v.x, b1.y - v.y);
     }
     __syncthreads();
   }
