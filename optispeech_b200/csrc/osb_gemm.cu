@@ -732,9 +732,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int t0 = (blockIdx.x % p.m_tiles) * BM;
   const int n0 = blockIdx.y * BN;
   const int num_kb = (p.K + BKE - 1) / BKE;
-  // split precision: three passes over K per tap — (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo)
+  // split precision: three products per k-block — (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo).  The operands travel as TWO pipeline
+  // stages per k-block, (a_hi, w_hi) and (a_lo, w_lo), and the MMA warp forms the three products from the pair: 2/3 of the
+  // shared-memory fills of three separate passes (the main loop of these launches is bound by what one SM pulls from L2).
+  // With fewer than four stages (BN = 384: 64 KB per stage) a pair would leave 1.5 k-blocks in flight; those tiles keep three
+  // separate passes (pass-major order).
   const bool split_in = (p.flags & OSB_FLAG_SPLIT_IN) != 0;
-  const int nsub = split_in ? 3 : 1;
+  constexpr bool kPair = Cfg::STAGES >= 4;
+  const int nsub = split_in ? (kPair ? 2 : 3) : 1;
   const int iters = p.taps * nsub * num_kb;
 
   if (warp == 0) {
@@ -746,11 +751,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         const int tap = it / (nsub * num_kb);
         const int rem = it - tap * (nsub * num_kb);
-        const int sub = rem / num_kb;
-        const int kb = rem - sub * num_kb;
-        const int a_k = kb * BKE + (sub == 1 ? p.K : 0);
-        const int w_slice = tap + (sub == 2 ? p.w_lo_slice : 0) + (p.w_batch ? b : 0);
-        const int w_k = kb * BKE + (sub == 2 ? p.w_lo_koff : 0);
+        int kb, a_lo, w_lo;
+        if (kPair || !split_in) {     // k-block major: (hi, hi) then (lo, lo)
+          kb = rem / nsub;
+          a_lo = w_lo = (rem - kb * nsub) == 1;
+        } else {                      // pass major: (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo)
+          const int sub = rem / num_kb;
+          kb = rem - sub * num_kb;
+          a_lo = sub == 1;
+          w_lo = sub == 2;
+        }
+        const int a_k = kb * BKE + (a_lo ? p.K : 0);
+        const int w_slice = tap + (w_lo ? p.w_lo_slice : 0) + (p.w_batch ? b : 0);
+        const int w_k = kb * BKE + (w_lo ? p.w_lo_koff : 0);
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         if (p.row_stride > 1) {
@@ -779,6 +792,39 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = make_instr_desc(OSB_F16, BM, Cfg::NINST, 0, p.w_mn ? 1u : 0u);
     const uint64_t d0 = make_smem_desc_sw128(smem_u32(smem), 16, 1024);
     const uint64_t d0_mn = make_smem_desc_sw128(smem_u32(smem), BKE * ROW_BYTES, 1024);   // LBO = stride between 64-column chunks
+    if (kPair && split_in) {
+      // pairs of stages: s0 = (a_hi, w_hi), s1 = (a_lo, w_lo) of one k-block
+      for (int it = 0; it < iters; it += 2) {
+        const int s0 = it % Cfg::STAGES, s1 = (it + 1) % Cfg::STAGES;
+        mbar_wait(&full_bar[s0], (it / Cfg::STAGES) & 1);
+        mbar_wait(&full_bar[s1], ((it + 1) / Cfg::STAGES) & 1);
+        tc_fence_after_sync();
+        if (it == 0 && lane == 0) GT_TRACE(4);
+        if (elect_one()) {
+          const uint64_t a_hi = d0 + static_cast<uint64_t>((s0 * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t a_lo = d0 + static_cast<uint64_t>((s1 * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t w_hi = a_hi + static_cast<uint64_t>(Cfg::A_BYTES >> 4);
+          const uint64_t w_lo = a_lo + static_cast<uint64_t>(Cfg::A_BYTES >> 4);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const uint64_t da0 = g == 1 ? a_lo : a_hi;
+            const uint64_t db0 = g == 2 ? w_lo : w_hi;
+#pragma unroll
+            for (int k = 0; k < ROW_BYTES / UMMA_K_BYTES; ++k) {
+#pragma unroll
+              for (int c = 0; c < Cfg::NCHUNK; ++c) {
+                umma_ss<false>(tmem_base + c * Cfg::NINST, da0 + static_cast<uint64_t>((k * UMMA_K_BYTES) >> 4),
+                               db0 + static_cast<uint64_t>((c * Cfg::NINST * ROW_BYTES + k * UMMA_K_BYTES) >> 4), idesc,
+                               (it | g | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(&empty_bar[s0]);
+          umma_commit(&empty_bar[s1]);
+        }
+        __syncwarp();
+      }
+    } else
     for (int it = 0; it < iters; ++it) {
       const int s = it % Cfg::STAGES;
       const uint32_t ph = (it / Cfg::STAGES) & 1;
