@@ -44,6 +44,8 @@ struct FusedParams {
   __half* h_out;         // (B, T, I) fp16 GELU output (A operand of pwconv2)
   int I;
   int B, T, m_tiles;
+  int pair;              // 1: (C = 384, T = 64) a 128-row tile holds TWO consecutive samples; B, T above are then B/2 and 128 (the
+                         //    rows of two 64-frame samples are contiguous), only the input staging and row_scale see the real samples
   int nsplit;            // > 1: blockIdx.y owns a slice of the intermediate chunks and adds its partial result into `out` (pre-zeroed)
   float eps;
   long long* trace;      // optional (developer): clock64 timeline of CTA 0, [role][event] (see tools/probe_fused.py)
@@ -154,7 +156,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     if (lane == 0) {
       mbar_expect_tx(x_full, Cfg::NXB * Cfg::XR * 128);
 #pragma unroll
-      for (int i = 0; i < Cfg::NXB; ++i) tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, t0 - 3, b);
+      for (int i = 0; i < Cfg::NXB; ++i) tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, t0 - 3, p.pair ? 2 * b : b);
       mbar_wait(a_ready, 0);   // the weight ring overlays the staged input tile: the prologue has to be done with it
       for (int j = 0; j < n_ch; ++j) {
         const int st = j % WS;
@@ -265,7 +267,8 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
           if (ww == 0 && lane == 0) {
             mbar_expect_tx(x_full, Cfg::NXB * Cfg::XR * 128);
 #pragma unroll
-            for (int i = 0; i < Cfg::NXB; ++i) tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, t0 + pass * Cfg::RP - 3, b);
+            for (int i = 0; i < Cfg::NXB; ++i)   // pair mode: the second half of the tile is the NEXT sample's rows 0..63 (+ its own zero halo)
+              tma_load_3d(sX + i * Cfg::XB_STRIDE, &tmX, x_full, i * 32, p.pair ? -3 : t0 + pass * Cfg::RP - 3, p.pair ? 2 * b + pass : b);
           }
         }
         mbar_wait(x_full, pass & 1);
@@ -453,7 +456,7 @@ convnext_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
     tc_fence_after_sync();
     float* stile = reinterpret_cast<float*>(smem);
     constexpr int OLD = Cfg::OUT_LD;
-    const float rs = p.row_scale != nullptr ? p.row_scale[b] : 1.f;
+    const float rs = p.row_scale != nullptr ? p.row_scale[p.pair ? 2 * b + (row >> 6) : b] : 1.f;
     constexpr int CH = C / 2;  // columns per worker half
     for (int c0 = half * CH; c0 < (half + 1) * CH; c0 += 32) {
       uint32_t rr[32];
@@ -532,7 +535,8 @@ int launch_fused(const void* w1_h16, const void* w2_h16, const FusedParams& p, c
   if (rc != OSB_OK) return rc;
   // input (B, T, C) fp32: boxes of 32 channels (128 B) x XR rows; rows outside [0, T) read as zero (Conv1d zero padding)
   CUtensorMap tmX;
-  rc = make_tmap_3d(&tmX, p.x, TMA_F32, C, p.T, p.B, C, static_cast<uint64_t>(p.T) * C, 32, Cfg::XR);
+  const int T_true = p.pair ? p.T / 2 : p.T, B_true = p.pair ? p.B * 2 : p.B;
+  rc = make_tmap_3d(&tmX, p.x, TMA_F32, C, T_true, B_true, C, static_cast<uint64_t>(T_true) * C, 32, Cfg::XR);
   if (rc != OSB_OK) return rc;
   static bool attr = false;
   if (!attr) {
@@ -570,6 +574,11 @@ static int fused_fwd_impl(const float* x, const float* dw_w, const float* dw_b, 
   if (train) OSB_REQUIRE(rstd_out && pre_out && h_out, OSB_ERR_ARG);
   FusedParams p;
   p.x = x; p.dw_w = dw_w; p.dw_b = dw_b; p.b1 = b1f; p.b2 = b2; p.gamma = gamma; p.row_scale = row_scale; p.pad_mask = pad_mask;
+  // Training vocoder: 64-frame segments.  One sample per 128-row tile would leave every tile half empty (twice the tensor and
+  // epilogue work per useful row); two consecutive samples share a tile instead — their rows are contiguous in (B, 64, C).
+  const bool pair = (C == 384 && T == 64 && B % 2 == 0);
+  p.pair = pair ? 1 : 0;
+  if (pair) { B /= 2; T = 128; }
   p.out = out; p.B = B; p.T = T; p.m_tiles = (T + FB_M - 1) / FB_M; p.eps = eps; p.I = I;
   p.xhat_out = static_cast<__half*>(xhat_out); p.rstd_out = rstd_out; p.pre_out = static_cast<__half*>(pre_out);
   p.h_out = static_cast<__half*>(h_out);
