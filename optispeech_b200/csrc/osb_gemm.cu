@@ -1151,6 +1151,9 @@ using namespace osb;
 
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_narrow_tiles = 0;
+static int g_wgrad_min_iters = 48;
+/* developer hook (not in the public header): minimum number of 64-row pipeline iterations per weight-gradient CTA */
+extern "C" void osb_debug_set_wgrad_min_iters(int n) { g_wgrad_min_iters = n > 0 ? n : 48; }
 /* developer hook (not in the public header): 0 = keep 256-wide tiles for small problems (A/B timing) */
 extern "C" void osb_debug_set_gemm_narrow_tiles(int on) { g_gemm_narrow_tiles = on; }
 /* developer hook (not in the public header): device buffer of 16 int64 receiving a clock64 timeline of CTA (0,0) */
@@ -1341,10 +1344,13 @@ static int wgrad_impl(const void* dy, int64_t ldy, const void* a, int64_t lda, f
   p.per_batch = per_batch;
   const int zcount = per_batch ? B : taps;
   const int total_rb = per_batch ? p.row_blocks_per_batch : B * p.row_blocks_per_batch;
-  // Split the contraction rows over CTAs to fill the machine, but keep >= 6 pipeline iterations per CTA: every CTA pays a
-  // fixed prologue and flushes a 128x128 fp32 tile with atomics, so over-splitting small problems costs more than it gains.
+  // Split the contraction rows over CTAs, but keep >= 48 pipeline iterations (64 rows each) per CTA.  Every CTA pays a fixed
+  // prologue and flushes a 128x128 fp32 tile with atomics, and in the training step these launches run on side streams beside
+  // the data-gradient chain: what counts there is the SM-time a launch takes from its neighbours, not its own latency.  Measured
+  // on the B=32 step (6144-row problems): >= 6 iterations -> 0.46 ms of weight-gradient kernels alone, 2.27 ms/step;
+  // >= 48 -> 0.69 ms alone, 2.18 ms/step; no split at all -> 1.3 ms alone, 2.26 ms/step.
   int splits = (148 + n_tiles * k_tiles * zcount - 1) / (n_tiles * k_tiles * zcount);
-  if (splits > total_rb / 6) splits = total_rb / 6;
+  if (splits > total_rb / g_wgrad_min_iters) splits = total_rb / g_wgrad_min_iters;
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.dw = dw;
