@@ -560,6 +560,8 @@ using namespace osb;
 
 static long long* g_fused_trace = nullptr;
 static int g_fused_nsplit = 0;
+static int g_fused_nsplit_cap = 4;
+extern "C" void osb_debug_set_fused_nsplit_cap(int n) { g_fused_nsplit_cap = n > 0 ? n : 4; }
 /* developer hook (not in the public header): force the intermediate-dimension split of the fused block (0 = automatic) */
 extern "C" void osb_debug_set_fused_nsplit(int n) { g_fused_nsplit = n; }
 /* developer hook (not in the public header): device buffer of 3*256 int64 receiving a clock64 timeline of CTA 0 */
@@ -589,7 +591,7 @@ static int fused_fwd_impl(const float* x, const float* dw_w, const float* dw_b, 
   {
     const int tiles = B * p.m_tiles;
     const int nch = I / FB_NC;
-    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > 4 ? 4 : 148 / tiles));
+    int ns = g_fused_nsplit > 0 ? g_fused_nsplit : (tiles * 2 > 148 ? 1 : (148 / tiles > g_fused_nsplit_cap ? g_fused_nsplit_cap : 148 / tiles));
     if (ns > nch / 2) ns = nch / 2;
     p.nsplit = ns < 1 ? 1 : ns;
   }

@@ -398,6 +398,41 @@ __global__ void pack_h16_kernel(const float* __restrict__ src, long long src_ld,
   if (dst_lo != nullptr) dst_lo[r * dst_rs + c] = __float2half_rn(v - __half2float(hi));
 }
 
+// Contiguous-source fast path of pack_h16: a thread converts 8 consecutive elements of a row (two 16-byte loads, one 16-byte
+// store per output).  Needs src_cs == 1, cols % 8 == 0 (so a group is either all data or all padding) and 16-byte aligned rows.
+__global__ void __launch_bounds__(256)
+pack_h16_vec8_kernel(const float* __restrict__ src, long long src_ld, const float* __restrict__ col_scale, __half* __restrict__ dst,
+                     __half* __restrict__ dst_lo, long long dst_rs, int dst_cols, long long rows, int cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = dst_cols >> 3;
+  if (i >= rows * groups) return;
+  const long long r = i / groups;
+  const int c = static_cast<int>(i - r * groups) << 3;
+  float v[8];
+  if (c < cols) {
+    const float4 a = *reinterpret_cast<const float4*>(src + r * src_ld + c);
+    const float4 b = *reinterpret_cast<const float4*>(src + r * src_ld + c + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if (col_scale != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] *= col_scale[c + q];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+  }
+  __half h[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) h[q] = __float2half_rn(v[q]);
+  *reinterpret_cast<uint4*>(dst + r * dst_rs + c) = *reinterpret_cast<const uint4*>(h);
+  if (dst_lo != nullptr) {
+    __half l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) l[q] = __float2half_rn(v[q] - __half2float(h[q]));
+    *reinterpret_cast<uint4*>(dst_lo + r * dst_rs + c) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 // Conv1d weight (N, Cin, k) fp32 -> fp16 tensor-core operand, all taps in one launch.
 //   forward form  (transpose_reverse = 0): dst[tap][n][c] = w[n][c][tap]            (k, N, Kp), zero for c >= Cin
 //   dgrad form    (transpose_reverse = 1): dst[tap][c][n] = w[n][c][k-1-tap]        (k, Cin, N)
@@ -628,8 +663,15 @@ extern "C" int osb_pack_h16(const float* src, int64_t src_ld, int64_t src_cs, co
   OSB_REQUIRE(src && dst, OSB_ERR_ARG);
   OSB_REQUIRE(rows > 0 && cols > 0 && dst_cols >= cols && dst_rs >= dst_cols, OSB_ERR_SHAPE);
   const long long n = rows * dst_cols;
-  pack_h16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, src_ld, src_cs, col_scale, static_cast<__half*>(dst), static_cast<__half*>(dst_lo), dst_rs, dst_cols, rows, cols);
+  const bool vec = src_cs == 1 && cols % 8 == 0 && dst_cols % 8 == 0 && src_ld % 4 == 0 && dst_rs % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                   (dst_lo == nullptr || (reinterpret_cast<uintptr_t>(dst_lo) & 15) == 0);
+  if (vec)
+    pack_h16_vec8_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, src_ld, col_scale, static_cast<__half*>(dst), static_cast<__half*>(dst_lo), dst_rs, dst_cols, rows, cols);
+  else
+    pack_h16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, src_ld, src_cs, col_scale, static_cast<__half*>(dst), static_cast<__half*>(dst_lo), dst_rs, dst_cols, rows, cols);
   count_launch();
   return launch_status();
 }
