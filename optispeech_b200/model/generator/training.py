@@ -40,8 +40,9 @@ class AlignmentModule(nn.Module):
         return ConvStackFn.apply(feats, ((odim + 63) // 64) * 64, self.f_conv1.weight, self.f_conv1.bias, self.f_conv2.weight,
                                  self.f_conv2.bias, self.f_conv3.weight, self.f_conv3.bias)
 
-    def attend(self, fe, te, text_lengths, feats_lengths):
-        prior = self._generate_prior(text_lengths, feats_lengths, te.shape[1], fe.shape[1])
+    def attend(self, fe, te, text_lengths, feats_lengths, prior=None):
+        if prior is None:
+            prior = self._generate_prior(text_lengths, feats_lengths, te.shape[1], fe.shape[1])
         # x_masks is the prefix mask of text_lengths in every reference call site (generator/__init__.py:120-126)
         return AttnLogProbFn.apply(fe, te, prior, text_lengths.contiguous(), feats_lengths.contiguous())
 
@@ -149,6 +150,9 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     s_feat = ops.side_stream(dev, 1)
     s_feat.wait_stream(main)
     with torch.cuda.stream(s_feat):
+        # the beta-binomial prior depends on the lengths only: computed here, at the start of the step, instead of between the
+        # text convolutions and the attention on the critical chain (30 us)
+        prior = am._generate_prior(x_lengths, mel_lengths, x.shape[1], mel.shape[-1])
         fe = am.encode_feats(mel.transpose(1, 2))     # depends on the mel input only
     h, _ = gen.text_embedding(x)
     h = gen.encoder(h, in_pad)
@@ -164,7 +168,7 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     s_attn.wait_stream(s_feat)
     with torch.cuda.stream(s_attn):
         te = am.encode_text(h)
-        log_p_attn = am.attend(fe, te, x_lengths, mel_lengths)
+        log_p_attn = am.attend(fe, te, x_lengths, mel_lengths, prior=prior)
     main.wait_stream(s_attn)
     # The forward-sum loss only meets the rest of the step at the final sum: its sequential recursion (one CTA per sample)
     # runs on a side stream, next to the alignment search, the predictors and the decoder.
