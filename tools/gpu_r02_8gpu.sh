@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for n in 8 4; do
+for n in 8 4 2; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 20 --warmup 5 --no-variants > gpurun_out/bench_${n}gpu.json 2> gpurun_out/bench_${n}gpu.err; echo "bench$n rc=$?"
 python - <<PY
 import json
