@@ -250,8 +250,17 @@ class BaseModule(nn.Module):
         wav = wav.to(dev, non_blocking=True).to(torch.float32).contiguous()
         from .. import ops
         # ground-truth crop wav[b, start*hop : start*hop + seg], zero-filled past the end like get_segments_numpy's pre-zeroed
-        # array (utils/segments.py:63-72) and the host path (stage_batch)
-        gen_outputs["wav"] = ops.crop_segments(wav, gen_outputs["start_idx"], seg, self.hop_length).type_as(gen_outputs["wav_hat"])
+        # array (utils/segments.py:63-72) and the host path (stage_batch).  start_idx is produced by the decoder / vocoder branch:
+        # when that branch has not been joined yet (pre-training, deferred join) the crop is queued on the branch's stream, behind
+        # the kernel that writes start_idx — on the current stream it would read the previous step's indices.
+        pending = gen_outputs.get("_pending_streams") or []
+        if pending:
+            pending[0].wait_stream(torch.cuda.current_stream())      # `wav` was made contiguous / fp32 on the current stream
+            with torch.cuda.stream(pending[0]):
+                gen_outputs["wav"] = ops.crop_segments(wav, gen_outputs["start_idx"], seg, self.hop_length).type_as(gen_outputs["wav_hat"])
+            gen_outputs.setdefault("_pending_keepalive", []).append(wav)
+        else:
+            gen_outputs["wav"] = ops.crop_segments(wav, gen_outputs["start_idx"], seg, self.hop_length).type_as(gen_outputs["wav_hat"])
         return gen_outputs
 
     def configure_optimizers(self):

@@ -136,15 +136,22 @@ class OptiSpeechGenerator(nn.Module):
                     cache["seen"].clear()
                 cache["seen"][key] = True
                 return fn(**inputs)
+            if cache["seen"][key] == "eager":     # a capture of this shape failed before: stay on the launch path
+                return fn(**inputs)
             static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in inputs.items()}
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                fn(**static)                      # warm-up on the capture stream (allocator, tensor maps, packs)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = fn(**static)
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn(**static)                      # warm-up on the capture stream (allocator, tensor maps, packs)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = fn(**static)
+            except RuntimeError:                      # e.g. another thread of the process is capturing: not an error of the request
+                torch.cuda.synchronize()
+                cache["seen"][key] = "eager"
+                return fn(**inputs)
             entry = (graph, static, out)
             while len(cache["graphs"]) >= self._SYNTH_MAX_GRAPHS:
                 cache["graphs"].pop(next(iter(cache["graphs"])))

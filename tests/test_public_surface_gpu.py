@@ -268,3 +268,31 @@ def test_checkpoint_round_trip_resumes_optimizer_state(cuda_device, tmp_path):
     ref_opt.step()
     resumed.optimizers()[0].load_state_dict(ref_opt.state_dict())
     assert resumed.optimizers()[0]._steps[0] == 1
+
+
+def test_ground_truth_crop_follows_the_deferred_branch(cuda_device):
+    """Pre-training phase: the decoder / vocoder branch (which draws the segment starts) is joined only at the end of the step.
+    The ground-truth waveform crop must use THIS call's start indices, not whatever the buffer held before."""
+    spec = ModelSpec()
+    model = _fresh_model(spec, cuda_device)
+    gen = model.generator
+    hop = spec.hop_length
+    for seed in (1, 2, 3):
+        batch = _small_batch(spec, 3, 48, 200, seed=seed, dev=cuda_device)
+        gen.vocoder_needs_grad, gen.defer_vocoder_join = False, True
+        try:
+            out = model._process_batch(batch)
+        finally:
+            gen.vocoder_needs_grad, gen.defer_vocoder_join = True, False
+        for s_ in out.get("_pending_streams", []):
+            torch.cuda.current_stream().wait_stream(s_)
+        torch.cuda.synchronize()
+        start = out["start_idx"].cpu()
+        seg = out["segment_size"] * hop
+        wav = batch["wav"].cpu()
+        for b in range(3):
+            lo = int(start[b]) * hop
+            want = torch.zeros(seg)
+            chunk = wav[b, lo: lo + seg]
+            want[: chunk.shape[0]] = chunk
+            assert torch.equal(out["wav"][b].cpu().float(), want), (seed, b)
