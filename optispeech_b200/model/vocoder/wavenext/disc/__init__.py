@@ -23,10 +23,20 @@ class VocosDiscriminator(BaseVocoderDiscriminator):
                                                       win_length=fe.win_length, n_mels=fe.n_feats, f_min=fe.f_min, f_max=fe.f_max)
         self.mr_stft_loss = MultiResolutionSTFTLoss()
 
+    @staticmethod
+    def _all_discriminators(wav):
+        """On the device the eight discriminators run side by side on their own streams, joined when the block ends."""
+        if wav.is_cuda:
+            from . import native
+            return native.deferred_join()
+        import contextlib
+        return contextlib.nullcontext()
+
     # Log dictionaries hold device scalars (detached); the reference calls .item() on every term (one host sync each).
     def forward_disc(self, wav, wav_hat):
-        real_mp, gen_mp, _, _ = self.multiperioddisc(y=wav, y_hat=wav_hat)
-        real_mrd, gen_mrd, _, _ = self.multiresddisc(y=wav, y_hat=wav_hat)
+        with self._all_discriminators(wav):
+            real_mp, gen_mp, _, _ = self.multiperioddisc(y=wav, y_hat=wav_hat)
+            real_mrd, gen_mrd, _, _ = self.multiresddisc(y=wav, y_hat=wav_hat)
         loss_mp, parts_mp, _ = self.disc_loss(disc_real_outputs=real_mp, disc_generated_outputs=gen_mp)
         loss_mrd, parts_mrd, _ = self.disc_loss(disc_real_outputs=real_mrd, disc_generated_outputs=gen_mrd)
         loss_mp = loss_mp / len(parts_mp)
@@ -38,8 +48,9 @@ class VocosDiscriminator(BaseVocoderDiscriminator):
         if wav.is_cuda:   # weight packs are shared between this turn and the discriminator turn of the same step only
             from . import native
             native.reset_pack_memo()
-        _, gen_mp, fr_mp, fg_mp = self.multiperioddisc(y=wav, y_hat=wav_hat)
-        _, gen_mrd, fr_mrd, fg_mrd = self.multiresddisc(y=wav, y_hat=wav_hat)
+        with self._all_discriminators(wav):
+            _, gen_mp, fr_mp, fg_mp = self.multiperioddisc(y=wav, y_hat=wav_hat)
+            _, gen_mrd, fr_mrd, fg_mrd = self.multiresddisc(y=wav, y_hat=wav_hat)
         loss_gen_mp, parts_mp = self.gen_loss(disc_outputs=gen_mp)
         loss_gen_mrd, parts_mrd = self.gen_loss(disc_outputs=gen_mrd)
         loss_gen_mp = loss_gen_mp / len(parts_mp)

@@ -116,8 +116,7 @@ class MultiPeriodDiscriminator(_Multi):
             return super().forward(y, y_hat)
         from . import native
         real, fake, fr, ff = [], [], [], []
-        for d in self.discriminators:
-            a, b, fa, fb = native.period_forward_pair(d, y, y_hat)
+        for a, b, fa, fb in native.fan_out(self.discriminators, y, y_hat, native.period_forward_pair, native.DISC_STREAM_SLOT0):
             real.append(a); fr.append(fa); fake.append(b); ff.append(fb)
         return real, fake, fr, ff
 
@@ -132,7 +131,6 @@ class MultiResolutionDiscriminator(_Multi):
             return super().forward(y, y_hat)
         from . import native
         real, fake, fr, ff = [], [], [], []
-        for d in self.discriminators:
-            a, b, fa, fb = native.resolution_forward_pair(d, y, y_hat)
+        for a, b, fa, fb in native.fan_out(self.discriminators, y, y_hat, native.resolution_forward_pair, native.DISC_STREAM_SLOT0 + 8):
             real.append(a); fr.append(fa); fake.append(b); ff.append(fb)
         return real, fake, fr, ff

@@ -317,6 +317,56 @@ def _pair(disc, y, y_hat, forward, weights, detach):
     return s[:B], s[B:], fr, fg
 
 
+DISC_STREAM_SLOT0 = 20       # side-stream slots 20.. : one per discriminator (default priority)
+PARALLEL_DISCRIMINATORS = True
+_DEFERRED_JOINS: list = []   # side streams of fan-outs whose join was left to the caller (deferred_join)
+
+
+class deferred_join:
+    """Context manager: fan-outs inside it do not join their streams on return; the join happens when the context ends.
+    VocosDiscriminator uses it so that the resolution discriminators start next to the period discriminators instead of behind
+    their join."""
+
+    def __enter__(self):
+        self.depth0 = len(_DEFERRED_JOINS)
+        _DEFERRED_JOINS.append(None)   # marker: a context is open
+        return self
+
+    def __exit__(self, *exc):
+        pending = _DEFERRED_JOINS[self.depth0 + 1:]
+        del _DEFERRED_JOINS[self.depth0:]
+        for s in pending:
+            torch.cuda.current_stream(s.device).wait_stream(s)
+        return False
+
+
+def fan_out(discs, y: torch.Tensor, y_hat: torch.Tensor, pair_fn, slot0: int):
+    """Runs `pair_fn(d, y, y_hat)` for every discriminator on the discriminator's OWN side stream and joins them.
+
+    The five period and three resolution discriminators are independent chains of ~40 launches each whose small kernels
+    (layer 1, conv_post, gates, gathers, weight-norm, packs) and GEMM wave tails leave most SMs idle when they run one after
+    the other; on separate streams they fill each other's gaps.  Autograd replays a node's backward on the stream its forward
+    ran on, so the backward chains overlap the same way, and inside a captured step the forks / joins are graph edges.  A
+    discriminator keeps its slot, so the layer outputs it leaves for the discriminator turn (`_turn_cache`) and its memoised
+    weight packs are produced and consumed in stream order."""
+    dev = y.device
+    cur = torch.cuda.current_stream(dev)
+    outs, streams = [], []
+    for i, d in enumerate(discs):
+        s = ops.side_stream(dev, slot0 + i) if PARALLEL_DISCRIMINATORS else cur
+        if s != cur:
+            s.wait_stream(cur)
+            streams.append(s)
+        with torch.cuda.stream(s):
+            outs.append(pair_fn(d, y, y_hat))
+    if _DEFERRED_JOINS:
+        _DEFERRED_JOINS.extend(streams)
+    else:
+        for s in streams:
+            cur.wait_stream(s)
+    return outs
+
+
 def period_forward_pair(disc, y: torch.Tensor, y_hat: torch.Tensor):
     return _pair(disc, y, y_hat, period_forward, effective_weights(disc), lambda ws: [(w.detach(), b.detach(), wp, k) for w, b, wp, k in ws])
 

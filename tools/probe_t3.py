@@ -23,6 +23,8 @@ for mode in which:
     print(f"[{mode}] T3 graph replay: {t3:.3f} ms/step")
     if model._graphed is not None:
         model._graphed.release()
+    if int(os.environ.get('T3_ROWS', '28')) == 0:
+        continue
     model.cuda_graph = False
     model._graphed = None
     for i in range(2):
@@ -35,7 +37,7 @@ for mode in which:
     rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
     total = sum(e.device_time_total for e in rows)
     print(f"[{mode}] eager step: {total / 1e3:.2f} ms of kernel time, {sum(e.count for e in rows)} launches")
-    for e in rows[:28]:
+    for e in rows[:int(os.environ.get('T3_ROWS', '28'))]:
         print(f"   {e.device_time_total / 1e3:8.3f} ms  x{e.count:<4d} {e.key[:110]}")
     del model
     torch.cuda.empty_cache()
