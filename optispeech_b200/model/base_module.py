@@ -14,6 +14,7 @@ Departures, all to keep the hot loop free of host synchronisation:
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from types import SimpleNamespace
 from typing import Any, Dict, Optional
@@ -23,6 +24,10 @@ import torch
 from torch import nn
 
 from ..optim import FlatAdamW
+
+
+OVERLAP_TURNS = True    # GAN phase: the discriminator turn is queued next to the generator's backward pass (see _training_step_eager)
+DISC_TURN_SLOT = 19     # ops.side_stream slot of the discriminator turn
 
 
 class _FitLoopState:
@@ -325,6 +330,14 @@ class BaseModule(nn.Module):
         self.toggle_optimizer(opt_g)
         loss_g, wav_outputs = self.training_step_g(batch, train_discriminator=train_discriminator)
         loss_g = loss_g / loss_scaling_factor
+        # The discriminator turn reads the two waveforms, the discriminator weights and what the discriminators' forward
+        # left behind (layer outputs, weight packs) — all complete here — and nothing the generator's backward pass or
+        # optimizer writes.  With cached generator outputs (the reference default) it is therefore queued on its own stream
+        # forked HERE, so its kernels run next to the generator's backward pass instead of behind the generator optimizer.
+        overlap = (train_discriminator and OVERLAP_TURNS and self.device.type == "cuda" and self.train_args.cache_generator_outputs)
+        if overlap:
+            fork_event = torch.cuda.Event()
+            fork_event.record()
         if should_apply:
             opt_g.zero_grad()
         self.manual_backward(loss_g)
@@ -345,15 +358,32 @@ class BaseModule(nn.Module):
         self.toggle_optimizer(opt_d)
         if not self.train_args.cache_generator_outputs:
             wav_outputs = None
-        loss_d = self.training_step_d(batch, wav_outputs=wav_outputs) / loss_scaling_factor
-        if should_apply:
-            opt_d.zero_grad()
-        self.manual_backward(loss_d)
-        self.clip_gradients(opt_d, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
-        if should_apply:
-            opt_d.step()
-            if not self._capturing:
-                sched_d.step()
+        turn_ctx = contextlib.nullcontext()
+        if overlap:
+            from .. import ops
+            from .vocoder.wavenext.disc import native as disc_native
+            main_stream = torch.cuda.current_stream()
+            turn_stream = ops.side_stream(self.device, DISC_TURN_SLOT)
+            if turn_stream != main_stream:
+                turn_stream.wait_event(fork_event)
+                turn_ctx = torch.cuda.stream(turn_stream)
+                disc_native.STREAM_SET = 1
+        try:
+            with turn_ctx:
+                loss_d = self.training_step_d(batch, wav_outputs=wav_outputs) / loss_scaling_factor
+                if should_apply:
+                    opt_d.zero_grad()
+                self.manual_backward(loss_d)
+                self.clip_gradients(opt_d, gradient_clip_val=self.train_args.gradient_clip_val, gradient_clip_algorithm="norm")
+                if should_apply:
+                    opt_d.step()
+                    if not self._capturing:
+                        sched_d.step()
+        finally:
+            if overlap:
+                disc_native.STREAM_SET = 0
+                if turn_stream != main_stream:
+                    main_stream.wait_stream(turn_stream)
         self.untoggle_optimizer(opt_d)
 
     def training_step_g(self, batch, train_discriminator):

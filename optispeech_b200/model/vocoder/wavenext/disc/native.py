@@ -139,6 +139,20 @@ class _FirstFn(torch.autograd.Function):
         return dwav, (dw.reshape(ctx.w_shape) if dw is not None else None), db, None, None, None, None
 
 
+def _conv_dgrad_pack(w, cin_p: int, stride: int, pkey):
+    """Phase-decomposed data-gradient pack of a strided (5,1) layer (memoised per step).  It is first requested in the FORWARD
+    pass of a turn that will need it: the pack kernels then sit before the point where the discriminator turn forks off
+    (BaseModule: the two turns overlap), so both turns read a finished pack."""
+    def make():
+        cout, cin = w.shape[0], w.shape[1]
+        w4 = w.detach().reshape(cout, cin, KSIZE, 1)
+        if cin_p != cin:
+            w4 = F.pad(w4, (0, 0, 0, 0, 0, cin_p - cin))
+        return _phase_dgrad_pack(w4, PAD, stride)
+
+    return _memo(("dgrad",) + pkey if pkey else None, make)
+
+
 class _ConvFn(torch.autograd.Function):
     """One (5,1) convolution + LeakyReLU on the flat layout: x (rows_in, Cin_p) fp16 -> y (rows_out, Cout) fp16."""
 
@@ -147,6 +161,8 @@ class _ConvFn(torch.autograd.Function):
         ctx.pkey = pkey
         rows_in, cin_p = x.shape
         rows_out = rows_in // stride
+        if stride != 1 and pkey is not None and ctx.needs_input_grad[0]:
+            _conv_dgrad_pack(w, cin_p, stride, pkey)
         if y_pre is not None:
             y = y_pre
         else:
@@ -180,13 +196,7 @@ class _ConvFn(torch.autograd.Function):
                 dx = dx.view(rows_in, cin_p)
             else:
                 # phase decomposition: one stride-1 GEMM over g writes the three interleaved input-row phases side by side
-                def make():
-                    w4 = w.detach().reshape(cout, cin, KSIZE, 1)
-                    if cin_p != cin:
-                        w4 = F.pad(w4, (0, 0, 0, 0, 0, cin_p - cin))
-                    return _phase_dgrad_pack(w4, PAD, stride)
-
-                wd, dpad = _memo(("dgrad",) + ctx.pkey if ctx.pkey else None, make)
+                wd, dpad = _conv_dgrad_pack(w, cin_p, stride, ctx.pkey)
                 _, dxp, _ = ops.gemm(g.view(1, rows_out, cout), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32, pad=dpad)
                 dx = dxp.view(rows_in, cin_p)
         return dx, dw, db, None, None, None, None, None, None, None
@@ -319,6 +329,7 @@ def _pair(disc, y, y_hat, forward, weights, detach):
 
 DISC_STREAM_SLOT0 = 20       # side-stream slots 20.. : one per discriminator (default priority)
 PARALLEL_DISCRIMINATORS = True
+STREAM_SET = 0               # 1 while the discriminator turn of an overlapped step runs (BaseModule): its own set of streams
 _DEFERRED_JOINS: list = []   # side streams of fan-outs whose join was left to the caller (deferred_join)
 
 
@@ -353,7 +364,7 @@ def fan_out(discs, y: torch.Tensor, y_hat: torch.Tensor, pair_fn, slot0: int):
     cur = torch.cuda.current_stream(dev)
     outs, streams = [], []
     for i, d in enumerate(discs):
-        s = ops.side_stream(dev, slot0 + i) if PARALLEL_DISCRIMINATORS else cur
+        s = ops.side_stream(dev, slot0 + 20 * STREAM_SET + i) if PARALLEL_DISCRIMINATORS else cur
         if s != cur:
             s.wait_stream(cur)
             streams.append(s)
@@ -397,6 +408,11 @@ class GeometryR:
         return GeometryR(tuple(H), tuple(W), P)
 
 
+def _rfirst_dgrad_pack(w, pkey):
+    return _memo(("dgrad",) + pkey if pkey else None,
+                 lambda: F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64))   # [tap][cout]
+
+
 class _RFirstFn(torch.autograd.Function):
     """Layer 1 (Conv2d(1, 64, (7,5), (2,2), (3,2)) + LeakyReLU) as a GEMM: the 35 taps of every output position are gathered
     into a 64-wide fp16 row (osb_spec_im2col_h16), which is also the operand of the weight gradient."""
@@ -406,6 +422,8 @@ class _RFirstFn(torch.autograd.Function):
         """`spec` only routes the gradient (it may be None when nothing upstream needs one); `xcol` is its tap gather."""
         ctx.pkey = pkey
         rows = xcol.shape[0]
+        if pkey is not None and spec is not None and ctx.needs_input_grad[0]:
+            _rfirst_dgrad_pack(w, pkey)
         if y_pre is not None:
             y = y_pre
         else:
@@ -431,8 +449,7 @@ class _RFirstFn(torch.autograd.Function):
         else:
             g = ops.lrelu_bwd_h16(gy.contiguous(), y, geom.P[1], geom.H[1], ctx.slope)
         if ctx.needs_input_grad[0] and ctx.spec_shape is not None:
-            wd = _memo(("dgrad",) + ctx.pkey if ctx.pkey else None,
-                       lambda: F.pad(w.detach().reshape(64, 35).t(), (0, 0, 0, 29)).to(torch.float16).contiguous().view(1, 64, 64))   # [tap][cout]
+            wd = _rfirst_dgrad_pack(w, ctx.pkey)
             _, col, _ = ops.gemm(g.view(1, rows, 64), wd, epi=ops.EPI_BIAS, flags=ops.FLAG_OUT_H16 | ops.FLAG_NO_F32)
             dspec = ops.spec_col2im(col.view(rows, 64), ctx.spec_shape, geom.H[1], geom.W[1], geom.P[1], 1.0 / GRAD_SCALE)
         return dspec, None, dw, db, None, None, None, None
@@ -460,6 +477,8 @@ class _RConvFn(torch.autograd.Function):
                 pkey=None):
         kh, kw, _sh, sw, ph, pw = layer
         ctx.pkey = pkey
+        if pkey is not None and ctx.needs_input_grad[0]:
+            _memo(("dgrad",) + pkey, lambda: _phase_dgrad_pack(w.detach(), ph))
         if y_pre is not None:
             y = y_pre
         else:

@@ -159,3 +159,59 @@ def test_graph_replay_draws_fresh_dropout_masks(cuda_device):
     assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
     for mk in masks:
         assert abs(float(mk.float().mean()) - (1 - p)) < 0.05
+
+
+def test_gan_step_overlapped_schedule_matches_serial_schedule(cuda_device):
+    """The GAN step runs the eight discriminators on their own streams and queues the discriminator turn next to the
+    generator's backward pass (disc/native.fan_out, BaseModule.OVERLAP_TURNS).  Scheduling must not change the numbers: the
+    gradient every generator / discriminator parameter receives equals that of the fully serial schedule up to the
+    run-to-run noise of one gradient evaluation (fp32 atomics in the weight-gradient kernels, fp16 operands), eagerly after
+    one step and through a captured graph after five."""
+    from optispeech_b200.factory import build_model, model_config_from_spec
+    from optispeech_b200.model import base_module
+    from optispeech_b200.model.vocoder.wavenext.disc import native
+
+    spec = ModelSpec()
+    batch = _batch(spec, 2, 40, 170)
+
+    def run(parallel: bool, graph: bool, steps: int):
+        torch.manual_seed(1234)
+        model = build_model(model_config_from_spec(spec), train_args=dict(pretraining_steps=0))
+        model.generator.load_state_dict(deterministic_state_dict(generator_shapes(spec), seed=0, frames_per_token=3.0))
+        model = model.to(cuda_device).eval()       # eval: no dropout / DropPath draws, the schedules see the same function
+        model.cuda_graph = graph
+        native.PARALLEL_DISCRIMINATORS = parallel
+        base_module.OVERLAP_TURNS = parallel
+        try:
+            for i in range(steps):                 # graph mode: 3 eager warm-ups, the capture, one replay
+                model.training_step(batch, i)
+            torch.cuda.synchronize()
+        finally:
+            native.PARALLEL_DISCRIMINATORS = True
+            base_module.OVERLAP_TURNS = True
+        grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+        losses = (float(model.logged["total_loss/generator"]), float(model.logged["total_loss/discriminator"]))
+        if model._graphed is not None:
+            assert model._graphed.replays >= 1
+            model._graphed.release()
+        return grads, losses
+
+    def rel(a, b):   # gradients carry the loss scale (1024): 1e-3 absolute is 1e-6 of a true gradient (conv_post biases are exact zeros)
+        return float((a - b).norm() / b.norm().clamp_min(1e-3))
+
+    for graph, steps, tol in ((False, 1, 2e-2), (True, 5, 5e-2)):
+        ref, ref_losses = run(False, False, steps)
+        again, _ = run(False, False, steps)          # the serial schedule twice: the noise floor of every parameter's gradient
+        got, losses = run(True, graph, steps)
+        assert np.allclose(losses, ref_losses, rtol=5e-3), (graph, losses, ref_losses)
+        assert set(got) == set(ref) and len(ref) > 150, (len(got), len(ref))
+        worst, worst_noise = ("", 0.0), ("", 0.0)
+        for n, g in ref.items():
+            err, noise = rel(got[n], g), rel(again[n], g)
+            if err > worst[1]:
+                worst = (n, err)
+            if noise > worst_noise[1]:
+                worst_noise = (n, noise)
+            assert err <= max(tol, 4.0 * noise), (graph, n, err, noise)
+        print(f"serial vs overlapped schedule (graph={graph}, {steps} steps): worst relative gradient difference {worst[1]:.2e} ({worst[0]}); "
+              f"serial vs serial: {worst_noise[1]:.2e} ({worst_noise[0]})")
