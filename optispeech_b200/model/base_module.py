@@ -28,6 +28,7 @@ from ..optim import FlatAdamW
 
 OVERLAP_TURNS = True    # GAN phase: the discriminator turn is queued next to the generator's backward pass (see _training_step_eager)
 DISC_TURN_SLOT = 19     # ops.side_stream slot of the discriminator turn
+PREFETCH_REAL = True    # GAN phase: the discriminators' pass over the real signals starts before the generator forward (_process_batch)
 
 
 class _FitLoopState:
@@ -233,26 +234,41 @@ class BaseModule(nn.Module):
         return int(sum(v.numel() * v.element_size() if isinstance(v, torch.Tensor) else v.nbytes
                        for v in batch.values() if isinstance(v, (torch.Tensor, np.ndarray)) and not (isinstance(v, torch.Tensor) and v.is_cuda)))
 
-    def _process_batch(self, batch, vocoder_grad: bool = True):
+    def _process_batch(self, batch, vocoder_grad: bool = True, prefetch_real: bool = False):
+        """Generator forward + ground-truth crop (reference base_lightning_module.py:24-45).  `prefetch_real` (GAN phase): the
+        ground-truth crop depends on the batch alone, so it is cut BEFORE the generator runs and the discriminators' forward
+        pass over the real signals is queued on their streams right away (VocosDiscriminator.prefetch_real) — it then runs next
+        to the generator's forward pass, whose kernels leave most of the machine idle, instead of after it."""
         dev = self.device
         sids, lids = batch.get("sids"), batch.get("lids")
         seg_rand = batch.get("seg_rand")
+        mel_lengths = batch["mel_lengths"].to(dev, non_blocking=True)
+        wav_real = None
+        prefetch_real = prefetch_real and dev.type == "cuda" and PREFETCH_REAL
+        if "wav_segment" in batch:  # host-staged crop (stage_batch)
+            wav_real = batch["wav_segment"].to(dev, non_blocking=True).to(torch.float32)
+        elif prefetch_real:
+            from .. import ops
+            seg_frames = min(int(self.generator.segment_size), int(batch["mel"].shape[-1]))
+            if seg_rand is None:   # the draw the generator would make (generator/training.py), made here and handed over
+                seg_rand = torch.rand([mel_lengths.shape[0]], device=dev) if torch.cuda.is_current_stream_capturing() else torch.rand([mel_lengths.shape[0]])
+            seg_rand = seg_rand.to(dev, non_blocking=True).float()
+            start_idx = ops.segment_starts(seg_rand, mel_lengths, seg_frames, margin=4)
+            wav_real = ops.crop_segments(self._device_wav(batch["wav"]), start_idx, seg_frames * self.hop_length, self.hop_length)
+        if prefetch_real and wav_real is not None:
+            self.discriminator.prefetch_real(wav_real)
         gen_outputs = self.generator(
             x=batch["x"].to(dev, non_blocking=True), x_lengths=batch["x_lengths"].to(dev, non_blocking=True),
-            mel=batch["mel"].to(dev, non_blocking=True), mel_lengths=batch["mel_lengths"].to(dev, non_blocking=True),
+            mel=batch["mel"].to(dev, non_blocking=True), mel_lengths=mel_lengths,
             pitches=batch["pitches"].to(dev, non_blocking=True), energies=batch["energies"].to(dev, non_blocking=True),
             sids=sids.to(dev) if sids is not None else None, lids=lids.to(dev) if lids is not None else None,
             **({"seg_rand": seg_rand.to(dev, non_blocking=True)} if seg_rand is not None else {}),
         )
-        if "wav_segment" in batch:  # host-staged crop (stage_batch)
-            gen_outputs["wav"] = batch["wav_segment"].to(dev, non_blocking=True).type_as(gen_outputs["wav_hat"])
+        if wav_real is not None:
+            gen_outputs["wav"] = wav_real.type_as(gen_outputs["wav_hat"])
             return gen_outputs
         seg = gen_outputs["segment_size"] * self.hop_length
-        wav = batch["wav"]
-        wav = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
-        if wav.dim() == 3:      # (B, 1, Tw) as the reference's collate function hands it over (text_wav_datamodule.py:253-266)
-            wav = wav[:, 0]
-        wav = wav.to(dev, non_blocking=True).to(torch.float32).contiguous()
+        wav = self._device_wav(batch["wav"])
         from .. import ops
         # ground-truth crop wav[b, start*hop : start*hop + seg], zero-filled past the end like get_segments_numpy's pre-zeroed
         # array (utils/segments.py:63-72) and the host path (stage_batch).  start_idx is produced by the decoder / vocoder branch:
@@ -267,6 +283,12 @@ class BaseModule(nn.Module):
         else:
             gen_outputs["wav"] = ops.crop_segments(wav, gen_outputs["start_idx"], seg, self.hop_length).type_as(gen_outputs["wav_hat"])
         return gen_outputs
+
+    def _device_wav(self, wav):
+        wav = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
+        if wav.dim() == 3:      # (B, 1, Tw) as the reference's collate function hands it over (text_wav_datamodule.py:253-266)
+            wav = wav[:, 0]
+        return wav.to(self.device, non_blocking=True).to(torch.float32).contiguous()
 
     def configure_optimizers(self):
         gen_params = [{"params": list(self.generator.parameters())}]
@@ -389,7 +411,7 @@ class BaseModule(nn.Module):
     def training_step_g(self, batch, train_discriminator):
         log_outputs = {}
         if train_discriminator:
-            gen_outputs = self._process_batch(batch)
+            gen_outputs = self._process_batch(batch, prefetch_real=True)
         else:
             # pre-training: the vocoder output feeds no loss, so its autograd graph is not built and its stream is only joined
             # at the end of the step (the decoder / vocoder forward overlaps the backward pass)

@@ -32,6 +32,19 @@ class VocosDiscriminator(BaseVocoderDiscriminator):
         import contextlib
         return contextlib.nullcontext()
 
+    def prefetch_real(self, wav):
+        """Queues every discriminator's forward pass over the real signals on the discriminator's stream, without joining:
+        `forward_gen` on the same `wav` tensor picks the results up (native._pair).  Called before the generator forward."""
+        if not wav.is_cuda:
+            return
+        from . import native
+        native.reset_pack_memo()
+        native.MEMO_IS_FRESH = True
+        native.prefetch_real(self.multiperioddisc.discriminators, wav, native.period_forward, native.effective_weights,
+                             native.DISC_STREAM_SLOT0)
+        native.prefetch_real(self.multiresddisc.discriminators, wav, native.resolution_forward, native._resolution_weights,
+                             native.DISC_STREAM_SLOT0 + 8)
+
     # Log dictionaries hold device scalars (detached); the reference calls .item() on every term (one host sync each).
     def forward_disc(self, wav, wav_hat):
         with self._all_discriminators(wav):
@@ -47,7 +60,9 @@ class VocosDiscriminator(BaseVocoderDiscriminator):
     def forward_gen(self, wav, wav_hat):
         if wav.is_cuda:   # weight packs are shared between this turn and the discriminator turn of the same step only
             from . import native
-            native.reset_pack_memo()
+            if not native.MEMO_IS_FRESH:     # prefetch_real of this step already emptied it (and left this step's packs in it)
+                native.reset_pack_memo()
+            native.MEMO_IS_FRESH = False
         with self._all_discriminators(wav):
             _, gen_mp, fr_mp, fg_mp = self.multiperioddisc(y=wav, y_hat=wav_hat)
             _, gen_mrd, fr_mrd, fg_mrd = self.multiresddisc(y=wav, y_hat=wav_hat)

@@ -36,6 +36,7 @@ C1_PAD = 64          # layer 1 has 32 channels; its output is stored 64 wide (on
 # FlatAdamW bumps `_osb_epoch`); emptied at the start of every generator turn (VocosDiscriminator.forward_gen), so an entry never
 # outlives a step — inside a captured step the pack kernels of the generator turn are part of the graph and replayed with it.
 _PACK_MEMO = {}
+MEMO_IS_FRESH = False   # set by VocosDiscriminator.prefetch_real: the memo was emptied for this step already
 
 
 def reset_pack_memo() -> None:
@@ -295,6 +296,26 @@ def _reuse_key(disc, y, y_hat):
             tuple((p._version, getattr(p, "_osb_epoch", 0)) for p in disc.parameters()))
 
 
+def _real_key(disc, y):
+    return (y.data_ptr(), y._version, tuple(y.shape), tuple((p._version, getattr(p, "_osb_epoch", 0)) for p in disc.parameters()))
+
+
+def prefetch_real(discs, y: torch.Tensor, forward, weights_of, slot0: int) -> None:
+    """Generator turn, early: the real signals' forward pass (no graph, frozen weights) of every discriminator, queued on the
+    discriminator's stream behind whatever produced `y` and NOT joined — the generator-turn call of `_pair` for the same
+    `y` and the same weights, which runs on the same stream, takes the results instead of recomputing them."""
+    dev = y.device
+    cur = torch.cuda.current_stream(dev)
+    for i, d in enumerate(discs):
+        s = ops.side_stream(dev, slot0 + i) if PARALLEL_DISCRIMINATORS else cur
+        if s != cur:
+            s.wait_stream(cur)
+        with torch.cuda.stream(s), torch.no_grad():
+            rec = []
+            sr, fr = forward(d, y, weights_of(d), record=rec)
+            d.__dict__["_real_prefetch"] = (_real_key(d, y), sr, fr, rec)
+
+
 def _pair(disc, y, y_hat, forward, weights, detach):
     """(score_real, score_fake, fmap_real, fmap_fake) of one discriminator.
 
@@ -306,10 +327,14 @@ def _pair(disc, y, y_hat, forward, weights, detach):
     discriminator turn only builds its autograd graph around them — one of the step's three discriminator forwards is not
     recomputed.  The reference recomputes it; the values are identical."""
     gen_turn = torch.is_grad_enabled() and y_hat.requires_grad
+    ahead = disc.__dict__.pop("_real_prefetch", None)
     if gen_turn:
         rec_r, rec_g = [], []
-        with torch.no_grad():
-            sr, fr = forward(disc, y, detach(weights), record=rec_r)
+        if ahead is not None and ahead[0] == _real_key(disc, y):
+            _, sr, fr, rec_r = ahead
+        else:
+            with torch.no_grad():
+                sr, fr = forward(disc, y, detach(weights), record=rec_r)
         sg, fg = forward(disc, y_hat, weights, record=rec_g)
         if REUSE_GENERATOR_TURN:
             disc.__dict__["_turn_cache"] = (_reuse_key(disc, y, y_hat), rec_r, rec_g)

@@ -163,7 +163,8 @@ def test_graph_replay_draws_fresh_dropout_masks(cuda_device):
 
 def test_gan_step_overlapped_schedule_matches_serial_schedule(cuda_device):
     """The GAN step runs the eight discriminators on their own streams and queues the discriminator turn next to the
-    generator's backward pass (disc/native.fan_out, BaseModule.OVERLAP_TURNS).  Scheduling must not change the numbers: the
+    generator's backward pass (disc/native.fan_out, BaseModule.OVERLAP_TURNS), and the real signals' discriminator pass starts
+    before the generator forward (PREFETCH_REAL).  Scheduling must not change the numbers: the
     gradient every generator / discriminator parameter receives equals that of the fully serial schedule up to the
     run-to-run noise of one gradient evaluation (fp32 atomics in the weight-gradient kernels, fp16 operands), eagerly after
     one step and through a captured graph after five."""
@@ -182,6 +183,7 @@ def test_gan_step_overlapped_schedule_matches_serial_schedule(cuda_device):
         model.cuda_graph = graph
         native.PARALLEL_DISCRIMINATORS = parallel
         base_module.OVERLAP_TURNS = parallel
+        base_module.PREFETCH_REAL = parallel
         try:
             for i in range(steps):                 # graph mode: 3 eager warm-ups, the capture, one replay
                 model.training_step(batch, i)
@@ -189,6 +191,7 @@ def test_gan_step_overlapped_schedule_matches_serial_schedule(cuda_device):
         finally:
             native.PARALLEL_DISCRIMINATORS = True
             base_module.OVERLAP_TURNS = True
+            base_module.PREFETCH_REAL = True
         grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
         losses = (float(model.logged["total_loss/generator"]), float(model.logged["total_loss/discriminator"]))
         if model._graphed is not None:
@@ -196,8 +199,9 @@ def test_gan_step_overlapped_schedule_matches_serial_schedule(cuda_device):
             model._graphed.release()
         return grads, losses
 
-    def rel(a, b):   # gradients carry the loss scale (1024): 1e-3 absolute is 1e-6 of a true gradient (conv_post biases are exact zeros)
-        return float((a - b).norm() / b.norm().clamp_min(1e-3))
+    def rel(a, b):   # gradients carry the loss scale (1024): 1e-2 absolute is 1e-5 of a true gradient (the conv_post bias
+        # gradients of the discriminator turn are exact cancellations: -1/N per real score, +1/N per generated one)
+        return float((a - b).norm() / b.norm().clamp_min(1e-2))
 
     for graph, steps, tol in ((False, 1, 2e-2), (True, 5, 5e-2)):
         ref, ref_losses = run(False, False, steps)
