@@ -371,10 +371,9 @@ predictor_ln_bwd_kernel(const float* __restrict__ d_out, const __half* __restric
         float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);  // dropout mask (with 1/keep) of the forward pass
         if (drop_p > 0.f) {
           const unsigned long long base = static_cast<unsigned long long>(row) * C + v * 128 + lane * 4;
-          mk.x = dropout_scale(drop_seed, base + 0, drop_p, drop_inv_keep);
-          mk.y = dropout_scale(drop_seed, base + 1, drop_p, drop_inv_keep);
-          mk.z = dropout_scale(drop_seed, base + 2, drop_p, drop_inv_keep);
-          mk.w = dropout_scale(drop_seed, base + 3, drop_p, drop_inv_keep);
+          float m4[4] = {1.f, 1.f, 1.f, 1.f};
+          dropout_apply(m4, drop_seed, base, drop_p, drop_inv_keep);
+          mk = make_float4(m4[0], m4[1], m4[2], m4[3]);
         }
         g[v] = make_float4(d * li[v].x * mk.x, d * li[v].y * mk.y, d * li[v].z * mk.z, d * li[v].w * mk.w);
         a_lin[v].x = fmaf(d * mk.x, fmaf(xh[v].x, lw[v].x, lb[v].x), a_lin[v].x);

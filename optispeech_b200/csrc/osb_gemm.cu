@@ -507,8 +507,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       ld_chunk(taddr, c0, v);
       ld_h16x32(rrow + c0, r);
       if (p.drop_p > 0.f) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+        dropout_apply(v, drop_seed, dbase + c0, p.drop_p, p.drop_inv_keep);
       }
       if (p.flags & OSB_FLAG_OUT_H16) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + c0, p.ldo, nrows, v);
       float lw[32];
@@ -525,8 +524,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       ld_chunk(taddr, c0, v);
       ld_h16x32(rrow + c0, r);
       if (p.drop_p > 0.f) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + c0 + i, p.drop_p, p.drop_inv_keep);
+        dropout_apply(v, drop_seed, dbase + c0, p.drop_p, p.drop_inv_keep);
       }
       float lw[32];
       ld_f32x32(sv1 + c0, lw);
@@ -574,16 +572,14 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         if (p.drop_p > 0.f) {  // Dropout after the ReLU (MultiLayeredConv1d, multi_layer_conv.py:60-62)
           const unsigned long long dbase = static_cast<unsigned long long>(row) * p.N + n;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
+          dropout_apply(v, drop_seed, dbase, p.drop_p, p.drop_inv_keep);
         }
         warp_store_h(p, sl, p.out, row0, n, nrows, v);
       } else {  // RESID
         if (p.flags & OSB_FLAG_SAVE_PRE) warp_store_h16(sl, static_cast<__half*>(p.aux) + row0 * p.ldo + n, p.ldo, nrows, v);
         if (p.drop_p > 0.f) {  // element dropout on the branch before the residual add (EncoderLayer, encoder_layer.py:103,111)
           const unsigned long long dbase = static_cast<unsigned long long>(row) * p.N + n;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, dbase + i, p.drop_p, p.drop_inv_keep);
+          dropout_apply(v, drop_seed, dbase, p.drop_p, p.drop_inv_keep);
         }
         float r[32];
         if constexpr (kTileF32) ld_f32x32(tile32 + lane * TLD32 + c0, r);
@@ -673,8 +669,7 @@ __device__ __forceinline__ void run_epilogue(const GemmKParams& p, uint32_t tadd
       }
       if (kRelu && p.drop_p > 0.f) {
         const unsigned long long base = static_cast<unsigned long long>(valid ? row : 0) * BN + c0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(drop_seed, base + i, p.drop_p, p.drop_inv_keep);
+        dropout_apply(v, drop_seed, base, p.drop_p, p.drop_inv_keep);
       }
       if (p.flags & OSB_FLAG_DOT) {
         float dw[32];
@@ -1179,6 +1174,15 @@ extern "C" int osb_gemm(const osb_gemm_desc* d, void* stream_) {
   if (!attn && !full_row && bn == 256 && g_gemm_narrow_tiles) {
     const long long tiles = static_cast<long long>(d->B) * ((d->T + BM - 1) / BM) * (d->N / 256);
     if (tiles * 2 <= 148) bn = 128;
+  }
+  // Split-precision launches (the synthesis path: one stream, nothing to take SMs from) with few tiles: 64-wide tiles.  A
+  // B=1 utterance is 1-2 row tiles, so a 256-wide tile leaves ONE or two SMs pulling the whole hi + lo weight matrix through
+  // their ~64 B/clk L2 port (1 MB for a 256 x 1024 pwconv2: 8 us before the first epilogue); 64-wide tiles spread the
+  // weight rows over 4x the SMs (the A tile is re-read per column tile, from L2).
+  if (!attn && !full_row && (d->flags & OSB_FLAG_SPLIT_IN) && !w_mn && d->N % 64 == 0 && bn > 64) {
+    const long long tiles = static_cast<long long>(d->B) * ((d->T + BM - 1) / BM) * (d->N / bn);
+    if (tiles * 4 <= 148) bn = 64;
+    else if (tiles * 2 <= 148 && d->N % 128 == 0 && bn > 128) bn = 128;
   }
   OSB_REQUIRE(bn > 0 && bn <= 512, OSB_ERR_SHAPE);
   const int ninst = bn <= 256 ? bn : bn / 2;

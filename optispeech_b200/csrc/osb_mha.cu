@@ -270,10 +270,7 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           v[i] = (kc + i < kv) ? e : 0.f;
           l += v[i];
         }
-        if (p.drop_p > 0.f) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= dropout_scale(seed, drow + kc + i, p.drop_p, p.drop_inv_keep);
-        }
+        if (p.drop_p > 0.f) dropout_apply(v, seed, drow + kc, p.drop_p, p.drop_inv_keep);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4)
           *reinterpret_cast<uint4*>(prow + (cc >> 1) * MH_KB + sw128(row, (cc & 1) * 4 + c4)) = pack8(v + c4 * 8);

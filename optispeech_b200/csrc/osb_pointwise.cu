@@ -102,12 +102,16 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w /*(C,7
 #pragma unroll
   for (int j = 0; j < 6; ++j) load_row(t_begin + j - 3, win[j + 1]);
 
+  float4 nxt[VPL];   // row t + 3 of the coming iteration, requested one iteration ahead (its latency hides behind the FMAs)
+  load_row(t_begin + 3, nxt);
   for (int t = t_begin; t < t_end; ++t) {
 #pragma unroll
     for (int j = 0; j < 6; ++j)
 #pragma unroll
       for (int v = 0; v < VPL; ++v) win[j][v] = win[j + 1][v];
-    load_row(t + 3, win[6]);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) win[6][v] = nxt[v];
+    if (t + 1 < t_end) load_row(t + 4, nxt);
 
     float4 d[VPL];
     float s = 0.f;
@@ -563,7 +567,10 @@ extern "C" int osb_dwconv_ln(const float* x, const float* w, const float* bias, 
                              int32_t C, float eps, int32_t split, void* stream) {
   OSB_REQUIRE(x && w && bias && xhat_h16, OSB_ERR_ARG);
   OSB_REQUIRE(B > 0 && T > 0 && (C == 256 || C == 384 || C == 128 || C == 512), OSB_ERR_SHAPE);
-  const int ppw = T >= 64 ? 16 : 8;
+  // positions per warp: long runs re-use the 7-row window (1.4x reads at 16), short runs fill the machine when there are few
+  // positions (a B=1 utterance: 243 frames = 16 warps at 16 positions each, 13 us of serial row latency; 243 warps at 1)
+  int ppw = 16;
+  while (ppw > 1 && static_cast<long long>(B) * ((T + ppw - 1) / ppw) < 148LL * WARPS_PER_BLOCK * 2) ppw >>= 1;
   const int groups = B * ((T + ppw - 1) / ppw);
   const int blocks = (groups + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -149,15 +149,26 @@ class PitchPredictor(nn.Module):
         return ops.variance_embed(x.contiguous(), values.contiguous(), conv.weight.view(self.dim, -1), conv.bias, mask_u8,
                                   f32=True, h16=want_h16, split=split)
 
-    def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor, side_stream=None):
+    def predict_ahead(self, x: torch.Tensor, padding_mask: torch.Tensor, side_stream):
+        """The prediction stack alone, queued on `side_stream` forked from the current stream NOW.  The stack reads `x` only,
+        not the targets, so the training forward calls this as soon as `x` exists — before the alignment search that produces
+        the targets — and hands the result to forward(preds=...); the CALLER joins the stream before using it."""
+        side_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side_stream):
+            return self.predictor(x, padding_mask)
+
+    def forward(self, x: torch.Tensor, padding_mask: torch.Tensor, target: torch.Tensor, side_stream=None, preds=None):
         """Teacher-forced: returns (x + embed(target), preds) (reference core.py:152-166), eval-mode numerics.
         The prediction only meets the rest of the step at the loss (the embedding is driven by `target`), so with
-        `side_stream` it is enqueued there, forked from the current stream; the CALLER joins (`wait_stream`) before using it."""
+        `side_stream` it is enqueued there, forked from the current stream; the CALLER joins (`wait_stream`) before using it.
+        `preds`: the prediction computed earlier by predict_ahead() on the same `x`."""
         mask_u8 = _as_u8(padding_mask)
         if torch.is_grad_enabled():
             from ....autograd import VarianceEmbedFn
 
-            if side_stream is not None and x.is_cuda:
+            if preds is not None:
+                pass
+            elif side_stream is not None and x.is_cuda:
                 side_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side_stream):
                     preds = self.predictor(x, padding_mask)

@@ -135,6 +135,9 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
         return _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand)
 
 
+PITCH_AHEAD = True
+
+
 def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
     dev = x.device
     _require_cuda(x, "OptiSpeechGenerator.forward")
@@ -161,6 +164,10 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     s_dur.wait_stream(main)
     with torch.cuda.stream(s_dur):
         duration_hat = gen.duration_predictor(h.detach(), in_pad)   # detached input: meets the rest only at the loss
+    # the pitch prediction stack (5 convolutions) reads the encoder output only: forked here, it runs under the alignment
+    # search instead of behind it (the pitch EMBEDDING below needs the search's averaged targets, the prediction does not)
+    s_pitch = ops.side_stream(dev, 3)
+    pitch_hat = gen.pitch_predictor.predict_ahead(h, in_pad, s_pitch) if PITCH_AHEAD else None
     # text-side alignment convs + attention on their own stream: in the backward pass (autograd replays a node on its forward
     # stream) the attention gradient chain then runs next to the predictors' instead of queueing behind them on the main stream
     s_attn = ops.side_stream(dev, ops.ATTN_SLOT)
@@ -182,9 +189,8 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     e_avg = average_by_duration(durations, energies, x_lengths, mel_lengths)
 
     # teacher forcing: the embeddings are driven by the targets, the predictions only feed the loss -> side streams
-    s_pitch = ops.side_stream(dev, 3)
     s_energy = ops.side_stream(dev, 4)
-    h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg, side_stream=s_pitch)
+    h, pitch_hat = gen.pitch_predictor(h, in_pad, p_avg, side_stream=s_pitch, preds=pitch_hat)
     h, energy_hat = gen.energy_predictor(h, in_pad, e_avg, side_stream=s_energy)
 
     # Upsampler, decoder and vocoder input carry no gradient in the reference (the vocoder is fed segment.detach(),
