@@ -203,6 +203,14 @@ int osb_dwconv_ln(const float* x, const float* w /*(C,7)*/, const float* bias, v
 int osb_layernorm(const float* x, const float* w, const float* b, float* out_f32, void* out_h16, int64_t rows, int32_t C,
                   float eps, int32_t split, void* stream);
 
+/* y = LayerNorm(relu(x)) * w + b per row -> fp16 (plain / split rows [hi C | lo C]) and / or out_dot[row] =
+ * pad_mask[row] ? 0 : y . dot_w + dot_b[0].  The stand-alone form of OSB_EPI_RELU_LN (+ OSB_FLAG_DOT): a VariancePredictor
+ * layer's ReLU -> LayerNorm (-> Linear(C,1) -> masked_fill) (modules/core.py:73-96) behind a plain-bias osb_gemm in narrow
+ * tiles, used when the problem is a few row tiles (synthesis of one utterance).  x already holds conv + bias. */
+int osb_relu_layernorm(const float* x, const float* w, const float* b, void* out_h16 /* or NULL */, int64_t rows, int32_t C, float eps,
+                       int32_t split, const float* dot_w /* or NULL */, const float* dot_b /* or NULL */,
+                       const uint8_t* pad_mask /* (rows) or NULL */, float* out_dot /* (rows) or NULL */, void* stream);
+
 /* out = (x + emb_scale * (bias + Conv1d(1->C, k, same)(val))) * (1 - pad_mask); emb_scale (B,T,C) is the optional
  * dropout mask/(1-p) of the embedding branch (NULL = 1).  Replaces PitchPredictor.forward/infer's embed + add + mask
  * (modules/core.py:143-176). */

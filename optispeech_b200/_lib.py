@@ -106,6 +106,7 @@ def load() -> C.CDLL:
         "osb_embed_text": [P, P, P, P, P, I32, I32, I32, I32, P],
         "osb_dwconv_ln": [P, P, P, P, P, I32, I32, I32, F, I32, P],
         "osb_layernorm": [P, P, P, P, P, I64, I32, F, I32, P],
+        "osb_relu_layernorm": [P, P, P, P, I64, I32, F, I32, P, P, P, P, P],
         "osb_variance_embed": [P, P, P, P, P, P, P, P, I32, I32, I32, I32, I32, P],
         "osb_durations": [P, P, P, P, I32, I32, F, F, P],
         "osb_centres": [P, I32, P, P, I32, I32, P],

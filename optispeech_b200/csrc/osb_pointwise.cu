@@ -188,6 +188,59 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 }
 
 // ------------------------------------------------------------------------------------------
+// y = LayerNorm(relu(x)) * w + b over the last dim (one warp per row) -> fp16 (plain or split) and / or the masked
+// Linear(C -> 1) of a VariancePredictor's tail.  The stand-alone form of osb_gemm's RELU_LN epilogue, for problems of a few
+// row tiles where that epilogue forces ONE CTA per 128 rows to stream the whole weight matrix (see osb_relu_layernorm).
+// ------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+relu_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, __half* __restrict__ out_h16,
+                      long long rows, float eps, int split, const float* __restrict__ dot_w, const float* __restrict__ dot_b,
+                      const uint8_t* __restrict__ pad_mask, float* __restrict__ out_dot) {
+  constexpr int C = 128 * VPL;
+  const long long row = static_cast<long long>(blockIdx.x) * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 d[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    d[v] = *reinterpret_cast<const float4*>(x + row * C + v * 128 + lane * 4);
+    d[v].x = fmaxf(d[v].x, 0.f); d[v].y = fmaxf(d[v].y, 0.f); d[v].z = fmaxf(d[v].z, 0.f); d[v].w = fmaxf(d[v].w, 0.f);
+    s += (d[v].x + d[v].y) + (d[v].z + d[v].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    d[v].x -= mean; d[v].y -= mean; d[v].z -= mean; d[v].w -= mean;
+    q += (d[v].x * d[v].x + d[v].y * d[v].y) + (d[v].z * d[v].z + d[v].w * d[v].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  float dot = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int c = v * 128 + lane * 4;
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    float4 y;
+    y.x = d[v].x * rstd * ww.x + bb.x;
+    y.y = d[v].y * rstd * ww.y + bb.y;
+    y.z = d[v].z * rstd * ww.z + bb.z;
+    y.w = d[v].w * rstd * ww.w + bb.w;
+    if (out_h16 != nullptr) store_h4_row(out_h16, row, C, c, split, y.x, y.y, y.z, y.w);
+    if (dot_w != nullptr) {
+      const float4 dw = *reinterpret_cast<const float4*>(dot_w + c);
+      dot += (y.x * dw.x + y.y * dw.y) + (y.z * dw.z + y.w * dw.w);
+    }
+  }
+  if (out_dot != nullptr) {
+    dot = warp_sum(dot);
+    if (lane == 0) out_dot[row] = (pad_mask != nullptr && pad_mask[row]) ? 0.f : dot + (dot_b != nullptr ? dot_b[0] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // variance embedding: out = (x + bias + conv1d(val; 1->C, k taps, same)) * keep
 // ------------------------------------------------------------------------------------------
 __global__ void variance_embed_kernel(const float* __restrict__ x, const float* __restrict__ val, const float* __restrict__ w /*(C,k)*/,
@@ -597,6 +650,25 @@ extern "C" int osb_layernorm(const float* x, const float* w, const float* b, flo
     case 2: layernorm_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
     case 3: layernorm_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
     case 4: layernorm_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, out_f32, oh, rows, eps, split); break;
+  }
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_relu_layernorm(const float* x, const float* w, const float* b, void* out_h16, int64_t rows, int32_t C, float eps,
+                                  int32_t split, const float* dot_w, const float* dot_b, const uint8_t* pad_mask, float* out_dot,
+                                  void* stream) {
+  OSB_REQUIRE(x && w && b && (out_h16 || out_dot), OSB_ERR_ARG);
+  OSB_REQUIRE(out_dot == nullptr || dot_w != nullptr, OSB_ERR_ARG);
+  OSB_REQUIRE(rows > 0 && (C == 128 || C == 256 || C == 384 || C == 512), OSB_ERR_SHAPE);
+  const unsigned blocks = static_cast<unsigned>((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  __half* oh = static_cast<__half*>(out_h16);
+  switch (C / 128) {
+    case 1: relu_layernorm_kernel<1><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, oh, rows, eps, split, dot_w, dot_b, pad_mask, out_dot); break;
+    case 2: relu_layernorm_kernel<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, oh, rows, eps, split, dot_w, dot_b, pad_mask, out_dot); break;
+    case 3: relu_layernorm_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, oh, rows, eps, split, dot_w, dot_b, pad_mask, out_dot); break;
+    case 4: relu_layernorm_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(x, w, b, oh, rows, eps, split, dot_w, dot_b, pad_mask, out_dot); break;
   }
   count_launch();
   return launch_status();

@@ -101,13 +101,29 @@ class OptiSpeechGenerator(nn.Module):
         if sids is not None or lids is not None:
             h = self._speaker_language(h, sids, lids).contiguous()
             h16 = ops.to_h16(h, split=split)
-        d_pred, y_lengths = self.duration_predictor.infer(h, in_pad, factor=d_factor, x_h16=h16)
+        # the duration stack reads the encoder output only: on a side stream next to the pitch / energy stacks (in a captured
+        # stage the fork and join are graph edges).  A B=1 utterance is ONE 128-row tile per predictor layer.
+        main = torch.cuda.current_stream(dev)
+        side = ops.side_stream(dev, 2)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            d_pred, y_lengths = self.duration_predictor.infer(h, in_pad, factor=d_factor, x_h16=h16)
+            # the output length is the one value the host has to read before it can size the next stage: it leaves through
+            # page-locked memory as part of this stage (no separate reduction launch + blocking read behind it)
+            y_max_pin = self._y_max_pin(dev)
+            y_max_pin.copy_(y_lengths.max().reshape(1), non_blocking=True)
         h, pitch, h16 = self.pitch_predictor.infer(h, in_pad, p_factor, x_h16=h16, want_h16=True)
         if self.energy_predictor is not None:
             h, energy = self.energy_predictor.infer(h, in_pad, e_factor, x_h16=h16)
         else:
             energy = None
-        return {"h": h, "d_pred": d_pred, "y_lengths": y_lengths, "pitch": pitch, "energy": energy, "x_mask": x_mask}
+        main.wait_stream(side)
+        return {"h": h, "d_pred": d_pred, "y_lengths": y_lengths, "pitch": pitch, "energy": energy, "x_mask": x_mask,
+                "y_max_pin": y_max_pin}
+
+    def _y_max_pin(self, dev) -> torch.Tensor:
+        """A page-locked int64 scalar per call site of stage A (a captured stage keeps writing to the one it was captured with)."""
+        return torch.zeros(1, dtype=torch.int64, pin_memory=True)
 
     def _synth_stage_b(self, h, durations, x_mask, x_lengths, y_lengths, y_max_length: int):
         split = precision.use_split(False)
@@ -123,7 +139,12 @@ class OptiSpeechGenerator(nn.Module):
         return {"wav": wav, "f0_cond": f0_cond}
 
     def _weights_token(self) -> int:
-        return sum(p._version for p in self.parameters())
+        """Changes whenever a parameter is modified in place (optimizer step, load_state_dict).  The parameter list is cached:
+        walking the module tree costs ~0.2 ms per call, more than a B=1 stage."""
+        ps = self.__dict__.get("_synth_params")
+        if ps is None:
+            ps = self.__dict__["_synth_params"] = list(self.parameters())
+        return sum([p._version for p in ps])
 
     def _graphed_stage(self, key, fn, inputs):
         """Run `fn(**inputs)` through the graph cache: eager the first time a key is seen, captured the second time, replayed
@@ -138,7 +159,11 @@ class OptiSpeechGenerator(nn.Module):
                 return fn(**inputs)
             if cache["seen"][key] == "eager":     # a capture of this shape failed before: stay on the launch path
                 return fn(**inputs)
-            static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in inputs.items()}
+            # an input that IS the output of an earlier captured stage (fixed address, rewritten by that stage's replay) is
+            # read in place; everything else gets a static copy that is refreshed before each replay
+            stable = cache.setdefault("stable", set())
+            static = {k: (v if (isinstance(v, torch.Tensor) and v.data_ptr() in stable) else (v.clone() if isinstance(v, torch.Tensor) else v))
+                      for k, v in inputs.items()}
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -156,9 +181,12 @@ class OptiSpeechGenerator(nn.Module):
             while len(cache["graphs"]) >= self._SYNTH_MAX_GRAPHS:
                 cache["graphs"].pop(next(iter(cache["graphs"])))
             cache["graphs"][key] = entry
+            for t in out.values():
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    stable.add(t.data_ptr())
         graph, static, out = entry
         for k, v in inputs.items():
-            if isinstance(v, torch.Tensor):
+            if isinstance(v, torch.Tensor) and static[k].data_ptr() != v.data_ptr():
                 static[k].copy_(v, non_blocking=True)
         graph.replay()
         return out
@@ -177,7 +205,7 @@ class OptiSpeechGenerator(nn.Module):
             cache = self.__dict__.setdefault("_synth_cache", {"token": None, "seen": {}, "graphs": {}})
             token = self._weights_token()
             if cache["token"] != token:
-                cache.update(token=token, seen={}, graphs={})
+                cache.update(token=token, seen={}, graphs={}, stable=set())
         a_in = dict(x=x, x_lengths=x_lengths, sids=sids, lids=lids, d_factor=float(d_factor), p_factor=float(p_factor), e_factor=float(e_factor))
         if use_graphs:
             key_a = ("A", tuple(x.shape), sids is not None, lids is not None, float(d_factor), float(p_factor), float(e_factor))
@@ -186,10 +214,19 @@ class OptiSpeechGenerator(nn.Module):
             a = self._synth_stage_a(**a_in)
         if durations is None:
             durations, y_lengths = a["d_pred"], a["y_lengths"]
+            torch.cuda.current_stream(dev).synchronize()    # the one unavoidable device->host read: output length
+            y_max_length = int(a["y_max_pin"])
+        elif not durations.is_cuda:
+            # durations handed over in host memory: the lengths are host arithmetic, nothing waits for the device
+            durations = durations.to(torch.int64).contiguous()
+            y_lengths_host = durations.sum(dim=1)
+            y_max_length = int(y_lengths_host.max())
+            durations = durations.to(dev, non_blocking=True)
+            y_lengths = y_lengths_host.to(dev, non_blocking=True)
         else:
-            durations = durations.to(dev).to(torch.int64).contiguous()
+            durations = durations.to(torch.int64).contiguous()
             y_lengths = durations.sum(dim=1)
-        y_max_length = int(y_lengths.max().item())  # the one unavoidable device->host read: output length
+            y_max_length = int(y_lengths.max().item())
         if y_max_length == 0:
             # reference alignments.py:152-157: all-zero durations are patched to one frame per row
             durations = GaussianUpsampling.patch_all_zero(durations.clone())

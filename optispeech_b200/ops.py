@@ -194,6 +194,17 @@ def layernorm(x, w, b, eps: float, f32: bool = True, h16: bool = False, split: b
     return o32, o16
 
 
+def relu_layernorm(x, w, b, eps: float, h16: bool = True, split: bool = False, dot_w=None, dot_b=None, pad_mask=None):
+    """LayerNorm(relu(x)) * w + b per row -> (fp16 (…, C) or split (…, 2C) or None, fp32 (rows-shaped) masked dot or None)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    o16 = _h16_like(x, split) if h16 else None
+    od = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32) if dot_w is not None else None
+    _lib.check(_lib.load().osb_relu_layernorm(_ptr(_f32(x)), _ptr(_f32(w)), _ptr(_f32(b)), _ptr(o16), rows, Cc, eps, int(split),
+                                              _ptr(dot_w), _ptr(dot_b), _ptr(pad_mask), _ptr(od), _stream()), "osb_relu_layernorm")
+    return o16, od
+
+
 def variance_embed(x, val, w, bias, pad_mask, f32: bool = True, h16: bool = False, split: bool = False, emb_scale=None):
     B, T, Cc = x.shape
     k = w.shape[-1]
