@@ -54,6 +54,9 @@ class TextEmbedding(nn.Module):
         return x, None
 
 
+NARROW_PREDICTOR_MAX_TILES = 37   # row tiles up to which a predictor layer runs as narrow-tile GEMM + row kernel (forward_h16)
+
+
 class VariancePredictor(nn.Module):
     def __init__(self, dim: int, num_layers: int, intermediate_dim: int, kernel_size: int, dropout: float = 0.1,
                  conv_layer_class: type = torch.nn.Conv1d):
@@ -87,7 +90,7 @@ class VariancePredictor(nn.Module):
         h = x_h16
         n = len(self.conv)
         B, T = x_h16.shape[0], x_h16.shape[1]
-        if split and B * ((T + 127) // 128) * 4 <= 148:
+        if split and B * ((T + 127) // 128) <= NARROW_PREDICTOR_MAX_TILES:
             # A few row tiles (synthesis of one or a few utterances): the fused ReLU + LayerNorm epilogue needs whole rows, i.e.
             # ONE CTA per 128 rows streams the layer's whole hi + lo weight matrix through one SM's L2 port (33 us per layer at
             # B=1).  A plain-bias GEMM in 64-wide tiles spreads the weight rows over 4-6x the SMs and a row kernel does

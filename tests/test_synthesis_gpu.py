@@ -130,3 +130,44 @@ def test_fused_convnext_block_kernel(cuda_device, C, I, T):
     err_3 = (three.cpu() - ref).abs().max().item()
     print(f"  C={C} T={T}: fused(fp16) max-abs err {err_f:.3e}; three-kernel fp16x3 {err_3:.3e}")
     assert err_f <= 5e-3 and err_3 <= 1e-4
+
+
+def test_predictor_small_problem_path_equals_fused_epilogue(setup, cuda_device):
+    """A predictor layer of a few row tiles runs as a narrow-tile bias GEMM + osb_relu_layernorm (modules/core.py
+    forward_h16), larger problems through the fused ReLU + LayerNorm (+ Linear) epilogue of osb_gemm.  Same arithmetic: the
+    two paths agree to fp32 rounding on the same split-precision input, and the row kernel matches torch's
+    layer_norm(relu(x)) and the masked dot product."""
+    from optispeech_b200 import ops
+    from optispeech_b200.model.generator.modules import core
+
+    spec, sd, gen = setup
+    g = torch.Generator().manual_seed(5)
+    B, T, C = 3, 150, 256
+    x = torch.randn(B, T, C, generator=g).to(cuda_device)
+    pad = (torch.arange(T)[None] >= torch.tensor([150, 97, 140])[:, None]).to(cuda_device)
+    mask_u8 = pad.to(torch.uint8).contiguous()
+    x16 = ops.to_h16(x.contiguous(), split=True)
+    for pred in (gen.duration_predictor, gen.pitch_predictor.predictor, gen.energy_predictor.predictor):
+        with torch.inference_mode():
+            small = pred.forward_h16(x16, mask_u8, True)
+            keep, core.NARROW_PREDICTOR_MAX_TILES = core.NARROW_PREDICTOR_MAX_TILES, 0
+            try:
+                fused = pred.forward_h16(x16, mask_u8, True)
+            finally:
+                core.NARROW_PREDICTOR_MAX_TILES = keep
+        assert small.shape == fused.shape == (B, T)
+        assert torch.equal(small[pad], torch.zeros_like(small[pad]))
+        err = (small - fused).abs().max().item()
+        print(f"{type(pred).__name__}: small-problem path vs fused epilogue, max-abs diff {err:.2e} (|out| max {fused.abs().max().item():.2f})")
+        assert err <= 2e-5 * max(1.0, fused.abs().max().item())
+
+    # the row kernel alone against torch
+    z = torch.randn(B, T, 384, generator=g).to(cuda_device) * 3.0
+    w, b = torch.randn(384, generator=g).to(cuda_device), torch.randn(384, generator=g).to(cuda_device)
+    dw, db = torch.randn(384, generator=g).to(cuda_device), torch.randn(1, generator=g).to(cuda_device)
+    ref = torch.nn.functional.layer_norm(torch.relu(z), (384,), w, b, 1e-12)
+    o16, od = ops.relu_layernorm(z, w, b, 1e-12, h16=True, split=True, dot_w=dw, dot_b=db, pad_mask=mask_u8)
+    hi, lo = o16[..., :384].float(), o16[..., 384:].float()
+    assert (hi + lo - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    ref_dot = ((ref * dw).sum(-1) + db).masked_fill(pad, 0.0)
+    assert (od - ref_dot).abs().max().item() <= 1e-4 * ref_dot.abs().max().item()

@@ -65,6 +65,21 @@ def _worker(rank, world, port, out_dir, graph):
     out["params"] = {n: p.detach().cpu().clone() for n, p in model2.generator.named_parameters()}
     if model2._graphed is not None:
         model2._graphed.release()
+    # (c) GAN phase: two optimizers, two all-reduces per step — the discriminator turn's is issued from the turn's own stream
+    # next to the generator's backward pass (BaseModule.OVERLAP_TURNS); both ranks must still end bit-identical, generator
+    # and discriminators alike
+    torch.manual_seed(4321)                    # same discriminator initialisation on both ranks
+    model3 = _fresh_model(spec, dev)
+    model3.train_args.pretraining_steps = 0
+    model3.cuda_graph = graph
+    for i in range(6):
+        model3.training_step(batch, i)
+    torch.cuda.synchronize()
+    assert "total_loss/discriminator" in model3.logged
+    out["gan_params"] = {n: p.detach().cpu().clone() for n, p in model3.named_parameters()}
+    out["gan_losses"] = (float(model3.logged["total_loss/generator"]), float(model3.logged["total_loss/discriminator"]))
+    if model3._graphed is not None:
+        model3._graphed.release()
     torch.save(out, os.path.join(out_dir, f"rank{rank}_{int(graph)}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -82,6 +97,10 @@ def test_two_rank_training_step_over_nccl(tmp_path, graph):
           f"|reduced - own local| / |own local| = {r0['own_rel']:.3e} (rank 0), {r1['own_rel']:.3e} (rank 1)")
     diverged = [(n, float((a - r1["params"][n]).abs().max())) for n, a in r0["params"].items() if not torch.equal(a, r1["params"][n])]
     assert not diverged, f"ranks diverged on {len(diverged)} of {len(r0['params'])} tensors, e.g. {diverged[:6]}"
+    gan_diverged = [(n, float((a - r1["gan_params"][n]).abs().max())) for n, a in r0["gan_params"].items() if not torch.equal(a, r1["gan_params"][n])]
+    print(f"graph={graph}: GAN phase losses rank 0 {r0['gan_losses']}, rank 1 {r1['gan_losses']}; {len(r0['gan_params'])} tensors compared")
+    assert not gan_diverged, f"GAN phase: ranks diverged on {len(gan_diverged)} of {len(r0['gan_params'])} tensors, e.g. {gan_diverged[:6]}"
+    assert all(v == v and abs(v) < 1e6 for v in r0["gan_losses"] + r1["gan_losses"])
     # run-to-run floor of one gradient evaluation is a few percent on the predictors (fp32 atomics + fp16 roundings); a
     # rank's own gradient differs from the sum by O(1)
     assert r0["mean_rel"] <= 5e-2 and r1["mean_rel"] <= 5e-2
