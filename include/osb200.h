@@ -232,6 +232,14 @@ int osb_centres(const void* dur, int32_t dur_is_i64, float* centres, int64_t* cs
 int osb_gaussian_upsample(const float* hs, const float* centres, const int64_t* x_len, const int64_t* y_len, float* out_f32,
                           void* out_h16, int32_t B, int32_t Tx, int32_t Tm, int32_t C, float delta, void* stream);
 
+/* The same rows for a WINDOW of frames per sample: output row j of sample b is frame win_start[b] - halo + j of the Tm-frame
+ * sequence, j < W; rows outside [0, Tm) are zero (what the zero padding of the decoder's convolutions reads there).  The
+ * training step only consumes `segment_size` decoder frames per sample (get_random_segments, generator/__init__.py:146-152) and
+ * the ConvNeXt decoder is local (3 frames of context per block), so upsampler + decoder run on segment + 2 * halo frames. */
+int osb_gaussian_upsample_window(const float* hs, const float* centres, const int64_t* x_len, const int64_t* y_len,
+                                 const int64_t* win_start /*(B)*/, float* out_f32, void* out_h16, int32_t B, int32_t Tx, int32_t Tm,
+                                 int32_t W, int32_t halo, int32_t C, float delta, void* stream);
+
 /* Hard length regulator: out[b,t,:] = x[b, i(t), :] with csum[i-1] <= t < csum[i]; zero past the length.
  * index_out (optional, int32, -1 past the length) is the bit-exact indexing target.
  * Replaces expand_by_duration (generator/alignments.py:283-297). */

@@ -111,6 +111,7 @@ def load() -> C.CDLL:
         "osb_durations": [P, P, P, P, I32, I32, F, F, P],
         "osb_centres": [P, I32, P, P, I32, I32, P],
         "osb_gaussian_upsample": [P, P, P, P, P, P, I32, I32, I32, I32, F, P],
+        "osb_gaussian_upsample_window": [P, P, P, P, P, P, P, I32, I32, I32, I32, I32, I32, F, P],
         "osb_expand_gather": [P, P, P, P, I32, I32, I32, I32, P],
         "osb_pack_h16": [P, I64, I64, P, P, P, I64, I32, I64, I32, P],
         "osb_pack_conv_h16": [P, P, P, I32, I32, I32, I32, I32, P],

@@ -337,20 +337,27 @@ template <int FR>
 __global__ void __launch_bounds__(256)
 gaussian_upsample_kernel(const float* __restrict__ hs, const float* __restrict__ centres, const long long* __restrict__ x_len,
                          const long long* __restrict__ y_len, float* __restrict__ out_f32, __half* __restrict__ out_h16, int Tx, int Tm,
-                         int C, float delta) {
+                         int C, float delta, const long long* __restrict__ win_start, int halo, int Tfull) {
+  // Window mode (win_start != NULL): output row j of sample b is frame win_start[b] - halo + j of the full (Tfull-frame)
+  // sequence; rows that fall outside [0, Tfull) are zero (what a convolution's zero padding reads there).  Tm = rows per sample.
   extern __shared__ float sp[];  // FR * Tx attention weights
   __shared__ int s_rng[2];       // tokens [lo, hi] with a non-zero weight for any frame of the block
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const int nx = static_cast<int>(x_len[b]);
   const int ny = static_cast<int>(y_len[b]);
+  const int shift = win_start != nullptr ? static_cast<int>(win_start[b]) - halo : 0;   // full-sequence frame of output row 0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { s_rng[0] = Tx; s_rng[1] = -1; }
   __syncthreads();
   // one warp per frame builds the softmax row
   for (int f = warp; f < FR; f += (blockDim.x >> 5)) {
-    const int t = t0 + f;
-    if (t >= Tm) continue;
+    if (t0 + f >= Tm) continue;
+    const int t = t0 + f + shift;
+    if (t < 0 || t >= Tfull) {           // outside the sequence (window mode only): an all-zero row
+      for (int i = lane; i < Tx; i += 32) sp[f * Tx + i] = 0.f;
+      continue;
+    }
     const float tf = (t < ny) ? static_cast<float>(t) : 0.f;
     float* p = sp + f * Tx;
     float mx = -INFINITY;
@@ -721,7 +728,23 @@ extern "C" int osb_gaussian_upsample(const float* hs, const float* centres, cons
   dim3 grid((Tm + FR - 1) / FR, B);
   gaussian_upsample_kernel<FR><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       hs, centres, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(y_len), out_f32,
-      static_cast<__half*>(out_h16), Tx, Tm, C, delta);
+      static_cast<__half*>(out_h16), Tx, Tm, C, delta, nullptr, 0, Tm);
+  count_launch();
+  return launch_status();
+}
+
+extern "C" int osb_gaussian_upsample_window(const float* hs, const float* centres, const int64_t* x_len, const int64_t* y_len,
+                                            const int64_t* win_start, float* out_f32, void* out_h16, int32_t B, int32_t Tx, int32_t Tm,
+                                            int32_t W, int32_t halo, int32_t C, float delta, void* stream) {
+  OSB_REQUIRE(hs && centres && x_len && y_len && win_start && (out_f32 || out_h16), OSB_ERR_ARG);
+  OSB_REQUIRE(B > 0 && Tx > 0 && Tm > 0 && W > 0 && halo >= 0 && C > 0, OSB_ERR_SHAPE);
+  constexpr int FR = 8;
+  const size_t smem = static_cast<size_t>(FR) * Tx * sizeof(float);
+  OSB_REQUIRE(smem <= 48 * 1024, OSB_ERR_SHAPE);
+  dim3 grid((W + FR - 1) / FR, B);
+  gaussian_upsample_kernel<FR><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      hs, centres, reinterpret_cast<const long long*>(x_len), reinterpret_cast<const long long*>(y_len), out_f32,
+      static_cast<__half*>(out_h16), Tx, W, C, delta, reinterpret_cast<const long long*>(win_start), halo, Tm);
   count_launch();
   return launch_status();
 }

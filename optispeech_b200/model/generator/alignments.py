@@ -44,6 +44,14 @@ class GaussianUpsampling(torch.nn.Module):
                                          f32=True, h16=want_h16)
         return (o32, o16) if want_h16 else o32
 
+    def forward_window(self, hs, ds, x_lengths, y_lengths, win_start, Tm: int, W: int, halo: int):
+        """Frames win_start[b] - halo .. + W of forward()'s result for every sample (zero outside [0, Tm)): (B, W, C)."""
+        if ds.dtype not in (torch.int64, torch.float32):
+            ds = ds.float()
+        c, _ = ops.centres(ds.contiguous(), want_csum=False)
+        return ops.gaussian_upsample_window(hs.contiguous(), c, x_lengths.contiguous(), y_lengths.contiguous(), win_start, Tm, W, halo,
+                                            self.delta)
+
     @staticmethod
     def patch_all_zero(ds):
         """alignments.py:152-157: an all-zero duration batch gets its empty rows set to 1 (with a warning)."""

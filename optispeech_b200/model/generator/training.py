@@ -136,6 +136,17 @@ def generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, ene
 
 
 PITCH_AHEAD = True
+WINDOWED_DECODER = True   # training: upsampler + ConvNeXt decoder on the frames the vocoder segment depends on only
+
+
+def _decoder_halo(decoder):
+    """Frames of context on either side that one output frame of the decoder depends on, or None when the decoder is not a
+    stack of local blocks (Transformer decoder: every frame sees the whole sequence)."""
+    from .modules.convnext import ConvNeXtBackbone
+
+    if not isinstance(decoder, ConvNeXtBackbone):
+        return None
+    return sum((blk.dwconv.kernel_size[0] - 1) // 2 for blk in decoder.convnext)
 
 
 def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, energies, sids, lids, seg_rand=None):
@@ -202,18 +213,34 @@ def _generator_training_forward(gen, x, x_lengths, mel, mel_lengths, pitches, en
     s_voc.wait_stream(main)
     with torch.cuda.stream(s_voc):
         with torch.no_grad():
-            y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
-                                      y_lengths=mel_lengths)
-            y = gen.decoder(y, tgt_pad, split=False)
-            segment_size = min(gen.segment_size, y.shape[1])
+            Tm = mel.shape[-1]
+            segment_size = min(gen.segment_size, Tm)
             if seg_rand is None:
                 # inside a CUDA-graph capture the draw has to live on the device (a pageable H2D copy cannot be captured)
                 capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
                 seg_rand = torch.rand([x.shape[0]], device=dev) if capturing else torch.rand([x.shape[0]])
-            # start = floor(rand * max(len - 4 - S, 0)) and the (B, S, C) crop: two launches (osb_glue.cu); the f0_cond crop
-            # of generator/__init__.py:156-158 is not taken: WaveNeXt ignores it (wavenext/__init__.py:82)
+            # start = floor(rand * max(len - 4 - S, 0)) (osb_glue.cu); the f0_cond crop of generator/__init__.py:156-158 is not
+            # taken: WaveNeXt ignores it (wavenext/__init__.py:82)
             start_idx = ops.segment_starts(seg_rand.to(dev, non_blocking=True).float(), mel_lengths, segment_size, margin=4)
-            segment = ops.gather_segments(y.contiguous(), start_idx, segment_size)
+            halo = _decoder_halo(gen.decoder) if WINDOWED_DECODER else None
+            if halo is not None and segment_size + 2 * halo < Tm:
+                # The step consumes `segment_size` decoder frames per sample and nothing else of the decoder output (the
+                # reference crops it right away, generator/__init__.py:146-152, and returns only wav_hat and the losses), and a
+                # ConvNeXt decoder is local: frame t of its output depends on upsampler frames t-halo .. t+halo (3 per block).
+                # So upsampler and decoder run on the window [start - halo, start + S + halo) of every sample — 88 of 864 frames
+                # at the benchmark shape — with rows outside [0, Tm) zero and masked exactly as the convolutions' zero padding
+                # and the padding mask present them in the full-length computation: same values for the segment.
+                W = segment_size + 2 * halo
+                y = gen.feature_upsampler.forward_window(h.detach(), durations, x_lengths, mel_lengths, start_idx, Tm, W, halo)
+                t_full = start_idx[:, None] - halo + torch.arange(W, device=dev)[None, :]
+                win_pad = ((t_full < 0) | (t_full >= mel_lengths[:, None])).contiguous()
+                y = gen.decoder(y, win_pad, split=False)
+                segment = y[:, halo:halo + segment_size].contiguous()
+            else:
+                y = gen.feature_upsampler(hs=h.detach(), ds=durations, h_masks=mel_mask, d_masks=x_mask, x_lengths=x_lengths,
+                                          y_lengths=mel_lengths)
+                y = gen.decoder(y, tgt_pad, split=False)
+                segment = ops.gather_segments(y.contiguous(), start_idx, segment_size)
 
         if getattr(gen, "vocoder_needs_grad", True):
             wav_hat = gen.vocoder.forward_train(segment)

@@ -242,6 +242,16 @@ def gaussian_upsample(hs, centres_, x_len, y_len, Tm: int, delta: float = 0.1, f
     return o32, o16
 
 
+def gaussian_upsample_window(hs, centres_, x_len, y_len, win_start, Tm: int, W: int, halo: int, delta: float = 0.1):
+    """Rows win_start[b] - halo + j (j < W) of gaussian_upsample's (B, Tm, C) result, zero outside [0, Tm): (B, W, C) fp32."""
+    B, Tx, Cc = hs.shape
+    out = torch.empty((B, W, Cc), device=hs.device, dtype=torch.float32)
+    _lib.check(_lib.load().osb_gaussian_upsample_window(_ptr(_f32(hs)), _ptr(centres_), _ptr(x_len), _ptr(y_len),
+                                                        _ptr(win_start.to(torch.int64).contiguous()), _ptr(out), None, B, Tx, int(Tm),
+                                                        int(W), int(halo), Cc, delta, _stream()), "osb_gaussian_upsample_window")
+    return out
+
+
 def expand_gather(x, csum, Tm: int):
     B, Tx, Cc = x.shape
     out = torch.empty((B, Tm, Cc), device=x.device, dtype=torch.float32)

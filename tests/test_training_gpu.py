@@ -127,3 +127,51 @@ def test_training_forward_backward_matches_oracle(setup, cuda_device, B, Tx, Tm)
     for name, rel in bad:
         print(f"BAD {name}: relative gradient error {rel:.3e}")
     assert not bad
+
+
+def test_windowed_decoder_equals_full_length_decoder(setup, cuda_device):
+    """Training runs the Gaussian upsampler and the ConvNeXt decoder on the frames the vocoder segment depends on only
+    (training.WINDOWED_DECODER: segment + 12 frames of context on either side, osb_gaussian_upsample_window).  The segment the
+    vocoder receives — and with it wav_hat — must equal the one cut from the full-length computation, including segments at
+    the very start / end of an utterance (window rows outside the sequence) and next to the padding of a short sample."""
+    from optispeech_b200.model.generator import training
+    from optispeech_b200.model.generator.training import generator_training_forward
+
+    spec, sd, gen = setup
+    dev = cuda_device
+    B, Tx, Tm = 5, 48, 200
+    batch = make_batch(spec, B, Tx, Tm, seed=9)
+    # draws that put segments at frame 0, at the last admissible start, and in the middle
+    batch["seg_rand"] = torch.tensor([0.0, 0.999999, 0.999999, 0.0, 0.73])   # sample 2 is full length: its window runs past Tm
+
+    def run(windowed):
+        training.WINDOWED_DECODER = windowed
+        try:
+            with torch.no_grad():
+                out = generator_training_forward(gen, batch["x"].to(dev), batch["x_lengths"].to(dev), batch["mel"].to(dev),
+                                                 batch["mel_lengths"].to(dev), batch["pitches"].to(dev), batch["energies"].to(dev),
+                                                 None, None, seg_rand=batch["seg_rand"])
+            torch.cuda.synchronize()
+        finally:
+            training.WINDOWED_DECODER = True
+        return out
+
+    full, win = run(False), run(True)
+    assert torch.equal(full["start_idx"], win["start_idx"])
+    assert full["_aux"]["decoder_out"].shape[1] == Tm and win["_aux"]["decoder_out"].shape[1] == gen.segment_size + 24
+    # The decoder rows of the segment: the same per-row arithmetic.  Not bit-identical: with few row tiles the fused block splits
+    # the intermediate dimension over CTAs and sums the partial results in a different order, and an fp32 ulp in a block's output
+    # now and then flips the fp16 rounding of the next block's tensor-core operand (2^-11 of that element).  A wrong window edge
+    # (padding, mask, offset) would show up as O(0.1 .. 1) errors in the samples whose segment touches the sequence ends.
+    S = gen.segment_size
+    errs = []
+    for b in range(B):
+        s = int(full["start_idx"][b])
+        a = full["_aux"]["decoder_out"][b, s:s + S]
+        w = win["_aux"]["decoder_out"][b, 12:12 + S]
+        errs.append((a - w).abs().max().item() / max(1.0, a.abs().max().item()))
+        print(f"sample {b}: start {s}, length {int(batch['mel_lengths'][b])}: decoder rows max diff {errs[-1]:.2e} of the largest value")
+    assert max(errs) <= 2e-4, errs
+    err = (full["wav_hat"] - win["wav_hat"]).abs().max().item()
+    print(f"wav_hat: windowed vs full-length decoder, max-abs diff {err:.2e}")
+    assert err <= 1e-3
