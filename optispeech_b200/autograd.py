@@ -160,10 +160,13 @@ class ConvNeXtBlockFn(Function):
             out = z_or_out
             dyg, dh, dxh = ops.convnext_block_bwd(dout, gamma, row_scale, pad_mask, pre, w2_h[0], w1f_h[0])
             dx, ddw, ddb = ops.ln_dwconv_bwd(dxh, xhat, rstd, dout, x, dw_w.view(C, 7), pad_mask)
-            with ops.grad_side(x, dout, dyg, dh, h, xhat, out, x):     # parameter gradients: off the critical path
+            # parameter gradients: off the critical path, as two independent chains on two side streams (the five launches in a
+            # row were ~100 us behind the LAST block of the backward pass, i.e. the tail of the step)
+            with ops.grad_side(x, dout, dyg, h, out, x):
                 dgamma, db2 = ops.resid_param_grad(dout, out, x, gamma, pad_mask, row_scale)
                 dw2 = ops.zeros((1, C, I), x)
                 ops.gemm_wgrad(dyg, h, dw2)
+            with ops.grad_side(x, dh, xhat):
                 dw1f = ops.zeros((1, I, C), x)
                 ops.gemm_wgrad(dh, xhat, dw1f)
                 db1 = ops.colsum_h16(dh)
