@@ -403,3 +403,35 @@ def test_reference_style_checkpoint_loads_without_omegaconf(tmp_path):
     assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
     opts, _ = loaded.configure_optimizers()
     assert opts[0].defaults["betas"] == (0.8, 0.99)
+
+
+def test_decoder_window_geometry_and_join_bookkeeping():
+    """Host logic of the second half of round 2: the training forward runs upsampler + decoder on segment + 2 * halo frames
+    only when the decoder is a stack of local ConvNeXt blocks (halo = 3 frames per block; a Transformer decoder keeps the
+    full-length path), and the discriminators' deferred stream joins nest and clean up after themselves."""
+    import torch
+
+    from optispeech_b200.factory import DEFAULT_MODEL, build_generator, transformer_model_config
+    from optispeech_b200.model.generator.training import _decoder_halo
+    from optispeech_b200.model.vocoder.wavenext.disc import native
+
+    gen = build_generator(DEFAULT_MODEL["generator"] if "generator" in DEFAULT_MODEL else None)
+    assert _decoder_halo(gen.decoder) == 3 * len(gen.decoder.convnext) == 12
+    tgen = build_generator(transformer_model_config()["generator"] if "generator" in transformer_model_config() else transformer_model_config())
+    assert _decoder_halo(tgen.decoder) is None
+
+    # the window mask of training.py: rows outside [0, len_b) are padding, exactly the rows the full-length mask / zero padding cover
+    start, lens, halo, S = torch.tensor([0, 131, 85]), torch.tensor([200, 200, 154]), 12, 64
+    t_full = start[:, None] - halo + torch.arange(S + 2 * halo)[None, :]
+    win_pad = (t_full < 0) | (t_full >= lens[:, None])
+    assert win_pad[0, :halo].all() and not win_pad[0, halo:].any()                 # segment at frame 0: the left halo is outside
+    assert not win_pad[1, : 200 - 131 + halo].any() and win_pad[1, 200 - 131 + halo:].all()   # runs past Tm = 200
+    assert int((~win_pad[2]).sum()) == 154 - (85 - halo)                            # short sample: rows up to its length
+
+    assert native._DEFERRED_JOINS == []
+    with native.deferred_join():
+        assert native._DEFERRED_JOINS == [None]
+        with native.deferred_join():
+            assert native._DEFERRED_JOINS == [None, None]
+        assert native._DEFERRED_JOINS == [None]
+    assert native._DEFERRED_JOINS == []
