@@ -713,22 +713,24 @@ __device__ __forceinline__ float l2add3(float a, float b, float c) { // log2(2^a
 // W warps per recursion (a single warp issues at ~0.45 instructions / cycle: the recursion is issue bound, not latency bound —
 // ncu, round 2): the chain of a sample is spread over W warps; the one value (alpha) / two values (beta) that cross a warp
 // boundary go through a double-buffered shared-memory mailbox and ONE named barrier per step and chain.
-template <int SPL, int W>
-__global__ void __launch_bounds__(64 * W)
+// SPLIT: the alpha and the beta chain of a sample are two CTAs (grid 2B, 32 W threads each) instead of two halves of one: the
+// recursion is bound by instruction issue, and two chains on one SM share its four schedulers (T = 864 steps: 252 us together).
+template <int SPL, int W, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 32 * W : 64 * W)
 forward_sum_warp_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                         float blank_logit, const float* __restrict__ lse_ws, float* __restrict__ aw_all, float* __restrict__ bw_all,
                         float* __restrict__ nll_ws, float* __restrict__ loss, int B, int Tm, int Tx) {
   constexpr int TPL = SPL / 2;                 // token states per lane
   __shared__ float mbox[2][2][W][2];           // [chain][slot][warp][value]
   __shared__ float fin[2];
-  const int b = blockIdx.x;
+  const int b = SPLIT ? static_cast<int>(blockIdx.x) % B : static_cast<int>(blockIdx.x);
   const int lane = threadIdx.x & 31;
-  const bool is_beta = threadIdx.x >= 32 * W;
-  const int wc = (threadIdx.x >> 5) - (is_beta ? W : 0);      // warp index inside its chain
+  const bool is_beta = SPLIT ? static_cast<int>(blockIdx.x) >= B : threadIdx.x >= 32 * W;
+  const int wc = (threadIdx.x >> 5) - ((!SPLIT && is_beta) ? W : 0);      // warp index inside its chain
   const int gl = wc * 32 + lane;                               // lane index inside the chain
   const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
   if (N <= 0 || T <= 0) {
-    if (threadIdx.x == 0) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
+    if (threadIdx.x == 0 && !is_beta) { loss[b] = 0.f; nll_ws[b] = INFINITY; }
     return;
   }
   const int S = 2 * N + 1;
@@ -883,6 +885,41 @@ __global__ void fs_grad_log2_kernel(const float* __restrict__ lpa, const long lo
   grad[idx] = g;
 }
 
+// the same, four consecutive tokens per thread (Tx % 4 == 0): 16-byte loads / stores — the kernel is on the step's critical path
+// right behind the recursion (85 MB of traffic: 36 us with scalar accesses)
+__global__ void __launch_bounds__(256)
+fs_grad_log2_vec4_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
+                         const float* __restrict__ lse_ws, const float* __restrict__ aw, const float* __restrict__ bw,
+                         const float* __restrict__ nll_ws, float* __restrict__ grad, int B, int Tm, int Tx) {
+  const long long i4 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Tx4 = Tx >> 2;
+  if (i4 >= static_cast<long long>(B) * Tm * Tx4) return;
+  const int n0 = static_cast<int>(i4 % Tx4) * 4;
+  const long long row = i4 / Tx4;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row % Tm);
+  const int N = static_cast<int>(x_len[b]), T = static_cast<int>(m_len[b]);
+  const float nll = nll_ws[b];
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < T && n0 < N && nll < INFINITY) {
+    const float l = lse_ws[row];
+    const float4 lp = *reinterpret_cast<const float4*>(lpa + i4 * 4);
+    const float4 av = *reinterpret_cast<const float4*>(aw + i4 * 4);
+    const float4 bv = *reinterpret_cast<const float4*>(bw + i4 * 4);
+    const float inv = 1.f / (static_cast<float>(N) * static_cast<float>(B));
+    auto one = [&](float lpv, float a, float bb, int n) -> float {
+      if (n >= N) return 0.f;
+      const float e = lpv - l;
+      const float post = (a > 0.5f * FSW_NEG && bb > 0.5f * FSW_NEG) ? expf((a + bb) * FSW_LN2 - e + nll) : 0.f;
+      return (expf(e) - post) * inv;
+    };
+    g.x = one(lp.x, av.x, bv.x, n0);
+    g.y = one(lp.y, av.y, bv.y, n0 + 1);
+    g.z = one(lp.z, av.z, bv.z, n0 + 2);
+    g.w = one(lp.w, av.w, bv.w, n0 + 3);
+  }
+  *reinterpret_cast<float4*>(grad + i4 * 4) = g;
+}
+
 // gradient, fully parallel over (b, t, n): softmax minus posterior occupancy, with the per-sample 1/N and the batch 1/B
 __global__ void fs_grad_kernel(const float* __restrict__ lpa, const long long* __restrict__ x_len, const long long* __restrict__ m_len,
                                const float* __restrict__ lse_ws, const float* __restrict__ aw, const float* __restrict__ bw,
@@ -906,6 +943,10 @@ __global__ void fs_grad_kernel(const float* __restrict__ lpa, const long long* _
 }  // namespace osb
 
 static int g_fs_force_legacy = 0;
+/* developer hook (not in the public header): launch shape of the warp recursion — 1 (default): one CTA per chain; 0: the alpha
+ * and the beta chain of a sample in one CTA.  (8 warps x 2 states per chain was measured too: 275 us split, 382 us fused.) */
+static int g_fs_variant = 1;
+extern "C" void osb_debug_forward_sum_variant(int v) { g_fs_variant = v; }
 /* developer hook (not in the public header): 1 = always use the shared-memory recursion (parity tests compare the two) */
 extern "C" void osb_debug_forward_sum_legacy(int on) { g_fs_force_legacy = on; }
 
@@ -936,10 +977,23 @@ extern "C" int osb_forward_sum(const float* log_p_attn, const int64_t* x_len, co
   // warp-synchronous register recursion when the 2 Tx + 1 states fit 32 lanes x SPL registers; else the shared-memory kernel
   const int S_max = 2 * Tx + 1;
   if (S_max <= 1024 && !g_fs_force_legacy) {
-    if (S_max <= 256) osb::forward_sum_warp_kernel<4, 2><<<B, 128, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    else if (S_max <= 512) osb::forward_sum_warp_kernel<4, 4><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    else osb::forward_sum_warp_kernel<8, 4><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
-    osb::fs_grad_log2_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
+    // default: one CTA per CHAIN (alpha / beta of a sample on different SMs): 224 -> 165 us at B=32, Tm=864, Tx=192, bit-identical
+    // results (tools/probe_fs.py); g_fs_variant 0 keeps both chains of a sample in one CTA (A/B)
+    const bool split = g_fs_variant != 0;
+    if (S_max <= 256) {
+      if (split) osb::forward_sum_warp_kernel<4, 2, true><<<2 * B, 64, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+      else osb::forward_sum_warp_kernel<4, 2, false><<<B, 128, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    } else if (S_max <= 512) {
+      if (split) osb::forward_sum_warp_kernel<4, 4, true><<<2 * B, 128, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+      else osb::forward_sum_warp_kernel<4, 4, false><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    } else {
+      if (split) osb::forward_sum_warp_kernel<8, 4, true><<<2 * B, 128, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+      else osb::forward_sum_warp_kernel<8, 4, false><<<B, 256, 0, s>>>(log_p_attn, xl, ml, blank_logit, lse_ws, aw, bw, nll_ws, loss, B, Tm, Tx);
+    }
+    const bool vec4 = Tx % 4 == 0 && (reinterpret_cast<uintptr_t>(log_p_attn) & 15) == 0 && (reinterpret_cast<uintptr_t>(aw) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(bw) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0;
+    if (vec4) osb::fs_grad_log2_vec4_kernel<<<static_cast<unsigned>((plane / 4 + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
+    else osb::fs_grad_log2_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, s>>>(log_p_attn, xl, ml, lse_ws, aw, bw, nll_ws, grad, B, Tm, Tx);
     osb::count_launch(3);
     return osb::launch_status();
   }
