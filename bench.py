@@ -625,6 +625,32 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                         "peak": peak_t, "unit": "TFLOP/s", "frac": flops / (dms * 1e-3) / 1e12 / peak_t,
                                         "hbm_floor_bytes": 1024 * frames, "d2h_bytes": int(nsamp * 4)}}
         model.train()
+    if world > 1:
+        # BASELINE config 5 ("long-form B=8, 512 phonemes, N x B200"): synthesis does not shard inside an utterance — REPLICAS ONLY
+        # (utils/sharding.py deals whole utterances to the ranks).  Every rank synthesises its own B=8 x 512 batch at the same
+        # time, no collective on the data path; aggregate = sum of the ranks' samples / the slowest rank's wall time per call.
+        model.eval()
+        ids, lens, durs = synth_inputs("long_B8_Tx512")
+        ids_pin = ids.pin_memory()
+        for _ in range(3):
+            out = model.generator.synthesise(ids_pin.to(dev, non_blocking=True), lens, durations=durs)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = model.generator.synthesise(ids_pin.to(dev, non_blocking=True), lens, durations=durs)
+        dt = (time.perf_counter() - t0) / reps
+        stat = torch.tensor([dt, float(int(out["wav_lengths"].sum()))], device=dev, dtype=torch.float64)
+        mx = stat.clone()
+        torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(stat, op=torch.distributed.ReduceOp.SUM)
+        model.train()
+        if rank == 0:
+            synth["long_B8_Tx512_replicas"] = {
+                "n_gpus": world, "utterances": 8 * world, "ms_slowest_rank": 1e3 * float(mx[0]), "audio_samples_per_s_e2e": float(stat[1]) / float(mx[0]),
+                "vs_one_gpu": (float(stat[1]) / float(mx[0])) / synth["long_B8_Tx512"]["audio_samples_per_s_e2e"] if "long_B8_Tx512" in synth else None,
+                "scaling": "replicas only: every rank synthesises its own B=8 x 512 batch concurrently, no collective on the data path"}
 
     # ---- BASELINE config 4: the same step and synthesis with the Transformer backbone (self-attention kernel path) ----
     variants = {}

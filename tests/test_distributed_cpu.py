@@ -84,3 +84,70 @@ def test_two_rank_bucket_allreduce_matches_single_process(tmp_path):
     for a, b in zip(r0[:3], params):
         assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
     assert torch.equal(r0[3], frozen), "parameter without gradient must stay untouched (no weight decay)"
+
+
+# --------------------------------------------------------------------------------------------------
+# synthesis: replicas only — utterances are sharded by length, results gathered on the host (utils/sharding.py)
+# --------------------------------------------------------------------------------------------------
+class _EchoSynth(torch.nn.Module):
+    """Stand-in for OptiSpeechGenerator.synthesise on the CPU: two samples per phoneme id value, so that the gathered result
+    identifies the utterance it came from (the kernels cannot run here; the sharding / batching / gather logic is what is tested)."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.calls = []
+
+    def synthesise(self, x, x_lengths, **kw):
+        self.calls.append(tuple(int(v) for v in x_lengths))
+        assert x.shape[1] == int(x_lengths.max()), "a batch is cut to its longest utterance"
+        wav_lengths = x_lengths * 2
+        wav = torch.zeros(x.shape[0], int(wav_lengths.max()))
+        for b in range(x.shape[0]):
+            n = int(x_lengths[b])
+            wav[b, : 2 * n] = x[b, :n].float().repeat_interleave(2)
+        return {"wav": wav, "wav_lengths": wav_lengths, "durations": torch.full_like(x, 2)}
+
+
+def _synth_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from optispeech_b200.utils.sharding import gather_outputs, synthesise_sharded
+
+    g = torch.Generator().manual_seed(3)
+    N = 11
+    lens = torch.randint(5, 40, (N,), generator=g)
+    x = torch.zeros(N, int(lens.max()), dtype=torch.int64)
+    for i in range(N):
+        x[i, : lens[i]] = torch.randint(1, 159, (int(lens[i]),), generator=g)
+    model = _EchoSynth()
+    local = synthesise_sharded(model, x, lens, rank, world, max_batch=3)
+    merged = gather_outputs(local, world)
+    torch.save({"local": sorted(local), "merged": {k: v["wav"] for k, v in merged.items()}, "calls": model.calls,
+                "expect": {i: x[i, : lens[i]].float().repeat_interleave(2) for i in range(N)}}, os.path.join(out_dir, f"synth{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_synthesis_shards_by_length_and_gathers(tmp_path):
+    from optispeech_b200.utils.sharding import shard_by_length
+
+    shards = shard_by_length([10, 50, 30, 30, 5, 70, 20], 3)
+    assert sorted(i for s in shards for i in s) == list(range(7))                  # a partition
+    assert [max(len(s) for s in shards) - min(len(s) for s in shards)] == [1]
+    loads = [sum([10, 50, 30, 30, 5, 70, 20][i] for i in s) for s in shards]
+    assert max(loads) - min(loads) <= 70                                           # within one utterance of each other
+    assert shard_by_length([3, 1, 2], 1) == [[0, 2, 1]]                            # longest first
+    with pytest.raises(ValueError):
+        shard_by_length([1], 0)
+
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_synth_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "synth0.pt"), torch.load(tmp_path / "synth1.pt")
+    assert not set(r0["local"]) & set(r1["local"]) and sorted(r0["local"] + r1["local"]) == list(range(11))
+    for r in (r0, r1):                                                             # every rank holds every waveform after the gather
+        assert sorted(r["merged"]) == list(range(11))
+        for i, w in r["merged"].items():
+            assert torch.equal(w, r["expect"][i]), i
+        assert all(len(c) <= 3 for c in r["calls"])                                # max_batch honoured
+        assert all(list(c) == sorted(c, reverse=True) for c in r["calls"])         # similar lengths share a batch, longest first
