@@ -174,4 +174,6 @@ def test_windowed_decoder_equals_full_length_decoder(setup, cuda_device):
     assert max(errs) <= 2e-4, errs
     err = (full["wav_hat"] - win["wav_hat"]).abs().max().item()
     print(f"wav_hat: windowed vs full-length decoder, max-abs diff {err:.2e}")
-    assert err <= 1e-3
+    # the 5e-5 differences of the segment go through eight vocoder blocks on single-pass fp16 operands (measured 6.5e-4 .. 6.8e-4;
+    # the same operands against the fp32 oracle: 2.6e-3 .. 3.7e-3); a wrong window edge is >= 1e-2
+    assert err <= 3e-3
